@@ -1,0 +1,219 @@
+"""CPU oracle for the hex-lattice operators of HyGrid/HexFrames.py (torch CPU).
+
+TEST INFRASTRUCTURE ONLY -- see the header of ``hygrid_oracle.py`` for who may
+import this.  These are floating-point kernels, so the oracle is a plain
+torch-CPU fp32/fp64 restatement (autograd supplies the backward oracle).
+
+Parity pin: the reference has no tests; ``tests/golden/make_golden.py`` runs the
+reference's own ``HexConv2d`` / ``HexPool2d`` / ``heximage_to_type1`` ... in the
+build container and commits inputs+outputs; ``tests/test_oracle_golden.py``
+checks the restatement below against them.
+
+The reference evaluates the hex convolution by materialising a 2x-wide
+"doubled" image and running two dense strided ``F.conv2d`` with a zero-stuffed
+(2r-1)x(4r-3) kernel (HexFrames.py:96-169).  The restatement here is the closed
+form in *offset* coordinates: one gather per hexagonal tap, no doubled image.
+
+All ``file:line`` citations are into ``/root/reference/HyGrid/``.
+"""
+from __future__ import annotations
+
+import math
+import torch
+import torch.nn.functional as F
+
+__all__ = [
+    "hex_taps", "hexconv_out_shape", "hexconv2d", "adaptive_padding",
+    "hexpool_out_shape", "hexpool2d", "hexadaptivepool2d", "hexglobalpool2d",
+    "reduce_max", "reduce_min", "reduce_average",
+    "heximage_to_type1", "heximage_to_type2", "type1_to_heximage",
+]
+
+
+# --------------------------------------------------------------------------
+# hex convolution (HexFrames.py:22-185)
+# --------------------------------------------------------------------------
+def hex_taps(radius: int):
+    """[(a, t, m)] for every weight index, in the reference's running-sum order
+    (HexFrames.py:112-118): kernel row a, |a-(r-1)| = t, m-th cell of that row."""
+    taps = []
+    for a in range(2 * radius - 1):
+        t = abs(a - radius + 1)
+        for m in range(2 * radius - 1 - t):
+            taps.append((a, t, m))
+    return taps
+
+
+def hexconv_out_shape(Hp, Wp, radius, stride, dilation):
+    """Rows / cols of the interleaved output for a padded Hp x Wp input
+    (HexFrames.py:127-162 with k_h, k_w from :82-83).  Returns (rows_even,
+    rows_odd, cols); a count <= 0 means that conv is skipped (``None``)."""
+    s, d = stride, dilation
+    k_h = (2 * radius - 2) * d + 1
+    k_w = 2 * d * (2 * radius - 2) + 1
+    wt = 2 * Wp - s                       # width of both sliced doubled images
+    cols = (wt - k_w) // (2 * s) + 1 if wt >= k_w else 0
+    rows_e = (Hp - k_h) // (2 * s) + 1 if Hp >= k_h else 0
+    rows_o = (Hp - s - k_h) // (2 * s) + 1 if Hp - s >= k_h else 0
+    return rows_e, rows_o, cols
+
+
+def hexconv2d(x, kernel, bias=None, even_odd_offset=0, radius=2, stride=1, padding=0,
+              dilation=1, groups=1, padding_mode="constant", padding_value=0):
+    """Closed form of HexConv2d.forward.
+
+    With P = F.pad(x), o = (even_odd_offset + padding) % 2, output row R, col q:
+        y[R, q] = bias + sum_taps w * D[s*R + a*d, 1 + (R%2)*s + 2*s*q + t*d + 2*d*m]
+    where D is the doubled image: D[i, c] = P[i, (c - s_i) // 2] for
+    s_i <= c < 2*Wp + s_i (s_i = (i + o) % 2) and 0 elsewhere
+    (HexFrames.py:417-445 for D; :129-144 for the two strided convs whose
+    interleave (:157-162) gives the single formula in R)."""
+    while x.dim() < 4:
+        x = x.unsqueeze(0)
+    x = x.to(kernel.dtype)
+    s, d, r = stride, dilation, radius
+    P = F.pad(x, (padding,) * 4, padding_mode, padding_value)
+    N, Cin, Hp, Wp = P.shape
+    Cout = kernel.shape[0]
+    o = (even_odd_offset + padding) % 2
+    rows_e, rows_o, cols = hexconv_out_shape(Hp, Wp, r, s, d)
+    if rows_e <= 0 or rows_o <= 0 or cols <= 0:
+        raise ValueError("input too small: the reference takes an undefined path here")
+    if rows_e - rows_o not in (0, 1):
+        raise ValueError("even/odd row counts cannot be interleaved (the reference raises too)")
+    Ho = rows_e + rows_o
+    R = torch.arange(Ho).view(Ho, 1)
+    q = torch.arange(cols).view(1, cols)
+    cin_g, cout_g = Cin // groups, Cout // groups
+    y = torch.zeros(N, Cout, Ho, cols, dtype=kernel.dtype)
+    for k, (a, t, m) in enumerate(hex_taps(r)):
+        i = s * R + a * d                                   # (Ho,1) row in P
+        c = 1 + (R % 2) * s + 2 * s * q + t * d + 2 * d * m  # (Ho,cols) doubled column
+        si = (i + o) % 2
+        ok = (c >= si) & (c < 2 * Wp + si)
+        pc = torch.div(c - si, 2, rounding_mode="floor").clamp(0, Wp - 1)
+        g = P[:, :, i.expand(Ho, cols), pc] * ok.to(P.dtype)  # (N,Cin,Ho,cols)
+        wk = kernel[:, :, 0, k]                               # (Cout, Cin/g)
+        for gi in range(groups):
+            y[:, gi * cout_g:(gi + 1) * cout_g] += torch.einsum(
+                "oc,nchw->nohw", wk[gi * cout_g:(gi + 1) * cout_g], g[:, gi * cin_g:(gi + 1) * cin_g])
+    if bias is not None:
+        y = y + bias.view(1, -1, 1, 1)
+    return y
+
+
+def adaptive_padding(Hin, Win, radius, stride, dilation):
+    """(left, right, top, bottom) of HexConv2dAdaptivePadding (HexFrames.py:235-250)."""
+    ks = 2 * radius - 1
+    oh, ow = math.ceil(Hin / stride), math.ceil(Win / stride)
+    pad_h = max((oh - 1) * stride + (ks - 1) * dilation + 1 - Hin, 0)
+    pad_w = max(ow * stride + (ks - 1) * dilation + 1 - Win, 0)
+    return (pad_w // 2, pad_w - pad_w // 2, pad_h // 2, pad_h - pad_h // 2)
+
+
+# --------------------------------------------------------------------------
+# pooling (HexFrames.py:255-414, 461-479)
+# --------------------------------------------------------------------------
+def reduce_max(v):   # HexFrames.py:461-463
+    return torch.max(v.masked_fill(v.isnan(), float("-inf")), dim=-1)[0]
+
+
+def reduce_min(v):   # HexFrames.py:464-466
+    return torch.min(v.masked_fill(v.isnan(), float("inf")), dim=-1)[0]
+
+
+def reduce_average(v):  # HexFrames.py:467-479
+    nan = v.isnan()
+    cnt = (~nan).to(v.dtype).sum(-1)
+    tot = torch.where(nan, torch.zeros_like(v), v).sum(-1)
+    out = tot / cnt
+    return torch.where(cnt == 0, torch.full_like(out, float("nan")), out)
+
+
+_REDUCE = {"max": reduce_max, "min": reduce_min, "average": reduce_average}
+
+
+def hexpool_out_shape(h, w, kh, kw, sh, sw):
+    """HexFrames.py:302-303."""
+    return (h - kh) // sh + 1, (w - sw // 2) // sw
+
+
+def _windows(P, hn, wn, kh, kw, sh, sw, shift):
+    """(B,C,hn,wn,kh*kw) windows: top-left of out(I,J) is
+    (sh*I, ((I%2)*shift)//2 + J*sw)  (HexFrames.py:318-325 / 385-392)."""
+    B, C, h, w = P.shape
+    I = torch.arange(hn).view(hn, 1, 1, 1)
+    J = torch.arange(wn).view(1, wn, 1, 1)
+    a = torch.arange(kh).view(1, 1, kh, 1)
+    b = torch.arange(kw).view(1, 1, 1, kw)
+    ii = (sh * I + a).expand(hn, wn, kh, kw)
+    jj = (torch.div((I % 2) * shift, 2, rounding_mode="floor") + J * sw + b).expand(hn, wn, kh, kw)
+    if hn > 0 and wn > 0 and (int(ii.max()) >= h or int(jj.max()) >= w):
+        raise IndexError("pool window leaves the image (the reference raises IndexError here)")
+    return P[:, :, ii, jj].reshape(B, C, hn, wn, kh * kw)
+
+
+def hexpool2d(x, method, kernel_size=2, stride=None, padding=0, padding_mode="constant",
+              padding_value=0, ceil_mode=False, count_include_pad=True):
+    """HexPool2d.forward (HexFrames.py:286-336).  ``stride=None`` means
+    stride = kernel_size (the evident intent of :273-274; the reference crashes)."""
+    kh, kw = (kernel_size, kernel_size) if isinstance(kernel_size, int) else kernel_size
+    if stride is None:
+        stride = (kh, kw)
+    sh, sw = (stride, stride) if isinstance(stride, int) else stride
+    while x.dim() < 4:
+        x = x.unsqueeze(0)
+    P = F.pad(x, (padding,) * 4, padding_mode, padding_value)
+    if ceil_mode:
+        h, w = P.shape[-2:]
+        hn0 = h // sh
+        wn0 = (w - sw // 2 - sw) // sw + 1
+        ph = (kh - h + hn0 * sh) % kh
+        pw = (kw - w + (wn0 * sw + sw // 2)) % kw
+        # literal argument order of HexFrames.py:298 -- (left,right,top,bottom)=(0,ph,0,pw)
+        P = F.pad(P, (0, ph, 0, pw), mode="constant",
+                  value=0 if count_include_pad else float("nan"))
+    h, w = P.shape[-2:]
+    hn, wn = hexpool_out_shape(h, w, kh, kw, sh, sw)
+    return _REDUCE[method](_windows(P, hn, wn, kh, kw, sh, sw, sw))
+
+
+def hexadaptivepool2d(x, outsize: int, method):
+    """HexAdaptivePool2d.forward (HexFrames.py:362-401)."""
+    while x.dim() < 4:
+        x = x.unsqueeze(0)
+    h, w = x.shape[-2:]
+    hn = wn = outsize
+    gh = int(h / hn)
+    gw = int(w / (wn + 0.5)) if gh > 1 else int(w / wn)
+    return _REDUCE[method](_windows(x, hn, wn, gh, gw, gh, gw, gw))
+
+
+def hexglobalpool2d(x, method):
+    """HexGlobalPool2d.forward (HexFrames.py:410-414): returns (B, C)."""
+    while x.dim() < 4:
+        x = x.unsqueeze(0)
+    return _REDUCE[method](x.reshape(x.size(0), x.size(1), -1))
+
+
+# --------------------------------------------------------------------------
+# layout converters (HexFrames.py:417-458)
+# --------------------------------------------------------------------------
+def heximage_to_type1(x, even_odd_offset):
+    while x.dim() < 4:
+        x = x.unsqueeze(0)
+    B, C, H, W = x.shape
+    out = torch.zeros(B, C, H, 2 * W + 1, dtype=torch.float32)
+    rep = x.repeat_interleave(2, dim=3).to(torch.float32)
+    for i in range(H):
+        s = (i + even_odd_offset) % 2
+        out[:, :, i, s:s + 2 * W] = rep[:, :, i]
+    return out
+
+
+def heximage_to_type2(x, even_odd_offset):
+    return heximage_to_type1(x, even_odd_offset).repeat_interleave(2, dim=2)
+
+
+def type1_to_heximage(t1, even_odd_offset):
+    return t1[:, :, :, 1::2], even_odd_offset

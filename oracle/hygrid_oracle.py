@@ -1,0 +1,360 @@
+"""CPU oracle for the HyGrid rect<->hex resampling path (numpy, float64).
+
+TEST INFRASTRUCTURE ONLY.  Nothing under the product package may import this
+module: only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs use it, and only as the checker /
+the CPU baseline.
+
+Parity pin: the reference ships no tests or golden vectors,
+so this restatement is pinned against outputs of the reference itself, run in the
+build container by ``tests/golden/make_golden.py`` and committed as
+``tests/golden/*.npz``.  ``tests/test_oracle_golden.py`` checks every function
+below against those fixtures bit-for-bit (float64 results compared with ``==``).
+
+The restatement is deliberately *not* structured like the reference: the
+reference materialises 2-D meshgrids, float masks and boolean-mask scatters;
+here every quantity that depends only on the output row or only on the output
+column is kept as a 1-D table and broadcast.  The per-element floating-point
+operations (and their order) are the reference's, which is what makes the
+float64 outputs bit-identical.
+
+All ``file:line`` citations are into ``/root/reference/HyGrid/``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+__all__ = [
+    "rect2hex_coords", "rect2hex_index", "rect_to_hex_resample",
+    "hex2rect_coords", "hexresize_coords", "hexsrc_index", "hexsrc_resample",
+    "hex_to_rect_resample", "hexresize", "warp_coords", "hex_warp",
+    "offset_to_axial", "axial_to_offset",
+    "hex_to_type1", "hex_to_type2", "type1_to_hex", "type2_to_hex",
+]
+
+
+# --------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------
+def _as_chw(img):
+    """(C,H,W) view of a 2-D / 3-D array (geometry_np.py:365-371)."""
+    img = np.asarray(img)
+    if img.ndim == 3:
+        return img
+    if img.ndim == 2:
+        return img[None]
+    raise Exception(f"dim of image should be 2 or 3, but got dim = {img.ndim} instead")
+
+
+def _trunc_div2(v):
+    """``((v) / 2).astype(int)``: true division then truncation toward zero
+    (geometry_np.py:122-128) -- differs from ``v // 2`` for negative odd v."""
+    return (v / 2).astype(np.int64)
+
+
+def _fetch(img_hwc, i, j):
+    """Zero-filled gather ``img[i, j]`` (geometry_np.py:465-486 / 303-323)."""
+    h, w = img_hwc.shape[:2]
+    ok = (i >= 0) & (j >= 0) & (i < h) & (j < w)
+    out = np.zeros(np.broadcast(i, j).shape + (img_hwc.shape[2],), dtype=img_hwc.dtype)
+    ib, jb = np.broadcast_arrays(i, j)
+    out[ok] = img_hwc[ib[ok], jb[ok]]
+    return out, ok
+
+
+# --------------------------------------------------------------------------
+# R1  rect -> hex   (geometry_np.py:358-519)
+# --------------------------------------------------------------------------
+def rect2hex_coords(h, w, h1, w1):
+    """1-D sample coordinates of the h1 x w1 output lattice in the centred frame
+    of an h x w rectangular image (geometry_np.py:401-421)."""
+    xs = np.linspace(-(h / 2), h / 2, h1)
+    ys = np.linspace(-(w / 2 + 0.5), w / 2 + 0.5, w1)
+    return xs, ys
+
+
+def rect2hex_index(h, w, xs, ys):
+    """Row / column tables: continuous index, truncated index, fraction
+    (geometry_np.py:440-449).  Returns (i_n, i_f, j_n, j_f)."""
+    i_ = xs + (h - 1) * 0.5
+    j_ = ys + (w - 1) * 0.5
+    i_n = i_.astype(np.int64)
+    j_n = j_.astype(np.int64)
+    i_f = i_ - i_n.astype(np.float32)
+    j_f = j_ - j_n.astype(np.float32)
+    return i_n, i_f, j_n, j_f
+
+
+def rect_to_hex_resample(rect_image, hex_dsize=None, interpolation="nearest", offset=0):
+    """geometry_np.py:358-519.  ``offset`` is dead in the reference as well."""
+    method = {"nearest": 0, "bilinear": 1}[interpolation]
+    img = _as_chw(rect_image)
+    c, h, w = img.shape
+    if hex_dsize is None:
+        hex_dsize = (h, w)
+    h1, w1 = hex_dsize
+    xs, ys = rect2hex_coords(h, w, h1, w1)
+    i_n, i_f, j_n, j_f = rect2hex_index(h, w, xs, ys)
+    hwc = np.transpose(img, (1, 2, 0))
+    I0, J0 = i_n[:, None], j_n[None, :]
+    p1, _ = _fetch(hwc, I0, J0)          # (i_n  , j_n  )
+    p2, _ = _fetch(hwc, I0, J0 + 1)      # (i_n  , j_n+1)
+    p3, _ = _fetch(hwc, I0 + 1, J0)      # (i_n+1, j_n  )
+    p4, _ = _fetch(hwc, I0 + 1, J0 + 1)  # (i_n+1, j_n+1)
+    if method == 0:
+        # geometry_np.py:489-512: distances between the *centred* sample
+        # coordinates and the *un-centred* integer corner indices.
+        X, Y = xs[:, None], ys[None, :]
+        dx0 = (X - I0) * (X - I0)
+        dx1 = (X - (I0 + 1)) * (X - (I0 + 1))
+        dy0 = (Y - J0) * (Y - J0)
+        dy1 = (Y - (J0 + 1)) * (Y - (J0 + 1))
+        d = np.stack((dx0 + dy0, dx0 + dy1, dx1 + dy0, dx1 + dy1), axis=0)
+        sel = np.argmin(d, axis=0)
+        out = np.zeros((h1, w1, c), dtype=hwc.dtype)
+        for k, p in enumerate((p1, p2, p3, p4)):
+            out[sel == k] = p[sel == k]
+    else:
+        u = i_f[:, None, None]
+        v = j_f[None, :, None]
+        t1 = u * p3 + (1 - u) * p1        # geometry_np.py:515
+        t2 = u * p4 + (1 - u) * p2        # geometry_np.py:516
+        out = v * t2 + (1 - v) * t1       # geometry_np.py:517
+    return np.transpose(out, (2, 0, 1)).squeeze()
+
+
+# --------------------------------------------------------------------------
+# R2 / R4  hex -> rect, hex -> hex resize  (geometry_np.py:191-356, 520-681;
+#                                            geometry_torch.py:191-358)
+# --------------------------------------------------------------------------
+def hex2rect_coords(h, w, h1, w1, twin="np"):
+    """1-D sample coordinates for hex->rect.  ``twin='np'`` follows
+    geometry_np.py:236-254 (float64 linspace); ``twin='torch'`` follows
+    geometry_torch.py:235-253 (float32 ``torch.linspace`` widened to double)."""
+    x_lo, x_hi = -(h / 2 - 0.5), h / 2 - 0.5
+    y_lo, y_hi = -((w + 0.5) / 2 - 0.75), (w + 0.5) / 2 - 0.75
+    return _linspace_pair(x_lo, x_hi, h1, y_lo, y_hi, w1, twin)
+
+
+def hexresize_coords(h, w, h1, w1):
+    """geometry_np.py:560-578: as hex2rect but the y-range is +-((w+.5)/2-.5)."""
+    x_lo, x_hi = -(h / 2 - 0.5), h / 2 - 0.5
+    y_lo, y_hi = -((w + 0.5) / 2 - 0.5), (w + 0.5) / 2 - 0.5
+    return _linspace_pair(x_lo, x_hi, h1, y_lo, y_hi, w1, "np")
+
+
+def _linspace_pair(x_lo, x_hi, h1, y_lo, y_hi, w1, twin):
+    if twin == "np":
+        return np.linspace(x_lo, x_hi, h1), np.linspace(y_lo, y_hi, w1)
+    if twin == "torch":
+        import torch
+        xs = torch.linspace(x_lo, x_hi, h1).double().numpy()
+        ys = torch.linspace(y_lo, y_hi, w1).double().numpy()
+        return xs, ys
+    raise KeyError(twin)
+
+
+def hexsrc_index(h, w, x_, y_, coord_dtype=np.float64):
+    """Affine (axial) cell of every sample and the four lattice points around it.
+
+    ``x_``/``y_`` are broadcastable 2-D coordinate planes (or (h1,1)/(1,w1)
+    tables).  Follows geometry_np.py:276-298 (== geometry_torch.py:278-300).
+    ``coord_dtype=float32`` reproduces the torch warp, whose inverse-mapped
+    coordinates are cast to float32 (geometry_torch.py:99) so that every
+    following operation runs in float32.
+    Returns dict with i_n, j_n, i_f, j_f, flag, and offset-lattice (i_k, j_k).
+    """
+    ct = np.dtype(coord_dtype).type
+    x_ = np.asarray(x_, dtype=coord_dtype)
+    y_ = np.asarray(y_, dtype=coord_dtype)
+    i_ = x_ + ct((h - 1) * 0.5)
+    j_ = ct(0.5) * i_ + y_ + ct((w - 0.5) * 0.5)
+    i_, j_ = np.broadcast_arrays(i_, j_)
+    i_n = i_.astype(np.int64)
+    j_n = j_.astype(np.int64)
+    i_f = i_ - i_n.astype(np.float32)
+    j_f = j_ - j_n.astype(np.float32)
+    r = dict(i_=i_, j_=j_, i_n=i_n, j_n=j_n, i_f=i_f, j_f=j_f)
+    r["i_1"], r["j_1"] = i_n, j_n - _trunc_div2(i_n + 1)
+    r["i_2"], r["j_2"] = i_n + 1, j_n - _trunc_div2(i_n + 2)
+    r["i_3"], r["j_3"] = i_n, j_n + 1 - _trunc_div2(i_n + 1)
+    r["i_4"], r["j_4"] = i_n + 1, j_n + 1 - _trunc_div2(i_n + 2)
+    r["flag"] = i_f > j_f
+    return r
+
+
+def hexsrc_resample(img_chw, x_, y_, method, coord_dtype=np.float64):
+    """Triangle interpolation on the offset-stored hex lattice at the sample
+    coordinates (x_, y_) (broadcastable).  method 0 = nearest of the three
+    triangle vertices, 1 = barycentric by sub-triangle areas.
+    geometry_np.py:300-354 / geometry_torch.py:302-356.
+
+    In float32 coordinate mode the vertex coordinates follow torch's type
+    promotion (int64 tensor with python float -> float32)."""
+    c, h, w = img_chw.shape
+    hwc = np.transpose(img_chw, (1, 2, 0))
+    r = hexsrc_index(h, w, x_, y_, coord_dtype)
+    ct = np.dtype(coord_dtype).type
+    i_n, j_n, flag = r["i_n"], r["j_n"], r["flag"]
+    x_ = np.broadcast_to(np.asarray(x_, dtype=coord_dtype), i_n.shape)
+    y_ = np.broadcast_to(np.asarray(y_, dtype=coord_dtype), i_n.shape)
+    p1, _ = _fetch(hwc, r["i_1"], r["j_1"])
+    pa, _ = _fetch(hwc, r["i_2"], r["j_2"])
+    pb, _ = _fetch(hwc, r["i_3"], r["j_3"])
+    p3, _ = _fetch(hwc, r["i_4"], r["j_4"])
+    p2 = np.where(flag[..., None], pa, pb)
+    f = flag.astype(coord_dtype)
+    inf_, jnf = i_n.astype(coord_dtype), j_n.astype(coord_dtype)
+    hx, wy = ct((h - 1) / 2), ct((w - 0.5) / 2)
+    two = ct(2)
+    p1_x = inf_ - hx                                         # :326
+    p1_y = jnf - inf_ / two - wy                             # :327
+    p2_x = (inf_ + f) - hx                                   # :328
+    p2_y = (jnf + ct(1) - f) - (inf_ + f) / two - wy         # :329
+    p3_x = (inf_ + ct(1)) - hx                               # :330
+    p3_y = (jnf + ct(1)) - (inf_ + ct(1)) / two - wy         # :331
+    if method == 0:
+        d1 = (x_ - p1_x) * (x_ - p1_x) + (y_ - p1_y) * (y_ - p1_y)
+        d2 = (x_ - p2_x) * (x_ - p2_x) + (y_ - p2_y) * (y_ - p2_y)
+        d3 = (x_ - p3_x) * (x_ - p3_x) + (y_ - p3_y) * (y_ - p3_y)
+        sel = np.argmin(np.stack((d1, d2, d3), 0), axis=0)   # torch.min: first minimum
+        out = np.zeros(p1.shape, dtype=hwc.dtype)
+        for k, p in enumerate((p1, p2, p3)):
+            out[sel == k] = p[sel == k]
+    elif method == 1:
+        half = ct(0.5)
+        S1 = half * np.abs((x_ - p2_x) * (y_ - p3_y) - (y_ - p2_y) * (x_ - p3_x))
+        S2 = half * np.abs((x_ - p1_x) * (y_ - p3_y) - (y_ - p1_y) * (x_ - p3_x))
+        S3 = half * np.abs((x_ - p1_x) * (y_ - p2_y) - (y_ - p1_y) * (x_ - p2_x))
+        with np.errstate(invalid="ignore", divide="ignore"):
+            al = (S1 / (S1 + S2 + S3))[..., None]
+            be = (S2 / (S1 + S2 + S3))[..., None]
+            ga = (S3 / (S1 + S2 + S3))[..., None]
+            out = al * p1 + be * p2 + ga * p3
+    else:
+        raise NotImplementedError("'bilinear' on a hex source executes no branch in the reference")
+    return np.transpose(out, (2, 0, 1)).squeeze()
+
+
+def hex_to_rect_resample(hex_image, rect_dsize=None, interpolation="nearest", offset=0, twin="np"):
+    """geometry_np.py:191-356 (twin='np') / geometry_torch.py:191-358 (twin='torch').
+    'nearest' raises in the numpy reference (np.min unpacking, :339); the oracle
+    gives the result of the working torch twin's selection rule instead."""
+    method = {"nearest": 0, "linear": 1, "bilinear": 2}[interpolation]
+    img = _as_chw(hex_image)
+    c, h, w = img.shape
+    if rect_dsize is None:
+        rect_dsize = (h, w)
+    h1, w1 = rect_dsize
+    xs, ys = hex2rect_coords(h, w, h1, w1, twin)
+    return hexsrc_resample(img, xs[:, None], ys[None, :], method)
+
+
+def hexresize(image, dsize, interpolation="linear", offset=0):
+    """geometry_np.py:520-681."""
+    method = {"nearest": 0, "linear": 1}[interpolation]
+    img = _as_chw(image)
+    c, h, w = img.shape
+    h1, w1 = dsize
+    xs, ys = hexresize_coords(h, w, h1, w1)
+    return hexsrc_resample(img, xs[:, None], ys[None, :], method)
+
+
+# --------------------------------------------------------------------------
+# R3  hex -> hex affine warp (geometry_np.py:6-189, geometry_torch.py:7-189)
+# --------------------------------------------------------------------------
+def warp_coords(h, w, H, twin="np"):
+    """Output lattice of the warp and its inverse-mapped coordinates.
+
+    geometry_np.py:56-100: corners of the source lattice are pushed through H,
+    the output lattice is ``arange`` over their bounding box with odd rows
+    shifted +0.5, then pulled back with inv(H) (no perspective divide).
+    twin='torch' additionally casts to float32 (geometry_torch.py:99)."""
+    H = np.asarray(H, dtype=np.float64)
+    cx, cy = h / 2 - 0.5, (w + 0.5) / 2 - 0.5
+    corners = np.array([[-cx, -cy, 1.0], [-cx, cy, 1.0], [cx, -cy, 1.0], [cx, cy, 1.0]]).T
+    if twin == "np":
+        tc = np.matmul(H, corners)
+        lo0, lo1, hi0, hi1 = tc[0].min(), tc[1].min(), tc[0].max(), tc[1].max()
+        rows = np.arange(lo0, hi0 + 1, 1)
+        cols = np.arange(lo1, hi1 + 0.5, 1)
+        Hi = np.linalg.inv(H)
+    else:
+        import torch
+        Ht = torch.tensor(H).to(torch.float64)
+        tc = torch.matmul(Ht, torch.tensor(corners, dtype=torch.double))
+        lo0, lo1 = torch.min(tc[0]).item(), torch.min(tc[1]).item()
+        hi0, hi1 = torch.max(tc[0]).item(), torch.max(tc[1]).item()
+        rows = torch.arange(lo0, hi0 + 1, 1).double().numpy()
+        cols = torch.arange(lo1, hi1 + 0.5, 1).double().numpy()
+        Hi = torch.linalg.inv(Ht).numpy()
+    h1, w1 = rows.shape[0], cols.shape[0]
+    X = np.broadcast_to(rows[:, None], (h1, w1)).copy()
+    Y = np.broadcast_to(cols[None, :], (h1, w1)).copy()
+    Y[1::2] += 0.5
+    return X, Y, Hi
+
+
+def hex_warp(img, H=np.eye(3), interpolation="nearest", offset=0, twin="np"):
+    """geometry_np.image_geometric_transformation (twin='np', float64 coords) /
+    geometry_torch.image_geometric_transformation_gpu (twin='torch', float32
+    coords).  The inverse map is applied with the same contraction call as the
+    reference so that the coordinates are bit-identical."""
+    method = {"nearest": 0, "linear": 1, "bilinear": 2}[interpolation]
+    img = _as_chw(img)
+    c, h, w = img.shape
+    X, Y, Hi = warp_coords(h, w, H, twin)
+    hom = np.stack([X, Y, np.ones_like(X)], 0)
+    if twin == "np":
+        inv = np.einsum("ij, jkl -> ikl", Hi, hom)
+        return hexsrc_resample(img, inv[0], inv[1], method, np.float64)
+    import torch
+    inv = torch.einsum("ij, jkl -> ikl", torch.tensor(Hi), torch.tensor(hom)).to(torch.float).numpy()
+    return hexsrc_resample(img, inv[0], inv[1], method, np.float32)
+
+
+# --------------------------------------------------------------------------
+# axial <-> offset column index (geometry_np.py:288-295)
+# --------------------------------------------------------------------------
+def axial_to_offset(i, j_ax):
+    i = np.asarray(i, dtype=np.int64)
+    return np.asarray(j_ax, dtype=np.int64) - _trunc_div2(i + 1)
+
+
+def offset_to_axial(i, j_off):
+    i = np.asarray(i, dtype=np.int64)
+    return np.asarray(j_off, dtype=np.int64) + _trunc_div2(i + 1)
+
+
+# --------------------------------------------------------------------------
+# R5  doubled rasters (HexImage.py:139-170 encode, :106-111 decode;
+#                      HexFrames.py:417-458 torch twins)
+# --------------------------------------------------------------------------
+def hex_to_type1(hex_img, even_odd_offset=0, dtype=np.float64):
+    """(..., H, W) -> (..., H, 2W+1): every cell twice along W; rows with
+    (i + offset) odd get one leading zero, the others one trailing zero."""
+    a = np.asarray(hex_img)
+    H, W = a.shape[-2:]
+    out = np.zeros(a.shape[:-1] + (2 * W + 1,), dtype=dtype)
+    rep = np.repeat(a, 2, axis=-1)
+    shift = (np.arange(H) + int(even_odd_offset)) % 2
+    for s in (0, 1):
+        rows = np.nonzero(shift == s)[0]
+        out[..., rows, s:s + 2 * W] = rep[..., rows, :]
+    return out
+
+
+def hex_to_type2(hex_img, even_odd_offset=0, dtype=np.float64):
+    """type1 with every row written twice (HexImage.py:154-170)."""
+    return np.repeat(hex_to_type1(hex_img, even_odd_offset, dtype), 2, axis=-2)
+
+
+def type1_to_hex(t1):
+    """HexImage.py:109 ``data[:, :, 1:-1:2]`` (== HexFrames.py:457 ``[..., 1::2]``
+    for an odd-width raster)."""
+    return np.asarray(t1)[..., 1:-1:2]
+
+
+def type2_to_hex(t2):
+    """HexImage.py:111 ``data[:, ::2, 1:-1:2]``."""
+    return np.asarray(t2)[..., ::2, 1:-1:2]
