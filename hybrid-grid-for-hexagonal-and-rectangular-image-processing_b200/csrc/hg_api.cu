@@ -1,0 +1,32 @@
+// hg_api.cu -- version, thread-local error string, launch counter.
+#include "hg_common.cuh"
+#include <string.h>
+
+namespace hg {
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+int finish_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  g_launches += 1;
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return HG_OK;
+}
+}  // namespace hg
+
+extern "C" {
+int hg_version(void) { return HG_VERSION; }
+const char* hg_last_error(void) { return hg::g_err; }
+int64_t hg_launch_count(void) { return hg::g_launches; }
+void hg_reset_launch_count(void) { hg::g_launches = 0; }
+}

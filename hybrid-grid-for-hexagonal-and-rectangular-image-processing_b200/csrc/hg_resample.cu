@@ -1,0 +1,675 @@
+// hg_resample.cu -- rect<->hex resampling gathers and the lattice index kernels (sm_100a).
+//
+// Every kernel here is HBM-bound: one pass over the source planes, one pass over the
+// destination planes.  Work decomposition shared by all of them:
+//   CTA = 256 threads = 8 warps; tile = 32 output rows x 128 output columns;
+//   warp w owns rows 4w..4w+3, lane l owns columns l, l+32, l+64, l+96 of the tile
+//   (lane-consecutive columns: every warp store is one full 128-byte line for fp32, and the
+//   gathered taps of neighbouring lanes fall in the same / adjacent 128-byte source lines).
+// The sampling geometry depends only on the shapes, never on the image: each thread derives
+// its column (and row) tables once and re-uses them for every plane it processes.
+#include "hg_common.cuh"
+#include <type_traits>
+
+namespace hg {
+
+constexpr int kTileW = 128;
+constexpr int kTileH = 32;
+constexpr int kThreads = 256;
+constexpr int kColsPerThread = 4;
+constexpr int kRowsPerWarp = 4;
+
+template <typename T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
+
+// ==========================================================================================
+// R1  rect -> hex   (ref: geometry_np.py:358-519)
+// ==========================================================================================
+struct RectCol {  // per output column (ref: geometry_np.py:441-449)
+  int j_n;
+  double j_f;
+};
+
+__device__ __forceinline__ void rect_axis(double coord, int n, int& idx, double& frac) {
+  // i_ = x_ + (h-1)*0.5 ; i_n = trunc(i_) ; i_f = i_ - float32(i_n)
+  double c = dadd(coord, (double)(n - 1) * 0.5);
+  idx = trunc_i32(c);
+  frac = dsub(c, (double)(float)idx);
+}
+
+__global__ void rect2hex_index_kernel(const double* __restrict__ xs, const double* __restrict__ ys, int h, int w,
+                                      int h1, int w1, int32_t* i_n, double* i_f, int32_t* j_n, double* j_f) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < h1) {
+    int n; double f;
+    rect_axis(xs[t], h, n, f);
+    i_n[t] = n; i_f[t] = f;
+  }
+  if (t < w1) {
+    int n; double f;
+    rect_axis(ys[t], w, n, f);
+    j_n[t] = n; j_f[t] = f;
+  }
+}
+
+// Bilinear blend, literal operation order of geometry_np.py:515-517.
+template <typename TS, typename TD, bool EXACT>
+__global__ void __launch_bounds__(kThreads)
+rect2hex_bilinear_kernel(const TS* __restrict__ src, TD* __restrict__ dst, const double* __restrict__ xs,
+                         const double* __restrict__ ys, int h, int w, int h1, int w1, int tiles_x, int tiles_y) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int tile = blockIdx.x;
+  const int tx = tile % tiles_x; tile /= tiles_x;
+  const int ty = tile % tiles_y;
+  const int64_t plane = tile / tiles_y;
+  const TS* __restrict__ sp = src + plane * (int64_t)h * w;
+  TD* __restrict__ dp = dst + plane * (int64_t)h1 * w1;
+
+  int jn[kColsPerThread];
+  double jf[kColsPerThread];
+  bool cok[kColsPerThread];
+#pragma unroll
+  for (int k = 0; k < kColsPerThread; ++k) {
+    const int b = tx * kTileW + lane + 32 * k;
+    cok[k] = b < w1;
+    rect_axis(cok[k] ? ys[b] : 0.0, w, jn[k], jf[k]);
+  }
+#pragma unroll
+  for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+    const int a = ty * kTileH + warp * kRowsPerWarp + rr;
+    if (a >= h1) break;
+    int in; double u;
+    rect_axis(xs[a], h, in, u);
+    const bool r0 = in >= 0 && in < h, r1 = in + 1 >= 0 && in + 1 < h;
+    const TS* row0 = sp + (int64_t)in * w;
+    const TS* row1 = row0 + w;
+    TS p[kColsPerThread][4];
+#pragma unroll
+    for (int k = 0; k < kColsPerThread; ++k) {
+      const bool c0 = jn[k] >= 0 && jn[k] < w, c1 = jn[k] + 1 >= 0 && jn[k] + 1 < w;
+      p[k][0] = (r0 && c0 && cok[k]) ? ldg(row0 + jn[k]) : TS(0);
+      p[k][1] = (r0 && c1 && cok[k]) ? ldg(row0 + jn[k] + 1) : TS(0);
+      p[k][2] = (r1 && c0 && cok[k]) ? ldg(row1 + jn[k]) : TS(0);
+      p[k][3] = (r1 && c1 && cok[k]) ? ldg(row1 + jn[k] + 1) : TS(0);
+    }
+#pragma unroll
+    for (int k = 0; k < kColsPerThread; ++k) {
+      if (!cok[k]) continue;
+      const int b = tx * kTileW + lane + 32 * k;
+      TD o;
+      if (EXACT) {
+        const double v = jf[k];
+        const double u1 = dsub(1.0, u), v1 = dsub(1.0, v);
+        const double t1 = dadd(dmul(u, to_f64(p[k][2])), dmul(u1, to_f64(p[k][0])));
+        const double t2 = dadd(dmul(u, to_f64(p[k][3])), dmul(u1, to_f64(p[k][1])));
+        o = (TD)dadd(dmul(v, t2), dmul(v1, t1));
+      } else {
+        const float uf = (float)u, vf = (float)jf[k];
+        const float t1 = fmaf(uf, to_f32(p[k][2]) - to_f32(p[k][0]), to_f32(p[k][0]));
+        const float t2 = fmaf(uf, to_f32(p[k][3]) - to_f32(p[k][1]), to_f32(p[k][1]));
+        o = (TD)fmaf(vf, t2 - t1, t1);
+      }
+      st_stream(dp + (int64_t)a * w1 + b, o);
+    }
+  }
+}
+
+// Nearest: literal 4-way argmin of geometry_np.py:499-512 (distances between the centred sample
+// coordinates and the un-centred corner indices; first minimum wins), then one gather.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+rect2hex_nearest_kernel(const T* __restrict__ src, T* __restrict__ dst, const double* __restrict__ xs,
+                        const double* __restrict__ ys, int h, int w, int h1, int w1, int tiles_x, int tiles_y) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int tile = blockIdx.x;
+  const int tx = tile % tiles_x; tile /= tiles_x;
+  const int ty = tile % tiles_y;
+  const int64_t plane = tile / tiles_y;
+  const T* __restrict__ sp = src + plane * (int64_t)h * w;
+  T* __restrict__ dp = dst + plane * (int64_t)h1 * w1;
+
+  int jn[kColsPerThread];
+  double dy0[kColsPerThread], dy1[kColsPerThread];
+  bool cok[kColsPerThread];
+#pragma unroll
+  for (int k = 0; k < kColsPerThread; ++k) {
+    const int b = tx * kTileW + lane + 32 * k;
+    cok[k] = b < w1;
+    const double y = cok[k] ? ys[b] : 0.0;
+    double f;
+    rect_axis(y, w, jn[k], f);
+    const double e0 = dsub(y, (double)jn[k]), e1 = dsub(y, (double)(jn[k] + 1));
+    dy0[k] = dmul(e0, e0);
+    dy1[k] = dmul(e1, e1);
+  }
+#pragma unroll
+  for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+    const int a = ty * kTileH + warp * kRowsPerWarp + rr;
+    if (a >= h1) break;
+    const double x = xs[a];
+    int in; double f;
+    rect_axis(x, h, in, f);
+    const double e0 = dsub(x, (double)in), e1 = dsub(x, (double)(in + 1));
+    const double dx0 = dmul(e0, e0), dx1 = dmul(e1, e1);
+#pragma unroll
+    for (int k = 0; k < kColsPerThread; ++k) {
+      if (!cok[k]) continue;
+      const double d1 = dadd(dx0, dy0[k]), d2 = dadd(dx0, dy1[k]), d3 = dadd(dx1, dy0[k]), d4 = dadd(dx1, dy1[k]);
+      int sel = 0; double best = d1;
+      if (d2 < best) { best = d2; sel = 1; }
+      if (d3 < best) { best = d3; sel = 2; }
+      if (d4 < best) { best = d4; sel = 3; }
+      const int i = in + (sel >> 1), j = jn[k] + (sel & 1);
+      T v = T(0);
+      if (i >= 0 && i < h && j >= 0 && j < w) v = ldg(sp + (int64_t)i * w + j);
+      dp[(int64_t)a * w1 + tx * kTileW + lane + 32 * k] = v;
+    }
+  }
+}
+
+// ==========================================================================================
+// R2/R3/R4  sampling a hex-lattice image (ref: geometry_np.py:276-354, geometry_torch.py:278-356)
+// ==========================================================================================
+template <typename CT> struct Arith;
+template <> struct Arith<double> {
+  static __device__ __forceinline__ double add(double a, double b) { return dadd(a, b); }
+  static __device__ __forceinline__ double sub(double a, double b) { return dsub(a, b); }
+  static __device__ __forceinline__ double mul(double a, double b) { return dmul(a, b); }
+  static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+  static __device__ __forceinline__ double abs(double a) { return fabs(a); }
+};
+template <> struct Arith<float> {
+  static __device__ __forceinline__ float add(float a, float b) { return fadd(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return fsub(a, b); }
+  static __device__ __forceinline__ float mul(float a, float b) { return fmul(a, b); }
+  static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+  static __device__ __forceinline__ float abs(float a) { return fabsf(a); }
+};
+
+// The three lattice points fetched for one sample and their weights.
+template <typename CT>
+struct HexSample {
+  int i_n, j_n;
+  int off[3];   // linear offset i*w + j_off of P1, (P2 or P3), P4; -1 = outside (zero-filled)
+  bool flag;    // up_down_flag = i_f > j_f
+  CT wgt[3];    // barycentric weights alpha, beta, gamma (linear)
+  int nearest;  // index (0..2) of the closest vertex (nearest)
+};
+
+template <typename CT, bool WANT_LINEAR, bool WANT_NEAREST>
+__device__ __forceinline__ void hex_locate(CT x, CT y, int h, int w, CT hx, CT wy, CT ci, CT cj, HexSample<CT>& s) {
+  using A = Arith<CT>;
+  // ref geometry_np.py:276-285: i_ = x_ + (h-1)*0.5 ; j_ = 0.5*i_ + y_ + (w-0.5)*0.5
+  const CT i_ = A::add(x, ci);
+  const CT j_ = A::add(A::add(A::mul(CT(0.5), i_), y), cj);
+  const int in = trunc_i32(i_), jn = trunc_i32(j_);
+  const CT i_f = A::sub(i_, (CT)(float)in), j_f = A::sub(j_, (CT)(float)jn);
+  const bool f = i_f > j_f;  // :298
+  s.i_n = in; s.j_n = jn; s.flag = f;
+  // :288-295 axial -> offset columns of the cell's lattice points
+  const int j1 = jn - trunc_half(in + 1), j2 = jn - trunc_half(in + 2);
+  const int iA = in, jA = j1;                       // P1
+  const int iB = f ? in + 1 : in, jB = f ? j2 : j1 + 1;  // P2 (below) or P3 (right)
+  const int iC = in + 1, jC = j2 + 1;               // P4
+  s.off[0] = (iA >= 0 && iA < h && jA >= 0 && jA < w) ? iA * w + jA : -1;
+  s.off[1] = (iB >= 0 && iB < h && jB >= 0 && jB < w) ? iB * w + jB : -1;
+  s.off[2] = (iC >= 0 && iC < h && jC >= 0 && jC < w) ? iC * w + jC : -1;
+  // :326-331 cartesian coordinates of the triangle vertices
+  const CT fi = (CT)in, fj = (CT)jn, ff = f ? CT(1) : CT(0);
+  const CT p1x = A::sub(fi, hx);
+  const CT p1y = A::sub(A::sub(fj, A::div(fi, CT(2))), wy);
+  const CT p2x = A::sub(A::add(fi, ff), hx);
+  const CT p2y = A::sub(A::sub(A::sub(A::add(fj, CT(1)), ff), A::div(A::add(fi, ff), CT(2))), wy);
+  const CT p3x = A::sub(A::add(fi, CT(1)), hx);
+  const CT p3y = A::sub(A::sub(A::add(fj, CT(1)), A::div(A::add(fi, CT(1)), CT(2))), wy);
+  const CT ax = A::sub(x, p1x), ay = A::sub(y, p1y);
+  const CT bx = A::sub(x, p2x), by = A::sub(y, p2y);
+  const CT cx = A::sub(x, p3x), cy = A::sub(y, p3y);
+  if (WANT_NEAREST) {  // :334-347, first minimum wins
+    const CT d1 = A::add(A::mul(ax, ax), A::mul(ay, ay));
+    const CT d2 = A::add(A::mul(bx, bx), A::mul(by, by));
+    const CT d3 = A::add(A::mul(cx, cx), A::mul(cy, cy));
+    int sel = 0; CT best = d1;
+    if (d2 < best) { best = d2; sel = 1; }
+    if (d3 < best) { sel = 2; }
+    s.nearest = sel;
+  }
+  if (WANT_LINEAR) {   // :348-354 sub-triangle areas
+    const CT S1 = A::mul(CT(0.5), A::abs(A::sub(A::mul(bx, cy), A::mul(by, cx))));
+    const CT S2 = A::mul(CT(0.5), A::abs(A::sub(A::mul(ax, cy), A::mul(ay, cx))));
+    const CT S3 = A::mul(CT(0.5), A::abs(A::sub(A::mul(ax, by), A::mul(ay, bx))));
+    const CT tot = A::add(A::add(S1, S2), S3);
+    s.wgt[0] = A::div(S1, tot);
+    s.wgt[1] = A::div(S2, tot);
+    s.wgt[2] = A::div(S3, tot);
+  }
+}
+
+// Fast (fp32) variant: simplex interpolation in the axial unit cell (SURVEY 8a closed form):
+// u = i_f, v = j_f;  u > v : (1-u, u-v, v)   else (1-v, v-u, u).  Index math stays exact.
+__device__ __forceinline__ void hex_locate_fast(double x, double y, int h, int w, double ci, double cj,
+                                                HexSample<float>& s) {
+  const double i_ = dadd(x, ci);
+  const double j_ = dadd(dadd(dmul(0.5, i_), y), cj);
+  const int in = trunc_i32(i_), jn = trunc_i32(j_);
+  const double i_f = dsub(i_, (double)in), j_f = dsub(j_, (double)jn);
+  const bool f = i_f > j_f;
+  s.i_n = in; s.j_n = jn; s.flag = f;
+  const int j1 = jn - trunc_half(in + 1), j2 = jn - trunc_half(in + 2);
+  const int iA = in, jA = j1;
+  const int iB = f ? in + 1 : in, jB = f ? j2 : j1 + 1;
+  const int iC = in + 1, jC = j2 + 1;
+  s.off[0] = (iA >= 0 && iA < h && jA >= 0 && jA < w) ? iA * w + jA : -1;
+  s.off[1] = (iB >= 0 && iB < h && jB >= 0 && jB < w) ? iB * w + jB : -1;
+  s.off[2] = (iC >= 0 && iC < h && jC >= 0 && jC < w) ? iC * w + jC : -1;
+  const float u = (float)i_f, v = (float)j_f;
+  s.wgt[0] = f ? 1.f - u : 1.f - v;
+  s.wgt[1] = f ? u - v : v - u;
+  s.wgt[2] = f ? v : u;
+}
+
+// ---- coordinate sources ------------------------------------------------------------------
+struct CoordTables {  // separable: hex->rect, hexresize (ref geometry_np.py:253-254 linspace)
+  using CT = double;
+  const double* xs; const double* ys;
+  __device__ __forceinline__ void get(int a, int b, int w1, double& x, double& y) const { x = xs[a]; y = ys[b]; }
+};
+template <typename CT_>
+struct CoordPlanes {  // warp with host-evaluated inverse map (bit-identical to the reference einsum)
+  using CT = CT_;
+  const CT_* cx; const CT_* cy;
+  __device__ __forceinline__ void get(int a, int b, int w1, CT_& x, CT_& y) const {
+    x = cx[(int64_t)a * w1 + b]; y = cy[(int64_t)a * w1 + b];
+  }
+};
+template <typename CT_>
+struct CoordAffine {  // warp with the inverse map evaluated in-kernel
+  using CT = CT_;
+  double m[6]; double row0, col0;
+  __device__ __forceinline__ void get(int a, int b, int w1, CT_& x, CT_& y) const {
+    const double X = dadd(row0, (double)a);
+    const double Y = dadd(dadd(col0, (double)b), (a & 1) ? 0.5 : 0.0);
+    x = (CT_)dadd(dadd(dmul(m[0], X), dmul(m[1], Y)), m[2]);
+    y = (CT_)dadd(dadd(dmul(m[3], X), dmul(m[4], Y)), m[5]);
+  }
+};
+
+struct HexConsts { double hx, wy, ci, cj; };
+static HexConsts hex_consts(int64_t h, int64_t w) {
+  // the reference evaluates these python-float expressions in double
+  return HexConsts{(h - 1) / 2.0, (w - 0.5) / 2.0, (h - 1) * 0.5, (w - 0.5) * 0.5};
+}
+
+// Blend type of `alpha * p1 + beta * p2 + gamma * p3` under numpy/torch promotion:
+// float32 weights stay float32 unless the image is float64.
+template <typename CT, typename TS> struct BlendT { using type = double; };
+template <> struct BlendT<float, float> { using type = float; };
+template <> struct BlendT<float, uint8_t> { using type = float; };
+
+constexpr int kPlaneChunk = 8;  // planes per CTA: amortises the per-sample geometry
+
+template <typename TS, typename TD, typename Coord, bool FAST>
+__global__ void __launch_bounds__(kThreads)
+hexsrc_linear_kernel(const TS* __restrict__ src, TD* __restrict__ dst, Coord coord, HexConsts hc, int64_t planes,
+                     int h, int w, int h1, int w1, int tiles_x, int tiles_y) {
+  using CT = typename Coord::CT;
+  using WT = typename std::conditional<FAST, float, CT>::type;
+  using BT = typename std::conditional<FAST, float, typename BlendT<CT, TS>::type>::type;
+  using AB = Arith<BT>;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int tile = blockIdx.x;
+  const int tx = tile % tiles_x; tile /= tiles_x;
+  const int ty = tile % tiles_y;
+  const int64_t p0 = (int64_t)(tile / tiles_y) * kPlaneChunk;
+  const int np = (int)min((int64_t)kPlaneChunk, planes - p0);
+  const int64_t sps = (int64_t)h * w, dps = (int64_t)h1 * w1;
+
+  for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+    const int a = ty * kTileH + warp * kRowsPerWarp + rr;
+    if (a >= h1) break;
+    HexSample<WT> s[kColsPerThread];
+    bool cok[kColsPerThread];
+#pragma unroll
+    for (int k = 0; k < kColsPerThread; ++k) {
+      const int b = tx * kTileW + lane + 32 * k;
+      cok[k] = b < w1;
+      CT x, y;
+      coord.get(a, cok[k] ? b : 0, w1, x, y);
+      if (FAST) hex_locate_fast((double)x, (double)y, h, w, hc.ci, hc.cj, (HexSample<float>&)s[k]);
+      else hex_locate<CT, true, false>(x, y, h, w, (CT)hc.hx, (CT)hc.wy, (CT)hc.ci, (CT)hc.cj, (HexSample<CT>&)s[k]);
+    }
+    const TS* __restrict__ sp = src + p0 * sps;
+    TD* __restrict__ dp = dst + p0 * dps + (int64_t)a * w1 + tx * kTileW + lane;
+    for (int p = 0; p < np; ++p, sp += sps, dp += dps) {
+      TS v[kColsPerThread][3];
+#pragma unroll
+      for (int k = 0; k < kColsPerThread; ++k)
+#pragma unroll
+        for (int t = 0; t < 3; ++t) v[k][t] = (cok[k] && s[k].off[t] >= 0) ? ldg(sp + s[k].off[t]) : TS(0);
+#pragma unroll
+      for (int k = 0; k < kColsPerThread; ++k) {
+        if (!cok[k]) continue;
+        BT o;
+        if (FAST) {
+          o = fmaf((float)s[k].wgt[2], to_f32(v[k][2]),
+                   fmaf((float)s[k].wgt[1], to_f32(v[k][1]), (float)s[k].wgt[0] * to_f32(v[k][0])));
+        } else {
+          // ref geometry_np.py:354  alpha * p1 + beta * p2 + gamma * p3
+          o = AB::add(AB::add(AB::mul((BT)s[k].wgt[0], (BT)v[k][0]), AB::mul((BT)s[k].wgt[1], (BT)v[k][1])),
+                      AB::mul((BT)s[k].wgt[2], (BT)v[k][2]));
+        }
+        st_stream(dp + 32 * k, (TD)o);
+      }
+    }
+  }
+}
+
+template <typename T, typename Coord>
+__global__ void __launch_bounds__(kThreads)
+hexsrc_nearest_kernel(const T* __restrict__ src, T* __restrict__ dst, Coord coord, HexConsts hc, int64_t planes,
+                      int h, int w, int h1, int w1, int tiles_x, int tiles_y) {
+  using CT = typename Coord::CT;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int tile = blockIdx.x;
+  const int tx = tile % tiles_x; tile /= tiles_x;
+  const int ty = tile % tiles_y;
+  const int64_t p0 = (int64_t)(tile / tiles_y) * kPlaneChunk;
+  const int np = (int)min((int64_t)kPlaneChunk, planes - p0);
+  const int64_t sps = (int64_t)h * w, dps = (int64_t)h1 * w1;
+  for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+    const int a = ty * kTileH + warp * kRowsPerWarp + rr;
+    if (a >= h1) break;
+    int off[kColsPerThread];
+#pragma unroll
+    for (int k = 0; k < kColsPerThread; ++k) {
+      const int b = tx * kTileW + lane + 32 * k;
+      off[k] = -2;
+      if (b < w1) {
+        CT x, y;
+        coord.get(a, b, w1, x, y);
+        HexSample<CT> s;
+        hex_locate<CT, false, true>(x, y, h, w, (CT)hc.hx, (CT)hc.wy, (CT)hc.ci, (CT)hc.cj, s);
+        off[k] = s.off[s.nearest];
+      }
+    }
+    const T* __restrict__ sp = src + p0 * sps;
+    T* __restrict__ dp = dst + p0 * dps + (int64_t)a * w1 + tx * kTileW + lane;
+    for (int p = 0; p < np; ++p, sp += sps, dp += dps) {
+#pragma unroll
+      for (int k = 0; k < kColsPerThread; ++k)
+        if (off[k] != -2) dp[32 * k] = off[k] >= 0 ? ldg(sp + off[k]) : T(0);
+    }
+  }
+}
+
+template <typename Coord>
+__global__ void hexsrc_index_kernel(Coord coord, HexConsts hc, int h, int w, int h1, int w1, int32_t* i_n,
+                                    int32_t* j_n, uint8_t* tri, int32_t* off) {
+  using CT = typename Coord::CT;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)h1 * w1) return;
+  const int a = (int)(t / w1), b = (int)(t % w1);
+  CT x, y;
+  coord.get(a, b, w1, x, y);
+  HexSample<CT> s;
+  hex_locate<CT, false, false>(x, y, h, w, (CT)hc.hx, (CT)hc.wy, (CT)hc.ci, (CT)hc.cj, s);
+  i_n[t] = s.i_n; j_n[t] = s.j_n;
+  tri[t] = (uint8_t)((s.flag ? 1 : 0) | (s.off[0] >= 0 ? 2 : 0) | (s.off[1] >= 0 ? 4 : 0) | (s.off[2] >= 0 ? 8 : 0));
+  const int64_t n = (int64_t)h1 * w1;
+  off[t] = s.off[0]; off[n + t] = s.off[1]; off[2 * n + t] = s.off[2];
+}
+
+__global__ void axial_offset_kernel(const int32_t* i, const int32_t* jin, int32_t* jout, int64_t n, int sign) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) jout[t] = jin[t] + sign * trunc_half(i[t] + 1);
+}
+
+// ---- host-side launch helpers -------------------------------------------------------------
+struct Tiling { int tx, ty; int64_t blocks; };
+static int make_tiling(int64_t h1, int64_t w1, int64_t plane_groups, Tiling& t) {
+  t.tx = (int)ceil_div(w1, kTileW);
+  t.ty = (int)ceil_div(h1, kTileH);
+  t.blocks = (int64_t)t.tx * t.ty * plane_groups;
+  HG_REQUIRE(t.blocks > 0 && t.blocks < (1ll << 31), HG_E_SHAPE, "grid of %lld tiles is out of range", (long long)t.blocks);
+  return HG_OK;
+}
+static int check_plane(int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1) {
+  HG_REQUIRE(planes >= 0 && h > 0 && w > 0 && h1 >= 0 && w1 >= 0, HG_E_SHAPE, "bad shape planes=%lld h=%lld w=%lld h1=%lld w1=%lld",
+             (long long)planes, (long long)h, (long long)w, (long long)h1, (long long)w1);
+  HG_REQUIRE(h * w < (1ll << 31) && h1 * w1 < (1ll << 31), HG_E_SHAPE, "a single plane must have < 2^31 cells");
+  return HG_OK;
+}
+
+template <typename TS, typename TD>
+static int launch_rect2hex_bilinear(const void* src, void* dst, const double* xs, const double* ys, int64_t planes,
+                                    int64_t h, int64_t w, int64_t h1, int64_t w1, int math, cudaStream_t st) {
+  Tiling t;
+  int rc = make_tiling(h1, w1, planes, t);
+  if (rc) return rc;
+  if (math == HG_MATH_EXACT)
+    rect2hex_bilinear_kernel<TS, TD, true><<<(unsigned)t.blocks, kThreads, 0, st>>>(
+        (const TS*)src, (TD*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, t.tx, t.ty);
+  else
+    rect2hex_bilinear_kernel<TS, TD, false><<<(unsigned)t.blocks, kThreads, 0, st>>>(
+        (const TS*)src, (TD*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, t.tx, t.ty);
+  return finish_launch("rect2hex_bilinear");
+}
+
+template <typename T>
+static int launch_rect2hex_nearest(const void* src, void* dst, const double* xs, const double* ys, int64_t planes,
+                                   int64_t h, int64_t w, int64_t h1, int64_t w1, cudaStream_t st) {
+  Tiling t;
+  int rc = make_tiling(h1, w1, planes, t);
+  if (rc) return rc;
+  rect2hex_nearest_kernel<T><<<(unsigned)t.blocks, kThreads, 0, st>>>((const T*)src, (T*)dst, xs, ys, (int)h, (int)w,
+                                                                      (int)h1, (int)w1, t.tx, t.ty);
+  return finish_launch("rect2hex_nearest");
+}
+
+template <typename TS, typename TD, typename Coord, bool FAST>
+static int launch_hexsrc_linear(const void* src, void* dst, const Coord& c, int64_t planes, int64_t h, int64_t w,
+                                int64_t h1, int64_t w1, cudaStream_t st) {
+  Tiling t;
+  int rc = make_tiling(h1, w1, ceil_div(planes, kPlaneChunk), t);
+  if (rc) return rc;
+  hexsrc_linear_kernel<TS, TD, Coord, FAST><<<(unsigned)t.blocks, kThreads, 0, st>>>(
+      (const TS*)src, (TD*)dst, c, hex_consts(h, w), planes, (int)h, (int)w, (int)h1, (int)w1, t.tx, t.ty);
+  return finish_launch("hexsrc_linear");
+}
+
+template <typename Coord, bool FAST>
+static int dispatch_hexsrc_linear(const void* src, void* dst, const Coord& c, int64_t planes, int64_t h, int64_t w,
+                                  int64_t h1, int64_t w1, int sdt, int ddt, cudaStream_t st) {
+#define HG_CASE(S, TS, D, TD) \
+  if (sdt == S && ddt == D) return launch_hexsrc_linear<TS, TD, Coord, FAST>(src, dst, c, planes, h, w, h1, w1, st);
+  HG_CASE(HG_U8, uint8_t, HG_F32, float)
+  HG_CASE(HG_U8, uint8_t, HG_F64, double)
+  HG_CASE(HG_F32, float, HG_F32, float)
+  HG_CASE(HG_F32, float, HG_F64, double)
+  HG_CASE(HG_F64, double, HG_F32, float)
+  HG_CASE(HG_F64, double, HG_F64, double)
+#undef HG_CASE
+  set_error("hexsrc_linear: unsupported dtypes src=%d dst=%d", sdt, ddt);
+  return HG_E_DTYPE;
+}
+
+template <typename Coord>
+static int dispatch_hexsrc_nearest(const void* src, void* dst, const Coord& c, int64_t planes, int64_t h, int64_t w,
+                                   int64_t h1, int64_t w1, int elem, cudaStream_t st) {
+  Tiling t;
+  int rc = make_tiling(h1, w1, ceil_div(planes, kPlaneChunk), t);
+  if (rc) return rc;
+  const HexConsts hc = hex_consts(h, w);
+#define HG_CASE(E, T)                                                                                          \
+  if (elem == E) {                                                                                             \
+    hexsrc_nearest_kernel<T, Coord><<<(unsigned)t.blocks, kThreads, 0, st>>>((const T*)src, (T*)dst, c, hc, planes, \
+                                                                            (int)h, (int)w, (int)h1, (int)w1, t.tx, t.ty); \
+    return finish_launch("hexsrc_nearest");                                                                    \
+  }
+  HG_CASE(1, uint8_t)
+  HG_CASE(2, uint16_t)
+  HG_CASE(4, uint32_t)
+  HG_CASE(8, uint64_t)
+#undef HG_CASE
+  set_error("hexsrc_nearest: unsupported element size %d", elem);
+  return HG_E_DTYPE;
+}
+
+}  // namespace hg
+
+using namespace hg;
+
+extern "C" {
+
+int hg_axial_to_offset_i32(const int32_t* i, const int32_t* j_ax, int32_t* j_off, int64_t n, hg_stream_t stream) {
+  HG_REQUIRE(n >= 0, HG_E_SHAPE, "n < 0");
+  if (n == 0) return HG_OK;
+  axial_offset_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(i, j_ax, j_off, n, -1);
+  return finish_launch("axial_to_offset");
+}
+int hg_offset_to_axial_i32(const int32_t* i, const int32_t* j_off, int32_t* j_ax, int64_t n, hg_stream_t stream) {
+  HG_REQUIRE(n >= 0, HG_E_SHAPE, "n < 0");
+  if (n == 0) return HG_OK;
+  axial_offset_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(i, j_off, j_ax, n, +1);
+  return finish_launch("offset_to_axial");
+}
+
+int hg_rect2hex_index(const double* xs, const double* ys, int64_t h, int64_t w, int64_t h1, int64_t w1, int32_t* i_n,
+                      double* i_f, int32_t* j_n, double* j_f, hg_stream_t stream) {
+  int rc = check_plane(0, h, w, h1, w1);
+  if (rc) return rc;
+  const int64_t n = h1 > w1 ? h1 : w1;
+  if (n == 0) return HG_OK;
+  rect2hex_index_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(xs, ys, (int)h, (int)w, (int)h1,
+                                                                                  (int)w1, i_n, i_f, j_n, j_f);
+  return finish_launch("rect2hex_index");
+}
+
+int hg_hexsrc_index(const void* xs, const void* ys, int coords_2d, int coord_f32, int64_t h, int64_t w, int64_t h1,
+                    int64_t w1, int32_t* i_n, int32_t* j_n, uint8_t* tri, int32_t* off, hg_stream_t stream) {
+  int rc = check_plane(0, h, w, h1, w1);
+  if (rc) return rc;
+  const int64_t n = h1 * w1;
+  if (n == 0) return HG_OK;
+  const unsigned g = (unsigned)ceil_div(n, 256);
+  const HexConsts hc = hex_consts(h, w);
+  cudaStream_t st = as_stream(stream);
+  if (!coords_2d) {
+    HG_REQUIRE(!coord_f32, HG_E_UNSUPPORTED, "separable coordinate tables are float64");
+    hexsrc_index_kernel<<<g, 256, 0, st>>>(CoordTables{(const double*)xs, (const double*)ys}, hc, (int)h, (int)w,
+                                           (int)h1, (int)w1, i_n, j_n, tri, off);
+  } else if (coord_f32) {
+    hexsrc_index_kernel<<<g, 256, 0, st>>>(CoordPlanes<float>{(const float*)xs, (const float*)ys}, hc, (int)h, (int)w,
+                                           (int)h1, (int)w1, i_n, j_n, tri, off);
+  } else {
+    hexsrc_index_kernel<<<g, 256, 0, st>>>(CoordPlanes<double>{(const double*)xs, (const double*)ys}, hc, (int)h,
+                                           (int)w, (int)h1, (int)w1, i_n, j_n, tri, off);
+  }
+  return finish_launch("hexsrc_index");
+}
+
+int hg_rect2hex_nearest(const void* src, void* dst, const double* xs, const double* ys, int64_t planes, int64_t h,
+                        int64_t w, int64_t h1, int64_t w1, int elem_size, hg_stream_t stream) {
+  int rc = check_plane(planes, h, w, h1, w1);
+  if (rc) return rc;
+  if (planes == 0 || h1 == 0 || w1 == 0) return HG_OK;
+  cudaStream_t st = as_stream(stream);
+  switch (elem_size) {
+    case 1: return launch_rect2hex_nearest<uint8_t>(src, dst, xs, ys, planes, h, w, h1, w1, st);
+    case 2: return launch_rect2hex_nearest<uint16_t>(src, dst, xs, ys, planes, h, w, h1, w1, st);
+    case 4: return launch_rect2hex_nearest<uint32_t>(src, dst, xs, ys, planes, h, w, h1, w1, st);
+    case 8: return launch_rect2hex_nearest<uint64_t>(src, dst, xs, ys, planes, h, w, h1, w1, st);
+  }
+  set_error("rect2hex_nearest: unsupported element size %d", elem_size);
+  return HG_E_DTYPE;
+}
+
+int hg_rect2hex_bilinear(const void* src, void* dst, const double* xs, const double* ys, int64_t planes, int64_t h,
+                         int64_t w, int64_t h1, int64_t w1, int src_dtype, int dst_dtype, int math, hg_stream_t stream) {
+  int rc = check_plane(planes, h, w, h1, w1);
+  if (rc) return rc;
+  HG_REQUIRE(math == HG_MATH_EXACT || math == HG_MATH_FAST, HG_E_ARG, "bad math mode %d", math);
+  if (planes == 0 || h1 == 0 || w1 == 0) return HG_OK;
+  cudaStream_t st = as_stream(stream);
+#define HG_CASE(S, TS, D, TD) \
+  if (src_dtype == S && dst_dtype == D) return launch_rect2hex_bilinear<TS, TD>(src, dst, xs, ys, planes, h, w, h1, w1, math, st);
+  HG_CASE(HG_U8, uint8_t, HG_F32, float)
+  HG_CASE(HG_U8, uint8_t, HG_F64, double)
+  HG_CASE(HG_F32, float, HG_F32, float)
+  HG_CASE(HG_F32, float, HG_F64, double)
+  HG_CASE(HG_F64, double, HG_F32, float)
+  HG_CASE(HG_F64, double, HG_F64, double)
+#undef HG_CASE
+  set_error("rect2hex_bilinear: unsupported dtypes src=%d dst=%d", src_dtype, dst_dtype);
+  return HG_E_DTYPE;
+}
+
+int hg_hex2rect_nearest(const void* src, void* dst, const double* xs, const double* ys, int64_t planes, int64_t h,
+                        int64_t w, int64_t h1, int64_t w1, int elem_size, hg_stream_t stream) {
+  int rc = check_plane(planes, h, w, h1, w1);
+  if (rc) return rc;
+  if (planes == 0 || h1 == 0 || w1 == 0) return HG_OK;
+  return dispatch_hexsrc_nearest(src, dst, CoordTables{xs, ys}, planes, h, w, h1, w1, elem_size, as_stream(stream));
+}
+
+int hg_hex2rect_linear(const void* src, void* dst, const double* xs, const double* ys, int64_t planes, int64_t h,
+                       int64_t w, int64_t h1, int64_t w1, int src_dtype, int dst_dtype, int math, hg_stream_t stream) {
+  int rc = check_plane(planes, h, w, h1, w1);
+  if (rc) return rc;
+  HG_REQUIRE(math == HG_MATH_EXACT || math == HG_MATH_FAST, HG_E_ARG, "bad math mode %d", math);
+  if (planes == 0 || h1 == 0 || w1 == 0) return HG_OK;
+  CoordTables c{xs, ys};
+  if (math == HG_MATH_EXACT)
+    return dispatch_hexsrc_linear<CoordTables, false>(src, dst, c, planes, h, w, h1, w1, src_dtype, dst_dtype, as_stream(stream));
+  return dispatch_hexsrc_linear<CoordTables, true>(src, dst, c, planes, h, w, h1, w1, src_dtype, dst_dtype, as_stream(stream));
+}
+
+int hg_hexwarp_nearest(const void* src, void* dst, const void* cx, const void* cy, int coord_f32, int64_t planes,
+                       int64_t h, int64_t w, int64_t h1, int64_t w1, int elem_size, hg_stream_t stream) {
+  int rc = check_plane(planes, h, w, h1, w1);
+  if (rc) return rc;
+  if (planes == 0 || h1 == 0 || w1 == 0) return HG_OK;
+  if (coord_f32)
+    return dispatch_hexsrc_nearest(src, dst, CoordPlanes<float>{(const float*)cx, (const float*)cy}, planes, h, w, h1,
+                                   w1, elem_size, as_stream(stream));
+  return dispatch_hexsrc_nearest(src, dst, CoordPlanes<double>{(const double*)cx, (const double*)cy}, planes, h, w, h1,
+                                 w1, elem_size, as_stream(stream));
+}
+
+int hg_hexwarp_linear(const void* src, void* dst, const void* cx, const void* cy, int coord_f32, int64_t planes,
+                      int64_t h, int64_t w, int64_t h1, int64_t w1, int src_dtype, int dst_dtype, hg_stream_t stream) {
+  int rc = check_plane(planes, h, w, h1, w1);
+  if (rc) return rc;
+  if (planes == 0 || h1 == 0 || w1 == 0) return HG_OK;
+  if (coord_f32)
+    return dispatch_hexsrc_linear<CoordPlanes<float>, false>(src, dst, CoordPlanes<float>{(const float*)cx, (const float*)cy},
+                                                             planes, h, w, h1, w1, src_dtype, dst_dtype, as_stream(stream));
+  return dispatch_hexsrc_linear<CoordPlanes<double>, false>(src, dst, CoordPlanes<double>{(const double*)cx, (const double*)cy},
+                                                            planes, h, w, h1, w1, src_dtype, dst_dtype, as_stream(stream));
+}
+
+int hg_hexwarp_affine(const void* src, void* dst, const double* host_hinv, double row0, double col0, int coord_f32,
+                      int interp, int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1, int src_dtype,
+                      int dst_dtype, hg_stream_t stream) {
+  int rc = check_plane(planes, h, w, h1, w1);
+  if (rc) return rc;
+  HG_REQUIRE(host_hinv != nullptr, HG_E_ARG, "host_hinv is NULL");
+  HG_REQUIRE(interp == 0 || interp == 1, HG_E_ARG, "interp must be 0 (nearest) or 1 (linear)");
+  if (planes == 0 || h1 == 0 || w1 == 0) return HG_OK;
+  cudaStream_t st = as_stream(stream);
+  if (coord_f32) {
+    CoordAffine<float> c;
+    for (int k = 0; k < 6; ++k) c.m[k] = host_hinv[k];
+    c.row0 = row0; c.col0 = col0;
+    if (interp == 1) return dispatch_hexsrc_linear<CoordAffine<float>, false>(src, dst, c, planes, h, w, h1, w1, src_dtype, dst_dtype, st);
+    HG_REQUIRE(src_dtype == dst_dtype, HG_E_DTYPE, "nearest keeps the element type");
+    return dispatch_hexsrc_nearest(src, dst, c, planes, h, w, h1, w1, dtype_size(src_dtype), st);
+  }
+  CoordAffine<double> c;
+  for (int k = 0; k < 6; ++k) c.m[k] = host_hinv[k];
+  c.row0 = row0; c.col0 = col0;
+  if (interp == 1) return dispatch_hexsrc_linear<CoordAffine<double>, false>(src, dst, c, planes, h, w, h1, w1, src_dtype, dst_dtype, st);
+  HG_REQUIRE(src_dtype == dst_dtype, HG_E_DTYPE, "nearest keeps the element type");
+  return dispatch_hexsrc_nearest(src, dst, c, planes, h, w, h1, w1, dtype_size(src_dtype), st);
+}
+
+}  // extern "C"

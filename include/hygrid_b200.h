@@ -1,0 +1,202 @@
+/* hygrid_b200.h -- C ABI of libhygrid_b200.so (sm_100a CUDA kernels for the HyGrid hot path).
+ *
+ * The reference (HyGrid, pure Python) has no FFI: the path sits behind plain Python call
+ * signatures.  Every entry point below therefore names the reference
+ * *function* it replaces as `ref:` (file:line under /root/reference/HyGrid/); INTEGRATION.md
+ * shows the ctypes stub a HyGrid maintainer would add at that call site.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all tensor pointers are DEVICE pointers unless the
+ *     parameter is called host_*; tensors are dense, row-major, planes = N*C leading images.
+ *   - the library never allocates, frees or keeps tensor memory; outputs are caller-allocated.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls only
+ *     enqueue work; they do not synchronise.
+ *   - return 0 on success, <0 invalid argument (HG_E_*), >0 a cudaError_t.  hg_last_error()
+ *     returns a thread-local message for the last non-zero return.
+ *   - re-entrant, no global mutable state besides the thread-local error string.
+ */
+#ifndef HYGRID_B200_H_
+#define HYGRID_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HG_VERSION 100 /* 0.1.0 */
+
+typedef void* hg_stream_t;
+
+/* element types */
+enum { HG_U8 = 0, HG_I16 = 1, HG_I32 = 2, HG_I64 = 3, HG_F32 = 4, HG_F64 = 5, HG_BF16 = 6, HG_U16 = 7 };
+/* arithmetic of the interpolating kernels:
+ *   HG_MATH_EXACT  float64, no FMA contraction, the reference's operation order.  With a
+ *                  float64 destination the result is bit-identical to the reference; with a
+ *                  float32 destination it is that value rounded once.
+ *   HG_MATH_FAST   float32 weights and FMAs (|err| <= 1e-5 * max|x|).                          */
+enum { HG_MATH_EXACT = 0, HG_MATH_FAST = 1 };
+/* pooling reductions (ref: HexFrames.py:461-479) */
+enum { HG_POOL_MAX = 0, HG_POOL_MIN = 1, HG_POOL_AVG = 2 };
+/* error codes */
+enum { HG_OK = 0, HG_E_ARG = -1, HG_E_DTYPE = -2, HG_E_SHAPE = -3, HG_E_UNSUPPORTED = -4 };
+
+int hg_version(void);
+const char* hg_last_error(void);
+/* number of kernels launched by this thread since the last hg_reset_launch_count() (bench.py's
+ * gpu_launches claim is read from here, not guessed). */
+int64_t hg_launch_count(void);
+void hg_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Lattice index kernels (integer; bit-exact with the reference)
+ * ---------------------------------------------------------------------------------------- */
+
+/* axial <-> offset column index of the "odd rows shifted right" hex lattice.
+ * ref: geometry_np.py:288-295  j_off = j_ax - trunc((i+1)/2)  (true division, truncation). */
+int hg_axial_to_offset_i32(const int32_t* i, const int32_t* j_ax, int32_t* j_off, int64_t n, hg_stream_t stream);
+int hg_offset_to_axial_i32(const int32_t* i, const int32_t* j_off, int32_t* j_ax, int64_t n, hg_stream_t stream);
+
+/* Row / column tables of rect->hex sampling.  ref: geometry_np.py:440-449.
+ * xs[h1], ys[w1]: the reference's 1-D sample coordinates (host computes them with the very
+ * same linspace call).  Outputs: i_n[h1], j_n[w1] truncated indices; i_f[h1], j_f[w1]
+ * fractions (float64). */
+int hg_rect2hex_index(const double* xs, const double* ys, int64_t h, int64_t w, int64_t h1, int64_t w1,
+                      int32_t* i_n, double* i_f, int32_t* j_n, double* j_f, hg_stream_t stream);
+
+/* Per-sample tables of sampling a hex-lattice image.  ref: geometry_np.py:276-316
+ * (== geometry_torch.py:278-316).  Coordinates are either separable (coords_2d = 0: xs[h1],
+ * ys[w1]) or full planes (coords_2d = 1: xs[h1*w1], ys[h1*w1]); coord_f32 = 1 evaluates the
+ * index arithmetic in float32 like the torch warp (geometry_torch.py:99-118).
+ * Outputs (each h1*w1): i_n, j_n (axial cell), tri (bit0 = up_down_flag i_f > j_f, bits 1..3 =
+ * validity of the three fetched lattice points P1, P2|P3, P4), off[3*h1*w1] linear offsets
+ * i*w + j_off of the three points (-1 where invalid). */
+int hg_hexsrc_index(const void* xs, const void* ys, int coords_2d, int coord_f32,
+                    int64_t h, int64_t w, int64_t h1, int64_t w1,
+                    int32_t* i_n, int32_t* j_n, uint8_t* tri, int32_t* off, hg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Resampling (memory-bound gathers).  src: [planes, h, w] -> dst: [planes, h1, w1]
+ * ---------------------------------------------------------------------------------------- */
+
+/* ref: geometry_np.py:358-519 rect_to_hex_resample(..., 'nearest'): literal 4-way argmin of
+ * geometry_np.py:499-512.  dst has the src element type (elem_size 1, 2, 4 or 8 bytes). */
+int hg_rect2hex_nearest(const void* src, void* dst, const double* xs, const double* ys,
+                        int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1,
+                        int elem_size, hg_stream_t stream);
+/* ref: geometry_np.py:358-519 rect_to_hex_resample(..., 'bilinear') (blend :514-517).
+ * src_dtype in {HG_U8, HG_F32, HG_F64}, dst_dtype in {HG_F32, HG_F64}. */
+int hg_rect2hex_bilinear(const void* src, void* dst, const double* xs, const double* ys,
+                         int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1,
+                         int src_dtype, int dst_dtype, int math, hg_stream_t stream);
+
+/* ref: geometry_torch.py:191-358 hex_to_square_resample / geometry_np.py:191-356
+ * hex_to_rect_resample / geometry_np.py:520-681 hexresize -- they differ only in the 1-D
+ * coordinate tables xs[h1], ys[w1], which the host computes with the reference's own
+ * linspace call (float32 torch.linspace for the torch twin). */
+int hg_hex2rect_nearest(const void* src, void* dst, const double* xs, const double* ys,
+                        int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1,
+                        int elem_size, hg_stream_t stream);
+int hg_hex2rect_linear(const void* src, void* dst, const double* xs, const double* ys,
+                       int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1,
+                       int src_dtype, int dst_dtype, int math, hg_stream_t stream);
+
+/* ref: geometry_torch.py:7-189 image_geometric_transformation_gpu (coord_f32 = 1) /
+ * geometry_np.py:6-189 image_geometric_transformation (coord_f32 = 0).  cx, cy: inverse-mapped
+ * sample coordinate planes [h1*w1] (float32 or float64), shared by all planes. */
+int hg_hexwarp_nearest(const void* src, void* dst, const void* cx, const void* cy, int coord_f32,
+                       int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1,
+                       int elem_size, hg_stream_t stream);
+int hg_hexwarp_linear(const void* src, void* dst, const void* cx, const void* cy, int coord_f32,
+                      int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1,
+                      int src_dtype, int dst_dtype, hg_stream_t stream);
+/* Same warp with the inverse affine map evaluated in-kernel (no coordinate planes in HBM):
+ * sample (a,b) sits at X = row0 + a, Y = col0 + b + 0.5*(a odd); (x,y) = Hinv[0:2,:] * (X,Y,1)
+ * in float64 (products summed left to right), then cast to float32 when coord_f32.
+ * hinv: 6 doubles (HOST pointer, row-major first two rows of inv(H)). */
+int hg_hexwarp_affine(const void* src, void* dst, const double* host_hinv, double row0, double col0,
+                      int coord_f32, int interp, int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1,
+                      int src_dtype, int dst_dtype, hg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Doubled-raster layouts.  ref: HexImage.py:139-170 (encode), :106-111 (decode);
+ * HexFrames.py:417-458 (torch twins).  hex [planes,H,W] <-> type1 [planes,H,2W+1] /
+ * type2 [planes,2H,2W+1]; rows with (i + offset) odd carry the leading zero.
+ * ---------------------------------------------------------------------------------------- */
+int hg_hex_to_type1(const void* hex, void* t1, int64_t planes, int64_t H, int64_t W, int offset,
+                    int src_dtype, int dst_dtype, hg_stream_t stream);
+int hg_hex_to_type2(const void* hex, void* t2, int64_t planes, int64_t H, int64_t W, int offset,
+                    int src_dtype, int dst_dtype, hg_stream_t stream);
+/* rows_step = 1 decodes type1 ([..., 1::2]), 2 decodes type2 ([..., ::2, 1::2]); Wt = raster width */
+int hg_type_to_hex(const void* t, void* hex, int64_t planes, int64_t Ht, int64_t Wt, int rows_step,
+                   int src_dtype, int dst_dtype, hg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Hex pooling.  ref: HexFrames.py:255-341 HexPool2d, :344-401 HexAdaptivePool2d,
+ * :402-414 HexGlobalPool2d, reductions :461-479 (NaN-aware).
+ * The virtual input is x [planes,H,W] framed by `pad` cells of pad_value on every side and then
+ * extended by tail_w columns / tail_h rows of tail_value (ceil_mode, value 0 or NaN).  Window of
+ * out(I,J): rows sh*I + a, cols ((I%2)*shift)/2 + J*sw + b, a < kh, b < kw.
+ * aux [planes,hn,wn] (int8, may be NULL): max/min -> winning window slot a*kw+b; avg -> number
+ * of non-NaN cells.  dtype in {HG_F32, HG_F64, HG_BF16}.
+ * ---------------------------------------------------------------------------------------- */
+int hg_hexpool_fwd(const void* x, void* y, int8_t* aux, int64_t planes, int64_t H, int64_t W,
+                   int64_t hn, int64_t wn, int kh, int kw, int sh, int sw, int shift,
+                   int pad, double pad_value, int tail_h, int tail_w, double tail_value,
+                   int method, int dtype, hg_stream_t stream);
+/* gx [planes,H,W] is fully written (no pre-zeroing needed). */
+int hg_hexpool_bwd(const void* gy, const int8_t* aux, void* gx, int64_t planes, int64_t H, int64_t W,
+                   int64_t hn, int64_t wn, int kh, int kw, int sh, int sw, int shift,
+                   int pad, int method, int dtype, hg_stream_t stream);
+/* x [planes, L] -> y [planes]; aux_idx [planes] int32 (argmax / non-NaN count), may be NULL */
+int hg_hexglobalpool_fwd(const void* x, void* y, int32_t* aux_idx, int64_t planes, int64_t L,
+                         int method, int dtype, hg_stream_t stream);
+int hg_hexglobalpool_bwd(const void* gy, const void* x, const int32_t* aux_idx, void* gx, int64_t planes,
+                         int64_t L, int method, int dtype, hg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Hex convolution.  ref: HexFrames.py:22-185 HexConv2d.forward (closed form in DESIGN.md):
+ *   y[n,co,R,q] = bias[co] + sum_{ci,tap} w[co,ci,0,tap] * D[s*R + a*d, 1 + (R%2)*s + 2*s*q + t*d + 2*d*m]
+ * with D the doubled view of the (virtually) padded input, parity o = (even_odd_offset+pad)%2.
+ * x [N,Cin,H,W], w [Cout,Cin/groups,1,K] (K = 3r^2-3r+1), y [N,Cout,Ho,Wo].  Padding is virtual
+ * (constant pad_value); other padding modes are applied by the caller (pad = 0, parity passed).
+ * io_dtype: element type of x / y / gradients in {HG_F32, HG_BF16}; weights and bias are
+ * float32, accumulation is float32.  algo: 0 = auto, 1 = direct stencil, 2 = tcgen05 implicit GEMM.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct hg_conv_desc {
+  int64_t N, Cin, Cout, H, W, Ho, Wo;
+  int radius, stride, dilation, groups, pad, parity;
+  float pad_value;
+  int x_dtype, y_dtype; /* HG_F32 / HG_BF16 */
+  int algo;
+  int relu;             /* fused epilogue of HexConvModule (conv -> act), 0/1 */
+} hg_conv_desc;
+
+int hg_hexconv_out_shape(int64_t H, int64_t W, int radius, int stride, int dilation, int pad,
+                         int64_t* Ho, int64_t* Wo);
+int hg_hexconv_fwd(const hg_conv_desc* d, const void* x, const float* w, const float* bias, void* y,
+                   hg_stream_t stream);
+/* gx [N,Cin,H,W] fully written.  gy has y_dtype, gx has x_dtype. */
+int hg_hexconv_dgrad(const hg_conv_desc* d, const void* gy, const float* w, void* gx, hg_stream_t stream);
+/* gw [Cout,Cin/groups,1,K] float32 and gbias [Cout] float32 (may be NULL) are ACCUMULATED into
+ * (caller zeroes them), so that per-layer partials can land directly in a flat all-reduce bucket. */
+int hg_hexconv_wgrad(const hg_conv_desc* d, const void* x, const void* gy, float* gw, float* gbias,
+                     hg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-buffer entry points (what a numpy caller binds): pinned-staged, chunked over planes,
+ * H2D / kernel / D2H overlapped on internal streams.  host_src / host_dst are HOST pointers
+ * (pageable or pinned).  device: CUDA device ordinal.  Synchronous (returns when host_dst is
+ * complete).  ref: the numpy-in / numpy-out contract of geometry_np.py:358 and :191.
+ * ---------------------------------------------------------------------------------------- */
+int hg_host_rect2hex(const void* host_src, void* host_dst, const double* host_xs, const double* host_ys,
+                     int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1,
+                     int src_dtype, int dst_dtype, int interp, int math, int device);
+int hg_host_hex2rect(const void* host_src, void* host_dst, const double* host_xs, const double* host_ys,
+                     int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1,
+                     int src_dtype, int dst_dtype, int interp, int math, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYGRID_B200_H_ */
