@@ -1,0 +1,519 @@
+"""Hex-lattice torch layers -- the API of the reference's ``HyGrid/HexFrames.py`` on sm_100a kernels.
+
+Same names, constructor arguments, public attributes, parameter names (``kernel``, ``bias``) and
+error behaviour as the reference (file:line citations are into ``/root/reference/HyGrid/``), but no
+doubled "type1" image, no zero-stuffed dense window and no index tables are ever materialised: every
+forward / backward is one launch of a hand-written kernel from ``libhygrid_b200.so`` reached through
+the C ABI.  CUDA tensors only; there is no CPU path.
+
+Deliberate deviations: ``HexPool2d(stride=None)`` means stride = kernel_size
+(the reference crashes, HexFrames.py:272-278); ``HexAdaptivePool2d`` / ``HexGlobalPool2d`` construct
+(the reference raises NameError on the undefined ``centroid_pooling``, :360/:408) and only
+``method='centroid'`` raises NotImplementedError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+from torch.nn import init
+
+from . import _native as nv
+
+__all__ = ["pad", "HexConv2d", "HexConv2dAdaptivePadding", "HexPool2d", "HexAdaptivePool2d", "HexGlobalPool2d",
+           "heximage_to_type1", "heximage_to_type2", "type1_to_heximage", "max_pooling", "min_pooling",
+           "average_pooling", "hexconv2d", "hexpool2d"]
+
+_PAD_MODES = {"constant": 0, "reflect": 1, "replicate": 2, "circular": 3}
+_POOL = {"max": nv.POOL_MAX, "min": nv.POOL_MIN, "average": nv.POOL_AVG}
+_FLOATS = (torch.float32, torch.float64, torch.bfloat16)
+
+
+def _as4(x: Tensor) -> Tensor:
+    while x.dim() < 4:
+        x = x.unsqueeze(0)
+    return x
+
+
+# ------------------------------------------------------------------------------------------------
+# pad (HexFrames.py:13-21)
+# ------------------------------------------------------------------------------------------------
+class _Pad2dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pl, pr, pt, pb, mode, value):
+        x = nv.require_cuda(x, "input").contiguous()
+        H, W = x.shape[-2:]
+        planes = x.numel() // (H * W)
+        y = torch.empty(x.shape[:-2] + (H + pt + pb, W + pl + pr), dtype=x.dtype, device=x.device)
+        nv.call("hg_pad2d", nv.ptr(x), nv.ptr(y), planes, H, W, pl, pr, pt, pb, mode, float(value),
+                nv.hg_dtype(x.dtype), nv.stream_ptr(x.device))
+        ctx.meta = (pl, pr, pt, pb, mode, H, W, planes)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        pl, pr, pt, pb, mode, H, W, planes = ctx.meta
+        gy = gy.contiguous()
+        gx = torch.empty(gy.shape[:-2] + (H, W), dtype=gy.dtype, device=gy.device)
+        nv.call("hg_pad2d_bwd", nv.ptr(gy), nv.ptr(gx), planes, H, W, pl, pr, pt, pb, mode, nv.hg_dtype(gy.dtype),
+                nv.stream_ptr(gy.device))
+        return gx, None, None, None, None, None, None
+
+
+def _pad4(x: Tensor, pl: int, pr: int, pt: int, pb: int, mode="constant", value=0) -> Tensor:
+    if mode not in _PAD_MODES:
+        raise NotImplementedError(f"Unrecognised padding mode {mode}")
+    if pl == pr == pt == pb == 0:
+        return x
+    return _Pad2dFn.apply(x, int(pl), int(pr), int(pt), int(pb), _PAD_MODES[mode], 0 if value is None else value)
+
+
+def pad(input: Tensor, padding: int = 0, mode="constant", value=0) -> Tensor:
+    """``F.pad(input, (padding,)*4, mode, value)`` (HexFrames.py:13-21)."""
+    return _pad4(input, padding, padding, padding, padding, mode, value)
+
+
+# ------------------------------------------------------------------------------------------------
+# hex convolution (HexFrames.py:22-185)
+# ------------------------------------------------------------------------------------------------
+def _conv_desc(x, Cout, Ho, Wo, radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, relu):
+    N, Cin, H, W = x.shape
+    return nv.ConvDesc(N, Cin, Cout, H, W, Ho, Wo, radius, stride, dilation, groups, pad_, parity, float(pad_value),
+                       nv.hg_dtype(x.dtype), nv.hg_dtype(y_dtype), algo, int(relu))
+
+
+def _conv_out_shape(H, W, radius, stride, dilation, pad_):
+    Ho, Wo = C.c_int64(0), C.c_int64(0)
+    try:
+        nv.call("hg_hexconv_out_shape", H, W, radius, stride, dilation, pad_, C.byref(Ho), C.byref(Wo))
+    except nv.HyGridNativeError as e:
+        raise ValueError(str(e)) from None
+    return Ho.value, Wo.value
+
+
+class _HexConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kernel, bias, meta):
+        radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, relu = meta
+        x = nv.require_cuda(x, "input").contiguous()
+        w = kernel.detach().float().contiguous()
+        b = bias.detach().float().contiguous() if bias is not None else None
+        N, Cin, H, W = x.shape
+        Cout = w.shape[0]
+        Ho, Wo = _conv_out_shape(H, W, radius, stride, dilation, pad_)
+        y = torch.empty((N, Cout, Ho, Wo), dtype=y_dtype, device=x.device)
+        d = _conv_desc(x, Cout, Ho, Wo, radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, relu)
+        nv.call("hg_hexconv_fwd", C.byref(d), nv.ptr(x), nv.ptr(w), nv.ptr(b), nv.ptr(y), nv.stream_ptr(x.device))
+        ctx.save_for_backward(x, w)
+        ctx.meta = meta
+        ctx.has_bias = bias is not None
+        ctx.param_dtypes = (kernel.dtype, bias.dtype if bias is not None else None)
+        ctx.out_shape = (Ho, Wo)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, relu = ctx.meta
+        if relu:
+            raise RuntimeError("the fused ReLU epilogue is inference-only")
+        Ho, Wo = ctx.out_shape
+        gy = gy.to(y_dtype).contiguous()
+        d = _conv_desc(x, w.shape[0], Ho, Wo, radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, 0)
+        st = nv.stream_ptr(x.device)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            nv.call("hg_hexconv_dgrad", C.byref(d), nv.ptr(gy), nv.ptr(w), nv.ptr(gx), st)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            gw = torch.zeros_like(w)
+            gb = torch.zeros(w.shape[0], dtype=torch.float32, device=x.device) if ctx.has_bias else None
+            nv.call("hg_hexconv_wgrad", C.byref(d), nv.ptr(x), nv.ptr(gy), nv.ptr(gw), nv.ptr(gb), st)
+            gw = gw.to(ctx.param_dtypes[0])
+            if gb is not None:
+                gb = gb.to(ctx.param_dtypes[1])
+        return gx, gw, gb, None
+
+
+def hexconv2d(x: Tensor, kernel: Tensor, bias: Optional[Tensor] = None, even_odd_offset=0, radius=2, stride=1, padding=0,
+              dilation=1, groups=1, padding_value=0.0, out_dtype=torch.float32, algo=0, relu=False) -> Tensor:
+    """Functional hex convolution with virtual constant padding (closed form of HexFrames.py:96-169)."""
+    x = _as4(x)
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError(f"hex convolution runs on float32 or bfloat16 activations, got {x.dtype}")
+    parity = (int(even_odd_offset) + int(padding)) % 2
+    meta = (int(radius), int(stride), int(dilation), int(groups), int(padding), parity, float(padding_value or 0),
+            out_dtype, int(algo), bool(relu))
+    return _HexConvFn.apply(x, kernel, bias, meta)
+
+
+class HexConv2d(nn.Module):
+    """Hexagonal-footprint convolution on an offset-stored hex lattice (HexFrames.py:22-185).
+
+    Parameters ``kernel`` ``[out, in/groups, 1, 3r^2-3r+1]`` and ``bias`` ``[out]`` keep the reference's
+    names, shapes and initialisation (:74-95), so ``state_dict``s interchange.  The output is float32
+    (the reference interleaves into a float32 buffer, :157-160); under ``torch.autocast(bfloat16)`` the
+    activations are read as bfloat16 with float32 accumulation."""
+
+    def __init__(self, in_channels, out_channels, even_odd_offset, hexkernel_radius, stride=1,
+                 padding=0, dilation=1, groups=1, bias=True,
+                 padding_mode='constant', padding_value=0):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.even_odd_offset = even_odd_offset
+        self.padded_even_odd_offset = (even_odd_offset + padding) % 2
+        self.hexkernel_radius = hexkernel_radius
+        self.hexkernel_size = 2 * hexkernel_radius - 1
+        self.kernelnum = 3 * hexkernel_radius ** 2 - 3 * hexkernel_radius + 1
+        self.stride = stride
+        self.sh = stride
+        self.sw = stride * 2
+        self.out_even_odd_offset = 0
+        self.pad = padding
+        self.groups = groups
+        self.b = bias
+        self.dilation = dilation
+        self.padding_mode = padding_mode
+        self.padding_value = padding_value
+        if in_channels % groups != 0:
+            raise ValueError('in_channels must be divisible by groups')
+        if out_channels % groups != 0:
+            raise ValueError('out_channels must be divisible by groups')
+        self.kernel = nn.Parameter(torch.empty([out_channels, in_channels // groups, 1, self.kernelnum], dtype=torch.float))
+        if self.b == True:  # noqa: E712  (the reference's own test)
+            self.bias = nn.Parameter(torch.empty([out_channels, ]))
+        else:
+            self.register_parameter('bias', None)
+        self.k_w = 2 * self.dilation * (2 * self.hexkernel_radius - 2) + 1
+        self.k_h = (self.hexkernel_size - 1) * self.dilation + 1
+        self.algo = 0            # 0 auto, 1 direct stencil, 2 tcgen05 implicit GEMM
+        self.out_dtype = torch.float32
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        init.kaiming_uniform_(self.kernel, a=math.sqrt(5))
+        if self.bias is not None:
+            fan_in, _ = init._calculate_fan_in_and_fan_out(self.kernel)
+            if fan_in != 0:
+                bound = 1 / math.sqrt(fan_in)
+                init.uniform_(self.bias, -bound, bound)
+
+    def _activation(self, input: Tensor) -> Tensor:
+        if torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16:
+            return input.to(torch.bfloat16)
+        if self.kernel.dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError(f"HexConv2d parameters must be float32 (or bfloat16), got {self.kernel.dtype}")
+        return input.to(self.kernel.dtype)
+
+    def forward(self, input: Tensor, relu: bool = False) -> Tensor:
+        input = _as4(self._activation(input))
+        pad_, parity = self.pad, self.padded_even_odd_offset
+        if self.pad and self.padding_mode != 'constant':
+            input = pad(input, self.pad, self.padding_mode, self.padding_value)
+            pad_ = 0
+        meta = (self.hexkernel_radius, self.stride, self.dilation, self.groups, pad_, parity,
+                float(self.padding_value or 0), self.out_dtype, self.algo, bool(relu))
+        return _HexConvFn.apply(input, self.kernel, self.bias, meta)
+
+    def extra_repr(self):
+        s = ('{in_channels}, {out_channels}, kernel_radius={hexkernel_radius}'
+             ', stride={stride}')
+        if self.pad != (0,):
+            s += ', padding={pad}'
+        if self.dilation != (1,):
+            s += ', dilation={dilation}'
+        if self.groups != 1:
+            s += ', groups={groups}'
+        if self.bias is None:
+            s += ', bias=False'
+        if self.padding_mode != 'zeros':
+            s += ', padding_mode={padding_mode}'
+        return s.format(**self.__dict__)
+
+
+class HexConv2dAdaptivePadding(HexConv2d):
+    """TF-"same" variant (HexFrames.py:187-253): ignores ``padding`` and pads so that the filter covers
+    the whole input.  Like the reference, the parity flip caused by the top pad is not compensated."""
+
+    def __init__(self, in_channels: int, out_channels: int, even_odd_offset: int, hexkernel_radius: int,
+                 stride: int = 1, padding: int = 0, dilation: int = 1, groups: int = 1, bias: bool = True):
+        super().__init__(in_channels, out_channels, even_odd_offset=even_odd_offset,
+                         hexkernel_radius=hexkernel_radius, stride=stride, padding=0, dilation=dilation,
+                         groups=groups, bias=bias)
+
+    def __repr__(self):
+        return (f"HexConv2dAdaptivePadding({self.in_channels}, {self.out_channels}, kernel_radius={self.hexkernel_radius}, "
+                f"stride={self.sh}, padding={self.pad}, dilation={self.dilation}, groups={self.groups}, bias={self.b})")
+
+    def forward(self, input: Tensor, relu: bool = False) -> Tensor:
+        input = pad(input, self.pad, self.padding_mode, self.padding_value)
+        self.pad = 0
+        img_h, img_w = input.size()[-2:]
+        kernel_size = self.hexkernel_radius * 2 - 1
+        stride = self.stride
+        output_h = math.ceil(img_h / stride)
+        output_w = math.ceil(img_w / stride)
+        pad_h = max((output_h - 1) * self.stride + (kernel_size - 1) * self.dilation + 1 - img_h, 0)
+        pad_w = max(output_w * self.stride + (kernel_size - 1) * self.dilation + 1 - img_w, 0)
+        input = _as4(self._activation(input))
+        if pad_h > 0 or pad_w > 0:
+            input = _pad4(input, pad_w // 2, pad_w - pad_w // 2, pad_h // 2, pad_h - pad_h // 2)
+        return super().forward(input, relu)
+
+
+# ------------------------------------------------------------------------------------------------
+# pooling (HexFrames.py:255-414, reductions :461-479)
+# ------------------------------------------------------------------------------------------------
+class _HexPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, method, geom):
+        kh, kw, sh, sw, shift, pad_, pad_value, tail_h, tail_w, tail_value, hn, wn = geom
+        x = nv.require_cuda(x, "input").contiguous()
+        B, Cc, H, W = x.shape
+        planes = B * Cc
+        y = torch.empty((B, Cc, hn, wn), dtype=x.dtype, device=x.device)
+        need_aux = ctx.needs_input_grad[0]
+        aux_bytes = 1 if kh * kw <= 127 else 4
+        aux = (torch.empty((B, Cc, hn, wn), dtype=torch.int8 if aux_bytes == 1 else torch.int32, device=x.device)
+               if need_aux else None)
+        try:
+            nv.call("hg_hexpool_fwd", nv.ptr(x), nv.ptr(y), nv.ptr(aux), aux_bytes, planes, H, W, hn, wn, kh, kw, sh, sw,
+                    shift, pad_, float(pad_value), tail_h, tail_w, float(tail_value), method, nv.hg_dtype(x.dtype),
+                    nv.stream_ptr(x.device))
+        except nv.HyGridNativeError as e:
+            if "leaves the image" in str(e):
+                raise IndexError(str(e)) from None
+            raise
+        ctx.geom, ctx.method, ctx.aux_bytes, ctx.in_hw = geom, method, aux_bytes, (H, W)
+        if need_aux:
+            ctx.save_for_backward(aux, x if method == nv.POOL_AVG else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        aux, x = ctx.saved_tensors
+        kh, kw, sh, sw, shift, pad_, _, _, _, _, hn, wn = ctx.geom
+        gy = gy.contiguous()
+        B, Cc = gy.shape[:2]
+        H, W = ctx.in_hw
+        gx = torch.empty((B, Cc, H, W), dtype=gy.dtype, device=gy.device)
+        nv.call("hg_hexpool_bwd", nv.ptr(gy), nv.ptr(aux), ctx.aux_bytes, nv.ptr(x), nv.ptr(gx), B * Cc, H, W, hn, wn,
+                kh, kw, sh, sw, shift, pad_, ctx.method, nv.hg_dtype(gy.dtype), nv.stream_ptr(gy.device))
+        return gx, None, None
+
+
+def _pool_apply(x, method, geom):
+    x = _as4(x)
+    if x.dtype not in _FLOATS:
+        raise TypeError(f"hex pooling runs on float32 / float64 / bfloat16 tensors, got {x.dtype}")
+    return _HexPoolFn.apply(x, method, geom)
+
+
+def hexpool2d(x: Tensor, method: str, kh: int, kw: int, sh: int, sw: int, shift: int, padding=0, padding_value=0.0,
+              tail_h=0, tail_w=0, tail_value=0.0) -> Tensor:
+    """Windows ``rows sh*I + a, cols ((I%2)*shift)//2 + J*sw + b`` over the virtually padded input."""
+    x = _as4(x)
+    H, W = x.shape[-2:]
+    h, w = H + 2 * padding + tail_h, W + 2 * padding + tail_w
+    hn = (h - kh) // sh + 1
+    wn = (w - sw // 2) // sw
+    geom = (kh, kw, sh, sw, shift, padding, padding_value, tail_h, tail_w, tail_value, max(hn, 0), max(wn, 0))
+    return _pool_apply(x, _POOL[method], geom)
+
+
+def centroid_pooling(input):
+    raise NotImplementedError("'centroid' pooling is referenced but never defined in the reference "
+                              "(HexFrames.py:360, :408)")
+
+
+class HexPool2d(nn.Module):
+    """Hex pooling (HexFrames.py:255-341): odd output rows start half a stride to the right;
+    ``even_odd_offset`` is stored but, like in the reference, does not enter the window arithmetic."""
+
+    def __init__(self, method, kernel_size=2, stride=None, padding=0, even_odd_offset=0,
+                 padding_mode='constant', padding_value=0, ceil_mode: bool = False,
+                 count_include_pad: bool = True, divisor_override: Optional[int] = None):
+        super().__init__()
+        self.out_offset = 0
+        self.offset = (even_odd_offset + padding) % 2
+        self.PoolingMethods = {'max': max_pooling, 'min': min_pooling, 'average': average_pooling}
+        self.method = self.PoolingMethods[method]
+        self._method_name = method
+        if isinstance(kernel_size, int):
+            kernel_size = [kernel_size, kernel_size]
+        self.kernel_size = kernel_size
+        self.kh, self.kw = kernel_size
+        if stride is None:          # deviation: the reference overwrites this with None and crashes
+            stride = list(kernel_size)
+        if isinstance(stride, int):
+            stride = [stride, stride]
+        self.stride = stride
+        self.sh, self.sw = self.stride
+        self.padding = padding
+        self.padding_mode = padding_mode
+        self.padding_value = padding_value
+        self.ceil_mode = ceil_mode
+        self.count_include_pad = count_include_pad
+
+    def forward(self, input):
+        input = _as4(input)
+        pad_ = self.padding
+        if pad_ and self.padding_mode != 'constant':
+            input = pad(input, pad_, self.padding_mode, self.padding_value)
+            pad_ = 0
+        H, W = input.shape[-2:]
+        h, w = H + 2 * pad_, W + 2 * pad_
+        self.hn = h // self.sh
+        self.wn = (w - self.sw // 2 - self.sw) // self.sw + 1
+        tail_h = tail_w = 0
+        tail_value = 0.0
+        if self.ceil_mode:
+            ph = (self.kh - h + self.hn * self.sh) % self.kh
+            pw = (self.kw - w + (self.wn * self.sw + self.sw // 2)) % self.kw
+            # literal argument order of HexFrames.py:297-298: F.pad(input, (0, ph, 0, pw)) pads ph COLUMNS and pw ROWS
+            tail_w, tail_h = ph, pw
+            tail_value = 0.0 if self.count_include_pad else float('nan')
+        h, w = h + tail_h, w + tail_w
+        self.hn = (h - self.kh) // self.sh + 1
+        self.wn = (w - self.sw // 2) // self.sw
+        geom = (self.kh, self.kw, self.sh, self.sw, self.sw, pad_, float(self.padding_value or 0), tail_h, tail_w,
+                tail_value, max(self.hn, 0), max(self.wn, 0))
+        return _pool_apply(input, _POOL[self._method_name], geom)
+
+    def extra_repr(self) -> str:
+        return 'kernel_size={}, stride={}, padding={}'.format(self.kernel_size, self.stride, self.padding)
+
+
+class HexAdaptivePool2d(nn.Module):
+    """HexFrames.py:344-401: ``outsize`` must be an int; windows of ``int(h/n) x int(w/(n+.5))``."""
+
+    def __init__(self, outsize, method, padding=0, padding_mode='constant', padding_value=0):
+        super().__init__()
+        if isinstance(outsize, int):
+            outsize = [outsize, outsize]
+        else:
+            raise Exception('outsize = 整数 s 或者列表[h, w]，其它的不行')
+        self.hn, self.wn = outsize
+        self.PoolingMethods = {'max': max_pooling, 'min': min_pooling, 'average': average_pooling,
+                               'centroid': centroid_pooling}
+        self.method = self.PoolingMethods[method]
+        self._method_name = method
+
+    def forward(self, input):
+        if self._method_name == 'centroid':
+            centroid_pooling(input)
+        input = _as4(input)
+        h, w = input.shape[-2:]
+        grid_h = int(h / self.hn)
+        grid_w = int(w / (self.wn + 0.5)) if grid_h > 1 else int(w / self.wn)
+        if grid_h < 1 or grid_w < 1:
+            raise IndexError("adaptive pool window is empty")
+        geom = (grid_h, grid_w, grid_h, grid_w, grid_w, 0, 0.0, 0, 0, 0.0, self.hn, self.wn)
+        return _pool_apply(input, _POOL[self._method_name], geom)
+
+
+class _ReduceLastFn(torch.autograd.Function):
+    """NaN-aware max / min / mean over the last dimension (HexFrames.py:461-479)."""
+
+    @staticmethod
+    def forward(ctx, x, method):
+        x = nv.require_cuda(x, "input").contiguous()
+        if x.dtype not in _FLOATS:
+            raise TypeError(f"hex pooling runs on float32 / float64 / bfloat16 tensors, got {x.dtype}")
+        L = x.shape[-1]
+        planes = x.numel() // L if L else 0
+        y = torch.empty(x.shape[:-1], dtype=x.dtype, device=x.device)
+        aux = torch.empty(x.shape[:-1], dtype=torch.int32, device=x.device)
+        nv.call("hg_hexglobalpool_fwd", nv.ptr(x), nv.ptr(y), nv.ptr(aux), planes, L, method, nv.hg_dtype(x.dtype),
+                nv.stream_ptr(x.device))
+        ctx.save_for_backward(x, aux)
+        ctx.method = method
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, aux = ctx.saved_tensors
+        gy = gy.contiguous()
+        L = x.shape[-1]
+        gx = torch.empty_like(x)
+        nv.call("hg_hexglobalpool_bwd", nv.ptr(gy), nv.ptr(x), nv.ptr(aux), nv.ptr(gx), x.numel() // L, L, ctx.method,
+                nv.hg_dtype(x.dtype), nv.stream_ptr(x.device))
+        return gx, None
+
+
+def max_pooling(input):
+    return _ReduceLastFn.apply(input, nv.POOL_MAX)
+
+
+def min_pooling(input):
+    return _ReduceLastFn.apply(input, nv.POOL_MIN)
+
+
+def average_pooling(input):
+    return _ReduceLastFn.apply(input, nv.POOL_AVG)
+
+
+class HexGlobalPool2d(nn.Module):
+    """HexFrames.py:402-414: reduce over H*W, returns ``(B, C)`` (no trailing 1x1)."""
+
+    def __init__(self, method):
+        super().__init__()
+        self.PoolingMethods = {'max': max_pooling, 'min': min_pooling, 'average': average_pooling,
+                               'centroid': centroid_pooling}
+        self.method = self.PoolingMethods[method]
+
+    def forward(self, input):
+        input = _as4(input)
+        unfolded = input.reshape(input.size(0), input.size(1), input.size(2) * input.size(3))
+        return self.method(unfolded)
+
+
+# ------------------------------------------------------------------------------------------------
+# format conversion (HexFrames.py:417-458)
+# ------------------------------------------------------------------------------------------------
+class _ToTypeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, offset, rows_mul):
+        x = nv.require_cuda(x, "input").contiguous()
+        B, Cc, H, W = x.shape
+        y = torch.empty((B, Cc, rows_mul * H, 2 * W + 1), dtype=torch.float32, device=x.device)
+        nv.call("hg_hex_to_type1" if rows_mul == 1 else "hg_hex_to_type2", nv.ptr(x), nv.ptr(y), B * Cc, H, W, offset % 2,
+                nv.hg_dtype(x.dtype), nv.F32, nv.stream_ptr(x.device))
+        ctx.meta = (offset % 2, rows_mul, x.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        # every cell was written 2 (type1) or 4 (type2) times: the gradient is the sum of its copies.
+        # Rarely needed (the converters sit outside the conv path here), so composed from strided views.
+        offset, rows_mul, dtype = ctx.meta
+        g = gy if rows_mul == 1 else gy[:, :, 0::2] + gy[:, :, 1::2]
+        H = g.shape[2]
+        W = (g.shape[3] - 1) // 2
+        gx = torch.empty(g.shape[:2] + (H, W), dtype=g.dtype, device=g.device)
+        for par in (0, 1):
+            s = (par + offset) % 2
+            rows = g[:, :, par::2]
+            gx[:, :, par::2] = rows[..., s:s + 2 * W:2] + rows[..., s + 1:s + 1 + 2 * W:2]
+        return gx.to(dtype), None, None
+
+
+def heximage_to_type1(input: Tensor, even_odd_offset) -> Tensor:
+    """(B,C,H,W) -> (B,C,H,2W+1) float32 doubled raster (HexFrames.py:417-445)."""
+    return _ToTypeFn.apply(_as4(input), int(even_odd_offset), 1)
+
+
+def heximage_to_type2(input: Tensor, even_odd_offset) -> Tensor:
+    """type1 with every row repeated (HexFrames.py:446-449)."""
+    return _ToTypeFn.apply(_as4(input), int(even_odd_offset), 2)
+
+
+def type1_to_heximage(input: Tensor, even_odd_offset: int):
+    """``input[:, :, :, 1::2]`` (HexFrames.py:450-458): a strided view, exactly like the reference."""
+    out = input[:, :, :, 1::2]
+    return out, even_odd_offset

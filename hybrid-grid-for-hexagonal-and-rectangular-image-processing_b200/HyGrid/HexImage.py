@@ -1,0 +1,174 @@
+"""``HyGrid.HexImage.HEXIMAGE`` (/root/reference/HyGrid/HexImage.py:43-276): hex image container.
+The doubled-raster encoders ``GenerateType1Image`` / ``GenerateType2Image`` (per-row Python loops of
+``np.insert`` / ``np.append`` in the reference, :139-170) run as one pack kernel; the type1 / type2 decode of
+the constructor is the reference's own strided view.  Saving rasters and the OpenGL viewer are outside the
+hot path (lazy, optional back-ends)."""
+from __future__ import annotations
+
+import inspect
+import os
+import pickle
+import warnings
+
+import numpy as np
+import torch
+
+from . import functional as Fn
+from .Image import IMAGE, _need
+from ._hostapi import device_index
+
+__all__ = ["HEXIMAGE"]
+
+
+class HEXIMAGE(IMAGE):
+    def __init__(self, pathname=None, heximagetype=None, data=None, geotrans=None, proj=None, even_odd_offset=False,
+                 backend='gdal'):
+        if pathname is None and data is None:
+            raise ValueError("pathname and data can not be None at the same time")
+        if pathname is not None and data is not None:
+            raise ValueError("pathname and data can not be Given at the same time")
+        if pathname is not None:
+            file_name, file_extension = os.path.splitext(pathname)
+            if file_extension == ".heximg":
+                if not os.path.exists(pathname):
+                    raise OSError("path dosen't exist.")
+                self.path = self.datapath = pathname
+                with open(pathname, "rb") as f:
+                    self.Heximagedataset = pickle.load(f)
+                self.filetype = 2
+                self.height = self.Heximagedataset['height']
+                self.width = self.Heximagedataset['width']
+                self.bands = self.Heximagedataset['bands']
+                self.geotrans = self.Heximagedataset['geotransform']
+                self.proj = self.Heximagedataset['projection']
+                even_odd_offset = self.Heximagedataset['offset']
+                self.HexagonImage = self.Heximagedataset['HexMatrix']
+                if self.HexagonImage.ndim < 3:
+                    self.HexagonImage = np.broadcast_to(self.HexagonImage, (3, self.height, self.width))
+                self.backend = backend
+                self.heximagetype = heximagetype
+            else:
+                super().__init__(pathname, backend=backend)
+                self.heximagetype = heximagetype
+                if heximagetype == None:  # noqa: E711
+                    self.HexagonImage = self.ConvertToHexagon()
+                    if self.HexagonImage.ndim == 2:
+                        self.HexagonImage = self.HexagonImage[None]
+                    self.bands, self.height, self.width = self.HexagonImage.shape[0:3]
+                elif heximagetype == 1:
+                    tmp = self.LoadImageArray()
+                    self.width = (self.width - 1) // 2
+                    self.HexagonImage = np.zeros([self.bands, self.height, self.width])
+                    self.HexagonImage[:, :, :] = tmp[:, :, 1::2]
+                elif heximagetype == 2:
+                    tmp = self.LoadImageArray()
+                    if (self.width & 1) == 0:
+                        zeros = np.zeros((self.bands, self.height, 1))
+                        tmp = np.append(tmp, zeros, axis=2)
+                        self.width += 1
+                    self.height = self.height // 2
+                    self.width = (self.width - 1) // 2
+                    self.HexagonImage = np.zeros([self.bands, self.height, self.width])
+                    self.HexagonImage[:, :, :] = tmp[:, ::2, 1::2] if tmp.ndim == 3 else tmp[::2, 1::2]
+                else:
+                    raise Exception("不支持的文件类型\n要么输入的是普通图像文件：None\n要么输入的是六边形图像通用格式：1\n"
+                                    "要么输入后缀为‘.heximg'的六边形图像专用文件格式：2")
+        elif data is not None:
+            if data.ndim == 2:
+                data = np.broadcast_to(data, (1, data.shape[0], data.shape[1]))
+            if heximagetype == None:  # noqa: E711
+                self.HexagonImage = data
+            elif heximagetype == 1:
+                self.HexagonImage = data[:, :, 1:-1:2]
+            elif heximagetype == 2:
+                self.HexagonImage = data[:, ::2, 1:-1:2]
+            self.heximagetype = heximagetype
+            self.bands = self.HexagonImage.shape[0]
+            self.height = self.HexagonImage.shape[1]
+            self.width = self.HexagonImage.shape[2]
+            self.geotrans = geotrans
+            if self.geotrans == None:  # noqa: E711
+                self.geotrans = (0, 1, 0, 0, 0, 1)
+            self.proj = proj
+            self.path = inspect.signature(self.__init__).parameters['data'].name
+            self.backend = backend
+        self.even_odd_offset = int(even_odd_offset)
+        self.shape = (self.bands, self.height, self.width)
+
+    def size(self, index):
+        return self.HexagonImage.shape[index]
+
+    def build_Heximagedataset(self):
+        self.Heximagedataset = {}
+        self.Heximagedataset['height'] = self.height
+        self.Heximagedataset['width'] = self.width
+        self.Heximagedataset['bands'] = self.bands
+        self.Heximagedataset['geotransform'] = self.geotrans
+        self.Heximagedataset['projection'] = self.proj
+        self.Heximagedataset['offset'] = self.even_odd_offset
+        self.Heximagedataset['HexMatrix'] = self.HexagonImage
+
+    def _pack(self, rows_mul):
+        hexm = np.ascontiguousarray(self.HexagonImage)
+        if hexm.dtype not in (np.uint8, np.int16, np.uint16, np.int32, np.int64, np.float32, np.float64):
+            hexm = hexm.astype(np.float64)
+        if hexm.dtype == np.uint16:          # torch has no device uint16 arithmetic: same bits as int16 would
+            hexm = hexm.astype(np.int32)     # change sign; widen instead (exact)
+        x = torch.from_numpy(hexm).to(torch.device("cuda", device_index()))
+        fn = Fn.hex_to_type1 if rows_mul == 1 else Fn.hex_to_type2
+        return fn(x, self.even_odd_offset, out_dtype=torch.float64).cpu().numpy()
+
+    def GenerateType1Image(self):
+        """HexImage.py:139-153 -> (C x H x (2W+1) float64, geotrans with [5] doubled)."""
+        Heximg_type1 = self._pack(1)
+        geotrans_type1 = (self.geotrans[0], self.geotrans[1], self.geotrans[2],
+                          self.geotrans[3], self.geotrans[4], self.geotrans[5] * 2,)
+        return Heximg_type1, geotrans_type1
+
+    def GenerateType2Image(self):
+        """HexImage.py:154-170 -> (C x 2H x (2W+1) float64, geotrans)."""
+        Heximg_type2 = self._pack(2)
+        geotrans_type2 = (self.geotrans[0], self.geotrans[1], self.geotrans[2],
+                          self.geotrans[3], self.geotrans[4], self.geotrans[5],)
+        return Heximg_type2, geotrans_type2
+
+    def SaveHexImage(self, pathname, imagetype=1, filetype=1):
+        """HexImage.py:171-218: '.heximg' pickles are written here; raster formats need an I/O back-end."""
+        file_name, file_extension = os.path.splitext(pathname)
+        if file_extension == ".heximg":
+            filetype = 2
+        if file_extension in (".tif", ".TIF", ".tiff", ".TIFF", ".png", "bmp"):
+            self.filetype = 1
+        if file_extension in ("JPG", ".jpg", "JPEG", "jpeg"):
+            warnings.warn("jpg and jpeg are lossy compression formats, switching to png")
+            file_extension = ".png"
+        pathname = file_name + file_extension
+        if filetype == 1:
+            tmp, geotrans_out = self.GenerateType1Image() if imagetype == 1 else self.GenerateType2Image()
+            if 'int16' in self.HexagonImage.dtype.name:
+                tmp = tmp.astype(np.uint16)
+            else:
+                tmp = tmp.astype(np.uint8)
+            if self.backend == 'gdal':
+                gdal = _need("osgeo.gdal")
+                datatype = gdal.GDT_UInt16 if tmp.dtype == np.uint16 else gdal.GDT_Byte
+                driver = gdal.GetDriverByName("GTiff")
+                self.Hex_dataset = driver.Create(pathname, tmp.shape[2], tmp.shape[1], tmp.shape[0], datatype,
+                                                 options=["TILED=YES", "COMPRESS=LZW"])
+                self.Hex_dataset.SetGeoTransform(geotrans_out)
+                if self.proj != None:  # noqa: E711
+                    self.Hex_dataset.SetProjection(self.proj)
+                for i in range(tmp.shape[0]):
+                    self.Hex_dataset.GetRasterBand(i + 1).WriteArray(tmp[i])
+                self.Hex_dataset.FlushCache()
+            elif self.backend == 'mmcv':
+                _need("mmcv").imwrite(tmp[::-1, ...].transpose(1, 2, 0), pathname)
+            elif self.backend == 'cv2':
+                _need("cv2").imwrite(pathname, tmp[::-1, ...].transpose(1, 2, 0))
+        else:
+            with open(pathname, "wb") as f:
+                self.build_Heximagedataset()
+                pickle.dump(self.Heximagedataset, f)
+
+    def Hex_imshow(self):
+        raise NotImplementedError("the OpenGL hex-mosaic viewer (HexPixelArt) is outside the B200 hot path")

@@ -54,8 +54,10 @@ _SIGS = {
     "hg_hex_to_type1": [_p, _p, _l, _l, _l, _i, _i, _i, _p],
     "hg_hex_to_type2": [_p, _p, _l, _l, _l, _i, _i, _i, _p],
     "hg_type_to_hex": [_p, _p, _l, _l, _l, _i, _i, _i, _p],
-    "hg_hexpool_fwd": [_p, _p, _p, _l, _l, _l, _l, _l, _i, _i, _i, _i, _i, _i, _d, _i, _i, _d, _i, _i, _p],
-    "hg_hexpool_bwd": [_p, _p, _p, _l, _l, _l, _l, _l, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "hg_pad2d": [_p, _p, _l, _l, _l, _i, _i, _i, _i, _i, _d, _i, _p],
+    "hg_pad2d_bwd": [_p, _p, _l, _l, _l, _i, _i, _i, _i, _i, _i, _p],
+    "hg_hexpool_fwd": [_p, _p, _p, _i, _l, _l, _l, _l, _l, _i, _i, _i, _i, _i, _i, _d, _i, _i, _d, _i, _i, _p],
+    "hg_hexpool_bwd": [_p, _p, _i, _p, _p, _l, _l, _l, _l, _l, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "hg_hexglobalpool_fwd": [_p, _p, _p, _l, _l, _i, _i, _p],
     "hg_hexglobalpool_bwd": [_p, _p, _p, _p, _l, _l, _i, _i, _p],
     "hg_hexconv_out_shape": [_l, _l, _i, _i, _i, _i, C.POINTER(_l), C.POINTER(_l)],
@@ -82,6 +84,7 @@ def lib():
         L.hg_last_error.restype = C.c_char_p
         L.hg_launch_count.restype = C.c_int64
         L.hg_reset_launch_count.restype = None
+        L.hg_host_release.restype = None
         for name, sig in _SIGS.items():
             fn = getattr(L, name, None)
             if fn is None:
@@ -123,8 +126,8 @@ def torch_dtype(code: int) -> torch.dtype:
     return _HG2TORCH[code]
 
 
-def ptr(t: torch.Tensor):
-    return C.c_void_p(t.data_ptr())
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
 def stream_ptr(device=None):

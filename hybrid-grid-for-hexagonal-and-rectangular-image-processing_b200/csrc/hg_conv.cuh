@@ -1,0 +1,63 @@
+// hg_conv.cuh -- geometry shared by the hex-convolution kernels (direct stencil and tcgen05 paths).
+//
+// ref: HexFrames.py:96-169 HexConv2d.forward.  The reference materialises a 2x-wide "doubled" image and
+// runs two dense strided F.conv2d with a zero-stuffed (2r-1)x(4r-3) window; in *offset* coordinates the
+// same result is a sparse correlation whose tap columns depend only on the parity of the output row:
+//
+//   y[n,co,R,q] = bias[co] + sum_{ci,k} w[co,ci,0,k] * P[n, ci, s*R + ro[k], s*q + co[R&1][k]]
+//
+// with P the input framed by `pad` cells of pad_value (and literal zero one column beyond the frame,
+// which is the doubled image's extra zero column), and for tap k = (a, t, m) in the reference's
+// running-sum order (HexFrames.py:112-118):
+//   ro[k]      = a*d
+//   co[par][k] = floor((1 + par*s + t*d + 2*d*m - s_i) / 2),  s_i = ((s&1)*par + a*d + o) & 1,
+//   o = (even_odd_offset + pad) & 1  ("parity" in hg_conv_desc).
+#pragma once
+#include "hg_common.cuh"
+
+namespace hg {
+
+constexpr int kMaxTaps = 64;  // radius <= 5 (61 taps)
+
+struct ConvTaps {
+  int K;
+  int ro[kMaxTaps];      // row offset in the padded frame
+  int co[2][kMaxTaps];   // column offset in the padded frame, per output-row parity
+};
+
+struct ConvGeom {
+  int N, Cin, Cout, H, W, Ho, Wo;
+  int s, d, groups, pad, cin_g, cout_g;
+  float pad_value;
+  int relu;
+};
+
+static inline int conv_num_taps(int r) { return 3 * r * r - 3 * r + 1; }
+
+static inline void conv_make_taps(int radius, int s, int d, int parity, ConvTaps& T) {
+  int k = 0;
+  for (int a = 0; a < 2 * radius - 1; ++a) {
+    const int t = a - radius + 1 < 0 ? radius - 1 - a : a - radius + 1;
+    const int ln = 2 * radius - 1 - t;
+    for (int m = 0; m < ln; ++m, ++k) {
+      T.ro[k] = a * d;
+      for (int par = 0; par < 2; ++par) {
+        const int si = ((s & 1) * par + a * d + parity) & 1;
+        const int e = 1 + par * s + t * d + 2 * d * m - si;  // >= 0
+        T.co[par][k] = e >> 1;
+      }
+    }
+  }
+  T.K = k;
+}
+
+// rows / cols of the interleaved output (HexFrames.py:127-162; k_h, k_w from :82-83)
+static inline void conv_out_shape(int64_t Hp, int64_t Wp, int radius, int s, int d, int64_t& rows_e, int64_t& rows_o, int64_t& cols) {
+  const int64_t k_h = (int64_t)(2 * radius - 2) * d + 1, k_w = (int64_t)2 * d * (2 * radius - 2) + 1;
+  const int64_t wt = 2 * Wp - s;
+  cols = wt >= k_w ? (wt - k_w) / (2 * s) + 1 : 0;
+  rows_e = Hp >= k_h ? (Hp - k_h) / (2 * s) + 1 : 0;
+  rows_o = Hp - s >= k_h ? (Hp - s - k_h) / (2 * s) + 1 : 0;
+}
+
+}  // namespace hg

@@ -1,0 +1,347 @@
+// hg_pool.cu -- hex-lattice pooling, forward and backward (sm_100a).  HBM-bound.
+//
+//   ref: HexFrames.py:255-341 HexPool2d, :344-401 HexAdaptivePool2d, :402-414 HexGlobalPool2d,
+//        reductions :461-479 (max: NaN -> -inf, min: NaN -> +inf, average: mean of the non-NaN cells,
+//        all-NaN -> NaN).
+// The reference builds int64 index tables on the CPU and gathers a (hn*wn*kh*kw, B, C) tensor; here the
+// window of out(I, J) -- rows sh*I + a, cols ((I%2)*shift)/2 + J*sw + b -- is pure index arithmetic and
+// padding / ceil-mode tails are virtual (never materialised).
+// Forward: one thread per output cell, lanes along J (a warp reads one contiguous span per window row).
+// Backward: one thread per *input* cell gathers from the (few) windows covering it -- deterministic, no
+// atomics, gx written exactly once.
+#include "hg_common.cuh"
+#include <math_constants.h>
+
+namespace hg {
+
+constexpr int kPoolThreads = 256;
+
+struct PoolGeom {
+  int H, W, hn, wn, kh, kw, sh, sw, shift, pad, tail_h, tail_w;
+};
+
+template <typename T> struct Acc { using type = float; };
+template <> struct Acc<double> { using type = double; };
+
+template <typename T> __device__ __forceinline__ typename Acc<T>::type ld_acc(const T* p) { return (typename Acc<T>::type)__ldg(p); }
+template <> __device__ __forceinline__ float ld_acc<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T, typename A> __device__ __forceinline__ T st_acc(A v) { return (T)v; }
+template <> __device__ __forceinline__ __nv_bfloat16 st_acc<__nv_bfloat16, float>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename T, int METHOD, typename AUX>
+__global__ void __launch_bounds__(kPoolThreads)
+hexpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, AUX* __restrict__ aux, int64_t total, PoolGeom g,
+                   typename Acc<T>::type pad_value, typename Acc<T>::type tail_value) {
+  using A = typename Acc<T>::type;
+  const int64_t t = (int64_t)blockIdx.x * kPoolThreads + threadIdx.x;
+  if (t >= total) return;
+  const int J = (int)(t % g.wn);
+  const int64_t r = t / g.wn;
+  const int I = (int)(r % g.hn);
+  const int64_t plane = r / g.hn;
+  const T* __restrict__ xp = x + plane * (int64_t)g.H * g.W;
+  const int r0 = g.sh * I, c0 = ((I & 1) * g.shift) / 2 + J * g.sw;
+  const int Hp = g.H + 2 * g.pad, Wp = g.W + 2 * g.pad;
+  const A inf = (A)CUDART_INF;
+  A best = METHOD == HG_POOL_MAX ? -inf : inf;
+  A sum = 0;
+  int slot = 0, cnt = 0;
+  bool best_masked = false;
+  for (int a = 0; a < g.kh; ++a) {
+    const int rr = r0 + a;
+    for (int b = 0; b < g.kw; ++b) {
+      const int cc = c0 + b;
+      A v;
+      if (rr >= Hp || cc >= Wp) v = tail_value;
+      else {
+        const int i = rr - g.pad, j = cc - g.pad;
+        v = (i >= 0 && i < g.H && j >= 0 && j < g.W) ? ld_acc(xp + (int64_t)i * g.W + j) : pad_value;
+      }
+      const bool nan = v != v;
+      if (METHOD == HG_POOL_AVG) {
+        if (!nan) { sum += v; ++cnt; }
+      } else {
+        const A m = nan ? (METHOD == HG_POOL_MAX ? -inf : inf) : v;
+        const bool first = (a == 0 && b == 0);
+        const bool better = METHOD == HG_POOL_MAX ? (m > best) : (m < best);
+        if (first || better) { best = m; slot = a * g.kw + b; best_masked = nan; }
+      }
+    }
+  }
+  if (METHOD == HG_POOL_AVG) {
+    y[t] = st_acc<T, A>(cnt ? sum / (A)cnt : (A)CUDART_NAN);
+    if (aux) aux[t] = (AUX)cnt;
+  } else {
+    y[t] = st_acc<T, A>(best);
+    if (aux) aux[t] = best_masked ? (AUX)-1 : (AUX)slot;  // a NaN "winner" passes no gradient (masked_fill)
+  }
+}
+
+__device__ __forceinline__ int ceil_div_i(int a, int b) { return a >= 0 ? (a + b - 1) / b : -((-a) / b); }
+__device__ __forceinline__ int floor_div_i(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+
+template <typename T, int METHOD, typename AUX>
+__global__ void __launch_bounds__(kPoolThreads)
+hexpool_bwd_kernel(const T* __restrict__ gy, const AUX* __restrict__ aux, const T* __restrict__ x, T* __restrict__ gx,
+                   int64_t total, PoolGeom g) {
+  using A = typename Acc<T>::type;
+  const int64_t t = (int64_t)blockIdx.x * kPoolThreads + threadIdx.x;
+  if (t >= total) return;
+  const int j = (int)(t % g.W);
+  const int64_t r = t / g.W;
+  const int i = (int)(r % g.H);
+  const int64_t plane = r / g.H;
+  const int64_t ob = plane * (int64_t)g.hn * g.wn;
+  const int rr = i + g.pad, cc = j + g.pad;
+  A acc = 0;
+  bool live = true;
+  if (METHOD == HG_POOL_AVG && x != nullptr) { const A v = ld_acc(x + t); live = (v == v); }
+  if (live) {
+    const int I_lo = max(ceil_div_i(rr - g.kh + 1, g.sh), 0), I_hi = min(floor_div_i(rr, g.sh), g.hn - 1);
+    for (int I = I_lo; I <= I_hi; ++I) {
+      const int off = ((I & 1) * g.shift) / 2;
+      const int J_lo = max(ceil_div_i(cc - off - g.kw + 1, g.sw), 0), J_hi = min(floor_div_i(cc - off, g.sw), g.wn - 1);
+      for (int J = J_lo; J <= J_hi; ++J) {
+        const int64_t o = ob + (int64_t)I * g.wn + J;
+        if (METHOD == HG_POOL_AVG) {
+          const int cnt = (int)aux[o];
+          if (cnt > 0) acc += ld_acc(gy + o) / (A)cnt;
+        } else {
+          const int slot = (rr - g.sh * I) * g.kw + (cc - off - J * g.sw);
+          if ((int)aux[o] == slot) acc += ld_acc(gy + o);
+        }
+      }
+    }
+  }
+  gx[t] = st_acc<T, A>(acc);
+}
+
+// ---- global pooling: x [planes, L] -> y [planes] ------------------------------------------------------
+template <typename A> struct Red { A v; int idx; int cnt; };
+
+template <typename A, int METHOD>
+__device__ __forceinline__ void red_merge(Red<A>& a, const Red<A>& b) {
+  if (METHOD == HG_POOL_AVG) { a.v += b.v; a.cnt += b.cnt; }
+  else {
+    const bool better = METHOD == HG_POOL_MAX ? (b.v > a.v) : (b.v < a.v);
+    if (better || (b.v == a.v && b.idx < a.idx)) { a.v = b.v; a.idx = b.idx; }
+  }
+}
+
+template <typename T, int METHOD, int GROUP>  // GROUP threads cooperate on one plane (32 or 256)
+__global__ void __launch_bounds__(256)
+globalpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int32_t* __restrict__ aux, int64_t planes, int64_t L) {
+  using A = typename Acc<T>::type;
+  const int lane = threadIdx.x % GROUP;
+  const int64_t plane = (int64_t)blockIdx.x * (256 / GROUP) + threadIdx.x / GROUP;
+  const bool active = plane < planes;
+  const A inf = (A)CUDART_INF;
+  Red<A> r;
+  r.v = METHOD == HG_POOL_AVG ? (A)0 : (METHOD == HG_POOL_MAX ? -inf : inf);
+  r.idx = 0x7fffffff; r.cnt = 0;
+  if (active) {
+    const T* __restrict__ xp = x + plane * L;
+    for (int64_t l = lane; l < L; l += GROUP) {
+      const A v = ld_acc(xp + l);
+      const bool nan = v != v;
+      if (METHOD == HG_POOL_AVG) { if (!nan) { r.v += v; ++r.cnt; } }
+      else {
+        const A m = nan ? (METHOD == HG_POOL_MAX ? -inf : inf) : v;
+        const bool better = METHOD == HG_POOL_MAX ? (m > r.v) : (m < r.v);
+        if (better || (m == r.v && (int)l < r.idx)) { r.v = m; r.idx = (int)l; }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Red<A> b;
+    b.v = __shfl_xor_sync(0xffffffffu, r.v, o);
+    b.idx = __shfl_xor_sync(0xffffffffu, r.idx, o);
+    b.cnt = __shfl_xor_sync(0xffffffffu, r.cnt, o);
+    red_merge<A, METHOD>(r, b);
+  }
+  if (GROUP > 32) {
+    __shared__ Red<A> part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; ++w) red_merge<A, METHOD>(r, part[w]);
+    }
+  }
+  if (active && lane == 0) {
+    if (METHOD == HG_POOL_AVG) {
+      y[plane] = st_acc<T, A>(r.cnt ? r.v / (A)r.cnt : (A)CUDART_NAN);
+      if (aux) aux[plane] = r.cnt;
+    } else {
+      y[plane] = st_acc<T, A>(r.v);
+      if (aux) aux[plane] = r.idx;
+    }
+  }
+}
+
+template <typename T, int METHOD>
+__global__ void __launch_bounds__(kPoolThreads)
+globalpool_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ x, const int32_t* __restrict__ aux, T* __restrict__ gx,
+                      int64_t total, int64_t L) {
+  using A = typename Acc<T>::type;
+  const int64_t t = (int64_t)blockIdx.x * kPoolThreads + threadIdx.x;
+  if (t >= total) return;
+  const int64_t plane = t / L;
+  const int64_t l = t - plane * L;
+  bool nan = false;
+  if (x != nullptr) { const A v = ld_acc(x + t); nan = v != v; }
+  A g = 0;
+  if (!nan) {
+    if (METHOD == HG_POOL_AVG) { const int cnt = aux[plane]; if (cnt > 0) g = ld_acc(gy + plane) / (A)cnt; }
+    else if ((int64_t)aux[plane] == l) g = ld_acc(gy + plane);
+  }
+  gx[t] = st_acc<T, A>(g);
+}
+
+// ---- host dispatch ------------------------------------------------------------------------------------
+static int check_geom(int64_t planes, int64_t H, int64_t W, int64_t hn, int64_t wn, int kh, int kw, int sh, int sw, int shift,
+                      int pad, int tail_h, int tail_w, PoolGeom& g) {
+  HG_REQUIRE(planes >= 0 && H > 0 && W > 0 && hn >= 0 && wn >= 0, HG_E_SHAPE, "bad pool shape");
+  HG_REQUIRE(kh > 0 && kw > 0 && sh > 0 && sw > 0 && shift >= 0 && pad >= 0 && tail_h >= 0 && tail_w >= 0, HG_E_ARG, "bad pool parameters");
+  HG_REQUIRE(H < (1 << 30) && W < (1 << 30) && hn < (1 << 30) && wn < (1 << 30), HG_E_SHAPE, "pool plane too large");
+  const int64_t Hv = H + 2 * pad + tail_h, Wv = W + 2 * pad + tail_w;
+  if (hn > 0 && wn > 0) {
+    const int64_t max_r = (int64_t)sh * (hn - 1) + kh - 1;
+    const int64_t max_c = (hn > 1 ? shift / 2 : 0) + (int64_t)sw * (wn - 1) + kw - 1;
+    HG_REQUIRE(max_r < Hv && max_c < Wv, HG_E_SHAPE,
+               "pool window leaves the image (row %lld of %lld, col %lld of %lld): the reference raises IndexError here",
+               (long long)max_r, (long long)Hv, (long long)max_c, (long long)Wv);
+  }
+  g = PoolGeom{(int)H, (int)W, (int)hn, (int)wn, kh, kw, sh, sw, shift, pad, tail_h, tail_w};
+  return HG_OK;
+}
+
+template <typename T, typename AUX>
+static int launch_pool_fwd(const void* x, void* y, void* aux, int64_t total, const PoolGeom& g, double pv, double tv, int method, cudaStream_t st) {
+  using A = typename Acc<T>::type;
+  const unsigned grid = (unsigned)ceil_div(total, kPoolThreads);
+  switch (method) {
+    case HG_POOL_MAX: hexpool_fwd_kernel<T, HG_POOL_MAX, AUX><<<grid, kPoolThreads, 0, st>>>((const T*)x, (T*)y, (AUX*)aux, total, g, (A)pv, (A)tv); break;
+    case HG_POOL_MIN: hexpool_fwd_kernel<T, HG_POOL_MIN, AUX><<<grid, kPoolThreads, 0, st>>>((const T*)x, (T*)y, (AUX*)aux, total, g, (A)pv, (A)tv); break;
+    default: hexpool_fwd_kernel<T, HG_POOL_AVG, AUX><<<grid, kPoolThreads, 0, st>>>((const T*)x, (T*)y, (AUX*)aux, total, g, (A)pv, (A)tv); break;
+  }
+  return finish_launch("hexpool_fwd");
+}
+template <typename T, typename AUX>
+static int launch_pool_bwd(const void* gy, const void* aux, const void* x, void* gx, int64_t total, const PoolGeom& g, int method, cudaStream_t st) {
+  const unsigned grid = (unsigned)ceil_div(total, kPoolThreads);
+  switch (method) {
+    case HG_POOL_MAX: hexpool_bwd_kernel<T, HG_POOL_MAX, AUX><<<grid, kPoolThreads, 0, st>>>((const T*)gy, (const AUX*)aux, (const T*)x, (T*)gx, total, g); break;
+    case HG_POOL_MIN: hexpool_bwd_kernel<T, HG_POOL_MIN, AUX><<<grid, kPoolThreads, 0, st>>>((const T*)gy, (const AUX*)aux, (const T*)x, (T*)gx, total, g); break;
+    default: hexpool_bwd_kernel<T, HG_POOL_AVG, AUX><<<grid, kPoolThreads, 0, st>>>((const T*)gy, (const AUX*)aux, (const T*)x, (T*)gx, total, g); break;
+  }
+  return finish_launch("hexpool_bwd");
+}
+
+template <typename T>
+static int launch_gpool_fwd(const void* x, void* y, int32_t* aux, int64_t planes, int64_t L, int method, cudaStream_t st) {
+#define HG_GP(M)                                                                                                         \
+  if (L >= 1024) globalpool_fwd_kernel<T, M, 256><<<(unsigned)planes, 256, 0, st>>>((const T*)x, (T*)y, aux, planes, L); \
+  else globalpool_fwd_kernel<T, M, 32><<<(unsigned)ceil_div(planes, 8), 256, 0, st>>>((const T*)x, (T*)y, aux, planes, L);
+  switch (method) {
+    case HG_POOL_MAX: HG_GP(HG_POOL_MAX) break;
+    case HG_POOL_MIN: HG_GP(HG_POOL_MIN) break;
+    default: HG_GP(HG_POOL_AVG) break;
+  }
+#undef HG_GP
+  return finish_launch("hexglobalpool_fwd");
+}
+template <typename T>
+static int launch_gpool_bwd(const void* gy, const void* x, const int32_t* aux, void* gx, int64_t planes, int64_t L, int method, cudaStream_t st) {
+  const int64_t total = planes * L;
+  const unsigned grid = (unsigned)ceil_div(total, kPoolThreads);
+  switch (method) {
+    case HG_POOL_MAX: globalpool_bwd_kernel<T, HG_POOL_MAX><<<grid, kPoolThreads, 0, st>>>((const T*)gy, (const T*)x, aux, (T*)gx, total, L); break;
+    case HG_POOL_MIN: globalpool_bwd_kernel<T, HG_POOL_MIN><<<grid, kPoolThreads, 0, st>>>((const T*)gy, (const T*)x, aux, (T*)gx, total, L); break;
+    default: globalpool_bwd_kernel<T, HG_POOL_AVG><<<grid, kPoolThreads, 0, st>>>((const T*)gy, (const T*)x, aux, (T*)gx, total, L); break;
+  }
+  return finish_launch("hexglobalpool_bwd");
+}
+
+}  // namespace hg
+
+using namespace hg;
+
+extern "C" {
+
+int hg_hexpool_fwd(const void* x, void* y, void* aux, int aux_bytes, int64_t planes, int64_t H, int64_t W, int64_t hn,
+                   int64_t wn, int kh, int kw, int sh, int sw, int shift, int pad, double pad_value, int tail_h, int tail_w,
+                   double tail_value, int method, int dtype, hg_stream_t stream) {
+  PoolGeom g;
+  int rc = check_geom(planes, H, W, hn, wn, kh, kw, sh, sw, shift, pad, tail_h, tail_w, g);
+  if (rc) return rc;
+  HG_REQUIRE(method >= HG_POOL_MAX && method <= HG_POOL_AVG, HG_E_ARG, "bad pool method %d", method);
+  HG_REQUIRE(aux == nullptr || aux_bytes == 1 || aux_bytes == 4, HG_E_ARG, "aux_bytes must be 1 or 4");
+  HG_REQUIRE(aux == nullptr || aux_bytes == 4 || (int64_t)kh * kw <= 127, HG_E_ARG, "windows of more than 127 cells need a 4-byte aux");
+  const int64_t total = planes * hn * wn;
+  if (total == 0) return HG_OK;
+  cudaStream_t st = as_stream(stream);
+  const bool wide = aux != nullptr && aux_bytes == 4;
+#define HG_CASE(D, T)                                                                                          \
+  if (dtype == D) return wide ? launch_pool_fwd<T, int32_t>(x, y, aux, total, g, pad_value, tail_value, method, st) \
+                              : launch_pool_fwd<T, int8_t>(x, y, aux, total, g, pad_value, tail_value, method, st);
+  HG_CASE(HG_F32, float)
+  HG_CASE(HG_F64, double)
+  HG_CASE(HG_BF16, __nv_bfloat16)
+#undef HG_CASE
+  set_error("hexpool_fwd: unsupported dtype %d", dtype);
+  return HG_E_DTYPE;
+}
+
+int hg_hexpool_bwd(const void* gy, const void* aux, int aux_bytes, const void* x, void* gx, int64_t planes, int64_t H,
+                   int64_t W, int64_t hn, int64_t wn, int kh, int kw, int sh, int sw, int shift, int pad, int method,
+                   int dtype, hg_stream_t stream) {
+  PoolGeom g;
+  int rc = check_geom(planes, H, W, 0, 0, kh, kw, sh, sw, shift, pad, 0, 0, g);
+  if (rc) return rc;
+  g.hn = (int)hn; g.wn = (int)wn;
+  HG_REQUIRE(hn >= 0 && wn >= 0 && hn < (1 << 30) && wn < (1 << 30), HG_E_SHAPE, "bad pool output shape");
+  HG_REQUIRE(method >= HG_POOL_MAX && method <= HG_POOL_AVG, HG_E_ARG, "bad pool method %d", method);
+  HG_REQUIRE(aux != nullptr && (aux_bytes == 1 || aux_bytes == 4), HG_E_ARG, "hexpool_bwd needs the aux buffer written by the forward");
+  const int64_t total = planes * H * W;
+  if (total == 0) return HG_OK;
+  cudaStream_t st = as_stream(stream);
+#define HG_CASE(D, T)                                                                              \
+  if (dtype == D) return aux_bytes == 4 ? launch_pool_bwd<T, int32_t>(gy, aux, x, gx, total, g, method, st) \
+                                        : launch_pool_bwd<T, int8_t>(gy, aux, x, gx, total, g, method, st);
+  HG_CASE(HG_F32, float)
+  HG_CASE(HG_F64, double)
+  HG_CASE(HG_BF16, __nv_bfloat16)
+#undef HG_CASE
+  set_error("hexpool_bwd: unsupported dtype %d", dtype);
+  return HG_E_DTYPE;
+}
+
+int hg_hexglobalpool_fwd(const void* x, void* y, int32_t* aux_idx, int64_t planes, int64_t L, int method, int dtype,
+                         hg_stream_t stream) {
+  HG_REQUIRE(planes >= 0 && L > 0 && L < (1ll << 31) && planes < (1ll << 31), HG_E_SHAPE, "bad global pool shape");
+  HG_REQUIRE(method >= HG_POOL_MAX && method <= HG_POOL_AVG, HG_E_ARG, "bad pool method %d", method);
+  if (planes == 0) return HG_OK;
+  cudaStream_t st = as_stream(stream);
+  if (dtype == HG_F32) return launch_gpool_fwd<float>(x, y, aux_idx, planes, L, method, st);
+  if (dtype == HG_F64) return launch_gpool_fwd<double>(x, y, aux_idx, planes, L, method, st);
+  if (dtype == HG_BF16) return launch_gpool_fwd<__nv_bfloat16>(x, y, aux_idx, planes, L, method, st);
+  set_error("hexglobalpool_fwd: unsupported dtype %d", dtype);
+  return HG_E_DTYPE;
+}
+
+int hg_hexglobalpool_bwd(const void* gy, const void* x, const int32_t* aux_idx, void* gx, int64_t planes, int64_t L,
+                         int method, int dtype, hg_stream_t stream) {
+  HG_REQUIRE(planes >= 0 && L > 0 && L < (1ll << 31), HG_E_SHAPE, "bad global pool shape");
+  HG_REQUIRE(method >= HG_POOL_MAX && method <= HG_POOL_AVG, HG_E_ARG, "bad pool method %d", method);
+  HG_REQUIRE(aux_idx != nullptr, HG_E_ARG, "hexglobalpool_bwd needs the aux buffer written by the forward");
+  if (planes == 0) return HG_OK;
+  cudaStream_t st = as_stream(stream);
+  if (dtype == HG_F32) return launch_gpool_bwd<float>(gy, x, aux_idx, gx, planes, L, method, st);
+  if (dtype == HG_F64) return launch_gpool_bwd<double>(gy, x, aux_idx, gx, planes, L, method, st);
+  if (dtype == HG_BF16) return launch_gpool_bwd<__nv_bfloat16>(gy, x, aux_idx, gx, planes, L, method, st);
+  set_error("hexglobalpool_bwd: unsupported dtype %d", dtype);
+  return HG_E_DTYPE;
+}
+
+}  // extern "C"

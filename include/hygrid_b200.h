@@ -131,22 +131,35 @@ int hg_hex_to_type2(const void* hex, void* t2, int64_t planes, int64_t H, int64_
 int hg_type_to_hex(const void* t, void* hex, int64_t planes, int64_t Ht, int64_t Wt, int rows_step,
                    int src_dtype, int dst_dtype, hg_stream_t stream);
 
+/* F.pad(x, (pl, pr, pt, pb), mode, value) on [planes,H,W] -> [planes,H+pt+pb,W+pl+pr].
+ * ref: HexFrames.py:13-21 pad().  mode: 0 constant, 1 reflect, 2 replicate, 3 circular,
+ * 4 symmetric (cv2.BORDER_REFLECT, geometry_np.py:720-725 heximpad).
+ * dtype in {HG_U8, HG_F32, HG_F64, HG_BF16}; the backward ({HG_F32, HG_BF16}) writes gx fully. */
+int hg_pad2d(const void* x, void* y, int64_t planes, int64_t H, int64_t W, int pl, int pr, int pt, int pb,
+             int mode, double value, int dtype, hg_stream_t stream);
+int hg_pad2d_bwd(const void* gy, void* gx, int64_t planes, int64_t H, int64_t W, int pl, int pr, int pt, int pb,
+                 int mode, int dtype, hg_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Hex pooling.  ref: HexFrames.py:255-341 HexPool2d, :344-401 HexAdaptivePool2d,
  * :402-414 HexGlobalPool2d, reductions :461-479 (NaN-aware).
  * The virtual input is x [planes,H,W] framed by `pad` cells of pad_value on every side and then
  * extended by tail_w columns / tail_h rows of tail_value (ceil_mode, value 0 or NaN).  Window of
  * out(I,J): rows sh*I + a, cols ((I%2)*shift)/2 + J*sw + b, a < kh, b < kw.
- * aux [planes,hn,wn] (int8, may be NULL): max/min -> winning window slot a*kw+b; avg -> number
- * of non-NaN cells.  dtype in {HG_F32, HG_F64, HG_BF16}.
+ * aux [planes,hn,wn] (may be NULL when no backward is needed; aux_bytes = 1 -> int8, 4 -> int32,
+ * windows of more than 127 cells need int32): max/min -> winning window slot a*kw+b (-1 when the
+ * winner is a masked NaN, which passes no gradient); avg -> number of non-NaN cells.
+ * dtype in {HG_F32, HG_F64, HG_BF16}.  A window that leaves the virtual input returns HG_E_SHAPE
+ * (the reference raises IndexError).
  * ---------------------------------------------------------------------------------------- */
-int hg_hexpool_fwd(const void* x, void* y, int8_t* aux, int64_t planes, int64_t H, int64_t W,
+int hg_hexpool_fwd(const void* x, void* y, void* aux, int aux_bytes, int64_t planes, int64_t H, int64_t W,
                    int64_t hn, int64_t wn, int kh, int kw, int sh, int sw, int shift,
                    int pad, double pad_value, int tail_h, int tail_w, double tail_value,
                    int method, int dtype, hg_stream_t stream);
-/* gx [planes,H,W] is fully written (no pre-zeroing needed). */
-int hg_hexpool_bwd(const void* gy, const int8_t* aux, void* gx, int64_t planes, int64_t H, int64_t W,
-                   int64_t hn, int64_t wn, int kh, int kw, int sh, int sw, int shift,
+/* gx [planes,H,W] is fully written (no pre-zeroing needed).  x (may be NULL) is only read by the
+ * average method to keep NaN cells gradient-free. */
+int hg_hexpool_bwd(const void* gy, const void* aux, int aux_bytes, const void* x, void* gx, int64_t planes,
+                   int64_t H, int64_t W, int64_t hn, int64_t wn, int kh, int kw, int sh, int sw, int shift,
                    int pad, int method, int dtype, hg_stream_t stream);
 /* x [planes, L] -> y [planes]; aux_idx [planes] int32 (argmax / non-NaN count), may be NULL */
 int hg_hexglobalpool_fwd(const void* x, void* y, int32_t* aux_idx, int64_t planes, int64_t L,
@@ -195,6 +208,9 @@ int hg_host_rect2hex(const void* host_src, void* host_dst, const double* host_xs
 int hg_host_hex2rect(const void* host_src, void* host_dst, const double* host_xs, const double* host_ys,
                      int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1,
                      int src_dtype, int dst_dtype, int interp, int math, int device);
+/* frees the streams, device ring and pinned bounce buffers the host entry points created lazily
+ * (the only memory the library ever owns). */
+void hg_host_release(void);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,81 @@
+"""CPU-side checks of the drop-in boundary: libhygrid_b200.so loads and exports every symbol
+include/hygrid_b200.h declares (no compute calls without a GPU), the ctypes table covers the header,
+and argument validation that happens before any launch returns the documented error codes."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from HyGrid import _native as nv
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "hygrid_b200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_expected_surface():
+    syms = declared_symbols()
+    assert len(syms) >= 30
+    for must in ("hg_rect2hex_bilinear", "hg_hex2rect_linear", "hg_hexwarp_affine", "hg_hexsrc_index",
+                 "hg_hex_to_type1", "hg_hexpool_fwd", "hg_hexpool_bwd", "hg_hexconv_fwd", "hg_hexconv_dgrad",
+                 "hg_hexconv_wgrad", "hg_host_rect2hex", "hg_host_hex2rect"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(nv.LIB_PATH), "build the library first: python __graft_entry__.py"
+    lib = C.CDLL(nv.LIB_PATH)
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_ctypes_table_covers_the_header():
+    bound = set(nv._SIGS) | {"hg_version", "hg_last_error", "hg_launch_count", "hg_reset_launch_count", "hg_host_release"}
+    assert set(declared_symbols()) <= bound, set(declared_symbols()) - bound
+
+
+def test_version_and_error_string():
+    L = nv.lib()
+    assert L.hg_version() == 100
+    # invalid arguments are rejected before any CUDA call: safe without a GPU
+    rc = L.hg_rect2hex_bilinear(None, None, None, None, 1, 0, 4, 4, 4, nv.F32, nv.F32, 0, None)
+    assert rc == -3 and b"bad shape" in L.hg_last_error()
+    rc = L.hg_hexconv_out_shape(2, 2, 2, 1, 1, 0, C.byref(C.c_int64()), C.byref(C.c_int64()))
+    assert rc == -3 and b"too small" in L.hg_last_error()
+    ho, wo = C.c_int64(), C.c_int64()
+    assert L.hg_hexconv_out_shape(256, 256, 2, 1, 1, 1, C.byref(ho), C.byref(wo)) == 0
+    assert (ho.value, wo.value) == (256, 256)
+    assert L.hg_hexconv_out_shape(8, 8, 3, 2, 1, 0, C.byref(ho), C.byref(wo)) == 0
+    with pytest.raises(nv.HyGridNativeError):
+        nv.call("hg_type_to_hex", None, None, 1, 4, 9, 3, nv.F32, nv.F32, None)
+
+
+def test_conv_out_shape_matches_oracle():
+    from oracle import hexframes_oracle as HO
+    L = nv.lib()
+    for H in (5, 8, 9, 16, 33):
+        for W in (5, 8, 13):
+            for r in (2, 3):
+                for s in (1, 2):
+                    for d in (1, 2):
+                        for pad in (0, 1, 2):
+                            re_, ro, cols = HO.hexconv_out_shape(H + 2 * pad, W + 2 * pad, r, s, d)
+                            ho, wo = C.c_int64(), C.c_int64()
+                            rc = L.hg_hexconv_out_shape(H, W, r, s, d, pad, C.byref(ho), C.byref(wo))
+                            ok = re_ > 0 and ro > 0 and cols > 0 and re_ - ro in (0, 1)
+                            assert (rc == 0) == ok
+                            if ok:
+                                assert (ho.value, wo.value) == (re_ + ro, cols)
+
+
+def test_no_cpu_fallback():
+    import torch
+    from HyGrid import functional as Fn
+    with pytest.raises(nv.HyGridNativeError):
+        Fn.rect_to_hex(torch.zeros(1, 4, 4), None, "bilinear")

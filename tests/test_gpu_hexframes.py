@@ -1,0 +1,236 @@
+"""GPU parity tests of the hex-lattice operators (HexFrames mirror) against the golden fixtures generated
+from the reference's own HexConv2d / HexPool2d / converters and against the torch-CPU oracle.
+
+Tolerances: conv fp32 1e-4 (summation order), bf16 activations 2e-2 relative to max|y|; pooling max/min
+bit-exact, average 1e-6; layout converters bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hexframes_oracle as HO
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hf():
+    from HyGrid import HexFrames
+    return HexFrames
+
+
+def t(a, **kw):
+    return torch.tensor(np.asarray(a), device="cuda", **kw)
+
+
+def test_hexconv_golden_forward_backward(hf, hexframes_golden):
+    G = hexframes_golden
+    assert int(G["conv_count"]) > 40
+    for n in range(int(G["conv_count"])):
+        r, s, d, pad, off, g, hb = (int(v) for v in G[f"conv_{n}_cfg"])
+        x = t(G[f"conv_{n}_x"]).requires_grad_()
+        w = t(G[f"conv_{n}_w"])
+        m = hf.HexConv2d(x.shape[1], w.shape[0], off, r, stride=s, padding=pad, dilation=d, groups=g, bias=bool(hb)).cuda()
+        with torch.no_grad():
+            m.kernel.copy_(w)
+            if hb:
+                m.bias.copy_(t(G[f"conv_{n}_b"]))
+        y = m(x)
+        ref = G[f"conv_{n}_y"]
+        assert tuple(y.shape) == ref.shape and y.dtype == torch.float32, (n, y.shape, ref.shape)
+        np.testing.assert_allclose(y.detach().cpu().numpy(), ref, rtol=1e-4, atol=1e-4)
+        (y * t(G[f"conv_{n}_gy"])).sum().backward()
+        np.testing.assert_allclose(x.grad.cpu().numpy(), G[f"conv_{n}_dx"], rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(m.kernel.grad.cpu().numpy(), G[f"conv_{n}_dw"], rtol=1e-3, atol=1e-3)
+        if hb:
+            np.testing.assert_allclose(m.bias.grad.cpu().numpy(), G[f"conv_{n}_db"], rtol=1e-3, atol=1e-3)
+
+
+def test_hexconv_adaptive_padding_golden(hf, hexframes_golden):
+    G = hexframes_golden
+    for n in range(int(G["aconv_count"])):
+        r, s, d = (int(v) for v in G[f"aconv_{n}_cfg"])
+        x = t(G[f"aconv_{n}_x"])
+        w = t(G[f"aconv_{n}_w"])
+        m = hf.HexConv2dAdaptivePadding(x.shape[1], w.shape[0], 0, r, stride=s, dilation=d).cuda()
+        with torch.no_grad():
+            m.kernel.copy_(w); m.bias.copy_(t(G[f"aconv_{n}_b"]))
+        y = m(x)
+        assert tuple(y.shape) == G[f"aconv_{n}_y"].shape
+        np.testing.assert_allclose(y.detach().cpu().numpy(), G[f"aconv_{n}_y"], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("cfg", [
+    # N, Cin, Cout, H, W, r, s, d, pad, off, groups
+    (2, 3, 32, 37, 41, 2, 1, 1, 1, 0, 1),
+    (2, 16, 24, 33, 70, 2, 1, 1, 1, 1, 1),
+    (1, 8, 8, 40, 45, 3, 2, 1, 2, 0, 2),
+    (2, 6, 10, 29, 31, 2, 2, 2, 2, 1, 1),
+    (1, 20, 36, 64, 64, 2, 1, 1, 1, 0, 4),
+    (1, 5, 7, 30, 30, 4, 1, 1, 3, 1, 1),
+])
+def test_hexconv_vs_oracle(hf, cfg):
+    N, Cin, Cout, H, W, r, s, d, pad, off, groups = cfg
+    torch.manual_seed(0)
+    x = torch.randn(N, Cin, H, W)
+    K = 3 * r * r - 3 * r + 1
+    w = torch.randn(Cout, Cin // groups, 1, K) * 0.2
+    b = torch.randn(Cout)
+    xr, wr, br = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
+    ref = HO.hexconv2d(xr, wr, br, off, r, s, pad, d, groups, padding_value=0.5)
+    gy = torch.randn_like(ref)
+    (ref * gy).sum().backward()
+    xg, wg, bg = x.cuda().requires_grad_(), w.cuda().requires_grad_(), b.cuda().requires_grad_()
+    y = hf.hexconv2d(xg, wg, bg, off, r, s, pad, d, groups, padding_value=0.5)
+    assert y.shape == ref.shape
+    scale = float(ref.abs().max())
+    assert float((y.cpu() - ref).abs().max()) <= 1e-4 * scale
+    (y * gy.cuda()).sum().backward()
+    assert float((xg.grad.cpu() - xr.grad).abs().max()) <= 1e-4 * float(xr.grad.abs().max())
+    assert float((wg.grad.cpu() - wr.grad).abs().max()) <= 1e-3 * float(wr.grad.abs().max())
+    assert float((bg.grad.cpu() - br.grad).abs().max()) <= 1e-3 * float(br.grad.abs().max())
+    # bf16 activations (what autocast feeds), fp32 accumulation
+    yb = hf.hexconv2d(x.cuda().bfloat16(), w.cuda(), b.cuda(), off, r, s, pad, d, groups, padding_value=0.5)
+    assert float((yb.cpu() - ref.detach()).abs().max()) <= 2e-2 * scale
+
+
+def test_hexconv_padding_modes_and_autocast(hf):
+    torch.manual_seed(1)
+    x = torch.randn(2, 4, 20, 22)
+    for mode in ("reflect", "replicate", "circular"):
+        m = hf.HexConv2d(4, 6, 1, 2, padding=2, padding_mode=mode).cuda()
+        ref = HO.hexconv2d(x, m.kernel.detach().cpu(), m.bias.detach().cpu(), 1, 2, 1, 2, 1, 1, padding_mode=mode)
+        y = m(x.cuda())
+        assert float((y.cpu() - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
+    m = hf.HexConv2d(4, 6, 0, 2, padding=1).cuda()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = m(x.cuda())
+    assert y.dtype == torch.float32
+    ref = HO.hexconv2d(x, m.kernel.detach().cpu(), m.bias.detach().cpu(), 0, 2, 1, 1)
+    assert float((y.cpu() - ref).abs().max()) <= 2e-2 * float(ref.abs().max())
+    assert list(m.state_dict().keys()) == ["kernel", "bias"]
+    with pytest.raises(ValueError):
+        hf.HexConv2d(4, 6, 0, 2).cuda()(torch.randn(1, 4, 2, 2).cuda())
+
+
+def test_pad_function_all_modes(hf):
+    x = torch.randn(2, 3, 9, 11, device="cuda", requires_grad=True)
+    for mode in ("constant", "reflect", "replicate", "circular"):
+        xr = x.detach().clone().requires_grad_()
+        ref = torch.nn.functional.pad(xr, (3, 3, 3, 3), mode, 1.5) if mode == "constant" else torch.nn.functional.pad(xr, (3, 3, 3, 3), mode)
+        x.grad = None
+        y = hf.pad(x, 3, mode, 1.5)
+        assert torch.equal(y, ref)
+        g = torch.randn_like(ref)
+        (y * g).sum().backward(); (ref * g).sum().backward()
+        assert torch.allclose(x.grad, xr.grad, atol=1e-6)
+
+
+def test_hexpool_golden_forward_backward(hf, hexframes_golden):
+    G = hexframes_golden
+    assert int(G["pool_count"]) >= 18
+    for n in range(int(G["pool_count"])):
+        kh, kw, sh, sw, pad, ceil, cip = (int(v) for v in G[f"pool_{n}_cfg"])
+        method = str(G[f"pool_{n}_method"])
+        x = t(G[f"pool_{n}_x"]).requires_grad_()
+        m = hf.HexPool2d(method, (kh, kw), (sh, sw), pad, ceil_mode=bool(ceil), count_include_pad=bool(cip))
+        y = m(x)
+        ref = G[f"pool_{n}_y"]
+        assert tuple(y.shape) == ref.shape, (n, y.shape, ref.shape)
+        if method == "average":
+            np.testing.assert_allclose(y.detach().cpu().numpy(), ref, rtol=1e-6, atol=1e-7, equal_nan=True)
+        else:
+            assert np.array_equal(y.detach().cpu().numpy(), ref, equal_nan=True)
+        (torch.nan_to_num(y) * t(G[f"pool_{n}_gy"])).sum().backward()
+        np.testing.assert_allclose(x.grad.cpu().numpy(), G[f"pool_{n}_dx"], rtol=1e-6, atol=1e-7)
+
+
+def test_adaptive_and_global_pool_golden(hf, hexframes_golden):
+    G = hexframes_golden
+    for n in range(int(G["apool_count"])):
+        method = str(G[f"apool_{n}_method"])
+        y = hf.HexAdaptivePool2d(int(G[f"apool_{n}_out"]), method)(t(G[f"apool_{n}_x"]))
+        np.testing.assert_allclose(y.cpu().numpy(), G[f"apool_{n}_y"], rtol=1e-6, atol=1e-7)
+        if method != "average":
+            assert np.array_equal(y.cpu().numpy(), G[f"apool_{n}_y"])
+    for method in ("max", "min", "average"):
+        y = hf.HexGlobalPool2d(method)(t(G[f"gpool_{method}_x"]))
+        assert tuple(y.shape) == G[f"gpool_{method}_y"].shape
+        np.testing.assert_allclose(y.cpu().numpy(), G[f"gpool_{method}_y"], rtol=1e-6, atol=1e-7)
+    with pytest.raises(Exception):
+        hf.HexAdaptivePool2d([2, 2], "max")
+    with pytest.raises(NotImplementedError):
+        hf.HexGlobalPool2d("centroid")(torch.zeros(1, 1, 4, 4, device="cuda"))
+
+
+@pytest.mark.parametrize("method", ["max", "min", "average"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64, torch.bfloat16])
+def test_hexpool_vs_oracle_with_nans(hf, method, dtype):
+    torch.manual_seed(2)
+    x = torch.randn(3, 5, 66, 75).to(dtype)
+    x[torch.rand_like(x.float()) < 0.15] = float("nan")
+    x[0, 0, :4, :8] = float("nan")                       # whole windows of NaN
+    for (k, s, pad, ceil, cip) in ((2, 2, 0, False, True), (3, 2, 1, False, True), (2, 2, 0, True, False), ((2, 3), (2, 4), 2, True, True)):
+        xr = x.clone().requires_grad_()
+        ref = HO.hexpool2d(xr, method, k, s, pad, ceil_mode=ceil, count_include_pad=cip)
+        xg = x.cuda().requires_grad_()
+        y = hf.HexPool2d(method, k, s, pad, ceil_mode=ceil, count_include_pad=cip)(xg)
+        assert y.shape == ref.shape
+        tol = dict(rtol=1e-6, atol=1e-7) if dtype != torch.bfloat16 else dict(rtol=2e-2, atol=2e-2)
+        if method == "average":
+            np.testing.assert_allclose(y.detach().float().cpu().numpy(), ref.detach().float().numpy(), equal_nan=True, **tol)
+        else:
+            assert np.array_equal(y.detach().float().cpu().numpy(), ref.detach().float().numpy(), equal_nan=True)
+        g = torch.randn(ref.shape).to(dtype)
+        (torch.nan_to_num(ref) * g).sum().backward()
+        (torch.nan_to_num(y) * g.cuda()).sum().backward()
+        np.testing.assert_allclose(xg.grad.float().cpu().numpy(), xr.grad.float().numpy(), **tol)
+
+
+def test_hexpool_errors_and_defaults(hf):
+    p = hf.HexPool2d("max", 2)                           # stride=None -> kernel_size (reference crashes)
+    y = p(torch.randn(1, 2, 16, 16, device="cuda"))
+    assert y.shape == (1, 2, 8, 7) and (p.hn, p.wn) == (8, 7)
+    with pytest.raises(IndexError):                      # kw > sw runs off the image in the reference too
+        hf.HexPool2d("max", 2, 1)(torch.randn(1, 1, 8, 8, device="cuda"))
+    with pytest.raises(KeyError):
+        hf.HexPool2d("median", 2, 2)
+
+
+def test_pool_pyramid_full_size(hf):
+    """config 4 pyramid geometry on one 4K plane: shapes and a window spot-check at every level."""
+    x = torch.rand(1, 1, 2160, 3840, device="cuda")
+    pool = hf.HexPool2d("average", 2, 2)
+    shapes = []
+    cur = x
+    for _ in range(5):
+        nxt = pool(cur)
+        shapes.append(tuple(nxt.shape[-2:]))
+        I, J = nxt.shape[-2] // 2 + 1, nxt.shape[-1] // 3
+        c0 = (I % 2) + 2 * J
+        exp = cur[0, 0, 2 * I:2 * I + 2, c0:c0 + 2].mean()
+        assert abs(float(nxt[0, 0, I, J]) - float(exp)) <= 1e-6
+        cur = nxt
+    assert shapes == [(1080, 1919), (540, 959), (270, 479), (135, 239), (67, 119)]
+
+
+def test_reductions_and_converters(hf, hexframes_golden, resample_golden):
+    v = torch.randn(4, 3, 5, 7, 9, device="cuda")
+    v[v > 1.2] = float("nan")
+    assert torch.equal(hf.max_pooling(v).cpu(), HO.reduce_max(v.cpu()))
+    assert torch.equal(hf.min_pooling(v).cpu(), HO.reduce_min(v.cpu()))
+    np.testing.assert_allclose(hf.average_pooling(v).cpu().numpy(), HO.reduce_average(v.cpu()).numpy(), rtol=1e-6, atol=1e-7, equal_nan=True)
+    G = resample_golden
+    for n in range(int(G["r5_count"])):
+        img, off = G[f"r5_{n}_img"], int(G[f"r5_{n}_off"])
+        x = t(img, dtype=torch.float32)[None]
+        t1 = hf.heximage_to_type1(x, off)
+        assert np.array_equal(t1.cpu().numpy(), G[f"r5_{n}_tt1"])
+        assert np.array_equal(hf.heximage_to_type2(x, off).cpu().numpy(), G[f"r5_{n}_tt2"])
+        back, o2 = hf.type1_to_heximage(t1, off)
+        assert o2 == off and np.array_equal(back.cpu().numpy(), G[f"r5_{n}_tdec"])
+    x = torch.randn(2, 3, 6, 5, device="cuda", requires_grad=True)
+    xr = x.detach().cpu().clone().requires_grad_()
+    g = torch.randn(2, 3, 12, 11)
+    (hf.heximage_to_type2(x, 1) * g.cuda()).sum().backward()
+    (HO.heximage_to_type2(xr, 1) * g).sum().backward()
+    assert torch.allclose(x.grad.cpu(), xr.grad, atol=1e-6)
