@@ -50,8 +50,8 @@ def _tables(kind, h, w, h1, w1, twin, device):
     else:
         raise KeyError(kind)
     dev = torch.device(device)
-    return (torch.from_numpy(np.ascontiguousarray(xs)).to(dev), torch.from_numpy(np.ascontiguousarray(ys)).to(dev),
-            xs, ys)
+    xs, ys = np.ascontiguousarray(xs, dtype=np.float64), np.ascontiguousarray(ys, dtype=np.float64)
+    return torch.from_numpy(xs).to(dev), torch.from_numpy(ys).to(dev), xs, ys
 
 
 def coordinate_tables(kind, h, w, h1, w1, twin="np", device="cuda"):
@@ -92,7 +92,7 @@ def rect_to_hex(x: torch.Tensor, hex_dsize=None, interpolation="nearest", out_dt
     method = {"nearest": 0, "bilinear": 1}[interpolation]
     x, planes, h, w = _planes(x)
     h1, w1 = (h, w) if hex_dsize is None else (int(hex_dsize[0]), int(hex_dsize[1]))
-    xs, ys, _, _ = coordinate_tables("rect2hex", h, w, h1, w1, "np", x.device)
+    xs, ys, hxs, hys = coordinate_tables("rect2hex", h, w, h1, w1, "np", x.device)
     shape = x.shape[:-2] + (h1, w1)
     st = nv.stream_ptr(x.device)
     if method == 0:
@@ -101,7 +101,8 @@ def rect_to_hex(x: torch.Tensor, hex_dsize=None, interpolation="nearest", out_dt
                 x.element_size(), st)
     else:
         y = out if out is not None else torch.empty(shape, dtype=_out_dtype(x, out_dtype), device=x.device)
-        nv.call("hg_rect2hex_bilinear", nv.ptr(x), nv.ptr(y), nv.ptr(xs), nv.ptr(ys), planes, h, w, h1, w1,
+        nv.call("hg_rect2hex_bilinear", nv.ptr(x), nv.ptr(y), nv.ptr(xs), nv.ptr(ys), C.c_void_p(hxs.ctypes.data),
+                C.c_void_p(hys.ctypes.data), planes, h, w, h1, w1,
                 nv.hg_dtype(x.dtype), nv.hg_dtype(y.dtype), _MATH[math], st)
     return y
 

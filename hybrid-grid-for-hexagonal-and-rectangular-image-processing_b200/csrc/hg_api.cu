@@ -1,5 +1,6 @@
 // hg_api.cu -- version, thread-local error string, launch counter.
 #include "hg_common.cuh"
+#include "hg_ptx.cuh"
 #include <string.h>
 
 namespace hg {
@@ -21,6 +22,19 @@ int finish_launch(const char* what) {
     return (int)e;
   }
   return HG_OK;
+}
+
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+    }
+    return reinterpret_cast<PFN_encodeTiled>(p);
+  }();
+  return fn;
 }
 }  // namespace hg
 

@@ -150,7 +150,7 @@ static int run_host(int kind, const void* host_src, void* host_dst, const double
     HG_CUDA(cudaMemcpyAsync(ws.dsrc[s], hsrc, (size_t)n * src_plane, cudaMemcpyHostToDevice, ws.st[s]));
     if (kind == 0) {
       rc = interp == 0 ? hg_rect2hex_nearest(ws.dsrc[s], ws.ddst[s], dxs, dys, n, h, w, h1, w1, dtype_size(sdt), ws.st[s])
-                       : hg_rect2hex_bilinear(ws.dsrc[s], ws.ddst[s], dxs, dys, n, h, w, h1, w1, sdt, ddt, math, ws.st[s]);
+                       : hg_rect2hex_bilinear(ws.dsrc[s], ws.ddst[s], dxs, dys, host_xs, host_ys, n, h, w, h1, w1, sdt, ddt, math, ws.st[s]);
     } else {
       rc = interp == 0 ? hg_hex2rect_nearest(ws.dsrc[s], ws.ddst[s], dxs, dys, n, h, w, h1, w1, dtype_size(sdt), ws.st[s])
                        : hg_hex2rect_linear(ws.dsrc[s], ws.ddst[s], dxs, dys, n, h, w, h1, w1, sdt, ddt, math, ws.st[s]);

@@ -439,6 +439,11 @@ static int check_plane(int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t
   return HG_OK;
 }
 
+// hg_resample_tma.cu: HG_OK launched, 1 not applicable (fall back to the direct gather), else error
+int try_rect2hex_bilinear_tma(const void* src, void* dst, const double* xs, const double* ys, const double* host_xs,
+                              const double* host_ys, int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1, int sdt,
+                              int ddt, int math, cudaStream_t st);
+
 template <typename TS, typename TD>
 static int launch_rect2hex_bilinear(const void* src, void* dst, const double* xs, const double* ys, int64_t planes,
                                     int64_t h, int64_t w, int64_t h1, int64_t w1, int math, cudaStream_t st) {
@@ -583,13 +588,17 @@ int hg_rect2hex_nearest(const void* src, void* dst, const double* xs, const doub
   return HG_E_DTYPE;
 }
 
-int hg_rect2hex_bilinear(const void* src, void* dst, const double* xs, const double* ys, int64_t planes, int64_t h,
-                         int64_t w, int64_t h1, int64_t w1, int src_dtype, int dst_dtype, int math, hg_stream_t stream) {
+int hg_rect2hex_bilinear(const void* src, void* dst, const double* xs, const double* ys, const double* host_xs,
+                         const double* host_ys, int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1, int src_dtype,
+                         int dst_dtype, int math, hg_stream_t stream) {
   int rc = check_plane(planes, h, w, h1, w1);
   if (rc) return rc;
   HG_REQUIRE(math == HG_MATH_EXACT || math == HG_MATH_FAST, HG_E_ARG, "bad math mode %d", math);
   if (planes == 0 || h1 == 0 || w1 == 0) return HG_OK;
   cudaStream_t st = as_stream(stream);
+  // TMA-staged tiles when the host copies of the tables are available and the lattices have similar pitch
+  rc = try_rect2hex_bilinear_tma(src, dst, xs, ys, host_xs, host_ys, planes, h, w, h1, w1, src_dtype, dst_dtype, math, st);
+  if (rc != 1) return rc;
 #define HG_CASE(S, TS, D, TD) \
   if (src_dtype == S && dst_dtype == D) return launch_rect2hex_bilinear<TS, TD>(src, dst, xs, ys, planes, h, w, h1, w1, math, st);
   HG_CASE(HG_U8, uint8_t, HG_F32, float)

@@ -1,0 +1,253 @@
+// hg_resample_tma.cu -- rect -> hex bilinear resampling with TMA-staged source tiles (sm_100a).
+//
+// ref: geometry_np.py:358-519 rect_to_hex_resample(..., 'bilinear').
+//
+// The direct gather kernel (hg_resample.cu) is issue-bound when the lattices have similar pitch: four
+// predicated global loads with 64-bit addressing per output.  Here a persistent CTA walks a list of
+// (tile position, plane) items; for each item ONE thread issues a 3-D TMA box load
+// (cp.async.bulk.tensor) of the source footprint of the 32 x 128 (or 64 x 128) output tile -- rows
+// i_n(a0) .. i_n(a1)+1, columns j_n(b0) .. j_n(b1)+1 -- into a ring of shared-memory stages.  Box elements
+// outside the image are zero-filled by the TMA unit, which *is* the reference's zero-fill of
+// out-of-range taps, so the compute loop has no bounds checks at all: per output two shared loads
+// (the upper pair is carried in registers from the previous row whenever i_n advances by one), three
+// FMAs and one coalesced streaming store.  Items are ordered position-major / plane-minor so that the
+// per-thread row / column tables are computed once per position and reused for every plane.
+#include "hg_common.cuh"
+#include "hg_ptx.cuh"
+#include <stdlib.h>
+
+namespace hg {
+
+constexpr int kTW = 128;       // output tile width  (4 columns per lane, 32 apart)
+constexpr int kTmaThreads = 256;
+constexpr int kTmaStages = 3;
+
+__device__ __forceinline__ void rect_axis_d(double coord, int n, int& idx, double& frac) {
+  // i_ = x_ + (h-1)*0.5 ; i_n = trunc(i_) ; i_f = i_ - float32(i_n)      (geometry_np.py:440-449)
+  const double c = dadd(coord, (double)(n - 1) * 0.5);
+  idx = trunc_i32(c);
+  frac = dsub(c, (double)(float)idx);
+}
+
+template <typename TS, typename TD, bool EXACT, int RW>  // RW = output rows per warp; tile height = 8*RW
+__global__ void __launch_bounds__(kTmaThreads)
+rect2hex_bilinear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __restrict__ dst, const double* __restrict__ xs,
+                             const double* __restrict__ ys, int h, int w, int h1, int w1, int tiles_x, int planes,
+                             long long total_items, long long items_per_cta, int BW, int BH, int stage_bytes) {
+  using WT = typename std::conditional<EXACT, double, float>::type;
+  constexpr int TH = 8 * RW;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kTmaStages * stage_bytes);
+
+  const long long g_begin = (long long)blockIdx.x * items_per_cta;
+  const long long g_end = min(total_items, g_begin + items_per_cta);
+  if (g_begin >= g_end) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&tmap);
+    for (int s = 0; s < kTmaStages; ++s) ptx::mbar_init(&full[s], 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](long long g, int s) {   // one thread
+    const long long pos = g / planes;
+    const int plane = (int)(g - pos * planes);
+    const int tx = (int)(pos % tiles_x), ty = (int)(pos / tiles_x);
+    int row0, col0; double f;
+    rect_axis_d(xs[ty * TH], h, row0, f);
+    rect_axis_d(ys[tx * kTW], w, col0, f);
+    ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(BW * BH * (int)sizeof(TS)));
+    ptx::tma_load_3d(smem_raw + (size_t)s * stage_bytes, &tmap, &full[s], col0, row0, plane);
+  };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTmaStages && g_begin + s < g_end; ++s) issue(g_begin + s, s);
+  }
+
+  long long pos = g_begin / planes;
+  int plane = (int)(g_begin - pos * planes);
+  long long cur_pos = -1;
+  int coff[4], roff[RW];
+  WT jf[4], uf[RW];
+  bool cok[4];
+  int nrows = 0, a0 = 0, b0 = 0;
+
+  for (long long k = 0; g_begin + k < g_end; ++k) {
+    const int s = (int)(k % kTmaStages);
+    const uint32_t parity = (uint32_t)((k / kTmaStages) & 1);
+    if (pos != cur_pos) {                       // new tile position: rebuild the per-thread tables
+      cur_pos = pos;
+      const int tx = (int)(pos % tiles_x), ty = (int)(pos / tiles_x);
+      a0 = ty * TH + warp * RW; b0 = tx * kTW + lane;
+      int row0, col0; double f;
+      rect_axis_d(xs[ty * TH], h, row0, f);
+      rect_axis_d(ys[tx * kTW], w, col0, f);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int b = b0 + 32 * c;
+        cok[c] = b < w1;
+        int jn; double v;
+        rect_axis_d(cok[c] ? ys[b] : ys[tx * kTW], w, jn, v);
+        coff[c] = jn - col0;
+        jf[c] = (WT)v;
+      }
+      nrows = 0;
+#pragma unroll
+      for (int r = 0; r < RW; ++r) {
+        const int a = a0 + r;
+        int in = row0; double u = 0.0;
+        if (a < h1) { rect_axis_d(xs[a], h, in, u); nrows = r + 1; }
+        roff[r] = (in - row0) * BW;
+        uf[r] = (WT)u;
+      }
+    }
+    ptx::mbar_wait(&full[s], parity);
+    const TS* __restrict__ t = reinterpret_cast<const TS*>(smem_raw + (size_t)s * stage_bytes);
+    TD* __restrict__ dp = dst + (size_t)plane * h1 * w1 + (size_t)a0 * w1 + b0;
+
+    WT bl[4], br[4];   // lower pair of the previous row (= upper pair of this row when i_n advanced by one)
+#pragma unroll
+    for (int r = 0; r < RW; ++r) {
+      if (r < nrows) {
+        const bool carry = (r > 0) && (roff[r] == roff[r > 0 ? r - 1 : 0] + BW);   // warp-uniform
+        WT tl[4], tr[4];
+        if (carry) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { tl[c] = bl[c]; tr[c] = br[c]; }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int o = roff[r] + coff[c];
+            tl[c] = (WT)t[o];
+            tr[c] = (WT)t[o + 1];
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int o = roff[r] + BW + coff[c];
+          bl[c] = (WT)t[o];
+          br[c] = (WT)t[o + 1];
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          TD o;
+          if (EXACT) {   // literal operation order of geometry_np.py:515-517, no contraction
+            const double u = uf[r], v = jf[c];
+            const double u1 = dsub(1.0, u), v1 = dsub(1.0, v);
+            const double t1 = dadd(dmul(u, bl[c]), dmul(u1, tl[c]));
+            const double t2 = dadd(dmul(u, br[c]), dmul(u1, tr[c]));
+            o = (TD)dadd(dmul(v, t2), dmul(v1, t1));
+          } else {
+            const float u = uf[r], v = jf[c];
+            const float t1 = fmaf(u, bl[c] - tl[c], tl[c]);
+            const float t2 = fmaf(u, br[c] - tr[c], tr[c]);
+            o = (TD)fmaf(v, t2 - t1, t1);
+          }
+          if (cok[c]) st_stream(dp + (size_t)r * w1 + 32 * c, o);
+        }
+      }
+    }
+    __syncthreads();                            // every thread is done reading stage s
+    if (threadIdx.x == 0 && g_begin + k + kTmaStages < g_end) issue(g_begin + k + kTmaStages, s);
+    if (++plane == planes) { plane = 0; ++pos; }
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+static inline int host_axis_index(double coord, int64_t n) {
+  const double c = coord + (double)(n - 1) * 0.5;
+  return (int)c;  // truncation toward zero, like the device path
+}
+
+// Largest source footprint of any tile along one axis (+1 for the "index + 1" tap); -1 when the table is
+// not monotone (then the tiled kernel does not apply).
+static int axis_span(const double* tab, int64_t n_out, int64_t n_src, int tile) {
+  int span = 0;
+  for (int64_t t0 = 0; t0 < n_out; t0 += tile) {
+    const int64_t t1 = (t0 + tile < n_out ? t0 + tile : n_out) - 1;
+    const int first = host_axis_index(tab[t0], n_src);
+    int prev = first;
+    for (int64_t t = t0 + 1; t <= t1; ++t) {
+      const int cur = host_axis_index(tab[t], n_src);
+      if (cur < prev) return -1;
+      prev = cur;
+    }
+    if (prev - first + 2 > span) span = prev - first + 2;
+  }
+  return span;
+}
+
+template <typename T> struct TmaType;
+template <> struct TmaType<float> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; };
+template <> struct TmaType<double> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_FLOAT64; };
+template <> struct TmaType<uint8_t> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_UINT8; };
+
+static int g_sm_count = 0;
+
+template <typename TS, typename TD, bool EXACT, int RW>
+static int launch_tma(const void* src, void* dst, const double* xs, const double* ys, int64_t planes, int64_t h, int64_t w,
+                      int64_t h1, int64_t w1, int BW, int BH, cudaStream_t st) {
+  constexpr int TH = 8 * RW;
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return 1;
+  alignas(64) CUtensorMap tmap;
+  const cuuint64_t gdim[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)planes};
+  const cuuint64_t gstr[2] = {(cuuint64_t)w * sizeof(TS), (cuuint64_t)w * h * sizeof(TS)};
+  const cuuint32_t box[3] = {(cuuint32_t)BW, (cuuint32_t)BH, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  if (enc(&tmap, TmaType<TS>::v, 3, const_cast<void*>(src), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return 1;
+  const int stage_bytes = (int)ceil_div((int64_t)BW * BH * sizeof(TS), 128) * 128;
+  const int smem = kTmaStages * stage_bytes + kTmaStages * 8;
+  auto kern = rect2hex_bilinear_tma_kernel<TS, TD, EXACT, RW>;
+  static thread_local int configured_smem = 0;
+  if (smem > configured_smem) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) { cudaGetLastError(); return 1; }
+    configured_smem = smem;
+  }
+  if (g_sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTmaThreads, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); return 1; }
+  const int tiles_x = (int)ceil_div(w1, kTW), tiles_y = (int)ceil_div(h1, TH);
+  const long long total = (long long)tiles_x * tiles_y * planes;
+  long long grid = (long long)g_sm_count * occ;
+  if (grid > total) grid = total;
+  const long long per = (total + grid - 1) / grid;
+  grid = (total + per - 1) / per;
+  kern<<<(unsigned)grid, kTmaThreads, smem, st>>>(tmap, (TD*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, tiles_x, (int)planes,
+                                                   total, per, BW, BH, stage_bytes);
+  return finish_launch("rect2hex_bilinear_tma");
+}
+
+// Returns HG_OK when the tiled kernel was launched, 1 when it does not apply (caller falls back to the
+// direct gather), or an error code.
+int try_rect2hex_bilinear_tma(const void* src, void* dst, const double* xs, const double* ys, const double* host_xs,
+                              const double* host_ys, int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1, int sdt,
+                              int ddt, int math, cudaStream_t st) {
+  if (!host_xs || !host_ys || sdt != HG_F32 || ddt != HG_F32) return 1;
+  if ((w * 4) % 16 != 0 || (reinterpret_cast<uintptr_t>(src) & 15) != 0 || planes >= (1ll << 31)) return 1;
+  static const int rows_per_warp = [] { const char* e = getenv("HG_R2H_ROWS"); return e ? atoi(e) : 4; }();
+  if (rows_per_warp == 0) return 1;              // HG_R2H_ROWS=0 forces the direct kernel (A/B measurements)
+  const int RW = rows_per_warp == 8 ? 8 : 4;
+  const int TH = 8 * RW;
+  const int span_r = axis_span(host_xs, h1, h, TH), span_c = axis_span(host_ys, w1, w, kTW);
+  if (span_r < 0 || span_c < 0) return 1;
+  const int BH = span_r, BW = (span_c + 3) / 4 * 4;
+  if (BH > 256 || BW > 256) return 1;
+  // staging pays off while the footprint is close to the tile (every staged byte is used ~4 times);
+  // for strong down-sampling the direct gather already runs at the HBM roofline.
+  if ((int64_t)BH * BW > (int64_t)2 * TH * kTW) return 1;
+  if (math == HG_MATH_EXACT)
+    return RW == 8 ? launch_tma<float, float, true, 8>(src, dst, xs, ys, planes, h, w, h1, w1, BW, BH, st)
+                   : launch_tma<float, float, true, 4>(src, dst, xs, ys, planes, h, w, h1, w1, BW, BH, st);
+  return RW == 8 ? launch_tma<float, float, false, 8>(src, dst, xs, ys, planes, h, w, h1, w1, BW, BH, st)
+                 : launch_tma<float, float, false, 4>(src, dst, xs, ys, planes, h, w, h1, w1, BW, BH, st);
+}
+
+}  // namespace hg

@@ -85,9 +85,12 @@ int hg_rect2hex_nearest(const void* src, void* dst, const double* xs, const doub
                         int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1,
                         int elem_size, hg_stream_t stream);
 /* ref: geometry_np.py:358-519 rect_to_hex_resample(..., 'bilinear') (blend :514-517).
- * src_dtype in {HG_U8, HG_F32, HG_F64}, dst_dtype in {HG_F32, HG_F64}. */
+ * src_dtype in {HG_U8, HG_F32, HG_F64}, dst_dtype in {HG_F32, HG_F64}.
+ * host_xs / host_ys (may be NULL): HOST copies of the same tables.  With them the library sizes the
+ * source footprint of an output tile and, when the two lattices have similar pitch (float32 in/out),
+ * runs the TMA-staged tile kernel instead of the direct gather; results are identical. */
 int hg_rect2hex_bilinear(const void* src, void* dst, const double* xs, const double* ys,
-                         int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1,
+                         const double* host_xs, const double* host_ys, int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1,
                          int src_dtype, int dst_dtype, int math, hg_stream_t stream);
 
 /* ref: geometry_torch.py:191-358 hex_to_square_resample / geometry_np.py:191-356

@@ -44,7 +44,7 @@ def test_version_and_error_string():
     L = nv.lib()
     assert L.hg_version() == 100
     # invalid arguments are rejected before any CUDA call: safe without a GPU
-    rc = L.hg_rect2hex_bilinear(None, None, None, None, 1, 0, 4, 4, 4, nv.F32, nv.F32, 0, None)
+    rc = L.hg_rect2hex_bilinear(None, None, None, None, None, None, 1, 0, 4, 4, 4, nv.F32, nv.F32, 0, None)
     assert rc == -3 and b"bad shape" in L.hg_last_error()
     rc = L.hg_hexconv_out_shape(2, 2, 2, 1, 1, 0, C.byref(C.c_int64()), C.byref(C.c_int64()))
     assert rc == -3 and b"too small" in L.hg_last_error()

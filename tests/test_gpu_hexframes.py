@@ -169,7 +169,7 @@ def test_hexpool_vs_oracle_with_nans(hf, method, dtype):
     x = torch.randn(3, 5, 66, 75).to(dtype)
     x[torch.rand_like(x.float()) < 0.15] = float("nan")
     x[0, 0, :4, :8] = float("nan")                       # whole windows of NaN
-    for (k, s, pad, ceil, cip) in ((2, 2, 0, False, True), (3, 2, 1, False, True), (2, 2, 0, True, False), ((2, 3), (2, 4), 2, True, True)):
+    for (k, s, pad, ceil, cip) in ((2, 2, 0, False, True), ((3, 2), (2, 2), 1, False, True), (2, 2, 0, True, False), ((2, 3), (2, 4), 2, True, True)):
         xr = x.clone().requires_grad_()
         ref = HO.hexpool2d(xr, method, k, s, pad, ceil_mode=ceil, count_include_pad=cip)
         xg = x.cuda().requires_grad_()
