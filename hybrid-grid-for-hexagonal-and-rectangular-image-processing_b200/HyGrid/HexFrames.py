@@ -125,14 +125,18 @@ class _HexConvFn(torch.autograd.Function):
         gy = gy.to(y_dtype).contiguous()
         d = _conv_desc(x, w.shape[0], Ho, Wo, radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, 0)
         st = nv.stream_ptr(x.device)
+
+        def pick(op):   # a forced tcgen05 forward does not oblige the backward ops to have a tcgen05 kernel
+            d.algo = algo if (algo != 2 or nv.query("hg_hexconv_umma_eligible", C.byref(d), op)) else 1
+            return d
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)
-            nv.call("hg_hexconv_dgrad", C.byref(d), nv.ptr(gy), nv.ptr(w), nv.ptr(gx), st)
+            nv.call("hg_hexconv_dgrad", C.byref(pick(1)), nv.ptr(gy), nv.ptr(w), nv.ptr(gx), st)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             gw = torch.zeros_like(w)
             gb = torch.zeros(w.shape[0], dtype=torch.float32, device=x.device) if ctx.has_bias else None
-            nv.call("hg_hexconv_wgrad", C.byref(d), nv.ptr(x), nv.ptr(gy), nv.ptr(gw), nv.ptr(gb), st)
+            nv.call("hg_hexconv_wgrad", C.byref(pick(2)), nv.ptr(x), nv.ptr(gy), nv.ptr(gw), nv.ptr(gb), st)
             gw = gw.to(ctx.param_dtypes[0])
             if gb is not None:
                 gb = gb.to(ctx.param_dtypes[1])
@@ -203,21 +207,40 @@ class HexConv2d(nn.Module):
                 bound = 1 / math.sqrt(fan_in)
                 init.uniform_(self.bias, -bound, bound)
 
+    def _tensor_core_ok(self, input: Tensor) -> bool:
+        """Would the tcgen05 kernel take this layer?  Then fp32 activations are fed to it directly (it rounds
+        them to bfloat16 on the way into shared memory) instead of paying a separate cast pass."""
+        x = _as4(input)
+        if x.dtype not in (torch.float32, torch.bfloat16) or self.padding_mode != 'constant' or x.dim() != 4:
+            return False
+        try:
+            Ho, Wo = _conv_out_shape(x.shape[2], x.shape[3], self.hexkernel_radius, self.stride, self.dilation, self.pad)
+        except ValueError:
+            return False
+        d = _conv_desc(x, self.out_channels, Ho, Wo, self.hexkernel_radius, self.stride, self.dilation, self.groups,
+                       self.pad, self.padded_even_odd_offset, 0.0, self.out_dtype, 2, 0)
+        return bool(nv.query("hg_hexconv_umma_eligible", C.byref(d), 0))
+
     def _activation(self, input: Tensor) -> Tensor:
         if torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16:
+            if self.algo != 1 and self._tensor_core_ok(input):
+                self._autocast_tc = True
+                return input if input.dtype in (torch.float32, torch.bfloat16) else input.float()
             return input.to(torch.bfloat16)
         if self.kernel.dtype not in (torch.float32, torch.bfloat16):
             raise TypeError(f"HexConv2d parameters must be float32 (or bfloat16), got {self.kernel.dtype}")
         return input.to(self.kernel.dtype)
 
     def forward(self, input: Tensor, relu: bool = False) -> Tensor:
+        self._autocast_tc = False
         input = _as4(self._activation(input))
+        algo = 2 if self._autocast_tc else self.algo
         pad_, parity = self.pad, self.padded_even_odd_offset
         if self.pad and self.padding_mode != 'constant':
             input = pad(input, self.pad, self.padding_mode, self.padding_value)
             pad_ = 0
         meta = (self.hexkernel_radius, self.stride, self.dilation, self.groups, pad_, parity,
-                float(self.padding_value or 0), self.out_dtype, self.algo, bool(relu))
+                float(self.padding_value or 0), self.out_dtype, algo, bool(relu))
         return _HexConvFn.apply(input, self.kernel, self.bias, meta)
 
     def extra_repr(self):

@@ -61,6 +61,7 @@ _SIGS = {
     "hg_hexglobalpool_fwd": [_p, _p, _p, _l, _l, _i, _i, _p],
     "hg_hexglobalpool_bwd": [_p, _p, _p, _p, _l, _l, _i, _i, _p],
     "hg_hexconv_out_shape": [_l, _l, _i, _i, _i, _i, C.POINTER(_l), C.POINTER(_l)],
+    "hg_hexconv_umma_eligible": [C.POINTER(ConvDesc), _i],
     "hg_hexconv_fwd": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],
     "hg_hexconv_dgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p],
     "hg_hexconv_wgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],
@@ -93,6 +94,11 @@ def lib():
             fn.restype = C.c_int
         _lib = L
     return _lib
+
+
+def query(name, *args) -> int:
+    """Call an entry point whose return value is an answer, not a status."""
+    return int(getattr(lib(), name)(*args))
 
 
 def call(name, *args):

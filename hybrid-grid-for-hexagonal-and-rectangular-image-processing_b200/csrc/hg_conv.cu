@@ -68,6 +68,14 @@ int hg_hexconv_out_shape(int64_t H, int64_t W, int radius, int stride, int dilat
   return HG_OK;
 }
 
+int hg_hexconv_umma_eligible(const hg_conv_desc* d, int op) {
+  ConvGeom g; ConvTaps tp;
+  if (d == nullptr || op < 0 || op > 2 || make_geom(d, g, tp) != HG_OK) return 0;
+  hg_conv_desc forced = *d;
+  forced.algo = 2;
+  return conv_umma_eligible(&forced, op) ? 1 : 0;
+}
+
 int hg_hexconv_fwd(const hg_conv_desc* d, const void* x, const float* w, const float* bias, void* y, hg_stream_t stream) {
   ConvGeom g; ConvTaps tp;
   int rc = make_geom(d, g, tp);

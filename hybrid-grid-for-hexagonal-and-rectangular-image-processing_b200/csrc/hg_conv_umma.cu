@@ -1,19 +1,364 @@
-// hg_conv_umma.cu -- tcgen05 / TMEM implicit-GEMM hex convolution (placeholder until the kernel lands:
-// reports "not eligible", so hg_conv.cu routes everything to the direct stencil).
+// hg_conv_umma.cu -- 7-tap hex convolution (radius 2, stride 1, dilation 1) as an implicit GEMM on the
+// 5th-generation tensor cores: tcgen05.mma with the accumulator in TMEM (sm_100a).  Forward and data
+// gradient share one kernel (the data gradient is the same 3-row stencil with transposed weights and
+// mirrored tap offsets).  ref: HexFrames.py:96-169; geometry in hg_conv.cuh.
+//
+// GEMM view, per output row segment of 128 pixels:   D[128 px, Nout] = sum over 7 taps
+//        A_tap[128 px, Cred] * B_tap[Cred, Nout]      (bf16 x bf16 -> fp32 in TMEM)
+// A_tap is a *shifted view* of an input row kept in shared memory: input rows are stored K-major without
+// swizzle as [Cred/8][PW pixels][8 channels] (one 16-byte core-matrix row per pixel), so that moving the
+// UMMA descriptor start address by 16 bytes moves the view by exactly one pixel.  One input row is
+// therefore fetched from HBM once, converted fp32 -> bf16 once, and serves all 7 taps of the three output
+// rows that touch it.  NCHW activations are read with plain coalesced loads (lanes along the row) -- the
+// [pixel][channel] transposition TMA cannot do happens in registers on the way to shared memory.
+//
+// Persistent CTA = 13 warps:  warps 0-7 loaders (global -> bf16 -> smem ring of input rows),
+//                             warps 8-11 epilogue (TMEM -> registers -> bias/ReLU -> coalesced NCHW stores),
+//                             warp 12 MMA issuer (one lane) + TMEM allocator.
+// Pipelines: full/empty mbarriers per ring slot (loaders <-> MMA, slots released by tcgen05.commit),
+//            tmem_full/tmem_empty per accumulator stage (MMA <-> epilogue), 2 accumulator stages.
 #include "hg_conv.cuh"
+#include "hg_ptx.cuh"
 
 namespace hg {
-bool conv_umma_eligible(const hg_conv_desc*, int) { return false; }
-int conv_fwd_umma(const hg_conv_desc*, const ConvGeom&, const ConvTaps&, const void*, const float*, const float*, void*, cudaStream_t) {
-  set_error("tcgen05 path not built");
-  return HG_E_UNSUPPORTED;
+
+constexpr int kUmTile = 128;                 // output pixels per MMA (UMMA M)
+constexpr int kUmPW = 136;                   // pixels per ring slot (tile + halo, multiple of 8)
+constexpr int kUmLoaders = 256;
+constexpr int kUmThreads = kUmLoaders + 128 + 32;
+constexpr int kUmBand = 32;                  // output rows per work item
+constexpr int kUmMaxQ = 5;                   // ceil(8 * 136 / 256): (chunk, pixel) tasks per loader thread, Cred <= 64
+constexpr int kTaps = 7;
+
+struct UmmaParams {
+  int N, Cred, Nout, Hi, Wi, Ho, Wo;
+  int row0, col0;                // input row / col of (output 0,0) for row slot 0 / shift 0
+  int ra[kTaps];                 // row slot 0..2 of each tap
+  int sh[2][kTaps];              // column shift 0..3 of each tap, per output-row parity
+  int pad;                       // frame of pad_value around the input; literal zero beyond
+  float pad_value;
+  int relu, has_bias, transpose_w;   // transpose_w: weights indexed [red][out] (dgrad)
+  int slots, bands, ctiles;
+  long long items;
+};
+
+template <typename T> __device__ __forceinline__ float ld_in(const T* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ld_in<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(__ldg(p)); }
+template <typename T> __device__ __forceinline__ void st_out(T* p, float v) { __stcs(p, v); }
+template <> __device__ __forceinline__ void st_out<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
 }
-int conv_dgrad_umma(const hg_conv_desc*, const ConvGeom&, const ConvTaps&, const void*, const float*, void*, cudaStream_t) {
-  set_error("tcgen05 path not built");
-  return HG_E_UNSUPPORTED;
+
+template <typename TIN, typename TOUT>
+__global__ void __launch_bounds__(kUmThreads, 1)
+hexconv_umma_kernel(const TIN* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                    TOUT* __restrict__ out, UmmaParams P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkc = P.Cred >> 3;
+  const int slot_bytes = P.Cred * kUmPW * 2;
+  const int wtap_bytes = P.Cred * P.Nout * 2;
+  unsigned char* w_smem = smem;                                   // [tap][Cred/8][Nout][8] bf16
+  unsigned char* ring = smem + kTaps * wtap_bytes;                // [slot][Cred/8][PW][8] bf16
+  float* bias_s = reinterpret_cast<float*>(ring + P.slots * slot_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + P.Nout);
+  uint64_t* full = bars;                    // [slots]  loaders -> MMA        (count kUmLoaders)
+  uint64_t* empty = bars + P.slots;         // [slots]  MMA commit -> loaders (count 1)
+  uint64_t* tfull = empty + P.slots;        // [2]      MMA commit -> epilogue
+  uint64_t* tempty = tfull + 2;             // [2]      epilogue -> MMA       (count 128)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  // ---- one-time setup ---------------------------------------------------------------------------------
+  // weights: fp32 [Cout][Cin][1][7] in global -> bf16 UMMA B image in shared memory
+  {
+    const int per_tap = P.Cred * P.Nout;
+    for (int e = tid; e < kTaps * per_tap; e += kUmThreads) {
+      const int k = e / per_tap, r = e - k * per_tap;
+      const int kc = r / (P.Nout * 8), r2 = r - kc * P.Nout * 8;
+      const int n = r2 >> 3, j = r2 & 7;
+      const int red = kc * 8 + j;
+      const float v = P.transpose_w ? __ldg(w + ((size_t)red * P.Nout + n) * kTaps + k)      // w[co=red][ci=n][k]
+                                    : __ldg(w + ((size_t)n * P.Cred + red) * kTaps + k);     // w[co=n][ci=red][k]
+      reinterpret_cast<__nv_bfloat16*>(w_smem)[e] = __float2bfloat16_rn(v);
+    }
+    for (int e = tid; e < P.Nout; e += kUmThreads) bias_s[e] = P.has_bias ? __ldg(bias + e) : 0.f;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < P.slots; ++s) { ptx::mbar_init(&full[s], kUmLoaders); ptx::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull[s], 1); ptx::mbar_init(&tempty[s], 128); }
+    ptx::fence_barrier_init();
+  }
+  const uint32_t tmem_cols = 2 * P.Nout <= 32 ? 32 : 2 * P.Nout <= 64 ? 64 : 2 * P.Nout <= 128 ? 128 : 2 * P.Nout <= 256 ? 256 : 512;
+  if (warp == 12) { ptx::tmem_alloc(tmem_slot, tmem_cols); ptx::tmem_relinquish(); }
+  ptx::fence_proxy_async_smem();            // weight image written by the generic proxy, read by tcgen05.mma
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int per_n = P.bands * P.ctiles;
+
+  if (warp < 8) {
+    // ===== loaders ========================================================================================
+    const int ntasks = nkc * kUmPW;
+    const size_t plane = (size_t)P.Hi * P.Wi;
+    long long lt = 0;                        // input rows produced so far (ring position)
+    for (long long item = blockIdx.x; item < P.items; item += gridDim.x) {
+      const int n = (int)(item / per_n);
+      const int rem = (int)(item - (long long)n * per_n);
+      const int band = rem / P.ctiles, ct = rem - band * P.ctiles;
+      const int r0 = band * kUmBand, rows = min(kUmBand, P.Ho - r0), c0 = ct * kUmTile;
+      const TIN* __restrict__ in_n = in + (size_t)n * P.Cred * plane;
+      for (int t = 0; t < rows + 2; ++t, ++lt) {
+        const int slot = (int)(lt % P.slots);
+        const uint32_t use = (uint32_t)(lt / P.slots);
+        ptx::mbar_wait(&empty[slot], (use & 1) ^ 1);
+        const int i = r0 + P.row0 + t;
+        const bool row_in = i >= 0 && i < P.Hi;
+        const bool row_frame = i >= -P.pad && i < P.Hi + P.pad;
+        unsigned char* sb = ring + (size_t)slot * slot_bytes;
+        float v[kUmMaxQ][8];
+#pragma unroll
+        for (int q = 0; q < kUmMaxQ; ++q) {
+          const int task = tid + q * kUmLoaders;
+          if (task < ntasks) {
+            const int kc = task / kUmPW, p = task - kc * kUmPW;
+            const int j = c0 + P.col0 + p;
+            const bool col_in = j >= 0 && j < P.Wi;
+            const float fill = (row_frame && j >= -P.pad && j < P.Wi + P.pad) ? P.pad_value : 0.f;
+            const TIN* __restrict__ src = in_n + (size_t)(kc * 8) * plane + (size_t)i * P.Wi + j;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[q][e] = (row_in && col_in) ? ld_in(src + (size_t)e * plane) : fill;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < kUmMaxQ; ++q) {
+          const int task = tid + q * kUmLoaders;
+          if (task < ntasks) {
+            uint4 pk;
+            pk.x = pack_bf16(v[q][0], v[q][1]); pk.y = pack_bf16(v[q][2], v[q][3]);
+            pk.z = pack_bf16(v[q][4], v[q][5]); pk.w = pack_bf16(v[q][6], v[q][7]);
+            *reinterpret_cast<uint4*>(sb + (size_t)task * 16) = pk;      // task == kc * PW + p
+          }
+        }
+        ptx::fence_proxy_async_smem();       // generic-proxy smem writes -> visible to tcgen05.mma
+        ptx::mbar_arrive(&full[slot]);
+      }
+    }
+  } else if (warp < 12) {
+    // ===== epilogue ========================================================================================
+    const int q4 = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int px = q4 * 32 + lane;
+    long long at = 0;                        // output rows consumed so far (accumulator stage position)
+    for (long long item = blockIdx.x; item < P.items; item += gridDim.x) {
+      const int n = (int)(item / per_n);
+      const int rem = (int)(item - (long long)n * per_n);
+      const int band = rem / P.ctiles, ct = rem - band * P.ctiles;
+      const int r0 = band * kUmBand, rows = min(kUmBand, P.Ho - r0), c = ct * kUmTile + px;
+      for (int rr = 0; rr < rows; ++rr, ++at) {
+        const int acc = (int)(at & 1);
+        ptx::mbar_wait(&tfull[acc], (uint32_t)((at >> 1) & 1));
+        ptx::tc_fence_after_sync();
+        TOUT* __restrict__ op = out + (((size_t)n * P.Nout) * P.Ho + (r0 + rr)) * P.Wo + c;
+        const size_t cstride = (size_t)P.Ho * P.Wo;
+        for (int cb = 0; cb < P.Nout; cb += 32) {
+          uint32_t v[32];
+          ptx::tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * P.Nout + cb), v);
+          ptx::tmem_ld_wait();
+          if (cb + 32 >= P.Nout) {           // last chunk read: hand the accumulator back to the MMA warp
+            ptx::tc_fence_before_sync();
+            ptx::mbar_arrive(&tempty[acc]);
+          }
+          if (c < P.Wo) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (cb + j < P.Nout) {
+                float f = __uint_as_float(v[j]) + bias_s[cb + j];
+                if (P.relu) f = fmaxf(f, 0.f);
+                st_out(op + (size_t)(cb + j) * cstride, f);
+              }
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ===== MMA issuer ======================================================================================
+    const uint32_t idesc = ptx::umma_idesc_bf16(kUmTile, P.Nout);
+    const uint32_t ring_addr = ptx::smem_u32(ring), w_addr = ptx::smem_u32(w_smem);
+    const uint32_t lbo_a = kUmPW * 16, lbo_b = (uint32_t)P.Nout * 16;
+    long long mt = 0, at = 0;                // ring position of the band's first input row; accumulator position
+    for (long long item = blockIdx.x; item < P.items; item += gridDim.x) {
+      const int rem = (int)(item % per_n);
+      const int band = rem / P.ctiles;
+      const int r0 = band * kUmBand, rows = min(kUmBand, P.Ho - r0);
+      for (int rr = 0; rr < rows; ++rr, ++at) {
+        const int acc = (int)(at & 1);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const long long lt = mt + rr + d;
+          ptx::mbar_wait(&full[lt % P.slots], (uint32_t)((lt / P.slots) & 1));
+        }
+        ptx::mbar_wait(&tempty[acc], (uint32_t)(((at >> 1) & 1) ^ 1));
+        ptx::tc_fence_after_sync();
+        if (lane == 0) {
+          const int par = (r0 + rr) & 1;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.Nout);
+          uint32_t accum = 0;
+          for (int k = 0; k < kTaps; ++k) {
+            const long long lt = mt + rr + P.ra[k];
+            const uint32_t a0 = ring_addr + (uint32_t)(lt % P.slots) * (uint32_t)slot_bytes + (uint32_t)P.sh[par][k] * 16u;
+            const uint32_t b0 = w_addr + (uint32_t)k * (uint32_t)wtap_bytes;
+            for (int j = 0; j < (P.Cred >> 4); ++j) {
+              const uint64_t ad = ptx::umma_desc_kmajor_noswizzle(a0 + (uint32_t)j * 2u * lbo_a, lbo_a, 128);
+              const uint64_t bd = ptx::umma_desc_kmajor_noswizzle(b0 + (uint32_t)j * 2u * lbo_b, lbo_b, 128);
+              ptx::umma_bf16(d_tmem, ad, bd, idesc, accum);
+              accum = 1;
+            }
+          }
+          ptx::umma_commit(&tfull[acc]);                         // accumulator ready for the epilogue
+          ptx::umma_commit(&empty[(mt + rr) % P.slots]);         // input row rr is not needed any more
+          if (rr == rows - 1) {                                  // band done: release its two trailing rows too
+            ptx::umma_commit(&empty[(mt + rows) % P.slots]);
+            ptx::umma_commit(&empty[(mt + rows + 1) % P.slots]);
+          }
+        }
+        __syncwarp();
+      }
+      mt += rows + 2;
+    }
+  }
+
+  // ---- teardown ---------------------------------------------------------------------------------------------
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 12) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, tmem_cols);
+  }
 }
+
+// ---- host side --------------------------------------------------------------------------------------------
+static int g_um_sms = 0, g_um_smem_max = 0;
+
+static size_t umma_smem_bytes(int Cred, int Nout, int slots) {
+  return (size_t)kTaps * Cred * Nout * 2 + (size_t)slots * Cred * kUmPW * 2 + (size_t)Nout * 4 + (size_t)(2 * slots + 4) * 8 + 16;
+}
+
+static int umma_pick_slots(int Cred, int Nout) {
+  if (g_um_smem_max == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_um_smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&g_um_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaGetLastError() != cudaSuccess || g_um_smem_max <= 0) { g_um_smem_max = 0; return 0; }
+  }
+  for (int s = 6; s >= 4; --s)
+    if (umma_smem_bytes(Cred, Nout, s) <= (size_t)g_um_smem_max) return s;
+  return 0;
+}
+
+// op: 0 forward (reduce over Cin), 1 dgrad (reduce over Cout), 2 wgrad (not covered)
+bool conv_umma_eligible(const hg_conv_desc* d, int op) {
+  if (op == 2) return false;
+  if (d->radius != 2 || d->stride != 1 || d->dilation != 1 || d->groups != 1) return false;
+  const int64_t Cred = op == 0 ? d->Cin : d->Cout, Nout = op == 0 ? d->Cout : d->Cin;
+  if (Cred % 16 != 0 || Cred < 16 || Cred > 64) return false;
+  if (Nout % 16 != 0 || Nout < 16 || Nout > 256) return false;
+  if (op == 1 && d->relu) return false;
+  // auto: bf16 activations only (fp32 callers keep fp32 accuracy on the direct stencil) and only when the
+  // channel contraction is dense enough to feed a 128 x Nout x Cred tile
+  if (d->algo == 0 && ((op == 0 ? d->x_dtype : d->y_dtype) != HG_BF16 || Cred * Nout < 32 * 32)) return false;
+  return umma_pick_slots((int)Cred, (int)Nout) > 0;
+}
+
+template <typename TIN, typename TOUT>
+static int launch_umma(const void* in, const float* w, const float* bias, void* out, const UmmaParams& P, cudaStream_t st) {
+  const size_t smem = umma_smem_bytes(P.Cred, P.Nout, P.slots);
+  auto kern = hexconv_umma_kernel<TIN, TOUT>;
+  static thread_local size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("hexconv_umma: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e)); return (int)e; }
+    configured = smem;
+  }
+  long long grid = g_um_sms > 0 ? g_um_sms : 148;
+  if (grid > P.items) grid = P.items;
+  kern<<<(unsigned)grid, kUmThreads, smem, st>>>((const TIN*)in, w, bias, (TOUT*)out, P);
+  return finish_launch("hexconv_umma");
+}
+
+static int dispatch_umma(int in_dt, int out_dt, const void* in, const float* w, const float* bias, void* out, const UmmaParams& P,
+                         cudaStream_t st) {
+  if (in_dt == HG_F32 && out_dt == HG_F32) return launch_umma<float, float>(in, w, bias, out, P, st);
+  if (in_dt == HG_BF16 && out_dt == HG_F32) return launch_umma<__nv_bfloat16, float>(in, w, bias, out, P, st);
+  if (in_dt == HG_F32 && out_dt == HG_BF16) return launch_umma<float, __nv_bfloat16>(in, w, bias, out, P, st);
+  if (in_dt == HG_BF16 && out_dt == HG_BF16) return launch_umma<__nv_bfloat16, __nv_bfloat16>(in, w, bias, out, P, st);
+  set_error("hexconv_umma: unsupported dtypes in=%d out=%d", in_dt, out_dt);
+  return HG_E_DTYPE;
+}
+
+static void umma_common(UmmaParams& P, int Ho, int Wo, int N) {
+  P.N = N; P.Ho = Ho; P.Wo = Wo;
+  P.bands = (int)ceil_div(Ho, kUmBand);
+  P.ctiles = (int)ceil_div(Wo, kUmTile);
+  P.items = (long long)N * P.bands * P.ctiles;
+  P.slots = umma_pick_slots(P.Cred, P.Nout);
+}
+
+int conv_fwd_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp, const void* x, const float* w, const float* bias,
+                  void* y, cudaStream_t st) {
+  UmmaParams P{};
+  P.Cred = g.Cin; P.Nout = g.Cout; P.Hi = g.H; P.Wi = g.W;
+  int cmin = 1 << 30, cmax = -(1 << 30);
+  for (int par = 0; par < 2; ++par)
+    for (int k = 0; k < kTaps; ++k) { cmin = min(cmin, tp.co[par][k]); cmax = max(cmax, tp.co[par][k]); }
+  HG_REQUIRE(tp.K == kTaps && cmax - cmin <= kUmPW - kUmTile, HG_E_UNSUPPORTED, "hexconv_umma: unexpected tap geometry");
+  for (int k = 0; k < kTaps; ++k) {
+    P.ra[k] = tp.ro[k];
+    for (int par = 0; par < 2; ++par) P.sh[par][k] = tp.co[par][k] - cmin;
+  }
+  P.row0 = -g.pad; P.col0 = cmin - g.pad;
+  P.pad = g.pad; P.pad_value = g.pad_value;
+  P.relu = g.relu; P.has_bias = bias != nullptr; P.transpose_w = 0;
+  umma_common(P, g.Ho, g.Wo, g.N);
+  HG_REQUIRE(P.slots > 0, HG_E_UNSUPPORTED, "hexconv_umma: shared memory does not fit");
+  return dispatch_umma(d->x_dtype, d->y_dtype, x, w, bias, y, P, st);
+}
+
+// gx[n,ci,i,j] = sum_{co,k} w[co,ci,k] * gy[n,co, i + pad - ro[k], j + pad - co[(i + pad - ro[k]) & 1][k]]   (zero outside)
+int conv_dgrad_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp, const void* gy, const float* w, void* gx,
+                    cudaStream_t st) {
+  UmmaParams P{};
+  P.Cred = g.Cout; P.Nout = g.Cin; P.Hi = g.Ho; P.Wi = g.Wo;
+  int cs[2][kTaps];
+  int cmin = 1 << 30, cmax = -(1 << 30);
+  HG_REQUIRE(tp.K == kTaps, HG_E_UNSUPPORTED, "hexconv_umma: unexpected tap geometry");
+  for (int ipar = 0; ipar < 2; ++ipar)
+    for (int k = 0; k < kTaps; ++k) {
+      const int rpar = (ipar + g.pad - tp.ro[k]) & 1;           // parity of the gy row this tap reads
+      cs[ipar][k] = g.pad - tp.co[rpar][k];
+      cmin = min(cmin, cs[ipar][k]); cmax = max(cmax, cs[ipar][k]);
+    }
+  HG_REQUIRE(cmax - cmin <= kUmPW - kUmTile, HG_E_UNSUPPORTED, "hexconv_umma: unexpected tap geometry");
+  for (int k = 0; k < kTaps; ++k) {
+    P.ra[k] = 2 - tp.ro[k];
+    for (int ipar = 0; ipar < 2; ++ipar) P.sh[ipar][k] = cs[ipar][k] - cmin;
+  }
+  P.row0 = g.pad - 2; P.col0 = cmin;
+  P.pad = 0; P.pad_value = 0.f;
+  P.relu = 0; P.has_bias = 0; P.transpose_w = 1;
+  umma_common(P, g.H, g.W, g.N);
+  HG_REQUIRE(P.slots > 0, HG_E_UNSUPPORTED, "hexconv_umma: shared memory does not fit");
+  return dispatch_umma(d->y_dtype, d->x_dtype, gy, w, nullptr, gx, P, st);
+}
+
 int conv_wgrad_umma(const hg_conv_desc*, const ConvGeom&, const ConvTaps&, const void*, const void*, float*, float*, cudaStream_t) {
-  set_error("tcgen05 path not built");
+  set_error("hexconv wgrad has no tcgen05 path yet");
   return HG_E_UNSUPPORTED;
 }
+
 }  // namespace hg

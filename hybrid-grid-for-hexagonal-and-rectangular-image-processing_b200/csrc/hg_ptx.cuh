@@ -36,8 +36,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Spin on a phase.  HG_SPIN_LIMIT (default on) turns a pipeline deadlock into a trap after ~2^28 polls
+// instead of a hung GPU; a healthy wait takes a few polls.
+#ifndef HG_SPIN_LIMIT
+#define HG_SPIN_LIMIT (1u << 28)
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (HG_SPIN_LIMIT && ++spins > HG_SPIN_LIMIT) __trap();
   }
 }
 

@@ -190,6 +190,11 @@ typedef struct hg_conv_desc {
 
 int hg_hexconv_out_shape(int64_t H, int64_t W, int radius, int stride, int dilation, int pad,
                          int64_t* Ho, int64_t* Wo);
+/* 1 when the tcgen05 / TMEM implicit-GEMM kernel covers this configuration for op (0 forward, 1 data
+ * gradient, 2 weight gradient): radius 2, stride 1, dilation 1, groups 1, reduction channels in
+ * {16,32,48,64}, output channels a multiple of 16 up to 256.  algo = 0 picks it by itself only for
+ * bfloat16 activations (it rounds activations and weights to bfloat16, fp32 accumulation). */
+int hg_hexconv_umma_eligible(const hg_conv_desc* d, int op);
 int hg_hexconv_fwd(const hg_conv_desc* d, const void* x, const float* w, const float* bias, void* y,
                    hg_stream_t stream);
 /* gx [N,Cin,H,W] fully written.  gy has y_dtype, gx has x_dtype. */

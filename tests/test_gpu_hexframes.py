@@ -234,3 +234,61 @@ def test_reductions_and_converters(hf, hexframes_golden, resample_golden):
     (hf.heximage_to_type2(x, 1) * g.cuda()).sum().backward()
     (HO.heximage_to_type2(xr, 1) * g).sum().backward()
     assert torch.allclose(x.grad.cpu(), xr.grad, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 / TMEM implicit-GEMM path (algo=2): compared with the oracle evaluated on the SAME bf16-rounded
+# operands, so the only difference left is the fp32 summation order -> 1e-4, which pins the tap geometry,
+# the shifted shared-memory views and the TMEM epilogue exactly.
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [
+    # N, Cin, Cout, H, W, pad, off, x dtype
+    (2, 64, 64, 70, 300, 1, 0, torch.float32),
+    (1, 64, 64, 33, 128, 1, 1, torch.bfloat16),
+    (2, 32, 32, 40, 150, 0, 0, torch.float32),
+    (1, 16, 48, 37, 131, 2, 1, torch.float32),
+    (1, 64, 128, 20, 260, 1, 0, torch.bfloat16),
+    (1, 48, 16, 65, 64, 1, 1, torch.float32),
+])
+def test_hexconv_tcgen05_vs_oracle(hf, cfg):
+    N, Cin, Cout, H, W, pad, off, xdt = cfg
+    torch.manual_seed(3)
+    xq = torch.randn(N, Cin, H, W).bfloat16().float()
+    wq = (torch.randn(Cout, Cin, 1, 7) * 0.1).bfloat16().float()
+    b = torch.randn(Cout)
+    xr, wr = xq.clone().requires_grad_(), wq.clone().requires_grad_()
+    ref = HO.hexconv2d(xr, wr, b, off, 2, 1, pad, 1, 1, padding_value=0.25)
+    gyq = torch.randn_like(ref).bfloat16().float()
+    (ref * gyq).sum().backward()
+    xg = xq.to(xdt).cuda().requires_grad_()
+    wg = wq.cuda().requires_grad_()
+    y = hf.hexconv2d(xg, wg, b.cuda(), off, 2, 1, pad, 1, 1, padding_value=0.25, algo=2)
+    assert y.shape == ref.shape and y.dtype == torch.float32
+    scale = float(ref.detach().abs().max())
+    assert float((y.detach().cpu() - ref.detach()).abs().max()) <= 1e-4 * scale
+    (y * gyq.cuda()).sum().backward()          # dgrad on tcgen05 (gy is rounded to bf16 in the loader), wgrad direct
+    gscale = float(xr.grad.abs().max())
+    assert float((xg.grad.float().cpu() - xr.grad).abs().max()) <= (1e-4 if xdt == torch.float32 else 1e-2) * gscale
+    assert float((wg.grad.cpu() - wr.grad).abs().max()) <= 1e-3 * float(wr.grad.abs().max())
+    # fused ReLU epilogue (inference)
+    with torch.no_grad():
+        yr = hf.hexconv2d(xg.detach(), wg.detach(), b.cuda(), off, 2, 1, pad, 1, 1, padding_value=0.25, algo=2, relu=True)
+    assert float((yr.cpu() - ref.detach().clamp_min(0)).abs().max()) <= 1e-4 * scale
+
+
+def test_hexconv_autocast_routes_to_tcgen05(hf):
+    from HyGrid import _native as nv
+    torch.manual_seed(4)
+    m = hf.HexConv2d(64, 64, 0, 2, padding=1).cuda()
+    x = torch.randn(2, 64, 48, 200, device="cuda", requires_grad=True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = m(x)
+    assert m._autocast_tc and y.dtype == torch.float32 and y.shape == x.shape
+    ref = HO.hexconv2d(x.detach().cpu().bfloat16().float(), m.kernel.detach().cpu().bfloat16().float(), m.bias.detach().cpu(), 0, 2, 1, 1)
+    assert float((y.detach().cpu() - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
+    y.sum().backward()
+    assert x.grad is not None and m.kernel.grad is not None and bool(torch.isfinite(x.grad).all())
+    # fp32 module call without autocast keeps fp32 accuracy (direct stencil)
+    y32 = m(x.detach())
+    ref32 = HO.hexconv2d(x.detach().cpu(), m.kernel.detach().cpu(), m.bias.detach().cpu(), 0, 2, 1, 1)
+    assert float((y32.cpu() - ref32).abs().max()) <= 1e-4 * float(ref32.abs().max())
