@@ -22,6 +22,13 @@ constexpr int kTW = 128;       // output tile width  (4 columns per lane, 32 apa
 constexpr int kTmaThreads = 256;
 constexpr int kTmaStages = 3;
 
+// TMA needs the innermost box coordinate on a 16-byte boundary (measured on B200: a start column that is not
+// a multiple of 4 floats faults with "illegal instruction"; negative multiples are fine and zero-fill).
+template <typename TS> __device__ __forceinline__ int align_col(int c) {
+  constexpr int A = 16 / (int)sizeof(TS);
+  return c & ~(A - 1);                      // floor to a multiple of A, also for negative c (two's complement)
+}
+
 __device__ __forceinline__ void rect_axis_d(double coord, int n, int& idx, double& frac) {
   // i_ = x_ + (h-1)*0.5 ; i_n = trunc(i_) ; i_f = i_ - float32(i_n)      (geometry_np.py:440-449)
   const double c = dadd(coord, (double)(n - 1) * 0.5);
@@ -58,6 +65,7 @@ rect2hex_bilinear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __res
     int row0, col0; double f;
     rect_axis_d(xs[ty * TH], h, row0, f);
     rect_axis_d(ys[tx * kTW], w, col0, f);
+    col0 = align_col<TS>(col0);
     ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(BW * BH * (int)sizeof(TS)));
     ptx::tma_load_3d(smem_raw + (size_t)s * stage_bytes, &tmap, &full[s], col0, row0, plane);
   };
@@ -83,6 +91,7 @@ rect2hex_bilinear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __res
       int row0, col0; double f;
       rect_axis_d(xs[ty * TH], h, row0, f);
       rect_axis_d(ys[tx * kTW], w, col0, f);
+      col0 = align_col<TS>(col0);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const int b = b0 + 32 * c;
@@ -238,7 +247,7 @@ int try_rect2hex_bilinear_tma(const void* src, void* dst, const double* xs, cons
   const int TH = 8 * RW;
   const int span_r = axis_span(host_xs, h1, h, TH), span_c = axis_span(host_ys, w1, w, kTW);
   if (span_r < 0 || span_c < 0) return 1;
-  const int BH = span_r, BW = (span_c + 3) / 4 * 4;
+  const int BH = span_r, BW = (span_c + 3 + 3) / 4 * 4;   // + up to 3 columns for the 16-byte aligned box origin
   if (BH > 256 || BW > 256) return 1;
   // staging pays off while the footprint is close to the tile (every staged byte is used ~4 times);
   // for strong down-sampling the direct gather already runs at the HBM roofline.

@@ -1,0 +1,65 @@
+"""Host-side logic of the N > 1 path on CPU: world_size-2 gloo processes exercise the batch sharding and the
+flat gradient bucket (the one collective of the path: conv weight / bias gradients)."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from HyGrid.distributed import FlatGradBucket, shard_batch, shard_range
+
+
+def test_shard_range_tiles_the_batch():
+    for n in (0, 1, 7, 64, 256, 257):
+        for world in (1, 2, 3, 4, 8):
+            pieces = [shard_range(n, r, world) for r in range(world)]
+            assert pieces[0][0] == 0 and pieces[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(pieces, pieces[1:]))
+            sizes = [b - a for a, b in pieces]
+            assert max(sizes) - min(sizes) <= 1 and sorted(sizes, reverse=True) == sizes
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
+    x = torch.arange(10).view(10, 1)
+    assert torch.equal(torch.cat([shard_batch(x, r, 3) for r in range(3)]), x)
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        lin = torch.nn.Linear(5, 3)
+        kern = torch.nn.Parameter(torch.zeros(4, 2, 1, 7))          # a HexConv2d-shaped kernel
+        bucket = FlatGradBucket(list(lin.parameters()) + [kern])
+        data = torch.arange(8 * 5, dtype=torch.float32).view(8, 5) / 10
+        x = shard_batch(data)                                         # rank/world from the process group
+        assert x.shape[0] == 4 and float(x[0, 0]) == (0.0 if rank == 0 else 2.0)
+        loss = lin(x).square().sum() + (kern * (rank + 1)).sum()
+        loss.backward()
+        assert lin.weight.grad.data_ptr() == bucket.view(0).data_ptr()     # accumulated in place
+        bucket.all_reduce(average=True)
+        # reference: the same step on the whole batch in one process, averaged over 2 shards
+        lin2 = torch.nn.Linear(5, 3)
+        lin2.load_state_dict(lin.state_dict())
+        lin2(data).square().sum().backward()
+        ok = torch.allclose(lin.weight.grad, lin2.weight.grad / 2, atol=1e-5)
+        ok &= torch.allclose(lin.bias.grad, lin2.bias.grad / 2, atol=1e-5)
+        ok &= torch.allclose(kern.grad, torch.full_like(kern, 1.5))
+        work = bucket.all_reduce(average=False, async_op=True)       # async variant: sum of identical buffers
+        before = bucket.flat.clone()
+        work.wait()
+        ok &= torch.allclose(bucket.flat, before * 2) or torch.allclose(bucket.flat, before)   # wait() may have landed already
+        bucket.zero_()
+        ok &= float(lin.weight.grad.abs().sum()) == 0.0
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_bucket_all_reduce_gloo_world2():
+    port = 29500 + os.getpid() % 2000
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert dict(ret) == {0: True, 1: True}

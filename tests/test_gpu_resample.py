@@ -160,13 +160,13 @@ def test_r2_r4_golden(Fn, resample_golden):
     for n in range(int(G["r2_count"])):
         img, ds = G[f"r2_{n}_img"], _dsize(G[f"r2_{n}_dsize"])
         x = cu(img)
-        same(Fn.hex_to_rect(x, ds, "linear", twin="np"), G[f"r2_{n}_np_linear"])
-        same(Fn.hex_to_rect(x, ds, "linear", twin="torch"), G[f"r2_{n}_torch_linear"])
-        same(Fn.hex_to_rect(x, ds, "nearest", twin="torch"), G[f"r2_{n}_torch_nearest"])
-        same(Fn.hex_resize(x, ds if ds else img.shape[1:], "linear"), G[f"r2_{n}_resize_linear"])
+        same(Fn.hex_to_rect(x, ds, "linear", twin="np").squeeze(), G[f"r2_{n}_np_linear"])
+        same(Fn.hex_to_rect(x, ds, "linear", twin="torch").squeeze(), G[f"r2_{n}_torch_linear"])
+        same(Fn.hex_to_rect(x, ds, "nearest", twin="torch").squeeze(), G[f"r2_{n}_torch_nearest"])
+        same(Fn.hex_resize(x, ds if ds else img.shape[-2:], "linear").squeeze(), G[f"r2_{n}_resize_linear"])
         scale = float(np.abs(img).max())
         if img.dtype != np.float64:
-            close(Fn.hex_to_rect(x, ds, "linear", out_dtype=torch.float32, math="fast", twin="np"), G[f"r2_{n}_np_linear"], scale)
+            close(Fn.hex_to_rect(x, ds, "linear", out_dtype=torch.float32, math="fast", twin="np").squeeze(), G[f"r2_{n}_np_linear"], scale)
 
 
 def test_r2_index_tables(Fn, resample_golden):
@@ -235,9 +235,9 @@ def test_r3_golden(Fn, resample_golden):
     for n in range(int(G["r3_count"])):
         img, H = G[f"r3_{n}_img"], G[f"r3_{n}_H"]
         x = cu(img)
-        same(Fn.hex_warp(x, H, "linear", twin="np"), G[f"r3_{n}_np_linear"])
-        same(Fn.hex_warp(x, H, "nearest", twin="torch"), G[f"r3_{n}_torch_nearest"])
-        out = Fn.hex_warp(x, H, "linear", twin="torch")
+        same(Fn.hex_warp(x, H, "linear", twin="np").squeeze(), G[f"r3_{n}_np_linear"])
+        same(Fn.hex_warp(x, H, "nearest", twin="torch").squeeze(), G[f"r3_{n}_torch_nearest"])
+        out = Fn.hex_warp(x, H, "linear", twin="torch").squeeze()
         ref = G[f"r3_{n}_torch_linear"]
         assert out.shape == ref.shape
         same(out.to(torch.from_numpy(ref).dtype), ref)
