@@ -12,22 +12,32 @@
 // rows that touch it.  NCHW activations are read with plain coalesced loads (lanes along the row) -- the
 // [pixel][channel] transposition TMA cannot do happens in registers on the way to shared memory.
 //
-// Persistent CTA = 13 warps:  warps 0-7 loaders (global -> bf16 -> smem ring of input rows),
+// Persistent CTA = 14 warps:  warps 0-7 loaders / converters (-> bf16 -> smem ring of input rows),
 //                             warps 8-11 epilogue (TMEM -> registers -> bias/ReLU -> coalesced NCHW stores),
-//                             warp 12 MMA issuer (one lane) + TMEM allocator.
-// Pipelines: full/empty mbarriers per ring slot (loaders <-> MMA, slots released by tcgen05.commit),
-//            tmem_full/tmem_empty per accumulator stage (MMA <-> epilogue), 2 accumulator stages.
+//                             warp 12 MMA issuer (one lane) + TMEM allocator,
+//                             warp 13 TMA producer (one lane; TMA variant only).
+// Two variants of the input path:
+//   TMA  : a 4-D tensor map over NCHW; one cp.async.bulk.tensor box [Cred][1 row][PW px] per input row lands
+//          in a raw staging ring (deep hardware prefetch, zero-fill of halo rows / columns for free); the
+//          converter warps read it conflict-free (lanes along pixels), pack 8 channels to 16 bytes, and
+//          write the K-major ring.  Needs pad_value == 0 and 16-byte aligned rows.
+//   LDG  : the same conversion straight from global memory with coalesced loads (any pad value / width).
+// Pipelines: raw full/empty (TMA <-> converters), full/empty per ring slot (converters <-> MMA, slots released
+//            by tcgen05.commit), tmem_full/tmem_empty per accumulator stage (MMA <-> epilogue).
 #include "hg_conv.cuh"
 #include "hg_ptx.cuh"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace hg {
 
 constexpr int kUmTile = 128;                 // output pixels per MMA (UMMA M)
-constexpr int kUmPW = 136;                   // pixels per ring slot (tile + halo, multiple of 8)
+constexpr int kUmPW = 144;                   // pixels per ring slot: tile + tap shifts (<= 3) + alignment slack (<= 7)
 constexpr int kUmLoaders = 256;
-constexpr int kUmThreads = kUmLoaders + 128 + 32;
+constexpr int kUmThreads = kUmLoaders + 128 + 32 + 32;
 constexpr int kUmBand = 32;                  // output rows per work item
-constexpr int kUmMaxQ = 5;                   // ceil(8 * 136 / 256): (chunk, pixel) tasks per loader thread, Cred <= 64
+constexpr int kUmMaxQ = 5;                   // ceil(8 * 144 / 256): (chunk, pixel) tasks per loader thread, Cred <= 64
 constexpr int kTaps = 7;
 
 struct UmmaParams {
@@ -39,6 +49,7 @@ struct UmmaParams {
   float pad_value;
   int relu, has_bias, transpose_w;   // transpose_w: weights indexed [red][out] (dgrad)
   int slots, bands, ctiles;
+  int rstages, raw_bytes;        // TMA variant: raw staging ring
   long long items;
 };
 
@@ -52,10 +63,10 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <typename TIN, typename TOUT>
+template <typename TIN, typename TOUT, bool TMA>
 __global__ void __launch_bounds__(kUmThreads, 1)
-hexconv_umma_kernel(const TIN* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
-                    TOUT* __restrict__ out, UmmaParams P) {
+hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restrict__ in, const float* __restrict__ w,
+                    const float* __restrict__ bias, TOUT* __restrict__ out, UmmaParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nkc = P.Cred >> 3;
@@ -63,13 +74,16 @@ hexconv_umma_kernel(const TIN* __restrict__ in, const float* __restrict__ w, con
   const int wtap_bytes = P.Cred * P.Nout * 2;
   unsigned char* w_smem = smem;                                   // [tap][Cred/8][Nout][8] bf16
   unsigned char* ring = smem + kTaps * wtap_bytes;                // [slot][Cred/8][PW][8] bf16
-  float* bias_s = reinterpret_cast<float*>(ring + P.slots * slot_bytes);
+  unsigned char* raw = ring + P.slots * slot_bytes;               // [rstage][Cred][PW] TIN (TMA variant)
+  float* bias_s = reinterpret_cast<float*>(raw + (size_t)P.rstages * P.raw_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + P.Nout);
   uint64_t* full = bars;                    // [slots]  loaders -> MMA        (count kUmLoaders)
   uint64_t* empty = bars + P.slots;         // [slots]  MMA commit -> loaders (count 1)
   uint64_t* tfull = empty + P.slots;        // [2]      MMA commit -> epilogue
   uint64_t* tempty = tfull + 2;             // [2]      epilogue -> MMA       (count 128)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* rfull = tempty + 2;             // [rstages] TMA bytes landed
+  uint64_t* rempty = rfull + P.rstages;     // [rstages] converters done      (count kUmLoaders)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + P.rstages);
 
   // ---- one-time setup ---------------------------------------------------------------------------------
   // weights: fp32 [Cout][Cin][1][7] in global -> bf16 UMMA B image in shared memory
@@ -89,6 +103,8 @@ hexconv_umma_kernel(const TIN* __restrict__ in, const float* __restrict__ w, con
   if (tid == 0) {
     for (int s = 0; s < P.slots; ++s) { ptx::mbar_init(&full[s], kUmLoaders); ptx::mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull[s], 1); ptx::mbar_init(&tempty[s], 128); }
+    for (int s = 0; s < P.rstages; ++s) { ptx::mbar_init(&rfull[s], 1); ptx::mbar_init(&rempty[s], kUmLoaders); }
+    if (TMA) ptx::prefetch_tensormap(&tmap);
     ptx::fence_barrier_init();
   }
   const uint32_t tmem_cols = 2 * P.Nout <= 32 ? 32 : 2 * P.Nout <= 64 ? 64 : 2 * P.Nout <= 128 ? 128 : 2 * P.Nout <= 256 ? 256 : 512;
@@ -115,23 +131,41 @@ hexconv_umma_kernel(const TIN* __restrict__ in, const float* __restrict__ w, con
       for (int t = 0; t < rows + 2; ++t, ++lt) {
         const int slot = (int)(lt % P.slots);
         const uint32_t use = (uint32_t)(lt / P.slots);
-        ptx::mbar_wait(&empty[slot], (use & 1) ^ 1);
-        const int i = r0 + P.row0 + t;
-        const bool row_in = i >= 0 && i < P.Hi;
-        const bool row_frame = i >= -P.pad && i < P.Hi + P.pad;
         unsigned char* sb = ring + (size_t)slot * slot_bytes;
         float v[kUmMaxQ][8];
+        if (TMA) {
+          // raw row [Cred][PW] landed by TMA (halo rows / columns already zero-filled) -> registers
+          const int rs = (int)(lt % P.rstages);
+          ptx::mbar_wait(&rfull[rs], (uint32_t)((lt / P.rstages) & 1));
+          const TIN* __restrict__ rp = reinterpret_cast<const TIN*>(raw + (size_t)rs * P.raw_bytes);
 #pragma unroll
-        for (int q = 0; q < kUmMaxQ; ++q) {
-          const int task = tid + q * kUmLoaders;
-          if (task < ntasks) {
-            const int kc = task / kUmPW, p = task - kc * kUmPW;
-            const int j = c0 + P.col0 + p;
-            const bool col_in = j >= 0 && j < P.Wi;
-            const float fill = (row_frame && j >= -P.pad && j < P.Wi + P.pad) ? P.pad_value : 0.f;
-            const TIN* __restrict__ src = in_n + (size_t)(kc * 8) * plane + (size_t)i * P.Wi + j;
+          for (int q = 0; q < kUmMaxQ; ++q) {
+            const int task = tid + q * kUmLoaders;
+            if (task < ntasks) {
+              const int kc = task / kUmPW, p = task - kc * kUmPW;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[q][e] = (row_in && col_in) ? ld_in(src + (size_t)e * plane) : fill;
+              for (int e = 0; e < 8; ++e) v[q][e] = to_f32(rp[(kc * 8 + e) * kUmPW + p]);
+            }
+          }
+          ptx::mbar_arrive(&rempty[rs]);     // values are in registers: the stage can be refilled
+          ptx::mbar_wait(&empty[slot], (use & 1) ^ 1);
+        } else {
+          ptx::mbar_wait(&empty[slot], (use & 1) ^ 1);
+          const int i = r0 + P.row0 + t;
+          const bool row_in = i >= 0 && i < P.Hi;
+          const bool row_frame = i >= -P.pad && i < P.Hi + P.pad;
+#pragma unroll
+          for (int q = 0; q < kUmMaxQ; ++q) {
+            const int task = tid + q * kUmLoaders;
+            if (task < ntasks) {
+              const int kc = task / kUmPW, p = task - kc * kUmPW;
+              const int j = c0 + P.col0 + p;
+              const bool col_in = j >= 0 && j < P.Wi;
+              const float fill = (row_frame && j >= -P.pad && j < P.Wi + P.pad) ? P.pad_value : 0.f;
+              const TIN* __restrict__ src = in_n + (size_t)(kc * 8) * plane + (size_t)i * P.Wi + j;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[q][e] = (row_in && col_in) ? ld_in(src + (size_t)e * plane) : fill;
+            }
           }
         }
 #pragma unroll
@@ -185,7 +219,7 @@ hexconv_umma_kernel(const TIN* __restrict__ in, const float* __restrict__ w, con
         }
       }
     }
-  } else {
+  } else if (warp == 12) {
     // ===== MMA issuer ======================================================================================
     const uint32_t idesc = ptx::umma_idesc_bf16(kUmTile, P.Nout);
     const uint32_t ring_addr = ptx::smem_u32(ring), w_addr = ptx::smem_u32(w_smem);
@@ -230,6 +264,23 @@ hexconv_umma_kernel(const TIN* __restrict__ in, const float* __restrict__ w, con
       }
       mt += rows + 2;
     }
+  } else if (TMA) {
+    // ===== TMA producer (one lane) ===========================================================================
+    if (lane == 0) {
+      long long rt = 0;
+      for (long long item = blockIdx.x; item < P.items; item += gridDim.x) {
+        const int n = (int)(item / per_n);
+        const int rem = (int)(item - (long long)n * per_n);
+        const int band = rem / P.ctiles, ct = rem - band * P.ctiles;
+        const int r0 = band * kUmBand, rows = min(kUmBand, P.Ho - r0), c0 = ct * kUmTile;
+        for (int t = 0; t < rows + 2; ++t, ++rt) {
+          const int rs = (int)(rt % P.rstages);
+          ptx::mbar_wait(&rempty[rs], (uint32_t)(((rt / P.rstages) & 1) ^ 1));
+          ptx::mbar_arrive_expect_tx(&rfull[rs], (uint32_t)P.raw_bytes);
+          ptx::tma_load_4d(raw + (size_t)rs * P.raw_bytes, &tmap, &rfull[rs], c0 + P.col0, r0 + P.row0 + t, 0, n);
+        }
+      }
+    }
   }
 
   // ---- teardown ---------------------------------------------------------------------------------------------
@@ -244,26 +295,43 @@ hexconv_umma_kernel(const TIN* __restrict__ in, const float* __restrict__ w, con
 // ---- host side --------------------------------------------------------------------------------------------
 static int g_um_sms = 0, g_um_smem_max = 0;
 
-static size_t umma_smem_bytes(int Cred, int Nout, int slots) {
-  return (size_t)kTaps * Cred * Nout * 2 + (size_t)slots * Cred * kUmPW * 2 + (size_t)Nout * 4 + (size_t)(2 * slots + 4) * 8 + 16;
+static size_t umma_smem_bytes(int Cred, int Nout, int slots, int rstages, int raw_bytes) {
+  return (size_t)kTaps * Cred * Nout * 2 + (size_t)slots * Cred * kUmPW * 2 + (size_t)rstages * raw_bytes + (size_t)Nout * 4 +
+         (size_t)(2 * slots + 4 + 2 * rstages) * 8 + 16;
 }
 
-static int umma_pick_slots(int Cred, int Nout) {
+static bool umma_device_limits() {
   if (g_um_smem_max == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_um_smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaDeviceGetAttribute(&g_um_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaGetLastError() != cudaSuccess || g_um_smem_max <= 0) { g_um_smem_max = 0; return 0; }
+    if (cudaGetLastError() != cudaSuccess || g_um_smem_max <= 0) { g_um_smem_max = 0; return false; }
   }
-  for (int s = 6; s >= 4; --s)
-    if (umma_smem_bytes(Cred, Nout, s) <= (size_t)g_um_smem_max) return s;
-  return 0;
+  return true;
 }
 
-// op: 0 forward (reduce over Cin), 1 dgrad (reduce over Cout), 2 wgrad (not covered)
+// ring slots (and raw stages for the TMA variant) that fit; 0 slots = does not fit
+static void umma_pick_stages(int Cred, int Nout, int in_elem, bool tma, int& slots, int& rstages, int& raw_bytes) {
+  slots = rstages = raw_bytes = 0;
+  if (!umma_device_limits()) return;
+  if (tma) {
+    raw_bytes = (int)ceil_div((int64_t)Cred * kUmPW * in_elem, 128) * 128;
+    for (int r = (in_elem == 2 ? 3 : 2); r >= 2 && !slots; --r)
+      for (int sl = 6; sl >= 4; --sl)
+        if (umma_smem_bytes(Cred, Nout, sl, r, raw_bytes) <= (size_t)g_um_smem_max) { slots = sl; rstages = r; break; }
+    if (!slots) raw_bytes = 0;
+    return;
+  }
+  for (int sl = 6; sl >= 4; --sl)
+    if (umma_smem_bytes(Cred, Nout, sl, 0, 0) <= (size_t)g_um_smem_max) { slots = sl; return; }
+}
+
+// op: 0 forward (reduce over Cin), 1 dgrad (reduce over Cout), 2 wgrad (reduce over pixels)
+bool conv_wgrad_umma_eligible(const hg_conv_desc* d);   // hg_conv_wgrad_umma.cu
+
 bool conv_umma_eligible(const hg_conv_desc* d, int op) {
-  if (op == 2) return false;
+  if (op == 2) return conv_wgrad_umma_eligible(d);
   if (d->radius != 2 || d->stride != 1 || d->dilation != 1 || d->groups != 1) return false;
   const int64_t Cred = op == 0 ? d->Cin : d->Cout, Nout = op == 0 ? d->Cout : d->Cin;
   if (Cred % 16 != 0 || Cred < 16 || Cred > 64) return false;
@@ -272,13 +340,18 @@ bool conv_umma_eligible(const hg_conv_desc* d, int op) {
   // auto: bf16 activations only (fp32 callers keep fp32 accuracy on the direct stencil) and only when the
   // channel contraction is dense enough to feed a 128 x Nout x Cred tile
   if (d->algo == 0 && ((op == 0 ? d->x_dtype : d->y_dtype) != HG_BF16 || Cred * Nout < 32 * 32)) return false;
-  return umma_pick_slots((int)Cred, (int)Nout) > 0;
+  int slots, rst, rb;
+  umma_pick_stages((int)Cred, (int)Nout, 4, false, slots, rst, rb);
+  return slots > 0;
 }
 
-template <typename TIN, typename TOUT>
-static int launch_umma(const void* in, const float* w, const float* bias, void* out, const UmmaParams& P, cudaStream_t st) {
-  const size_t smem = umma_smem_bytes(P.Cred, P.Nout, P.slots);
-  auto kern = hexconv_umma_kernel<TIN, TOUT>;
+static bool g_um_no_tma = [] { const char* e = getenv("HG_CONV_NO_TMA"); return e && e[0] == '1'; }();
+
+template <typename TIN, typename TOUT, bool TMA>
+static int launch_umma(const CUtensorMap& tmap, const void* in, const float* w, const float* bias, void* out, const UmmaParams& P,
+                       cudaStream_t st) {
+  const size_t smem = umma_smem_bytes(P.Cred, P.Nout, P.slots, P.rstages, P.raw_bytes);
+  auto kern = hexconv_umma_kernel<TIN, TOUT, TMA>;
   static thread_local size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -287,16 +360,60 @@ static int launch_umma(const void* in, const float* w, const float* bias, void* 
   }
   long long grid = g_um_sms > 0 ? g_um_sms : 148;
   if (grid > P.items) grid = P.items;
-  kern<<<(unsigned)grid, kUmThreads, smem, st>>>((const TIN*)in, w, bias, (TOUT*)out, P);
-  return finish_launch("hexconv_umma");
+  kern<<<(unsigned)grid, kUmThreads, smem, st>>>(tmap, (const TIN*)in, w, bias, (TOUT*)out, P);
+  return finish_launch(TMA ? "hexconv_umma_tma" : "hexconv_umma");
+}
+
+// Completes P (stage counts, column alignment) and launches the TMA variant when the input qualifies.
+template <typename TIN, typename TOUT>
+static int launch_umma_any(const void* in, const float* w, const float* bias, void* out, UmmaParams P, cudaStream_t st) {
+  alignas(64) CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  constexpr int es = (int)sizeof(TIN), A = 16 / es;
+  PFN_encodeTiled enc = get_encode_tiled();
+  bool tma = !g_um_no_tma && enc != nullptr && P.pad_value == 0.f && ((int64_t)P.Wi * es) % 16 == 0 &&
+             (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+  if (tma) {
+    int slots, rst, rb;
+    umma_pick_stages(P.Cred, P.Nout, es, true, slots, rst, rb);
+    tma = slots > 0;
+    if (tma) {
+      // 16-byte aligned box origin: move the ring origin left by e0 pixels and the tap views right by e0
+      const int col0a = (int)(floor((double)P.col0 / A)) * A, e0 = P.col0 - col0a;
+      int smax = 0;
+      for (int par = 0; par < 2; ++par) for (int k = 0; k < kTaps; ++k) smax = max(smax, P.sh[par][k] + e0);
+      if (kUmTile + smax > kUmPW) tma = false;
+      else {
+        const cuuint64_t gdim[4] = {(cuuint64_t)P.Wi, (cuuint64_t)P.Hi, (cuuint64_t)P.Cred, (cuuint64_t)P.N};
+        const cuuint64_t gstr[3] = {(cuuint64_t)P.Wi * es, (cuuint64_t)P.Wi * P.Hi * es, (cuuint64_t)P.Wi * P.Hi * P.Cred * es};
+        const cuuint32_t box[4] = {(cuuint32_t)kUmPW, 1, (cuuint32_t)P.Cred, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        const CUtensorMapDataType dt = es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+        if (enc(&tmap, dt, 4, const_cast<void*>(in), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+          tma = false;
+        else {
+          P.col0 = col0a;
+          for (int par = 0; par < 2; ++par) for (int k = 0; k < kTaps; ++k) P.sh[par][k] += e0;
+          P.slots = slots; P.rstages = rst; P.raw_bytes = rb;
+          return launch_umma<TIN, TOUT, true>(tmap, in, w, bias, out, P, st);
+        }
+      }
+    }
+  }
+  int rst, rb;
+  umma_pick_stages(P.Cred, P.Nout, es, false, P.slots, rst, rb);
+  P.rstages = 0; P.raw_bytes = 0;
+  HG_REQUIRE(P.slots > 0, HG_E_UNSUPPORTED, "hexconv_umma: shared memory does not fit");
+  return launch_umma<TIN, TOUT, false>(tmap, in, w, bias, out, P, st);
 }
 
 static int dispatch_umma(int in_dt, int out_dt, const void* in, const float* w, const float* bias, void* out, const UmmaParams& P,
                          cudaStream_t st) {
-  if (in_dt == HG_F32 && out_dt == HG_F32) return launch_umma<float, float>(in, w, bias, out, P, st);
-  if (in_dt == HG_BF16 && out_dt == HG_F32) return launch_umma<__nv_bfloat16, float>(in, w, bias, out, P, st);
-  if (in_dt == HG_F32 && out_dt == HG_BF16) return launch_umma<float, __nv_bfloat16>(in, w, bias, out, P, st);
-  if (in_dt == HG_BF16 && out_dt == HG_BF16) return launch_umma<__nv_bfloat16, __nv_bfloat16>(in, w, bias, out, P, st);
+  if (in_dt == HG_F32 && out_dt == HG_F32) return launch_umma_any<float, float>(in, w, bias, out, P, st);
+  if (in_dt == HG_BF16 && out_dt == HG_F32) return launch_umma_any<__nv_bfloat16, float>(in, w, bias, out, P, st);
+  if (in_dt == HG_F32 && out_dt == HG_BF16) return launch_umma_any<float, __nv_bfloat16>(in, w, bias, out, P, st);
+  if (in_dt == HG_BF16 && out_dt == HG_BF16) return launch_umma_any<__nv_bfloat16, __nv_bfloat16>(in, w, bias, out, P, st);
   set_error("hexconv_umma: unsupported dtypes in=%d out=%d", in_dt, out_dt);
   return HG_E_DTYPE;
 }
@@ -306,7 +423,6 @@ static void umma_common(UmmaParams& P, int Ho, int Wo, int N) {
   P.bands = (int)ceil_div(Ho, kUmBand);
   P.ctiles = (int)ceil_div(Wo, kUmTile);
   P.items = (long long)N * P.bands * P.ctiles;
-  P.slots = umma_pick_slots(P.Cred, P.Nout);
 }
 
 int conv_fwd_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp, const void* x, const float* w, const float* bias,
@@ -316,7 +432,7 @@ int conv_fwd_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp, 
   int cmin = 1 << 30, cmax = -(1 << 30);
   for (int par = 0; par < 2; ++par)
     for (int k = 0; k < kTaps; ++k) { cmin = min(cmin, tp.co[par][k]); cmax = max(cmax, tp.co[par][k]); }
-  HG_REQUIRE(tp.K == kTaps && cmax - cmin <= kUmPW - kUmTile, HG_E_UNSUPPORTED, "hexconv_umma: unexpected tap geometry");
+  HG_REQUIRE(tp.K == kTaps && cmax - cmin <= 3, HG_E_UNSUPPORTED, "hexconv_umma: unexpected tap geometry");
   for (int k = 0; k < kTaps; ++k) {
     P.ra[k] = tp.ro[k];
     for (int par = 0; par < 2; ++par) P.sh[par][k] = tp.co[par][k] - cmin;
@@ -325,7 +441,6 @@ int conv_fwd_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp, 
   P.pad = g.pad; P.pad_value = g.pad_value;
   P.relu = g.relu; P.has_bias = bias != nullptr; P.transpose_w = 0;
   umma_common(P, g.Ho, g.Wo, g.N);
-  HG_REQUIRE(P.slots > 0, HG_E_UNSUPPORTED, "hexconv_umma: shared memory does not fit");
   return dispatch_umma(d->x_dtype, d->y_dtype, x, w, bias, y, P, st);
 }
 
@@ -343,7 +458,7 @@ int conv_dgrad_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp
       cs[ipar][k] = g.pad - tp.co[rpar][k];
       cmin = min(cmin, cs[ipar][k]); cmax = max(cmax, cs[ipar][k]);
     }
-  HG_REQUIRE(cmax - cmin <= kUmPW - kUmTile, HG_E_UNSUPPORTED, "hexconv_umma: unexpected tap geometry");
+  HG_REQUIRE(cmax - cmin <= 3, HG_E_UNSUPPORTED, "hexconv_umma: unexpected tap geometry");
   for (int k = 0; k < kTaps; ++k) {
     P.ra[k] = 2 - tp.ro[k];
     for (int ipar = 0; ipar < 2; ++ipar) P.sh[ipar][k] = cs[ipar][k] - cmin;
@@ -352,13 +467,7 @@ int conv_dgrad_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp
   P.pad = 0; P.pad_value = 0.f;
   P.relu = 0; P.has_bias = 0; P.transpose_w = 1;
   umma_common(P, g.H, g.W, g.N);
-  HG_REQUIRE(P.slots > 0, HG_E_UNSUPPORTED, "hexconv_umma: shared memory does not fit");
   return dispatch_umma(d->y_dtype, d->x_dtype, gy, w, nullptr, gx, P, st);
-}
-
-int conv_wgrad_umma(const hg_conv_desc*, const ConvGeom&, const ConvTaps&, const void*, const void*, float*, float*, cudaStream_t) {
-  set_error("hexconv wgrad has no tcgen05 path yet");
-  return HG_E_UNSUPPORTED;
 }
 
 }  // namespace hg

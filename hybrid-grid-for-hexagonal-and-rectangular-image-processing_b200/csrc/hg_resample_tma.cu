@@ -36,90 +36,122 @@ __device__ __forceinline__ void rect_axis_d(double coord, int n, int& idx, doubl
   frac = dsub(c, (double)(float)idx);
 }
 
+// Per-item lattice tables in shared memory (double-buffered): the 128 column entries and 8*RW row entries of
+// the tile are computed by one thread each (instead of 4 + RW by every thread) while the previous tile is
+// being blended.
+template <typename WT, int RW>
+struct TileTables {
+  int cidx[kTW];        // j_n - col0  (column inside the staged box)
+  WT cfrac[kTW];        // j_f
+  int ridx[8 * RW];     // (i_n - row0) * BW  (row offset inside the staged box)
+  WT rfrac[8 * RW];     // i_f
+  int nrows;            // valid output rows of the tile
+  int ncols;            // valid output columns of the tile
+};
+
 template <typename TS, typename TD, bool EXACT, int RW>  // RW = output rows per warp; tile height = 8*RW
 __global__ void __launch_bounds__(kTmaThreads)
 rect2hex_bilinear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __restrict__ dst, const double* __restrict__ xs,
-                             const double* __restrict__ ys, int h, int w, int h1, int w1, int tiles_x, int planes,
+                             const double* __restrict__ ys, int h, int w, int h1, int w1, int tiles_x, int tiles_y,
                              long long total_items, long long items_per_cta, int BW, int BH, int stage_bytes) {
   using WT = typename std::conditional<EXACT, double, float>::type;
+  using Tab = TileTables<WT, RW>;
   constexpr int TH = 8 * RW;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kTmaStages * stage_bytes);
+  Tab* tabs = reinterpret_cast<Tab*>(smem_raw + (size_t)kTmaStages * stage_bytes + 64);
 
   const long long g_begin = (long long)blockIdx.x * items_per_cta;
   const long long g_end = min(total_items, g_begin + items_per_cta);
   if (g_begin >= g_end) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int npos = tiles_x * tiles_y;
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&tmap);
     for (int s = 0; s < kTmaStages; ++s) ptx::mbar_init(&full[s], 1);
     ptx::fence_barrier_init();
   }
-  __syncthreads();
 
-  auto issue = [&](long long g, int s) {   // one thread
-    const long long pos = g / planes;
-    const int plane = (int)(g - pos * planes);
-    const int tx = (int)(pos % tiles_x), ty = (int)(pos / tiles_x);
-    int row0, col0; double f;
+  // items run plane-major, tiles row-major inside a plane: horizontally and vertically adjacent tiles are
+  // staged close in time by the same CTA, so their halo rows / columns come out of L2, not HBM.
+  auto decode = [&](long long g, int& plane, int& tx, int& ty) {
+    plane = (int)(g / npos);
+    const int pos = (int)(g - (long long)plane * npos);
+    ty = pos / tiles_x; tx = pos - ty * tiles_x;
+  };
+  auto origin = [&](int tx, int ty, int& row0, int& col0) {
+    double f;
     rect_axis_d(xs[ty * TH], h, row0, f);
     rect_axis_d(ys[tx * kTW], w, col0, f);
     col0 = align_col<TS>(col0);
+  };
+  auto issue = [&](long long g, int s) {   // one thread
+    int plane, tx, ty, row0, col0;
+    decode(g, plane, tx, ty);
+    origin(tx, ty, row0, col0);
     ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(BW * BH * (int)sizeof(TS)));
     ptx::tma_load_3d(smem_raw + (size_t)s * stage_bytes, &tmap, &full[s], col0, row0, plane);
   };
+  auto build_tables = [&](long long g, Tab& T) {   // threads 0 .. kTW + TH - 1, one entry each
+    int plane, tx, ty, row0, col0;
+    decode(g, plane, tx, ty);
+    origin(tx, ty, row0, col0);
+    const int t = threadIdx.x;
+    if (t < kTW) {
+      const int b = tx * kTW + t;
+      int jn = col0; double v = 0.0;
+      if (b < w1) rect_axis_d(ys[b], w, jn, v);
+      T.cidx[t] = jn - col0;
+      T.cfrac[t] = (WT)v;
+      if (t == 0) { T.ncols = min(kTW, w1 - tx * kTW); T.nrows = min(TH, h1 - ty * TH); }
+    } else if (t < kTW + TH) {
+      const int r = t - kTW, a = ty * TH + r;
+      int in = row0; double u = 0.0;
+      if (a < h1) rect_axis_d(xs[a], h, in, u);
+      T.ridx[r] = (in - row0) * BW;
+      T.rfrac[r] = (WT)u;
+    }
+  };
+
+  build_tables(g_begin, tabs[0]);
+  __syncthreads();
   if (threadIdx.x == 0) {
     for (int s = 0; s < kTmaStages && g_begin + s < g_end; ++s) issue(g_begin + s, s);
   }
 
-  long long pos = g_begin / planes;
-  int plane = (int)(g_begin - pos * planes);
-  long long cur_pos = -1;
-  int coff[4], roff[RW];
-  WT jf[4], uf[RW];
-  bool cok[4];
-  int nrows = 0, a0 = 0, b0 = 0;
-
   for (long long k = 0; g_begin + k < g_end; ++k) {
     const int s = (int)(k % kTmaStages);
     const uint32_t parity = (uint32_t)((k / kTmaStages) & 1);
-    if (pos != cur_pos) {                       // new tile position: rebuild the per-thread tables
-      cur_pos = pos;
-      const int tx = (int)(pos % tiles_x), ty = (int)(pos / tiles_x);
-      a0 = ty * TH + warp * RW; b0 = tx * kTW + lane;
-      int row0, col0; double f;
-      rect_axis_d(xs[ty * TH], h, row0, f);
-      rect_axis_d(ys[tx * kTW], w, col0, f);
-      col0 = align_col<TS>(col0);
+    const Tab& T = tabs[k & 1];
+    if (g_begin + k + 1 < g_end) build_tables(g_begin + k + 1, tabs[(k + 1) & 1]);
+
+    int plane, tx, ty;
+    decode(g_begin + k, plane, tx, ty);
+    int coff[4];
+    WT jf[4];
+    bool cok[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int b = b0 + 32 * c;
-        cok[c] = b < w1;
-        int jn; double v;
-        rect_axis_d(cok[c] ? ys[b] : ys[tx * kTW], w, jn, v);
-        coff[c] = jn - col0;
-        jf[c] = (WT)v;
-      }
-      nrows = 0;
-#pragma unroll
-      for (int r = 0; r < RW; ++r) {
-        const int a = a0 + r;
-        int in = row0; double u = 0.0;
-        if (a < h1) { rect_axis_d(xs[a], h, in, u); nrows = r + 1; }
-        roff[r] = (in - row0) * BW;
-        uf[r] = (WT)u;
-      }
+    for (int c = 0; c < 4; ++c) {
+      coff[c] = T.cidx[lane + 32 * c];
+      jf[c] = T.cfrac[lane + 32 * c];
+      cok[c] = lane + 32 * c < T.ncols;
     }
+    const int nrows = min(RW, T.nrows - warp * RW);
+    TD* __restrict__ dp = dst + (size_t)plane * h1 * w1 + (size_t)(ty * TH + warp * RW) * w1 + (tx * kTW + lane);
+
     ptx::mbar_wait(&full[s], parity);
     const TS* __restrict__ t = reinterpret_cast<const TS*>(smem_raw + (size_t)s * stage_bytes);
-    TD* __restrict__ dp = dst + (size_t)plane * h1 * w1 + (size_t)a0 * w1 + b0;
 
     WT bl[4], br[4];   // lower pair of the previous row (= upper pair of this row when i_n advanced by one)
+    int prev_roff = 0;
 #pragma unroll
     for (int r = 0; r < RW; ++r) {
       if (r < nrows) {
-        const bool carry = (r > 0) && (roff[r] == roff[r > 0 ? r - 1 : 0] + BW);   // warp-uniform
+        const int roff = T.ridx[warp * RW + r];
+        const WT u = T.rfrac[warp * RW + r];
+        const bool carry = (r > 0) && (roff == prev_roff + BW);   // warp-uniform
+        prev_roff = roff;
         WT tl[4], tr[4];
         if (carry) {
 #pragma unroll
@@ -127,14 +159,14 @@ rect2hex_bilinear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __res
         } else {
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const int o = roff[r] + coff[c];
+            const int o = roff + coff[c];
             tl[c] = (WT)t[o];
             tr[c] = (WT)t[o + 1];
           }
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const int o = roff[r] + BW + coff[c];
+          const int o = roff + BW + coff[c];
           bl[c] = (WT)t[o];
           br[c] = (WT)t[o + 1];
         }
@@ -142,13 +174,13 @@ rect2hex_bilinear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __res
         for (int c = 0; c < 4; ++c) {
           TD o;
           if (EXACT) {   // literal operation order of geometry_np.py:515-517, no contraction
-            const double u = uf[r], v = jf[c];
+            const double v = jf[c];
             const double u1 = dsub(1.0, u), v1 = dsub(1.0, v);
             const double t1 = dadd(dmul(u, bl[c]), dmul(u1, tl[c]));
             const double t2 = dadd(dmul(u, br[c]), dmul(u1, tr[c]));
             o = (TD)dadd(dmul(v, t2), dmul(v1, t1));
           } else {
-            const float u = uf[r], v = jf[c];
+            const float v = jf[c];
             const float t1 = fmaf(u, bl[c] - tl[c], tl[c]);
             const float t2 = fmaf(u, br[c] - tr[c], tr[c]);
             o = (TD)fmaf(v, t2 - t1, t1);
@@ -157,9 +189,8 @@ rect2hex_bilinear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __res
         }
       }
     }
-    __syncthreads();                            // every thread is done reading stage s
+    __syncthreads();                            // stage s fully read; next tile's tables complete
     if (threadIdx.x == 0 && g_begin + k + kTmaStages < g_end) issue(g_begin + k + kTmaStages, s);
-    if (++plane == planes) { plane = 0; ++pos; }
   }
 }
 
@@ -209,7 +240,8 @@ static int launch_tma(const void* src, void* dst, const double* xs, const double
           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return 1;
   const int stage_bytes = (int)ceil_div((int64_t)BW * BH * sizeof(TS), 128) * 128;
-  const int smem = kTmaStages * stage_bytes + kTmaStages * 8;
+  using WT = typename std::conditional<EXACT, double, float>::type;
+  const int smem = kTmaStages * stage_bytes + 64 + 2 * (int)sizeof(TileTables<WT, RW>);
   auto kern = rect2hex_bilinear_tma_kernel<TS, TD, EXACT, RW>;
   static thread_local int configured_smem = 0;
   if (smem > configured_smem) {
@@ -225,11 +257,12 @@ static int launch_tma(const void* src, void* dst, const double* xs, const double
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTmaThreads, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); return 1; }
   const int tiles_x = (int)ceil_div(w1, kTW), tiles_y = (int)ceil_div(h1, TH);
   const long long total = (long long)tiles_x * tiles_y * planes;
+  if (kTW + TH > kTmaThreads) return 1;
   long long grid = (long long)g_sm_count * occ;
   if (grid > total) grid = total;
   const long long per = (total + grid - 1) / grid;
   grid = (total + per - 1) / per;
-  kern<<<(unsigned)grid, kTmaThreads, smem, st>>>(tmap, (TD*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, tiles_x, (int)planes,
+  kern<<<(unsigned)grid, kTmaThreads, smem, st>>>(tmap, (TD*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, tiles_x, tiles_y,
                                                    total, per, BW, BH, stage_bytes);
   return finish_launch("rect2hex_bilinear_tma");
 }

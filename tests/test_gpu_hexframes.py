@@ -249,30 +249,36 @@ def test_reductions_and_converters(hf, hexframes_golden, resample_golden):
     (1, 16, 48, 37, 131, 2, 1, torch.float32),
     (1, 64, 128, 20, 260, 1, 0, torch.bfloat16),
     (1, 48, 16, 65, 64, 1, 1, torch.float32),
+    (2, 64, 64, 35, 256, 1, 1, torch.bfloat16),
+    (1, 32, 64, 34, 264, 2, 0, torch.float32),
 ])
-def test_hexconv_tcgen05_vs_oracle(hf, cfg):
+@pytest.mark.parametrize("pad_value", [0.0, 0.25])      # 0 -> TMA-staged input path, != 0 -> coalesced-load path
+def test_hexconv_tcgen05_vs_oracle(hf, cfg, pad_value):
     N, Cin, Cout, H, W, pad, off, xdt = cfg
     torch.manual_seed(3)
     xq = torch.randn(N, Cin, H, W).bfloat16().float()
     wq = (torch.randn(Cout, Cin, 1, 7) * 0.1).bfloat16().float()
     b = torch.randn(Cout)
     xr, wr = xq.clone().requires_grad_(), wq.clone().requires_grad_()
-    ref = HO.hexconv2d(xr, wr, b, off, 2, 1, pad, 1, 1, padding_value=0.25)
+    ref = HO.hexconv2d(xr, wr, b, off, 2, 1, pad, 1, 1, padding_value=pad_value)
     gyq = torch.randn_like(ref).bfloat16().float()
     (ref * gyq).sum().backward()
     xg = xq.to(xdt).cuda().requires_grad_()
     wg = wq.cuda().requires_grad_()
-    y = hf.hexconv2d(xg, wg, b.cuda(), off, 2, 1, pad, 1, 1, padding_value=0.25, algo=2)
+    bg = b.cuda().requires_grad_()
+    y = hf.hexconv2d(xg, wg, bg, off, 2, 1, pad, 1, 1, padding_value=pad_value, algo=2)
     assert y.shape == ref.shape and y.dtype == torch.float32
     scale = float(ref.detach().abs().max())
     assert float((y.detach().cpu() - ref.detach()).abs().max()) <= 1e-4 * scale
-    (y * gyq.cuda()).sum().backward()          # dgrad on tcgen05 (gy is rounded to bf16 in the loader), wgrad direct
+    (y * gyq.cuda()).sum().backward()          # dgrad and wgrad on tcgen05 where covered (operands are bf16-exact here)
     gscale = float(xr.grad.abs().max())
     assert float((xg.grad.float().cpu() - xr.grad).abs().max()) <= (1e-4 if xdt == torch.float32 else 1e-2) * gscale
     assert float((wg.grad.cpu() - wr.grad).abs().max()) <= 1e-3 * float(wr.grad.abs().max())
+    gb_ref = gyq.sum(dim=(0, 2, 3))
+    assert float((bg.grad.cpu() - gb_ref).abs().max()) <= 1e-3 * max(float(gb_ref.abs().max()), 1.0)
     # fused ReLU epilogue (inference)
     with torch.no_grad():
-        yr = hf.hexconv2d(xg.detach(), wg.detach(), b.cuda(), off, 2, 1, pad, 1, 1, padding_value=0.25, algo=2, relu=True)
+        yr = hf.hexconv2d(xg.detach(), wg.detach(), bg.detach(), off, 2, 1, pad, 1, 1, padding_value=pad_value, algo=2, relu=True)
     assert float((yr.cpu() - ref.detach().clamp_min(0)).abs().max()) <= 1e-4 * scale
 
 
