@@ -186,21 +186,21 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
     // ===== epilogue ========================================================================================
     const int q4 = warp & 3;                 // TMEM lane quadrant this warp may access
     const int px = q4 * 32 + lane;
-    long long at = 0;                        // output rows consumed so far (accumulator stage position)
+    const size_t cstride = (size_t)P.Ho * P.Wo;
+    uint32_t acc = 0, acc_phase = 0;
     for (long long item = blockIdx.x; item < P.items; item += gridDim.x) {
       const int n = (int)(item / per_n);
       const int rem = (int)(item - (long long)n * per_n);
       const int band = rem / P.ctiles, ct = rem - band * P.ctiles;
       const int r0 = band * kUmBand, rows = min(kUmBand, P.Ho - r0), c = ct * kUmTile + px;
-      for (int rr = 0; rr < rows; ++rr, ++at) {
-        const int acc = (int)(at & 1);
-        ptx::mbar_wait(&tfull[acc], (uint32_t)((at >> 1) & 1));
+      TOUT* __restrict__ orow = out + (((size_t)n * P.Nout) * P.Ho + r0) * P.Wo + c;
+      for (int rr = 0; rr < rows; ++rr, orow += P.Wo) {
+        ptx::mbar_wait(&tfull[acc], acc_phase);
         ptx::tc_fence_after_sync();
-        TOUT* __restrict__ op = out + (((size_t)n * P.Nout) * P.Ho + (r0 + rr)) * P.Wo + c;
-        const size_t cstride = (size_t)P.Ho * P.Wo;
+        TOUT* __restrict__ op = orow;
         for (int cb = 0; cb < P.Nout; cb += 32) {
           uint32_t v[32];
-          ptx::tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * P.Nout + cb), v);
+          ptx::tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * (uint32_t)P.Nout + (uint32_t)cb, v);
           ptx::tmem_ld_wait();
           if (cb + 32 >= P.Nout) {           // last chunk read: hand the accumulator back to the MMA warp
             ptx::tc_fence_before_sync();
@@ -212,57 +212,75 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
               if (cb + j < P.Nout) {
                 float f = __uint_as_float(v[j]) + bias_s[cb + j];
                 if (P.relu) f = fmaxf(f, 0.f);
-                st_out(op + (size_t)(cb + j) * cstride, f);
+                st_out(op, f);
+                op += cstride;
               }
             }
           }
         }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp == 12) {
     // ===== MMA issuer ======================================================================================
+    // Single-lane issue loop: everything that does not change per instruction is hoisted -- ring slots and
+    // mbarrier parities advance incrementally (no 64-bit division), descriptors are built from a constant
+    // high word and a low word that only gets an address increment added.
     const uint32_t idesc = ptx::umma_idesc_bf16(kUmTile, P.Nout);
     const uint32_t ring_addr = ptx::smem_u32(ring), w_addr = ptx::smem_u32(w_smem);
     const uint32_t lbo_a = kUmPW * 16, lbo_b = (uint32_t)P.Nout * 16;
-    long long mt = 0, at = 0;                // ring position of the band's first input row; accumulator position
+    const uint32_t desc_hi = (128u >> 4) | (1u << 14);                       // SBO = 128 B, descriptor version 1
+    const uint32_t a_lo_const = ((lbo_a >> 4) << 16), b_lo_const = ((lbo_b >> 4) << 16);
+    const uint32_t a_step = (2u * lbo_a) >> 4, b_step = (2u * lbo_b) >> 4;  // one K = 16 step, in 16-byte units
+    const int ksteps = P.Cred >> 4;
+    uint32_t slot0 = 0, phase0 = 0;          // ring slot / parity of the current output row's first input row
+    uint32_t acc = 0, acc_phase = 0;         // accumulator stage / parity
+    auto next_slot = [&](uint32_t& sl, uint32_t& ph) { if (++sl == (uint32_t)P.slots) { sl = 0; ph ^= 1; } };
     for (long long item = blockIdx.x; item < P.items; item += gridDim.x) {
       const int rem = (int)(item % per_n);
       const int band = rem / P.ctiles;
       const int r0 = band * kUmBand, rows = min(kUmBand, P.Ho - r0);
-      for (int rr = 0; rr < rows; ++rr, ++at) {
-        const int acc = (int)(at & 1);
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const long long lt = mt + rr + d;
-          ptx::mbar_wait(&full[lt % P.slots], (uint32_t)((lt / P.slots) & 1));
-        }
-        ptx::mbar_wait(&tempty[acc], (uint32_t)(((at >> 1) & 1) ^ 1));
+      for (int rr = 0; rr < rows; ++rr) {
+        uint32_t s1 = slot0, p1 = phase0; next_slot(s1, p1);
+        uint32_t s2 = s1, p2 = p1; next_slot(s2, p2);
+        ptx::mbar_wait(&full[slot0], phase0);
+        ptx::mbar_wait(&full[s1], p1);
+        ptx::mbar_wait(&full[s2], p2);
+        ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
         ptx::tc_fence_after_sync();
         if (lane == 0) {
           const int par = (r0 + rr) & 1;
-          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.Nout);
+          const uint32_t d_tmem = tmem_base + acc * (uint32_t)P.Nout;
+          const uint32_t rb0 = (ring_addr + slot0 * (uint32_t)slot_bytes) >> 4;
+          const uint32_t rb1 = (ring_addr + s1 * (uint32_t)slot_bytes) >> 4;
+          const uint32_t rb2 = (ring_addr + s2 * (uint32_t)slot_bytes) >> 4;
           uint32_t accum = 0;
+#pragma unroll
           for (int k = 0; k < kTaps; ++k) {
-            const long long lt = mt + rr + P.ra[k];
-            const uint32_t a0 = ring_addr + (uint32_t)(lt % P.slots) * (uint32_t)slot_bytes + (uint32_t)P.sh[par][k] * 16u;
-            const uint32_t b0 = w_addr + (uint32_t)k * (uint32_t)wtap_bytes;
-            for (int j = 0; j < (P.Cred >> 4); ++j) {
-              const uint64_t ad = ptx::umma_desc_kmajor_noswizzle(a0 + (uint32_t)j * 2u * lbo_a, lbo_a, 128);
-              const uint64_t bd = ptx::umma_desc_kmajor_noswizzle(b0 + (uint32_t)j * 2u * lbo_b, lbo_b, 128);
+            const int ra = P.ra[k];
+            uint32_t a_lo = (ra == 0 ? rb0 : (ra == 1 ? rb1 : rb2)) + (uint32_t)P.sh[par][k] + a_lo_const;
+            uint32_t b_lo = ((w_addr + (uint32_t)k * (uint32_t)wtap_bytes) >> 4) + b_lo_const;
+            for (int j = 0; j < ksteps; ++j) {
+              const uint64_t ad = ((uint64_t)desc_hi << 32) | a_lo;
+              const uint64_t bd = ((uint64_t)desc_hi << 32) | b_lo;
               ptx::umma_bf16(d_tmem, ad, bd, idesc, accum);
               accum = 1;
+              a_lo += a_step; b_lo += b_step;
             }
           }
           ptx::umma_commit(&tfull[acc]);                         // accumulator ready for the epilogue
-          ptx::umma_commit(&empty[(mt + rr) % P.slots]);         // input row rr is not needed any more
+          ptx::umma_commit(&empty[slot0]);                       // input row rr is not needed any more
           if (rr == rows - 1) {                                  // band done: release its two trailing rows too
-            ptx::umma_commit(&empty[(mt + rows) % P.slots]);
-            ptx::umma_commit(&empty[(mt + rows + 1) % P.slots]);
+            ptx::umma_commit(&empty[s1]);
+            ptx::umma_commit(&empty[s2]);
           }
         }
         __syncwarp();
+        next_slot(slot0, phase0);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      mt += rows + 2;
+      next_slot(slot0, phase0);              // the band's two trailing input rows
+      next_slot(slot0, phase0);
     }
   } else if (TMA) {
     // ===== TMA producer (one lane) ===========================================================================

@@ -134,26 +134,28 @@ hexconv_wgrad_umma_kernel(const TX* __restrict__ x, const TG* __restrict__ gy, f
       const int slot = (int)(gt % kWuGSlots);
       ptx::mbar_wait(&gempty[slot], (uint32_t)(((gt / kWuGSlots) & 1) ^ 1));
       unsigned char* sb = gring + (size_t)slot * gslot_bytes;
-      float v[kWuMaxQ][8];
+      for (int base = 0; base < gtasks; base += kWuMaxQ * kWuLoaders) {   // Cout = 128 needs two passes
+        float v[kWuMaxQ][8];
 #pragma unroll
-      for (int q = 0; q < kWuMaxQ; ++q) {
-        const int task = tid + q * kWuLoaders;
-        if (task < gtasks) {
-          const int kc = task / kWuTile, p = task - kc * kWuTile;
-          const int c = c0 + p;
-          const TG* __restrict__ src = gn + (size_t)(kc * 8) * gplane + (size_t)R * P.Wo + c;
+        for (int q = 0; q < kWuMaxQ; ++q) {
+          const int task = base + tid + q * kWuLoaders;
+          if (task < gtasks) {
+            const int kc = task / kWuTile, p = task - kc * kWuTile;
+            const int c = c0 + p;
+            const TG* __restrict__ src = gn + (size_t)(kc * 8) * gplane + (size_t)R * P.Wo + c;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[q][e] = c < P.Wo ? wu_ld(src + (size_t)e * gplane) : 0.f;
+            for (int e = 0; e < 8; ++e) v[q][e] = c < P.Wo ? wu_ld(src + (size_t)e * gplane) : 0.f;
+          }
         }
-      }
 #pragma unroll
-      for (int q = 0; q < kWuMaxQ; ++q) {
-        const int task = tid + q * kWuLoaders;
-        if (task < gtasks) {
-          uint4 pk;
-          pk.x = wu_pack(v[q][0], v[q][1]); pk.y = wu_pack(v[q][2], v[q][3]);
-          pk.z = wu_pack(v[q][4], v[q][5]); pk.w = wu_pack(v[q][6], v[q][7]);
-          *reinterpret_cast<uint4*>(sb + (size_t)task * 16) = pk;
+        for (int q = 0; q < kWuMaxQ; ++q) {
+          const int task = base + tid + q * kWuLoaders;
+          if (task < gtasks) {
+            uint4 pk;
+            pk.x = wu_pack(v[q][0], v[q][1]); pk.y = wu_pack(v[q][2], v[q][3]);
+            pk.z = wu_pack(v[q][4], v[q][5]); pk.w = wu_pack(v[q][6], v[q][7]);
+            *reinterpret_cast<uint4*>(sb + (size_t)task * 16) = pk;
+          }
         }
       }
       ptx::fence_proxy_async_smem();
@@ -179,48 +181,65 @@ hexconv_wgrad_umma_kernel(const TX* __restrict__ x, const TG* __restrict__ gy, f
     const uint32_t idesc = wu_idesc(128, P.Cin), idesc_b = wu_idesc(128, 16);
     const uint32_t g_addr = ptx::smem_u32(gring), x_addr = ptx::smem_u32(xring), o_addr = ptx::smem_u32(ones);
     const uint32_t sbo_g = kWuTile * 16, sbo_x = kWuPW * 16;
-    long long mt = 0, gt = 0;
+    // descriptor = constant high word (SBO, version) | low word (start >> 4, LBO = 128 B between 8-pixel groups)
+    const uint32_t g_hi = (sbo_g >> 4) | (1u << 14), x_hi = (sbo_x >> 4) | (1u << 14), o_hi = (256u >> 4) | (1u << 14);
+    const uint32_t lo_const = (128u >> 4) << 16;
+    const uint64_t od = ((uint64_t)o_hi << 32) | ((o_addr >> 4) + lo_const);
+    uint32_t slot0 = 0, phase0 = 0, gs = 0, gphase = 0;
+    auto next_slot = [&](uint32_t& sl, uint32_t& ph) { if (++sl == (uint32_t)P.xslots) { sl = 0; ph ^= 1; } };
     uint32_t started = 0;
     for (long long item = blockIdx.x; item < P.items; item += gridDim.x) {
       const int rem = (int)(item % per_n);
       const int band = rem / P.ctiles;
       const int r0 = band * kWuBand, rows = min(kWuBand, P.Ho - r0);
-      for (int rr = 0; rr < rows; ++rr, ++gt) {
-        const int gs = (int)(gt % kWuGSlots);
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const long long lt = mt + rr + d;
-          ptx::mbar_wait(&xfull[lt % P.xslots], (uint32_t)((lt / P.xslots) & 1));
-        }
-        ptx::mbar_wait(&gfull[gs], (uint32_t)((gt / kWuGSlots) & 1));
+      for (int rr = 0; rr < rows; ++rr) {
+        uint32_t s1 = slot0, p1 = phase0; next_slot(s1, p1);
+        uint32_t s2 = s1, p2 = p1; next_slot(s2, p2);
+        ptx::mbar_wait(&xfull[slot0], phase0);
+        ptx::mbar_wait(&xfull[s1], p1);
+        ptx::mbar_wait(&xfull[s2], p2);
+        ptx::mbar_wait(&gfull[gs], gphase);
         ptx::tc_fence_after_sync();
         if (lane == 0) {
           const int par = (r0 + rr) & 1;
-          const uint32_t a0 = g_addr + (uint32_t)gs * (uint32_t)gslot_bytes;
+          const uint32_t a_lo0 = ((g_addr + gs * (uint32_t)gslot_bytes) >> 4) + lo_const;
+          const uint32_t xb0 = (x_addr + slot0 * (uint32_t)xslot_bytes) >> 4;
+          const uint32_t xb1 = (x_addr + s1 * (uint32_t)xslot_bytes) >> 4;
+          const uint32_t xb2 = (x_addr + s2 * (uint32_t)xslot_bytes) >> 4;
+#pragma unroll
           for (int k = 0; k < kWuTaps; ++k) {
-            const long long lt = mt + rr + P.ra[k];
-            const uint32_t b0 = x_addr + (uint32_t)(lt % P.xslots) * (uint32_t)xslot_bytes + (uint32_t)P.sh[par][k] * 16u;
+            const int ra = P.ra[k];
+            uint32_t b_lo = (ra == 0 ? xb0 : (ra == 1 ? xb1 : xb2)) + (uint32_t)P.sh[par][k] + lo_const;
+            uint32_t a_lo = a_lo0;
             const uint32_t d_tmem = tmem_base + (uint32_t)(k * P.Cin);
-            for (int j = 0; j < kWuTile / 16; ++j)
-              ptx::umma_bf16(d_tmem, wu_desc(a0 + (uint32_t)j * 256u, 128, sbo_g), wu_desc(b0 + (uint32_t)j * 256u, 128, sbo_x), idesc,
-                             started | (uint32_t)j);
+#pragma unroll
+            for (int j = 0; j < kWuTile / 16; ++j) {
+              ptx::umma_bf16(d_tmem, ((uint64_t)g_hi << 32) | a_lo, ((uint64_t)x_hi << 32) | b_lo, idesc, started | (uint32_t)j);
+              a_lo += 16; b_lo += 16;                       // 16 pixels = 256 bytes
+            }
           }
           if (P.has_bias) {
-            const uint64_t od = wu_desc(o_addr, 128, 256);
-            for (int j = 0; j < kWuTile / 16; ++j)
-              ptx::umma_bf16(tmem_base + (uint32_t)bias_col, wu_desc(a0 + (uint32_t)j * 256u, 128, sbo_g), od, idesc_b, started | (uint32_t)j);
+            uint32_t a_lo = a_lo0;
+#pragma unroll
+            for (int j = 0; j < kWuTile / 16; ++j) {
+              ptx::umma_bf16(tmem_base + (uint32_t)bias_col, ((uint64_t)g_hi << 32) | a_lo, od, idesc_b, started | (uint32_t)j);
+              a_lo += 16;
+            }
           }
           started = 1;
           ptx::umma_commit(&gempty[gs]);
-          ptx::umma_commit(&xempty[(mt + rr) % P.xslots]);
+          ptx::umma_commit(&xempty[slot0]);
           if (rr == rows - 1) {
-            ptx::umma_commit(&xempty[(mt + rows) % P.xslots]);
-            ptx::umma_commit(&xempty[(mt + rows + 1) % P.xslots]);
+            ptx::umma_commit(&xempty[s1]);
+            ptx::umma_commit(&xempty[s2]);
           }
         }
         __syncwarp();
+        next_slot(slot0, phase0);
+        if (++gs == (uint32_t)kWuGSlots) { gs = 0; gphase ^= 1; }
       }
-      mt += rows + 2;
+      next_slot(slot0, phase0);
+      next_slot(slot0, phase0);
     }
     if (lane == 0) ptx::umma_commit(done);
     __syncwarp();
