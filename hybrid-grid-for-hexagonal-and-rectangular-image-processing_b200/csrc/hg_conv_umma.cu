@@ -113,7 +113,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the issue loop
 
   const int per_n = P.bands * P.ctiles;
 
@@ -248,7 +248,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
         ptx::mbar_wait(&full[s2], p2);
         ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
         ptx::tc_fence_after_sync();
-        if (lane == 0) {
+        {
           const int par = (r0 + rr) & 1;
           const uint32_t d_tmem = tmem_base + acc * (uint32_t)P.Nout;
           const uint32_t rb0 = (ring_addr + slot0 * (uint32_t)slot_bytes) >> 4;
@@ -261,18 +261,16 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
             uint32_t a_lo = (ra == 0 ? rb0 : (ra == 1 ? rb1 : rb2)) + (uint32_t)P.sh[par][k] + a_lo_const;
             uint32_t b_lo = ((w_addr + (uint32_t)k * (uint32_t)wtap_bytes) >> 4) + b_lo_const;
             for (int j = 0; j < ksteps; ++j) {
-              const uint64_t ad = ((uint64_t)desc_hi << 32) | a_lo;
-              const uint64_t bd = ((uint64_t)desc_hi << 32) | b_lo;
-              ptx::umma_bf16(d_tmem, ad, bd, idesc, accum);
+              ptx::umma_bf16_elect(d_tmem, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, accum);
               accum = 1;
               a_lo += a_step; b_lo += b_step;
             }
           }
-          ptx::umma_commit(&tfull[acc]);                         // accumulator ready for the epilogue
-          ptx::umma_commit(&empty[slot0]);                       // input row rr is not needed any more
+          ptx::umma_commit_elect(&tfull[acc]);                   // accumulator ready for the epilogue
+          ptx::umma_commit_elect(&empty[slot0]);                 // input row rr is not needed any more
           if (rr == rows - 1) {                                  // band done: release its two trailing rows too
-            ptx::umma_commit(&empty[s1]);
-            ptx::umma_commit(&empty[s2]);
+            ptx::umma_commit_elect(&empty[s1]);
+            ptx::umma_commit_elect(&empty[s2]);
           }
         }
         __syncwarp();
