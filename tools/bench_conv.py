@@ -40,6 +40,8 @@ def main():
     ap.add_argument("--hw", type=int, default=256)
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--direct", action="store_true", help="also time the CUDA-core direct stencil (slow at 64x64)")
+    ap.add_argument("--only", default="", help="comma list of ops to run (fwd,dgrad,wgrad); default all")
+    ap.add_argument("--dtypes", default="", help="e.g. f32f32 to run a single activation dtype pair")
     a = ap.parse_args()
     N, Ci, Co, H = a.batch, a.cin, a.cout, a.hw
     dev = "cuda"
@@ -50,7 +52,12 @@ def main():
     res = {"config": f"HexConv2d {Ci}->{Co} r=2 s=1 pad=1, {N}x{Ci}x{H}x{H}", "flop_per_pass": flops, "rows": []}
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     hbm, tf = peaks.get("hbm_gbs", 6650.0), peaks.get("bf16_tflops_sustained", 1400.0)
-    for xdt, ydt in ((torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16), (torch.bfloat16, torch.float32)):
+    pairs = ((torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16), (torch.bfloat16, torch.float32))
+    if a.dtypes == "f32f32":
+        pairs = pairs[:1]
+    elif a.dtypes == "bf16bf16":
+        pairs = pairs[1:2]
+    for xdt, ydt in pairs:
         x = torch.randn(N, Ci, H, H, device=dev).to(xdt)
         gy = torch.randn(N, Co, H, H, device=dev).to(ydt)
         y = torch.empty(N, Co, H, H, device=dev, dtype=ydt)
@@ -68,6 +75,8 @@ def main():
                     ops["wgrad(direct)"] = lambda: nv.call("hg_hexconv_wgrad", C.byref(dw), nv.ptr(x), nv.ptr(gy), nv.ptr(gw), nv.ptr(gb), st)
             else:
                 ops["wgrad"] = lambda: nv.call("hg_hexconv_wgrad", C.byref(d), nv.ptr(x), nv.ptr(gy), nv.ptr(gw), nv.ptr(gb), st)
+            if a.only:
+                ops = {k: v for k, v in ops.items() if k.split("(")[0] in a.only.split(",")}
             for name, fn in ops.items():
                 reps = a.reps if "direct" not in name and algo == 2 else max(1, a.reps // 5)
                 ms = timeit(fn, reps)
