@@ -76,13 +76,13 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
   unsigned char* ring = smem + kTaps * wtap_bytes;                // [slot][Cred/8][PW][8] bf16
   unsigned char* raw = ring + P.slots * slot_bytes;               // [rstage][Cred][PW] TIN (TMA variant)
   float* bias_s = reinterpret_cast<float*>(raw + (size_t)P.rstages * P.raw_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + P.Nout);
-  uint64_t* full = bars;                    // [slots]  loaders -> MMA        (count kUmLoaders)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + ((P.Nout + 31) & ~31));
+  uint64_t* full = bars;                    // [slots]  loaders -> MMA        (one arrival per loader warp)
   uint64_t* empty = bars + P.slots;         // [slots]  MMA commit -> loaders (count 1)
   uint64_t* tfull = empty + P.slots;        // [2]      MMA commit -> epilogue
   uint64_t* tempty = tfull + 2;             // [2]      epilogue -> MMA       (count 128)
   uint64_t* rfull = tempty + 2;             // [rstages] TMA bytes landed
-  uint64_t* rempty = rfull + P.rstages;     // [rstages] converters done      (count kUmLoaders)
+  uint64_t* rempty = rfull + P.rstages;     // [rstages] converters done      (one arrival per warp)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + P.rstages);
 
   // ---- one-time setup ---------------------------------------------------------------------------------
@@ -98,12 +98,12 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
                                     : __ldg(w + ((size_t)n * P.Cred + red) * kTaps + k);     // w[co=n][ci=red][k]
       reinterpret_cast<__nv_bfloat16*>(w_smem)[e] = __float2bfloat16_rn(v);
     }
-    for (int e = tid; e < P.Nout; e += kUmThreads) bias_s[e] = P.has_bias ? __ldg(bias + e) : 0.f;
+    for (int e = tid; e < ((P.Nout + 31) & ~31); e += kUmThreads) bias_s[e] = (P.has_bias && e < P.Nout) ? __ldg(bias + e) : 0.f;
   }
   if (tid == 0) {
-    for (int s = 0; s < P.slots; ++s) { ptx::mbar_init(&full[s], kUmLoaders); ptx::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < P.slots; ++s) { ptx::mbar_init(&full[s], kUmLoaders / 32); ptx::mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull[s], 1); ptx::mbar_init(&tempty[s], 128); }
-    for (int s = 0; s < P.rstages; ++s) { ptx::mbar_init(&rfull[s], 1); ptx::mbar_init(&rempty[s], kUmLoaders); }
+    for (int s = 0; s < P.rstages; ++s) { ptx::mbar_init(&rfull[s], 1); ptx::mbar_init(&rempty[s], kUmLoaders / 32); }
     if (TMA) ptx::prefetch_tensormap(&tmap);
     ptx::fence_barrier_init();
   }
@@ -147,7 +147,8 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
               for (int e = 0; e < 8; ++e) v[q][e] = to_f32(rp[(kc * 8 + e) * kUmPW + p]);
             }
           }
-          ptx::mbar_arrive(&rempty[rs]);     // values are in registers: the stage can be refilled
+          __syncwarp();                      // the whole warp holds its values in registers:
+          if (lane == 0) ptx::mbar_arrive(&rempty[rs]);   // one arrival per warp, the stage can be refilled
           ptx::mbar_wait(&empty[slot], (use & 1) ^ 1);
         } else {
           ptx::mbar_wait(&empty[slot], (use & 1) ^ 1);
@@ -179,7 +180,8 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
           }
         }
         ptx::fence_proxy_async_smem();       // generic-proxy smem writes -> visible to tcgen05.mma
-        ptx::mbar_arrive(&full[slot]);
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&full[slot]);    // one arrival per converter warp
       }
     }
   } else if (warp < 12) {
@@ -201,16 +203,32 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
         for (int cb = 0; cb < P.Nout; cb += 32) {
           uint32_t v[32];
           ptx::tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * (uint32_t)P.Nout + (uint32_t)cb, v);
+          // bias of this chunk in registers (8 vector LDS in flight together with the TMEM load) -- a scalar
+          // LDS in front of every FADD serialises the epilogue on shared-memory latency (ncu r1i).
+          float4 bb[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bb[i] = *reinterpret_cast<const float4*>(bias_s + cb + 4 * i);
           ptx::tmem_ld_wait();
-          if (cb + 32 >= P.Nout) {           // last chunk read: hand the accumulator back to the MMA warp
+          const bool last = cb + 32 >= P.Nout;
+          if (last) {                        // accumulator fully read: hand it back to the MMA warp
             ptx::tc_fence_before_sync();
             ptx::mbar_arrive(&tempty[acc]);
           }
           if (c < P.Wo) {
+            const int nvalid = min(32, P.Nout - cb);      // warp-uniform; 32 except for a trailing 16-channel chunk
+            const float* bf = reinterpret_cast<const float*>(bb);
+            if (nvalid == 32) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (cb + j < P.Nout) {
-                float f = __uint_as_float(v[j]) + bias_s[cb + j];
+              for (int j = 0; j < 32; ++j) {
+                float f = __uint_as_float(v[j]) + bf[j];
+                if (P.relu) f = fmaxf(f, 0.f);
+                st_out(op, f);
+                op += cstride;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float f = __uint_as_float(v[j]) + bf[j];
                 if (P.relu) f = fmaxf(f, 0.f);
                 st_out(op, f);
                 op += cstride;
@@ -312,7 +330,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
 static int g_um_sms = 0, g_um_smem_max = 0;
 
 static size_t umma_smem_bytes(int Cred, int Nout, int slots, int rstages, int raw_bytes) {
-  return (size_t)kTaps * Cred * Nout * 2 + (size_t)slots * Cred * kUmPW * 2 + (size_t)rstages * raw_bytes + (size_t)Nout * 4 +
+  return (size_t)kTaps * Cred * Nout * 2 + (size_t)slots * Cred * kUmPW * 2 + (size_t)rstages * raw_bytes + (size_t)((Nout + 31) & ~31) * 4 +
          (size_t)(2 * slots + 4 + 2 * rstages) * 8 + 16;
 }
 

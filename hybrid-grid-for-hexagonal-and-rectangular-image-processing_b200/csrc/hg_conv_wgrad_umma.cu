@@ -14,21 +14,27 @@
 // round of fp32 atomics at the end.  UMMA M is 128: rows 64..127 of the A view run past the Cout = 64
 // channel groups into the neighbouring ring memory; those accumulator lanes are never read.
 //
-// CTA = 14 warps: warps 0-7 loaders (x rows and gy rows -> bf16 -> rings), warps 8-11 final epilogue,
-// warp 12 MMA issuer + TMEM allocator, warp 13 idle (reserved for a TMA producer).
+// CTA = 14 warps: warps 0-11 converters (x rows and gy rows -> bf16 -> rings; warps 8-11 also run the final
+// epilogue), warp 12 MMA issuer + TMEM allocator, warp 13 TMA producer.  Input path as in hg_conv_umma.cu:
+//   TMA : 4-D boxes [C][1 row][px] of x and gy land in a shared raw staging ring (zero-fill of halos and of the
+//         columns past Wo for free); needs pad_value == 0 and 16-byte aligned rows of both tensors.
+//   LDG : coalesced global loads (any pad value / width).
 #include "hg_conv.cuh"
 #include "hg_ptx.cuh"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace hg {
 
 constexpr int kWuTile = 128;
 constexpr int kWuPW = 144;
-constexpr int kWuLoaders = 256;
+constexpr int kWuConv = 384;                 // converter threads (warps 0-11)
+constexpr int kWuConvWarps = kWuConv / 32;
 constexpr int kWuThreads = 448;
 constexpr int kWuBand = 32;
-constexpr int kWuMaxQ = 5;
+constexpr int kWuMaxQ = 3;                   // ceil(8 * 144 / 384)
 constexpr int kWuTaps = 7;
-constexpr int kWuGSlots = 3;
 
 struct WgParams {
   int N, Cin, Cout, H, W, Ho, Wo;
@@ -37,7 +43,8 @@ struct WgParams {
   int sh[2][kWuTaps];
   int pad;
   float pad_value;
-  int xslots, bands, ctiles, has_bias;
+  int xslots, gslots, bands, ctiles, has_bias;
+  int rstages, raw_bytes;        // TMA variant
   long long items;
 };
 
@@ -57,30 +64,36 @@ __host__ __device__ constexpr uint32_t wu_idesc(int M, int N) {   // bf16 x bf16
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <typename TX, typename TG>
+template <typename TX, typename TG, bool TMA>
 __global__ void __launch_bounds__(kWuThreads, 1)
-hexconv_wgrad_umma_kernel(const TX* __restrict__ x, const TG* __restrict__ gy, float* __restrict__ gw, float* __restrict__ gb,
+hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap gmap,
+                          const TX* __restrict__ x, const TG* __restrict__ gy, float* __restrict__ gw, float* __restrict__ gb,
                           WgParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gslot_bytes = P.Cout * kWuTile * 2;         // [Cout/8][128 px][16 B]
   const int xslot_bytes = P.Cin * kWuPW * 2;            // [Cin/8][PW px][16 B]
   unsigned char* gring = smem;                          // gy ring first: its M = 128 view may run into the x ring
-  unsigned char* xring = gring + kWuGSlots * gslot_bytes;
-  unsigned char* ones = xring + P.xslots * xslot_bytes; // 512 B of bf16 1.0 (bias accumulator operand)
+  unsigned char* xring = gring + P.gslots * gslot_bytes;
+  unsigned char* raw = xring + P.xslots * xslot_bytes;  // [rstage] raw rows (TMA variant)
+  unsigned char* ones = raw + (size_t)P.rstages * P.raw_bytes;   // 512 B of bf16 1.0 (bias accumulator operand)
   uint64_t* bars = reinterpret_cast<uint64_t*>(ones + 512);
-  uint64_t* xfull = bars;                   // [xslots]
-  uint64_t* xempty = xfull + P.xslots;      // [xslots]
-  uint64_t* gfull = xempty + P.xslots;      // [kWuGSlots]
-  uint64_t* gempty = gfull + kWuGSlots;     // [kWuGSlots]
-  uint64_t* done = gempty + kWuGSlots;      // [1]
+  uint64_t* xfull = bars;                   // [xslots]   converters -> MMA   (one arrival per converter warp)
+  uint64_t* xempty = xfull + P.xslots;      // [xslots]   MMA commit -> converters
+  uint64_t* gfull = xempty + P.xslots;      // [gslots]
+  uint64_t* gempty = gfull + P.gslots;      // [gslots]
+  uint64_t* rfull = gempty + P.gslots;      // [rstages]  TMA bytes landed
+  uint64_t* rempty = rfull + P.rstages;     // [rstages]  converters done
+  uint64_t* done = rempty + P.rstages;      // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
   for (int e = tid; e < 256; e += kWuThreads) reinterpret_cast<__nv_bfloat16*>(ones)[e] = __float2bfloat16_rn(1.f);
   if (tid == 0) {
-    for (int s = 0; s < P.xslots; ++s) { ptx::mbar_init(&xfull[s], kWuLoaders); ptx::mbar_init(&xempty[s], 1); }
-    for (int s = 0; s < kWuGSlots; ++s) { ptx::mbar_init(&gfull[s], kWuLoaders); ptx::mbar_init(&gempty[s], 1); }
+    for (int s = 0; s < P.xslots; ++s) { ptx::mbar_init(&xfull[s], kWuConvWarps); ptx::mbar_init(&xempty[s], 1); }
+    for (int s = 0; s < P.gslots; ++s) { ptx::mbar_init(&gfull[s], kWuConvWarps); ptx::mbar_init(&gempty[s], 1); }
+    for (int s = 0; s < P.rstages; ++s) { ptx::mbar_init(&rfull[s], 1); ptx::mbar_init(&rempty[s], kWuConvWarps); }
     ptx::mbar_init(done, 1);
+    if (TMA) { ptx::prefetch_tensormap(&xmap); ptx::prefetch_tensormap(&gmap); }
     ptx::fence_barrier_init();
   }
   if (warp == 12) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
@@ -92,75 +105,108 @@ hexconv_wgrad_umma_kernel(const TX* __restrict__ x, const TG* __restrict__ gy, f
   const int per_n = P.bands * P.ctiles;
   const int bias_col = kWuTaps * P.Cin;
 
-  if (warp < 8) {
-    // ===== loaders =========================================================================================
+  if (warp < kWuConvWarps) {
+    // ===== converters ========================================================================================
     const size_t xplane = (size_t)P.H * P.W, gplane = (size_t)P.Ho * P.Wo;
     const int xtasks = (P.Cin >> 3) * kWuPW, gtasks = (P.Cout >> 3) * kWuTile;
-    long long xt = 0, gt = 0;
-    auto load_x = [&](const TX* __restrict__ xn, int i, int c0) {
-      const int slot = (int)(xt % P.xslots);
-      ptx::mbar_wait(&xempty[slot], (uint32_t)(((xt / P.xslots) & 1) ^ 1));
-      const bool row_in = i >= 0 && i < P.H, row_frame = i >= -P.pad && i < P.H + P.pad;
-      unsigned char* sb = xring + (size_t)slot * xslot_bytes;
-      float v[kWuMaxQ][8];
-#pragma unroll
-      for (int q = 0; q < kWuMaxQ; ++q) {
-        const int task = tid + q * kWuLoaders;
-        if (task < xtasks) {
-          const int kc = task / kWuPW, p = task - kc * kWuPW;
-          const int j = c0 + P.col0 + p;
-          const bool col_in = j >= 0 && j < P.W;
-          const float fill = (row_frame && j >= -P.pad && j < P.W + P.pad) ? P.pad_value : 0.f;
-          const TX* __restrict__ src = xn + (size_t)(kc * 8) * xplane + (size_t)i * P.W + j;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[q][e] = (row_in && col_in) ? wu_ld(src + (size_t)e * xplane) : fill;
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < kWuMaxQ; ++q) {
-        const int task = tid + q * kWuLoaders;
-        if (task < xtasks) {
-          uint4 pk;
-          pk.x = wu_pack(v[q][0], v[q][1]); pk.y = wu_pack(v[q][2], v[q][3]);
-          pk.z = wu_pack(v[q][4], v[q][5]); pk.w = wu_pack(v[q][6], v[q][7]);
-          *reinterpret_cast<uint4*>(sb + (size_t)task * 16) = pk;
-        }
-      }
+    uint32_t xs = 0, xph = 0, gs = 0, gph = 0, rs = 0, rph = 0;      // ring positions / parities
+    auto pack_store = [&](unsigned char* sb, int task, const float (&v)[8]) {
+      uint4 pk;
+      pk.x = wu_pack(v[0], v[1]); pk.y = wu_pack(v[2], v[3]); pk.z = wu_pack(v[4], v[5]); pk.w = wu_pack(v[6], v[7]);
+      *reinterpret_cast<uint4*>(sb + (size_t)task * 16) = pk;
+    };
+    auto publish = [&](uint64_t* bar) {     // all of this warp's writes fenced, then one arrival per warp
       ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&xfull[slot]);
-      ++xt;
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar);
+    };
+    auto raw_done = [&]() {                 // this warp has the raw row in registers
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&rempty[rs]);
+      if (++rs == (uint32_t)P.rstages) { rs = 0; rph ^= 1; }
+    };
+    auto load_x = [&](const TX* __restrict__ xn, int i, int c0) {
+      unsigned char* sb = xring + (size_t)xs * xslot_bytes;
+      float v[kWuMaxQ][8];
+      if (TMA) {
+        ptx::mbar_wait(&rfull[rs], rph);
+        const TX* __restrict__ rp = reinterpret_cast<const TX*>(raw + (size_t)rs * P.raw_bytes);
+#pragma unroll
+        for (int q = 0; q < kWuMaxQ; ++q) {
+          const int task = tid + q * kWuConv;
+          if (task < xtasks) {
+            const int kc = task / kWuPW, p = task - kc * kWuPW;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[q][e] = to_f32(rp[(kc * 8 + e) * kWuPW + p]);
+          }
+        }
+        raw_done();
+        ptx::mbar_wait(&xempty[xs], xph ^ 1);
+      } else {
+        ptx::mbar_wait(&xempty[xs], xph ^ 1);
+        const bool row_in = i >= 0 && i < P.H, row_frame = i >= -P.pad && i < P.H + P.pad;
+#pragma unroll
+        for (int q = 0; q < kWuMaxQ; ++q) {
+          const int task = tid + q * kWuConv;
+          if (task < xtasks) {
+            const int kc = task / kWuPW, p = task - kc * kWuPW;
+            const int j = c0 + P.col0 + p;
+            const bool col_in = j >= 0 && j < P.W;
+            const float fill = (row_frame && j >= -P.pad && j < P.W + P.pad) ? P.pad_value : 0.f;
+            const TX* __restrict__ src = xn + (size_t)(kc * 8) * xplane + (size_t)i * P.W + j;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[q][e] = (row_in && col_in) ? wu_ld(src + (size_t)e * xplane) : fill;
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kWuMaxQ; ++q) {
+        const int task = tid + q * kWuConv;
+        if (task < xtasks) pack_store(sb, task, v[q]);
+      }
+      publish(&xfull[xs]);
+      if (++xs == (uint32_t)P.xslots) { xs = 0; xph ^= 1; }
     };
     auto load_g = [&](const TG* __restrict__ gn, int R, int c0) {
-      const int slot = (int)(gt % kWuGSlots);
-      ptx::mbar_wait(&gempty[slot], (uint32_t)(((gt / kWuGSlots) & 1) ^ 1));
-      unsigned char* sb = gring + (size_t)slot * gslot_bytes;
-      for (int base = 0; base < gtasks; base += kWuMaxQ * kWuLoaders) {   // Cout = 128 needs two passes
+      unsigned char* sb = gring + (size_t)gs * gslot_bytes;
+      bool waited = false;
+      for (int base = 0; base < gtasks; base += kWuMaxQ * kWuConv) {   // Cout = 128 needs two passes
         float v[kWuMaxQ][8];
+        if (TMA) {
+          if (base == 0) ptx::mbar_wait(&rfull[rs], rph);
+          const TG* __restrict__ rp = reinterpret_cast<const TG*>(raw + (size_t)rs * P.raw_bytes);
 #pragma unroll
-        for (int q = 0; q < kWuMaxQ; ++q) {
-          const int task = base + tid + q * kWuLoaders;
-          if (task < gtasks) {
-            const int kc = task / kWuTile, p = task - kc * kWuTile;
-            const int c = c0 + p;
-            const TG* __restrict__ src = gn + (size_t)(kc * 8) * gplane + (size_t)R * P.Wo + c;
+          for (int q = 0; q < kWuMaxQ; ++q) {
+            const int task = base + tid + q * kWuConv;
+            if (task < gtasks) {
+              const int kc = task / kWuTile, p = task - kc * kWuTile;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[q][e] = c < P.Wo ? wu_ld(src + (size_t)e * gplane) : 0.f;
+              for (int e = 0; e < 8; ++e) v[q][e] = to_f32(rp[(kc * 8 + e) * kWuTile + p]);
+            }
+          }
+          if (base + kWuMaxQ * kWuConv >= gtasks) raw_done();
+        } else {
+#pragma unroll
+          for (int q = 0; q < kWuMaxQ; ++q) {
+            const int task = base + tid + q * kWuConv;
+            if (task < gtasks) {
+              const int kc = task / kWuTile, p = task - kc * kWuTile;
+              const int c = c0 + p;
+              const TG* __restrict__ src = gn + (size_t)(kc * 8) * gplane + (size_t)R * P.Wo + c;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[q][e] = c < P.Wo ? wu_ld(src + (size_t)e * gplane) : 0.f;
+            }
           }
         }
+        if (!waited) { ptx::mbar_wait(&gempty[gs], gph ^ 1); waited = true; }
 #pragma unroll
         for (int q = 0; q < kWuMaxQ; ++q) {
-          const int task = base + tid + q * kWuLoaders;
-          if (task < gtasks) {
-            uint4 pk;
-            pk.x = wu_pack(v[q][0], v[q][1]); pk.y = wu_pack(v[q][2], v[q][3]);
-            pk.z = wu_pack(v[q][4], v[q][5]); pk.w = wu_pack(v[q][6], v[q][7]);
-            *reinterpret_cast<uint4*>(sb + (size_t)task * 16) = pk;
-          }
+          const int task = base + tid + q * kWuConv;
+          if (task < gtasks) pack_store(sb, task, v[q]);
         }
       }
-      ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&gfull[slot]);
-      ++gt;
+      publish(&gfull[gs]);
+      if (++gs == (uint32_t)P.gslots) { gs = 0; gph ^= 1; }
     };
     for (long long item = blockIdx.x; item < P.items; item += gridDim.x) {
       const int n = (int)(item / per_n);
@@ -174,6 +220,31 @@ hexconv_wgrad_umma_kernel(const TX* __restrict__ x, const TG* __restrict__ gy, f
       for (int rr = 0; rr < rows; ++rr) {
         load_x(xn, r0 + P.row0 + rr + 2, c0);
         load_g(gn, r0 + rr, c0);
+      }
+    }
+    if (warp >= 8) {
+      // ===== final epilogue (warps 8-11): TMEM partials -> fp32 atomics ======================================
+      const int q4 = warp & 3;
+      const int co = q4 * 32 + lane;
+      ptx::mbar_wait(done, 0);
+      ptx::tc_fence_after_sync();
+      for (int k = 0; k < kWuTaps; ++k) {
+        for (int cb = 0; cb < P.Cin; cb += 32) {
+          uint32_t v[32];
+          ptx::tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(k * P.Cin + cb), v);
+          ptx::tmem_ld_wait();
+          if (co < P.Cout) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (cb + j < P.Cin) atomicAdd(gw + ((size_t)co * P.Cin + cb + j) * kWuTaps + k, __uint_as_float(v[j]));
+          }
+        }
+      }
+      if (P.has_bias) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)bias_col, v);
+        ptx::tmem_ld_wait();
+        if (co < P.Cout) atomicAdd(gb + co, __uint_as_float(v[0]));
       }
     }
   } else if (warp == 12) {
@@ -236,36 +307,36 @@ hexconv_wgrad_umma_kernel(const TX* __restrict__ x, const TG* __restrict__ gy, f
         }
         __syncwarp();
         next_slot(slot0, phase0);
-        if (++gs == (uint32_t)kWuGSlots) { gs = 0; gphase ^= 1; }
+        if (++gs == (uint32_t)P.gslots) { gs = 0; gphase ^= 1; }
       }
       next_slot(slot0, phase0);
       next_slot(slot0, phase0);
     }
     ptx::umma_commit_elect(done);
     __syncwarp();
-  } else if (warp >= 8 && warp < 12) {
-    // ===== final epilogue: TMEM partials -> fp32 atomics ====================================================
-    const int q4 = warp & 3;
-    const int co = q4 * 32 + lane;
-    ptx::mbar_wait(done, 0);
-    ptx::tc_fence_after_sync();
-    for (int k = 0; k < kWuTaps; ++k) {
-      for (int cb = 0; cb < P.Cin; cb += 32) {
-        uint32_t v[32];
-        ptx::tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(k * P.Cin + cb), v);
-        ptx::tmem_ld_wait();
-        if (co < P.Cout) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (cb + j < P.Cin) atomicAdd(gw + ((size_t)co * P.Cin + cb + j) * kWuTaps + k, __uint_as_float(v[j]));
+  } else if (TMA) {
+    // ===== TMA producer (warp 13, one lane): same row order as the converters =================================
+    if (lane == 0) {
+      uint32_t rs = 0, rph = 0;
+      auto push = [&](const CUtensorMap* m, uint32_t bytes, int c, int r, int n) {
+        ptx::mbar_wait(&rempty[rs], rph ^ 1);
+        ptx::mbar_arrive_expect_tx(&rfull[rs], bytes);
+        ptx::tma_load_4d(raw + (size_t)rs * P.raw_bytes, m, &rfull[rs], c, r, 0, n);
+        if (++rs == (uint32_t)P.rstages) { rs = 0; rph ^= 1; }
+      };
+      const uint32_t xbytes = (uint32_t)(P.Cin * kWuPW * (int)sizeof(TX)), gbytes = (uint32_t)(P.Cout * kWuTile * (int)sizeof(TG));
+      for (long long item = blockIdx.x; item < P.items; item += gridDim.x) {
+        const int n = (int)(item / per_n);
+        const int rem = (int)(item - (long long)n * per_n);
+        const int band = rem / P.ctiles, ct = rem - band * P.ctiles;
+        const int r0 = band * kWuBand, rows = min(kWuBand, P.Ho - r0), c0 = ct * kWuTile;
+        push(&xmap, xbytes, c0 + P.col0, r0 + P.row0 + 0, n);
+        push(&xmap, xbytes, c0 + P.col0, r0 + P.row0 + 1, n);
+        for (int rr = 0; rr < rows; ++rr) {
+          push(&xmap, xbytes, c0 + P.col0, r0 + P.row0 + rr + 2, n);
+          push(&gmap, gbytes, c0, r0 + rr, n);
         }
       }
-    }
-    if (P.has_bias) {
-      uint32_t v[32];
-      ptx::tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)bias_col, v);
-      ptx::tmem_ld_wait();
-      if (co < P.Cout) atomicAdd(gb + co, __uint_as_float(v[0]));
     }
   }
 
@@ -279,40 +350,62 @@ hexconv_wgrad_umma_kernel(const TX* __restrict__ x, const TG* __restrict__ gy, f
 
 // ---- host side --------------------------------------------------------------------------------------------
 static int g_wu_sms = 0, g_wu_smem_max = 0;
+static bool g_wu_no_tma = [] { const char* e = getenv("HG_CONV_NO_TMA"); return e && e[0] == '1'; }();
 
-static size_t wu_smem_bytes(int Cin, int Cout, int xslots) {
-  return (size_t)kWuGSlots * Cout * kWuTile * 2 + (size_t)xslots * Cin * kWuPW * 2 + 512 + (size_t)(2 * xslots + 2 * kWuGSlots + 1) * 8 + 16;
+static size_t wu_smem_bytes(int Cin, int Cout, int xslots, int gslots, int rstages, int raw_bytes) {
+  return (size_t)gslots * Cout * kWuTile * 2 + (size_t)xslots * Cin * kWuPW * 2 + (size_t)rstages * raw_bytes + 512 +
+         (size_t)(2 * xslots + 2 * gslots + 2 * rstages + 1) * 8 + 16;
 }
 
-static int wu_pick_slots(int Cin, int Cout) {
+static bool wu_limits() {
   if (g_wu_smem_max == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_wu_smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaDeviceGetAttribute(&g_wu_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaGetLastError() != cudaSuccess || g_wu_smem_max <= 0) { g_wu_smem_max = 0; return 0; }
+    if (cudaGetLastError() != cudaSuccess || g_wu_smem_max <= 0) { g_wu_smem_max = 0; return false; }
   }
-  for (int s = 6; s >= 4; --s)
-    if (wu_smem_bytes(Cin, Cout, s) <= (size_t)g_wu_smem_max) return s;
-  return 0;
+  return true;
+}
+
+// the M = 128 view of the last gy slot runs (16 - Cout/8) channel groups past it: that must stay inside the x ring
+static bool wu_view_fits(int Cin, int Cout, int xslots) {
+  return (size_t)(16 - Cout / 8) * kWuTile * 16 <= (size_t)xslots * Cin * kWuPW * 2;
+}
+
+static bool wu_pick(int Cin, int Cout, int xes, int ges, bool tma, int& xslots, int& gslots, int& rstages, int& raw_bytes) {
+  xslots = gslots = rstages = raw_bytes = 0;
+  if (!wu_limits()) return false;
+  if (tma) {
+    const int64_t xb = (int64_t)Cin * kWuPW * xes, gb = (int64_t)Cout * kWuTile * ges;
+    raw_bytes = (int)ceil_div(xb > gb ? xb : gb, 128) * 128;
+  }
+  for (int r = tma ? 3 : 0; r >= (tma ? 2 : 0); --r)
+    for (int g = 3; g >= 2; --g)
+      for (int xsl = 6; xsl >= 4; --xsl)
+        if (wu_smem_bytes(Cin, Cout, xsl, g, r, raw_bytes) <= (size_t)g_wu_smem_max && wu_view_fits(Cin, Cout, xsl)) {
+          xslots = xsl; gslots = g; rstages = r;
+          return true;
+        }
+  raw_bytes = 0;
+  return false;
 }
 
 bool conv_wgrad_umma_eligible(const hg_conv_desc* d) {
   if (d->radius != 2 || d->stride != 1 || d->dilation != 1 || d->groups != 1) return false;
   if (d->Cin % 16 != 0 || d->Cin < 16 || d->Cin > 64) return false;        // 7*Cin + 16 TMEM columns <= 512
   if (d->Cout % 8 != 0 || d->Cout < 8 || d->Cout > 128) return false;      // UMMA M = 128 rows of 8-channel groups
-  // the M = 128 view of the last gy slot runs (16 - Cout/8) channel groups past it: that must stay inside the x ring
-  const int xslots = wu_pick_slots((int)d->Cin, (int)d->Cout);
-  if (xslots == 0) return false;
-  if ((size_t)(16 - d->Cout / 8) * kWuTile * 16 > (size_t)xslots * d->Cin * kWuPW * 2) return false;
+  int a, b, c, e;
+  if (!wu_pick((int)d->Cin, (int)d->Cout, 4, 4, false, a, b, c, e)) return false;
   if (d->algo == 0 && (d->x_dtype != HG_BF16 || d->Cin * d->Cout < 32 * 32)) return false;
   return true;
 }
 
-template <typename TX, typename TG>
-static int launch_wu(const void* x, const void* gy, float* gw, float* gb, const WgParams& P, cudaStream_t st) {
-  const size_t smem = wu_smem_bytes(P.Cin, P.Cout, P.xslots);
-  auto kern = hexconv_wgrad_umma_kernel<TX, TG>;
+template <typename TX, typename TG, bool TMA>
+static int launch_wu(const CUtensorMap& xmap, const CUtensorMap& gmap, const void* x, const void* gy, float* gw, float* gb,
+                     const WgParams& P, cudaStream_t st) {
+  const size_t smem = wu_smem_bytes(P.Cin, P.Cout, P.xslots, P.gslots, P.rstages, P.raw_bytes);
+  auto kern = hexconv_wgrad_umma_kernel<TX, TG, TMA>;
   static thread_local size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -321,8 +414,53 @@ static int launch_wu(const void* x, const void* gy, float* gw, float* gb, const 
   }
   long long grid = g_wu_sms > 0 ? g_wu_sms : 148;
   if (grid > P.items) grid = P.items;
-  kern<<<(unsigned)grid, kWuThreads, smem, st>>>((const TX*)x, (const TG*)gy, gw, gb, P);
-  return finish_launch("hexconv_wgrad_umma");
+  kern<<<(unsigned)grid, kWuThreads, smem, st>>>(xmap, gmap, (const TX*)x, (const TG*)gy, gw, gb, P);
+  return finish_launch(TMA ? "hexconv_wgrad_umma_tma" : "hexconv_wgrad_umma");
+}
+
+template <typename T>
+static bool wu_encode(PFN_encodeTiled enc, CUtensorMap* m, const void* base, int Wd, int Hd, int Cd, int Nd, int box_w) {
+  constexpr int es = (int)sizeof(T);
+  const cuuint64_t gdim[4] = {(cuuint64_t)Wd, (cuuint64_t)Hd, (cuuint64_t)Cd, (cuuint64_t)Nd};
+  const cuuint64_t gstr[3] = {(cuuint64_t)Wd * es, (cuuint64_t)Wd * Hd * es, (cuuint64_t)Wd * Hd * Cd * es};
+  const cuuint32_t box[4] = {(cuuint32_t)box_w, 1, (cuuint32_t)Cd, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUtensorMapDataType dt = es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  return enc(m, dt, 4, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename TX, typename TG>
+static int launch_wu_any(const void* x, const void* gy, float* gw, float* gb, WgParams P, cudaStream_t st) {
+  alignas(64) CUtensorMap xmap, gmap;
+  memset(&xmap, 0, sizeof(xmap));
+  memset(&gmap, 0, sizeof(gmap));
+  constexpr int xes = (int)sizeof(TX), ges = (int)sizeof(TG), A = 16 / xes;
+  PFN_encodeTiled enc = get_encode_tiled();
+  bool tma = !g_wu_no_tma && enc != nullptr && P.pad_value == 0.f && ((int64_t)P.W * xes) % 16 == 0 && ((int64_t)P.Wo * ges) % 16 == 0 &&
+             (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(gy) & 15) == 0;
+  if (tma) {
+    int xs_, gs_, rst, rb;
+    tma = wu_pick(P.Cin, P.Cout, xes, ges, true, xs_, gs_, rst, rb);
+    if (tma) {
+      const int col0a = (int)(floor((double)P.col0 / A)) * A, e0 = P.col0 - col0a;
+      int smax = 0;
+      for (int par = 0; par < 2; ++par) for (int k = 0; k < kWuTaps; ++k) smax = max(smax, P.sh[par][k] + e0);
+      if (kWuTile + smax > kWuPW || !wu_encode<TX>(enc, &xmap, x, P.W, P.H, P.Cin, P.N, kWuPW) ||
+          !wu_encode<TG>(enc, &gmap, gy, P.Wo, P.Ho, P.Cout, P.N, kWuTile))
+        tma = false;
+      else {
+        P.col0 = col0a;
+        for (int par = 0; par < 2; ++par) for (int k = 0; k < kWuTaps; ++k) P.sh[par][k] += e0;
+        P.xslots = xs_; P.gslots = gs_; P.rstages = rst; P.raw_bytes = rb;
+        return launch_wu<TX, TG, true>(xmap, gmap, x, gy, gw, gb, P, st);
+      }
+    }
+  }
+  int rst, rb;
+  HG_REQUIRE(wu_pick(P.Cin, P.Cout, xes, ges, false, P.xslots, P.gslots, rst, rb), HG_E_UNSUPPORTED, "hexconv_wgrad_umma: shared memory does not fit");
+  P.rstages = 0; P.raw_bytes = 0;
+  return launch_wu<TX, TG, false>(xmap, gmap, x, gy, gw, gb, P, st);
 }
 
 int conv_wgrad_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp, const void* x, const void* gy, float* gw,
@@ -332,7 +470,7 @@ int conv_wgrad_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp
   int cmin = 1 << 30, cmax = -(1 << 30);
   for (int par = 0; par < 2; ++par)
     for (int k = 0; k < kWuTaps; ++k) { cmin = min(cmin, tp.co[par][k]); cmax = max(cmax, tp.co[par][k]); }
-  HG_REQUIRE(tp.K == kWuTaps && cmax - cmin <= kWuPW - kWuTile, HG_E_UNSUPPORTED, "hexconv_wgrad_umma: unexpected tap geometry");
+  HG_REQUIRE(tp.K == kWuTaps && cmax - cmin <= 3, HG_E_UNSUPPORTED, "hexconv_wgrad_umma: unexpected tap geometry");
   for (int k = 0; k < kWuTaps; ++k) {
     P.ra[k] = tp.ro[k];
     for (int par = 0; par < 2; ++par) P.sh[par][k] = tp.co[par][k] - cmin;
@@ -343,13 +481,11 @@ int conv_wgrad_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp
   P.bands = (int)ceil_div(g.Ho, kWuBand);
   P.ctiles = (int)ceil_div(g.Wo, kWuTile);
   P.items = (long long)g.N * P.bands * P.ctiles;
-  P.xslots = wu_pick_slots(g.Cin, g.Cout);
-  HG_REQUIRE(P.xslots > 0, HG_E_UNSUPPORTED, "hexconv_wgrad_umma: shared memory does not fit");
   const int xdt = d->x_dtype, gdt = d->y_dtype;
-  if (xdt == HG_F32 && gdt == HG_F32) return launch_wu<float, float>(x, gy, gw, gbias, P, st);
-  if (xdt == HG_BF16 && gdt == HG_F32) return launch_wu<__nv_bfloat16, float>(x, gy, gw, gbias, P, st);
-  if (xdt == HG_F32 && gdt == HG_BF16) return launch_wu<float, __nv_bfloat16>(x, gy, gw, gbias, P, st);
-  if (xdt == HG_BF16 && gdt == HG_BF16) return launch_wu<__nv_bfloat16, __nv_bfloat16>(x, gy, gw, gbias, P, st);
+  if (xdt == HG_F32 && gdt == HG_F32) return launch_wu_any<float, float>(x, gy, gw, gbias, P, st);
+  if (xdt == HG_BF16 && gdt == HG_F32) return launch_wu_any<__nv_bfloat16, float>(x, gy, gw, gbias, P, st);
+  if (xdt == HG_F32 && gdt == HG_BF16) return launch_wu_any<float, __nv_bfloat16>(x, gy, gw, gbias, P, st);
+  if (xdt == HG_BF16 && gdt == HG_BF16) return launch_wu_any<__nv_bfloat16, __nv_bfloat16>(x, gy, gw, gbias, P, st);
   set_error("hexconv_wgrad_umma: unsupported dtypes x=%d gy=%d", xdt, gdt);
   return HG_E_DTYPE;
 }

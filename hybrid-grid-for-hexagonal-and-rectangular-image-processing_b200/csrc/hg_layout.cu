@@ -34,15 +34,18 @@ hex_to_type_kernel(const TS* __restrict__ hex, TD* __restrict__ out, int64_t tot
   int64_t r = t / Wt;
   int c = (int)(t - r * Wt);
   const int step_r = kLayoutThreads / Wt, step_c = kLayoutThreads % Wt;
+  // rows are tracked as (plane, row-in-plane) with carries: no division inside the loop
+  int64_t plane = r / Hout;
+  int ro = (int)(r - plane * Hout);
   for (; t < end; t += kLayoutThreads) {
-    const int64_t plane = r / Hout;
-    const int i = (int)(r - plane * Hout) / rows_mul;
+    const int i = rows_mul == 2 ? (ro >> 1) : ro;
     const int s = (i + offset) & 1;
     TD v = zero_of<TD>();
     if (c >= s && c < 2 * W + s) v = convert<TS, TD>(__ldg(hex + (plane * H + i) * (int64_t)W + ((c - s) >> 1)));
     out[t] = v;
-    r += step_r; c += step_c;
-    if (c >= Wt) { c -= Wt; ++r; }
+    ro += step_r; c += step_c;
+    if (c >= Wt) { c -= Wt; ++ro; }
+    while (ro >= Hout) { ro -= Hout; ++plane; }
   }
 }
 
@@ -57,12 +60,13 @@ type_to_hex_kernel(const TS* __restrict__ tin, TD* __restrict__ hex, int64_t tot
   int64_t r = t / W;
   int c = (int)(t - r * W);
   const int step_r = kLayoutThreads / W, step_c = kLayoutThreads % W;
+  int64_t plane = r / H;
+  int i = (int)(r - plane * H);
   for (; t < end; t += kLayoutThreads) {
-    const int64_t plane = r / H;
-    const int i = (int)(r - plane * H);
     hex[t] = convert<TS, TD>(__ldg(tin + (plane * Ht + (int64_t)i * rows_step) * Wt + 1 + 2 * c));
-    r += step_r; c += step_c;
-    if (c >= W) { c -= W; ++r; }
+    i += step_r; c += step_c;
+    if (c >= W) { c -= W; ++i; }
+    while (i >= H) { i -= H; ++plane; }
   }
 }
 
@@ -100,14 +104,15 @@ pad2d_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t total, int H, i
   int64_t r = t / Wo;
   int c = (int)(t - r * Wo);
   const int step_r = kLayoutThreads / Wo, step_c = kLayoutThreads % Wo;
+  int64_t plane = r / Ho;
+  int i = (int)(r - plane * Ho);
   for (; t < end; t += kLayoutThreads) {
-    const int64_t plane = r / Ho;
-    const int i = (int)(r - plane * Ho);
     bool in_r, in_c;
     const int si = pad_index(i - pt, H, mode, in_r), sj = pad_index(c - pl, W, mode, in_c);
     y[t] = (in_r && in_c) ? __ldg(x + (plane * H + si) * (int64_t)W + sj) : value;
-    r += step_r; c += step_c;
-    if (c >= Wo) { c -= Wo; ++r; }
+    i += step_r; c += step_c;
+    if (c >= Wo) { c -= Wo; ++i; }
+    while (i >= Ho) { i -= Ho; ++plane; }
   }
 }
 

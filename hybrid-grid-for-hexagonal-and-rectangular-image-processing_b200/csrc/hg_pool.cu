@@ -28,18 +28,21 @@ template <> __device__ __forceinline__ float ld_acc<__nv_bfloat16>(const __nv_bf
 template <typename T, typename A> __device__ __forceinline__ T st_acc(A v) { return (T)v; }
 template <> __device__ __forceinline__ __nv_bfloat16 st_acc<__nv_bfloat16, float>(float v) { return __float2bfloat16_rn(v); }
 
+// rows = planes * hn output rows; grid.x = rows * jtiles (one CTA = one output row segment of kPoolThreads cells).
 template <typename T, int METHOD, typename AUX>
 __global__ void __launch_bounds__(kPoolThreads)
-hexpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, AUX* __restrict__ aux, int64_t total, PoolGeom g,
-                   typename Acc<T>::type pad_value, typename Acc<T>::type tail_value) {
+hexpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, AUX* __restrict__ aux, unsigned jtiles, unsigned nrows, int tw_log2,
+                   PoolGeom g, typename Acc<T>::type pad_value, typename Acc<T>::type tail_value) {
   using A = typename Acc<T>::type;
-  const int64_t t = (int64_t)blockIdx.x * kPoolThreads + threadIdx.x;
-  if (t >= total) return;
-  const int J = (int)(t % g.wn);
-  const int64_t r = t / g.wn;
-  const int I = (int)(r % g.hn);
-  const int64_t plane = r / g.hn;
-  const T* __restrict__ xp = x + plane * (int64_t)g.H * g.W;
+  // CTA = (256 >> tw_log2) rows x (1 << tw_log2) columns, so narrow maps still fill the block
+  const unsigned rgrp = blockIdx.x / jtiles;
+  const unsigned row = rgrp * (kPoolThreads >> tw_log2) + (threadIdx.x >> tw_log2);
+  const int J = (int)((blockIdx.x - rgrp * jtiles) << tw_log2) + (int)(threadIdx.x & ((1u << tw_log2) - 1));
+  if (J >= g.wn || row >= nrows) return;
+  const unsigned plane = row / (unsigned)g.hn;
+  const int I = (int)(row - plane * (unsigned)g.hn);
+  const T* __restrict__ xp = x + (size_t)plane * g.H * g.W;
+  const size_t t = ((size_t)plane * g.hn + I) * g.wn + J;
   const int r0 = g.sh * I, c0 = ((I & 1) * g.shift) / 2 + J * g.sw;
   const int Hp = g.H + 2 * g.pad, Wp = g.W + 2 * g.pad;
   const A inf = (A)CUDART_INF;
@@ -47,15 +50,18 @@ hexpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, AUX* __restrict__
   A sum = 0;
   int slot = 0, cnt = 0;
   bool best_masked = false;
+  // interior window (no padding / tail cell touched): no per-cell bounds logic
+  const bool interior = g.pad == 0 && r0 + g.kh <= g.H && c0 + g.kw <= g.W;
   for (int a = 0; a < g.kh; ++a) {
     const int rr = r0 + a;
     for (int b = 0; b < g.kw; ++b) {
       const int cc = c0 + b;
       A v;
-      if (rr >= Hp || cc >= Wp) v = tail_value;
+      if (interior) v = ld_acc(xp + (size_t)rr * g.W + cc);
+      else if (rr >= Hp || cc >= Wp) v = tail_value;
       else {
         const int i = rr - g.pad, j = cc - g.pad;
-        v = (i >= 0 && i < g.H && j >= 0 && j < g.W) ? ld_acc(xp + (int64_t)i * g.W + j) : pad_value;
+        v = (i >= 0 && i < g.H && j >= 0 && j < g.W) ? ld_acc(xp + (size_t)i * g.W + j) : pad_value;
       }
       const bool nan = v != v;
       if (METHOD == HG_POOL_AVG) {
@@ -80,35 +86,56 @@ hexpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, AUX* __restrict__
 __device__ __forceinline__ int ceil_div_i(int a, int b) { return a >= 0 ? (a + b - 1) / b : -((-a) / b); }
 __device__ __forceinline__ int floor_div_i(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
 
-template <typename T, int METHOD, typename AUX>
+// rows = planes * H input rows; grid.x = rows * jtiles.  DISJOINT: windows do not overlap (kh <= sh, kw <= sw), so an
+// input cell belongs to at most one window and the gather is a single candidate.
+template <typename T, int METHOD, typename AUX, bool DISJOINT>
 __global__ void __launch_bounds__(kPoolThreads)
 hexpool_bwd_kernel(const T* __restrict__ gy, const AUX* __restrict__ aux, const T* __restrict__ x, T* __restrict__ gx,
-                   int64_t total, PoolGeom g) {
+                   unsigned jtiles, unsigned nrows, int tw_log2, PoolGeom g) {
   using A = typename Acc<T>::type;
-  const int64_t t = (int64_t)blockIdx.x * kPoolThreads + threadIdx.x;
-  if (t >= total) return;
-  const int j = (int)(t % g.W);
-  const int64_t r = t / g.W;
-  const int i = (int)(r % g.H);
-  const int64_t plane = r / g.H;
-  const int64_t ob = plane * (int64_t)g.hn * g.wn;
+  const unsigned rgrp = blockIdx.x / jtiles;
+  const unsigned row = rgrp * (kPoolThreads >> tw_log2) + (threadIdx.x >> tw_log2);
+  const int j = (int)((blockIdx.x - rgrp * jtiles) << tw_log2) + (int)(threadIdx.x & ((1u << tw_log2) - 1));
+  if (j >= g.W || row >= nrows) return;
+  const unsigned plane = row / (unsigned)g.H;
+  const int i = (int)(row - plane * (unsigned)g.H);
+  const size_t t = ((size_t)plane * g.H + i) * g.W + j;
+  const size_t ob = (size_t)plane * g.hn * g.wn;
   const int rr = i + g.pad, cc = j + g.pad;
   A acc = 0;
   bool live = true;
   if (METHOD == HG_POOL_AVG && x != nullptr) { const A v = ld_acc(x + t); live = (v == v); }
   if (live) {
-    const int I_lo = max(ceil_div_i(rr - g.kh + 1, g.sh), 0), I_hi = min(floor_div_i(rr, g.sh), g.hn - 1);
-    for (int I = I_lo; I <= I_hi; ++I) {
-      const int off = ((I & 1) * g.shift) / 2;
-      const int J_lo = max(ceil_div_i(cc - off - g.kw + 1, g.sw), 0), J_hi = min(floor_div_i(cc - off, g.sw), g.wn - 1);
-      for (int J = J_lo; J <= J_hi; ++J) {
-        const int64_t o = ob + (int64_t)I * g.wn + J;
-        if (METHOD == HG_POOL_AVG) {
-          const int cnt = (int)aux[o];
-          if (cnt > 0) acc += ld_acc(gy + o) / (A)cnt;
-        } else {
-          const int slot = (rr - g.sh * I) * g.kw + (cc - off - J * g.sw);
-          if ((int)aux[o] == slot) acc += ld_acc(gy + o);
+    if (DISJOINT) {
+      const int I = rr / g.sh;                       // warp-uniform
+      const int a = rr - I * g.sh;
+      if (I < g.hn && a < g.kh) {
+        const int cj = cc - ((I & 1) * g.shift) / 2;
+        if (cj >= 0) {
+          const int J = cj / g.sw, b = cj - J * g.sw;
+          if (J < g.wn && b < g.kw) {
+            const size_t o = ob + (size_t)I * g.wn + J;
+            if (METHOD == HG_POOL_AVG) {
+              const int cnt = (int)aux[o];
+              if (cnt > 0) acc = ld_acc(gy + o) / (A)cnt;
+            } else if ((int)aux[o] == a * g.kw + b) acc = ld_acc(gy + o);
+          }
+        }
+      }
+    } else {
+      const int I_lo = max(ceil_div_i(rr - g.kh + 1, g.sh), 0), I_hi = min(floor_div_i(rr, g.sh), g.hn - 1);
+      for (int I = I_lo; I <= I_hi; ++I) {
+        const int off = ((I & 1) * g.shift) / 2;
+        const int J_lo = max(ceil_div_i(cc - off - g.kw + 1, g.sw), 0), J_hi = min(floor_div_i(cc - off, g.sw), g.wn - 1);
+        for (int J = J_lo; J <= J_hi; ++J) {
+          const size_t o = ob + (size_t)I * g.wn + J;
+          if (METHOD == HG_POOL_AVG) {
+            const int cnt = (int)aux[o];
+            if (cnt > 0) acc += ld_acc(gy + o) / (A)cnt;
+          } else {
+            const int slot = (rr - g.sh * I) * g.kw + (cc - off - J * g.sw);
+            if ((int)aux[o] == slot) acc += ld_acc(gy + o);
+          }
         }
       }
     }
@@ -217,24 +244,41 @@ static int check_geom(int64_t planes, int64_t H, int64_t W, int64_t hn, int64_t 
 }
 
 template <typename T, typename AUX>
-static int launch_pool_fwd(const void* x, void* y, void* aux, int64_t total, const PoolGeom& g, double pv, double tv, int method, cudaStream_t st) {
+static int launch_pool_fwd(const void* x, void* y, void* aux, int64_t planes, const PoolGeom& g, double pv, double tv, int method, cudaStream_t st) {
   using A = typename Acc<T>::type;
-  const unsigned grid = (unsigned)ceil_div(total, kPoolThreads);
+  int tw_log2 = 5;
+  while ((1 << tw_log2) < g.wn && tw_log2 < 8) ++tw_log2;
+  const unsigned jtiles = (unsigned)ceil_div(g.wn, 1 << tw_log2);
+  const int64_t nrows64 = planes * g.hn;
+  const int64_t blocks = ceil_div(nrows64, kPoolThreads >> tw_log2) * jtiles;
+  HG_REQUIRE(blocks < (1ll << 31) && nrows64 < (1ll << 32), HG_E_SHAPE, "hexpool_fwd: too many rows for one launch");
+  const unsigned grid = (unsigned)blocks, nrows = (unsigned)nrows64;
   switch (method) {
-    case HG_POOL_MAX: hexpool_fwd_kernel<T, HG_POOL_MAX, AUX><<<grid, kPoolThreads, 0, st>>>((const T*)x, (T*)y, (AUX*)aux, total, g, (A)pv, (A)tv); break;
-    case HG_POOL_MIN: hexpool_fwd_kernel<T, HG_POOL_MIN, AUX><<<grid, kPoolThreads, 0, st>>>((const T*)x, (T*)y, (AUX*)aux, total, g, (A)pv, (A)tv); break;
-    default: hexpool_fwd_kernel<T, HG_POOL_AVG, AUX><<<grid, kPoolThreads, 0, st>>>((const T*)x, (T*)y, (AUX*)aux, total, g, (A)pv, (A)tv); break;
+    case HG_POOL_MAX: hexpool_fwd_kernel<T, HG_POOL_MAX, AUX><<<grid, kPoolThreads, 0, st>>>((const T*)x, (T*)y, (AUX*)aux, jtiles, nrows, tw_log2, g, (A)pv, (A)tv); break;
+    case HG_POOL_MIN: hexpool_fwd_kernel<T, HG_POOL_MIN, AUX><<<grid, kPoolThreads, 0, st>>>((const T*)x, (T*)y, (AUX*)aux, jtiles, nrows, tw_log2, g, (A)pv, (A)tv); break;
+    default: hexpool_fwd_kernel<T, HG_POOL_AVG, AUX><<<grid, kPoolThreads, 0, st>>>((const T*)x, (T*)y, (AUX*)aux, jtiles, nrows, tw_log2, g, (A)pv, (A)tv); break;
   }
   return finish_launch("hexpool_fwd");
 }
 template <typename T, typename AUX>
-static int launch_pool_bwd(const void* gy, const void* aux, const void* x, void* gx, int64_t total, const PoolGeom& g, int method, cudaStream_t st) {
-  const unsigned grid = (unsigned)ceil_div(total, kPoolThreads);
+static int launch_pool_bwd(const void* gy, const void* aux, const void* x, void* gx, int64_t planes, const PoolGeom& g, int method, cudaStream_t st) {
+  int tw_log2 = 5;
+  while ((1 << tw_log2) < g.W && tw_log2 < 8) ++tw_log2;
+  const unsigned jtiles = (unsigned)ceil_div(g.W, 1 << tw_log2);
+  const int64_t nrows64 = planes * g.H;
+  const int64_t blocks = ceil_div(nrows64, kPoolThreads >> tw_log2) * jtiles;
+  HG_REQUIRE(blocks < (1ll << 31) && nrows64 < (1ll << 32), HG_E_SHAPE, "hexpool_bwd: too many rows for one launch");
+  const unsigned grid = (unsigned)blocks, nrows = (unsigned)nrows64;
+  const bool disjoint = g.kh <= g.sh && g.kw <= g.sw;
+#define HG_BWD(M)                                                                                                                  \
+  if (disjoint) hexpool_bwd_kernel<T, M, AUX, true><<<grid, kPoolThreads, 0, st>>>((const T*)gy, (const AUX*)aux, (const T*)x, (T*)gx, jtiles, nrows, tw_log2, g); \
+  else hexpool_bwd_kernel<T, M, AUX, false><<<grid, kPoolThreads, 0, st>>>((const T*)gy, (const AUX*)aux, (const T*)x, (T*)gx, jtiles, nrows, tw_log2, g);
   switch (method) {
-    case HG_POOL_MAX: hexpool_bwd_kernel<T, HG_POOL_MAX, AUX><<<grid, kPoolThreads, 0, st>>>((const T*)gy, (const AUX*)aux, (const T*)x, (T*)gx, total, g); break;
-    case HG_POOL_MIN: hexpool_bwd_kernel<T, HG_POOL_MIN, AUX><<<grid, kPoolThreads, 0, st>>>((const T*)gy, (const AUX*)aux, (const T*)x, (T*)gx, total, g); break;
-    default: hexpool_bwd_kernel<T, HG_POOL_AVG, AUX><<<grid, kPoolThreads, 0, st>>>((const T*)gy, (const AUX*)aux, (const T*)x, (T*)gx, total, g); break;
+    case HG_POOL_MAX: HG_BWD(HG_POOL_MAX) break;
+    case HG_POOL_MIN: HG_BWD(HG_POOL_MIN) break;
+    default: HG_BWD(HG_POOL_AVG) break;
   }
+#undef HG_BWD
   return finish_launch("hexpool_bwd");
 }
 
@@ -283,8 +327,8 @@ int hg_hexpool_fwd(const void* x, void* y, void* aux, int aux_bytes, int64_t pla
   cudaStream_t st = as_stream(stream);
   const bool wide = aux != nullptr && aux_bytes == 4;
 #define HG_CASE(D, T)                                                                                          \
-  if (dtype == D) return wide ? launch_pool_fwd<T, int32_t>(x, y, aux, total, g, pad_value, tail_value, method, st) \
-                              : launch_pool_fwd<T, int8_t>(x, y, aux, total, g, pad_value, tail_value, method, st);
+  if (dtype == D) return wide ? launch_pool_fwd<T, int32_t>(x, y, aux, planes, g, pad_value, tail_value, method, st) \
+                              : launch_pool_fwd<T, int8_t>(x, y, aux, planes, g, pad_value, tail_value, method, st);
   HG_CASE(HG_F32, float)
   HG_CASE(HG_F64, double)
   HG_CASE(HG_BF16, __nv_bfloat16)
@@ -307,8 +351,8 @@ int hg_hexpool_bwd(const void* gy, const void* aux, int aux_bytes, const void* x
   if (total == 0) return HG_OK;
   cudaStream_t st = as_stream(stream);
 #define HG_CASE(D, T)                                                                              \
-  if (dtype == D) return aux_bytes == 4 ? launch_pool_bwd<T, int32_t>(gy, aux, x, gx, total, g, method, st) \
-                                        : launch_pool_bwd<T, int8_t>(gy, aux, x, gx, total, g, method, st);
+  if (dtype == D) return aux_bytes == 4 ? launch_pool_bwd<T, int32_t>(gy, aux, x, gx, planes, g, method, st) \
+                                        : launch_pool_bwd<T, int8_t>(gy, aux, x, gx, planes, g, method, st);
   HG_CASE(HG_F32, float)
   HG_CASE(HG_F64, double)
   HG_CASE(HG_BF16, __nv_bfloat16)
