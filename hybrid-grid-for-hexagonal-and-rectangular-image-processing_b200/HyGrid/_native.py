@@ -47,7 +47,7 @@ _SIGS = {
     "hg_rect2hex_nearest": [_p, _p, _p, _p, _l, _l, _l, _l, _l, _i, _p],
     "hg_rect2hex_bilinear": [_p, _p, _p, _p, _p, _p, _l, _l, _l, _l, _l, _i, _i, _i, _p],
     "hg_hex2rect_nearest": [_p, _p, _p, _p, _l, _l, _l, _l, _l, _i, _p],
-    "hg_hex2rect_linear": [_p, _p, _p, _p, _l, _l, _l, _l, _l, _i, _i, _i, _p],
+    "hg_hex2rect_linear": [_p, _p, _p, _p, _p, _p, _l, _l, _l, _l, _l, _i, _i, _i, _p],
     "hg_hexwarp_nearest": [_p, _p, _p, _p, _i, _l, _l, _l, _l, _l, _i, _p],
     "hg_hexwarp_linear": [_p, _p, _p, _p, _i, _l, _l, _l, _l, _l, _i, _i, _p],
     "hg_hexwarp_affine": [_p, _p, C.POINTER(_d), _d, _d, _i, _i, _l, _l, _l, _l, _l, _i, _i, _p],

@@ -128,7 +128,7 @@ def _hexsrc(kind, x, dsize, interpolation, out_dtype, math, twin, out):
                                   "(geometry_np.py:333-356 returns uninitialised memory)")
     x, planes, h, w = _planes(x)
     h1, w1 = (h, w) if dsize is None else (int(dsize[0]), int(dsize[1]))
-    xs, ys, _, _ = coordinate_tables(kind, h, w, h1, w1, twin, x.device)
+    xs, ys, hxs, hys = coordinate_tables(kind, h, w, h1, w1, twin, x.device)
     shape = x.shape[:-2] + (h1, w1)
     st = nv.stream_ptr(x.device)
     if method == 0:
@@ -137,7 +137,8 @@ def _hexsrc(kind, x, dsize, interpolation, out_dtype, math, twin, out):
                 x.element_size(), st)
     else:
         y = out if out is not None else torch.empty(shape, dtype=_out_dtype(x, out_dtype), device=x.device)
-        nv.call("hg_hex2rect_linear", nv.ptr(x), nv.ptr(y), nv.ptr(xs), nv.ptr(ys), planes, h, w, h1, w1,
+        nv.call("hg_hex2rect_linear", nv.ptr(x), nv.ptr(y), nv.ptr(xs), nv.ptr(ys), C.c_void_p(hxs.ctypes.data),
+                C.c_void_p(hys.ctypes.data), planes, h, w, h1, w1,
                 nv.hg_dtype(x.dtype), nv.hg_dtype(y.dtype), _MATH[math], st)
     return y
 

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <mutex>
 #include "../../include/hygrid_b200.h"
 
 namespace hg {
@@ -21,6 +22,24 @@ int finish_launch(const char* what);  // cudaGetLastError() -> return code (+ me
       return (code);                               \
     }                                              \
   } while (0)
+
+// Opt-in dynamic shared memory of one kernel instantiation: the attribute is per (function, device) and
+// shared by every host thread (the autograd engine launches the backward kernels from its own thread), so
+// the high-water mark is process-wide and only ever raised.
+struct SmemReservation {
+  std::mutex m;
+  size_t bytes[64] = {};
+  template <typename K> cudaError_t reserve(K kern, size_t want) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(m);
+    size_t& have = bytes[dev & 63];
+    if (want <= have) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+    if (e == cudaSuccess) have = want; else cudaGetLastError();
+    return e;
+  }
+};
 
 static inline cudaStream_t as_stream(hg_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -386,12 +386,9 @@ static int launch_umma(const CUtensorMap& tmap, const void* in, const float* w, 
                        cudaStream_t st) {
   const size_t smem = umma_smem_bytes(P.Cred, P.Nout, P.slots, P.rstages, P.raw_bytes);
   auto kern = hexconv_umma_kernel<TIN, TOUT, TMA>;
-  static thread_local size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("hexconv_umma: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e)); return (int)e; }
-    configured = smem;
-  }
+  static SmemReservation reservation;
+  cudaError_t e = reservation.reserve(kern, smem);
+  if (e != cudaSuccess) { set_error("hexconv_umma: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e)); return (int)e; }
   long long grid = g_um_sms > 0 ? g_um_sms : 148;
   if (grid > P.items) grid = P.items;
   kern<<<(unsigned)grid, kUmThreads, smem, st>>>(tmap, (const TIN*)in, w, bias, (TOUT*)out, P);

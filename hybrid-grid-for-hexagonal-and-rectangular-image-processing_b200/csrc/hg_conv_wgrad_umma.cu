@@ -406,12 +406,9 @@ static int launch_wu(const CUtensorMap& xmap, const CUtensorMap& gmap, const voi
                      const WgParams& P, cudaStream_t st) {
   const size_t smem = wu_smem_bytes(P.Cin, P.Cout, P.xslots, P.gslots, P.rstages, P.raw_bytes);
   auto kern = hexconv_wgrad_umma_kernel<TX, TG, TMA>;
-  static thread_local size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("hexconv_wgrad_umma: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e)); return (int)e; }
-    configured = smem;
-  }
+  static SmemReservation reservation;
+  cudaError_t e = reservation.reserve(kern, smem);
+  if (e != cudaSuccess) { set_error("hexconv_wgrad_umma: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e)); return (int)e; }
   long long grid = g_wu_sms > 0 ? g_wu_sms : 148;
   if (grid > P.items) grid = P.items;
   kern<<<(unsigned)grid, kWuThreads, smem, st>>>(xmap, gmap, (const TX*)x, (const TG*)gy, gw, gb, P);

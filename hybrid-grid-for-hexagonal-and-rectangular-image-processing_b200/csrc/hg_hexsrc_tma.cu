@@ -1,0 +1,239 @@
+// hg_hexsrc_tma.cu -- hex -> rect / hex -> hex resampling ('linear') with TMA-staged source tiles (sm_100a).
+//
+// ref: geometry_np.py:191-356 hex_to_rect_resample, :520-681 hexresize, geometry_torch.py:191-358
+// hex_to_square_resample -- they differ only in the 1-D coordinate tables.
+//
+// Same scheme as hg_resample_tma.cu (persistent CTAs, 3-D TMA box per item into a 3-stage shared ring, TMA
+// zero-fill == the reference's zero-fill of out-of-range lattice points), with two differences:
+//   * the per-sample geometry is not separable: the axial column j_ = (0.5*i_ + y_) + (w-0.5)/2 depends on
+//     row and column together and must be truncated in float64 to stay bit-exact on the lattice indices
+//     (geometry_np.py:276-298).  It is plane independent, so an item stages kG = 3 planes (an RGB image)
+//     and every thread evaluates the cell / triangle / weights of a sample once and blends 3 planes;
+//   * the three lattice points of a sample sit in two source rows at columns j_ax - (i+1)/2 (offset
+//     storage, odd rows shifted right): relative to y_ + (w-0.5)/2 the source column moves by at most
+//     [-1, +1.5], so the box origin depends only on the tile column.
+// Weights are the float32 simplex form (u > v ? (1-u, u-v, v) : (1-v, v-u, u)), i.e. this is
+// the HG_MATH_FAST kernel; HG_MATH_EXACT stays on the direct gather (hg_resample.cu).
+#include "hg_common.cuh"
+#include "hg_ptx.cuh"
+#include <math.h>
+#include <stdlib.h>
+
+namespace hg {
+
+constexpr int kHsTW = 128;
+constexpr int kHsRW = 2;                 // output rows per warp
+constexpr int kHsTH = 8 * kHsRW;         // 16 output rows per tile
+constexpr int kHsThreads = 256;
+constexpr int kHsStages = 3;
+constexpr int kHsG = 3;                  // planes per item
+
+struct HsTables {
+  double y[kHsTW];        // column coordinate
+  double hrow[kHsTH];     // 0.5 * i_
+  double u[kHsTH];        // i_f
+  int in[kHsTH];          // i_n
+  int nrows, ncols, row0, col0;
+};
+
+__device__ __forceinline__ int hs_col_origin(double y0, double cj) {
+  // leftmost source column any sample of a tile starting at coordinate y0 can touch, minus slack, 16-byte aligned
+  const int c = __double2int_rd(dadd(y0, cj)) - 2;
+  return c & ~3;
+}
+
+template <typename TD>
+__global__ void __launch_bounds__(kHsThreads)
+hexsrc_linear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __restrict__ dst, const double* __restrict__ xs,
+                         const double* __restrict__ ys, int h, int w, int h1, int w1, int planes, int tiles_x, int tiles_y,
+                         long long total_items, long long items_per_cta, int BW, int BH, int stage_bytes, double ci, double cj) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kHsStages * stage_bytes);
+  HsTables* tabs = reinterpret_cast<HsTables*>(smem_raw + (size_t)kHsStages * stage_bytes + 64);
+
+  const long long g_begin = (long long)blockIdx.x * items_per_cta;
+  const long long g_end = min(total_items, g_begin + items_per_cta);
+  if (g_begin >= g_end) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int npos = tiles_x * tiles_y;
+  const int plane_elems = BW * BH;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&tmap);
+    for (int s = 0; s < kHsStages; ++s) ptx::mbar_init(&full[s], 1);
+    ptx::fence_barrier_init();
+  }
+
+  auto decode = [&](long long g, int& grp, int& tx, int& ty) {   // plane-group major, tiles row-major
+    grp = (int)(g / npos);
+    const int pos = (int)(g - (long long)grp * npos);
+    ty = pos / tiles_x; tx = pos - ty * tiles_x;
+  };
+  auto origin = [&](int tx, int ty, int& row0, int& col0) {
+    row0 = trunc_i32(dadd(xs[ty * kHsTH], ci));
+    col0 = hs_col_origin(ys[tx * kHsTW], cj);
+  };
+  auto issue = [&](long long g, int s) {   // one thread
+    int grp, tx, ty, row0, col0;
+    decode(g, grp, tx, ty);
+    origin(tx, ty, row0, col0);
+    ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(kHsG * plane_elems * 4));
+    ptx::tma_load_3d(smem_raw + (size_t)s * stage_bytes, &tmap, &full[s], col0, row0, grp * kHsG);
+  };
+  auto build_tables = [&](long long g, HsTables& T) {   // threads 0 .. kHsTW + kHsTH - 1
+    int grp, tx, ty, row0, col0;
+    decode(g, grp, tx, ty);
+    origin(tx, ty, row0, col0);
+    const int t = threadIdx.x;
+    if (t < kHsTW) {
+      const int b = tx * kHsTW + t;
+      T.y[t] = ys[b < w1 ? b : w1 - 1];
+      if (t == 0) { T.ncols = min(kHsTW, w1 - tx * kHsTW); T.nrows = min(kHsTH, h1 - ty * kHsTH); T.row0 = row0; T.col0 = col0; }
+    } else if (t < kHsTW + kHsTH) {
+      const int r = t - kHsTW, a = min(ty * kHsTH + r, h1 - 1);
+      const double i_ = dadd(xs[a], ci);                 // geometry_np.py:276
+      const int in = trunc_i32(i_);
+      T.in[r] = in;
+      T.u[r] = dsub(i_, (double)(float)in);              // :284
+      T.hrow[r] = dmul(0.5, i_);                         // first term of :277
+    }
+  };
+
+  build_tables(g_begin, tabs[0]);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kHsStages && g_begin + s < g_end; ++s) issue(g_begin + s, s);
+  }
+
+  for (long long k = 0; g_begin + k < g_end; ++k) {
+    const int s = (int)(k % kHsStages);
+    const uint32_t parity = (uint32_t)((k / kHsStages) & 1);
+    const HsTables& T = tabs[k & 1];
+    if (g_begin + k + 1 < g_end) build_tables(g_begin + k + 1, tabs[(k + 1) & 1]);
+
+    int grp, tx, ty;
+    decode(g_begin + k, grp, tx, ty);
+    const int np = min(kHsG, planes - grp * kHsG);
+    const int nrows = min(kHsRW, T.nrows - warp * kHsRW);
+    const int row0 = T.row0, col0 = T.col0;
+
+    // geometry of this thread's samples (plane independent)
+    int o1[kHsRW][4], oB[kHsRW][4], o4[kHsRW][4];
+    float wa[kHsRW][4], wb[kHsRW][4], wc[kHsRW][4];
+#pragma unroll
+    for (int r = 0; r < kHsRW; ++r) {
+      const int rl = warp * kHsRW + r;
+      const int in = T.in[rl];
+      const double u = T.u[rl], hrow = T.hrow[rl];
+      const int roff = (in - row0) * BW - col0;
+      const int kA = (in + 1) / 2, kB = (in + 2) / 2;   // true division then truncation (in >= 0 here)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const double j_ = dadd(dadd(hrow, T.y[lane + 32 * c]), cj);   // :277  (0.5*i_ + y_) + (w-0.5)*0.5
+        const int jn = trunc_i32(j_);
+        const double v = dsub(j_, (double)(float)jn);
+        const bool f = u > v;                                         // :298 up_down_flag
+        const int p1 = roff + jn - kA;                                // P1 (i_n, j_n)
+        const int p4 = roff + BW + jn - kB + 1;                       // P4 (i_n+1, j_n+1)
+        o1[r][c] = p1;
+        oB[r][c] = f ? p4 - 1 : p1 + 1;                               // P2 (i_n+1, j_n) or P3 (i_n, j_n+1)
+        o4[r][c] = p4;
+        const float uf = (float)u, vf = (float)v;
+        wa[r][c] = f ? 1.f - uf : 1.f - vf;
+        wb[r][c] = f ? uf - vf : vf - uf;
+        wc[r][c] = f ? vf : uf;
+      }
+    }
+    ptx::mbar_wait(&full[s], parity);
+    const float* __restrict__ t = reinterpret_cast<const float*>(smem_raw + (size_t)s * stage_bytes);
+    TD* __restrict__ dp = dst + ((size_t)grp * kHsG * h1 + (size_t)(ty * kHsTH + warp * kHsRW)) * w1 + (tx * kHsTW + lane);
+    for (int p = 0; p < np; ++p, t += plane_elems, dp += (size_t)h1 * w1) {
+#pragma unroll
+      for (int r = 0; r < kHsRW; ++r) {
+        if (r < nrows) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float o = fmaf(wc[r][c], t[o4[r][c]], fmaf(wb[r][c], t[oB[r][c]], wa[r][c] * t[o1[r][c]]));
+            if (lane + 32 * c < T.ncols) st_stream(dp + (size_t)r * w1 + 32 * c, (TD)o);
+          }
+        }
+      }
+    }
+    __syncthreads();                            // stage s fully read; next item's tables complete
+    if (threadIdx.x == 0 && g_begin + k + kHsStages < g_end) issue(g_begin + k + kHsStages, s);
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------
+static int g_hs_sms = 0;
+
+// HG_OK launched, 1 not applicable (fall back to the direct gather), else an error code
+int try_hexsrc_linear_tma(const void* src, void* dst, const double* xs, const double* ys, const double* host_xs, const double* host_ys,
+                          int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1, int sdt, int ddt, int math, cudaStream_t st) {
+  if (!host_xs || !host_ys || sdt != HG_F32 || ddt != HG_F32 || math != HG_MATH_FAST) return 1;
+  if ((w * 4) % 16 != 0 || (reinterpret_cast<uintptr_t>(src) & 15) != 0 || planes >= (1ll << 31) || h1 < 1 || w1 < 1) return 1;
+  static const bool off = [] { const char* e = getenv("HG_HEXSRC_NO_TMA"); return e && e[0] == '1'; }();
+  if (off) return 1;
+  const double ci = (h - 1) * 0.5, cj = (w - 0.5) * 0.5;
+  // rows: monotone, non-negative cell rows; footprint of a tile = i_n(a0) .. i_n(a1) + 1
+  int BH = 0;
+  for (int64_t a0 = 0; a0 < h1; a0 += kHsTH) {
+    const int64_t a1 = (a0 + kHsTH < h1 ? a0 + kHsTH : h1) - 1;
+    int prev = (int)(host_xs[a0] + ci);
+    if (host_xs[a0] + ci < 0.0) return 1;
+    const int first = prev;
+    for (int64_t a = a0 + 1; a <= a1; ++a) {
+      const int cur = (int)(host_xs[a] + ci);
+      if (cur < prev) return 1;
+      prev = cur;
+    }
+    if (prev - first + 2 > BH) BH = prev - first + 2;
+  }
+  // columns: monotone; source columns of a tile lie in [floor(y0 + cj) - 2, floor(y1 + cj) + 3]
+  int BW = 0;
+  for (int64_t b0 = 0; b0 < w1; b0 += kHsTW) {
+    const int64_t b1 = (b0 + kHsTW < w1 ? b0 + kHsTW : w1) - 1;
+    for (int64_t b = b0 + 1; b <= b1; ++b)
+      if (host_ys[b] < host_ys[b - 1]) return 1;
+    const int lo = ((int)floor(host_ys[b0] + cj) - 2) & ~3;
+    const int hi = (int)floor(host_ys[b1] + cj) + 3;
+    if (hi - lo + 1 > BW) BW = hi - lo + 1;
+  }
+  BW = (BW + 3) / 4 * 4;
+  if (BH > 256 || BW > 256) return 1;
+  if ((int64_t)BH * BW > (int64_t)3 * kHsTH * kHsTW) return 1;   // strong down-sampling: the direct gather is already at the roofline
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return 1;
+  alignas(64) CUtensorMap tmap;
+  const cuuint64_t gdim[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)planes};
+  const cuuint64_t gstr[2] = {(cuuint64_t)w * 4, (cuuint64_t)w * h * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)kHsG};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(src), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return 1;
+  const int stage_bytes = (int)ceil_div((int64_t)kHsG * BW * BH * 4, 128) * 128;
+  const int smem = kHsStages * stage_bytes + 64 + 2 * (int)sizeof(HsTables);
+  auto kern = hexsrc_linear_tma_kernel<float>;
+  static SmemReservation reservation;
+  if (reservation.reserve(kern, (size_t)smem) != cudaSuccess) return 1;
+  if (g_hs_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_hs_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kHsThreads, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); return 1; }
+  const int tiles_x = (int)ceil_div(w1, kHsTW), tiles_y = (int)ceil_div(h1, kHsTH);
+  const long long groups = ceil_div(planes, kHsG);
+  const long long total = (long long)tiles_x * tiles_y * groups;
+  long long grid = (long long)g_hs_sms * occ;
+  if (grid > total) grid = total;
+  const long long per = (total + grid - 1) / grid;
+  grid = (total + per - 1) / per;
+  kern<<<(unsigned)grid, kHsThreads, smem, st>>>(tmap, (float*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, (int)planes, tiles_x,
+                                                  tiles_y, total, per, BW, BH, stage_bytes, ci, cj);
+  return finish_launch("hexsrc_linear_tma");
+}
+
+}  // namespace hg

@@ -153,7 +153,7 @@ static int run_host(int kind, const void* host_src, void* host_dst, const double
                        : hg_rect2hex_bilinear(ws.dsrc[s], ws.ddst[s], dxs, dys, host_xs, host_ys, n, h, w, h1, w1, sdt, ddt, math, ws.st[s]);
     } else {
       rc = interp == 0 ? hg_hex2rect_nearest(ws.dsrc[s], ws.ddst[s], dxs, dys, n, h, w, h1, w1, dtype_size(sdt), ws.st[s])
-                       : hg_hex2rect_linear(ws.dsrc[s], ws.ddst[s], dxs, dys, n, h, w, h1, w1, sdt, ddt, math, ws.st[s]);
+                       : hg_hex2rect_linear(ws.dsrc[s], ws.ddst[s], dxs, dys, host_xs, host_ys, n, h, w, h1, w1, sdt, ddt, math, ws.st[s]);
     }
     if (rc) { for (int k = 0; k < kSlots; ++k) cudaStreamSynchronize(ws.st[k]); return rc; }
     void* hdst = dst_pinned ? (void*)(dst + (size_t)p0 * dst_plane) : ws.pin_out[s];

@@ -49,6 +49,64 @@ hex_to_type_kernel(const TS* __restrict__ hex, TD* __restrict__ out, int64_t tot
   }
 }
 
+// Vector variant: the output is treated as one flat array and every thread produces V = 16 / sizeof(TD)
+// consecutive elements as ONE aligned 16-byte streaming store (rows of 2W+1 elements are never 16-byte aligned
+// themselves, so vectors straddle row ends: each element resolves its own (row, column) by a carry).  Source
+// cells are read with scalar loads (neighbouring lanes share lines through L1; each cell is needed twice).
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(kLayoutThreads)
+hex_to_type_vec_kernel(const TS* __restrict__ hex, TD* __restrict__ out, int64_t total, int H, int W, int rows_mul, int offset) {
+  constexpr int V = 16 / (int)sizeof(TD);
+  struct alignas(16) Vec { TD v[V]; };
+  const int Wt = 2 * W + 1, Hout = H * rows_mul;
+  const int64_t base = (int64_t)blockIdx.x * kLayoutChunk;
+  const int64_t end = min(base + (int64_t)kLayoutChunk, total);      // kLayoutChunk % V == 0, total % V == 0
+  int64_t t = base + (int64_t)threadIdx.x * V;
+  if (t >= end) return;
+  int64_t r = t / Wt;
+  int c = (int)(t - r * Wt);
+  constexpr int kStep = kLayoutThreads * V;
+  const int step_r = kStep / Wt, step_c = kStep % Wt;
+  int64_t plane = r / Hout;
+  int ro = (int)(r - plane * Hout);
+  for (; t < end; t += kStep) {
+    Vec o;
+    int cc = c, rr = ro;
+    int64_t pp = plane;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      const int i = rows_mul == 2 ? (rr >> 1) : rr;
+      const int sft = (i + offset) & 1;
+      TD v = zero_of<TD>();
+      if (cc >= sft && cc < 2 * W + sft) v = convert<TS, TD>(__ldg(hex + (pp * H + i) * (int64_t)W + ((cc - sft) >> 1)));
+      o.v[e] = v;
+      if (++cc == Wt) { cc = 0; if (++rr == Hout) { rr = 0; ++pp; } }
+    }
+    __stcs(reinterpret_cast<uint4*>(out + t), *reinterpret_cast<const uint4*>(&o));
+    ro += step_r; c += step_c;
+    if (c >= Wt) { c -= Wt; ++ro; }
+    while (ro >= Hout) { ro -= Hout; ++plane; }
+  }
+}
+
+// the last (total % V) elements the vector kernel cannot cover
+template <typename TS, typename TD>
+__global__ void hex_to_type_tail_kernel(const TS* __restrict__ hex, TD* __restrict__ out, int64_t begin, int64_t total, int H, int W,
+                                        int rows_mul, int offset) {
+  const int64_t t = begin + threadIdx.x;
+  if (t >= total) return;
+  const int Wt = 2 * W + 1, Hout = H * rows_mul;
+  const int64_t r = t / Wt;
+  const int c = (int)(t - r * Wt);
+  const int64_t plane = r / Hout;
+  const int ro = (int)(r - plane * Hout);
+  const int i = rows_mul == 2 ? (ro >> 1) : ro;
+  const int sft = (i + offset) & 1;
+  TD v = zero_of<TD>();
+  if (c >= sft && c < 2 * W + sft) v = convert<TS, TD>(__ldg(hex + (plane * H + i) * (int64_t)W + ((c - sft) >> 1)));
+  out[t] = v;
+}
+
 // hex[r, j] = t[plane, i * rows_step, 1 + 2 j]
 template <typename TS, typename TD>
 __global__ void __launch_bounds__(kLayoutThreads)
@@ -149,7 +207,19 @@ static inline unsigned chunks(int64_t total) { return (unsigned)ceil_div(total, 
 template <typename TS, typename TD>
 static int launch_to_type(const void* hex, void* out, int64_t planes, int64_t H, int64_t W, int rows_mul, int offset, cudaStream_t st) {
   const int64_t total = planes * H * rows_mul * (2 * W + 1);
-  hex_to_type_kernel<TS, TD><<<chunks(total), kLayoutThreads, 0, st>>>((const TS*)hex, (TD*)out, total, (int)H, (int)W, rows_mul, offset);
+  constexpr int V = 16 / (int)sizeof(TD);
+  static_assert(kLayoutChunk % V == 0, "chunk must hold whole vectors");
+  const int64_t vec_total = (reinterpret_cast<uintptr_t>(out) & 15) == 0 && W >= 2 ? total / V * V : 0;
+  if (vec_total > 0) {
+    hex_to_type_vec_kernel<TS, TD><<<chunks(vec_total), kLayoutThreads, 0, st>>>((const TS*)hex, (TD*)out, vec_total, (int)H, (int)W, rows_mul, offset);
+    int rc = finish_launch("hex_to_type_vec");
+    if (rc || vec_total == total) return rc;
+    // the last total % V elements (same plane, last row): one tiny scalar launch over the whole tail row range
+  }
+  if (vec_total == 0)
+    hex_to_type_kernel<TS, TD><<<chunks(total), kLayoutThreads, 0, st>>>((const TS*)hex, (TD*)out, total, (int)H, (int)W, rows_mul, offset);
+  else
+    hex_to_type_tail_kernel<TS, TD><<<1, 32, 0, st>>>((const TS*)hex, (TD*)out, vec_total, total, (int)H, (int)W, rows_mul, offset);
   return finish_launch("hex_to_type");
 }
 template <typename TS, typename TD>

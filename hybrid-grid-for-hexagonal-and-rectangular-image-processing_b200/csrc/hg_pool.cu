@@ -11,6 +11,7 @@
 // atomics, gx written exactly once.
 #include "hg_common.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace hg {
 
@@ -141,6 +142,173 @@ hexpool_bwd_kernel(const T* __restrict__ gy, const AUX* __restrict__ aux, const 
     }
   }
   gx[t] = st_acc<T, A>(acc);
+}
+
+// ---- 2 x 2 / stride 2 fast path (HexPool2d(method, 2, 2): the C4 pyramid and the C5 network) --------------
+// kh = kw = sh = sw = shift = 2, no padding, no ceil-mode tail, float32, W % 4 == 0, 16-byte aligned planes:
+//   out(I, J) = reduce x[2I + a, (I & 1) + 2J + b],  a, b in {0, 1};  hn = H / 2, wn = (W - 1) / 2.
+// One warp owns a 128-column segment of one *pair* of output rows (I = 2g even, 2g + 1 odd): every lane reads
+// one aligned float4 of each of the four input rows (4 x LDG.128 in flight per lane, each byte of x read
+// once); the odd row's windows straddle the quads by one cell, which comes from the next lane by shuffle.
+// The reduction visits the cells in the reference's window order, so results (and max / min slots) are
+// bit-identical to the generic kernel.
+template <int METHOD>
+__device__ __forceinline__ void pool4(float v0, float v1, float v2, float v3, float& out, int& aux) {
+  const float v[4] = {v0, v1, v2, v3};
+  if (METHOD == HG_POOL_AVG) {
+    float sum = 0.f; int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (v[i] == v[i]) { sum += v[i]; ++cnt; }
+    out = cnt ? sum / (float)cnt : CUDART_NAN_F;
+    aux = cnt;
+  } else {
+    const float inf = CUDART_INF_F;
+    float best = 0.f; int slot = 0; bool masked = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const bool nan = v[i] != v[i];
+      const float m = nan ? (METHOD == HG_POOL_MAX ? -inf : inf) : v[i];
+      const bool better = METHOD == HG_POOL_MAX ? (m > best) : (m < best);
+      if (i == 0 || better) { best = m; slot = i; masked = nan; }
+    }
+    out = best;
+    aux = masked ? -1 : slot;
+  }
+}
+
+template <int METHOD>
+__global__ void __launch_bounds__(kPoolThreads)
+hexpool2x2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int8_t* __restrict__ aux, long long items, int pairs,
+                      int segs, int H, int W, int hn, int wn) {
+  const long long item = (long long)blockIdx.x * (kPoolThreads / 32) + (threadIdx.x >> 5);
+  if (item >= items) return;                              // warp-uniform
+  const int lane = threadIdx.x & 31;
+  const long long pr = item / segs;
+  const int seg = (int)(item - pr * segs);
+  const long long plane = pr / pairs;
+  const int g = (int)(pr - plane * pairs);
+  const int c4 = seg * 128 + 4 * lane;                    // first input column of this lane's quad
+  const bool live = c4 < W;
+  const int I0 = 2 * g;
+  const bool has_odd = I0 + 1 < hn;
+  const float* __restrict__ xp = x + ((size_t)plane * H + (size_t)2 * I0) * W + c4;
+  float4 r[4];
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) r[k] = (live && (k < 2 || has_odd)) ? __ldg(reinterpret_cast<const float4*>(xp + (size_t)k * W)) : z;
+  // odd output row: the window J = 2c + 1 ends in the first cell of the next quad
+  float n2 = __shfl_down_sync(0xffffffffu, r[2].x, 1), n3 = __shfl_down_sync(0xffffffffu, r[3].x, 1);
+  if (lane == 31 && has_odd && c4 + 4 < W) { n2 = __ldg(xp + (size_t)2 * W + 4); n3 = __ldg(xp + (size_t)3 * W + 4); }
+  if (!live) return;
+  const int J = c4 >> 1;                                  // outputs J, J + 1
+  float o; int a;
+  const size_t t0 = ((size_t)plane * hn + I0) * wn + J;
+  if (J < wn) {
+    pool4<METHOD>(r[0].x, r[0].y, r[1].x, r[1].y, o, a);
+    __stcs(y + t0, o);
+    if (aux) aux[t0] = (int8_t)a;
+  }
+  if (J + 1 < wn) {
+    pool4<METHOD>(r[0].z, r[0].w, r[1].z, r[1].w, o, a);
+    __stcs(y + t0 + 1, o);
+    if (aux) aux[t0 + 1] = (int8_t)a;
+  }
+  if (has_odd) {
+    const size_t t1 = t0 + wn;
+    if (J < wn) {
+      pool4<METHOD>(r[2].y, r[2].z, r[3].y, r[3].z, o, a);
+      __stcs(y + t1, o);
+      if (aux) aux[t1] = (int8_t)a;
+    }
+    if (J + 1 < wn) {
+      pool4<METHOD>(r[2].w, n2, r[3].w, n3, o, a);
+      __stcs(y + t1 + 1, o);
+      if (aux) aux[t1 + 1] = (int8_t)a;
+    }
+  }
+}
+
+// Backward of the same configuration: one warp writes a 128-column segment of FOUR input rows (two output
+// rows) of gx as aligned float4 stores; gy / aux of the (at most three) windows touching a quad are read once.
+template <int METHOD>
+__device__ __forceinline__ float pool4_grad(float gy, int aux, int slot) {
+  if (METHOD == HG_POOL_AVG) return aux > 0 ? gy / (float)aux : 0.f;
+  return aux == slot ? gy : 0.f;
+}
+
+template <int METHOD>
+__global__ void __launch_bounds__(kPoolThreads)
+hexpool2x2_bwd_kernel(const float* __restrict__ gy, const int8_t* __restrict__ aux, const float* __restrict__ x,
+                      float* __restrict__ gx, long long items, int pairs, int segs, int H, int W, int hn, int wn) {
+  const long long item = (long long)blockIdx.x * (kPoolThreads / 32) + (threadIdx.x >> 5);
+  if (item >= items) return;                              // warp-uniform
+  const int lane = threadIdx.x & 31;
+  const long long pr = item / segs;
+  const int seg = (int)(item - pr * segs);
+  const long long plane = pr / pairs;
+  const int g = (int)(pr - plane * pairs);
+  const int c4 = seg * 128 + 4 * lane;
+  const bool live = c4 < W;
+  const int I0 = 2 * g, J = c4 >> 1;
+  const int row0 = 4 * g;                                 // first of the (up to) four input rows
+  // windows J, J + 1 of the even row; J - 1, J, J + 1 of the odd row
+  float ge[2] = {0.f, 0.f}, go[3] = {0.f, 0.f, 0.f};
+  int ae[2] = {METHOD == HG_POOL_AVG ? 0 : -1, METHOD == HG_POOL_AVG ? 0 : -1};
+  int ao[3] = {ae[0], ae[0], ae[0]};
+  if (live && I0 < hn) {
+    const size_t t0 = ((size_t)plane * hn + I0) * wn + J;
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+      if (J + e < wn) { ge[e] = __ldg(gy + t0 + e); ae[e] = (int)aux[t0 + e]; }
+    if (I0 + 1 < hn) {
+      const size_t t1 = t0 + wn;
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        if (J + e < wn) { go[1 + e] = __ldg(gy + t1 + e); ao[1 + e] = (int)aux[t1 + e]; }
+    }
+  }
+  go[0] = __shfl_up_sync(0xffffffffu, go[2], 1);
+  ao[0] = __shfl_up_sync(0xffffffffu, ao[2], 1);
+  if (lane == 0) {
+    go[0] = 0.f; ao[0] = METHOD == HG_POOL_AVG ? 0 : -1;
+    if (live && I0 + 1 < hn && J >= 1) {
+      const size_t t = ((size_t)plane * hn + I0 + 1) * wn + J - 1;
+      go[0] = __ldg(gy + t); ao[0] = (int)aux[t];
+    }
+  }
+  if (!live) return;
+  float4 o[4];
+  // even output row -> input rows row0, row0 + 1; slots a * 2 + b
+  o[0] = make_float4(pool4_grad<METHOD>(ge[0], ae[0], 0), pool4_grad<METHOD>(ge[0], ae[0], 1),
+                     pool4_grad<METHOD>(ge[1], ae[1], 0), pool4_grad<METHOD>(ge[1], ae[1], 1));
+  o[1] = make_float4(pool4_grad<METHOD>(ge[0], ae[0], 2), pool4_grad<METHOD>(ge[0], ae[0], 3),
+                     pool4_grad<METHOD>(ge[1], ae[1], 2), pool4_grad<METHOD>(ge[1], ae[1], 3));
+  // odd output row -> input rows row0 + 2, row0 + 3; columns shifted right by one cell
+  o[2] = make_float4(pool4_grad<METHOD>(go[0], ao[0], 1), pool4_grad<METHOD>(go[1], ao[1], 0),
+                     pool4_grad<METHOD>(go[1], ao[1], 1), pool4_grad<METHOD>(go[2], ao[2], 0));
+  o[3] = make_float4(pool4_grad<METHOD>(go[0], ao[0], 3), pool4_grad<METHOD>(go[1], ao[1], 2),
+                     pool4_grad<METHOD>(go[1], ao[1], 3), pool4_grad<METHOD>(go[2], ao[2], 2));
+  const size_t base = ((size_t)plane * H + row0) * W + c4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (row0 + k >= H) break;
+    float4 v = o[k];
+    if (METHOD == HG_POOL_AVG && x != nullptr) {          // NaN cells took no part in the mean: no gradient
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + base + (size_t)k * W));
+      if (xv.x != xv.x) v.x = 0.f;
+      if (xv.y != xv.y) v.y = 0.f;
+      if (xv.z != xv.z) v.z = 0.f;
+      if (xv.w != xv.w) v.w = 0.f;
+    }
+    __stcs(reinterpret_cast<float4*>(gx + base + (size_t)k * W), v);
+  }
+}
+
+static bool pool2x2_ok(const PoolGeom& g, int tail_h, int tail_w, const void* a, const void* b) {
+  static const bool off = [] { const char* e = getenv("HG_POOL_GENERIC"); return e && e[0] == '1'; }();
+  return !off && g.kh == 2 && g.kw == 2 && g.sh == 2 && g.sw == 2 && g.shift == 2 && g.pad == 0 && tail_h == 0 && tail_w == 0 &&
+         g.W % 4 == 0 && g.hn == g.H / 2 && g.wn == (g.W - 1) / 2 && (reinterpret_cast<uintptr_t>(a) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(b) & 15) == 0;
 }
 
 // ---- global pooling: x [planes, L] -> y [planes] ------------------------------------------------------
@@ -325,6 +493,20 @@ int hg_hexpool_fwd(const void* x, void* y, void* aux, int aux_bytes, int64_t pla
   const int64_t total = planes * hn * wn;
   if (total == 0) return HG_OK;
   cudaStream_t st = as_stream(stream);
+  if (dtype == HG_F32 && (aux == nullptr || aux_bytes == 1) && pool2x2_ok(g, tail_h, tail_w, x, x)) {
+    const int pairs = (g.hn + 1) / 2, segs = (int)ceil_div(g.W, 128);
+    const long long items = (long long)planes * pairs * segs;
+    const long long blocks = ceil_div(items, kPoolThreads / 32);
+    HG_REQUIRE(blocks < (1ll << 31), HG_E_SHAPE, "hexpool_fwd: too many rows for one launch");
+#define HG_P2(M) hexpool2x2_fwd_kernel<M><<<(unsigned)blocks, kPoolThreads, 0, st>>>((const float*)x, (float*)y, (int8_t*)aux, items, pairs, segs, g.H, g.W, g.hn, g.wn)
+    switch (method) {
+      case HG_POOL_MAX: HG_P2(HG_POOL_MAX); break;
+      case HG_POOL_MIN: HG_P2(HG_POOL_MIN); break;
+      default: HG_P2(HG_POOL_AVG); break;
+    }
+#undef HG_P2
+    return finish_launch("hexpool2x2_fwd");
+  }
   const bool wide = aux != nullptr && aux_bytes == 4;
 #define HG_CASE(D, T)                                                                                          \
   if (dtype == D) return wide ? launch_pool_fwd<T, int32_t>(x, y, aux, planes, g, pad_value, tail_value, method, st) \
@@ -350,6 +532,20 @@ int hg_hexpool_bwd(const void* gy, const void* aux, int aux_bytes, const void* x
   const int64_t total = planes * H * W;
   if (total == 0) return HG_OK;
   cudaStream_t st = as_stream(stream);
+  if (dtype == HG_F32 && aux_bytes == 1 && pool2x2_ok(g, 0, 0, gx, x ? x : gx)) {
+    const int pairs = (int)ceil_div(g.H, 4), segs = (int)ceil_div(g.W, 128);
+    const long long items = (long long)planes * pairs * segs;
+    const long long blocks = ceil_div(items, kPoolThreads / 32);
+    HG_REQUIRE(blocks < (1ll << 31), HG_E_SHAPE, "hexpool_bwd: too many rows for one launch");
+#define HG_P2(M) hexpool2x2_bwd_kernel<M><<<(unsigned)blocks, kPoolThreads, 0, st>>>((const float*)gy, (const int8_t*)aux, (const float*)x, (float*)gx, items, pairs, segs, g.H, g.W, g.hn, g.wn)
+    switch (method) {
+      case HG_POOL_MAX: HG_P2(HG_POOL_MAX); break;
+      case HG_POOL_MIN: HG_P2(HG_POOL_MIN); break;
+      default: HG_P2(HG_POOL_AVG); break;
+    }
+#undef HG_P2
+    return finish_launch("hexpool2x2_bwd");
+  }
 #define HG_CASE(D, T)                                                                              \
   if (dtype == D) return aux_bytes == 4 ? launch_pool_bwd<T, int32_t>(gy, aux, x, gx, planes, g, method, st) \
                                         : launch_pool_bwd<T, int8_t>(gy, aux, x, gx, planes, g, method, st);

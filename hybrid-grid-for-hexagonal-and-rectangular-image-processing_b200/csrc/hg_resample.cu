@@ -51,118 +51,140 @@ __global__ void rect2hex_index_kernel(const double* __restrict__ xs, const doubl
   }
 }
 
-// Bilinear blend, literal operation order of geometry_np.py:515-517.
+// Bilinear blend, literal operation order of geometry_np.py:515-517.  A CTA owns one output tile of `chunk`
+// consecutive planes: the column / row geometry is evaluated once and re-used for every plane.
 template <typename TS, typename TD, bool EXACT>
 __global__ void __launch_bounds__(kThreads)
 rect2hex_bilinear_kernel(const TS* __restrict__ src, TD* __restrict__ dst, const double* __restrict__ xs,
-                         const double* __restrict__ ys, int h, int w, int h1, int w1, int tiles_x, int tiles_y) {
+                         const double* __restrict__ ys, int64_t planes, int chunk, int h, int w, int h1, int w1, int tiles_x,
+                         int tiles_y) {
+  using WT = typename std::conditional<EXACT, double, float>::type;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int tile = blockIdx.x;
   const int tx = tile % tiles_x; tile /= tiles_x;
   const int ty = tile % tiles_y;
-  const int64_t plane = tile / tiles_y;
-  const TS* __restrict__ sp = src + plane * (int64_t)h * w;
-  TD* __restrict__ dp = dst + plane * (int64_t)h1 * w1;
+  const int64_t p0 = (int64_t)(tile / tiles_y) * chunk;
+  const int np = (int)min((int64_t)chunk, planes - p0);
+  const int64_t sps = (int64_t)h * w, dps = (int64_t)h1 * w1;
 
   int jn[kColsPerThread];
-  double jf[kColsPerThread];
-  bool cok[kColsPerThread];
+  WT jf[kColsPerThread];
+  bool c0[kColsPerThread], c1[kColsPerThread];
 #pragma unroll
   for (int k = 0; k < kColsPerThread; ++k) {
     const int b = tx * kTileW + lane + 32 * k;
-    cok[k] = b < w1;
-    rect_axis(cok[k] ? ys[b] : 0.0, w, jn[k], jf[k]);
+    const bool cok = b < w1;
+    double f;
+    rect_axis(cok ? ys[b] : 0.0, w, jn[k], f);
+    jf[k] = (WT)f;
+    c0[k] = cok && jn[k] >= 0 && jn[k] < w;
+    c1[k] = cok && jn[k] + 1 >= 0 && jn[k] + 1 < w;
   }
-#pragma unroll
+#pragma unroll 1
   for (int rr = 0; rr < kRowsPerWarp; ++rr) {
     const int a = ty * kTileH + warp * kRowsPerWarp + rr;
     if (a >= h1) break;
-    int in; double u;
-    rect_axis(xs[a], h, in, u);
+    int in; double ud;
+    rect_axis(xs[a], h, in, ud);
+    const WT u = (WT)ud;
     const bool r0 = in >= 0 && in < h, r1 = in + 1 >= 0 && in + 1 < h;
-    const TS* row0 = sp + (int64_t)in * w;
-    const TS* row1 = row0 + w;
-    TS p[kColsPerThread][4];
+    const TS* __restrict__ row0 = src + p0 * sps + (int64_t)in * w;
+    TD* __restrict__ dp = dst + p0 * dps + (int64_t)a * w1 + tx * kTileW + lane;
+    for (int p = 0; p < np; ++p, row0 += sps, dp += dps) {
+      const TS* __restrict__ row1 = row0 + w;
+      TS q[kColsPerThread][4];
 #pragma unroll
-    for (int k = 0; k < kColsPerThread; ++k) {
-      const bool c0 = jn[k] >= 0 && jn[k] < w, c1 = jn[k] + 1 >= 0 && jn[k] + 1 < w;
-      p[k][0] = (r0 && c0 && cok[k]) ? ldg(row0 + jn[k]) : TS(0);
-      p[k][1] = (r0 && c1 && cok[k]) ? ldg(row0 + jn[k] + 1) : TS(0);
-      p[k][2] = (r1 && c0 && cok[k]) ? ldg(row1 + jn[k]) : TS(0);
-      p[k][3] = (r1 && c1 && cok[k]) ? ldg(row1 + jn[k] + 1) : TS(0);
-    }
-#pragma unroll
-    for (int k = 0; k < kColsPerThread; ++k) {
-      if (!cok[k]) continue;
-      const int b = tx * kTileW + lane + 32 * k;
-      TD o;
-      if (EXACT) {
-        const double v = jf[k];
-        const double u1 = dsub(1.0, u), v1 = dsub(1.0, v);
-        const double t1 = dadd(dmul(u, to_f64(p[k][2])), dmul(u1, to_f64(p[k][0])));
-        const double t2 = dadd(dmul(u, to_f64(p[k][3])), dmul(u1, to_f64(p[k][1])));
-        o = (TD)dadd(dmul(v, t2), dmul(v1, t1));
-      } else {
-        const float uf = (float)u, vf = (float)jf[k];
-        const float t1 = fmaf(uf, to_f32(p[k][2]) - to_f32(p[k][0]), to_f32(p[k][0]));
-        const float t2 = fmaf(uf, to_f32(p[k][3]) - to_f32(p[k][1]), to_f32(p[k][1]));
-        o = (TD)fmaf(vf, t2 - t1, t1);
+      for (int k = 0; k < kColsPerThread; ++k) {
+        q[k][0] = (r0 && c0[k]) ? ldg(row0 + jn[k]) : TS(0);
+        q[k][1] = (r0 && c1[k]) ? ldg(row0 + jn[k] + 1) : TS(0);
+        q[k][2] = (r1 && c0[k]) ? ldg(row1 + jn[k]) : TS(0);
+        q[k][3] = (r1 && c1[k]) ? ldg(row1 + jn[k] + 1) : TS(0);
       }
-      st_stream(dp + (int64_t)a * w1 + b, o);
+#pragma unroll
+      for (int k = 0; k < kColsPerThread; ++k) {
+        if (tx * kTileW + lane + 32 * k >= w1) continue;
+        TD o;
+        if (EXACT) {
+          const double v = jf[k];
+          const double u1 = dsub(1.0, u), v1 = dsub(1.0, v);
+          const double t1 = dadd(dmul(u, to_f64(q[k][2])), dmul(u1, to_f64(q[k][0])));
+          const double t2 = dadd(dmul(u, to_f64(q[k][3])), dmul(u1, to_f64(q[k][1])));
+          o = (TD)dadd(dmul(v, t2), dmul(v1, t1));
+        } else {
+          const float uf = (float)u, vf = (float)jf[k];
+          const float t1 = fmaf(uf, to_f32(q[k][2]) - to_f32(q[k][0]), to_f32(q[k][0]));
+          const float t2 = fmaf(uf, to_f32(q[k][3]) - to_f32(q[k][1]), to_f32(q[k][1]));
+          o = (TD)fmaf(vf, t2 - t1, t1);
+        }
+        st_stream(dp + 32 * k, o);
+      }
     }
   }
 }
 
 // Nearest: literal 4-way argmin of geometry_np.py:499-512 (distances between the centred sample
-// coordinates and the un-centred corner indices; first minimum wins), then one gather.
+// coordinates and the un-centred corner indices; first minimum wins), then one gather.  The selected corner
+// does not depend on the plane: a CTA resolves the source offsets of its tile once (float64) and then streams
+// `chunk` planes through them.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 rect2hex_nearest_kernel(const T* __restrict__ src, T* __restrict__ dst, const double* __restrict__ xs,
-                        const double* __restrict__ ys, int h, int w, int h1, int w1, int tiles_x, int tiles_y) {
+                        const double* __restrict__ ys, int64_t planes, int chunk, int h, int w, int h1, int w1, int tiles_x,
+                        int tiles_y) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int tile = blockIdx.x;
   const int tx = tile % tiles_x; tile /= tiles_x;
   const int ty = tile % tiles_y;
-  const int64_t plane = tile / tiles_y;
-  const T* __restrict__ sp = src + plane * (int64_t)h * w;
-  T* __restrict__ dp = dst + plane * (int64_t)h1 * w1;
+  const int64_t p0 = (int64_t)(tile / tiles_y) * chunk;
+  const int np = (int)min((int64_t)chunk, planes - p0);
+  const int64_t sps = (int64_t)h * w, dps = (int64_t)h1 * w1;
 
   int jn[kColsPerThread];
   double dy0[kColsPerThread], dy1[kColsPerThread];
-  bool cok[kColsPerThread];
 #pragma unroll
   for (int k = 0; k < kColsPerThread; ++k) {
     const int b = tx * kTileW + lane + 32 * k;
-    cok[k] = b < w1;
-    const double y = cok[k] ? ys[b] : 0.0;
+    const double y = b < w1 ? ys[b] : 0.0;
     double f;
     rect_axis(y, w, jn[k], f);
     const double e0 = dsub(y, (double)jn[k]), e1 = dsub(y, (double)(jn[k] + 1));
     dy0[k] = dmul(e0, e0);
     dy1[k] = dmul(e1, e1);
   }
+  int off[kRowsPerWarp][kColsPerThread];   // source offset, -1 = outside the image (zero), -2 = no such output
 #pragma unroll
   for (int rr = 0; rr < kRowsPerWarp; ++rr) {
     const int a = ty * kTileH + warp * kRowsPerWarp + rr;
-    if (a >= h1) break;
-    const double x = xs[a];
+    const double x = xs[a < h1 ? a : h1 - 1];
     int in; double f;
     rect_axis(x, h, in, f);
     const double e0 = dsub(x, (double)in), e1 = dsub(x, (double)(in + 1));
     const double dx0 = dmul(e0, e0), dx1 = dmul(e1, e1);
 #pragma unroll
     for (int k = 0; k < kColsPerThread; ++k) {
-      if (!cok[k]) continue;
       const double d1 = dadd(dx0, dy0[k]), d2 = dadd(dx0, dy1[k]), d3 = dadd(dx1, dy0[k]), d4 = dadd(dx1, dy1[k]);
       int sel = 0; double best = d1;
       if (d2 < best) { best = d2; sel = 1; }
       if (d3 < best) { best = d3; sel = 2; }
       if (d4 < best) { best = d4; sel = 3; }
       const int i = in + (sel >> 1), j = jn[k] + (sel & 1);
-      T v = T(0);
-      if (i >= 0 && i < h && j >= 0 && j < w) v = ldg(sp + (int64_t)i * w + j);
-      dp[(int64_t)a * w1 + tx * kTileW + lane + 32 * k] = v;
+      const bool live = a < h1 && tx * kTileW + lane + 32 * k < w1;
+      off[rr][k] = !live ? -2 : ((i >= 0 && i < h && j >= 0 && j < w) ? i * w + j : -1);
     }
+  }
+  const T* __restrict__ sp = src + p0 * sps;
+  T* __restrict__ dp = dst + p0 * dps + (int64_t)(ty * kTileH + warp * kRowsPerWarp) * w1 + tx * kTileW + lane;
+  for (int p = 0; p < np; ++p, sp += sps, dp += dps) {
+    T v[kRowsPerWarp][kColsPerThread];
+#pragma unroll
+    for (int rr = 0; rr < kRowsPerWarp; ++rr)
+#pragma unroll
+      for (int k = 0; k < kColsPerThread; ++k) v[rr][k] = off[rr][k] >= 0 ? ldg(sp + off[rr][k]) : T(0);
+#pragma unroll
+    for (int rr = 0; rr < kRowsPerWarp; ++rr)
+#pragma unroll
+      for (int k = 0; k < kColsPerThread; ++k)
+        if (off[rr][k] != -2) st_stream(dp + (int64_t)rr * w1 + 32 * k, v[rr][k]);
   }
 }
 
@@ -216,11 +238,11 @@ __device__ __forceinline__ void hex_locate(CT x, CT y, int h, int w, CT hx, CT w
   // :326-331 cartesian coordinates of the triangle vertices
   const CT fi = (CT)in, fj = (CT)jn, ff = f ? CT(1) : CT(0);
   const CT p1x = A::sub(fi, hx);
-  const CT p1y = A::sub(A::sub(fj, A::div(fi, CT(2))), wy);
+  const CT p1y = A::sub(A::sub(fj, A::mul(fi, CT(0.5))), wy);
   const CT p2x = A::sub(A::add(fi, ff), hx);
-  const CT p2y = A::sub(A::sub(A::sub(A::add(fj, CT(1)), ff), A::div(A::add(fi, ff), CT(2))), wy);
+  const CT p2y = A::sub(A::sub(A::sub(A::add(fj, CT(1)), ff), A::mul(A::add(fi, ff), CT(0.5))), wy);
   const CT p3x = A::sub(A::add(fi, CT(1)), hx);
-  const CT p3y = A::sub(A::sub(A::add(fj, CT(1)), A::div(A::add(fi, CT(1)), CT(2))), wy);
+  const CT p3y = A::sub(A::sub(A::add(fj, CT(1)), A::mul(A::add(fi, CT(1)), CT(0.5))), wy);
   const CT ax = A::sub(x, p1x), ay = A::sub(y, p1y);
   const CT bx = A::sub(x, p2x), by = A::sub(y, p2y);
   const CT cx = A::sub(x, p3x), cy = A::sub(y, p3y);
@@ -305,11 +327,21 @@ template <typename CT, typename TS> struct BlendT { using type = double; };
 template <> struct BlendT<float, float> { using type = float; };
 template <> struct BlendT<float, uint8_t> { using type = float; };
 
-constexpr int kPlaneChunk = 8;  // planes per CTA: amortises the per-sample geometry
+// Planes per CTA.  The per-sample geometry (float64, ~200 instructions in exact mode) does not depend on the
+// plane, so a CTA evaluates it once per output cell and streams `chunk` planes through it; the chunk is as
+// large as possible while the launch still has ~12 waves of CTAs (tail effect < 10 %).
+static int plane_chunk(int64_t planes, int64_t tiles) {
+  const int64_t want_blocks = 148 * 8 * 12;
+  int64_t groups = ceil_div(want_blocks, tiles);
+  const int64_t max_groups = ceil_div(planes, 8);
+  if (groups > max_groups) groups = max_groups;
+  if (groups < 1) groups = 1;
+  return (int)ceil_div(planes, groups);
+}
 
 template <typename TS, typename TD, typename Coord, bool FAST>
 __global__ void __launch_bounds__(kThreads)
-hexsrc_linear_kernel(const TS* __restrict__ src, TD* __restrict__ dst, Coord coord, HexConsts hc, int64_t planes,
+hexsrc_linear_kernel(const TS* __restrict__ src, TD* __restrict__ dst, Coord coord, HexConsts hc, int64_t planes, int chunk,
                      int h, int w, int h1, int w1, int tiles_x, int tiles_y) {
   using CT = typename Coord::CT;
   using WT = typename std::conditional<FAST, float, CT>::type;
@@ -319,8 +351,8 @@ hexsrc_linear_kernel(const TS* __restrict__ src, TD* __restrict__ dst, Coord coo
   int tile = blockIdx.x;
   const int tx = tile % tiles_x; tile /= tiles_x;
   const int ty = tile % tiles_y;
-  const int64_t p0 = (int64_t)(tile / tiles_y) * kPlaneChunk;
-  const int np = (int)min((int64_t)kPlaneChunk, planes - p0);
+  const int64_t p0 = (int64_t)(tile / tiles_y) * chunk;
+  const int np = (int)min((int64_t)chunk, planes - p0);
   const int64_t sps = (int64_t)h * w, dps = (int64_t)h1 * w1;
 
   for (int rr = 0; rr < kRowsPerWarp; ++rr) {
@@ -365,15 +397,15 @@ hexsrc_linear_kernel(const TS* __restrict__ src, TD* __restrict__ dst, Coord coo
 
 template <typename T, typename Coord>
 __global__ void __launch_bounds__(kThreads)
-hexsrc_nearest_kernel(const T* __restrict__ src, T* __restrict__ dst, Coord coord, HexConsts hc, int64_t planes,
+hexsrc_nearest_kernel(const T* __restrict__ src, T* __restrict__ dst, Coord coord, HexConsts hc, int64_t planes, int chunk,
                       int h, int w, int h1, int w1, int tiles_x, int tiles_y) {
   using CT = typename Coord::CT;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int tile = blockIdx.x;
   const int tx = tile % tiles_x; tile /= tiles_x;
   const int ty = tile % tiles_y;
-  const int64_t p0 = (int64_t)(tile / tiles_y) * kPlaneChunk;
-  const int np = (int)min((int64_t)kPlaneChunk, planes - p0);
+  const int64_t p0 = (int64_t)(tile / tiles_y) * chunk;
+  const int np = (int)min((int64_t)chunk, planes - p0);
   const int64_t sps = (int64_t)h * w, dps = (int64_t)h1 * w1;
   for (int rr = 0; rr < kRowsPerWarp; ++rr) {
     const int a = ty * kTileH + warp * kRowsPerWarp + rr;
@@ -439,6 +471,9 @@ static int check_plane(int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t
   return HG_OK;
 }
 
+// hg_hexsrc_tma.cu: same contract
+int try_hexsrc_linear_tma(const void* src, void* dst, const double* xs, const double* ys, const double* host_xs, const double* host_ys,
+                          int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1, int sdt, int ddt, int math, cudaStream_t st);
 // hg_resample_tma.cu: HG_OK launched, 1 not applicable (fall back to the direct gather), else error
 int try_rect2hex_bilinear_tma(const void* src, void* dst, const double* xs, const double* ys, const double* host_xs,
                               const double* host_ys, int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1, int sdt,
@@ -448,14 +483,15 @@ template <typename TS, typename TD>
 static int launch_rect2hex_bilinear(const void* src, void* dst, const double* xs, const double* ys, int64_t planes,
                                     int64_t h, int64_t w, int64_t h1, int64_t w1, int math, cudaStream_t st) {
   Tiling t;
-  int rc = make_tiling(h1, w1, planes, t);
+  const int chunk = plane_chunk(planes, ceil_div(h1, kTileH) * ceil_div(w1, kTileW));
+  int rc = make_tiling(h1, w1, ceil_div(planes, chunk), t);
   if (rc) return rc;
   if (math == HG_MATH_EXACT)
     rect2hex_bilinear_kernel<TS, TD, true><<<(unsigned)t.blocks, kThreads, 0, st>>>(
-        (const TS*)src, (TD*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, t.tx, t.ty);
+        (const TS*)src, (TD*)dst, xs, ys, planes, chunk, (int)h, (int)w, (int)h1, (int)w1, t.tx, t.ty);
   else
     rect2hex_bilinear_kernel<TS, TD, false><<<(unsigned)t.blocks, kThreads, 0, st>>>(
-        (const TS*)src, (TD*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, t.tx, t.ty);
+        (const TS*)src, (TD*)dst, xs, ys, planes, chunk, (int)h, (int)w, (int)h1, (int)w1, t.tx, t.ty);
   return finish_launch("rect2hex_bilinear");
 }
 
@@ -463,10 +499,11 @@ template <typename T>
 static int launch_rect2hex_nearest(const void* src, void* dst, const double* xs, const double* ys, int64_t planes,
                                    int64_t h, int64_t w, int64_t h1, int64_t w1, cudaStream_t st) {
   Tiling t;
-  int rc = make_tiling(h1, w1, planes, t);
+  const int chunk = plane_chunk(planes, ceil_div(h1, kTileH) * ceil_div(w1, kTileW));
+  int rc = make_tiling(h1, w1, ceil_div(planes, chunk), t);
   if (rc) return rc;
-  rect2hex_nearest_kernel<T><<<(unsigned)t.blocks, kThreads, 0, st>>>((const T*)src, (T*)dst, xs, ys, (int)h, (int)w,
-                                                                      (int)h1, (int)w1, t.tx, t.ty);
+  rect2hex_nearest_kernel<T><<<(unsigned)t.blocks, kThreads, 0, st>>>((const T*)src, (T*)dst, xs, ys, planes, chunk, (int)h,
+                                                                      (int)w, (int)h1, (int)w1, t.tx, t.ty);
   return finish_launch("rect2hex_nearest");
 }
 
@@ -474,10 +511,11 @@ template <typename TS, typename TD, typename Coord, bool FAST>
 static int launch_hexsrc_linear(const void* src, void* dst, const Coord& c, int64_t planes, int64_t h, int64_t w,
                                 int64_t h1, int64_t w1, cudaStream_t st) {
   Tiling t;
-  int rc = make_tiling(h1, w1, ceil_div(planes, kPlaneChunk), t);
+  const int chunk = plane_chunk(planes, ceil_div(h1, kTileH) * ceil_div(w1, kTileW));
+  int rc = make_tiling(h1, w1, ceil_div(planes, chunk), t);
   if (rc) return rc;
   hexsrc_linear_kernel<TS, TD, Coord, FAST><<<(unsigned)t.blocks, kThreads, 0, st>>>(
-      (const TS*)src, (TD*)dst, c, hex_consts(h, w), planes, (int)h, (int)w, (int)h1, (int)w1, t.tx, t.ty);
+      (const TS*)src, (TD*)dst, c, hex_consts(h, w), planes, chunk, (int)h, (int)w, (int)h1, (int)w1, t.tx, t.ty);
   return finish_launch("hexsrc_linear");
 }
 
@@ -501,12 +539,13 @@ template <typename Coord>
 static int dispatch_hexsrc_nearest(const void* src, void* dst, const Coord& c, int64_t planes, int64_t h, int64_t w,
                                    int64_t h1, int64_t w1, int elem, cudaStream_t st) {
   Tiling t;
-  int rc = make_tiling(h1, w1, ceil_div(planes, kPlaneChunk), t);
+  const int chunk = plane_chunk(planes, ceil_div(h1, kTileH) * ceil_div(w1, kTileW));
+  int rc = make_tiling(h1, w1, ceil_div(planes, chunk), t);
   if (rc) return rc;
   const HexConsts hc = hex_consts(h, w);
 #define HG_CASE(E, T)                                                                                          \
   if (elem == E) {                                                                                             \
-    hexsrc_nearest_kernel<T, Coord><<<(unsigned)t.blocks, kThreads, 0, st>>>((const T*)src, (T*)dst, c, hc, planes, \
+    hexsrc_nearest_kernel<T, Coord><<<(unsigned)t.blocks, kThreads, 0, st>>>((const T*)src, (T*)dst, c, hc, planes, chunk, \
                                                                             (int)h, (int)w, (int)h1, (int)w1, t.tx, t.ty); \
     return finish_launch("hexsrc_nearest");                                                                    \
   }
@@ -620,12 +659,15 @@ int hg_hex2rect_nearest(const void* src, void* dst, const double* xs, const doub
   return dispatch_hexsrc_nearest(src, dst, CoordTables{xs, ys}, planes, h, w, h1, w1, elem_size, as_stream(stream));
 }
 
-int hg_hex2rect_linear(const void* src, void* dst, const double* xs, const double* ys, int64_t planes, int64_t h,
-                       int64_t w, int64_t h1, int64_t w1, int src_dtype, int dst_dtype, int math, hg_stream_t stream) {
+int hg_hex2rect_linear(const void* src, void* dst, const double* xs, const double* ys, const double* host_xs,
+                       const double* host_ys, int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1, int src_dtype,
+                       int dst_dtype, int math, hg_stream_t stream) {
   int rc = check_plane(planes, h, w, h1, w1);
   if (rc) return rc;
   HG_REQUIRE(math == HG_MATH_EXACT || math == HG_MATH_FAST, HG_E_ARG, "bad math mode %d", math);
   if (planes == 0 || h1 == 0 || w1 == 0) return HG_OK;
+  rc = try_hexsrc_linear_tma(src, dst, xs, ys, host_xs, host_ys, planes, h, w, h1, w1, src_dtype, dst_dtype, math, as_stream(stream));
+  if (rc != 1) return rc;
   CoordTables c{xs, ys};
   if (math == HG_MATH_EXACT)
     return dispatch_hexsrc_linear<CoordTables, false>(src, dst, c, planes, h, w, h1, w1, src_dtype, dst_dtype, as_stream(stream));

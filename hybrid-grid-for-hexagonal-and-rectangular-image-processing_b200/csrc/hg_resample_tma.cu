@@ -243,11 +243,8 @@ static int launch_tma(const void* src, void* dst, const double* xs, const double
   using WT = typename std::conditional<EXACT, double, float>::type;
   const int smem = kTmaStages * stage_bytes + 64 + 2 * (int)sizeof(TileTables<WT, RW>);
   auto kern = rect2hex_bilinear_tma_kernel<TS, TD, EXACT, RW>;
-  static thread_local int configured_smem = 0;
-  if (smem > configured_smem) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) { cudaGetLastError(); return 1; }
-    configured_smem = smem;
-  }
+  static SmemReservation reservation;
+  if (reservation.reserve(kern, (size_t)smem) != cudaSuccess) return 1;
   if (g_sm_count == 0) {
     int dev = 0;
     cudaGetDevice(&dev);

@@ -100,8 +100,10 @@ int hg_rect2hex_bilinear(const void* src, void* dst, const double* xs, const dou
 int hg_hex2rect_nearest(const void* src, void* dst, const double* xs, const double* ys,
                         int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1,
                         int elem_size, hg_stream_t stream);
+/* host_xs / host_ys (may be NULL): host copies of the tables; with them float32 HG_MATH_FAST calls on
+ * lattices of similar pitch run the TMA-staged tile kernel (identical indices, float32 weights). */
 int hg_hex2rect_linear(const void* src, void* dst, const double* xs, const double* ys,
-                       int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1,
+                       const double* host_xs, const double* host_ys, int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1,
                        int src_dtype, int dst_dtype, int math, hg_stream_t stream);
 
 /* ref: geometry_torch.py:7-189 image_geometric_transformation_gpu (coord_f32 = 1) /

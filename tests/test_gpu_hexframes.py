@@ -186,6 +186,34 @@ def test_hexpool_vs_oracle_with_nans(hf, method, dtype):
         np.testing.assert_allclose(xg.grad.float().cpu().numpy(), xr.grad.float().numpy(), **tol)
 
 
+@pytest.mark.parametrize("method", ["max", "min", "average"])
+@pytest.mark.parametrize("shape", [(2, 3, 66, 76), (1, 2, 37, 64), (1, 1, 6, 8), (2, 2, 5, 132), (1, 1, 64, 260), (1, 3, 2, 4)])
+def test_hexpool_2x2_fast_path_vs_oracle(hf, method, shape):
+    """HexPool2d(method, 2, 2) on float32 maps whose width is a multiple of 4 runs the vectorised 2 x 2 kernels
+    (hexpool2x2_fwd / _bwd): same bit-exact max / min and slots, same NaN rules, odd heights, several segments."""
+    torch.manual_seed(5)
+    x = torch.randn(shape)
+    x[torch.rand_like(x) < 0.2] = float("nan")
+    if shape[2] >= 4:
+        x[0, 0, :4, :8] = float("nan")                   # whole windows of NaN
+    xr = x.clone().requires_grad_()
+    ref = HO.hexpool2d(xr, method, 2, 2)
+    xg = x.cuda().requires_grad_()
+    y = hf.HexPool2d(method, 2, 2)(xg)
+    assert y.shape == ref.shape
+    if method == "average":
+        np.testing.assert_allclose(y.detach().cpu().numpy(), ref.detach().numpy(), equal_nan=True, rtol=1e-6, atol=1e-7)
+    else:
+        assert np.array_equal(y.detach().cpu().numpy(), ref.detach().numpy(), equal_nan=True)
+    g = torch.randn(ref.shape)
+    (torch.nan_to_num(ref) * g).sum().backward()
+    (torch.nan_to_num(y) * g.cuda()).sum().backward()
+    np.testing.assert_allclose(xg.grad.cpu().numpy(), xr.grad.numpy(), rtol=1e-6, atol=1e-7)
+    # inference (no aux buffer) gives the same map
+    with torch.no_grad():
+        assert np.array_equal(hf.HexPool2d(method, 2, 2)(x.cuda()).cpu().numpy(), y.detach().cpu().numpy(), equal_nan=True)
+
+
 def test_hexpool_errors_and_defaults(hf):
     p = hf.HexPool2d("max", 2)                           # stride=None -> kernel_size (reference crashes)
     y = p(torch.randn(1, 2, 16, 16, device="cuda"))

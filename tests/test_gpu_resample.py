@@ -213,6 +213,25 @@ def test_r2_r4_vs_oracle(Fn, dtype, shape, dsize):
         Fn.hex_to_rect(cu(img), dsize, "bilinear")
 
 
+@pytest.mark.parametrize("shape,dsize", [((5, 64, 256), None), ((4, 96, 132), (200, 300)), ((1, 100, 120), (100, 120)),
+                                         ((7, 33, 16), (70, 40)), ((3, 50, 260), (47, 250)), ((6, 40, 64), (17, 300))])
+def test_r2_r4_tma_tiles_vs_oracle(Fn, shape, dsize):
+    """float32 HG_MATH_FAST hex-source resampling on 16-byte aligned rows runs the TMA-staged tile kernel
+    (hexsrc_linear_tma): plane groups of 3 with a ragged last group, tiles cut by the image border, up- and
+    down-sampling; same lattice points as the oracle, float32 weights (<= 1e-5 * max|x|)."""
+    rng = np.random.default_rng(13)
+    img = (rng.random(shape) * 255).astype(np.float32)
+    ds = dsize or shape[1:]
+    full = lambda a: np.asarray(a).reshape((shape[0],) + tuple(ds))
+    close(Fn.hex_to_rect(cu(img), dsize, "linear", out_dtype=torch.float32, math="fast", twin="np"),
+          full(O.hex_to_rect_resample(img, dsize, "linear", twin="np")), 255.0)
+    close(Fn.hex_resize(cu(img), ds, "linear", out_dtype=torch.float32, math="fast"), full(O.hexresize(img, ds, "linear")), 255.0)
+    # a constant image stays constant wherever all three lattice points are inside (weights sum to one)
+    ones = Fn.hex_to_rect(torch.ones(shape, device="cuda"), dsize, "linear", out_dtype=torch.float32, math="fast", twin="np")
+    ref1 = full(O.hex_to_rect_resample(np.ones(shape, np.float32), dsize, "linear", twin="np"))
+    close(ones, ref1, 1.0)
+
+
 def test_r2_full_size_properties(Fn):
     """4K geometry (config 4), one image: linearity + partition of unity of the barycentric weights."""
     torch.manual_seed(1)
