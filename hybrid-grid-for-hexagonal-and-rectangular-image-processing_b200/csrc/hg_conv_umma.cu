@@ -147,6 +147,9 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
               for (int e = 0; e < 8; ++e) v[q][e] = to_f32(rp[(kc * 8 + e) * kUmPW + p]);
             }
           }
+          // generic-proxy reads of the stage -> TMA (async proxy) refill: proxy fence before the release (the
+          // CUTLASS consumer_release pattern; see hg_conv_wgrad_umma.cu for the failure it prevents)
+          ptx::fence_proxy_async_smem();
           __syncwarp();                      // the whole warp holds its values in registers:
           if (lane == 0) ptx::mbar_arrive(&rempty[rs]);   // one arrival per warp, the stage can be refilled
           ptx::mbar_wait(&empty[slot], (use & 1) ^ 1);

@@ -110,24 +110,31 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
     const size_t xplane = (size_t)P.H * P.W, gplane = (size_t)P.Ho * P.Wo;
     const int xtasks = (P.Cin >> 3) * kWuPW, gtasks = (P.Cout >> 3) * kWuTile;
     uint32_t xs = 0, xph = 0, gs = 0, gph = 0, rs = 0, rph = 0;      // ring positions / parities
-    auto pack_store = [&](unsigned char* sb, int task, const float (&v)[8]) {
-      uint4 pk;
-      pk.x = wu_pack(v[0], v[1]); pk.y = wu_pack(v[2], v[3]); pk.z = wu_pack(v[4], v[5]); pk.w = wu_pack(v[6], v[7]);
-      *reinterpret_cast<uint4*>(sb + (size_t)task * 16) = pk;
-    };
     auto publish = [&](uint64_t* bar) {     // all of this warp's writes fenced, then one arrival per warp
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar);
     };
+    // The stage may be refilled by TMA (async proxy) as soon as rempty completes.  The refill of a stage that held a
+    // gy row is an x row and vice versa, so the zero-fill of the new box's out-of-range columns (written without
+    // any memory latency) lands on *valid* data of the old layout: the shared-memory reads above must have been
+    // performed before the arrival.  The values are packed (register dependency on every LDS) and a
+    // generic -> async proxy fence is issued first -- the CUTLASS consumer_release pattern for TMA-fed stages.
+    // (Measured on B200 without it: intermittent wrong gw rows, only on the TMA path.)
     auto raw_done = [&]() {                 // this warp has the raw row in registers
+      ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&rempty[rs]);
       if (++rs == (uint32_t)P.rstages) { rs = 0; rph ^= 1; }
     };
+    auto pack8 = [&](const float (&v)[8]) {
+      uint4 pk;
+      pk.x = wu_pack(v[0], v[1]); pk.y = wu_pack(v[2], v[3]); pk.z = wu_pack(v[4], v[5]); pk.w = wu_pack(v[6], v[7]);
+      return pk;
+    };
     auto load_x = [&](const TX* __restrict__ xn, int i, int c0) {
       unsigned char* sb = xring + (size_t)xs * xslot_bytes;
-      float v[kWuMaxQ][8];
+      uint4 pk[kWuMaxQ];
       if (TMA) {
         ptx::mbar_wait(&rfull[rs], rph);
         const TX* __restrict__ rp = reinterpret_cast<const TX*>(raw + (size_t)rs * P.raw_bytes);
@@ -136,8 +143,10 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
           const int task = tid + q * kWuConv;
           if (task < xtasks) {
             const int kc = task / kWuPW, p = task - kc * kWuPW;
+            float v[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[q][e] = to_f32(rp[(kc * 8 + e) * kWuPW + p]);
+            for (int e = 0; e < 8; ++e) v[e] = to_f32(rp[(kc * 8 + e) * kWuPW + p]);
+            pk[q] = pack8(v);
           }
         }
         raw_done();
@@ -154,15 +163,17 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
             const bool col_in = j >= 0 && j < P.W;
             const float fill = (row_frame && j >= -P.pad && j < P.W + P.pad) ? P.pad_value : 0.f;
             const TX* __restrict__ src = xn + (size_t)(kc * 8) * xplane + (size_t)i * P.W + j;
+            float v[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[q][e] = (row_in && col_in) ? wu_ld(src + (size_t)e * xplane) : fill;
+            for (int e = 0; e < 8; ++e) v[e] = (row_in && col_in) ? wu_ld(src + (size_t)e * xplane) : fill;
+            pk[q] = pack8(v);
           }
         }
       }
 #pragma unroll
       for (int q = 0; q < kWuMaxQ; ++q) {
         const int task = tid + q * kWuConv;
-        if (task < xtasks) pack_store(sb, task, v[q]);
+        if (task < xtasks) *reinterpret_cast<uint4*>(sb + (size_t)task * 16) = pk[q];
       }
       publish(&xfull[xs]);
       if (++xs == (uint32_t)P.xslots) { xs = 0; xph ^= 1; }
@@ -171,7 +182,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
       unsigned char* sb = gring + (size_t)gs * gslot_bytes;
       bool waited = false;
       for (int base = 0; base < gtasks; base += kWuMaxQ * kWuConv) {   // Cout = 128 needs two passes
-        float v[kWuMaxQ][8];
+        uint4 pk[kWuMaxQ];
         if (TMA) {
           if (base == 0) ptx::mbar_wait(&rfull[rs], rph);
           const TG* __restrict__ rp = reinterpret_cast<const TG*>(raw + (size_t)rs * P.raw_bytes);
@@ -180,8 +191,10 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
             const int task = base + tid + q * kWuConv;
             if (task < gtasks) {
               const int kc = task / kWuTile, p = task - kc * kWuTile;
+              float v[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[q][e] = to_f32(rp[(kc * 8 + e) * kWuTile + p]);
+              for (int e = 0; e < 8; ++e) v[e] = to_f32(rp[(kc * 8 + e) * kWuTile + p]);
+              pk[q] = pack8(v);
             }
           }
           if (base + kWuMaxQ * kWuConv >= gtasks) raw_done();
@@ -193,8 +206,10 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
               const int kc = task / kWuTile, p = task - kc * kWuTile;
               const int c = c0 + p;
               const TG* __restrict__ src = gn + (size_t)(kc * 8) * gplane + (size_t)R * P.Wo + c;
+              float v[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[q][e] = c < P.Wo ? wu_ld(src + (size_t)e * gplane) : 0.f;
+              for (int e = 0; e < 8; ++e) v[e] = c < P.Wo ? wu_ld(src + (size_t)e * gplane) : 0.f;
+              pk[q] = pack8(v);
             }
           }
         }
@@ -202,7 +217,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
 #pragma unroll
         for (int q = 0; q < kWuMaxQ; ++q) {
           const int task = base + tid + q * kWuConv;
-          if (task < gtasks) pack_store(sb, task, v[q]);
+          if (task < gtasks) *reinterpret_cast<uint4*>(sb + (size_t)task * 16) = pk[q];
         }
       }
       publish(&gfull[gs]);

@@ -64,25 +64,31 @@ hexsrc_linear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __restric
     ptx::fence_barrier_init();
   }
 
-  auto decode = [&](long long g, int& grp, int& tx, int& ty) {   // plane-group major, tiles row-major
-    grp = (int)(g / npos);
-    const int pos = (int)(g - (long long)grp * npos);
-    ty = pos / tiles_x; tx = pos - ty * tiles_x;
+  // plane-group major, tiles row-major; a CTA's items are consecutive, so positions advance by carries
+  struct Pos { int grp, tx, ty; };
+  auto decode = [&](long long g) {
+    Pos q;
+    q.grp = (int)(g / npos);
+    const int pos = (int)(g - (long long)q.grp * npos);
+    q.ty = pos / tiles_x; q.tx = pos - q.ty * tiles_x;
+    return q;
+  };
+  auto advance = [&](Pos& q) {
+    if (++q.tx == tiles_x) { q.tx = 0; if (++q.ty == tiles_y) { q.ty = 0; ++q.grp; } }
   };
   auto origin = [&](int tx, int ty, int& row0, int& col0) {
     row0 = trunc_i32(dadd(xs[ty * kHsTH], ci));
     col0 = hs_col_origin(ys[tx * kHsTW], cj);
   };
-  auto issue = [&](long long g, int s) {   // one thread
-    int grp, tx, ty, row0, col0;
-    decode(g, grp, tx, ty);
-    origin(tx, ty, row0, col0);
+  auto issue = [&](const Pos& q, int s) {   // one thread
+    int row0, col0;
+    origin(q.tx, q.ty, row0, col0);
     ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(kHsG * plane_elems * 4));
-    ptx::tma_load_3d(smem_raw + (size_t)s * stage_bytes, &tmap, &full[s], col0, row0, grp * kHsG);
+    ptx::tma_load_3d(smem_raw + (size_t)s * stage_bytes, &tmap, &full[s], col0, row0, q.grp * kHsG);
   };
-  auto build_tables = [&](long long g, HsTables& T) {   // threads 0 .. kHsTW + kHsTH - 1
-    int grp, tx, ty, row0, col0;
-    decode(g, grp, tx, ty);
+  auto build_tables = [&](const Pos& q, HsTables& T) {   // threads 0 .. kHsTW + kHsTH - 1
+    int row0, col0;
+    const int tx = q.tx, ty = q.ty;
     origin(tx, ty, row0, col0);
     const int t = threadIdx.x;
     if (t < kHsTW) {
@@ -99,20 +105,21 @@ hexsrc_linear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __restric
     }
   };
 
-  build_tables(g_begin, tabs[0]);
+  Pos cur = decode(g_begin), nxt = cur, iss = cur;
+  advance(nxt);
+  build_tables(cur, tabs[0]);
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kHsStages && g_begin + s < g_end; ++s) issue(g_begin + s, s);
+    for (int s = 0; s < kHsStages && g_begin + s < g_end; ++s) { issue(iss, s); advance(iss); }
   }
 
-  for (long long k = 0; g_begin + k < g_end; ++k) {
-    const int s = (int)(k % kHsStages);
-    const uint32_t parity = (uint32_t)((k / kHsStages) & 1);
+  const int n_items = (int)(g_end - g_begin);
+  int s = 0;
+  uint32_t parity = 0;
+  for (int k = 0; k < n_items; ++k) {
     const HsTables& T = tabs[k & 1];
-    if (g_begin + k + 1 < g_end) build_tables(g_begin + k + 1, tabs[(k + 1) & 1]);
-
-    int grp, tx, ty;
-    decode(g_begin + k, grp, tx, ty);
+    if (k + 1 < n_items) build_tables(nxt, tabs[(k + 1) & 1]);
+    const int grp = cur.grp, tx = cur.tx, ty = cur.ty;
     const int np = min(kHsG, planes - grp * kHsG);
     const int nrows = min(kHsRW, T.nrows - warp * kHsRW);
     const int row0 = T.row0, col0 = T.col0;
@@ -160,7 +167,10 @@ hexsrc_linear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __restric
       }
     }
     __syncthreads();                            // stage s fully read; next item's tables complete
-    if (threadIdx.x == 0 && g_begin + k + kHsStages < g_end) issue(g_begin + k + kHsStages, s);
+    if (threadIdx.x == 0 && k + kHsStages < n_items) { issue(iss, s); advance(iss); }
+    cur = nxt;
+    advance(nxt);
+    if (++s == kHsStages) { s = 0; parity ^= 1; }
   }
 }
 

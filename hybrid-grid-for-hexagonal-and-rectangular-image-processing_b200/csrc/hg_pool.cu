@@ -304,11 +304,108 @@ hexpool2x2_bwd_kernel(const float* __restrict__ gy, const int8_t* __restrict__ a
   }
 }
 
-static bool pool2x2_ok(const PoolGeom& g, int tail_h, int tail_w, const void* a, const void* b) {
+// Same configuration for ANY width / alignment (the deeper pyramid levels are 1919, 959, 479 ... cells wide):
+// lanes run along the input columns, so all 16 loads of a warp (4 rows x 128 columns) are fully coalesced
+// scalar loads; the horizontal neighbour of a window comes from lane + 1 by shuffle (from the first lane of the
+// next 32-column chunk, or one extra scalar load at the segment end).  Windows of the even output row start on
+// even lanes, those of the odd output row on odd lanes.
+template <int METHOD>
+__global__ void __launch_bounds__(kPoolThreads)
+hexpool2x2c_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int8_t* __restrict__ aux, long long items, int pairs,
+                       int segs, int H, int W, int hn, int wn) {
+  const long long item = (long long)blockIdx.x * (kPoolThreads / 32) + (threadIdx.x >> 5);
+  if (item >= items) return;                              // warp-uniform
+  const int lane = threadIdx.x & 31;
+  const long long pr = item / segs;
+  const int seg = (int)(item - pr * segs);
+  const long long plane = pr / pairs;
+  const int g = (int)(pr - plane * pairs);
+  const int I0 = 2 * g;
+  const bool has_odd = I0 + 1 < hn;
+  const int col0 = seg * 128 + lane;
+  const float* __restrict__ xp = x + ((size_t)plane * H + (size_t)2 * I0) * W;
+  float v[4][4];                                          // [chunk][row]
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      v[k][r] = (col0 + 32 * k < W && (r < 2 || has_odd)) ? __ldg(xp + (size_t)r * W + col0 + 32 * k) : 0.f;
+  float edge2 = 0.f, edge3 = 0.f;                         // column seg*128 + 128 of rows 2, 3 (lane 31 only)
+  if (lane == 31 && has_odd && seg * 128 + 128 < W) {
+    edge2 = __ldg(xp + (size_t)2 * W + seg * 128 + 128);
+    edge3 = __ldg(xp + (size_t)3 * W + seg * 128 + 128);
+  }
+  const size_t yb = ((size_t)plane * hn + I0) * wn;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int col = col0 + 32 * k;
+    float n[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) n[r] = __shfl_down_sync(0xffffffffu, v[k][r], 1);
+    if (k < 3) {
+      const float f2 = __shfl_sync(0xffffffffu, v[k < 3 ? k + 1 : 3][2], 0), f3 = __shfl_sync(0xffffffffu, v[k < 3 ? k + 1 : 3][3], 0);
+      if (lane == 31) { n[2] = f2; n[3] = f3; }
+    } else if (lane == 31) { n[2] = edge2; n[3] = edge3; }
+    float o; int a;
+    if ((lane & 1) == 0) {                                // even output row: window starts at this (even) column
+      const int J = col >> 1;
+      if (J < wn) {
+        pool4<METHOD>(v[k][0], n[0], v[k][1], n[1], o, a);
+        __stcs(y + yb + J, o);
+        if (aux) aux[yb + J] = (int8_t)a;
+      }
+    } else if (has_odd) {                                 // odd output row: window starts at this (odd) column
+      const int J = (col - 1) >> 1;
+      if (J < wn) {
+        pool4<METHOD>(v[k][2], n[2], v[k][3], n[3], o, a);
+        __stcs(y + yb + wn + J, o);
+        if (aux) aux[yb + wn + J] = (int8_t)a;
+      }
+    }
+  }
+}
+
+template <int METHOD>
+__global__ void __launch_bounds__(kPoolThreads)
+hexpool2x2c_bwd_kernel(const float* __restrict__ gy, const int8_t* __restrict__ aux, const float* __restrict__ x,
+                       float* __restrict__ gx, long long items, int pairs, int segs, int H, int W, int hn, int wn) {
+  const long long item = (long long)blockIdx.x * (kPoolThreads / 32) + (threadIdx.x >> 5);
+  if (item >= items) return;
+  const int lane = threadIdx.x & 31;
+  const long long pr = item / segs;
+  const int seg = (int)(item - pr * segs);
+  const long long plane = pr / pairs;
+  const int g = (int)(pr - plane * pairs);
+  const int I0 = 2 * g, row0 = 4 * g;
+  const size_t ob = (size_t)plane * hn * wn;
+  const size_t base = ((size_t)plane * H + row0) * W;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int col = seg * 128 + 32 * k + lane;
+    if (col >= W) continue;
+    float ge = 0.f, go = 0.f;
+    int ae = METHOD == HG_POOL_AVG ? 0 : -1, ao = ae;
+    const int Je = col >> 1, be = col & 1;                // even output row: window / slot column of this cell
+    const int Jo = (col - 1) >> 1, bo = (col - 1) & 1;    // odd output row (cells shifted right by one)
+    if (I0 < hn && Je < wn) { const size_t o = ob + (size_t)I0 * wn + Je; ge = __ldg(gy + o); ae = (int)aux[o]; }
+    if (I0 + 1 < hn && col >= 1 && Jo < wn) { const size_t o = ob + (size_t)(I0 + 1) * wn + Jo; go = __ldg(gy + o); ao = (int)aux[o]; }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (row0 + r >= H) break;
+      float v = r < 2 ? pool4_grad<METHOD>(ge, ae, r * 2 + be) : pool4_grad<METHOD>(go, ao, (r - 2) * 2 + bo);
+      if (METHOD == HG_POOL_AVG && x != nullptr) { const float xv = __ldg(x + base + (size_t)r * W + col); if (xv != xv) v = 0.f; }
+      __stcs(gx + base + (size_t)r * W + col, v);
+    }
+  }
+}
+
+static bool pool2x2_ok(const PoolGeom& g, int tail_h, int tail_w) {
   static const bool off = [] { const char* e = getenv("HG_POOL_GENERIC"); return e && e[0] == '1'; }();
   return !off && g.kh == 2 && g.kw == 2 && g.sh == 2 && g.sw == 2 && g.shift == 2 && g.pad == 0 && tail_h == 0 && tail_w == 0 &&
-         g.W % 4 == 0 && g.hn == g.H / 2 && g.wn == (g.W - 1) / 2 && (reinterpret_cast<uintptr_t>(a) & 15) == 0 &&
-         (reinterpret_cast<uintptr_t>(b) & 15) == 0;
+         g.hn == g.H / 2 && g.wn == (g.W - 1) / 2 && g.hn > 0 && g.wn > 0;
+}
+static bool pool2x2_vec_ok(const PoolGeom& g, const void* a, const void* b) {   // float4 rows
+  return g.W % 4 == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0;
 }
 
 // ---- global pooling: x [planes, L] -> y [planes] ------------------------------------------------------
@@ -493,12 +590,15 @@ int hg_hexpool_fwd(const void* x, void* y, void* aux, int aux_bytes, int64_t pla
   const int64_t total = planes * hn * wn;
   if (total == 0) return HG_OK;
   cudaStream_t st = as_stream(stream);
-  if (dtype == HG_F32 && (aux == nullptr || aux_bytes == 1) && pool2x2_ok(g, tail_h, tail_w, x, x)) {
+  if (dtype == HG_F32 && (aux == nullptr || aux_bytes == 1) && pool2x2_ok(g, tail_h, tail_w)) {
     const int pairs = (g.hn + 1) / 2, segs = (int)ceil_div(g.W, 128);
     const long long items = (long long)planes * pairs * segs;
     const long long blocks = ceil_div(items, kPoolThreads / 32);
     HG_REQUIRE(blocks < (1ll << 31), HG_E_SHAPE, "hexpool_fwd: too many rows for one launch");
-#define HG_P2(M) hexpool2x2_fwd_kernel<M><<<(unsigned)blocks, kPoolThreads, 0, st>>>((const float*)x, (float*)y, (int8_t*)aux, items, pairs, segs, g.H, g.W, g.hn, g.wn)
+    const bool vec = pool2x2_vec_ok(g, x, x);
+#define HG_P2(M)                                                                                                                          \
+  if (vec) hexpool2x2_fwd_kernel<M><<<(unsigned)blocks, kPoolThreads, 0, st>>>((const float*)x, (float*)y, (int8_t*)aux, items, pairs, segs, g.H, g.W, g.hn, g.wn); \
+  else hexpool2x2c_fwd_kernel<M><<<(unsigned)blocks, kPoolThreads, 0, st>>>((const float*)x, (float*)y, (int8_t*)aux, items, pairs, segs, g.H, g.W, g.hn, g.wn)
     switch (method) {
       case HG_POOL_MAX: HG_P2(HG_POOL_MAX); break;
       case HG_POOL_MIN: HG_P2(HG_POOL_MIN); break;
@@ -532,12 +632,15 @@ int hg_hexpool_bwd(const void* gy, const void* aux, int aux_bytes, const void* x
   const int64_t total = planes * H * W;
   if (total == 0) return HG_OK;
   cudaStream_t st = as_stream(stream);
-  if (dtype == HG_F32 && aux_bytes == 1 && pool2x2_ok(g, 0, 0, gx, x ? x : gx)) {
+  if (dtype == HG_F32 && aux_bytes == 1 && pool2x2_ok(g, 0, 0)) {
     const int pairs = (int)ceil_div(g.H, 4), segs = (int)ceil_div(g.W, 128);
     const long long items = (long long)planes * pairs * segs;
     const long long blocks = ceil_div(items, kPoolThreads / 32);
     HG_REQUIRE(blocks < (1ll << 31), HG_E_SHAPE, "hexpool_bwd: too many rows for one launch");
-#define HG_P2(M) hexpool2x2_bwd_kernel<M><<<(unsigned)blocks, kPoolThreads, 0, st>>>((const float*)gy, (const int8_t*)aux, (const float*)x, (float*)gx, items, pairs, segs, g.H, g.W, g.hn, g.wn)
+    const bool vec = pool2x2_vec_ok(g, gx, x ? x : gx);
+#define HG_P2(M)                                                                                                                          \
+  if (vec) hexpool2x2_bwd_kernel<M><<<(unsigned)blocks, kPoolThreads, 0, st>>>((const float*)gy, (const int8_t*)aux, (const float*)x, (float*)gx, items, pairs, segs, g.H, g.W, g.hn, g.wn); \
+  else hexpool2x2c_bwd_kernel<M><<<(unsigned)blocks, kPoolThreads, 0, st>>>((const float*)gy, (const int8_t*)aux, (const float*)x, (float*)gx, items, pairs, segs, g.H, g.W, g.hn, g.wn)
     switch (method) {
       case HG_POOL_MAX: HG_P2(HG_POOL_MAX); break;
       case HG_POOL_MIN: HG_P2(HG_POOL_MIN); break;

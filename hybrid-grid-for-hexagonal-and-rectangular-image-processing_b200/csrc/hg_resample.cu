@@ -80,43 +80,52 @@ rect2hex_bilinear_kernel(const TS* __restrict__ src, TD* __restrict__ dst, const
     c0[k] = cok && jn[k] >= 0 && jn[k] < w;
     c1[k] = cok && jn[k] + 1 >= 0 && jn[k] + 1 < w;
   }
-#pragma unroll 1
+  int in[kRowsPerWarp];
+  WT u[kRowsPerWarp];
+  bool r0[kRowsPerWarp], r1[kRowsPerWarp], rok[kRowsPerWarp];
+#pragma unroll
   for (int rr = 0; rr < kRowsPerWarp; ++rr) {
     const int a = ty * kTileH + warp * kRowsPerWarp + rr;
-    if (a >= h1) break;
-    int in; double ud;
-    rect_axis(xs[a], h, in, ud);
-    const WT u = (WT)ud;
-    const bool r0 = in >= 0 && in < h, r1 = in + 1 >= 0 && in + 1 < h;
-    const TS* __restrict__ row0 = src + p0 * sps + (int64_t)in * w;
-    TD* __restrict__ dp = dst + p0 * dps + (int64_t)a * w1 + tx * kTileW + lane;
-    for (int p = 0; p < np; ++p, row0 += sps, dp += dps) {
+    rok[rr] = a < h1;
+    double ud;
+    rect_axis(xs[rok[rr] ? a : h1 - 1], h, in[rr], ud);
+    u[rr] = (WT)ud;
+    r0[rr] = rok[rr] && in[rr] >= 0 && in[rr] < h;
+    r1[rr] = rok[rr] && in[rr] + 1 >= 0 && in[rr] + 1 < h;
+  }
+  const TS* __restrict__ sp = src + p0 * sps;
+  TD* __restrict__ dp = dst + p0 * dps + (int64_t)(ty * kTileH + warp * kRowsPerWarp) * w1 + tx * kTileW + lane;
+  for (int p = 0; p < np; ++p, sp += sps, dp += dps) {
+#pragma unroll
+    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+      if (!rok[rr]) continue;
+      const TS* __restrict__ row0 = sp + (int64_t)in[rr] * w;
       const TS* __restrict__ row1 = row0 + w;
       TS q[kColsPerThread][4];
 #pragma unroll
       for (int k = 0; k < kColsPerThread; ++k) {
-        q[k][0] = (r0 && c0[k]) ? ldg(row0 + jn[k]) : TS(0);
-        q[k][1] = (r0 && c1[k]) ? ldg(row0 + jn[k] + 1) : TS(0);
-        q[k][2] = (r1 && c0[k]) ? ldg(row1 + jn[k]) : TS(0);
-        q[k][3] = (r1 && c1[k]) ? ldg(row1 + jn[k] + 1) : TS(0);
+        q[k][0] = (r0[rr] && c0[k]) ? ldg(row0 + jn[k]) : TS(0);
+        q[k][1] = (r0[rr] && c1[k]) ? ldg(row0 + jn[k] + 1) : TS(0);
+        q[k][2] = (r1[rr] && c0[k]) ? ldg(row1 + jn[k]) : TS(0);
+        q[k][3] = (r1[rr] && c1[k]) ? ldg(row1 + jn[k] + 1) : TS(0);
       }
 #pragma unroll
       for (int k = 0; k < kColsPerThread; ++k) {
         if (tx * kTileW + lane + 32 * k >= w1) continue;
         TD o;
         if (EXACT) {
-          const double v = jf[k];
-          const double u1 = dsub(1.0, u), v1 = dsub(1.0, v);
-          const double t1 = dadd(dmul(u, to_f64(q[k][2])), dmul(u1, to_f64(q[k][0])));
-          const double t2 = dadd(dmul(u, to_f64(q[k][3])), dmul(u1, to_f64(q[k][1])));
+          const double uu = u[rr], v = jf[k];
+          const double u1 = dsub(1.0, uu), v1 = dsub(1.0, v);
+          const double t1 = dadd(dmul(uu, to_f64(q[k][2])), dmul(u1, to_f64(q[k][0])));
+          const double t2 = dadd(dmul(uu, to_f64(q[k][3])), dmul(u1, to_f64(q[k][1])));
           o = (TD)dadd(dmul(v, t2), dmul(v1, t1));
         } else {
-          const float uf = (float)u, vf = (float)jf[k];
+          const float uf = (float)u[rr], vf = (float)jf[k];
           const float t1 = fmaf(uf, to_f32(q[k][2]) - to_f32(q[k][0]), to_f32(q[k][0]));
           const float t2 = fmaf(uf, to_f32(q[k][3]) - to_f32(q[k][1]), to_f32(q[k][1]));
           o = (TD)fmaf(vf, t2 - t1, t1);
         }
-        st_stream(dp + 32 * k, o);
+        st_stream(dp + (int64_t)rr * w1 + 32 * k, o);
       }
     }
   }
@@ -395,6 +404,8 @@ hexsrc_linear_kernel(const TS* __restrict__ src, TD* __restrict__ dst, Coord coo
   }
 }
 
+// The closest lattice point of a sample does not depend on the plane: resolve the tile's 16 source offsets per
+// thread once (float64 / float32 distances exactly as the reference evaluates them), then stream `chunk` planes.
 template <typename T, typename Coord>
 __global__ void __launch_bounds__(kThreads)
 hexsrc_nearest_kernel(const T* __restrict__ src, T* __restrict__ dst, Coord coord, HexConsts hc, int64_t planes, int chunk,
@@ -407,29 +418,36 @@ hexsrc_nearest_kernel(const T* __restrict__ src, T* __restrict__ dst, Coord coor
   const int64_t p0 = (int64_t)(tile / tiles_y) * chunk;
   const int np = (int)min((int64_t)chunk, planes - p0);
   const int64_t sps = (int64_t)h * w, dps = (int64_t)h1 * w1;
+  int off[kRowsPerWarp][kColsPerThread];   // -1 = outside the lattice (zero), -2 = no such output cell
+#pragma unroll
   for (int rr = 0; rr < kRowsPerWarp; ++rr) {
     const int a = ty * kTileH + warp * kRowsPerWarp + rr;
-    if (a >= h1) break;
-    int off[kColsPerThread];
 #pragma unroll
     for (int k = 0; k < kColsPerThread; ++k) {
       const int b = tx * kTileW + lane + 32 * k;
-      off[k] = -2;
-      if (b < w1) {
+      off[rr][k] = -2;
+      if (a < h1 && b < w1) {
         CT x, y;
         coord.get(a, b, w1, x, y);
         HexSample<CT> s;
         hex_locate<CT, false, true>(x, y, h, w, (CT)hc.hx, (CT)hc.wy, (CT)hc.ci, (CT)hc.cj, s);
-        off[k] = s.off[s.nearest];
+        off[rr][k] = s.off[s.nearest];
       }
     }
-    const T* __restrict__ sp = src + p0 * sps;
-    T* __restrict__ dp = dst + p0 * dps + (int64_t)a * w1 + tx * kTileW + lane;
-    for (int p = 0; p < np; ++p, sp += sps, dp += dps) {
+  }
+  const T* __restrict__ sp = src + p0 * sps;
+  T* __restrict__ dp = dst + p0 * dps + (int64_t)(ty * kTileH + warp * kRowsPerWarp) * w1 + tx * kTileW + lane;
+  for (int p = 0; p < np; ++p, sp += sps, dp += dps) {
+    T v[kRowsPerWarp][kColsPerThread];
+#pragma unroll
+    for (int rr = 0; rr < kRowsPerWarp; ++rr)
+#pragma unroll
+      for (int k = 0; k < kColsPerThread; ++k) v[rr][k] = off[rr][k] >= 0 ? ldg(sp + off[rr][k]) : T(0);
+#pragma unroll
+    for (int rr = 0; rr < kRowsPerWarp; ++rr)
 #pragma unroll
       for (int k = 0; k < kColsPerThread; ++k)
-        if (off[k] != -2) dp[32 * k] = off[k] >= 0 ? ldg(sp + off[k]) : T(0);
-    }
+        if (off[rr][k] != -2) st_stream(dp + (int64_t)rr * w1 + 32 * k, v[rr][k]);
   }
 }
 
@@ -511,7 +529,7 @@ template <typename TS, typename TD, typename Coord, bool FAST>
 static int launch_hexsrc_linear(const void* src, void* dst, const Coord& c, int64_t planes, int64_t h, int64_t w,
                                 int64_t h1, int64_t w1, cudaStream_t st) {
   Tiling t;
-  const int chunk = plane_chunk(planes, ceil_div(h1, kTileH) * ceil_div(w1, kTileW));
+  const int chunk = 8;   // row-outer loop: larger chunks lose the L1 reuse of source rows shared by consecutive output rows (measured)
   int rc = make_tiling(h1, w1, ceil_div(planes, chunk), t);
   if (rc) return rc;
   hexsrc_linear_kernel<TS, TD, Coord, FAST><<<(unsigned)t.blocks, kThreads, 0, st>>>(

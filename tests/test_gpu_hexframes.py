@@ -187,7 +187,8 @@ def test_hexpool_vs_oracle_with_nans(hf, method, dtype):
 
 
 @pytest.mark.parametrize("method", ["max", "min", "average"])
-@pytest.mark.parametrize("shape", [(2, 3, 66, 76), (1, 2, 37, 64), (1, 1, 6, 8), (2, 2, 5, 132), (1, 1, 64, 260), (1, 3, 2, 4)])
+@pytest.mark.parametrize("shape", [(2, 3, 66, 76), (1, 2, 37, 64), (1, 1, 6, 8), (2, 2, 5, 132), (1, 1, 64, 260), (1, 3, 2, 4),
+                                   (1, 2, 9, 131), (1, 1, 10, 258), (2, 1, 7, 33), (1, 1, 4, 3)])   # last four: any-width kernels
 def test_hexpool_2x2_fast_path_vs_oracle(hf, method, shape):
     """HexPool2d(method, 2, 2) on float32 maps whose width is a multiple of 4 runs the vectorised 2 x 2 kernels
     (hexpool2x2_fwd / _bwd): same bit-exact max / min and slots, same NaN rules, odd heights, several segments."""
