@@ -249,16 +249,17 @@ hexconv_wgrad_direct(const TX* __restrict__ x, const TG* __restrict__ gy, float*
         }
 #pragma unroll
         for (int b = 0; b < kWgC; ++b) {
-          const int cl = cl0 + b;
-          if (cl >= g.cin_g) break;
+          // no `break` in these loops: they must unroll completely or acc[][][] lands in local memory
+          const int cl = min(cl0 + b, g.cin_g - 1);
+          const bool cl_ok = cl0 + b < g.cin_g;
           const TX* __restrict__ xc = x + ((int64_t)n * g.Cin + (int64_t)grp * g.cin_g + cl) * g.H * g.W;
 #pragma unroll
           for (int k = 0; k < kWgKT; ++k) {
-            if (k >= kn) break;
-            const int i = g.s * R + tp.ro[kb + k] - g.pad;
-            const int j = g.s * q + tp.co[par][kb + k] - g.pad;
+            const int kk = min(kb + k, K - 1);
+            const int i = g.s * R + tp.ro[kk] - g.pad;
+            const int j = g.s * q + tp.co[par][kk] - g.pad;
             float v = 0.f;
-            if (j < g.W + g.pad) {
+            if (cl_ok && k < kn && j < g.W + g.pad) {
               v = g.pad_value;
               if (i >= 0 && i < g.H && j >= 0 && j < g.W) v = ldf(xc + (int64_t)i * g.W + j);
             }

@@ -39,6 +39,7 @@ constexpr int kUmThreads = kUmLoaders + 128 + 32 + 32;
 constexpr int kUmBand = 32;                  // output rows per work item
 constexpr int kUmMaxQ = 5;                   // ceil(8 * 144 / 256): (chunk, pixel) tasks per loader thread, Cred <= 64
 constexpr int kTaps = 7;
+constexpr int kUmMaxCred = 512;              // reduction channels per call (passes of <= 64)
 
 struct UmmaParams {
   int N, Cred, Nout, Hi, Wi, Ho, Wo;
@@ -48,6 +49,8 @@ struct UmmaParams {
   int pad;                       // frame of pad_value around the input; literal zero beyond
   float pad_value;
   int relu, has_bias, transpose_w;   // transpose_w: weights indexed [red][out] (dgrad)
+  int cred_total, c_off, accumulate; // reduction channels > 64 run as passes of <= 64: this pass covers channels
+                                     // [c_off, c_off + Cred) of cred_total and (accumulate) adds to the output of the previous pass
   int slots, bands, ctiles;
   int rstages, raw_bytes;        // TMA variant: raw staging ring
   long long items;
@@ -55,6 +58,8 @@ struct UmmaParams {
 
 template <typename T> __device__ __forceinline__ float ld_in(const T* p) { return __ldg(p); }
 template <> __device__ __forceinline__ float ld_in<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(__ldg(p)); }
+template <typename T> __device__ __forceinline__ float ld_out(const T* p) { return *p; }
+template <> __device__ __forceinline__ float ld_out<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 template <typename T> __device__ __forceinline__ void st_out(T* p, float v) { __stcs(p, v); }
 template <> __device__ __forceinline__ void st_out<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
@@ -93,9 +98,9 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
       const int k = e / per_tap, r = e - k * per_tap;
       const int kc = r / (P.Nout * 8), r2 = r - kc * P.Nout * 8;
       const int n = r2 >> 3, j = r2 & 7;
-      const int red = kc * 8 + j;
-      const float v = P.transpose_w ? __ldg(w + ((size_t)red * P.Nout + n) * kTaps + k)      // w[co=red][ci=n][k]
-                                    : __ldg(w + ((size_t)n * P.Cred + red) * kTaps + k);     // w[co=n][ci=red][k]
+      const int red = P.c_off + kc * 8 + j;
+      const float v = P.transpose_w ? __ldg(w + ((size_t)red * P.Nout + n) * kTaps + k)          // w[co=red][ci=n][k]
+                                    : __ldg(w + ((size_t)n * P.cred_total + red) * kTaps + k);   // w[co=n][ci=red][k]
       reinterpret_cast<__nv_bfloat16*>(w_smem)[e] = __float2bfloat16_rn(v);
     }
     for (int e = tid; e < ((P.Nout + 31) & ~31); e += kUmThreads) bias_s[e] = (P.has_bias && e < P.Nout) ? __ldg(bias + e) : 0.f;
@@ -127,7 +132,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
       const int rem = (int)(item - (long long)n * per_n);
       const int band = rem / P.ctiles, ct = rem - band * P.ctiles;
       const int r0 = band * kUmBand, rows = min(kUmBand, P.Ho - r0), c0 = ct * kUmTile;
-      const TIN* __restrict__ in_n = in + (size_t)n * P.Cred * plane;
+      const TIN* __restrict__ in_n = in + ((size_t)n * P.cred_total + P.c_off) * plane;
       for (int t = 0; t < rows + 2; ++t, ++lt) {
         const int slot = (int)(lt % P.slots);
         const uint32_t use = (uint32_t)(lt / P.slots);
@@ -224,6 +229,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 float f = __uint_as_float(v[j]) + bf[j];
+                if (P.accumulate) f += ld_out(op);
                 if (P.relu) f = fmaxf(f, 0.f);
                 st_out(op, f);
                 op += cstride;
@@ -232,6 +238,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 float f = __uint_as_float(v[j]) + bf[j];
+                if (P.accumulate) f += ld_out(op);
                 if (P.relu) f = fmaxf(f, 0.f);
                 st_out(op, f);
                 op += cstride;
@@ -314,7 +321,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
           const int rs = (int)(rt % P.rstages);
           ptx::mbar_wait(&rempty[rs], (uint32_t)(((rt / P.rstages) & 1) ^ 1));
           ptx::mbar_arrive_expect_tx(&rfull[rs], (uint32_t)P.raw_bytes);
-          ptx::tma_load_4d(raw + (size_t)rs * P.raw_bytes, &tmap, &rfull[rs], c0 + P.col0, r0 + P.row0 + t, 0, n);
+          ptx::tma_load_4d(raw + (size_t)rs * P.raw_bytes, &tmap, &rfull[rs], c0 + P.col0, r0 + P.row0 + t, P.c_off, n);
         }
       }
     }
@@ -371,14 +378,14 @@ bool conv_umma_eligible(const hg_conv_desc* d, int op) {
   if (op == 2) return conv_wgrad_umma_eligible(d);
   if (d->radius != 2 || d->stride != 1 || d->dilation != 1 || d->groups != 1) return false;
   const int64_t Cred = op == 0 ? d->Cin : d->Cout, Nout = op == 0 ? d->Cout : d->Cin;
-  if (Cred % 16 != 0 || Cred < 16 || Cred > 64) return false;
+  if (Cred % 16 != 0 || Cred < 16 || Cred > kUmMaxCred) return false;      // > 64: passes of <= 64 channels
   if (Nout % 16 != 0 || Nout < 16 || Nout > 256) return false;
   if (op == 1 && d->relu) return false;
   // auto: bf16 activations only (fp32 callers keep fp32 accuracy on the direct stencil) and only when the
   // channel contraction is dense enough to feed a 128 x Nout x Cred tile
   if (d->algo == 0 && ((op == 0 ? d->x_dtype : d->y_dtype) != HG_BF16 || Cred * Nout < 32 * 32)) return false;
   int slots, rst, rb;
-  umma_pick_stages((int)Cred, (int)Nout, 4, false, slots, rst, rb);
+  umma_pick_stages((int)(Cred > 64 ? 64 : Cred), (int)Nout, 4, false, slots, rst, rb);
   return slots > 0;
 }
 
@@ -418,8 +425,8 @@ static int launch_umma_any(const void* in, const float* w, const float* bias, vo
       for (int par = 0; par < 2; ++par) for (int k = 0; k < kTaps; ++k) smax = max(smax, P.sh[par][k] + e0);
       if (kUmTile + smax > kUmPW) tma = false;
       else {
-        const cuuint64_t gdim[4] = {(cuuint64_t)P.Wi, (cuuint64_t)P.Hi, (cuuint64_t)P.Cred, (cuuint64_t)P.N};
-        const cuuint64_t gstr[3] = {(cuuint64_t)P.Wi * es, (cuuint64_t)P.Wi * P.Hi * es, (cuuint64_t)P.Wi * P.Hi * P.Cred * es};
+        const cuuint64_t gdim[4] = {(cuuint64_t)P.Wi, (cuuint64_t)P.Hi, (cuuint64_t)P.cred_total, (cuuint64_t)P.N};
+        const cuuint64_t gstr[3] = {(cuuint64_t)P.Wi * es, (cuuint64_t)P.Wi * P.Hi * es, (cuuint64_t)P.Wi * P.Hi * P.cred_total * es};
         const cuuint32_t box[4] = {(cuuint32_t)kUmPW, 1, (cuuint32_t)P.Cred, 1};
         const cuuint32_t estr[4] = {1, 1, 1, 1};
         const CUtensorMapDataType dt = es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -442,14 +449,32 @@ static int launch_umma_any(const void* in, const float* w, const float* bias, vo
   return launch_umma<TIN, TOUT, false>(tmap, in, w, bias, out, P, st);
 }
 
-static int dispatch_umma(int in_dt, int out_dt, const void* in, const float* w, const float* bias, void* out, const UmmaParams& P,
-                         cudaStream_t st) {
+static int dispatch_umma_pass(int in_dt, int out_dt, const void* in, const float* w, const float* bias, void* out, const UmmaParams& P,
+                              cudaStream_t st) {
   if (in_dt == HG_F32 && out_dt == HG_F32) return launch_umma_any<float, float>(in, w, bias, out, P, st);
   if (in_dt == HG_BF16 && out_dt == HG_F32) return launch_umma_any<__nv_bfloat16, float>(in, w, bias, out, P, st);
   if (in_dt == HG_F32 && out_dt == HG_BF16) return launch_umma_any<float, __nv_bfloat16>(in, w, bias, out, P, st);
   if (in_dt == HG_BF16 && out_dt == HG_BF16) return launch_umma_any<__nv_bfloat16, __nv_bfloat16>(in, w, bias, out, P, st);
   set_error("hexconv_umma: unsupported dtypes in=%d out=%d", in_dt, out_dt);
   return HG_E_DTYPE;
+}
+
+// Reduction channels beyond 64 do not fit the shared-memory budget (7 weight taps + the input-row ring) of one
+// CTA: they run as successive passes over channel slices of <= 64, every pass after the first adding to the
+// output of the previous one in the epilogue (bias in the first pass, ReLU in the last).
+static int dispatch_umma(int in_dt, int out_dt, const void* in, const float* w, const float* bias, void* out, UmmaParams P, cudaStream_t st) {
+  const int total = P.Cred, relu = P.relu, has_bias = P.has_bias;
+  P.cred_total = total;
+  for (int c0 = 0; c0 < total; c0 += 64) {
+    P.c_off = c0;
+    P.Cred = total - c0 < 64 ? total - c0 : 64;
+    P.accumulate = c0 > 0;
+    P.has_bias = has_bias && c0 == 0;
+    P.relu = relu && c0 + 64 >= total;
+    int rc = dispatch_umma_pass(in_dt, out_dt, in, w, P.has_bias ? bias : nullptr, out, P, st);
+    if (rc) return rc;
+  }
+  return HG_OK;
 }
 
 static void umma_common(UmmaParams& P, int Ho, int Wo, int N) {

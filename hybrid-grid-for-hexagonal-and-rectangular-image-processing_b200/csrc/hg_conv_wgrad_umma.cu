@@ -45,6 +45,7 @@ struct WgParams {
   float pad_value;
   int xslots, gslots, bands, ctiles, has_bias;
   int rstages, raw_bytes;        // TMA variant
+  int cin_total, ci_off, cout_total, co_off;   // this launch covers x channels [ci_off, ci_off + Cin) and gy channels [co_off, co_off + Cout)
   long long items;
 };
 
@@ -228,8 +229,8 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
       const int rem = (int)(item - (long long)n * per_n);
       const int band = rem / P.ctiles, ct = rem - band * P.ctiles;
       const int r0 = band * kWuBand, rows = min(kWuBand, P.Ho - r0), c0 = ct * kWuTile;
-      const TX* __restrict__ xn = x + (size_t)n * P.Cin * xplane;
-      const TG* __restrict__ gn = gy + (size_t)n * P.Cout * gplane;
+      const TX* __restrict__ xn = x + ((size_t)n * P.cin_total + P.ci_off) * xplane;
+      const TG* __restrict__ gn = gy + ((size_t)n * P.cout_total + P.co_off) * gplane;
       load_x(xn, r0 + P.row0 + 0, c0);
       load_x(xn, r0 + P.row0 + 1, c0);
       for (int rr = 0; rr < rows; ++rr) {
@@ -251,7 +252,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
           if (co < P.Cout) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (cb + j < P.Cin) atomicAdd(gw + ((size_t)co * P.Cin + cb + j) * kWuTaps + k, __uint_as_float(v[j]));
+              if (cb + j < P.Cin) atomicAdd(gw + ((size_t)(P.co_off + co) * P.cin_total + P.ci_off + cb + j) * kWuTaps + k, __uint_as_float(v[j]));
           }
         }
       }
@@ -259,7 +260,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
         uint32_t v[32];
         ptx::tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)bias_col, v);
         ptx::tmem_ld_wait();
-        if (co < P.Cout) atomicAdd(gb + co, __uint_as_float(v[0]));
+        if (co < P.Cout) atomicAdd(gb + P.co_off + co, __uint_as_float(v[0]));
       }
     }
   } else if (warp == 12) {
@@ -333,10 +334,10 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
     // ===== TMA producer (warp 13, one lane): same row order as the converters =================================
     if (lane == 0) {
       uint32_t rs = 0, rph = 0;
-      auto push = [&](const CUtensorMap* m, uint32_t bytes, int c, int r, int n) {
+      auto push = [&](const CUtensorMap* m, uint32_t bytes, int c, int r, int ch, int n) {
         ptx::mbar_wait(&rempty[rs], rph ^ 1);
         ptx::mbar_arrive_expect_tx(&rfull[rs], bytes);
-        ptx::tma_load_4d(raw + (size_t)rs * P.raw_bytes, m, &rfull[rs], c, r, 0, n);
+        ptx::tma_load_4d(raw + (size_t)rs * P.raw_bytes, m, &rfull[rs], c, r, ch, n);
         if (++rs == (uint32_t)P.rstages) { rs = 0; rph ^= 1; }
       };
       const uint32_t xbytes = (uint32_t)(P.Cin * kWuPW * (int)sizeof(TX)), gbytes = (uint32_t)(P.Cout * kWuTile * (int)sizeof(TG));
@@ -345,11 +346,11 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
         const int rem = (int)(item - (long long)n * per_n);
         const int band = rem / P.ctiles, ct = rem - band * P.ctiles;
         const int r0 = band * kWuBand, rows = min(kWuBand, P.Ho - r0), c0 = ct * kWuTile;
-        push(&xmap, xbytes, c0 + P.col0, r0 + P.row0 + 0, n);
-        push(&xmap, xbytes, c0 + P.col0, r0 + P.row0 + 1, n);
+        push(&xmap, xbytes, c0 + P.col0, r0 + P.row0 + 0, P.ci_off, n);
+        push(&xmap, xbytes, c0 + P.col0, r0 + P.row0 + 1, P.ci_off, n);
         for (int rr = 0; rr < rows; ++rr) {
-          push(&xmap, xbytes, c0 + P.col0, r0 + P.row0 + rr + 2, n);
-          push(&gmap, gbytes, c0, r0 + rr, n);
+          push(&xmap, xbytes, c0 + P.col0, r0 + P.row0 + rr + 2, P.ci_off, n);
+          push(&gmap, gbytes, c0, r0 + rr, P.co_off, n);
         }
       }
     }
@@ -408,10 +409,14 @@ static bool wu_pick(int Cin, int Cout, int xes, int ges, bool tma, int& xslots, 
 
 bool conv_wgrad_umma_eligible(const hg_conv_desc* d) {
   if (d->radius != 2 || d->stride != 1 || d->dilation != 1 || d->groups != 1) return false;
-  if (d->Cin % 16 != 0 || d->Cin < 16 || d->Cin > 64) return false;        // 7*Cin + 16 TMEM columns <= 512
-  if (d->Cout % 8 != 0 || d->Cout < 8 || d->Cout > 128) return false;      // UMMA M = 128 rows of 8-channel groups
+  // one launch covers <= 64 input channels (7*Cin + 16 TMEM columns <= 512) x <= 128 output channels (UMMA M);
+  // larger layers run as a grid of launches over channel slices (independent blocks of gw)
+  if (d->Cin % 16 != 0 || d->Cin < 16 || d->Cin > 1024) return false;
+  if (d->Cout % 8 != 0 || d->Cout < 8 || d->Cout > 1024) return false;
   int a, b, c, e;
-  if (!wu_pick((int)d->Cin, (int)d->Cout, 4, 4, false, a, b, c, e)) return false;
+  if (!wu_pick((int)(d->Cin > 64 ? 64 : d->Cin), (int)(d->Cout > 128 ? 128 : d->Cout), 4, 4, false, a, b, c, e)) return false;
+  if (d->Cin > 64 && d->Cin % 64 != 0 && !wu_pick((int)(d->Cin % 64), (int)(d->Cout > 128 ? 128 : d->Cout), 4, 4, false, a, b, c, e)) return false;
+  if (d->Cout > 128 && d->Cout % 128 != 0 && !wu_pick((int)(d->Cin > 64 ? 64 : d->Cin), (int)(d->Cout % 128), 4, 4, false, a, b, c, e)) return false;
   if (d->algo == 0 && (d->x_dtype != HG_BF16 || d->Cin * d->Cout < 32 * 32)) return false;
   return true;
 }
@@ -431,11 +436,11 @@ static int launch_wu(const CUtensorMap& xmap, const CUtensorMap& gmap, const voi
 }
 
 template <typename T>
-static bool wu_encode(PFN_encodeTiled enc, CUtensorMap* m, const void* base, int Wd, int Hd, int Cd, int Nd, int box_w) {
+static bool wu_encode(PFN_encodeTiled enc, CUtensorMap* m, const void* base, int Wd, int Hd, int Cd, int Nd, int box_w, int box_c) {
   constexpr int es = (int)sizeof(T);
   const cuuint64_t gdim[4] = {(cuuint64_t)Wd, (cuuint64_t)Hd, (cuuint64_t)Cd, (cuuint64_t)Nd};
   const cuuint64_t gstr[3] = {(cuuint64_t)Wd * es, (cuuint64_t)Wd * Hd * es, (cuuint64_t)Wd * Hd * Cd * es};
-  const cuuint32_t box[4] = {(cuuint32_t)box_w, 1, (cuuint32_t)Cd, 1};
+  const cuuint32_t box[4] = {(cuuint32_t)box_w, 1, (cuuint32_t)box_c, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUtensorMapDataType dt = es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   return enc(m, dt, 4, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -458,8 +463,8 @@ static int launch_wu_any(const void* x, const void* gy, float* gw, float* gb, Wg
       const int col0a = (int)(floor((double)P.col0 / A)) * A, e0 = P.col0 - col0a;
       int smax = 0;
       for (int par = 0; par < 2; ++par) for (int k = 0; k < kWuTaps; ++k) smax = max(smax, P.sh[par][k] + e0);
-      if (kWuTile + smax > kWuPW || !wu_encode<TX>(enc, &xmap, x, P.W, P.H, P.Cin, P.N, kWuPW) ||
-          !wu_encode<TG>(enc, &gmap, gy, P.Wo, P.Ho, P.Cout, P.N, kWuTile))
+      if (kWuTile + smax > kWuPW || !wu_encode<TX>(enc, &xmap, x, P.W, P.H, P.cin_total, P.N, kWuPW, P.Cin) ||
+          !wu_encode<TG>(enc, &gmap, gy, P.Wo, P.Ho, P.cout_total, P.N, kWuTile, P.Cout))
         tma = false;
       else {
         P.col0 = col0a;
@@ -494,12 +499,23 @@ int conv_wgrad_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp
   P.ctiles = (int)ceil_div(g.Wo, kWuTile);
   P.items = (long long)g.N * P.bands * P.ctiles;
   const int xdt = d->x_dtype, gdt = d->y_dtype;
-  if (xdt == HG_F32 && gdt == HG_F32) return launch_wu_any<float, float>(x, gy, gw, gbias, P, st);
-  if (xdt == HG_BF16 && gdt == HG_F32) return launch_wu_any<__nv_bfloat16, float>(x, gy, gw, gbias, P, st);
-  if (xdt == HG_F32 && gdt == HG_BF16) return launch_wu_any<float, __nv_bfloat16>(x, gy, gw, gbias, P, st);
-  if (xdt == HG_BF16 && gdt == HG_BF16) return launch_wu_any<__nv_bfloat16, __nv_bfloat16>(x, gy, gw, gbias, P, st);
-  set_error("hexconv_wgrad_umma: unsupported dtypes x=%d gy=%d", xdt, gdt);
-  return HG_E_DTYPE;
+  P.cin_total = g.Cin; P.cout_total = g.Cout;
+  for (int co0 = 0; co0 < g.Cout; co0 += 128) {
+    for (int ci0 = 0; ci0 < g.Cin; ci0 += 64) {
+      P.co_off = co0; P.Cout = g.Cout - co0 < 128 ? g.Cout - co0 : 128;
+      P.ci_off = ci0; P.Cin = g.Cin - ci0 < 64 ? g.Cin - ci0 : 64;
+      P.has_bias = gbias != nullptr && ci0 == 0;
+      float* gb = P.has_bias ? gbias : nullptr;
+      int rc;
+      if (xdt == HG_F32 && gdt == HG_F32) rc = launch_wu_any<float, float>(x, gy, gw, gb, P, st);
+      else if (xdt == HG_BF16 && gdt == HG_F32) rc = launch_wu_any<__nv_bfloat16, float>(x, gy, gw, gb, P, st);
+      else if (xdt == HG_F32 && gdt == HG_BF16) rc = launch_wu_any<float, __nv_bfloat16>(x, gy, gw, gb, P, st);
+      else if (xdt == HG_BF16 && gdt == HG_BF16) rc = launch_wu_any<__nv_bfloat16, __nv_bfloat16>(x, gy, gw, gb, P, st);
+      else { set_error("hexconv_wgrad_umma: unsupported dtypes x=%d gy=%d", xdt, gdt); return HG_E_DTYPE; }
+      if (rc) return rc;
+    }
+  }
+  return HG_OK;
 }
 
 }  // namespace hg

@@ -280,6 +280,10 @@ def test_reductions_and_converters(hf, hexframes_golden, resample_golden):
     (1, 48, 16, 65, 64, 1, 1, torch.float32),
     (2, 64, 64, 35, 256, 1, 1, torch.bfloat16),
     (1, 32, 64, 34, 264, 2, 0, torch.float32),
+    # more than 64 reduction channels: passes over channel slices (fwd / dgrad) and slice launches (wgrad)
+    (1, 128, 64, 20, 128, 1, 0, torch.float32),
+    (1, 64, 160, 18, 64, 1, 1, torch.float32),
+    (1, 96, 128, 12, 128, 1, 0, torch.bfloat16),
 ])
 @pytest.mark.parametrize("pad_value", [0.0, 0.25])      # 0 -> TMA-staged input path, != 0 -> coalesced-load path
 def test_hexconv_tcgen05_vs_oracle(hf, cfg, pad_value):
