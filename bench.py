@@ -287,7 +287,7 @@ def run_ours(args):
                        "math": math_mode, "out_dtype": "float32", "parallelism": f"image-sharded x{world}, no collective",
                        "l2": "inputs (3.2 GB) and outputs (3.2 GB) exceed the 126 MB L2; no flush needed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(wl), "peak_source": peak_src, "kernel": "rect2hex_bilinear_kernel",
+                         "traffic": ncu_traffic(wl), "peak_source": peak_src, "kernel": "rect2hex_bilinear_ws_kernel" if math_mode == "fast" else "rect2hex_bilinear_tma_kernel",
                          "algorithmic_bytes_per_launch": algorithmic_bytes(wl, n_img), "kernel_ms": kernel_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": hx.numel() * 4, "d2h_bytes_per_step": hy.numel() * 4,
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "api": "hg_host_rect2hex (C ABI, pinned host buffers)",
