@@ -2,10 +2,11 @@
 #include "hg_common.cuh"
 #include "hg_ptx.cuh"
 #include <string.h>
+#include <atomic>
 
 namespace hg {
 static thread_local char g_err[512] = "";
-static thread_local int64_t g_launches = 0;
+static std::atomic<int64_t> g_launches{0};   // process-wide: the autograd engine launches the backward kernels from its own thread
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -41,6 +42,6 @@ PFN_encodeTiled get_encode_tiled() {
 extern "C" {
 int hg_version(void) { return HG_VERSION; }
 const char* hg_last_error(void) { return hg::g_err; }
-int64_t hg_launch_count(void) { return hg::g_launches; }
-void hg_reset_launch_count(void) { hg::g_launches = 0; }
+int64_t hg_launch_count(void) { return hg::g_launches.load(); }
+void hg_reset_launch_count(void) { hg::g_launches.store(0); }
 }

@@ -35,7 +35,9 @@ namespace hg {
 constexpr int kUmTile = 128;                 // output pixels per MMA (UMMA M)
 constexpr int kUmPW = 144;                   // pixels per ring slot: tile + tap shifts (<= 3) + alignment slack (<= 7)
 constexpr int kUmLoaders = 256;
-constexpr int kUmThreads = kUmLoaders + 128 + 32 + 32;
+constexpr int kUmEpiWarps = 8;               // two warps per TMEM lane quadrant, alternating 32-channel chunks
+constexpr int kUmMmaWarp = kUmLoaders / 32 + kUmEpiWarps;
+constexpr int kUmThreads = kUmLoaders + kUmEpiWarps * 32 + 32 + 32;
 constexpr int kUmBand = 32;                  // output rows per work item
 constexpr int kUmMaxQ = 5;                   // ceil(8 * 144 / 256): (chunk, pixel) tasks per loader thread, Cred <= 64
 constexpr int kTaps = 7;
@@ -68,7 +70,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <typename TIN, typename TOUT, bool TMA>
+template <typename TIN, typename TOUT, bool TMA, bool ACC>   // ACC: add to the output of the previous channel-slice pass
 __global__ void __launch_bounds__(kUmThreads, 1)
 hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restrict__ in, const float* __restrict__ w,
                     const float* __restrict__ bias, TOUT* __restrict__ out, UmmaParams P) {
@@ -107,13 +109,13 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
   }
   if (tid == 0) {
     for (int s = 0; s < P.slots; ++s) { ptx::mbar_init(&full[s], kUmLoaders / 32); ptx::mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull[s], 1); ptx::mbar_init(&tempty[s], 128); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull[s], 1); ptx::mbar_init(&tempty[s], kUmEpiWarps * 32); }
     for (int s = 0; s < P.rstages; ++s) { ptx::mbar_init(&rfull[s], 1); ptx::mbar_init(&rempty[s], kUmLoaders / 32); }
     if (TMA) ptx::prefetch_tensormap(&tmap);
     ptx::fence_barrier_init();
   }
   const uint32_t tmem_cols = 2 * P.Nout <= 32 ? 32 : 2 * P.Nout <= 64 ? 64 : 2 * P.Nout <= 128 ? 128 : 2 * P.Nout <= 256 ? 256 : 512;
-  if (warp == 12) { ptx::tmem_alloc(tmem_slot, tmem_cols); ptx::tmem_relinquish(); }
+  if (warp == kUmMmaWarp) { ptx::tmem_alloc(tmem_slot, tmem_cols); ptx::tmem_relinquish(); }
   ptx::fence_proxy_async_smem();            // weight image written by the generic proxy, read by tcgen05.mma
   ptx::tc_fence_before_sync();
   __syncthreads();
@@ -137,7 +139,12 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
         const int slot = (int)(lt % P.slots);
         const uint32_t use = (uint32_t)(lt / P.slots);
         unsigned char* sb = ring + (size_t)slot * slot_bytes;
-        float v[kUmMaxQ][8];
+        uint4 pk[kUmMaxQ];                   // 8 channels of one pixel, packed to bf16 as soon as they are loaded
+        auto pack8 = [](const float (&v)[8]) {
+          uint4 r;
+          r.x = pack_bf16(v[0], v[1]); r.y = pack_bf16(v[2], v[3]); r.z = pack_bf16(v[4], v[5]); r.w = pack_bf16(v[6], v[7]);
+          return r;
+        };
         if (TMA) {
           // raw row [Cred][PW] landed by TMA (halo rows / columns already zero-filled) -> registers
           const int rs = (int)(lt % P.rstages);
@@ -148,8 +155,10 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
             const int task = tid + q * kUmLoaders;
             if (task < ntasks) {
               const int kc = task / kUmPW, p = task - kc * kUmPW;
+              float v[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[q][e] = to_f32(rp[(kc * 8 + e) * kUmPW + p]);
+              for (int e = 0; e < 8; ++e) v[e] = to_f32(rp[(kc * 8 + e) * kUmPW + p]);
+              pk[q] = pack8(v);
             }
           }
           // generic-proxy reads of the stage -> TMA (async proxy) refill: proxy fence before the release (the
@@ -172,29 +181,30 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
               const bool col_in = j >= 0 && j < P.Wi;
               const float fill = (row_frame && j >= -P.pad && j < P.Wi + P.pad) ? P.pad_value : 0.f;
               const TIN* __restrict__ src = in_n + (size_t)(kc * 8) * plane + (size_t)i * P.Wi + j;
+              float v[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[q][e] = (row_in && col_in) ? ld_in(src + (size_t)e * plane) : fill;
+              for (int e = 0; e < 8; ++e) v[e] = (row_in && col_in) ? ld_in(src + (size_t)e * plane) : fill;
+              pk[q] = pack8(v);
             }
           }
         }
 #pragma unroll
         for (int q = 0; q < kUmMaxQ; ++q) {
           const int task = tid + q * kUmLoaders;
-          if (task < ntasks) {
-            uint4 pk;
-            pk.x = pack_bf16(v[q][0], v[q][1]); pk.y = pack_bf16(v[q][2], v[q][3]);
-            pk.z = pack_bf16(v[q][4], v[q][5]); pk.w = pack_bf16(v[q][6], v[q][7]);
-            *reinterpret_cast<uint4*>(sb + (size_t)task * 16) = pk;      // task == kc * PW + p
-          }
+          if (task < ntasks) *reinterpret_cast<uint4*>(sb + (size_t)task * 16) = pk[q];      // task == kc * PW + p
         }
         ptx::fence_proxy_async_smem();       // generic-proxy smem writes -> visible to tcgen05.mma
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&full[slot]);    // one arrival per converter warp
       }
     }
-  } else if (warp < 12) {
+  } else if (warp < kUmMmaWarp) {
     // ===== epilogue ========================================================================================
+    // ncu r1t: with 4 epilogue warps the MMA warp spent ~39 polls per row waiting for a free accumulator --
+    // the epilogue (64 strided channel-plane stores per thread and row) paced the whole pipeline.  8 warps:
+    // quadrant q4 is shared by warps q4 and q4 + 4, which take the even / odd 32-channel chunks.
     const int q4 = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int half = (warp - kUmLoaders / 32) >> 2;
     const int px = q4 * 32 + lane;
     const size_t cstride = (size_t)P.Ho * P.Wo;
     uint32_t acc = 0, acc_phase = 0;
@@ -207,8 +217,14 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
       for (int rr = 0; rr < rows; ++rr, orow += P.Wo) {
         ptx::mbar_wait(&tfull[acc], acc_phase);
         ptx::tc_fence_after_sync();
-        TOUT* __restrict__ op = orow;
-        for (int cb = 0; cb < P.Nout; cb += 32) {
+        const int last_cb = ((P.Nout - 1) >> 5) << 5;                      // first channel of the last chunk
+        const int my_last = ((last_cb >> 5) & 1) == half ? last_cb : last_cb - 32;   // last chunk this warp owns (< 0: none)
+        if (my_last < 0) {                   // Nout <= 32: the odd warps have no chunk, they only release the accumulator
+          ptx::tc_fence_before_sync();
+          ptx::mbar_arrive(&tempty[acc]);
+        }
+        for (int cb = half * 32; cb < P.Nout; cb += 64) {
+          TOUT* __restrict__ op = orow + (size_t)cb * cstride;
           uint32_t v[32];
           ptx::tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * (uint32_t)P.Nout + (uint32_t)cb, v);
           // bias of this chunk in registers (8 vector LDS in flight together with the TMEM load) -- a scalar
@@ -217,8 +233,8 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
 #pragma unroll
           for (int i = 0; i < 8; ++i) bb[i] = *reinterpret_cast<const float4*>(bias_s + cb + 4 * i);
           ptx::tmem_ld_wait();
-          const bool last = cb + 32 >= P.Nout;
-          if (last) {                        // accumulator fully read: hand it back to the MMA warp
+          const bool last = cb == my_last;
+          if (last) {                        // this warp's part of the accumulator is in registers: hand it back
             ptx::tc_fence_before_sync();
             ptx::mbar_arrive(&tempty[acc]);
           }
@@ -229,7 +245,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 float f = __uint_as_float(v[j]) + bf[j];
-                if (P.accumulate) f += ld_out(op);
+                if (ACC) f += ld_out(op);
                 if (P.relu) f = fmaxf(f, 0.f);
                 st_out(op, f);
                 op += cstride;
@@ -238,7 +254,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 float f = __uint_as_float(v[j]) + bf[j];
-                if (P.accumulate) f += ld_out(op);
+                if (ACC) f += ld_out(op);
                 if (P.relu) f = fmaxf(f, 0.f);
                 st_out(op, f);
                 op += cstride;
@@ -249,7 +265,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp == 12) {
+  } else if (warp == kUmMmaWarp) {
     // ===== MMA issuer ======================================================================================
     // Single-lane issue loop: everything that does not change per instruction is hoisted -- ring slots and
     // mbarrier parities advance incrementally (no 64-bit division), descriptors are built from a constant
@@ -276,29 +292,29 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
         ptx::mbar_wait(&full[s2], p2);
         ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
         ptx::tc_fence_after_sync();
-        {
+        if (ptx::elect_one()) {                // single-thread region: descriptors travel R -> UR once per MMA
           const int par = (r0 + rr) & 1;
           const uint32_t d_tmem = tmem_base + acc * (uint32_t)P.Nout;
           const uint32_t rb0 = (ring_addr + slot0 * (uint32_t)slot_bytes) >> 4;
           const uint32_t rb1 = (ring_addr + s1 * (uint32_t)slot_bytes) >> 4;
           const uint32_t rb2 = (ring_addr + s2 * (uint32_t)slot_bytes) >> 4;
           uint32_t accum = 0;
+          uint32_t b_lo = (w_addr >> 4) + b_lo_const;            // taps are contiguous: one running weight descriptor
 #pragma unroll
           for (int k = 0; k < kTaps; ++k) {
             const int ra = P.ra[k];
             uint32_t a_lo = (ra == 0 ? rb0 : (ra == 1 ? rb1 : rb2)) + (uint32_t)P.sh[par][k] + a_lo_const;
-            uint32_t b_lo = ((w_addr + (uint32_t)k * (uint32_t)wtap_bytes) >> 4) + b_lo_const;
             for (int j = 0; j < ksteps; ++j) {
-              ptx::umma_bf16_elect(d_tmem, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, accum);
+              ptx::umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, accum);
               accum = 1;
               a_lo += a_step; b_lo += b_step;
             }
           }
-          ptx::umma_commit_elect(&tfull[acc]);                   // accumulator ready for the epilogue
-          ptx::umma_commit_elect(&empty[slot0]);                 // input row rr is not needed any more
+          ptx::umma_commit(&tfull[acc]);                         // accumulator ready for the epilogue
+          ptx::umma_commit(&empty[slot0]);                       // input row rr is not needed any more
           if (rr == rows - 1) {                                  // band done: release its two trailing rows too
-            ptx::umma_commit_elect(&empty[s1]);
-            ptx::umma_commit_elect(&empty[s2]);
+            ptx::umma_commit(&empty[s1]);
+            ptx::umma_commit(&empty[s2]);
           }
         }
         __syncwarp();
@@ -330,7 +346,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
   // ---- teardown ---------------------------------------------------------------------------------------------
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 12) {
+  if (warp == kUmMmaWarp) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -391,11 +407,11 @@ bool conv_umma_eligible(const hg_conv_desc* d, int op) {
 
 static bool g_um_no_tma = [] { const char* e = getenv("HG_CONV_NO_TMA"); return e && e[0] == '1'; }();
 
-template <typename TIN, typename TOUT, bool TMA>
-static int launch_umma(const CUtensorMap& tmap, const void* in, const float* w, const float* bias, void* out, const UmmaParams& P,
-                       cudaStream_t st) {
+template <typename TIN, typename TOUT, bool TMA, bool ACC>
+static int launch_umma_acc(const CUtensorMap& tmap, const void* in, const float* w, const float* bias, void* out, const UmmaParams& P,
+                           cudaStream_t st) {
   const size_t smem = umma_smem_bytes(P.Cred, P.Nout, P.slots, P.rstages, P.raw_bytes);
-  auto kern = hexconv_umma_kernel<TIN, TOUT, TMA>;
+  auto kern = hexconv_umma_kernel<TIN, TOUT, TMA, ACC>;
   static SmemReservation reservation;
   cudaError_t e = reservation.reserve(kern, smem);
   if (e != cudaSuccess) { set_error("hexconv_umma: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e)); return (int)e; }
@@ -403,6 +419,13 @@ static int launch_umma(const CUtensorMap& tmap, const void* in, const float* w, 
   if (grid > P.items) grid = P.items;
   kern<<<(unsigned)grid, kUmThreads, smem, st>>>(tmap, (const TIN*)in, w, bias, (TOUT*)out, P);
   return finish_launch(TMA ? "hexconv_umma_tma" : "hexconv_umma");
+}
+
+template <typename TIN, typename TOUT, bool TMA>
+static int launch_umma(const CUtensorMap& tmap, const void* in, const float* w, const float* bias, void* out, const UmmaParams& P,
+                       cudaStream_t st) {
+  return P.accumulate ? launch_umma_acc<TIN, TOUT, TMA, true>(tmap, in, w, bias, out, P, st)
+                      : launch_umma_acc<TIN, TOUT, TMA, false>(tmap, in, w, bias, out, P, st);
 }
 
 // Completes P (stage counts, column alignment) and launches the TMA variant when the input qualifies.

@@ -287,7 +287,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
         ptx::mbar_wait(&xfull[s2], p2);
         ptx::mbar_wait(&gfull[gs], gphase);
         ptx::tc_fence_after_sync();
-        {
+        if (ptx::elect_one()) {                // single-thread region: descriptors travel R -> UR once per MMA
           const int par = (r0 + rr) & 1;
           const uint32_t a_lo0 = ((g_addr + gs * (uint32_t)gslot_bytes) >> 4) + lo_const;
           const uint32_t xb0 = (x_addr + slot0 * (uint32_t)xslot_bytes) >> 4;
@@ -301,7 +301,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
             const uint32_t d_tmem = tmem_base + (uint32_t)(k * P.Cin);
 #pragma unroll
             for (int j = 0; j < kWuTile / 16; ++j) {
-              ptx::umma_bf16_elect(d_tmem, ((uint64_t)g_hi << 32) | a_lo, ((uint64_t)x_hi << 32) | b_lo, idesc, started | (uint32_t)j);
+              ptx::umma_bf16(d_tmem, ((uint64_t)g_hi << 32) | a_lo, ((uint64_t)x_hi << 32) | b_lo, idesc, started | (uint32_t)j);
               a_lo += 16; b_lo += 16;                       // 16 pixels = 256 bytes
             }
           }
@@ -309,16 +309,16 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
             uint32_t a_lo = a_lo0;
 #pragma unroll
             for (int j = 0; j < kWuTile / 16; ++j) {
-              ptx::umma_bf16_elect(tmem_base + (uint32_t)bias_col, ((uint64_t)g_hi << 32) | a_lo, od, idesc_b, started | (uint32_t)j);
+              ptx::umma_bf16(tmem_base + (uint32_t)bias_col, ((uint64_t)g_hi << 32) | a_lo, od, idesc_b, started | (uint32_t)j);
               a_lo += 16;
             }
           }
           started = 1;
-          ptx::umma_commit_elect(&gempty[gs]);
-          ptx::umma_commit_elect(&xempty[slot0]);
+          ptx::umma_commit(&gempty[gs]);
+          ptx::umma_commit(&xempty[slot0]);
           if (rr == rows - 1) {
-            ptx::umma_commit_elect(&xempty[s1]);
-            ptx::umma_commit_elect(&xempty[s2]);
+            ptx::umma_commit(&xempty[s1]);
+            ptx::umma_commit(&xempty[s2]);
           }
         }
         __syncwarp();
@@ -328,7 +328,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
       next_slot(slot0, phase0);
       next_slot(slot0, phase0);
     }
-    ptx::umma_commit_elect(done);
+    if (ptx::elect_one()) ptx::umma_commit(done);
     __syncwarp();
   } else if (TMA) {
     // ===== TMA producer (warp 13, one lane): same row order as the converters =================================
