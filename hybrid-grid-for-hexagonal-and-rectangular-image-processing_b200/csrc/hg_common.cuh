@@ -35,7 +35,7 @@ struct SmemReservation {
     std::lock_guard<std::mutex> lock(m);
     size_t& have = bytes[dev & 63];
     if (want <= have) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+    cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
     if (e == cudaSuccess) have = want; else cudaGetLastError();
     return e;
   }

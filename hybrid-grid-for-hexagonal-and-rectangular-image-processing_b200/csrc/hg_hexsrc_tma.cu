@@ -12,9 +12,12 @@
 //   * the three lattice points of a sample sit in two source rows at columns j_ax - (i+1)/2 (offset
 //     storage, odd rows shifted right): relative to y_ + (w-0.5)/2 the source column moves by at most
 //     [-1, +1.5], so the box origin depends only on the tile column.
-// Weights are the float32 simplex form (u > v ? (1-u, u-v, v) : (1-v, v-u, u)), i.e. this is
-// the HG_MATH_FAST kernel; HG_MATH_EXACT stays on the direct gather (hg_resample.cu).
+// HG_MATH_FAST: float32 simplex weights (u > v ? (1-u, u-v, v) : (1-v, v-u, u)).
+// HG_MATH_EXACT: the reference's own float64 sub-triangle-area weights and blend order (hg_hexgeom.cuh
+// hex_locate), bit-identical to geometry_np when written as float64 -- ~250 float64 instructions per sample,
+// evaluated once per item and shared by its three planes.
 #include "hg_common.cuh"
+#include "hg_hexgeom.cuh"
 #include "hg_ptx.cuh"
 #include <math.h>
 #include <stdlib.h>
@@ -30,6 +33,7 @@ constexpr int kHsG = 3;                  // planes per item
 
 struct HsTables {
   double y[kHsTW];        // column coordinate
+  double x[kHsTH];        // row coordinate (exact mode)
   double hrow[kHsTH];     // 0.5 * i_
   double u[kHsTH];        // i_f
   int in[kHsTH];          // i_n
@@ -42,11 +46,13 @@ __device__ __forceinline__ int hs_col_origin(double y0, double cj) {
   return c & ~3;
 }
 
-template <typename TD>
-__global__ void __launch_bounds__(kHsThreads)
+template <typename TD, bool EXACT>
+__global__ void __launch_bounds__(kHsThreads, 2)
 hexsrc_linear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __restrict__ dst, const double* __restrict__ xs,
                          const double* __restrict__ ys, int h, int w, int h1, int w1, int planes, int tiles_x, int tiles_y,
-                         long long total_items, long long items_per_cta, int BW, int BH, int stage_bytes, double ci, double cj) {
+                         long long total_items, long long items_per_cta, int BW, int BH, int stage_bytes, double ci, double cj,
+                         double hx, double wy) {
+  using WT = typename std::conditional<EXACT, double, float>::type;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kHsStages * stage_bytes);
   HsTables* tabs = reinterpret_cast<HsTables*>(smem_raw + (size_t)kHsStages * stage_bytes + 64);
@@ -97,6 +103,7 @@ hexsrc_linear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __restric
       if (t == 0) { T.ncols = min(kHsTW, w1 - tx * kHsTW); T.nrows = min(kHsTH, h1 - ty * kHsTH); T.row0 = row0; T.col0 = col0; }
     } else if (t < kHsTW + kHsTH) {
       const int r = t - kHsTW, a = min(ty * kHsTH + r, h1 - 1);
+      T.x[r] = xs[a];
       const double i_ = dadd(xs[a], ci);                 // geometry_np.py:276
       const int in = trunc_i32(i_);
       T.in[r] = in;
@@ -126,7 +133,7 @@ hexsrc_linear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __restric
 
     // geometry of this thread's samples (plane independent)
     int o1[kHsRW][4], oB[kHsRW][4], o4[kHsRW][4];
-    float wa[kHsRW][4], wb[kHsRW][4], wc[kHsRW][4];
+    WT wa[kHsRW][4], wb[kHsRW][4], wc[kHsRW][4];
 #pragma unroll
     for (int r = 0; r < kHsRW; ++r) {
       const int rl = warp * kHsRW + r;
@@ -136,19 +143,27 @@ hexsrc_linear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __restric
       const int kA = (in + 1) / 2, kB = (in + 2) / 2;   // true division then truncation (in >= 0 here)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const double j_ = dadd(dadd(hrow, T.y[lane + 32 * c]), cj);   // :277  (0.5*i_ + y_) + (w-0.5)*0.5
-        const int jn = trunc_i32(j_);
-        const double v = dsub(j_, (double)(float)jn);
-        const bool f = u > v;                                         // :298 up_down_flag
+        int jn; bool f;
+        if (EXACT) {   // the reference's own arithmetic, operation by operation
+          HexSample<double> hs;
+          hex_locate<double, true, false>(T.x[rl], T.y[lane + 32 * c], h, w, hx, wy, ci, cj, hs);
+          jn = hs.j_n; f = hs.flag;
+          wa[r][c] = (WT)hs.wgt[0]; wb[r][c] = (WT)hs.wgt[1]; wc[r][c] = (WT)hs.wgt[2];
+        } else {
+          const double j_ = dadd(dadd(hrow, T.y[lane + 32 * c]), cj);   // :277  (0.5*i_ + y_) + (w-0.5)*0.5
+          jn = trunc_i32(j_);
+          const double v = dsub(j_, (double)(float)jn);
+          f = u > v;                                                    // :298 up_down_flag
+          const float uf = (float)u, vf = (float)v;
+          wa[r][c] = (WT)(f ? 1.f - uf : 1.f - vf);
+          wb[r][c] = (WT)(f ? uf - vf : vf - uf);
+          wc[r][c] = (WT)(f ? vf : uf);
+        }
         const int p1 = roff + jn - kA;                                // P1 (i_n, j_n)
         const int p4 = roff + BW + jn - kB + 1;                       // P4 (i_n+1, j_n+1)
         o1[r][c] = p1;
         oB[r][c] = f ? p4 - 1 : p1 + 1;                               // P2 (i_n+1, j_n) or P3 (i_n, j_n+1)
         o4[r][c] = p4;
-        const float uf = (float)u, vf = (float)v;
-        wa[r][c] = f ? 1.f - uf : 1.f - vf;
-        wb[r][c] = f ? uf - vf : vf - uf;
-        wc[r][c] = f ? vf : uf;
       }
     }
     ptx::mbar_wait(&full[s], parity);
@@ -160,8 +175,13 @@ hexsrc_linear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __restric
         if (r < nrows) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const float o = fmaf(wc[r][c], t[o4[r][c]], fmaf(wb[r][c], t[oB[r][c]], wa[r][c] * t[o1[r][c]]));
-            if (lane + 32 * c < T.ncols) st_stream(dp + (size_t)r * w1 + 32 * c, (TD)o);
+            TD o;
+            if (EXACT)     // geometry_np.py:354  alpha * p1 + beta * p2 + gamma * p3, float64, no contraction
+              o = (TD)dadd(dadd(dmul(wa[r][c], (double)t[o1[r][c]]), dmul(wb[r][c], (double)t[oB[r][c]])),
+                           dmul(wc[r][c], (double)t[o4[r][c]]));
+            else
+              o = (TD)fmaf((float)wc[r][c], t[o4[r][c]], fmaf((float)wb[r][c], t[oB[r][c]], (float)wa[r][c] * t[o1[r][c]]));
+            if (lane + 32 * c < T.ncols) st_stream(dp + (size_t)r * w1 + 32 * c, o);
           }
         }
       }
@@ -180,7 +200,8 @@ static int g_hs_sms = 0;
 // HG_OK launched, 1 not applicable (fall back to the direct gather), else an error code
 int try_hexsrc_linear_tma(const void* src, void* dst, const double* xs, const double* ys, const double* host_xs, const double* host_ys,
                           int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1, int sdt, int ddt, int math, cudaStream_t st) {
-  if (!host_xs || !host_ys || sdt != HG_F32 || ddt != HG_F32 || math != HG_MATH_FAST) return 1;
+  if (!host_xs || !host_ys || sdt != HG_F32) return 1;
+  if (!((ddt == HG_F32) || (ddt == HG_F64 && math == HG_MATH_EXACT))) return 1;
   if ((w * 4) % 16 != 0 || (reinterpret_cast<uintptr_t>(src) & 15) != 0 || planes >= (1ll << 31) || h1 < 1 || w1 < 1) return 1;
   static const bool off = [] { const char* e = getenv("HG_HEXSRC_NO_TMA"); return e && e[0] == '1'; }();
   if (off) return 1;
@@ -224,9 +245,12 @@ int try_hexsrc_linear_tma(const void* src, void* dst, const double* xs, const do
     return 1;
   const int stage_bytes = (int)ceil_div((int64_t)kHsG * BW * BH * 4, 128) * 128;
   const int smem = kHsStages * stage_bytes + 64 + 2 * (int)sizeof(HsTables);
-  auto kern = hexsrc_linear_tma_kernel<float>;
-  static SmemReservation reservation;
-  if (reservation.reserve(kern, (size_t)smem) != cudaSuccess) return 1;
+  const int variant = math == HG_MATH_FAST ? 0 : (ddt == HG_F32 ? 1 : 2);
+  const void* kern = variant == 0 ? (const void*)hexsrc_linear_tma_kernel<float, false>
+                   : variant == 1 ? (const void*)hexsrc_linear_tma_kernel<float, true>
+                                  : (const void*)hexsrc_linear_tma_kernel<double, true>;
+  static SmemReservation reservation[3];
+  if (reservation[variant].reserve(kern, (size_t)smem) != cudaSuccess) return 1;
   if (g_hs_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -241,8 +265,13 @@ int try_hexsrc_linear_tma(const void* src, void* dst, const double* xs, const do
   if (grid > total) grid = total;
   const long long per = (total + grid - 1) / grid;
   grid = (total + per - 1) / per;
-  kern<<<(unsigned)grid, kHsThreads, smem, st>>>(tmap, (float*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, (int)planes, tiles_x,
-                                                  tiles_y, total, per, BW, BH, stage_bytes, ci, cj);
+  const double hx = (h - 1) / 2.0, wy = (w - 0.5) / 2.0;     // python-float expressions of geometry_np.py:326-331
+  if (variant == 0)
+    hexsrc_linear_tma_kernel<float, false><<<(unsigned)grid, kHsThreads, smem, st>>>(tmap, (float*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, (int)planes, tiles_x, tiles_y, total, per, BW, BH, stage_bytes, ci, cj, hx, wy);
+  else if (variant == 1)
+    hexsrc_linear_tma_kernel<float, true><<<(unsigned)grid, kHsThreads, smem, st>>>(tmap, (float*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, (int)planes, tiles_x, tiles_y, total, per, BW, BH, stage_bytes, ci, cj, hx, wy);
+  else
+    hexsrc_linear_tma_kernel<double, true><<<(unsigned)grid, kHsThreads, smem, st>>>(tmap, (double*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, (int)planes, tiles_x, tiles_y, total, per, BW, BH, stage_bytes, ci, cj, hx, wy);
   return finish_launch("hexsrc_linear_tma");
 }
 

@@ -226,6 +226,12 @@ def test_r2_r4_tma_tiles_vs_oracle(Fn, shape, dsize):
     close(Fn.hex_to_rect(cu(img), dsize, "linear", out_dtype=torch.float32, math="fast", twin="np"),
           full(O.hex_to_rect_resample(img, dsize, "linear", twin="np")), 255.0)
     close(Fn.hex_resize(cu(img), ds, "linear", out_dtype=torch.float32, math="fast"), full(O.hexresize(img, ds, "linear")), 255.0)
+    # HG_MATH_EXACT on the same tiles: float64 result bit-identical to the reference, float32 result = its rounding
+    for twin in ("np", "torch"):
+        ref = full(O.hex_to_rect_resample(img, dsize, "linear", twin=twin))
+        same(Fn.hex_to_rect(cu(img), dsize, "linear", twin=twin), ref)
+        same(Fn.hex_to_rect(cu(img), dsize, "linear", out_dtype=torch.float32, twin=twin), ref.astype(np.float32))
+    same(Fn.hex_resize(cu(img), ds, "linear"), full(O.hexresize(img, ds, "linear")))
     # a constant image stays constant wherever all three lattice points are inside (weights sum to one)
     ones = Fn.hex_to_rect(torch.ones(shape, device="cuda"), dsize, "linear", out_dtype=torch.float32, math="fast", twin="np")
     ref1 = full(O.hex_to_rect_resample(np.ones(shape, np.float32), dsize, "linear", twin="np"))
