@@ -97,7 +97,7 @@ def _conv_out_shape(H, W, radius, stride, dilation, pad_):
 
 class _HexConvFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, kernel, bias, meta):
+    def forward(ctx, x, kernel, bias, meta, scale=None):
         radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, relu = meta
         x = nv.require_cuda(x, "input").contiguous()
         w = kernel.detach().float().contiguous()
@@ -107,6 +107,12 @@ class _HexConvFn(torch.autograd.Function):
         Ho, Wo = _conv_out_shape(H, W, radius, stride, dilation, pad_)
         y = torch.empty((N, Cout, Ho, Wo), dtype=y_dtype, device=x.device)
         d = _conv_desc(x, Cout, Ho, Wo, radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, relu)
+        if scale is not None:      # inference-only fused per-channel affine (HexConvModule conv -> BN(eval) -> ReLU); b is the shift
+            sc = scale.detach().float().contiguous()
+            nv.call("hg_hexconv_fwd_affine", C.byref(d), nv.ptr(x), nv.ptr(w), nv.ptr(sc), nv.ptr(b), nv.ptr(y),
+                    nv.stream_ptr(x.device))
+            ctx.mark_non_differentiable(y)
+            return y
         nv.call("hg_hexconv_fwd", C.byref(d), nv.ptr(x), nv.ptr(w), nv.ptr(b), nv.ptr(y), nv.stream_ptr(x.device))
         ctx.save_for_backward(x, w)
         ctx.meta = meta
@@ -140,7 +146,7 @@ class _HexConvFn(torch.autograd.Function):
             gw = gw.to(ctx.param_dtypes[0])
             if gb is not None:
                 gb = gb.to(ctx.param_dtypes[1])
-        return gx, gw, gb, None
+        return gx, gw, gb, None, None
 
 
 def hexconv2d(x: Tensor, kernel: Tensor, bias: Optional[Tensor] = None, even_odd_offset=0, radius=2, stride=1, padding=0,
@@ -231,7 +237,9 @@ class HexConv2d(nn.Module):
             raise TypeError(f"HexConv2d parameters must be float32 (or bfloat16), got {self.kernel.dtype}")
         return input.to(self.kernel.dtype)
 
-    def forward(self, input: Tensor, relu: bool = False) -> Tensor:
+    def forward(self, input: Tensor, relu: bool = False, affine=None) -> Tensor:
+        """``affine=(scale, shift)``: inference-only fused ``act(conv(x) * scale[c] + shift[c])`` (the conv's own bias must
+        already be folded into ``shift``); ``relu=True`` fuses the ReLU.  Neither records anything for backward."""
         self._autocast_tc = False
         input = _as4(self._activation(input))
         algo = 2 if self._autocast_tc else self.algo
@@ -241,6 +249,10 @@ class HexConv2d(nn.Module):
             pad_ = 0
         meta = (self.hexkernel_radius, self.stride, self.dilation, self.groups, pad_, parity,
                 float(self.padding_value or 0), self.out_dtype, algo, bool(relu))
+        if affine is not None:
+            if torch.is_grad_enabled() and (input.requires_grad or self.kernel.requires_grad):
+                raise RuntimeError("the fused affine epilogue is inference-only: call it under torch.no_grad()")
+            return _HexConvFn.apply(input, self.kernel, affine[1], meta, affine[0])
         return _HexConvFn.apply(input, self.kernel, self.bias, meta)
 
     def extra_repr(self):

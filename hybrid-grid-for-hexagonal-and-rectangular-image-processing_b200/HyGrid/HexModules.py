@@ -203,15 +203,47 @@ class HexConvModule(nn.Module):
         rest = [l for l in self.order[idx + 1:] if not (l == 'norm' and not (norm and self.with_norm))]
         return bool(rest) and rest[0] == 'act'
 
+    def _fusable_bn(self, idx, activate, norm):
+        """Inference: conv -> BatchNorm(eval, running statistics) [-> ReLU] collapses into the conv epilogue
+        (hg_hexconv_fwd_affine): returns (scale, shift, relu) or None.  ref: HexModules.py:275-288."""
+        if torch.is_grad_enabled() or self.with_spectral_norm or not isinstance(self.conv, hnn.HexConv2d):
+            return None
+        if not (norm and self.with_norm) or self.order[idx + 1:idx + 2] != ('norm',):
+            return None
+        bn = self.norm
+        if not isinstance(bn, nn.modules.batchnorm._BatchNorm) or bn.training or bn.running_mean is None:
+            return None
+        scale = torch.rsqrt(bn.running_var.float() + bn.eps)
+        if bn.weight is not None:
+            scale = scale * bn.weight.float()
+        shift = -bn.running_mean.float() * scale
+        if bn.bias is not None:
+            shift = shift + bn.bias.float()
+        if self.conv.bias is not None:
+            shift = shift + self.conv.bias.float() * scale
+        tail = self.order[idx + 2:]
+        relu = bool(tail) and tail[0] == 'act' and activate and self.with_activation and type(self.activate) is nn.ReLU
+        return scale, shift, relu
+
     def forward(self, x: torch.Tensor, activate: bool = True, norm: bool = True) -> torch.Tensor:
         fused = False
+        skip_norm = False
         for idx, layer in enumerate(self.order):
             if layer == 'conv':
                 if self.with_explicit_padding:
                     x = self.padding_layer(x)
+                bn = self._fusable_bn(idx, activate, norm)
+                if bn is not None:
+                    scale, shift, fused = bn
+                    skip_norm = True
+                    x = self.conv(x, relu=fused, affine=(scale, shift))
+                    continue
                 fused = self._fusable_relu(idx, x, activate, norm)
                 x = self.conv(x, relu=True) if fused else self.conv(x)
             elif layer == 'norm' and norm and self.with_norm:
+                if skip_norm:
+                    skip_norm = False
+                    continue
                 x = self.norm(x)
             elif layer == 'act' and activate and self.with_activation:
                 if fused:

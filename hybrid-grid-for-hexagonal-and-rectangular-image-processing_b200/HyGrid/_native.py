@@ -63,6 +63,7 @@ _SIGS = {
     "hg_hexconv_out_shape": [_l, _l, _i, _i, _i, _i, C.POINTER(_l), C.POINTER(_l)],
     "hg_hexconv_umma_eligible": [C.POINTER(ConvDesc), _i],
     "hg_hexconv_fwd": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],
+    "hg_hexconv_fwd_affine": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p, _p],
     "hg_hexconv_dgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p],
     "hg_hexconv_wgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],
     "hg_host_rect2hex": [_p, _p, _p, _p, _l, _l, _l, _l, _l, _i, _i, _i, _i, _i],

@@ -4,12 +4,12 @@
 
 namespace hg {
 // hg_conv_direct.cu
-int conv_fwd_direct(const ConvGeom&, const ConvTaps&, const void* x, int xdt, const float* w, const float* bias, void* y, int ydt, cudaStream_t);
+int conv_fwd_direct(const ConvGeom&, const ConvTaps&, const void* x, int xdt, const float* w, const float* scale, const float* bias, void* y, int ydt, cudaStream_t);
 int conv_dgrad_direct(const ConvGeom&, const ConvTaps&, const void* gy, int gdt, const float* w, void* gx, int xdt, cudaStream_t);
 int conv_wgrad_direct(const ConvGeom&, const ConvTaps&, const void* x, int xdt, const void* gy, int gdt, float* gw, float* gbias, cudaStream_t);
 // hg_conv_umma.cu
 bool conv_umma_eligible(const hg_conv_desc* d, int op);
-int conv_fwd_umma(const hg_conv_desc* d, const ConvGeom&, const ConvTaps&, const void* x, const float* w, const float* bias, void* y, cudaStream_t);
+int conv_fwd_umma(const hg_conv_desc* d, const ConvGeom&, const ConvTaps&, const void* x, const float* w, const float* scale, const float* bias, void* y, cudaStream_t);
 int conv_dgrad_umma(const hg_conv_desc* d, const ConvGeom&, const ConvTaps&, const void* gy, const float* w, void* gx, cudaStream_t);
 int conv_wgrad_umma(const hg_conv_desc* d, const ConvGeom&, const ConvTaps&, const void* x, const void* gy, float* gw, float* gbias, cudaStream_t);
 
@@ -76,15 +76,20 @@ int hg_hexconv_umma_eligible(const hg_conv_desc* d, int op) {
   return conv_umma_eligible(&forced, op) ? 1 : 0;
 }
 
-int hg_hexconv_fwd(const hg_conv_desc* d, const void* x, const float* w, const float* bias, void* y, hg_stream_t stream) {
+int hg_hexconv_fwd_affine(const hg_conv_desc* d, const void* x, const float* w, const float* scale, const float* shift, void* y,
+                          hg_stream_t stream) {
   ConvGeom g; ConvTaps tp;
   int rc = make_geom(d, g, tp);
   if (rc) return rc;
   if (g.N == 0) return HG_OK;
   bool umma;
   if ((rc = pick_algo(d, OP_FWD, umma))) return rc;
-  if (umma) return conv_fwd_umma(d, g, tp, x, w, bias, y, as_stream(stream));
-  return conv_fwd_direct(g, tp, x, d->x_dtype, w, bias, y, d->y_dtype, as_stream(stream));
+  if (umma) return conv_fwd_umma(d, g, tp, x, w, scale, shift, y, as_stream(stream));
+  return conv_fwd_direct(g, tp, x, d->x_dtype, w, scale, shift, y, d->y_dtype, as_stream(stream));
+}
+
+int hg_hexconv_fwd(const hg_conv_desc* d, const void* x, const float* w, const float* bias, void* y, hg_stream_t stream) {
+  return hg_hexconv_fwd_affine(d, x, w, nullptr, bias, y, stream);
 }
 
 int hg_hexconv_dgrad(const hg_conv_desc* d, const void* gy, const float* w, void* gx, hg_stream_t stream) {

@@ -30,7 +30,7 @@ template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p,
 // ---------------------------------------------------------------------------------------------------
 template <typename TX, typename TY>
 __global__ void __launch_bounds__(kConvThreads)
-hexconv_fwd_direct(const TX* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, TY* __restrict__ y,
+hexconv_fwd_direct(const TX* __restrict__ x, const float* __restrict__ w, const float* __restrict__ scale, const float* __restrict__ bias, TY* __restrict__ y,
                    ConvGeom g, ConvTaps tp, int ci_chunk) {
   __shared__ __align__(16) float ws[kSmemFloats];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -60,7 +60,7 @@ hexconv_fwd_direct(const TX* __restrict__ x, const float* __restrict__ w, const 
     // ws[(ci*K + k)*CT + c] = w[co0 + c, cb + ci, k]
     for (int e = threadIdx.x; e < cn * K * kCT; e += kConvThreads) {
       const int c = e % kCT, k = (e / kCT) % K, ci = e / (kCT * K);
-      ws[e] = c < co_n ? __ldg(w + ((int64_t)(co0 + c) * g.cin_g + cb + ci) * K + k) : 0.f;
+      ws[e] = c < co_n ? __ldg(w + ((int64_t)(co0 + c) * g.cin_g + cb + ci) * K + k) * (scale ? __ldg(scale + co0 + c) : 1.f) : 0.f;
     }
     __syncthreads();
     if (!row_ok) continue;
@@ -317,15 +317,15 @@ static int red_chunk(int K) {
   return c < 1 ? 1 : c;
 }
 
-int conv_fwd_direct(const ConvGeom& g, const ConvTaps& tp, const void* x, int xdt, const float* w, const float* bias, void* y,
-                    int ydt, cudaStream_t st) {
+int conv_fwd_direct(const ConvGeom& g, const ConvTaps& tp, const void* x, int xdt, const float* w, const float* scale, const float* bias,
+                    void* y, int ydt, cudaStream_t st) {
   const int co_tiles = (g.cout_g + kCT - 1) / kCT;
   dim3 grid((unsigned)ceil_div(g.Wo, 32 * kPix), (unsigned)ceil_div(g.Ho, 8), (unsigned)((int64_t)g.N * co_tiles * g.groups));
   HG_REQUIRE((int64_t)g.N * co_tiles * g.groups <= 65535 && grid.y <= 65535, HG_E_SHAPE, "hexconv_fwd: batch x channel tiles exceed the grid");
   const int ch = red_chunk(tp.K);
 #define HG_CASE(XD, TX, YD, TY)                                                                                             \
   if (xdt == XD && ydt == YD) {                                                                                             \
-    hexconv_fwd_direct<TX, TY><<<grid, kConvThreads, 0, st>>>((const TX*)x, w, bias, (TY*)y, g, tp, ch);                     \
+    hexconv_fwd_direct<TX, TY><<<grid, kConvThreads, 0, st>>>((const TX*)x, w, scale, bias, (TY*)y, g, tp, ch);                     \
     return finish_launch("hexconv_fwd_direct");                                                                             \
   }
   HG_CASE(HG_F32, float, HG_F32, float)

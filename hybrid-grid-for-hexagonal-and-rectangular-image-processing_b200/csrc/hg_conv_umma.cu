@@ -73,7 +73,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 template <typename TIN, typename TOUT, bool TMA, bool ACC>   // ACC: add to the output of the previous channel-slice pass
 __global__ void __launch_bounds__(kUmThreads, 1)
 hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restrict__ in, const float* __restrict__ w,
-                    const float* __restrict__ bias, TOUT* __restrict__ out, UmmaParams P) {
+                    const float* __restrict__ scale, const float* __restrict__ bias, TOUT* __restrict__ out, UmmaParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nkc = P.Cred >> 3;
@@ -103,7 +103,8 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
       const int red = P.c_off + kc * 8 + j;
       const float v = P.transpose_w ? __ldg(w + ((size_t)red * P.Nout + n) * kTaps + k)          // w[co=red][ci=n][k]
                                     : __ldg(w + ((size_t)n * P.cred_total + red) * kTaps + k);   // w[co=n][ci=red][k]
-      reinterpret_cast<__nv_bfloat16*>(w_smem)[e] = __float2bfloat16_rn(v);
+      // per-output-channel scale (BN-inference affine of HexConvModule) folded into the weight image: free at run time
+      reinterpret_cast<__nv_bfloat16*>(w_smem)[e] = __float2bfloat16_rn(scale ? v * __ldg(scale + n) : v);
     }
     for (int e = tid; e < ((P.Nout + 31) & ~31); e += kUmThreads) bias_s[e] = (P.has_bias && e < P.Nout) ? __ldg(bias + e) : 0.f;
   }
@@ -408,8 +409,8 @@ bool conv_umma_eligible(const hg_conv_desc* d, int op) {
 static bool g_um_no_tma = [] { const char* e = getenv("HG_CONV_NO_TMA"); return e && e[0] == '1'; }();
 
 template <typename TIN, typename TOUT, bool TMA, bool ACC>
-static int launch_umma_acc(const CUtensorMap& tmap, const void* in, const float* w, const float* bias, void* out, const UmmaParams& P,
-                           cudaStream_t st) {
+static int launch_umma_acc(const CUtensorMap& tmap, const void* in, const float* w, const float* scale, const float* bias, void* out,
+                           const UmmaParams& P, cudaStream_t st) {
   const size_t smem = umma_smem_bytes(P.Cred, P.Nout, P.slots, P.rstages, P.raw_bytes);
   auto kern = hexconv_umma_kernel<TIN, TOUT, TMA, ACC>;
   static SmemReservation reservation;
@@ -417,20 +418,20 @@ static int launch_umma_acc(const CUtensorMap& tmap, const void* in, const float*
   if (e != cudaSuccess) { set_error("hexconv_umma: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e)); return (int)e; }
   long long grid = g_um_sms > 0 ? g_um_sms : 148;
   if (grid > P.items) grid = P.items;
-  kern<<<(unsigned)grid, kUmThreads, smem, st>>>(tmap, (const TIN*)in, w, bias, (TOUT*)out, P);
+  kern<<<(unsigned)grid, kUmThreads, smem, st>>>(tmap, (const TIN*)in, w, scale, bias, (TOUT*)out, P);
   return finish_launch(TMA ? "hexconv_umma_tma" : "hexconv_umma");
 }
 
 template <typename TIN, typename TOUT, bool TMA>
-static int launch_umma(const CUtensorMap& tmap, const void* in, const float* w, const float* bias, void* out, const UmmaParams& P,
-                       cudaStream_t st) {
-  return P.accumulate ? launch_umma_acc<TIN, TOUT, TMA, true>(tmap, in, w, bias, out, P, st)
-                      : launch_umma_acc<TIN, TOUT, TMA, false>(tmap, in, w, bias, out, P, st);
+static int launch_umma(const CUtensorMap& tmap, const void* in, const float* w, const float* scale, const float* bias, void* out,
+                       const UmmaParams& P, cudaStream_t st) {
+  return P.accumulate ? launch_umma_acc<TIN, TOUT, TMA, true>(tmap, in, w, scale, bias, out, P, st)
+                      : launch_umma_acc<TIN, TOUT, TMA, false>(tmap, in, w, scale, bias, out, P, st);
 }
 
 // Completes P (stage counts, column alignment) and launches the TMA variant when the input qualifies.
 template <typename TIN, typename TOUT>
-static int launch_umma_any(const void* in, const float* w, const float* bias, void* out, UmmaParams P, cudaStream_t st) {
+static int launch_umma_any(const void* in, const float* w, const float* scale, const float* bias, void* out, UmmaParams P, cudaStream_t st) {
   alignas(64) CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   constexpr int es = (int)sizeof(TIN), A = 16 / es;
@@ -460,7 +461,7 @@ static int launch_umma_any(const void* in, const float* w, const float* bias, vo
           P.col0 = col0a;
           for (int par = 0; par < 2; ++par) for (int k = 0; k < kTaps; ++k) P.sh[par][k] += e0;
           P.slots = slots; P.rstages = rst; P.raw_bytes = rb;
-          return launch_umma<TIN, TOUT, true>(tmap, in, w, bias, out, P, st);
+          return launch_umma<TIN, TOUT, true>(tmap, in, w, scale, bias, out, P, st);
         }
       }
     }
@@ -469,15 +470,15 @@ static int launch_umma_any(const void* in, const float* w, const float* bias, vo
   umma_pick_stages(P.Cred, P.Nout, es, false, P.slots, rst, rb);
   P.rstages = 0; P.raw_bytes = 0;
   HG_REQUIRE(P.slots > 0, HG_E_UNSUPPORTED, "hexconv_umma: shared memory does not fit");
-  return launch_umma<TIN, TOUT, false>(tmap, in, w, bias, out, P, st);
+  return launch_umma<TIN, TOUT, false>(tmap, in, w, scale, bias, out, P, st);
 }
 
-static int dispatch_umma_pass(int in_dt, int out_dt, const void* in, const float* w, const float* bias, void* out, const UmmaParams& P,
-                              cudaStream_t st) {
-  if (in_dt == HG_F32 && out_dt == HG_F32) return launch_umma_any<float, float>(in, w, bias, out, P, st);
-  if (in_dt == HG_BF16 && out_dt == HG_F32) return launch_umma_any<__nv_bfloat16, float>(in, w, bias, out, P, st);
-  if (in_dt == HG_F32 && out_dt == HG_BF16) return launch_umma_any<float, __nv_bfloat16>(in, w, bias, out, P, st);
-  if (in_dt == HG_BF16 && out_dt == HG_BF16) return launch_umma_any<__nv_bfloat16, __nv_bfloat16>(in, w, bias, out, P, st);
+static int dispatch_umma_pass(int in_dt, int out_dt, const void* in, const float* w, const float* scale, const float* bias, void* out,
+                              const UmmaParams& P, cudaStream_t st) {
+  if (in_dt == HG_F32 && out_dt == HG_F32) return launch_umma_any<float, float>(in, w, scale, bias, out, P, st);
+  if (in_dt == HG_BF16 && out_dt == HG_F32) return launch_umma_any<__nv_bfloat16, float>(in, w, scale, bias, out, P, st);
+  if (in_dt == HG_F32 && out_dt == HG_BF16) return launch_umma_any<float, __nv_bfloat16>(in, w, scale, bias, out, P, st);
+  if (in_dt == HG_BF16 && out_dt == HG_BF16) return launch_umma_any<__nv_bfloat16, __nv_bfloat16>(in, w, scale, bias, out, P, st);
   set_error("hexconv_umma: unsupported dtypes in=%d out=%d", in_dt, out_dt);
   return HG_E_DTYPE;
 }
@@ -485,7 +486,8 @@ static int dispatch_umma_pass(int in_dt, int out_dt, const void* in, const float
 // Reduction channels beyond 64 do not fit the shared-memory budget (7 weight taps + the input-row ring) of one
 // CTA: they run as successive passes over channel slices of <= 64, every pass after the first adding to the
 // output of the previous one in the epilogue (bias in the first pass, ReLU in the last).
-static int dispatch_umma(int in_dt, int out_dt, const void* in, const float* w, const float* bias, void* out, UmmaParams P, cudaStream_t st) {
+static int dispatch_umma(int in_dt, int out_dt, const void* in, const float* w, const float* scale, const float* bias, void* out, UmmaParams P,
+                         cudaStream_t st) {
   const int total = P.Cred, relu = P.relu, has_bias = P.has_bias;
   P.cred_total = total;
   for (int c0 = 0; c0 < total; c0 += 64) {
@@ -494,7 +496,7 @@ static int dispatch_umma(int in_dt, int out_dt, const void* in, const float* w, 
     P.accumulate = c0 > 0;
     P.has_bias = has_bias && c0 == 0;
     P.relu = relu && c0 + 64 >= total;
-    int rc = dispatch_umma_pass(in_dt, out_dt, in, w, P.has_bias ? bias : nullptr, out, P, st);
+    int rc = dispatch_umma_pass(in_dt, out_dt, in, w, scale, P.has_bias ? bias : nullptr, out, P, st);
     if (rc) return rc;
   }
   return HG_OK;
@@ -507,8 +509,8 @@ static void umma_common(UmmaParams& P, int Ho, int Wo, int N) {
   P.items = (long long)N * P.bands * P.ctiles;
 }
 
-int conv_fwd_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp, const void* x, const float* w, const float* bias,
-                  void* y, cudaStream_t st) {
+int conv_fwd_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp, const void* x, const float* w, const float* scale,
+                  const float* bias, void* y, cudaStream_t st) {
   UmmaParams P{};
   P.Cred = g.Cin; P.Nout = g.Cout; P.Hi = g.H; P.Wi = g.W;
   int cmin = 1 << 30, cmax = -(1 << 30);
@@ -523,7 +525,7 @@ int conv_fwd_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp, 
   P.pad = g.pad; P.pad_value = g.pad_value;
   P.relu = g.relu; P.has_bias = bias != nullptr; P.transpose_w = 0;
   umma_common(P, g.Ho, g.Wo, g.N);
-  return dispatch_umma(d->x_dtype, d->y_dtype, x, w, bias, y, P, st);
+  return dispatch_umma(d->x_dtype, d->y_dtype, x, w, scale, bias, y, P, st);
 }
 
 // gx[n,ci,i,j] = sum_{co,k} w[co,ci,k] * gy[n,co, i + pad - ro[k], j + pad - co[(i + pad - ro[k]) & 1][k]]   (zero outside)
@@ -549,7 +551,7 @@ int conv_dgrad_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp
   P.pad = 0; P.pad_value = 0.f;
   P.relu = 0; P.has_bias = 0; P.transpose_w = 1;
   umma_common(P, g.H, g.W, g.N);
-  return dispatch_umma(d->y_dtype, d->x_dtype, gy, w, nullptr, gx, P, st);
+  return dispatch_umma(d->y_dtype, d->x_dtype, gy, w, nullptr, nullptr, gx, P, st);
 }
 
 }  // namespace hg

@@ -346,21 +346,18 @@ hexpool2x2c_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int8_
       const float f2 = __shfl_sync(0xffffffffu, v[k < 3 ? k + 1 : 3][2], 0), f3 = __shfl_sync(0xffffffffu, v[k < 3 ? k + 1 : 3][3], 0);
       if (lane == 31) { n[2] = f2; n[3] = f3; }
     } else if (lane == 31) { n[2] = edge2; n[3] = edge3; }
+    // even lanes own a window of the even output row (rows 0, 1), odd lanes one of the odd output row (rows 2, 3):
+    // operands are selected first so that all 32 lanes run ONE reduction and one store (no divergent halves)
+    const bool odd = lane & 1;
+    const float a0 = odd ? v[k][2] : v[k][0], a1 = odd ? n[2] : n[0];
+    const float b0 = odd ? v[k][3] : v[k][1], b1 = odd ? n[3] : n[1];
+    const int J = (col - (odd ? 1 : 0)) >> 1;
     float o; int a;
-    if ((lane & 1) == 0) {                                // even output row: window starts at this (even) column
-      const int J = col >> 1;
-      if (J < wn) {
-        pool4<METHOD>(v[k][0], n[0], v[k][1], n[1], o, a);
-        __stcs(y + yb + J, o);
-        if (aux) aux[yb + J] = (int8_t)a;
-      }
-    } else if (has_odd) {                                 // odd output row: window starts at this (odd) column
-      const int J = (col - 1) >> 1;
-      if (J < wn) {
-        pool4<METHOD>(v[k][2], n[2], v[k][3], n[3], o, a);
-        __stcs(y + yb + wn + J, o);
-        if (aux) aux[yb + wn + J] = (int8_t)a;
-      }
+    pool4<METHOD>(a0, a1, b0, b1, o, a);
+    if (J < wn && (!odd || has_odd)) {
+      const size_t t = yb + (odd ? wn : 0) + J;
+      __stcs(y + t, o);
+      if (aux) aux[t] = (int8_t)a;
     }
   }
 }

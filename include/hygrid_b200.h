@@ -193,12 +193,20 @@ typedef struct hg_conv_desc {
 int hg_hexconv_out_shape(int64_t H, int64_t W, int radius, int stride, int dilation, int pad,
                          int64_t* Ho, int64_t* Wo);
 /* 1 when the tcgen05 / TMEM implicit-GEMM kernel covers this configuration for op (0 forward, 1 data
- * gradient, 2 weight gradient): radius 2, stride 1, dilation 1, groups 1, reduction channels in
- * {16,32,48,64}, output channels a multiple of 16 up to 256.  algo = 0 picks it by itself only for
+ * gradient, 2 weight gradient): radius 2, stride 1, dilation 1, groups 1, channels in multiples of 16
+ * (reduction channels beyond 64 run as passes over 64-channel slices; forward / data-gradient output channels
+ * up to 256 as far as the weight image fits shared memory).  algo = 0 picks it by itself only for
  * bfloat16 activations (it rounds activations and weights to bfloat16, fp32 accumulation). */
 int hg_hexconv_umma_eligible(const hg_conv_desc* d, int op);
 int hg_hexconv_fwd(const hg_conv_desc* d, const void* x, const float* w, const float* bias, void* y,
                    hg_stream_t stream);
+/* ref: HexModules.py:275-288 HexConvModule.forward in eval mode, order ('conv', 'norm', 'act'):
+ *   y = act(conv(x, w) * scale[co] + shift[co])    with scale = gamma / sqrt(running_var + eps) and
+ *   shift = beta - running_mean * scale (+ conv bias * scale); act = ReLU when d->relu, identity otherwise.
+ * scale (may be NULL = 1) is folded into the weights on their way into shared memory, shift (may be NULL)
+ * takes the bias slot: one pass over x and y instead of three.  Inference only (no backward counterpart). */
+int hg_hexconv_fwd_affine(const hg_conv_desc* d, const void* x, const float* w, const float* scale,
+                          const float* shift, void* y, hg_stream_t stream);
 /* gx [N,Cin,H,W] fully written.  gy has y_dtype, gx has x_dtype. */
 int hg_hexconv_dgrad(const hg_conv_desc* d, const void* gy, const float* w, void* gx, hg_stream_t stream);
 /* gw [Cout,Cin/groups,1,K] float32 and gbias [Cout] float32 (may be NULL) are ACCUMULATED into

@@ -331,3 +331,54 @@ def test_hexconv_autocast_routes_to_tcgen05(hf):
     y32 = m(x.detach())
     ref32 = HO.hexconv2d(x.detach().cpu(), m.kernel.detach().cpu(), m.bias.detach().cpu(), 0, 2, 1, 1)
     assert float((y32.cpu() - ref32).abs().max()) <= 1e-4 * float(ref32.abs().max())
+
+
+@pytest.mark.parametrize("cfg", [
+    # Cin, Cout, H, W, conv bias, act, autocast
+    (3, 8, 20, 24, False, True, False),       # direct stencil
+    (32, 64, 33, 128, True, True, True),      # tcgen05 (TMA staging) under autocast
+    (64, 32, 18, 130, False, False, True),    # tcgen05 (coalesced-load staging), no activation
+    (16, 16, 9, 12, True, True, False),
+])
+def test_hexconvmodule_eval_fuses_bn_relu(hf, cfg):
+    """HexConvModule in eval mode under no_grad: conv -> BatchNorm (running statistics) -> ReLU runs as ONE kernel
+    (hg_hexconv_fwd_affine: scale folded into the weights, shift in the bias slot); result equals the unfused
+    module path and the CPU oracle (HexModules.py:275-288)."""
+    from HyGrid import HexModules as hm
+    from HyGrid import _native as nv
+    Cin, Cout, H, W, bias, act, autocast = cfg
+    torch.manual_seed(11)
+    m = hm.HexConvModule(Cin, Cout, 0, 2, padding=1, bias=bias, norm_cfg=dict(type='BN'),
+                         act_cfg=dict(type='ReLU') if act else None).cuda()
+    with torch.no_grad():
+        m.norm.running_mean.uniform_(-0.5, 0.5)
+        m.norm.running_var.uniform_(0.5, 2.0)
+        m.norm.weight.uniform_(0.5, 1.5)
+        m.norm.bias.uniform_(-0.3, 0.3)
+    m.eval()
+    x = torch.randn(2, Cin, H, W, device="cuda")
+    if autocast:                               # bf16-exact activations
+        x = x.bfloat16().float()
+    ctx = torch.autocast("cuda", dtype=torch.bfloat16) if autocast else torch.autocast("cuda", enabled=False)
+    with torch.no_grad(), ctx:
+        nv.reset_launch_count()
+        y = m(x)
+        fused_launches = nv.launch_count()
+        z = m.conv(x)                          # unfused reference path on the GPU
+    z = torch.nn.functional.batch_norm(z.float(), m.norm.running_mean, m.norm.running_var, m.norm.weight.detach(),
+                                       m.norm.bias.detach(), False, 0.0, m.norm.eps)
+    if act:
+        z = torch.relu(z)
+    assert fused_launches == 1 and y.shape == z.shape and y.dtype == torch.float32
+    tol = 2e-2 if autocast else 1e-4          # autocast: scale*w is rounded to bf16 once instead of w alone
+    assert float((y - z).abs().max()) <= tol * max(1.0, float(z.abs().max()))
+    cb = None if m.conv.bias is None else m.conv.bias.detach().cpu()
+    ref = HO.hexconv2d(x.cpu(), m.conv.kernel.detach().cpu(), cb, 0, 2, 1, 1, 1, 1)
+    ref = torch.nn.functional.batch_norm(ref, m.norm.running_mean.cpu(), m.norm.running_var.cpu(), m.norm.weight.detach().cpu(),
+                                         m.norm.bias.detach().cpu(), False, 0.0, m.norm.eps)
+    if act:
+        ref = torch.relu(ref)
+    assert float((y.cpu() - ref).abs().max()) <= tol * max(1.0, float(ref.abs().max()))
+    # training mode / grad mode keep the three-step path (BN needs batch statistics, backward needs the conv output)
+    m.train()
+    assert m(x).requires_grad
