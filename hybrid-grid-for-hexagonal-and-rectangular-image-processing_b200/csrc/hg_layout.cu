@@ -71,6 +71,21 @@ hex_to_type_vec_kernel(const TS* __restrict__ hex, TD* __restrict__ out, int64_t
   int ro = (int)(r - plane * Hout);
   for (; t < end; t += kStep) {
     Vec o;
+    if (V == 4 && c >= 1 && c + V < 2 * W) {
+      // interior vector (all four elements inside one row and inside the doubled cells): element e reads cell
+      // (c + e - sft) >> 1 -- three consecutive cells cover it, no per-element bounds or carries
+      const int i = rows_mul == 2 ? (ro >> 1) : ro;
+      const int sft = (i + offset) & 1;
+      const int q = c - sft;
+      const TS* __restrict__ hp = hex + (plane * H + i) * (int64_t)W + (q >> 1);
+      const TD v0 = convert<TS, TD>(__ldg(hp)), v1 = convert<TS, TD>(__ldg(hp + 1));
+      if (q & 1) {
+        const TD v2 = convert<TS, TD>(__ldg(hp + 2));
+        o.v[0] = v0; o.v[1] = v1; o.v[V > 2 ? 2 : 0] = v1; o.v[V - 1] = v2;
+      } else {
+        o.v[0] = v0; o.v[1] = v0; o.v[V > 2 ? 2 : 0] = v1; o.v[V - 1] = v1;
+      }
+    } else {
     int cc = c, rr = ro;
     int64_t pp = plane;
 #pragma unroll
@@ -81,6 +96,7 @@ hex_to_type_vec_kernel(const TS* __restrict__ hex, TD* __restrict__ out, int64_t
       if (cc >= sft && cc < 2 * W + sft) v = convert<TS, TD>(__ldg(hex + (pp * H + i) * (int64_t)W + ((cc - sft) >> 1)));
       o.v[e] = v;
       if (++cc == Wt) { cc = 0; if (++rr == Hout) { rr = 0; ++pp; } }
+    }
     }
     __stcs(reinterpret_cast<uint4*>(out + t), *reinterpret_cast<const uint4*>(&o));
     ro += step_r; c += step_c;
