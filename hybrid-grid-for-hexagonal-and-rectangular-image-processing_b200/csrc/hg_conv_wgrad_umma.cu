@@ -14,8 +14,10 @@
 // round of fp32 atomics at the end.  UMMA M is 128: rows 64..127 of the A view run past the Cout = 64
 // channel groups into the neighbouring ring memory; those accumulator lanes are never read.
 //
-// CTA = 14 warps: warps 0-11 converters (x rows and gy rows -> bf16 -> rings; warps 8-11 also run the final
-// epilogue), warp 12 MMA issuer + TMEM allocator, warp 13 TMA producer.  Input path as in hg_conv_umma.cu:
+// CTA = 15 warps: warps 0-11 converters (x rows and gy rows -> bf16 -> rings; warps 8-11 also run the final
+// epilogue), warps 12 and 14 MMA issuers (taps 0-3 / taps 4-6 + bias: disjoint accumulators, so the two
+// instruction streams need no ordering; ncu r1z: one issuing warp was the pacemaker of the pipeline while the
+// tensor pipe was 46 % busy), warp 12 also allocates TMEM, warp 13 TMA producer.  Input path as in hg_conv_umma.cu:
 //   TMA : 4-D boxes [C][1 row][px] of x and gy land in a shared raw staging ring (zero-fill of halos and of the
 //         columns past Wo for free); needs pad_value == 0 and 16-byte aligned rows of both tensors.
 //   LDG : coalesced global loads (any pad value / width).
@@ -31,7 +33,7 @@ constexpr int kWuTile = 128;
 constexpr int kWuPW = 144;
 constexpr int kWuConv = 384;                 // converter threads (warps 0-11)
 constexpr int kWuConvWarps = kWuConv / 32;
-constexpr int kWuThreads = 448;
+constexpr int kWuThreads = 480;               // 12 converter warps, MMA issuer A (12), TMA producer (13), MMA issuer B (14)
 constexpr int kWuBand = 32;
 constexpr int kWuMaxQ = 3;                   // ceil(8 * 144 / 384)
 constexpr int kWuTaps = 7;
@@ -45,6 +47,7 @@ struct WgParams {
   float pad_value;
   int xslots, gslots, bands, ctiles, has_bias;
   int rstages, raw_bytes;        // TMA variant
+  int m64;                       // Cout <= 64: UMMA M = 64 (half the A-operand shared-memory reads of an M = 128 view)
   int cin_total, ci_off, cout_total, co_off;   // this launch covers x channels [ci_off, ci_off + Cin) and gy channels [co_off, co_off + Cout)
   long long items;
 };
@@ -90,10 +93,10 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
 
   for (int e = tid; e < 256; e += kWuThreads) reinterpret_cast<__nv_bfloat16*>(ones)[e] = __float2bfloat16_rn(1.f);
   if (tid == 0) {
-    for (int s = 0; s < P.xslots; ++s) { ptx::mbar_init(&xfull[s], kWuConvWarps); ptx::mbar_init(&xempty[s], 1); }
-    for (int s = 0; s < P.gslots; ++s) { ptx::mbar_init(&gfull[s], kWuConvWarps); ptx::mbar_init(&gempty[s], 1); }
+    for (int s = 0; s < P.xslots; ++s) { ptx::mbar_init(&xfull[s], kWuConvWarps); ptx::mbar_init(&xempty[s], 2); }   // one commit per issuer
+    for (int s = 0; s < P.gslots; ++s) { ptx::mbar_init(&gfull[s], kWuConvWarps); ptx::mbar_init(&gempty[s], 2); }
     for (int s = 0; s < P.rstages; ++s) { ptx::mbar_init(&rfull[s], 1); ptx::mbar_init(&rempty[s], kWuConvWarps); }
-    ptx::mbar_init(done, 1);
+    ptx::mbar_init(done, 2);
     if (TMA) { ptx::prefetch_tensormap(&xmap); ptx::prefetch_tensormap(&gmap); }
     ptx::fence_barrier_init();
   }
@@ -241,7 +244,11 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
     if (warp >= 8) {
       // ===== final epilogue (warps 8-11): TMEM partials -> fp32 atomics ======================================
       const int q4 = warp & 3;
-      const int co = q4 * 32 + lane;
+      // accumulator row (= output channel) held by this thread's TMEM lane.  M = 128: row == lane.  M = 64
+      // (cta_group::1): row r sits in lane 32 * (r / 16) + r % 16, i.e. 16 rows in the lower half of every
+      // 32-lane quadrant (measured on B200 against the oracle: the "first 64 lanes" reading is wrong).
+      int co = q4 * 32 + lane;
+      if (P.m64) co = lane < 16 ? q4 * 16 + lane : (1 << 30);
       ptx::mbar_wait(done, 0);
       ptx::tc_fence_after_sync();
       for (int k = 0; k < kWuTaps; ++k) {
@@ -263,9 +270,12 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
         if (co < P.Cout) atomicAdd(gb + P.co_off + co, __uint_as_float(v[0]));
       }
     }
-  } else if (warp == 12) {
-    // ===== MMA issuer ======================================================================================
-    const uint32_t idesc = wu_idesc(128, P.Cin), idesc_b = wu_idesc(128, 16);
+  } else if (warp == 12 || warp == 14) {
+    // ===== MMA issuers =====================================================================================
+    const int k_begin = warp == 12 ? 0 : 4, k_end = warp == 12 ? 4 : kWuTaps;
+    const bool do_bias = warp == 14 && P.has_bias;
+    const int umma_m = P.m64 ? 64 : 128;
+    const uint32_t idesc = wu_idesc(umma_m, P.Cin), idesc_b = wu_idesc(umma_m, 16);
     const uint32_t g_addr = ptx::smem_u32(gring), x_addr = ptx::smem_u32(xring), o_addr = ptx::smem_u32(ones);
     const uint32_t sbo_g = kWuTile * 16, sbo_x = kWuPW * 16;
     // descriptor = constant high word (SBO, version) | low word (start >> 4, LBO = 128 B between 8-pixel groups)
@@ -295,6 +305,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
           const uint32_t xb2 = (x_addr + s2 * (uint32_t)xslot_bytes) >> 4;
 #pragma unroll
           for (int k = 0; k < kWuTaps; ++k) {
+            if (k < k_begin || k >= k_end) continue;             // warp-uniform
             const int ra = P.ra[k];
             uint32_t b_lo = (ra == 0 ? xb0 : (ra == 1 ? xb1 : xb2)) + (uint32_t)P.sh[par][k] + lo_const;
             uint32_t a_lo = a_lo0;
@@ -305,7 +316,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
               a_lo += 16; b_lo += 16;                       // 16 pixels = 256 bytes
             }
           }
-          if (P.has_bias) {
+          if (do_bias) {
             uint32_t a_lo = a_lo0;
 #pragma unroll
             for (int j = 0; j < kWuTile / 16; ++j) {
@@ -505,6 +516,11 @@ int conv_wgrad_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp
       P.co_off = co0; P.Cout = g.Cout - co0 < 128 ? g.Cout - co0 : 128;
       P.ci_off = ci0; P.Cin = g.Cin - ci0 < 64 ? g.Cin - ci0 : 64;
       P.has_bias = gbias != nullptr && ci0 == 0;
+      // The kernel is shared-memory-bandwidth bound (per gy row: 64 MMAs x 6 KB of operand reads + ~175 KB of
+      // staging / conversion traffic at 128 B/clk): with Cout <= 64 an M = 64 tile reads 2 KB of A per MMA
+      // instead of 4 KB (half of an M = 128 view would be the neighbouring ring slots): 1.11 -> 0.81 ms on C3.
+      static const bool m128_only = [] { const char* e = getenv("HG_WU_M128"); return e && e[0] == '1'; }();
+      P.m64 = (P.Cout <= 64 && !m128_only) ? 1 : 0;
       float* gb = P.has_bias ? gbias : nullptr;
       int rc;
       if (xdt == HG_F32 && gdt == HG_F32) rc = launch_wu_any<float, float>(x, gy, gw, gb, P, st);
