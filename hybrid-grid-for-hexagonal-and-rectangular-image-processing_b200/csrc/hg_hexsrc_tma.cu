@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(kHsThreads, 2)
 hexsrc_linear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __restrict__ dst, const double* __restrict__ xs,
                          const double* __restrict__ ys, int h, int w, int h1, int w1, int planes, int tiles_x, int tiles_y,
                          long long total_items, long long items_per_cta, int BW, int BH, int stage_bytes, double ci, double cj,
-                         double hx, double wy) {
+                         double hx, double wy, int col_major) {
   using WT = typename std::conditional<EXACT, double, float>::type;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kHsStages * stage_bytes);
@@ -70,17 +70,22 @@ hexsrc_linear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __restric
     ptx::fence_barrier_init();
   }
 
-  // plane-group major, tiles row-major; a CTA's items are consecutive, so positions advance by carries
+  // plane-group major; inside a group the tiles run row-major.  (Column-major, which re-uses the 2-of-18-row halo
+  // at once, was measured and rejected: C4 0.73 -> 0.71, C2 0.88 -> 0.69 -- DRAM page locality of consecutive row
+  // segments matters more than the halo; HG_HEXSRC_ORDER=1 keeps it for A/B runs.)  A CTA's items are
+  // consecutive, so positions advance by carries.
   struct Pos { int grp, tx, ty; };
   auto decode = [&](long long g) {
     Pos q;
     q.grp = (int)(g / npos);
     const int pos = (int)(g - (long long)q.grp * npos);
-    q.ty = pos / tiles_x; q.tx = pos - q.ty * tiles_x;
+    if (col_major) { q.tx = pos / tiles_y; q.ty = pos - q.tx * tiles_y; }
+    else { q.ty = pos / tiles_x; q.tx = pos - q.ty * tiles_x; }
     return q;
   };
   auto advance = [&](Pos& q) {
-    if (++q.tx == tiles_x) { q.tx = 0; if (++q.ty == tiles_y) { q.ty = 0; ++q.grp; } }
+    if (col_major) { if (++q.ty == tiles_y) { q.ty = 0; if (++q.tx == tiles_x) { q.tx = 0; ++q.grp; } } }
+    else if (++q.tx == tiles_x) { q.tx = 0; if (++q.ty == tiles_y) { q.ty = 0; ++q.grp; } }
   };
   auto origin = [&](int tx, int ty, int& row0, int& col0) {
     row0 = trunc_i32(dadd(xs[ty * kHsTH], ci));
@@ -266,12 +271,14 @@ int try_hexsrc_linear_tma(const void* src, void* dst, const double* xs, const do
   const long long per = (total + grid - 1) / grid;
   grid = (total + per - 1) / per;
   const double hx = (h - 1) / 2.0, wy = (w - 0.5) / 2.0;     // python-float expressions of geometry_np.py:326-331
+  static const int order_env = [] { const char* e = getenv("HG_HEXSRC_ORDER"); return e ? atoi(e) : -1; }();   // A/B: 0 row-, 1 column-major
+  const int col_major = order_env > 0 ? 1 : 0;
   if (variant == 0)
-    hexsrc_linear_tma_kernel<float, false><<<(unsigned)grid, kHsThreads, smem, st>>>(tmap, (float*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, (int)planes, tiles_x, tiles_y, total, per, BW, BH, stage_bytes, ci, cj, hx, wy);
+    hexsrc_linear_tma_kernel<float, false><<<(unsigned)grid, kHsThreads, smem, st>>>(tmap, (float*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, (int)planes, tiles_x, tiles_y, total, per, BW, BH, stage_bytes, ci, cj, hx, wy, col_major);
   else if (variant == 1)
-    hexsrc_linear_tma_kernel<float, true><<<(unsigned)grid, kHsThreads, smem, st>>>(tmap, (float*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, (int)planes, tiles_x, tiles_y, total, per, BW, BH, stage_bytes, ci, cj, hx, wy);
+    hexsrc_linear_tma_kernel<float, true><<<(unsigned)grid, kHsThreads, smem, st>>>(tmap, (float*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, (int)planes, tiles_x, tiles_y, total, per, BW, BH, stage_bytes, ci, cj, hx, wy, col_major);
   else
-    hexsrc_linear_tma_kernel<double, true><<<(unsigned)grid, kHsThreads, smem, st>>>(tmap, (double*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, (int)planes, tiles_x, tiles_y, total, per, BW, BH, stage_bytes, ci, cj, hx, wy);
+    hexsrc_linear_tma_kernel<double, true><<<(unsigned)grid, kHsThreads, smem, st>>>(tmap, (double*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, (int)planes, tiles_x, tiles_y, total, per, BW, BH, stage_bytes, ci, cj, hx, wy, col_major);
   return finish_launch("hexsrc_linear_tma");
 }
 
