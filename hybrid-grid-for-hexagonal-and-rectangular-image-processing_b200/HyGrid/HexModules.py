@@ -14,6 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import HexFrames as hnn
+from . import _norm
 
 try:  # pragma: no cover - mmcv 1.x is not installed in the build image
     from mmcv.cnn.bricks.norm import build_norm_layer
@@ -243,6 +244,13 @@ class HexConvModule(nn.Module):
             elif layer == 'norm' and norm and self.with_norm:
                 if skip_norm:
                     skip_norm = False
+                    continue
+                if _norm.bn_supported(self.norm, x):
+                    # BatchNorm2d (+ a directly following plain ReLU) on the library's streaming kernels: two passes
+                    # forward, two backward, instead of cuDNN batch-norm + ReLU and their backward twins
+                    tail = self.order[idx + 1:]
+                    fused = bool(tail) and tail[0] == 'act' and activate and self.with_activation and type(self.activate) is nn.ReLU
+                    x = _norm.batch_norm_relu(self.norm, x, relu=fused)
                     continue
                 x = self.norm(x)
             elif layer == 'act' and activate and self.with_activation:

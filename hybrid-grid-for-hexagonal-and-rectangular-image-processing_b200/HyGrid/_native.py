@@ -64,6 +64,10 @@ _SIGS = {
     "hg_hexconv_umma_eligible": [C.POINTER(ConvDesc), _i],
     "hg_hexconv_fwd": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],
     "hg_hexconv_fwd_affine": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p, _p],
+    "hg_bn_stats": [_p, _p, _l, _l, _l, _p],
+    "hg_bn_apply": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _l, _l, C.c_float, _i, _p],
+    "hg_bn_bwd_reduce": [_p, _p, _p, _p, _p, _p, _p, _l, _l, _l, _i, _p],
+    "hg_bn_bwd_apply": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _l, _l, _i, _i, _p],
     "hg_hexconv_dgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p],
     "hg_hexconv_wgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],
     "hg_host_rect2hex": [_p, _p, _p, _p, _l, _l, _l, _l, _l, _i, _i, _i, _i, _i],

@@ -208,11 +208,11 @@ hexconv_dgrad_direct(const TG* __restrict__ gy, const float* __restrict__ w, TX*
 // grid: x = bands, y = (Cout/4) * (cin_g/4) tiles, z = N
 // ---------------------------------------------------------------------------------------------------
 constexpr int kWgC = 4;      // co and ci per CTA
-constexpr int kWgKT = 8;     // taps per pass
+constexpr int kWgKT = 4;     // taps per pass (4 x 4 x 4 = 64 accumulators per thread: no spills, 2 CTAs / SM)
 constexpr int kWgBand = 64;  // output rows per CTA
 
 template <typename TX, typename TG>
-__global__ void __launch_bounds__(kConvThreads)
+__global__ void __launch_bounds__(kConvThreads, 2)
 hexconv_wgrad_direct(const TX* __restrict__ x, const TG* __restrict__ gy, float* __restrict__ gw, ConvGeom g, ConvTaps tp) {
   __shared__ float red[kWgC * kWgC * kWgKT];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -230,6 +230,30 @@ int hg_host_hex2rect(const void* host_src, void* host_dst, const double* host_xs
  * (the only memory the library ever owns). */
 void hg_host_release(void);
 
+/* ----------------------------------------------------------------------------------------------------
+ * Batch normalisation (+ fused ReLU) of HexConvModule: conv -> norm -> act (ref: HexModules.py:146-288; the norm
+ * layer is torch.nn.BatchNorm2d built through mmcv's build_norm_layer, HexModules.py:57-76).  float32 NCHW,
+ * x / y / dy / dx are [N, C, HW] contiguous; gamma / beta may be NULL (affine=False); HBM-bound streaming kernels.
+ *   hg_bn_stats      sums[2c] += sum x, sums[2c+1] += sum x^2   (float64 [2*C], caller zeroes)
+ *   hg_bn_apply      y = act(x * gamma*rstd + (beta - mean*gamma*rstd)); statistics from `sums` (training: mean,
+ *                    biased variance and rstd are written to mean_out / var_out / rstd_out, each may be NULL) or from
+ *                    mean_in / var_in (inference, sums == NULL); relu != 0 fuses the ReLU
+ *   hg_bn_bwd_reduce dsums[2c] += sum dz, dsums[2c+1] += sum dz*xhat with dz = dy (masked by the fused ReLU's z > 0,
+ *                    z recomputed from x) -- float64 [2*C], caller zeroes
+ *   hg_bn_bwd_apply  dx = gamma*rstd*(dz - sum(dz)/n - xhat*sum(dz*xhat)/n) (training) or gamma*rstd*dz (inference);
+ *                    dgamma / dbeta (may be NULL) = sum dz*xhat / sum dz
+ * -------------------------------------------------------------------------------------------------- */
+int hg_bn_stats(const float* x, double* sums, int64_t N, int64_t C, int64_t HW, hg_stream_t stream);
+int hg_bn_apply(const float* x, float* y, const double* sums, const float* mean_in, const float* var_in,
+                const float* gamma, const float* beta, float* mean_out, float* var_out, float* rstd_out,
+                int64_t N, int64_t C, int64_t HW, float eps, int relu, hg_stream_t stream);
+int hg_bn_bwd_reduce(const float* x, const float* dy, const float* mean, const float* rstd, const float* gamma,
+                     const float* beta, double* dsums, int64_t N, int64_t C, int64_t HW, int relu,
+                     hg_stream_t stream);
+int hg_bn_bwd_apply(const float* x, const float* dy, const float* mean, const float* rstd, const float* gamma,
+                    const float* beta, const double* dsums, float* dx, float* dgamma, float* dbeta, int64_t N,
+                    int64_t C, int64_t HW, int relu, int training, hg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

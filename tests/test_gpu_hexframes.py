@@ -382,3 +382,71 @@ def test_hexconvmodule_eval_fuses_bn_relu(hf, cfg):
     # training mode / grad mode keep the three-step path (BN needs batch statistics, backward needs the conv output)
     m.train()
     assert m(x).requires_grad
+
+
+@pytest.mark.parametrize("cfg", [
+    # N, C, H, W, relu, affine, momentum, track
+    (4, 8, 16, 20, True, True, 0.1, True),
+    (3, 5, 7, 9, True, True, None, True),        # HW not a multiple of 4: scalar kernels; cumulative average
+    (2, 16, 64, 65, False, True, 0.3, True),     # several chunks per plane
+    (2, 4, 6, 8, True, False, 0.1, True),        # affine=False
+    (2, 4, 6, 8, True, True, 0.1, False),        # no running statistics: batch statistics in eval mode too
+])
+def test_batch_norm_relu_kernels_vs_torch(hf, cfg):
+    """hg_bn_* (HexConvModule's norm + act on the library kernels) against torch.nn.BatchNorm2d + ReLU: forward,
+    backward (dx, dgamma, dbeta), running statistics and num_batches_tracked, training and eval mode."""
+    from HyGrid import _norm
+    N, C_, H, W, relu, affine, momentum, track = cfg
+    torch.manual_seed(21)
+    ref = torch.nn.BatchNorm2d(C_, momentum=momentum, affine=affine, track_running_stats=track).cuda()
+    ours = torch.nn.BatchNorm2d(C_, momentum=momentum, affine=affine, track_running_stats=track).cuda()
+    if affine:
+        with torch.no_grad():
+            ref.weight.uniform_(0.5, 1.5); ref.bias.uniform_(-0.5, 0.5)
+        ours.load_state_dict(ref.state_dict())
+    for mode in ("train", "train", "eval"):
+        ref.train(mode == "train"); ours.train(mode == "train")
+        x = torch.randn(N, C_, H, W, device="cuda") * 2 + 0.5
+        xr, xo = x.clone().requires_grad_(), x.clone().requires_grad_()
+        yr = ref(xr)
+        if relu:
+            yr = torch.relu(yr)
+        assert _norm.bn_supported(ours, xo)
+        yo = _norm.batch_norm_relu(ours, xo, relu=relu)
+        assert float((yo - yr).abs().max()) <= 2e-5 * max(1.0, float(yr.abs().max()))
+        g = torch.randn_like(yr)
+        (yr * g).sum().backward()
+        (yo * g).sum().backward()
+        assert float((xo.grad - xr.grad).abs().max()) <= 5e-5 * max(1.0, float(xr.grad.abs().max()))
+        if affine:
+            for po, pr in ((ours.weight, ref.weight), (ours.bias, ref.bias)):
+                assert float((po.grad - pr.grad).abs().max()) <= 1e-4 * max(1.0, float(pr.grad.abs().max()))
+                po.grad = None; pr.grad = None
+        if track:
+            assert float((ours.running_mean - ref.running_mean).abs().max()) <= 1e-5
+            assert float((ours.running_var - ref.running_var).abs().max()) <= 1e-5 * max(1.0, float(ref.running_var.max()))
+            assert int(ours.num_batches_tracked) == int(ref.num_batches_tracked)
+
+
+def test_hexconvmodule_training_uses_library_bn(hf):
+    """conv -> BN -> ReLU in training mode: 1 conv + 2 batch-norm launches forward, gradients equal to the torch
+    composition of the same conv output."""
+    from HyGrid import HexModules as hm
+    from HyGrid import _native as nv
+    torch.manual_seed(5)
+    m = hm.HexConvModule(8, 16, 0, 2, padding=1, norm_cfg=dict(type='BN')).cuda()
+    x = torch.randn(3, 8, 12, 16, device="cuda", requires_grad=True)
+    nv.reset_launch_count()
+    y = m(x)
+    assert nv.launch_count() == 3
+    y.square().mean().backward()
+    gx, gk = x.grad.clone(), m.conv.kernel.grad.clone()
+    x.grad = None; m.zero_grad()
+    m2 = hm.HexConvModule(8, 16, 0, 2, padding=1, norm_cfg=dict(type='BN')).cuda()
+    m2.load_state_dict({k: v for k, v in m.state_dict().items()})
+    m2.norm.running_mean.zero_(); m2.norm.running_var.fill_(1); m2.norm.num_batches_tracked.zero_()
+    z = torch.relu(torch.nn.functional.batch_norm(m2.conv(x), None, None, m2.norm.weight, m2.norm.bias, True, 0.1, m2.norm.eps))
+    assert float((y - z).abs().max()) <= 2e-5 * max(1.0, float(z.abs().max()))
+    z.square().mean().backward()
+    assert float((x.grad - gx).abs().max()) <= 1e-4 * max(1e-3, float(gx.abs().max()))
+    assert float((m2.conv.kernel.grad - gk).abs().max()) <= 1e-4 * max(1e-3, float(gk.abs().max()))
