@@ -229,10 +229,19 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
           uint32_t v[32];
           ptx::tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * (uint32_t)P.Nout + (uint32_t)cb, v);
           // bias of this chunk in registers (8 vector LDS in flight together with the TMEM load) -- a scalar
-          // LDS in front of every FADD serialises the epilogue on shared-memory latency (ncu r1i).
+          // LDS in front of every FADD serialises the epilogue on shared-memory latency (ncu r1i).  Accumulating
+          // passes (ACC) carry no bias: the same registers take the 32 old output values instead, all loads in
+          // flight at once (one load in front of every add made the pass 4x slower than a first pass, ncu r2h).
           float4 bb[8];
+          if (ACC) {
+            float* bo = reinterpret_cast<float*>(bb);
+            const int nv_ = min(32, P.Nout - cb);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) bb[i] = *reinterpret_cast<const float4*>(bias_s + cb + 4 * i);
+            for (int j = 0; j < 32; ++j) bo[j] = (c < P.Wo && j < nv_) ? ld_out(op + (size_t)j * cstride) : 0.f;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bb[i] = *reinterpret_cast<const float4*>(bias_s + cb + 4 * i);
+          }
           ptx::tmem_ld_wait();
           const bool last = cb == my_last;
           if (last) {                        // this warp's part of the accumulator is in registers: hand it back
@@ -246,7 +255,6 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 float f = __uint_as_float(v[j]) + bf[j];
-                if (ACC) f += ld_out(op);
                 if (P.relu) f = fmaxf(f, 0.f);
                 st_out(op, f);
                 op += cstride;
@@ -255,7 +263,6 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 float f = __uint_as_float(v[j]) + bf[j];
-                if (ACC) f += ld_out(op);
                 if (P.relu) f = fmaxf(f, 0.f);
                 st_out(op, f);
                 op += cstride;
