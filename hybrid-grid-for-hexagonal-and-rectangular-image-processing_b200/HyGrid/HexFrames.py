@@ -151,7 +151,8 @@ class _HexConvFn(torch.autograd.Function):
                 if nv.query("hg_hexconv_umma_eligible", C.byref(dp), 2):
                     dp.algo = 2
                     xw, dw = xp, dp
-            gw = torch.zeros((w.shape[0], xw.shape[1]) + tuple(w.shape[2:]), dtype=torch.float32, device=x.device)
+            cin_w = w.shape[1] if xw is x else xw.shape[1]          # Cin / groups, or the padded channel count
+            gw = torch.zeros((w.shape[0], cin_w) + tuple(w.shape[2:]), dtype=torch.float32, device=x.device)
             nv.call("hg_hexconv_wgrad", C.byref(dw), nv.ptr(xw), nv.ptr(gy), nv.ptr(gw), nv.ptr(gb), st)
             if xw is not x:
                 gw = gw[:, :Cin].contiguous()
