@@ -450,3 +450,23 @@ def test_hexconvmodule_training_uses_library_bn(hf):
     z.square().mean().backward()
     assert float((x.grad - gx).abs().max()) <= 1e-4 * max(1e-3, float(gx.abs().max()))
     assert float((m2.conv.kernel.grad - gk).abs().max()) <= 1e-4 * max(1e-3, float(gk.abs().max()))
+
+
+def test_hexconv_autocast_rgb_first_layer(hf):
+    """Cin = 3 under autocast: forward on the direct stencil, weight gradient through the tcgen05 kernel with the
+    input channels zero-padded to 16 (the padded channels' gradients are dropped); vs the fp32 oracle at bf16 tolerance."""
+    torch.manual_seed(9)
+    conv = hf.HexConv2d(3, 32, 0, 2, padding=1).cuda()
+    x = torch.randn(4, 3, 40, 128, device="cuda").bfloat16().float()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = conv(x)
+    g = torch.randn_like(y).bfloat16().float()
+    (y * g).sum().backward()
+    wr, br = conv.kernel.detach().cpu().clone().requires_grad_(), conv.bias.detach().cpu().clone().requires_grad_()
+    yr = HO.hexconv2d(x.cpu(), wr, br, 0, 2, 1, 1, 1, 1)
+    (yr * g.cpu()).sum().backward()
+    assert y.dtype == torch.float32
+    assert float((y.detach().cpu() - yr.detach()).abs().max()) <= 2e-2 * float(yr.detach().abs().max())
+    assert conv.kernel.grad.shape == wr.grad.shape
+    assert float((conv.kernel.grad.cpu() - wr.grad).abs().max()) <= 2e-2 * float(wr.grad.abs().max())
+    assert float((conv.bias.grad.cpu() - br.grad).abs().max()) <= 2e-2 * float(br.grad.abs().max())
