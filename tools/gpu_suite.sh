@@ -23,6 +23,7 @@ if has bench; then
 fi
 if has path; then timeout 900 python tools/bench_path.py --reps 10 > $OUT/bench_path.jsonl 2>&1; echo "bench_path rc=$?"; grep -v '"rows"' $OUT/bench_path.jsonl | cut -c1-200; fi
 if has conv; then timeout 900 python tools/bench_conv.py --reps 10 > $OUT/bench_conv.jsonl 2>&1; echo "bench_conv rc=$?"; grep -v '"rows"' $OUT/bench_conv.jsonl | cut -c1-220; fi
+if has conv; then timeout 600 python tools/bench_c3.py > $OUT/bench_c3.json 2>&1; echo "bench_c3 rc=$?"; tail -1 $OUT/bench_c3.json | cut -c1-300; fi
 if has cnn; then
   timeout 300 python tools/hexcnn_ddp.py --batch 64 --steps 10 --autocast > $OUT/hexcnn_autocast.log 2>&1; echo "hexcnn(autocast) rc=$?"; tail -1 $OUT/hexcnn_autocast.log
   timeout 300 python tools/hexcnn_ddp.py --batch 64 --steps 10 > $OUT/hexcnn_fp32.log 2>&1; echo "hexcnn(fp32) rc=$?"; tail -1 $OUT/hexcnn_fp32.log
@@ -33,6 +34,7 @@ if has ncu; then   # launch list of the bench + one --set full capture per domin
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/bench_launches.csv $B > $OUT/ncu_launches.log 2>&1; echo "launch list rc=$?"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:rect2hex_bilinear_ws -s 3 -c 1 -o $OUT/prof_rect2hex_ws $B > $OUT/ncu_r2h.log 2>&1; echo "ncu rect2hex rc=$?"
   cap() { P="python tools/bench_path.py --reps 2 --small --only"; timeout 600 $P "$3" > $OUT/plain_$1.log 2>&1 && timeout 900 ncu --set full --clock-control none --import-source on -k regex:$2 -s 2 -c 1 -o $OUT/prof_$1 $P "$3" > $OUT/ncu_$1.log 2>&1; echo "ncu $1 rc=$?"; }
+  timeout 300 python tools/bench_pcie.py > $OUT/bench_pcie.json 2>&1; echo "pcie probe rc=$?"; cat $OUT/bench_pcie.json
   cap hexsrc_tma hexsrc_linear_tma "c4 hex->rect linear fast"
   cap pool_vec hexpool2x2_fwd "pool avg 2x2 level 0"
   cap type1 hex_to_type_vec "hex->type1"
