@@ -11,6 +11,7 @@
 #include "hg_common.cuh"
 #include "hg_hexgeom.cuh"
 #include <type_traits>
+#include <stdlib.h>
 
 namespace hg {
 
@@ -308,6 +309,61 @@ hexsrc_linear_kernel(const TS* __restrict__ src, TD* __restrict__ dst, Coord coo
   }
 }
 
+// float32-weight variant with the plane loop outermost: the 16 samples of a thread (3 offsets + 3 weights each) stay in
+// registers and `chunk` planes stream through them (the row-outer kernel above re-evaluates nothing either, but
+// keeps only 4 samples' loads in flight; measured on the 2:1 hexresize of C4: 0.68 -> see DESIGN.md).
+constexpr int kFastRows = 2;                 // output rows per warp of the plane-outer linear kernel (8 samples per thread in registers)
+constexpr int kFastTileH = 8 * kFastRows;
+
+template <typename TS, typename TD, typename Coord>
+__global__ void __launch_bounds__(kThreads, 2)
+hexsrc_linear_fast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, Coord coord, HexConsts hc, int64_t planes, int chunk,
+                          int h, int w, int h1, int w1, int tiles_x, int tiles_y) {
+  using CT = typename Coord::CT;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int tile = blockIdx.x;
+  const int tx = tile % tiles_x; tile /= tiles_x;
+  const int ty = tile % tiles_y;
+  const int64_t p0 = (int64_t)(tile / tiles_y) * chunk;
+  const int np = (int)min((int64_t)chunk, planes - p0);
+  const int64_t sps = (int64_t)h * w, dps = (int64_t)h1 * w1;
+  int off[kFastRows][kColsPerThread][3];
+  float wgt[kFastRows][kColsPerThread][3];
+  bool live[kFastRows][kColsPerThread];
+#pragma unroll
+  for (int rr = 0; rr < kFastRows; ++rr) {
+    const int a = ty * kFastTileH + warp * kFastRows + rr;
+#pragma unroll
+    for (int k = 0; k < kColsPerThread; ++k) {
+      const int b = tx * kTileW + lane + 32 * k;
+      live[rr][k] = a < h1 && b < w1;
+      CT x, y;
+      coord.get(live[rr][k] ? a : 0, live[rr][k] ? b : 0, w1, x, y);
+      HexSample<float> s;
+      hex_locate_fast((double)x, (double)y, h, w, hc.ci, hc.cj, s);
+#pragma unroll
+      for (int t = 0; t < 3; ++t) { off[rr][k][t] = live[rr][k] ? s.off[t] : -1; wgt[rr][k][t] = s.wgt[t]; }
+    }
+  }
+  const TS* __restrict__ sp = src + p0 * sps;
+  TD* __restrict__ dp = dst + p0 * dps + (int64_t)(ty * kFastTileH + warp * kFastRows) * w1 + tx * kTileW + lane;
+  for (int p = 0; p < np; ++p, sp += sps, dp += dps) {
+#pragma unroll
+    for (int rr = 0; rr < kFastRows; ++rr) {
+      float v[kColsPerThread][3];
+#pragma unroll
+      for (int k = 0; k < kColsPerThread; ++k)
+#pragma unroll
+        for (int t = 0; t < 3; ++t) v[k][t] = off[rr][k][t] >= 0 ? to_f32(ldg(sp + off[rr][k][t])) : 0.f;
+#pragma unroll
+      for (int k = 0; k < kColsPerThread; ++k)
+        if (live[rr][k])
+          st_stream(dp + (int64_t)rr * w1 + 32 * k,
+                    (TD)fmaf(wgt[rr][k][2], v[k][2], fmaf(wgt[rr][k][1], v[k][1], wgt[rr][k][0] * v[k][0])));
+    }
+  }
+}
+
 // The closest lattice point of a sample does not depend on the plane: resolve the tile's 16 source offsets per
 // thread once (float64 / float32 distances exactly as the reference evaluates them), then stream `chunk` planes.
 template <typename T, typename Coord>
@@ -433,6 +489,19 @@ template <typename TS, typename TD, typename Coord, bool FAST>
 static int launch_hexsrc_linear(const void* src, void* dst, const Coord& c, int64_t planes, int64_t h, int64_t w,
                                 int64_t h1, int64_t w1, cudaStream_t st) {
   Tiling t;
+  if (FAST && !std::is_same<TS, double>::value) {
+    static const bool rows_outer = [] { const char* e = getenv("HG_HEXSRC_ROWS_OUTER"); return e && e[0] == '1'; }();
+    if (!rows_outer) {
+      const int pc = plane_chunk(planes, ceil_div(h1, kFastTileH) * ceil_div(w1, kTileW));
+      t.tx = (int)ceil_div(w1, kTileW);
+      t.ty = (int)ceil_div(h1, kFastTileH);
+      t.blocks = (int64_t)t.tx * t.ty * ceil_div(planes, pc);
+      HG_REQUIRE(t.blocks > 0 && t.blocks < (1ll << 31), HG_E_SHAPE, "grid of %lld tiles is out of range", (long long)t.blocks);
+      hexsrc_linear_fast_kernel<TS, TD, Coord><<<(unsigned)t.blocks, kThreads, 0, st>>>(
+          (const TS*)src, (TD*)dst, c, hex_consts(h, w), planes, pc, (int)h, (int)w, (int)h1, (int)w1, t.tx, t.ty);
+      return finish_launch("hexsrc_linear_fast");
+    }
+  }
   const int chunk = 8;   // row-outer loop: larger chunks lose the L1 reuse of source rows shared by consecutive output rows (measured)
   int rc = make_tiling(h1, w1, ceil_div(planes, chunk), t);
   if (rc) return rc;
