@@ -309,17 +309,21 @@ hexsrc_linear_kernel(const TS* __restrict__ src, TD* __restrict__ dst, Coord coo
   }
 }
 
-// float32-weight variant with the plane loop outermost: the 16 samples of a thread (3 offsets + 3 weights each) stay in
-// registers and `chunk` planes stream through them (the row-outer kernel above re-evaluates nothing either, but
-// keeps only 4 samples' loads in flight; measured on the 2:1 hexresize of C4: 0.68 -> see DESIGN.md).
+// Plane loop outermost: the 8 samples of a thread (3 offsets + 3 weights each) stay in registers and `chunk` planes
+// stream through them, so the per-sample geometry -- ~250 float64 instructions in exact mode -- is paid once per
+// `chunk` planes (the row-outer kernel above pays it once per 8 and keeps only 4 samples' loads in flight).
+// Measured on C4: 2:1 hexresize fast 0.68 -> 1.06 of the HBM copy rate.
 constexpr int kFastRows = 2;                 // output rows per warp of the plane-outer linear kernel (8 samples per thread in registers)
 constexpr int kFastTileH = 8 * kFastRows;
 
-template <typename TS, typename TD, typename Coord>
+template <typename TS, typename TD, typename Coord, bool FAST>
 __global__ void __launch_bounds__(kThreads, 2)
 hexsrc_linear_fast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, Coord coord, HexConsts hc, int64_t planes, int chunk,
                           int h, int w, int h1, int w1, int tiles_x, int tiles_y) {
   using CT = typename Coord::CT;
+  using WT = typename std::conditional<FAST, float, CT>::type;
+  using BT = typename std::conditional<FAST, float, typename BlendT<CT, TS>::type>::type;
+  using AB = Arith<BT>;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int tile = blockIdx.x;
   const int tx = tile % tiles_x; tile /= tiles_x;
@@ -328,7 +332,7 @@ hexsrc_linear_fast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, Coor
   const int np = (int)min((int64_t)chunk, planes - p0);
   const int64_t sps = (int64_t)h * w, dps = (int64_t)h1 * w1;
   int off[kFastRows][kColsPerThread][3];
-  float wgt[kFastRows][kColsPerThread][3];
+  WT wgt[kFastRows][kColsPerThread][3];
   bool live[kFastRows][kColsPerThread];
 #pragma unroll
   for (int rr = 0; rr < kFastRows; ++rr) {
@@ -339,8 +343,9 @@ hexsrc_linear_fast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, Coor
       live[rr][k] = a < h1 && b < w1;
       CT x, y;
       coord.get(live[rr][k] ? a : 0, live[rr][k] ? b : 0, w1, x, y);
-      HexSample<float> s;
-      hex_locate_fast((double)x, (double)y, h, w, hc.ci, hc.cj, s);
+      HexSample<WT> s;
+      if (FAST) hex_locate_fast((double)x, (double)y, h, w, hc.ci, hc.cj, (HexSample<float>&)s);
+      else hex_locate<CT, true, false>(x, y, h, w, (CT)hc.hx, (CT)hc.wy, (CT)hc.ci, (CT)hc.cj, (HexSample<CT>&)s);
 #pragma unroll
       for (int t = 0; t < 3; ++t) { off[rr][k][t] = live[rr][k] ? s.off[t] : -1; wgt[rr][k][t] = s.wgt[t]; }
     }
@@ -350,16 +355,23 @@ hexsrc_linear_fast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, Coor
   for (int p = 0; p < np; ++p, sp += sps, dp += dps) {
 #pragma unroll
     for (int rr = 0; rr < kFastRows; ++rr) {
-      float v[kColsPerThread][3];
+      TS v[kColsPerThread][3];
 #pragma unroll
       for (int k = 0; k < kColsPerThread; ++k)
 #pragma unroll
-        for (int t = 0; t < 3; ++t) v[k][t] = off[rr][k][t] >= 0 ? to_f32(ldg(sp + off[rr][k][t])) : 0.f;
+        for (int t = 0; t < 3; ++t) v[k][t] = off[rr][k][t] >= 0 ? ldg(sp + off[rr][k][t]) : TS(0);
 #pragma unroll
-      for (int k = 0; k < kColsPerThread; ++k)
-        if (live[rr][k])
-          st_stream(dp + (int64_t)rr * w1 + 32 * k,
-                    (TD)fmaf(wgt[rr][k][2], v[k][2], fmaf(wgt[rr][k][1], v[k][1], wgt[rr][k][0] * v[k][0])));
+      for (int k = 0; k < kColsPerThread; ++k) {
+        if (!live[rr][k]) continue;
+        BT o;
+        if (FAST) {
+          o = fmaf((float)wgt[rr][k][2], to_f32(v[k][2]), fmaf((float)wgt[rr][k][1], to_f32(v[k][1]), (float)wgt[rr][k][0] * to_f32(v[k][0])));
+        } else {   // ref geometry_np.py:354  alpha * p1 + beta * p2 + gamma * p3, one rounding per operation
+          o = AB::add(AB::add(AB::mul((BT)wgt[rr][k][0], (BT)v[k][0]), AB::mul((BT)wgt[rr][k][1], (BT)v[k][1])),
+                      AB::mul((BT)wgt[rr][k][2], (BT)v[k][2]));
+        }
+        st_stream(dp + (int64_t)rr * w1 + 32 * k, (TD)o);
+      }
     }
   }
 }
@@ -489,7 +501,7 @@ template <typename TS, typename TD, typename Coord, bool FAST>
 static int launch_hexsrc_linear(const void* src, void* dst, const Coord& c, int64_t planes, int64_t h, int64_t w,
                                 int64_t h1, int64_t w1, cudaStream_t st) {
   Tiling t;
-  if (FAST && !std::is_same<TS, double>::value) {
+  if (FAST) {   // exact mode measured slower with the plane loop outermost (C4: 14.0 ms vs 9.2 ms row-outer, 7.1 ms TMA tiles)
     static const bool rows_outer = [] { const char* e = getenv("HG_HEXSRC_ROWS_OUTER"); return e && e[0] == '1'; }();
     if (!rows_outer) {
       const int pc = plane_chunk(planes, ceil_div(h1, kFastTileH) * ceil_div(w1, kTileW));
@@ -497,7 +509,7 @@ static int launch_hexsrc_linear(const void* src, void* dst, const Coord& c, int6
       t.ty = (int)ceil_div(h1, kFastTileH);
       t.blocks = (int64_t)t.tx * t.ty * ceil_div(planes, pc);
       HG_REQUIRE(t.blocks > 0 && t.blocks < (1ll << 31), HG_E_SHAPE, "grid of %lld tiles is out of range", (long long)t.blocks);
-      hexsrc_linear_fast_kernel<TS, TD, Coord><<<(unsigned)t.blocks, kThreads, 0, st>>>(
+      hexsrc_linear_fast_kernel<TS, TD, Coord, FAST><<<(unsigned)t.blocks, kThreads, 0, st>>>(
           (const TS*)src, (TD*)dst, c, hex_consts(h, w), planes, pc, (int)h, (int)w, (int)h1, (int)w1, t.tx, t.ty);
       return finish_launch("hexsrc_linear_fast");
     }
