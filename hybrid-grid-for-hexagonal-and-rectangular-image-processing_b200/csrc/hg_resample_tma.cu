@@ -222,7 +222,7 @@ template <> __device__ __forceinline__ uint8_t lds_at<uint8_t>(uint32_t addr) {
 // the table / TMA latency is hidden behind kStages tiles of lookahead.  full[s] completes on two arrivals (TMA
 // issue + tables written) plus the box's byte count; empty[s] on one arrival per consumer warp.
 template <typename TS, typename TD, bool EXACT, int RW, int NW>
-__global__ void __launch_bounds__((NW + 1) * 32, EXACT ? 1 : (NW == 16 ? 2 : 3))
+__global__ void __launch_bounds__((NW + 1) * 32, EXACT ? 2 : (NW == 16 ? 2 : 3))
 rect2hex_bilinear_ws_kernel(const __grid_constant__ CUtensorMap tmap, TD* __restrict__ dst, const double* __restrict__ xs,
                             const double* __restrict__ ys, int h, int w, int h1, int w1, int tiles_x, int tiles_y,
                             long long total_items, long long items_per_cta, int BW, int BH, int stage_bytes) {
@@ -491,6 +491,11 @@ static int launch_ws(const void* src, void* dst, const double* xs, const double*
   return finish_launch("rect2hex_bilinear_ws");
 }
 
+static bool exact_sync_env() {
+  static const bool v = [] { const char* e = getenv("HG_R2H_EXACT_SYNC"); return e && e[0] == '1'; }();
+  return v;
+}
+
 // Returns HG_OK when the tiled kernel was launched, 1 when it does not apply (caller falls back to the
 // direct gather), or an error code.
 int try_rect2hex_bilinear_tma(const void* src, void* dst, const double* xs, const double* ys, const double* host_xs,
@@ -503,7 +508,7 @@ int try_rect2hex_bilinear_tma(const void* src, void* dst, const double* xs, cons
   // HG_R2H_WS: 0 = CTA-synchronous kernel, 8 / 16 = warp-specialised kernel with that many consumer warps (default 8)
   static const int ws_warps = [] { const char* e = getenv("HG_R2H_WS"); return e ? atoi(e) : 8; }();
   const int RW = rows_per_warp == 8 ? 8 : 4;
-  const bool ws = ws_warps != 0 && math != HG_MATH_EXACT;
+  const bool ws = ws_warps != 0 && (math != HG_MATH_EXACT || !exact_sync_env());
   const int TH = (ws && ws_warps == 16 ? 16 : 8) * (ws ? 4 : RW);
   const int span_r = axis_span(host_xs, h1, h, TH), span_c = axis_span(host_ys, w1, w, kTW);
   if (span_r < 0 || span_c < 0) return 1;
@@ -512,11 +517,12 @@ int try_rect2hex_bilinear_tma(const void* src, void* dst, const double* xs, cons
   // staging pays off while the footprint is close to the tile (every staged byte is used ~4 times);
   // for strong down-sampling the direct gather already runs at the HBM roofline.
   if ((int64_t)BH * BW > (int64_t)2 * TH * kTW) return 1;
-  // float32 math: warp-specialised kernel (measured r1r: C2 0.88 / C4 0.85 of the HBM copy rate vs 0.82 / 0.83 for the
-  // CTA-synchronous one).  The float64 blend of HG_MATH_EXACT needs 145 registers there, so it stays on the
-  // CTA-synchronous kernel (60 registers).
+  // warp-specialised kernel (measured: C2 0.88 / C4 0.85 of the HBM copy rate vs 0.82 / 0.83 for the CTA-synchronous
+  // one with float32 math; HG_MATH_EXACT 0.74-0.81 vs 0.65).  HG_R2H_WS=0 / HG_R2H_EXACT_SYNC=1 select the
+  // CTA-synchronous kernel for A/B runs.
   if (math != HG_MATH_EXACT && ws_warps == 16) return launch_ws<float, float, false, 4, 16>(src, dst, xs, ys, planes, h, w, h1, w1, BW, BH, st);
   if (math != HG_MATH_EXACT && ws_warps) return launch_ws<float, float, false, 4, 8>(src, dst, xs, ys, planes, h, w, h1, w1, BW, BH, st);
+  if (math == HG_MATH_EXACT && ws_warps && !exact_sync_env()) return launch_ws<float, float, true, 4, 8>(src, dst, xs, ys, planes, h, w, h1, w1, BW, BH, st);
   if (math == HG_MATH_EXACT)
     return RW == 8 ? launch_tma<float, float, true, 8>(src, dst, xs, ys, planes, h, w, h1, w1, BW, BH, st)
                    : launch_tma<float, float, true, 4>(src, dst, xs, ys, planes, h, w, h1, w1, BW, BH, st);
