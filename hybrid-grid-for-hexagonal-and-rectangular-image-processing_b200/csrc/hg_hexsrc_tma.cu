@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(kHsThreads, 2)
 hexsrc_linear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __restrict__ dst, const double* __restrict__ xs,
                          const double* __restrict__ ys, int h, int w, int h1, int w1, int planes, int tiles_x, int tiles_y,
                          long long total_items, long long items_per_cta, int BW, int BH, int stage_bytes, double ci, double cj,
-                         double hx, double wy, int col_major) {
+                         double hx, double wy, int col_major, int R, int groups) {
   using WT = typename std::conditional<EXACT, double, float>::type;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kHsStages * stage_bytes);
@@ -74,18 +74,37 @@ hexsrc_linear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __restric
   // at once, was measured and rejected: C4 0.73 -> 0.71, C2 0.88 -> 0.69 -- DRAM page locality of consecutive row
   // segments matters more than the halo; HG_HEXSRC_ORDER=1 keeps it for A/B runs.)  A CTA's items are
   // consecutive, so positions advance by carries.
-  struct Pos { int grp, tx, ty; };
+  struct Pos { int grp, tx, ty, blk, sub; };
+  // Items run in blocks of R plane groups: inside a block the R groups of one tile position are consecutive, so a
+  // thread evaluates the (plane independent) geometry of its samples once per position and re-uses it R times.
+  const int full_blocks = groups / R, tail = groups - full_blocks * R;
   auto decode = [&](long long g) {
     Pos q;
-    q.grp = (int)(g / npos);
-    const int pos = (int)(g - (long long)q.grp * npos);
+    const long long per_block = (long long)R * npos;
+    int rb, pos;
+    if (g < (long long)full_blocks * per_block) {
+      q.blk = (int)(g / per_block); rb = R;
+      const int rem = (int)(g - (long long)q.blk * per_block);
+      pos = rem / R; q.sub = rem - pos * R;
+    } else {
+      q.blk = full_blocks; rb = tail;
+      const int rem = (int)(g - (long long)full_blocks * per_block);
+      pos = rem / rb; q.sub = rem - pos * rb;
+    }
+    q.grp = q.blk * R + q.sub;
     if (col_major) { q.tx = pos / tiles_y; q.ty = pos - q.tx * tiles_y; }
     else { q.ty = pos / tiles_x; q.tx = pos - q.ty * tiles_x; }
     return q;
   };
   auto advance = [&](Pos& q) {
-    if (col_major) { if (++q.ty == tiles_y) { q.ty = 0; if (++q.tx == tiles_x) { q.tx = 0; ++q.grp; } } }
-    else if (++q.tx == tiles_x) { q.tx = 0; if (++q.ty == tiles_y) { q.ty = 0; ++q.grp; } }
+    const int rb = q.blk < full_blocks ? R : tail;
+    if (++q.sub < rb) { ++q.grp; return; }
+    q.sub = 0;
+    bool wrapped = false;
+    if (col_major) { if (++q.ty == tiles_y) { q.ty = 0; if (++q.tx == tiles_x) { q.tx = 0; wrapped = true; } } }
+    else if (++q.tx == tiles_x) { q.tx = 0; if (++q.ty == tiles_y) { q.ty = 0; wrapped = true; } }
+    if (wrapped) ++q.blk;
+    q.grp = q.blk * R;
   };
   auto origin = [&](int tx, int ty, int& row0, int& col0) {
     row0 = trunc_i32(dadd(xs[ty * kHsTH], ci));
@@ -128,6 +147,8 @@ hexsrc_linear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __restric
   const int n_items = (int)(g_end - g_begin);
   int s = 0;
   uint32_t parity = 0;
+  int o1[kHsRW][4], oB[kHsRW][4], o4[kHsRW][4];
+  WT wa[kHsRW][4], wb[kHsRW][4], wc[kHsRW][4];
   for (int k = 0; k < n_items; ++k) {
     const HsTables& T = tabs[k & 1];
     if (k + 1 < n_items) build_tables(nxt, tabs[(k + 1) & 1]);
@@ -136,9 +157,8 @@ hexsrc_linear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __restric
     const int nrows = min(kHsRW, T.nrows - warp * kHsRW);
     const int row0 = T.row0, col0 = T.col0;
 
-    // geometry of this thread's samples (plane independent)
-    int o1[kHsRW][4], oB[kHsRW][4], o4[kHsRW][4];
-    WT wa[kHsRW][4], wb[kHsRW][4], wc[kHsRW][4];
+    // geometry of this thread's samples (plane independent): evaluated for the first group of a tile position
+    if (k == 0 || cur.sub == 0) {
 #pragma unroll
     for (int r = 0; r < kHsRW; ++r) {
       const int rl = warp * kHsRW + r;
@@ -170,6 +190,7 @@ hexsrc_linear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __restric
         oB[r][c] = f ? p4 - 1 : p1 + 1;                               // P2 (i_n+1, j_n) or P3 (i_n, j_n+1)
         o4[r][c] = p4;
       }
+    }
     }
     ptx::mbar_wait(&full[s], parity);
     const float* __restrict__ t = reinterpret_cast<const float*>(smem_raw + (size_t)s * stage_bytes);
@@ -273,12 +294,21 @@ int try_hexsrc_linear_tma(const void* src, void* dst, const double* xs, const do
   const double hx = (h - 1) / 2.0, wy = (w - 0.5) / 2.0;     // python-float expressions of geometry_np.py:326-331
   static const int order_env = [] { const char* e = getenv("HG_HEXSRC_ORDER"); return e ? atoi(e) : -1; }();   // A/B: 0 row-, 1 column-major
   const int col_major = order_env > 0 ? 1 : 0;
+  // plane groups that share one geometry evaluation (consecutive items of a CTA): more re-use of the float64 / index
+  // arithmetic against a longer L2 re-use distance of the tile halos (measured)
+  static const int share_env = [] { const char* e = getenv("HG_HEXSRC_SHARE"); return e ? atoi(e) : 0; }();
+  // measured on B200 (C4 / C2, fraction of the HBM copy rate): float32 weights R = 1: 0.70 / 0.88, R = 2: 0.85 / 0.83,
+  // R = 4: 0.75 / 0.75 -- sharing pays when a row of tiles is so long that the halo rows leave L2 anyway (4K images);
+  // float64 weights (exact): R = 1: 0.28, 2: 0.41, 4: 0.52, 8: 0.61 -- bound by the fp64 pipe, so share as much as possible.
+  const long long halo_footprint = (long long)tiles_x * stage_bytes * grid;        // bytes staged between two vertically adjacent tiles
+  int R = share_env > 0 ? share_env : (math == HG_MATH_EXACT ? 8 : (halo_footprint > (100ll << 20) ? 2 : 1));
+  if (R > (int)groups) R = (int)groups;
   if (variant == 0)
-    hexsrc_linear_tma_kernel<float, false><<<(unsigned)grid, kHsThreads, smem, st>>>(tmap, (float*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, (int)planes, tiles_x, tiles_y, total, per, BW, BH, stage_bytes, ci, cj, hx, wy, col_major);
+    hexsrc_linear_tma_kernel<float, false><<<(unsigned)grid, kHsThreads, smem, st>>>(tmap, (float*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, (int)planes, tiles_x, tiles_y, total, per, BW, BH, stage_bytes, ci, cj, hx, wy, col_major, R, (int)groups);
   else if (variant == 1)
-    hexsrc_linear_tma_kernel<float, true><<<(unsigned)grid, kHsThreads, smem, st>>>(tmap, (float*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, (int)planes, tiles_x, tiles_y, total, per, BW, BH, stage_bytes, ci, cj, hx, wy, col_major);
+    hexsrc_linear_tma_kernel<float, true><<<(unsigned)grid, kHsThreads, smem, st>>>(tmap, (float*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, (int)planes, tiles_x, tiles_y, total, per, BW, BH, stage_bytes, ci, cj, hx, wy, col_major, R, (int)groups);
   else
-    hexsrc_linear_tma_kernel<double, true><<<(unsigned)grid, kHsThreads, smem, st>>>(tmap, (double*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, (int)planes, tiles_x, tiles_y, total, per, BW, BH, stage_bytes, ci, cj, hx, wy, col_major);
+    hexsrc_linear_tma_kernel<double, true><<<(unsigned)grid, kHsThreads, smem, st>>>(tmap, (double*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, (int)planes, tiles_x, tiles_y, total, per, BW, BH, stage_bytes, ci, cj, hx, wy, col_major, R, (int)groups);
   return finish_launch("hexsrc_linear_tma");
 }
 
