@@ -470,3 +470,69 @@ def test_hexconv_autocast_rgb_first_layer(hf):
     assert conv.kernel.grad.shape == wr.grad.shape
     assert float((conv.kernel.grad.cpu() - wr.grad).abs().max()) <= 2e-2 * float(wr.grad.abs().max())
     assert float((conv.bias.grad.cpu() - br.grad).abs().max()) <= 2e-2 * float(br.grad.abs().max())
+
+
+def _pool_fuzz(n, seed):
+    rng = np.random.default_rng(seed)
+    return [(int(rng.integers(1, 4)), int(rng.integers(1, 5)), int(rng.integers(2, 70)), int(rng.integers(3, 300)),
+             ("max", "min", "average")[int(rng.integers(0, 3))]) for _ in range(n)]
+
+
+@pytest.mark.parametrize("case", _pool_fuzz(16, 7))
+def test_hexpool_2x2_shape_fuzz(hf, case):
+    """Random shapes through HexPool2d(method, 2, 2): float4 kernels (W % 4 == 0), any-width kernels, odd heights, widths
+    below / across the 128-column segments; forward bit-exact (max / min), backward against the oracle."""
+    B, C_, H, W, method = case
+    torch.manual_seed(B * 7919 + H * 31 + W)
+    x = torch.randn(B, C_, H, W)
+    x[torch.rand_like(x) < 0.1] = float("nan")
+    xr = x.clone().requires_grad_()
+    ref = HO.hexpool2d(xr, method, 2, 2)
+    xg = x.cuda().requires_grad_()
+    y = hf.HexPool2d(method, 2, 2)(xg)
+    assert y.shape == ref.shape
+    if method == "average":
+        np.testing.assert_allclose(y.detach().cpu().numpy(), ref.detach().numpy(), equal_nan=True, rtol=1e-6, atol=1e-7)
+    else:
+        assert np.array_equal(y.detach().cpu().numpy(), ref.detach().numpy(), equal_nan=True)
+    if ref.numel():
+        g = torch.randn(ref.shape)
+        (torch.nan_to_num(ref) * g).sum().backward()
+        (torch.nan_to_num(y) * g.cuda()).sum().backward()
+        np.testing.assert_allclose(xg.grad.cpu().numpy(), xr.grad.numpy(), rtol=1e-6, atol=1e-7)
+
+
+def _conv_fuzz(n, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        cin, cout = int(rng.integers(1, 9)) * 16, int(rng.integers(1, 9)) * 16
+        out.append((int(rng.integers(1, 3)), cin, cout, int(rng.integers(3, 70)), int(rng.integers(8, 300)),
+                    int(rng.integers(0, 3)), int(rng.integers(0, 2))))
+    return out
+
+
+@pytest.mark.parametrize("case", _conv_fuzz(10, 11))
+def test_hexconv_tcgen05_shape_fuzz(hf, case):
+    """Random channel counts (multiples of 16 up to 128: one pass, several reduction passes, wgrad channel slices, M = 64 and
+    M = 128 weight-gradient tiles), sizes, paddings and parities through the forced tcgen05 path, bf16-exact operands."""
+    N, Cin, Cout, H, W, pad, off = case
+    torch.manual_seed(Cin * 131 + Cout * 17 + H)
+    xq = torch.randn(N, Cin, H, W).bfloat16().float()
+    wq = (torch.randn(Cout, Cin, 1, 7) * 0.1).bfloat16().float()
+    b = torch.randn(Cout)
+    xr, wr, br = xq.clone().requires_grad_(), wq.clone().requires_grad_(), b.clone().requires_grad_()
+    try:
+        ref = HO.hexconv2d(xr, wr, br, off, 2, 1, pad, 1, 1)
+    except Exception:
+        pytest.skip("shape too small for this kernel in the reference")
+    gyq = torch.randn_like(ref).bfloat16().float()
+    (ref * gyq).sum().backward()
+    xg, wg, bg = xq.cuda().requires_grad_(), wq.cuda().requires_grad_(), b.cuda().requires_grad_()
+    y = hf.hexconv2d(xg, wg, bg, off, 2, 1, pad, 1, 1, algo=2)
+    assert y.shape == ref.shape
+    assert float((y.detach().cpu() - ref.detach()).abs().max()) <= 1e-4 * float(ref.detach().abs().max())
+    (y * gyq.cuda()).sum().backward()
+    assert float((xg.grad.cpu() - xr.grad).abs().max()) <= 1e-4 * float(xr.grad.abs().max())
+    assert float((wg.grad.cpu() - wr.grad).abs().max()) <= 1e-3 * float(wr.grad.abs().max())
+    assert float((bg.grad.cpu() - br.grad).abs().max()) <= 1e-3 * float(br.grad.abs().max())

@@ -346,3 +346,41 @@ def test_host_entry_points(Fn):
                    else O.hex_to_rect_resample(src, (h1, w1), "linear"))
             same(d.numpy(), ref)
     nv.lib().hg_host_release()
+
+
+# ------------------------------------------------------------------------------------------------
+# seeded shape fuzz over every resampling kernel family (TMA tiles, direct gathers, exact / fast math)
+# ------------------------------------------------------------------------------------------------
+def _fuzz_cases(n, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        planes = int(rng.integers(1, 8))
+        h = int(rng.integers(2, 90))
+        w = int(rng.integers(1, 40)) * 4 if rng.random() < 0.7 else int(rng.integers(2, 150))   # 16-byte rows: TMA tiles
+        fy, fx = rng.uniform(0.4, 2.5, 2)
+        out.append((planes, h, w, max(1, int(round(h * fy))), max(1, int(round(w * fx)))))
+    return out
+
+
+@pytest.mark.parametrize("case", _fuzz_cases(24, 2024))
+def test_resample_shape_fuzz(Fn, case):
+    planes, h, w, h1, w1 = case
+    rng = np.random.default_rng(planes * 1000003 + h * 1009 + w)
+    img = (rng.random((planes, h, w)) * 255).astype(np.float32)
+    x = cu(img)
+    full = lambda a: np.asarray(a).reshape(planes, h1, w1)
+    # R1 rect -> hex
+    r_bil = full(O.rect_to_hex_resample(img, (h1, w1), "bilinear"))
+    same(Fn.rect_to_hex(x, (h1, w1), "bilinear"), r_bil)                                        # exact: bit-identical float64
+    close(Fn.rect_to_hex(x, (h1, w1), "bilinear", out_dtype=torch.float32, math="fast"), r_bil, 255.0)
+    if h > 1 and w > 1:
+        same(Fn.rect_to_hex(x, (h1, w1), "nearest"), full(O.rect_to_hex_resample(img, (h1, w1), "nearest")))
+    # R2 / R4 hex -> rect, hexresize
+    h_lin = full(O.hex_to_rect_resample(img, (h1, w1), "linear", twin="np"))
+    same(Fn.hex_to_rect(x, (h1, w1), "linear", twin="np"), h_lin)
+    close(Fn.hex_to_rect(x, (h1, w1), "linear", out_dtype=torch.float32, math="fast", twin="np"), h_lin, 255.0)
+    same(Fn.hex_to_rect(x, (h1, w1), "nearest", twin="np"), full(O.hex_to_rect_resample(img, (h1, w1), "nearest", twin="np")))
+    z_lin = full(O.hexresize(img, (h1, w1), "linear"))
+    same(Fn.hex_resize(x, (h1, w1), "linear"), z_lin)
+    close(Fn.hex_resize(x, (h1, w1), "linear", out_dtype=torch.float32, math="fast"), z_lin, 255.0)
