@@ -26,6 +26,7 @@ if has conv; then timeout 900 python tools/bench_conv.py --reps 10 > $OUT/bench_
 if has conv; then timeout 600 python tools/bench_c3.py > $OUT/bench_c3.json 2>&1; echo "bench_c3 rc=$?"; tail -1 $OUT/bench_c3.json | cut -c1-300; fi
 if has cnn; then
   timeout 300 python tools/hexcnn_ddp.py --batch 64 --steps 10 --autocast > $OUT/hexcnn_autocast.log 2>&1; echo "hexcnn(autocast) rc=$?"; tail -1 $OUT/hexcnn_autocast.log
+  timeout 300 python tools/hexcnn_ddp.py --batch 64 --steps 20 --autocast --graph > $OUT/hexcnn_autocast_graph.log 2>&1; echo "hexcnn(autocast, CUDA graph) rc=$?"; tail -1 $OUT/hexcnn_autocast_graph.log
   timeout 300 python tools/hexcnn_ddp.py --batch 64 --steps 10 > $OUT/hexcnn_fp32.log 2>&1; echo "hexcnn(fp32) rc=$?"; tail -1 $OUT/hexcnn_fp32.log
 fi
 if has ncu; then   # launch list of the bench + one --set full capture per dominant kernel, each after its plain run exited 0
