@@ -124,6 +124,12 @@ def main():
                           "library_launches_per_step": nv.launch_count() // a.steps, "autocast": a.autocast,
                           "cuda_graph": a.graph}), flush=True)
     if world > 1:
+        if a.graph:
+            # tearing the process group down while a captured graph still holds NCCL kernels hung the run on 8 GPUs
+            # (the result line above had been printed): drop the graph first and leave without the collective teardown
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 
