@@ -1,0 +1,75 @@
+"""Live cross-check of the oracle against the UNMODIFIED reference on seeded random shapes (build container only).
+
+    python tests/golden/live_check.py        # exit code 0 = every comparison passed
+
+Run as its own process (tests/test_oracle_live_reference.py does that): the reference package is called ``HyGrid`` like
+ours, so it must not share ``sys.modules`` with the other tests.  Wider than the committed golden vectors: every case
+here is a fresh shape / scale factor / dtype.  float64 results are compared with ``==``.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import make_golden as MG  # noqa: E402
+
+
+def main():
+    gnp, gt, hf, IMAGE, HEXIMAGE = MG.load_reference()
+    from oracle import hygrid_oracle as O
+    from oracle import hexframes_oracle as HO
+    rng = np.random.default_rng(4711)
+    checked = 0
+
+    def eq(a, b, what):
+        nonlocal checked
+        a, b = np.asarray(a), np.asarray(b)
+        assert a.shape == b.shape and a.dtype == b.dtype, (what, a.shape, b.shape, a.dtype, b.dtype)
+        assert np.array_equal(a, b, equal_nan=True), (what, float(np.nanmax(np.abs(a.astype(np.float64) - b))))
+        checked += 1
+
+    for _ in range(30):
+        c, h, w = int(rng.integers(1, 5)), int(rng.integers(2, 70)), int(rng.integers(2, 90))
+        h1, w1 = max(2, int(h * rng.uniform(0.4, 2.4))), max(2, int(w * rng.uniform(0.4, 2.4)))
+        dt = ("u8", "f32", "f64")[int(rng.integers(0, 3))]
+        img = MG.rand_img(rng, (c, h, w), dt)
+        if c == 1:
+            continue                                   # the reference squeezes single-band results; covered by the goldens
+        for interp in ("nearest", "bilinear"):
+            eq(O.rect_to_hex_resample(img, (h1, w1), interp), gnp.rect_to_hex_resample(img.copy(), (h1, w1), interp), f"R1 {interp} {img.shape}->{h1, w1} {dt}")
+        eq(O.hex_to_rect_resample(img, (h1, w1), "linear", twin="np"), gnp.hex_to_rect_resample(img.copy(), (h1, w1), "linear"), f"R2 np {img.shape}")
+        eq(O.hexresize(img, (h1, w1), "linear"), gnp.hexresize(img.copy(), (h1, w1), "linear"), f"R4 {img.shape}")
+        for interp in ("nearest", "linear"):
+            eq(O.hex_to_rect_resample(img, (h1, w1), interp, twin="torch"), gt.hex_to_square_resample(img.copy(), (h1, w1), interp), f"R2 torch {interp} {img.shape}")
+
+    torch.manual_seed(4711)
+    for _ in range(12):
+        N, Cin, Cout = int(rng.integers(1, 3)), int(rng.integers(1, 6)), int(rng.integers(1, 6))
+        H, W = int(rng.integers(6, 20)), int(rng.integers(6, 20))
+        r, s_, d, pad, off = int(rng.integers(2, 4)), int(rng.integers(1, 3)), int(rng.integers(1, 3)), int(rng.integers(0, 3)), int(rng.integers(0, 2))
+        try:
+            m = hf.HexConv2d(Cin, Cout, off, r, stride=s_, padding=pad, dilation=d)
+            x = torch.randn(N, Cin, H, W)
+            yr = m(x)
+        except Exception:
+            continue                                   # shape too small for this kernel in the reference
+        yo = HO.hexconv2d(x, m.kernel.detach(), m.bias.detach(), off, r, s_, pad, d, 1)
+        assert yo.shape == yr.shape and float((yo - yr.detach()).abs().max()) <= 1e-5 * max(1.0, float(yr.abs().max())), "C1"
+        checked += 1
+    for _ in range(12):
+        B, C_, H, W = int(rng.integers(1, 3)), int(rng.integers(1, 4)), int(rng.integers(4, 24)), int(rng.integers(5, 30))
+        method = ("max", "min", "average")[int(rng.integers(0, 3))]
+        x = torch.randn(B, C_, H, W)
+        yr = hf.HexPool2d(method, 2, 2)(x)
+        yo = HO.hexpool2d(x, method, 2, 2)
+        assert yo.shape == yr.shape and torch.allclose(yo, yr, atol=1e-6, equal_nan=True), "P1"
+        checked += 1
+    print(f"live reference check ok: {checked} comparisons")
+
+
+if __name__ == "__main__":
+    main()
