@@ -46,6 +46,22 @@ def main():
         for interp in ("nearest", "linear"):
             eq(O.hex_to_rect_resample(img, (h1, w1), interp, twin="torch"), gt.hex_to_square_resample(img.copy(), (h1, w1), interp), f"R2 torch {interp} {img.shape}")
 
+    # R3 hex -> hex affine warp (numpy twin, float64 inverse map) and R5 doubled rasters
+    for _ in range(10):
+        c, h, w = int(rng.integers(2, 4)), int(rng.integers(6, 40)), int(rng.integers(6, 40))
+        img = MG.rand_img(rng, (c, h, w), "f64")
+        ang, sc = rng.uniform(-0.5, 0.5), rng.uniform(0.6, 1.6)
+        Hm = np.array([[sc * np.cos(ang), -sc * np.sin(ang), rng.uniform(-3, 3)],
+                       [sc * np.sin(ang), sc * np.cos(ang), rng.uniform(-3, 3)], [0, 0, 1.0]])
+        eq(O.hex_warp(img, Hm, "linear", twin="np"), gnp.image_geometric_transformation(img.copy(), Hm, "linear"), f"R3 linear {img.shape}")
+        hx = HEXIMAGE(data=img.copy(), even_odd_offset=bool(rng.integers(0, 2)))
+        t1, _ = hx.GenerateType1Image()
+        t2, _ = hx.GenerateType2Image()
+        eq(O.hex_to_type1(img, int(hx.even_odd_offset)), t1, "R5 type1")
+        eq(O.hex_to_type2(img, int(hx.even_odd_offset)), t2, "R5 type2")
+        eq(O.type1_to_hex(t1), HEXIMAGE(data=t1.copy(), heximagetype=1).HexagonImage, "R5 decode1")
+        eq(O.type2_to_hex(t2), HEXIMAGE(data=t2.copy(), heximagetype=2).HexagonImage, "R5 decode2")
+
     torch.manual_seed(4711)
     for _ in range(12):
         N, Cin, Cout = int(rng.integers(1, 3)), int(rng.integers(1, 6)), int(rng.integers(1, 6))
