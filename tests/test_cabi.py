@@ -56,6 +56,37 @@ def test_version_and_error_string():
         nv.call("hg_type_to_hex", None, None, 1, 4, 9, 3, nv.F32, nv.F32, None)
 
 
+def test_argument_validation_without_a_gpu():
+    """Every entry point validates its arguments before the first CUDA call and leaves a message in hg_last_error():
+    error codes are part of the ABI (HG_E_ARG -1, HG_E_DTYPE -2, HG_E_SHAPE -3, HG_E_UNSUPPORTED -4), and empty
+    inputs are a successful no-op."""
+    L = nv.lib()
+    err = lambda: L.hg_last_error().decode()
+    # resampling: empty batch / empty output is fine, bad math mode and bad shapes are not
+    assert L.hg_rect2hex_bilinear(None, None, None, None, None, None, 0, 8, 8, 8, 8, nv.F32, nv.F32, 0, None) == 0
+    assert L.hg_hex2rect_linear(None, None, None, None, None, None, 3, 8, 8, 0, 8, nv.F32, nv.F32, 0, None) == 0
+    assert L.hg_rect2hex_bilinear(None, None, None, None, None, None, 1, 8, 8, 8, 8, nv.F32, nv.F32, 7, None) == -1 and "math" in err()
+    assert L.hg_hex2rect_nearest(None, None, None, None, 1, -2, 8, 8, 8, 4, None) == -3
+    # pooling: unknown method, window leaving the image (the reference raises IndexError there)
+    assert L.hg_hexpool_fwd(None, None, None, 1, 1, 8, 8, 4, 3, 2, 2, 2, 2, 2, 0, 0.0, 0, 0, 0.0, 9, nv.F32, None) == -1
+    rc = L.hg_hexpool_fwd(None, None, None, 1, 1, 8, 8, 8, 7, 2, 2, 1, 1, 1, 0, 0.0, 0, 0, 0.0, nv.POOL_MAX, nv.F32, None)
+    assert rc == -3 and "leaves the image" in err()
+    assert L.hg_hexpool_fwd(None, None, None, 1, 0, 8, 8, 4, 3, 2, 2, 2, 2, 2, 0, 0.0, 0, 0, 0.0, nv.POOL_MAX, nv.F32, None) == 0
+    # convolution descriptor checks
+    bad = nv.ConvDesc(1, 4, 4, 8, 8, 9, 8, 2, 1, 1, 1, 1, 1, 0.0, nv.F32, nv.F32, 0, 0)  # wrong Ho
+    assert L.hg_hexconv_dgrad(C.byref(bad), None, None, None, None) == -3 and "output shape" in err()
+    bad = nv.ConvDesc(1, 4, 6, 8, 8, 8, 8, 2, 1, 1, 4, 1, 1, 0.0, nv.F32, nv.F32, 0, 0)  # out_channels % groups
+    assert L.hg_hexconv_wgrad(C.byref(bad), None, None, None, None, None) == -1
+    bad = nv.ConvDesc(1, 4, 4, 8, 8, 8, 8, 2, 1, 1, 1, 1, 1, 0.0, nv.F32, nv.F32, 2, 0)   # tcgen05 forced on 4 channels
+    assert L.hg_hexconv_dgrad(C.byref(bad), None, None, None, None) == -4 and "tcgen05" in err()
+    assert L.hg_hexconv_umma_eligible(C.byref(bad), 0) == 0
+    # layout / padding / batch norm
+    assert L.hg_pad2d(None, None, 1, 4, 4, 1, 1, 1, 1, 9, 0.0, nv.F32, None) == -1
+    assert L.hg_pad2d(None, None, 1, 4, 4, 4, 0, 0, 0, 1, 0.0, nv.F32, None) == -3 and "reflect" in err()
+    assert L.hg_bn_stats(None, None, 0, 4, 16, None) == -3
+    assert L.hg_bn_apply(None, None, None, None, None, None, None, None, None, None, 2, 4, 16, C.c_float(1e-5), 0, None) == -1
+
+
 def test_conv_out_shape_matches_oracle():
     from oracle import hexframes_oracle as HO
     L = nv.lib()
