@@ -11,13 +11,13 @@
 // serves all 7 taps of the three gy rows that touch it.  The 7 accumulators (7 x Cin fp32 columns) plus a
 // 16-column bias accumulator (B = a block of ones) live in TMEM for the whole kernel; each persistent CTA
 // reduces its share of (image, row band, column tile) items and adds its partial to gw / gb with one
-// round of fp32 atomics at the end.  UMMA M is 128: rows 64..127 of the A view run past the Cout = 64
-// channel groups into the neighbouring ring memory; those accumulator lanes are never read.
+// round of fp32 atomics at the end.  UMMA M is 64 for Cout <= 64 (the kernel is shared-memory-bandwidth bound and an
+// M = 128 view would read the neighbouring ring slots as its upper half: 4 KB of A per MMA instead of 2 KB) and
+// 128 for 64 < Cout <= 128; rows past Cout hold whatever the neighbouring ring memory holds and are never read.
 //
 // CTA = 15 warps: warps 0-11 converters (x rows and gy rows -> bf16 -> rings; warps 8-11 also run the final
 // epilogue), warps 12 and 14 MMA issuers (taps 0-3 / taps 4-6 + bias: disjoint accumulators, so the two
-// instruction streams need no ordering; ncu r1z: one issuing warp was the pacemaker of the pipeline while the
-// tensor pipe was 46 % busy), warp 12 also allocates TMEM, warp 13 TMA producer.  Input path as in hg_conv_umma.cu:
+// instruction streams need no ordering), warp 12 also allocates TMEM, warp 13 TMA producer.  Input path as in hg_conv_umma.cu:
 //   TMA : 4-D boxes [C][1 row][px] of x and gy land in a shared raw staging ring (zero-fill of halos and of the
 //         columns past Wo for free); needs pad_value == 0 and 16-byte aligned rows of both tensors.
 //   LDG : coalesced global loads (any pad value / width).
