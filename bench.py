@@ -137,6 +137,21 @@ def _cpu_one(args):
     return dt, float(out[0, h1 // 2, w1 // 2])
 
 
+def host_info():
+    """CPU model and library versions next to every CPU number."""
+    model = "unknown"
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    model = line.split(":", 1)[1].strip()
+                    break
+    except Exception:
+        pass
+    import numpy as np
+    return {"cpu_model": model, "os_cpu_count": os.cpu_count(), "numpy": np.__version__}
+
+
 def cpu_baseline(wl, images=8):
     """Single-process numpy port on `images` images of the workload (about 5-30 s of CPU work)."""
     _, c, h, w, h1, w1 = WORKLOADS[wl]
@@ -147,7 +162,7 @@ def cpu_baseline(wl, images=8):
     inner = images * h1 * w1 / dt / 1e6
     return {"value": inner, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"{images} images of {c}x{h}x{w} float32 -> {h1}x{w1}, oracle/hygrid_oracle.rect_to_hex_resample "
-                      f"(numpy restatement of geometry_np.py:358-519), single process, {dt:.1f} s"}
+                      f"(numpy restatement of geometry_np.py:358-519), single process, {dt:.1f} s", "host": host_info()}
 
 
 def run_reference(args):
@@ -176,7 +191,7 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(wl), "sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "host": host_info()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
