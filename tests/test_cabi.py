@@ -110,3 +110,34 @@ def test_no_cpu_fallback():
     from HyGrid import functional as Fn
     with pytest.raises(nv.HyGridNativeError):
         Fn.rect_to_hex(torch.zeros(1, 4, 4), None, "bilinear")
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Arity and scalar/pointer kind of every ctypes signature agree with the prototype in include/hygrid_b200.h
+    (a drifted table would pass garbage through the C ABI without any error)."""
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    protos = re.findall(r"\b(hg_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
+    assert len(protos) >= 30
+    scalars = {"int": C.c_int, "int64_t": C.c_int64, "double": C.c_double, "float": C.c_float}
+    checked = 0
+    for name, args in protos:
+        if name not in nv._SIGS:
+            continue
+        kinds = []
+        for a in args.split(","):
+            a = " ".join(a.split())
+            if a == "void":
+                continue
+            if "*" in a or "hg_stream_t" in a:
+                kinds.append("ptr")
+            else:
+                kinds.append(scalars[a.replace("const ", "").rsplit(" ", 1)[0]])
+        sig = nv._SIGS[name]
+        assert len(sig) == len(kinds), (name, len(sig), len(kinds))
+        for i, (s, k) in enumerate(zip(sig, kinds)):
+            is_ptr = s is C.c_void_p or (isinstance(s, type) and issubclass(s, C._Pointer))
+            assert (k == "ptr") == is_ptr and (k == "ptr" or s is k), (name, i, s, k)
+        checked += 1
+    assert checked == len(nv._SIGS)
