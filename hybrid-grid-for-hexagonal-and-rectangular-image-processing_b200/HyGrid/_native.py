@@ -107,8 +107,16 @@ def query(name, *args) -> int:
 
 
 def call(name, *args):
+    """Run one entry point; a non-zero status becomes an exception carrying hg_last_error().
+    When the stream argument (always last) belongs to another device than the current one, the call is made with
+    that device current, so tensors on ``cuda:1`` work from a process whose current device is ``cuda:0``."""
     L = lib()
-    rc = getattr(L, name)(*args)
+    st = args[-1] if args else None
+    if isinstance(st, StreamArg) and st.device_index != torch.cuda.current_device():
+        with torch.cuda.device(st.device_index):
+            rc = getattr(L, name)(*args)
+    else:
+        rc = getattr(L, name)(*args)
     if rc != 0:
         raise HyGridNativeError(f"{name} failed with code {rc}: {L.hg_last_error().decode()}")
 
@@ -141,8 +149,16 @@ def ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+class StreamArg(C.c_void_p):
+    """cudaStream_t handle that remembers which device it belongs to (see ``call``)."""
+    device_index = -1
+
+
 def stream_ptr(device=None):
-    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    s = torch.cuda.current_stream(device)
+    arg = StreamArg(s.cuda_stream)
+    arg.device_index = int(s.device_index)
+    return arg
 
 
 def require_cuda(t: torch.Tensor, what="tensor"):

@@ -72,6 +72,18 @@ def _planes(x):
     return x, planes, h, w
 
 
+def _result(out, shape, dtype, like):
+    """The result buffer: a fresh one, or the caller's ``out`` after checking that the kernel may write it."""
+    if out is None:
+        return torch.empty(shape, dtype=dtype, device=like.device)
+    if tuple(out.shape) != tuple(shape) or out.device != like.device or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous {tuple(shape)} tensor on {like.device}, "
+                         f"got {tuple(out.shape)} on {out.device} (contiguous={out.is_contiguous()})")
+    if dtype is not None and out.dtype != dtype:
+        raise TypeError(f"out must have dtype {dtype}, got {out.dtype}")
+    return out
+
+
 def _out_dtype(x, out_dtype):
     if out_dtype is None:   # numpy promotion of float64 weights with the image dtype
         return torch.float64
@@ -96,11 +108,11 @@ def rect_to_hex(x: torch.Tensor, hex_dsize=None, interpolation="nearest", out_dt
     shape = x.shape[:-2] + (h1, w1)
     st = nv.stream_ptr(x.device)
     if method == 0:
-        y = out if out is not None else torch.empty(shape, dtype=x.dtype, device=x.device)
+        y = _result(out, shape, x.dtype, x)
         nv.call("hg_rect2hex_nearest", nv.ptr(x), nv.ptr(y), nv.ptr(xs), nv.ptr(ys), planes, h, w, h1, w1,
                 x.element_size(), st)
     else:
-        y = out if out is not None else torch.empty(shape, dtype=_out_dtype(x, out_dtype), device=x.device)
+        y = _result(out, shape, _out_dtype(x, out_dtype) if out is None or out_dtype is not None else None, x)
         nv.call("hg_rect2hex_bilinear", nv.ptr(x), nv.ptr(y), nv.ptr(xs), nv.ptr(ys), C.c_void_p(hxs.ctypes.data),
                 C.c_void_p(hys.ctypes.data), planes, h, w, h1, w1,
                 nv.hg_dtype(x.dtype), nv.hg_dtype(y.dtype), _MATH[math], st)
@@ -132,11 +144,11 @@ def _hexsrc(kind, x, dsize, interpolation, out_dtype, math, twin, out):
     shape = x.shape[:-2] + (h1, w1)
     st = nv.stream_ptr(x.device)
     if method == 0:
-        y = out if out is not None else torch.empty(shape, dtype=x.dtype, device=x.device)
+        y = _result(out, shape, x.dtype, x)
         nv.call("hg_hex2rect_nearest", nv.ptr(x), nv.ptr(y), nv.ptr(xs), nv.ptr(ys), planes, h, w, h1, w1,
                 x.element_size(), st)
     else:
-        y = out if out is not None else torch.empty(shape, dtype=_out_dtype(x, out_dtype), device=x.device)
+        y = _result(out, shape, _out_dtype(x, out_dtype) if out is None or out_dtype is not None else None, x)
         nv.call("hg_hex2rect_linear", nv.ptr(x), nv.ptr(y), nv.ptr(xs), nv.ptr(ys), C.c_void_p(hxs.ctypes.data),
                 C.c_void_p(hys.ctypes.data), planes, h, w, h1, w1,
                 nv.hg_dtype(x.dtype), nv.hg_dtype(y.dtype), _MATH[math], st)

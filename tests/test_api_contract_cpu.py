@@ -91,3 +91,27 @@ def test_numpy_entry_points_reject_bad_arguments_before_any_launch():
     if not torch.cuda.is_available():                          # the padding runs on the device: no silent CPU fallback
         with pytest.raises((RuntimeError, AssertionError)):
             gnp.heximpad(np.ones((5, 7, 3)), shape=(8, 9))
+
+
+def test_out_buffer_is_validated_before_the_kernel_may_write_it():
+    from HyGrid import functional as Fn
+    like = torch.zeros(2, 3, 4, 5)
+    assert Fn._result(None, (2, 3, 8, 9), torch.float64, like).shape == (2, 3, 8, 9)
+    ok = torch.empty(2, 3, 8, 9)
+    assert Fn._result(ok, (2, 3, 8, 9), None, like) is ok and Fn._result(ok, (2, 3, 8, 9), torch.float32, like) is ok
+    with pytest.raises(ValueError):
+        Fn._result(torch.empty(2, 3, 8, 8), (2, 3, 8, 9), None, like)
+    with pytest.raises(ValueError):
+        Fn._result(torch.empty(2, 3, 9, 8).transpose(2, 3), (2, 3, 8, 9), None, like)
+    with pytest.raises(TypeError):
+        Fn._result(ok, (2, 3, 8, 9), torch.float64, like)
+
+
+def test_stream_argument_carries_its_device_through_ctypes():
+    import ctypes as C
+    from HyGrid import _native as nv
+    st = nv.StreamArg(0x1234)
+    st.device_index = 0
+    assert isinstance(st, C.c_void_p) and st.value == 0x1234
+    L = nv.lib()          # rejected for rows_step before the stream is touched: safe without a GPU
+    assert L.hg_type_to_hex(None, None, 1, 4, 9, 3, nv.F32, nv.F32, st) == -1
