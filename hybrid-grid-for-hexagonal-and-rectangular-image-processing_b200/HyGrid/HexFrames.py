@@ -20,6 +20,7 @@ from typing import Optional
 import torch
 import torch.nn as nn
 from torch import Tensor
+from torch.autograd.function import once_differentiable
 from torch.nn import init
 
 from . import _native as nv
@@ -55,6 +56,7 @@ class _Pad2dFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gy):
         pl, pr, pt, pb, mode, H, W, planes = ctx.meta
         gy = gy.contiguous()
@@ -122,6 +124,7 @@ class _HexConvFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
         radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, relu = ctx.meta
@@ -343,6 +346,7 @@ class _HexPoolFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gy):
         aux, x = ctx.saved_tensors
         kh, kw, sh, sw, shift, pad_, _, _, _, _, hn, wn = ctx.geom
@@ -484,6 +488,7 @@ class _ReduceLastFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gy):
         x, aux = ctx.saved_tensors
         gy = gy.contiguous()
@@ -536,6 +541,7 @@ class _ToTypeFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gy):
         # every cell was written 2 (type1) or 4 (type2) times: the gradient is the sum of its copies.
         # Rarely needed (the converters sit outside the conv path here), so composed from strided views.

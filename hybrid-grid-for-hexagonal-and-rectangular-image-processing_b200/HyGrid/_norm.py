@@ -14,6 +14,7 @@ import ctypes as C
 
 import torch
 import torch.nn as nn
+from torch.autograd.function import once_differentiable
 
 from . import _native as nv
 
@@ -59,6 +60,7 @@ class _BatchNormReluFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dy):
         x, w, b, mean, rstd = ctx.saved_tensors
         training, relu, has_w, has_b = ctx.cfg
