@@ -199,6 +199,13 @@ def warp_lattice(h, w, H, twin="torch"):
         rows = torch.arange(lo0, hi0 + 1, 1).double().numpy()
         cols = torch.arange(lo1, hi1 + 0.5, 1).double().numpy()
         Hi = torch.linalg.inv(Ht).numpy()
+    elif twin == "numba":
+        # legacy HyGrid/geometry.py:208-221: integer-truncated start, and the ROW extent reused for the columns
+        tc = np.matmul(H, np.array(corners).T)
+        lo0, hi0 = tc[0].min(), tc[0].max()
+        rows = np.arange(int(lo0), hi0 + 1, 1.0)
+        cols = np.arange(int(lo0), hi0 + 0.5, 1.0)
+        Hi = np.linalg.inv(H)
     else:
         tc = np.matmul(H, np.array(corners).T)
         rows = np.arange(tc[0].min(), tc[0].max() + 1, 1)
@@ -224,7 +231,8 @@ def _warp_planes(rows, cols, Hi, twin):
 
 def hex_warp(x, H=np.eye(3), interpolation="nearest", out_dtype=None, twin="torch"):
     """``geometry_torch.image_geometric_transformation_gpu`` (geometry_torch.py:7-189, ``twin='torch'``,
-    float32 coordinates) / ``geometry_np.image_geometric_transformation`` (geometry_np.py:6-189).
+    float32 coordinates) / ``geometry_np.image_geometric_transformation`` (geometry_np.py:6-189, ``twin='np'``) /
+    the legacy numba ``geometry.image_geometric_transformation_gpu`` (geometry.py:156-262, ``twin='numba'``).
     Coordinates are inverse-mapped on the host like the reference does; the rest runs on the GPU."""
     method = {"nearest": 0, "linear": 1, "bilinear": 2}[interpolation]
     if method == 2:

@@ -279,6 +279,12 @@ def warp_coords(h, w, H, twin="np"):
         rows = np.arange(lo0, hi0 + 1, 1)
         cols = np.arange(lo1, hi1 + 0.5, 1)
         Hi = np.linalg.inv(H)
+    elif twin == "numba":   # geometry.py:208-221 (np.mgrid with a truncated start; the row extent also spans the columns)
+        tc = np.matmul(H, corners)
+        lo0, hi0 = tc[0].min(), tc[0].max()
+        rows = np.arange(int(lo0), hi0 + 1, 1.0)
+        cols = np.arange(int(lo0), hi0 + 0.5, 1.0)
+        Hi = np.linalg.inv(H)
     else:
         import torch
         Ht = torch.tensor(H).to(torch.float64)
@@ -305,7 +311,7 @@ def hex_warp(img, H=np.eye(3), interpolation="nearest", offset=0, twin="np"):
     c, h, w = img.shape
     X, Y, Hi = warp_coords(h, w, H, twin)
     hom = np.stack([X, Y, np.ones_like(X)], 0)
-    if twin == "np":
+    if twin in ("np", "numba"):
         inv = np.einsum("ij, jkl -> ikl", Hi, hom)
         return hexsrc_resample(img, inv[0], inv[1], method, np.float64)
     import torch
