@@ -14,9 +14,11 @@ Deliberate deviations: ``HexPool2d(stride=None)`` means s
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import math
 from typing import Optional
 
+import numpy as np
 import torch
 import torch.nn as nn
 from torch import Tensor
@@ -27,7 +29,7 @@ from . import _native as nv
 
 __all__ = ["pad", "HexConv2d", "HexConv2dAdaptivePadding", "HexPool2d", "HexAdaptivePool2d", "HexGlobalPool2d",
            "heximage_to_type1", "heximage_to_type2", "type1_to_heximage", "max_pooling", "min_pooling",
-           "average_pooling", "hexconv2d", "hexpool2d"]
+           "average_pooling", "hexconv2d", "hexpool2d", "HexPixelShuffle", "pixel_shuffle_table"]
 
 _PAD_MODES = {"constant": 0, "reflect": 1, "replicate": 2, "circular": 3}
 _POOL = {"max": nv.POOL_MAX, "min": nv.POOL_MIN, "average": nv.POOL_AVG}
@@ -571,3 +573,109 @@ def type1_to_heximage(input: Tensor, even_odd_offset: int):
     """``input[:, :, :, 1::2]`` (HexFrames.py:450-458): a strided view, exactly like the reference."""
     out = input[:, :, :, 1::2]
     return out, even_odd_offset
+
+
+# ------------------------------------------------------------------------------------------------
+# hex pixel shuffle (retired from the reference: "codes in old versions.txt":68-126)
+# ------------------------------------------------------------------------------------------------
+@functools.lru_cache(maxsize=64)
+def pixel_shuffle_table(r: int, H: int, W: int):
+    """Which input element lands in every output cell of ``HexPixelShuffle(r)`` on an ``H x W`` lattice:
+    int64 arrays ``(n, row, col)`` of shape ``(Ho, Wo)`` -- sub-channel block, input row, input column -- ``n = -1``
+    where nothing lands (zero).  Closed form of the reference's slice assignments (old versions :95-126):
+
+    * the doubled canvas has ``r*H + r - 1`` rows and ``r*W + r//2`` hex cells per row; the result is the canvas
+      without its first / last ``r - 1`` rows and ``r//2`` / ``ceil(r/2)`` cells (:85-87, :126);
+    * sub-channel ``n`` enumerates the cells of a radius-``r`` hexagon row by row (row ``i`` of ``2r-1`` holds
+      ``r - t`` cells, ``t = |1 + i - r|``, :101-104, :123);
+    * even input rows ``2a`` write canvas row ``i + 2r*a``, sub-column ``1 + t + 2k + 2r*b`` and its neighbour at
+      ``+1`` (``r`` even) or ``-1`` (``r`` odd); odd input rows ``2a + 1`` the same ``r`` rows and ``r`` sub-columns
+      further (:105-122); only odd sub-columns survive ``type1_to_heximage`` (``[..., 1::2]``, :125);
+    * where two writes meet, the later one (larger ``n``, odd rows after even rows) stays."""
+    Hc, Wc = r * H + r - 1, r * W + r // 2
+    Yc, Xc = np.meshgrid(np.arange(r - 1, Hc - (r - 1)), np.arange(r // 2, Wc - (r + 1) // 2), indexing="ij")
+    starts = np.cumsum([0] + [r - abs(1 + i - r) for i in range(2 * r - 1)])
+    n_out = np.full(Yc.shape, -1, np.int64)
+    row_out, col_out, order = np.zeros_like(n_out), np.zeros_like(n_out), np.full(Yc.shape, -1, np.int64)
+    pair = 1 if r % 2 == 0 else -1
+    for par in (0, 1):
+        i = (Yc - par * r) % (2 * r)
+        ok = (i <= 2 * r - 2) & (Yc - par * r - i >= 0)
+        i = np.minimum(i, 2 * r - 2)
+        t = np.abs(1 + i - r)
+        first = 1 + t + par * r                                   # canvas sub-column of k = 0, b = 0
+        base = (np.where(first % 2 == 1, first, first + pair) - 1) // 2
+        d = Xc - base
+        k, b = d % r, d // r
+        row = 2 * ((Yc - par * r - i) // (2 * r)) + par
+        ok &= (d >= 0) & (k < r - t) & (b < W) & (row < H)
+        n = starts[i] + k
+        take = ok & (2 * n + par > order)
+        n_out[take], row_out[take], col_out[take], order[take] = n[take], row[take], b[take], (2 * n + par)[take]
+    return n_out, row_out, col_out
+
+
+@functools.lru_cache(maxsize=64)
+def _pixel_shuffle_offsets(r, H, W, cout, device):
+    n, row, col = pixel_shuffle_table(r, H, W)
+    off = np.where(n >= 0, n * (cout * H * W) + row * W + col, -1).astype(np.int64)
+    if np.unique(off[off >= 0]).size != int((off >= 0).sum()):
+        raise RuntimeError("hex pixel shuffle table is not injective")       # the scatter adjoint relies on it
+    return torch.from_numpy(np.ascontiguousarray(off.reshape(-1))).to(torch.device(device)), off.shape
+
+
+class _PlaneGatherFn(torch.autograd.Function):
+    """``y[b, c, e] = x[b].flatten()[c*chan_stride + table[e]]`` (0 where ``table[e] < 0``), float32 out."""
+
+    @staticmethod
+    def forward(ctx, x, table, out_hw, chans, chan_stride):
+        x = nv.require_cuda(x, "input").contiguous()
+        B = x.shape[0]
+        batch_stride = x.numel() // B if B else 0
+        y = torch.empty((B, chans) + tuple(out_hw), dtype=torch.float32, device=x.device)
+        nv.call("hg_plane_gather", nv.ptr(x), nv.ptr(y), nv.ptr(table), B, chans, out_hw[0] * out_hw[1], batch_stride,
+                chan_stride, nv.hg_dtype(x.dtype), nv.F32, nv.stream_ptr(x.device))
+        ctx.save_for_backward(table)
+        ctx.meta = (tuple(x.shape), x.dtype, chans, chan_stride, batch_stride, tuple(out_hw))
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        table, = ctx.saved_tensors
+        shape, dtype, chans, chan_stride, batch_stride, out_hw = ctx.meta
+        gy = gy.contiguous().float()
+        gx = torch.zeros(shape, dtype=torch.float32, device=gy.device)
+        nv.call("hg_plane_scatter", nv.ptr(gy), nv.ptr(gx), nv.ptr(table), shape[0], chans, out_hw[0] * out_hw[1],
+                batch_stride, chan_stride, nv.F32, nv.stream_ptr(gy.device))
+        return gx.to(dtype), None, None, None, None
+
+
+class HexPixelShuffle(nn.Module):
+    """Sub-pixel up-sampling on the hex lattice ("codes in old versions.txt":68-126): ``(B, C*r*r, H, W)`` ->
+    ``(B, C, r*H - r + 1, r*W - r + r//2 ... )`` float32, each group of ``r*r`` channels spread over a radius-``r``
+    hexagonal neighbourhood.  The reference needs ``2*(3r^2-3r+1)`` strided assignments into a doubled canvas plus a
+    ``torch.cat`` per sub-channel; here the index rule is evaluated once per shape on the host
+    (``pixel_shuffle_table``) and the shuffle is one gather launch (its adjoint, one scatter launch, in backward).
+    Deviation: ``upscale_factor = 1`` raises (the reference returns an empty tensor from its ``[0:-0]`` crop)."""
+
+    def __init__(self, upscale_factor):
+        super().__init__()
+        if int(upscale_factor) < 2:
+            raise ValueError("upscale_factor must be >= 2")
+        self.upscale_factor = int(upscale_factor)
+
+    def forward(self, input: Tensor) -> Tensor:
+        input = _as4(input)
+        r = self.upscale_factor
+        B, Cin, H, W = input.shape
+        if Cin % (r * r) != 0:
+            raise Exception(f"pixel shuffle needs the channel count ({Cin}) to be a multiple of upscale_factor**2 ({r * r})")
+        if input.dtype not in (torch.float32, torch.float64, torch.bfloat16, torch.uint8):
+            input = input.float()
+        cout = Cin // (r * r)
+        table, out_hw = _pixel_shuffle_offsets(r, H, W, cout, str(input.device))
+        return _PlaneGatherFn.apply(input, table, out_hw, cout, H * W)
+
+    def extra_repr(self):
+        return f"upscale_factor={self.upscale_factor}"

@@ -56,6 +56,8 @@ _SIGS = {
     "hg_type_to_hex": [_p, _p, _l, _l, _l, _i, _i, _i, _p],
     "hg_pad2d": [_p, _p, _l, _l, _l, _i, _i, _i, _i, _i, _d, _i, _p],
     "hg_pad2d_bwd": [_p, _p, _l, _l, _l, _i, _i, _i, _i, _i, _i, _p],
+    "hg_plane_gather": [_p, _p, _p, _l, _l, _l, _l, _l, _i, _i, _p],
+    "hg_plane_scatter": [_p, _p, _p, _l, _l, _l, _l, _l, _i, _p],
     "hg_hexpool_fwd": [_p, _p, _p, _i, _l, _l, _l, _l, _l, _i, _i, _i, _i, _i, _i, _d, _i, _i, _d, _i, _i, _p],
     "hg_hexpool_bwd": [_p, _p, _i, _p, _p, _l, _l, _l, _l, _l, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "hg_hexglobalpool_fwd": [_p, _p, _p, _l, _l, _i, _i, _p],

@@ -146,6 +146,22 @@ int hg_pad2d_bwd(const void* gy, void* gx, int64_t planes, int64_t H, int64_t W,
                  int mode, int dtype, hg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Table-driven plane gather / scatter: rearrangements whose index rule depends on shapes only.
+ * ref: the retired HexPixelShuffle, "HyGrid/codes in old versions.txt":68-126 -- 2*(3r^2-3r+1) strided
+ * slice assignments into a doubled type1 canvas, then [..., 1::2] and a crop; here one pass over a
+ * host-built table of `cells` int64 source offsets (relative to the (batch, channel) base; < 0 = zero):
+ *   gather : dst[b][c][e] = table[e] >= 0 ? src[b*batch_stride + c*chan_stride + table[e]] : 0
+ *   scatter: gsrc[b*batch_stride + c*chan_stride + table[e]] = gdst[b][c][e]   (adjoint of the gather: the table
+ *            must be injective and the caller zero-fills gsrc first)
+ * dst / gdst are dense [batches, chans, cells].  Offsets that leave [0, batches*batch_stride) are skipped.
+ * gather dtypes: {HG_F32, HG_BF16, HG_F64, HG_U8} -> HG_F32, HG_F64 -> HG_F64, HG_BF16 -> HG_BF16;
+ * scatter: HG_F32, HG_F64, HG_BF16. */
+int hg_plane_gather(const void* src, void* dst, const int64_t* table, int64_t batches, int64_t chans, int64_t cells,
+                    int64_t batch_stride, int64_t chan_stride, int src_dtype, int dst_dtype, hg_stream_t stream);
+int hg_plane_scatter(const void* gdst, void* gsrc, const int64_t* table, int64_t batches, int64_t chans, int64_t cells,
+                     int64_t batch_stride, int64_t chan_stride, int dtype, hg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Hex pooling.  ref: HexFrames.py:255-341 HexPool2d, :344-401 HexAdaptivePool2d,
  * :402-414 HexGlobalPool2d, reductions :461-479 (NaN-aware).
  * The virtual input is x [planes,H,W] framed by `pad` cells of pad_value on every side and then

@@ -26,7 +26,7 @@ __all__ = [
     "hex_taps", "hexconv_out_shape", "hexconv2d", "adaptive_padding",
     "hexpool_out_shape", "hexpool2d", "hexadaptivepool2d", "hexglobalpool2d",
     "reduce_max", "reduce_min", "reduce_average",
-    "heximage_to_type1", "heximage_to_type2", "type1_to_heximage",
+    "heximage_to_type1", "heximage_to_type2", "type1_to_heximage", "hex_pixel_shuffle",
 ]
 
 
@@ -217,3 +217,43 @@ def heximage_to_type2(x, even_odd_offset):
 
 def type1_to_heximage(t1, even_odd_offset):
     return t1[:, :, :, 1::2], even_odd_offset
+
+
+# --------------------------------------------------------------------------
+# hex pixel shuffle (retired; "codes in old versions.txt":68-126)
+# --------------------------------------------------------------------------
+def hex_pixel_shuffle(x, upscale_factor):
+    """(B, C*r*r, H, W) -> (B, C, r*H-r+1, r*W-ceil(r/2)) float32, written the way the reference does it: every
+    sub-channel block is painted into a doubled (type1) canvas, cell by cell, in the reference's order (later writes
+    overwrite earlier ones), then every second canvas column is kept and the frame is cropped.
+
+    :84-87 canvas of r*H+r-1 rows and 2*(r*W+r//2)+1 sub-columns; :90-93 the second sub-column of a cell lies at +1
+    (r even) or -1 (r odd); :101-104 sub-channel blocks enumerate hexagon rows i (r-t cells, t=|1+i-r|); :105-112
+    even input rows -> canvas rows i+2r*a, sub-columns 1+t+2k+2r*b; :114-122 odd input rows r rows lower and r
+    sub-columns further right; :125 type1 -> hex keeps sub-columns 1::2; :126 crop."""
+    r = int(upscale_factor)
+    while x.dim() < 4:
+        x = x.unsqueeze(0)
+    B, C, H, W = x.shape
+    if C % (r * r) != 0:
+        raise Exception("channel count must be a multiple of upscale_factor**2")   # :81-82
+    cout = C // (r * r)
+    rows_c, cells_c = r * H + r - 1, r * W + r // 2
+    canvas = torch.zeros(B, cout, rows_c, 2 * cells_c + 1, dtype=torch.float32)
+    pair = 1 if r % 2 == 0 else -1
+    n = 0
+    for i in range(2 * r - 1):
+        t = abs(1 + i - r)
+        for k in range(r - t):
+            block = x[:, n * cout:(n + 1) * cout].to(torch.float32)
+            for par in (0, 1):
+                src = block[:, :, par::2]
+                for a in range(src.shape[2]):
+                    y = par * r + i + 2 * r * a
+                    for b in range(W):
+                        c = par * r + 1 + t + 2 * k + 2 * r * b
+                        canvas[:, :, y, c] = src[:, :, a, b]
+                        canvas[:, :, y, c + pair] = src[:, :, a, b]
+            n += 1
+    hexed = canvas[:, :, :, 1::2]
+    return hexed[:, :, r - 1:rows_c - (r - 1), r // 2:hexed.shape[3] - (r + 1) // 2].contiguous()
