@@ -81,6 +81,18 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// Any early return (a CUDA error half-way through the ring) must not leave copies in flight that still read or
+// write the caller's host buffers: drain the ring streams on the way out unless the run completed.
+struct DrainOnExit {
+  Workspace& w;
+  bool armed = true;
+  ~DrainOnExit() {
+    if (!armed) return;
+    for (int s = 0; s < kSlots; ++s) if (w.st[s]) cudaStreamSynchronize(w.st[s]);
+    cudaGetLastError();
+  }
+};
+
 // kind: 0 rect->hex, 1 hex-source (hex->rect / hexresize: they differ only in the coordinate tables)
 static int run_host(int kind, const void* host_src, void* host_dst, const double* host_xs, const double* host_ys,
                     int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1, int sdt, int ddt, int interp, int math,
@@ -128,6 +140,7 @@ static int run_host(int kind, const void* host_src, void* host_dst, const double
 
   const char* src = (const char*)host_src;
   char* dst = (char*)host_dst;
+  DrainOnExit drain{ws};
   int64_t pending_p0[kSlots], pending_n[kSlots];
   for (int s = 0; s < kSlots; ++s) pending_n[s] = 0;
   int64_t c = 0;
@@ -155,7 +168,7 @@ static int run_host(int kind, const void* host_src, void* host_dst, const double
       rc = interp == 0 ? hg_hex2rect_nearest(ws.dsrc[s], ws.ddst[s], dxs, dys, n, h, w, h1, w1, dtype_size(sdt), ws.st[s])
                        : hg_hex2rect_linear(ws.dsrc[s], ws.ddst[s], dxs, dys, host_xs, host_ys, n, h, w, h1, w1, sdt, ddt, math, ws.st[s]);
     }
-    if (rc) { for (int k = 0; k < kSlots; ++k) cudaStreamSynchronize(ws.st[k]); return rc; }
+    if (rc) return rc;   // hg_last_error() already holds the kernel launcher's message; DrainOnExit waits for the ring
     void* hdst = dst_pinned ? (void*)(dst + (size_t)p0 * dst_plane) : ws.pin_out[s];
     HG_CUDA(cudaMemcpyAsync(hdst, ws.ddst[s], (size_t)n * dst_plane, cudaMemcpyDeviceToHost, ws.st[s]));
     if (!dst_pinned) { pending_p0[s] = p0; pending_n[s] = n; }
@@ -168,6 +181,7 @@ static int run_host(int kind, const void* host_src, void* host_dst, const double
       pending_n[s] = 0;
     }
   }
+  drain.armed = false;
   return HG_OK;
 }
 
