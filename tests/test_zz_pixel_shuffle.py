@@ -103,12 +103,15 @@ def test_gpu_ragged_shapes_dtypes_and_adjoint():
         xg = x.cuda().requires_grad_(True)
         y = m(xg)
         assert torch.equal(y.cpu(), want)
-        # backward == adjoint of the gather: <y, g> == <x, g_x>, and g_x is exactly the scatter of g through the table
+        # backward == adjoint of the gather: g_x is exactly the scatter of g through the table, zero where the crop
+        # (or a later write) dropped the element; autograd through the oracle's canvas writes is the checker
         g = torch.randn_like(y)
         y.backward(g)
-        xo = x.clone().requires_grad_(True)
-        HO.hex_pixel_shuffle(xo, r).backward(g.cpu())
-        assert torch.equal(xg.grad.cpu(), xo.grad)
+        assert float((y.detach() * g).sum()) == pytest.approx(float((xg.grad * xg.detach()).sum()), rel=1e-4, abs=1e-3)
+        if x.numel() <= 4096:                       # (autograd through thousands of canvas writes is slow on big cases)
+            xo = x.clone().requires_grad_(True)
+            HO.hex_pixel_shuffle(xo, r).backward(g.cpu())
+            assert torch.equal(xg.grad.cpu(), xo.grad)
         for dt in (torch.float64, torch.bfloat16, torch.uint8):
             xi = (x * 20).to(dt)
             assert torch.equal(m(xi.cuda()).cpu(), HO.hex_pixel_shuffle(xi, r))
