@@ -171,4 +171,11 @@ class HEXIMAGE(IMAGE):
                 pickle.dump(self.Heximagedataset, f)
 
     def Hex_imshow(self):
-        raise NotImplementedError("the OpenGL hex-mosaic viewer (HexPixelArt) is outside the B200 hot path")
+        raise NotImplementedError("the interactive OpenGL viewer (HexImage.py:219-276) has no place on a headless GPU node; "
+                                  "HexMosaic() returns the raster its fragment shader would draw")
+
+    def HexMosaic(self, out_size=None, hierarchy=0):
+        """The picture ``Hex_imshow`` draws, as an array: ``(bands, out_h, out_w)`` raster in which every pixel shows the
+        hex cell it falls in (HexPixelArt/hexagon_mosaic_shader.py:25-81 evaluated by one gather launch)."""
+        from .HexPixelArt import hexagon_mosaic
+        return hexagon_mosaic(self.HexagonImage, out_size, int(self.even_odd_offset), hierarchy)

@@ -127,6 +127,7 @@ int hg_plane_gather(const void* src, void* dst, const int64_t* table, int64_t ba
   HG_GATHER_CASE(HG_U8, uint8_t, HG_F32, float)
   HG_GATHER_CASE(HG_F64, double, HG_F64, double)
   HG_GATHER_CASE(HG_BF16, __nv_bfloat16, HG_BF16, __nv_bfloat16)
+  HG_GATHER_CASE(HG_U8, uint8_t, HG_U8, uint8_t)
 #undef HG_GATHER_CASE
   set_error("plane_gather: unsupported dtypes src=%d dst=%d", src_dtype, dst_dtype);
   return HG_E_DTYPE;

@@ -148,13 +148,14 @@ int hg_pad2d_bwd(const void* gy, void* gx, int64_t planes, int64_t H, int64_t W,
 /* ------------------------------------------------------------------------------------------
  * Table-driven plane gather / scatter: rearrangements whose index rule depends on shapes only.
  * ref: the retired HexPixelShuffle, "HyGrid/codes in old versions.txt":68-126 -- 2*(3r^2-3r+1) strided
- * slice assignments into a doubled type1 canvas, then [..., 1::2] and a crop; here one pass over a
+ * slice assignments into a doubled type1 canvas, then [..., 1::2] and a crop; and the viewer's fragment
+ * shader, HexPixelArt/hexagon_mosaic_shader.py:25-81 (screen pixel -> hex cell).  Here one pass over a
  * host-built table of `cells` int64 source offsets (relative to the (batch, channel) base; < 0 = zero):
  *   gather : dst[b][c][e] = table[e] >= 0 ? src[b*batch_stride + c*chan_stride + table[e]] : 0
  *   scatter: gsrc[b*batch_stride + c*chan_stride + table[e]] = gdst[b][c][e]   (adjoint of the gather: the table
  *            must be injective and the caller zero-fills gsrc first)
  * dst / gdst are dense [batches, chans, cells].  Offsets that leave [0, batches*batch_stride) are skipped.
- * gather dtypes: {HG_F32, HG_BF16, HG_F64, HG_U8} -> HG_F32, HG_F64 -> HG_F64, HG_BF16 -> HG_BF16;
+ * gather dtypes: {HG_F32, HG_BF16, HG_F64, HG_U8} -> HG_F32, HG_F64 -> HG_F64, HG_BF16 -> HG_BF16, HG_U8 -> HG_U8;
  * scatter: HG_F32, HG_F64, HG_BF16. */
 int hg_plane_gather(const void* src, void* dst, const int64_t* table, int64_t batches, int64_t chans, int64_t cells,
                     int64_t batch_stride, int64_t chan_stride, int src_dtype, int dst_dtype, hg_stream_t stream);
