@@ -98,6 +98,20 @@ def main():
     u8 = (x2[: N2 // 2]).to(torch.uint8)
     rec("c1-style rect->hex nearest u8 -> half res", lambda: timeit(lambda: Fn.rect_to_hex(u8, (512, 512), "nearest"), a.reps), (N2 // 2) * 3 * (q2 // 4 * 2), (N2 // 2) * q2 // 4)
     rec("c2 hex->rect linear fast", lambda: timeit(lambda: Fn.hex_to_rect(x2, None, "linear", out_dtype=torch.float32, math="fast", twin="np", out=y2), a.reps), 8 * p2 * q2, N2 * q2)
+    del x2, y2
+    torch.cuda.empty_cache()
+
+    # table-driven gathers (added after the last GPU run of round 1: first numbers come from the next one)
+    Ns = 4 if a.small else 32
+    xs_ = torch.randn(Ns, 64 * 4, 256, 256, device=dev)                      # 64 output channels, upscale 2
+    ps = hf.HexPixelShuffle(2)
+    ys_ = ps(xs_)
+    rec("pixel shuffle r=2 64ch 256x256 f32", lambda: timeit(lambda: ps(xs_), a.reps), 4 * (ys_.numel() * 2), Ns * ys_.shape[2] * ys_.shape[3])
+    del xs_, ys_
+    from HyGrid.HexPixelArt import hexagon_mosaic
+    xm = torch.randint(0, 256, (Ns * 3, 1024, 1024), device=dev, dtype=torch.uint8)
+    rec("hex mosaic 1024x1024 u8 -> 4096x4096", lambda: timeit(lambda: hexagon_mosaic(xm, (4096, 4096)), a.reps),
+        xm.numel() + xm.shape[0] * 4096 * 4096, Ns * 1024 * 1024)
     print(json.dumps({"hbm_peak_gbs": hbm, "rows": rows}))
 
 
