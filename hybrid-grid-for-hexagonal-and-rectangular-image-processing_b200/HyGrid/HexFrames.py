@@ -29,7 +29,8 @@ from . import _native as nv
 
 __all__ = ["pad", "HexConv2d", "HexConv2dAdaptivePadding", "HexPool2d", "HexAdaptivePool2d", "HexGlobalPool2d",
            "heximage_to_type1", "heximage_to_type2", "type1_to_heximage", "max_pooling", "min_pooling",
-           "average_pooling", "hexconv2d", "hexpool2d", "HexPixelShuffle", "pixel_shuffle_table"]
+           "average_pooling", "hexconv2d", "hexpool2d", "HexPixelShuffle", "pixel_shuffle_table",
+           "HexConvTranspose2d", "conv_transpose_tables"]
 
 _PAD_MODES = {"constant": 0, "reflect": 1, "replicate": 2, "circular": 3}
 _POOL = {"max": nv.POOL_MAX, "min": nv.POOL_MIN, "average": nv.POOL_AVG}
@@ -679,3 +680,138 @@ class HexPixelShuffle(nn.Module):
 
     def extra_repr(self):
         return f"upscale_factor={self.upscale_factor}"
+
+
+# ------------------------------------------------------------------------------------------------
+# hex transposed convolution (retired from the reference: "codes in old versions.txt":129-274)
+# ------------------------------------------------------------------------------------------------
+@functools.lru_cache(maxsize=64)
+def conv_transpose_tables(radius: int, stride: int, even_odd_offset: int, H: int, W: int):
+    """Host-side index rule of ``HexConvTranspose2d`` for an ``H x W`` input.
+
+    The reference (old versions :186-205) paints the input into a zero canvas in doubled (type1) coordinates -- even
+    input rows at canvas rows ``2s*a``, sub-columns ``eo*s + 2s*b`` and ``+1``; odd input rows at rows ``s + 2s*a``,
+    sub-columns ``(1-eo)*s + 2s*b`` and ``+1`` -- pads it by ``r-1`` rows and ``2(r-1)`` sub-columns, and runs the two
+    strided convs of ``HexConv2d`` on it, the odd one starting ``s`` rows lower and ``s`` sub-columns further right
+    (:232-243).  That canvas is the type1 raster of a zero-inserted hex lattice ``U`` with some row parity ``o_u``; the
+    even output rows are the even rows of ``Y = HexConv2d(stride=1, padding=0)(U)`` and the odd output rows are rows
+    ``2(p+k)+1`` (``s = 2k+1``) or ``2(p+k)`` (``s = 2k``) of ``Y`` taken ``k`` cells further right.
+
+    Returns ``(up, (Hu, Wu), o_u, sel, (Ho, Wo), (Hy, Wy))``: ``up`` int64 ``Hu*Wu`` offsets ``row*W + col`` into an input
+    plane (-1 = inserted zero), ``sel`` int64 ``Ho*Wo`` offsets into a ``Hy x Wy`` plane of ``Y``.  Raises ValueError
+    where the reference's slice assignments do not fit (it raises RuntimeError there)."""
+    r, s, eo = int(radius), int(stride), int(even_odd_offset)
+    p = r - 1
+    w1 = 2 * s * W - s + 2 + (1 - s % 2)                                   # :191
+    h1 = s * H - s + 1                                                     # :192
+    canvas = np.full((h1, w1), -1, np.int64)
+    src = np.arange(H * W, dtype=np.int64).reshape(H, W)
+    try:
+        canvas[0::2 * s, eo * s:-1:2 * s] = src[0::2]                      # :194-197
+        canvas[0::2 * s, eo * s + 1::2 * s] = src[0::2]
+        canvas[s::2 * s, (1 - eo) * s:-1:2 * s] = src[1::2]                # :199-202
+        canvas[s::2 * s, (1 - eo) * s + 1::2 * s] = src[1::2]
+    except ValueError as e:
+        raise ValueError(f"HexConvTranspose2d: a {H}x{W} input does not fit the stride-{s} canvas ({e})") from None
+    canvas = np.pad(canvas, ((p, p), (2 * p, 2 * p)), constant_values=-1)  # :203-204
+    Hu, Wc = canvas.shape
+    Wu = (Wc - 1) // 2
+    up = o_u = None
+    for o in (0, 1):                                                       # which row parity makes the canvas a type1 raster
+        shift = (np.arange(Hu) + o) % 2
+        cols = shift[:, None] + 2 * np.arange(Wu)[None, :]
+        first = np.take_along_axis(canvas, cols, 1)
+        again = np.full_like(canvas, -1)
+        np.put_along_axis(again, cols, first, 1)
+        np.put_along_axis(again, cols + 1, first, 1)
+        if np.array_equal(again, canvas):
+            up, o_u = first, o
+            break
+    if up is None:
+        raise ValueError("HexConvTranspose2d: the zero-stuffed canvas is not a doubled hex raster")
+    k_h, k_w = 2 * r - 1, 4 * r - 3
+    if Hu - s < k_h or Wc - 1 - s < k_w:
+        raise ValueError(f"HexConvTranspose2d: a {H}x{W} input is too small for radius {r}, stride {s}")
+    rows_e, rows_o = (Hu - k_h) // 2 + 1, (Hu - s - k_h) // 2 + 1
+    Wo = (Wc - 1 - s - k_w) // 2 + 1
+    if rows_e - rows_o not in (0, 1):
+        raise ValueError("HexConvTranspose2d: even / odd output rows cannot be interleaved")
+    Hy, Wy = _conv_out_shape(Hu, Wu, r, 1, 1, 0)
+    k = s // 2
+    Ho = rows_e + rows_o
+    R = np.arange(Ho)[:, None]
+    yrow = np.where(R % 2 == 0, R, 2 * (R // 2 + k) + (1 if s % 2 == 1 else 0))
+    ycol = np.arange(Wo)[None, :] + np.where(R % 2 == 0, 0, k)
+    if yrow.max() >= Hy or ycol.max() >= Wy:
+        raise ValueError("HexConvTranspose2d: selection leaves the stride-1 result")
+    sel = (yrow * Wy + ycol).astype(np.int64)
+    return up.reshape(-1), (Hu, Wu), o_u, sel.reshape(-1), (Ho, Wo), (Hy, Wy)
+
+
+@functools.lru_cache(maxsize=64)
+def _conv_transpose_device_tables(radius, stride, eo, H, W, device):
+    up, hu_wu, o_u, sel, ho_wo, hy_wy = conv_transpose_tables(radius, stride, eo, H, W)
+    dev = torch.device(device)
+    return (torch.from_numpy(np.ascontiguousarray(up)).to(dev), hu_wu, o_u,
+            torch.from_numpy(np.ascontiguousarray(sel)).to(dev), ho_wo, hy_wy)
+
+
+class HexConvTranspose2d(nn.Module):
+    """Hex transposed convolution as the reference retired it ("codes in old versions.txt":129-274): zero-insert the
+    lattice by ``stride``, frame it by ``radius-1`` cells, hex-convolve, interleave.  Same constructor, attribute names
+    (``in_channel`` / ``out_channel`` sic) and parameters (``kernel`` ``[out, in/groups, 1, 3r^2-3r+1]``, ``bias``).
+    Three launches: one table-driven gather (zero insertion), the ``HexConv2d`` kernels (tcgen05 where eligible), one
+    table-driven gather (row / column selection); autograd through all three.  The reference builds its canvas on the CPU
+    (:193), so it only ever ran on CPU tensors; here CUDA tensors only.  float32 result (:265-268)."""
+
+    def __init__(self, in_channels, out_channels, even_odd_offset, hexkernel_radius, stride=1, groups=1, bias=False):
+        super().__init__()
+        self.in_channel = in_channels
+        self.out_channel = out_channels
+        self.even_odd_offset = even_odd_offset
+        self.hexkernel_radius = hexkernel_radius
+        self.hexkernel_size = 2 * hexkernel_radius - 1
+        self.k_w = 4 * hexkernel_radius - 3
+        self.k_h = self.hexkernel_size
+        self.kernelnum = 3 * hexkernel_radius ** 2 - 3 * hexkernel_radius + 1
+        self.sh = stride
+        self.sw = stride * 2
+        self.out_even_odd_offset = 0
+        self.groups = groups
+        self.b = bias
+        if in_channels % groups != 0:
+            raise ValueError('in_channels must be divisible by groups')
+        if out_channels % groups != 0:
+            raise ValueError('out_channels must be divisible by groups')
+        self.kernel = nn.Parameter(torch.empty([out_channels, in_channels // groups, 1, self.kernelnum], dtype=torch.float))
+        if self.b == True:  # noqa: E712
+            self.bias = nn.Parameter(torch.empty([out_channels, ]))
+        else:
+            self.register_parameter('bias', None)
+        self.algo = 0
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        init.kaiming_uniform_(self.kernel, a=math.sqrt(5))
+        if self.bias is not None:
+            fan_in, _ = init._calculate_fan_in_and_fan_out(self.kernel)
+            if fan_in != 0:
+                bound = 1 / math.sqrt(fan_in)
+                init.uniform_(self.bias, -bound, bound)
+
+    def forward(self, input: Tensor) -> Tensor:
+        input = _as4(input)
+        if input.dtype not in (torch.float32, torch.bfloat16, torch.float64):
+            input = input.float()
+        B, Cin, H, W = input.shape
+        up, (Hu, Wu), o_u, sel, (Ho, Wo), (Hy, Wy) = _conv_transpose_device_tables(
+            self.hexkernel_radius, self.sh, int(self.even_odd_offset) % 2, H, W, str(input.device))
+        U = _PlaneGatherFn.apply(input, up, (Hu, Wu), Cin, H * W)                       # zero-inserted, framed lattice
+        Y = hexconv2d(U, self.kernel, self.bias, even_odd_offset=o_u, radius=self.hexkernel_radius, stride=1, padding=0,
+                      groups=self.groups, algo=self.algo)
+        assert tuple(Y.shape[-2:]) == (Hy, Wy)
+        return _PlaneGatherFn.apply(Y, sel, (Ho, Wo), self.out_channel, Hy * Wy)
+
+    def __repr__(self):
+        return (f"HexConvTranspose2d({self.in_channel}, {self.out_channel}, kernel_radius={self.hexkernel_radius}, "
+                f"stride={self.sh}, groups={self.groups}, bias={self.b})")

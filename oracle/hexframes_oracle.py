@@ -27,6 +27,7 @@ __all__ = [
     "hexpool_out_shape", "hexpool2d", "hexadaptivepool2d", "hexglobalpool2d",
     "reduce_max", "reduce_min", "reduce_average",
     "heximage_to_type1", "heximage_to_type2", "type1_to_heximage", "hex_pixel_shuffle",
+    "hex_conv_transpose2d",
 ]
 
 
@@ -257,3 +258,49 @@ def hex_pixel_shuffle(x, upscale_factor):
             n += 1
     hexed = canvas[:, :, :, 1::2]
     return hexed[:, :, r - 1:rows_c - (r - 1), r // 2:hexed.shape[3] - (r + 1) // 2].contiguous()
+
+
+# --------------------------------------------------------------------------
+# hex transposed convolution (retired; "codes in old versions.txt":129-274)
+# --------------------------------------------------------------------------
+def hex_conv_transpose2d(x, kernel, bias=None, even_odd_offset=0, radius=2, stride=1, groups=1):
+    """The reference's own route, step by step: paint the input into a zero canvas in doubled coordinates (:186-202),
+    frame it (:203-204), expand the hex kernel into its dense (2r-1) x (4r-3) window (:216-224), run one strided
+    correlation for the even output rows and one -- started ``stride`` rows lower and ``stride`` sub-columns further
+    right -- for the odd ones (:232-243), trim to the common width (:244-263) and interleave (:265-270)."""
+    r, s, eo = int(radius), int(stride), int(even_odd_offset)
+    while x.dim() < 4:
+        x = x.unsqueeze(0)
+    B, C, H, W = x.shape
+    p = r - 1
+    w1 = 2 * s * W - s + 2 + (1 - s % 2)
+    h1 = s * H - s + 1
+    # the reference assigns whole strided slices, which only works when their lengths equal the input's (:194-202)
+    for par, nrows in ((0, (H + 1) // 2), (1, H // 2)):
+        start = (eo if par == 0 else 1 - eo) * s
+        fits = (len(range(par * s, h1, 2 * s)) == nrows and len(range(start, w1 - 1, 2 * s)) == W
+                and len(range(start + 1, w1, 2 * s)) == W)
+        if nrows and not fits:
+            raise ValueError("input does not fit the canvas (the reference raises a shape mismatch)")
+    canvas = torch.zeros(B, C, h1 + 2 * p, w1 + 4 * p, dtype=torch.float32)
+    for i in range(H):
+        start = (eo if i % 2 == 0 else 1 - eo) * s
+        y = p + s * i                                   # even rows 2a -> 2s*a, odd rows 2a+1 -> s + 2s*a
+        for j in range(W):
+            c = 2 * p + start + 2 * s * j
+            canvas[:, :, y, c] = x[:, :, i, j].float()
+            canvas[:, :, y, c + 1] = x[:, :, i, j].float()
+    dense = torch.zeros(kernel.shape[0], kernel.shape[1], 2 * r - 1, 4 * r - 3, dtype=torch.float32)
+    for k, (a, t, m) in enumerate(hex_taps(r)):
+        dense[:, :, a, t + 2 * m] += kernel[:, :, 0, k].float()
+    b = None if bias is None else bias.float()
+    even = F.conv2d(canvas[:, :, :, 1:canvas.shape[3] - s], dense, b, stride=(2, 2), groups=groups)
+    odd = F.conv2d(canvas[:, :, s:, s + 1:], dense, b, stride=(2, 2), groups=groups)
+    wmin = min(even.shape[3], odd.shape[3])
+    even, odd = even[..., :wmin], odd[..., :wmin]
+    if even.shape[2] - odd.shape[2] not in (0, 1):
+        raise ValueError("even / odd rows cannot be interleaved (the reference raises a shape mismatch)")
+    out = torch.empty(B, kernel.shape[0], even.shape[2] + odd.shape[2], wmin, dtype=torch.float32)
+    out[:, :, 0::2] = even
+    out[:, :, 1::2] = odd
+    return out

@@ -2,8 +2,9 @@
 
     python tests/golden/make_retired_golden.py      # needs /root/reference (build container only)
 
-The text file is not importable; the class body of ``HexPixelShuffle`` (lines 68-126) is exec'd UNMODIFIED in a
-namespace holding the names it expects from the reference's own ``HexFrames`` module.  Output:
+The text file is not importable; the class bodies of ``HexPixelShuffle`` (lines 68-126) and ``HexConvTranspose2d``
+(lines 129-274) are exec'd UNMODIFIED in a namespace holding the names they expect from the reference's own
+``HexFrames`` module and from torch.  Output:
 tests/golden/retired_golden.npz (inputs are seeded integers stored as float32, outputs the class's results).
 """
 import math
@@ -23,17 +24,25 @@ CASES = [(2, 1, 4, 5), (2, 2, 5, 4), (2, 1, 1, 3), (3, 1, 4, 5), (3, 2, 3, 3), (
          (5, 1, 4, 3), (2, 3, 8, 8)]     # (upscale_factor, out_channels, H, W)
 
 
+# (radius, stride, even_odd_offset, groups, Cin, Cout, H, W, bias)
+CT_CASES = [(2, 1, 0, 1, 4, 6, 6, 7, True), (2, 2, 0, 1, 4, 6, 6, 7, True), (2, 2, 1, 2, 4, 6, 5, 5, False),
+            (3, 2, 0, 1, 2, 3, 8, 6, True), (2, 3, 1, 1, 3, 5, 6, 7, True), (3, 3, 0, 1, 2, 2, 4, 9, False),
+            (2, 2, 1, 1, 16, 16, 9, 12, True), (3, 1, 1, 2, 4, 4, 5, 5, True)]
+
+
 def load_class():
+    from torch import Tensor
+    from torch.nn import init
     src = open("/root/reference/HyGrid/codes in old versions.txt").read()
-    body = src[src.index("class HexPixelShuffle"):src.index("class HexConvTranspose2d")]
-    ns = dict(nn=nn, torch=torch, np=np, F=F, math=math, pad=hf.pad, heximage_to_type1=hf.heximage_to_type1,
-              type1_to_heximage=hf.type1_to_heximage)
-    exec(compile(body, "codes in old versions.txt[68:126]", "exec"), ns)
-    return ns["HexPixelShuffle"]
+    ns = dict(nn=nn, torch=torch, np=np, F=F, math=math, init=init, Tensor=Tensor, pad=hf.pad,
+              heximage_to_type1=hf.heximage_to_type1, type1_to_heximage=hf.type1_to_heximage)
+    body = src[src.index("class HexPixelShuffle"):src.index("class im2col_HexConv2d")]
+    exec(compile(body, "codes in old versions.txt[68:274]", "exec"), ns)
+    return ns["HexPixelShuffle"], ns["HexConvTranspose2d"]
 
 
 def main():
-    PS = load_class()
+    PS, CT = load_class()
     rng = np.random.default_rng(20260319)
     out = {"count": np.array(len(CASES))}
     for n, (r, cout, H, W) in enumerate(CASES):
@@ -42,6 +51,18 @@ def main():
         out[f"ps_{n}_r"] = np.array(r)
         out[f"ps_{n}_in"] = x
         out[f"ps_{n}_out"] = y.numpy()
+    torch.manual_seed(20260319)
+    out["ct_count"] = np.array(len(CT_CASES))
+    for n, (r, st, eo, g, cin, cout, H, W, bias) in enumerate(CT_CASES):
+        m = CT(cin, cout, eo, r, stride=st, groups=g, bias=bias)
+        x = torch.randn(2, cin, H, W)
+        with torch.no_grad():
+            y = m(x)
+        out[f"ct_{n}_cfg"] = np.array([r, st, eo, g, cin, cout, int(bias)])
+        out[f"ct_{n}_in"] = x.numpy()
+        out[f"ct_{n}_kernel"] = m.kernel.detach().numpy()
+        out[f"ct_{n}_bias"] = m.bias.detach().numpy() if bias else np.zeros(0, np.float32)
+        out[f"ct_{n}_out"] = y.numpy()
     np.savez_compressed(OUT, **out)
     print(OUT, os.path.getsize(OUT), "bytes")
 
