@@ -39,6 +39,7 @@ if has ncu; then   # launch list of the bench + one --set full capture per domin
   cap hexsrc_tma hexsrc_linear_tma "c4 hex->rect linear fast"
   cap pool_vec hexpool2x2_fwd "pool avg 2x2 level 0"
   cap type1 hex_to_type_vec "hex->type1"
+  cap gather plane_gather "pixel shuffle"
   for op in fwd wgrad; do
     C="python tools/bench_conv.py --reps 2 --only $op --dtypes f32f32"
     timeout 300 $C > $OUT/plain_conv_$op.log 2>&1 && timeout 900 ncu --set full --clock-control none --import-source on -k regex:hexconv_ -s 2 -c 1 -o $OUT/prof_conv_$op $C > $OUT/ncu_conv_$op.log 2>&1; echo "ncu conv $op rc=$?"
