@@ -1,8 +1,8 @@
 #!/usr/bin/env python
-"""Debug helper: tcgen05 wgrad vs the torch-CPU oracle for a list of shapes; prints where the error sits."""
+"""Stress check (part of the test infrastructure, run by tools/gpu_suite.sh stress): tcgen05 wgrad vs the torch-CPU oracle for a list of shapes; prints where the error sits."""
 import os, sys, itertools
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # tests/stress/ -> repo root
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "hybrid-grid-for-hexagonal-and-rectangular-image-processing_b200"))
 from HyGrid import HexFrames as hf
 from oracle import hexframes_oracle as HO

@@ -12,7 +12,7 @@ if has tests; then
   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $OUT/smoke.log
 fi
 if has stress; then   # the tcgen05 wgrad staging race showed up once per few processes: repeat fresh processes
-  for k in 0 1 2 3 4 5; do timeout 300 python tools/debug/wgrad_cfg.py 2>&1 | grep -c BAD; done > $OUT/wgrad_stress.log 2>&1
+  for k in 0 1 2 3 4 5; do timeout 300 python tests/stress/wgrad_cfg.py 2>&1 | grep -c BAD; done > $OUT/wgrad_stress.log 2>&1
   echo "wgrad stress (BAD configurations per process):" $(tr '\n' ' ' < $OUT/wgrad_stress.log)
 fi
 if has bench; then
