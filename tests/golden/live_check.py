@@ -84,6 +84,87 @@ def main():
         yo = HO.hexpool2d(x, method, 2, 2)
         assert yo.shape == yr.shape and torch.allclose(yo, yr, atol=1e-6, equal_nan=True), "P1"
         checked += 1
+    # P1 beyond 2x2: windows / strides / padding / ceil mode / NaN-aware reductions; error agreement where the window leaves the image
+    for _ in range(40):
+        B, C_, H, W = 1, int(rng.integers(1, 3)), int(rng.integers(6, 26)), int(rng.integers(8, 30))
+        method = ("max", "min", "average")[int(rng.integers(0, 3))]
+        kh, kw = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+        sh, sw = int(rng.integers(1, 4)), int(rng.integers(2, 5))
+        pad = int(rng.integers(0, 3))
+        ceil, cip = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        x = torch.randn(B, C_, H, W)
+        if rng.integers(0, 3) == 0:
+            x[torch.rand_like(x) < 0.2] = float("nan")
+        try:
+            yr = hf.HexPool2d(method, (kh, kw), (sh, sw), padding=pad, ceil_mode=ceil, count_include_pad=cip)(x)
+        except Exception:
+            try:
+                HO.hexpool2d(x, method, (kh, kw), (sh, sw), pad, "constant", 0, ceil, cip)
+            except Exception:
+                continue
+            raise AssertionError(f"P1: the reference raises but the oracle does not ({method} k={kh, kw} s={sh, sw} pad={pad} ceil={ceil})")
+        yo = HO.hexpool2d(x, method, (kh, kw), (sh, sw), pad, "constant", 0, ceil, cip)
+        assert yo.shape == yr.shape and torch.allclose(yo, yr, atol=1e-6, equal_nan=True), f"P1 {method} k={kh, kw} s={sh, sw} pad={pad} ceil={ceil} cip={cip}"
+        checked += 1
+    # P2 adaptive / global pooling (the one undefined name of the reference is injected by make_golden.load_reference)
+    for _ in range(16):
+        H, W, n = int(rng.integers(6, 30)), int(rng.integers(8, 34)), int(rng.integers(1, 6))
+        method = ("max", "min", "average")[int(rng.integers(0, 3))]
+        x = torch.randn(2, 3, H, W)
+        try:
+            yr = hf.HexAdaptivePool2d(n, method)(x)
+        except Exception:
+            continue
+        yo = HO.hexadaptivepool2d(x, n, method)
+        assert yo.shape == yr.shape and torch.allclose(yo, yr, atol=1e-6, equal_nan=True), f"P2 adaptive {H, W}->{n} {method}"
+        yg = hf.HexGlobalPool2d(method)(x)
+        og = HO.hexglobalpool2d(x, method)
+        assert og.shape == yg.shape and torch.allclose(og, yg, atol=1e-6), f"P2 global {method}"
+        checked += 2
+    # C1 with groups, C2 adaptive ("same") padding
+    for _ in range(10):
+        g = int(rng.integers(2, 4))
+        Cin, Cout = g * int(rng.integers(1, 3)), g * int(rng.integers(1, 3))
+        H, W, r, off = int(rng.integers(8, 18)), int(rng.integers(8, 18)), int(rng.integers(2, 4)), int(rng.integers(0, 2))
+        m = hf.HexConv2d(Cin, Cout, off, r, stride=1, padding=r - 1, groups=g)
+        x = torch.randn(1, Cin, H, W)
+        yr = m(x)
+        yo = HO.hexconv2d(x, m.kernel.detach(), m.bias.detach(), off, r, 1, r - 1, 1, g)
+        assert yo.shape == yr.shape and float((yo - yr.detach()).abs().max()) <= 1e-5 * max(1.0, float(yr.abs().max())), "C1 groups"
+        s_, d = int(rng.integers(1, 3)), int(rng.integers(1, 3))
+        try:
+            ma = hf.HexConv2dAdaptivePadding(Cin, Cout, off, r, stride=s_, dilation=d)
+            ya = ma(x)
+        except Exception:
+            continue
+        pl, pr, pt, pb = HO.adaptive_padding(H, W, r, s_, d)
+        xa = torch.nn.functional.pad(x, (pl, pr, pt, pb))
+        yo = HO.hexconv2d(xa, ma.kernel.detach(), ma.bias.detach(), off, r, s_, 0, d, 1)
+        assert yo.shape == ya.shape and float((yo - ya.detach()).abs().max()) <= 1e-5 * max(1.0, float(ya.abs().max())), "C2 adaptive padding"
+        checked += 2
+    # retired layers ("codes in old versions.txt"), classes exec'd unmodified by make_retired_golden.load_class
+    import make_retired_golden as MR
+    PS, CT = MR.load_class()
+    for _ in range(12):
+        r, cout, H, W = int(rng.integers(2, 6)), int(rng.integers(1, 3)), int(rng.integers(1, 9)), int(rng.integers(1, 9))
+        x = torch.randn(2, cout * r * r, H, W)
+        eq(HO.hex_pixel_shuffle(x, r).numpy(), PS(r)(x).numpy(), f"pixel shuffle r={r} {H, W}")
+    for _ in range(16):
+        r, s_, off, H, W = int(rng.integers(2, 4)), int(rng.integers(1, 4)), int(rng.integers(0, 2)), int(rng.integers(3, 10)), int(rng.integers(3, 10))
+        m = CT(3, 4, off, r, stride=s_, bias=True)
+        x = torch.randn(1, 3, H, W)
+        try:
+            with torch.no_grad():
+                yr = m(x)
+        except Exception:
+            try:
+                HO.hex_conv_transpose2d(x, m.kernel.detach(), m.bias.detach(), off, r, s_)
+            except ValueError:
+                continue
+            raise AssertionError(f"transposed conv: the reference raises but the oracle does not (r={r} s={s_} {H, W})")
+        yo = HO.hex_conv_transpose2d(x, m.kernel.detach(), m.bias.detach(), off, r, s_)
+        assert yo.shape == yr.shape and float((yo - yr).abs().max()) <= 1e-5 * max(1.0, float(yr.abs().max())), "transposed conv"
+        checked += 1
     print(f"live reference check ok: {checked} comparisons")
 
 
