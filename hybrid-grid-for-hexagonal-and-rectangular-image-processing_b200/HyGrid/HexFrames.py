@@ -625,31 +625,54 @@ def _pixel_shuffle_offsets(r, H, W, cout, device):
     return torch.from_numpy(np.ascontiguousarray(off.reshape(-1))).to(torch.device(device)), off.shape
 
 
+def _injective_layers(off: np.ndarray):
+    """Split a gather table into tables that each read every source element at most once (the j-th reader of an
+    element goes to layer j; other entries are -1).  The adjoint of the gather is then one plain scatter per layer,
+    summed -- no atomics, deterministic.  A table that is already injective comes back as itself."""
+    off = np.ascontiguousarray(off.reshape(-1))
+    valid = np.flatnonzero(off >= 0)
+    order = valid[np.argsort(off[valid], kind="stable")]
+    sorted_off = off[order]
+    first = np.r_[True, sorted_off[1:] != sorted_off[:-1]] if order.size else np.zeros(0, bool)
+    start = np.maximum.accumulate(np.where(first, np.arange(order.size), 0)) if order.size else np.zeros(0, np.int64)
+    rank = np.arange(order.size) - start                     # 0 for the first reader of an element, 1 for the second, ...
+    layers = []
+    for j in range(int(rank.max()) + 1 if order.size else 1):
+        t = np.full_like(off, -1)
+        pick = order[rank == j]
+        t[pick] = off[pick]
+        layers.append(t)
+    return layers
+
+
 class _PlaneGatherFn(torch.autograd.Function):
-    """``y[b, c, e] = x[b].flatten()[c*chan_stride + table[e]]`` (0 where ``table[e] < 0``), float32 out."""
+    """``y[b, c, e] = x[b].flatten()[c*chan_stride + table[e]]`` (0 where ``table[e] < 0``), float32 out.
+    ``bwd_tables``: the table split into injective layers (``_injective_layers``) for the scatter adjoint."""
 
     @staticmethod
-    def forward(ctx, x, table, out_hw, chans, chan_stride):
+    def forward(ctx, x, table, out_hw, chans, chan_stride, bwd_tables=None):
         x = nv.require_cuda(x, "input").contiguous()
         B = x.shape[0]
         batch_stride = x.numel() // B if B else 0
         y = torch.empty((B, chans) + tuple(out_hw), dtype=torch.float32, device=x.device)
         nv.call("hg_plane_gather", nv.ptr(x), nv.ptr(y), nv.ptr(table), B, chans, out_hw[0] * out_hw[1], batch_stride,
                 chan_stride, nv.hg_dtype(x.dtype), nv.F32, nv.stream_ptr(x.device))
-        ctx.save_for_backward(table)
+        ctx.save_for_backward(*(bwd_tables if bwd_tables is not None else (table,)))
         ctx.meta = (tuple(x.shape), x.dtype, chans, chan_stride, batch_stride, tuple(out_hw))
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
-        table, = ctx.saved_tensors
         shape, dtype, chans, chan_stride, batch_stride, out_hw = ctx.meta
         gy = gy.contiguous().float()
-        gx = torch.zeros(shape, dtype=torch.float32, device=gy.device)
-        nv.call("hg_plane_scatter", nv.ptr(gy), nv.ptr(gx), nv.ptr(table), shape[0], chans, out_hw[0] * out_hw[1],
-                batch_stride, chan_stride, nv.F32, nv.stream_ptr(gy.device))
-        return gx.to(dtype), None, None, None, None
+        gx = None
+        for layer in ctx.saved_tensors:
+            part = torch.zeros(shape, dtype=torch.float32, device=gy.device)
+            nv.call("hg_plane_scatter", nv.ptr(gy), nv.ptr(part), nv.ptr(layer), shape[0], chans, out_hw[0] * out_hw[1],
+                    batch_stride, chan_stride, nv.F32, nv.stream_ptr(gy.device))
+            gx = part if gx is None else gx.add_(part)
+        return gx.to(dtype), None, None, None, None, None
 
 
 class HexPixelShuffle(nn.Module):
@@ -752,8 +775,10 @@ def conv_transpose_tables(radius: int, stride: int, even_odd_offset: int, H: int
 def _conv_transpose_device_tables(radius, stride, eo, H, W, device):
     up, hu_wu, o_u, sel, ho_wo, hy_wy = conv_transpose_tables(radius, stride, eo, H, W)
     dev = torch.device(device)
-    return (torch.from_numpy(np.ascontiguousarray(up)).to(dev), hu_wu, o_u,
-            torch.from_numpy(np.ascontiguousarray(sel)).to(dev), ho_wo, hy_wy)
+    put = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    # for an even stride both output parities read even rows of the stride-1 result: the selection reads some elements
+    # twice, so its adjoint is a sum of scatters over injective layers
+    return put(up), hu_wu, o_u, put(sel), ho_wo, hy_wy, tuple(put(t) for t in _injective_layers(sel))
 
 
 class HexConvTranspose2d(nn.Module):
@@ -804,13 +829,13 @@ class HexConvTranspose2d(nn.Module):
         if input.dtype not in (torch.float32, torch.bfloat16, torch.float64):
             input = input.float()
         B, Cin, H, W = input.shape
-        up, (Hu, Wu), o_u, sel, (Ho, Wo), (Hy, Wy) = _conv_transpose_device_tables(
+        up, (Hu, Wu), o_u, sel, (Ho, Wo), (Hy, Wy), sel_layers = _conv_transpose_device_tables(
             self.hexkernel_radius, self.sh, int(self.even_odd_offset) % 2, H, W, str(input.device))
         U = _PlaneGatherFn.apply(input, up, (Hu, Wu), Cin, H * W)                       # zero-inserted, framed lattice
         Y = hexconv2d(U, self.kernel, self.bias, even_odd_offset=o_u, radius=self.hexkernel_radius, stride=1, padding=0,
                       groups=self.groups, algo=self.algo)
         assert tuple(Y.shape[-2:]) == (Hy, Wy)
-        return _PlaneGatherFn.apply(Y, sel, (Ho, Wo), self.out_channel, Hy * Wy)
+        return _PlaneGatherFn.apply(Y, sel, (Ho, Wo), self.out_channel, Hy * Wy, sel_layers)
 
     def __repr__(self):
         return (f"HexConvTranspose2d({self.in_channel}, {self.out_channel}, kernel_radius={self.hexkernel_radius}, "

@@ -114,3 +114,24 @@ def test_gpu_module_matches_fixture_and_oracle(golden):
         for got, ref in ((xg.grad, xo.grad), (m.kernel.grad, ko.grad)) + (((m.bias.grad, bo.grad),) if bias is not None else ()):
             tol = 1e-4 * max(1.0, float(ref.abs().max()))
             assert float((got.cpu() - ref).abs().max()) <= tol
+
+
+def test_selection_table_is_split_into_injective_layers_for_the_adjoint():
+    """For an even stride both output parities read even rows of the stride-1 result, so some elements are gathered
+    twice; the scatter kernel does plain stores, hence the backward sums one scatter per injective layer."""
+    from HyGrid import HexFrames as hf
+    for st, want_layers in ((1, 1), (2, 2), (3, 1)):
+        up, _, _, sel, _, _ = hf.conv_transpose_tables(2, st, 0, 6, 7)
+        assert len(hf._injective_layers(up)) == 1                     # zero insertion reads every input cell once
+        layers = hf._injective_layers(sel)
+        assert len(layers) == want_layers
+        total = np.zeros_like(sel)
+        for t in layers:
+            v = t[t >= 0]
+            assert len(np.unique(v)) == len(v)
+            total += (t >= 0)
+            assert np.array_equal(t[t >= 0], sel[t >= 0])
+        assert np.array_equal(total, (sel >= 0).astype(total.dtype))  # every entry lands in exactly one layer
+    t = np.array([3, -1, 5, 3, 0, 5, 3, 7])
+    assert [l.tolist() for l in hf._injective_layers(t)] == [[3, -1, 5, -1, 0, -1, -1, 7], [-1, -1, -1, 3, -1, 5, -1, -1],
+                                                            [-1, -1, -1, -1, -1, -1, 3, -1]]
