@@ -115,3 +115,28 @@ def test_stream_argument_carries_its_device_through_ctypes():
     assert isinstance(st, C.c_void_p) and st.value == 0x1234
     L = nv.lib()          # rejected for rows_step before the stream is touched: safe without a GPU
     assert L.hg_type_to_hex(None, None, 1, 4, 9, 3, nv.F32, nv.F32, st) == -1
+
+
+def test_call_switches_to_the_stream_device_only_when_it_differs(monkeypatch):
+    import contextlib
+    from HyGrid import _native as nv
+    entered = []
+
+    @contextlib.contextmanager
+    def fake_device(idx):
+        entered.append(idx)
+        yield
+
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    monkeypatch.setattr(torch.cuda, "device", fake_device)
+    st = nv.StreamArg(0)
+    for dev, want in ((0, []), (1, [1])):
+        st.device_index = dev
+        entered.clear()
+        with pytest.raises(nv.HyGridNativeError):           # rows_step = 3 is rejected before anything touches the stream
+            nv.call("hg_type_to_hex", None, None, 1, 4, 9, 3, nv.F32, nv.F32, st)
+        assert entered == want
+    entered.clear()
+    with pytest.raises(nv.HyGridNativeError):               # host entry points end in an int, not a stream: never switch
+        nv.call("hg_host_rect2hex", None, None, None, None, 1, 0, 4, 4, 4, nv.F32, nv.F32, 1, 0, 0)
+    assert entered == []
