@@ -246,22 +246,23 @@ class HexConv2d(nn.Module):
                        self.pad, self.padded_even_odd_offset, 0.0, self.out_dtype, 2, 0)
         return bool(nv.query("hg_hexconv_umma_eligible", C.byref(d), 0))
 
-    def _activation(self, input: Tensor) -> Tensor:
+    def _activation(self, input: Tensor):
+        """(input in the dtype the kernels read, whether autocast routes this call to the tcgen05 kernel)."""
         if torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16:
             if self.algo != 1 and self._tensor_core_ok(input):
-                self._autocast_tc = True
-                return input if input.dtype in (torch.float32, torch.bfloat16) else input.float()
-            return input.to(torch.bfloat16)
+                return (input if input.dtype in (torch.float32, torch.bfloat16) else input.float()), True
+            return input.to(torch.bfloat16), False
         if self.kernel.dtype not in (torch.float32, torch.bfloat16):
             raise TypeError(f"HexConv2d parameters must be float32 (or bfloat16), got {self.kernel.dtype}")
-        return input.to(self.kernel.dtype)
+        return input.to(self.kernel.dtype), False
 
     def forward(self, input: Tensor, relu: bool = False, affine=None) -> Tensor:
         """``affine=(scale, shift)``: inference-only fused ``act(conv(x) * scale[c] + shift[c])`` (the conv's own bias must
         already be folded into ``shift``); ``relu=True`` fuses the ReLU.  Neither records anything for backward."""
-        self._autocast_tc = False
-        input = _as4(self._activation(input))
-        algo = 2 if self._autocast_tc else self.algo
+        input, autocast_tc = self._activation(input)
+        self._autocast_tc = autocast_tc          # record of the last call (introspection / tests); not read by the forward
+        input = _as4(input)
+        algo = 2 if autocast_tc else self.algo
         pad_, parity = self.pad, self.padded_even_odd_offset
         if self.pad and self.padding_mode != 'constant':
             input = pad(input, self.pad, self.padding_mode, self.padding_value)
@@ -314,7 +315,7 @@ class HexConv2dAdaptivePadding(HexConv2d):
         output_w = math.ceil(img_w / stride)
         pad_h = max((output_h - 1) * self.stride + (kernel_size - 1) * self.dilation + 1 - img_h, 0)
         pad_w = max(output_w * self.stride + (kernel_size - 1) * self.dilation + 1 - img_w, 0)
-        input = _as4(self._activation(input))
+        input = _as4(self._activation(input)[0])
         if pad_h > 0 or pad_w > 0:
             input = _pad4(input, pad_w // 2, pad_w - pad_w // 2, pad_h // 2, pad_h - pad_h // 2)
         return super().forward(input, relu)
