@@ -9,7 +9,8 @@ bit-identical to the reference, and the integer lattice indexing is exact.
 Deviations: ``'nearest'`` on a hex source works (the reference raises from a
 ``np.min`` unpacking bug, geometry_np.py:172/339/664) and follows the working geometry_torch rule;
 ``'bilinear'`` on a hex source raises NotImplementedError (the reference returns uninitialised memory);
-2-D inputs are accepted as one band; ``heximpad`` works (the reference forgets ``import numbers``).
+2-D inputs are accepted as one band; ``heximpad`` works (the reference forgets ``import numbers``) and keeps the
+``cv2.copyMakeBorder`` semantics of the reference's call, quirks included (a scalar ``pad_val`` reaches band 0 only).
 The ``offset`` argument is dead in the reference too (it only perturbs a variable that is never read).
 """
 from __future__ import annotations
@@ -91,24 +92,37 @@ def heximpad(img: np.ndarray, *, shape: Optional[Tuple[int, int]] = None, paddin
                          f'But received {padding}')
     assert padding_mode in ['constant', 'edge', 'reflect', 'symmetric']
     mode = {'constant': 0, 'edge': 2, 'reflect': 1, 'symmetric': 4}[padding_mode]
+    padding = tuple(int(v) for v in padding)
     top, bottom = padding[1] - padding[1] % 2, padding[3] + padding[1] % 2
     left, right = padding[0], padding[2]
     from .HexFrames import _Pad2dFn
     arr = np.asarray(img)
     chw = arr[None] if arr.ndim == 2 else np.transpose(arr, (2, 0, 1))
-    x = torch.from_numpy(np.ascontiguousarray(chw)).cuda()
+    bands = chw.shape[0]
+    # border value as cv2.copyMakeBorder reads it (:722-730): a tuple is one value per band; a scalar is Scalar(v) =
+    # (v, 0, 0, 0), so only band 0 of a multi-band image receives it -- and more than 4 bands need v == 0
+    if isinstance(pad_val, tuple):
+        vals = [float(v) for v in pad_val]
+    else:
+        if bands > 4 and float(pad_val) != 0.0:
+            raise Exception("cv2.copyMakeBorder: a scalar border value must be 0 for images with more than 4 channels")
+        vals = [float(pad_val)] + [0.0] * (bands - 1)
+    if np.issubdtype(arr.dtype, np.integer):               # saturate_cast: round half to even, clamp to the type
+        info = np.iinfo(arr.dtype)
+        vals = [float(min(max(np.rint(v), info.min), info.max)) for v in vals]
     cast = None
-    if x.dtype not in (torch.uint8, torch.float32, torch.float64, torch.bfloat16):
-        cast, x = x.dtype, x.double()
-    vals = pad_val if isinstance(pad_val, tuple) else (pad_val,) * x.shape[0]
-    if len(set(vals)) == 1:
+    if chw.dtype not in (np.uint8, np.float32, np.float64):    # other integer types travel as float64 (exact up to 2^53)
+        cast, chw = chw.dtype, chw.astype(np.float64)
+    x = torch.from_numpy(np.ascontiguousarray(chw)).cuda()
+    if mode != 0 or len(set(vals)) == 1:
         y = _Pad2dFn.apply(x, left, right, top, bottom, mode, vals[0])
     else:
-        y = torch.cat([_Pad2dFn.apply(x[k:k + 1], left, right, top, bottom, mode, vals[k]) for k in range(x.shape[0])], 0)
-    if cast is not None:
-        y = y.to(cast)
+        y = torch.cat([_Pad2dFn.apply(x[k:k + 1], left, right, top, bottom, mode, vals[k]) for k in range(bands)], 0)
     y = y.cpu().numpy()
-    return y[0] if arr.ndim == 2 else np.ascontiguousarray(np.transpose(y, (1, 2, 0)))
+    if cast is not None:
+        y = y.astype(cast)
+    # OpenCV drops a single-band axis: (H, W, 1) comes back as (H', W')
+    return y[0] if bands == 1 else np.ascontiguousarray(np.transpose(y, (1, 2, 0)))
 
 
 def hex_impad_to_multiple(img: np.ndarray, divisor: int, pad_val: Union[float, List] = 0) -> np.ndarray:

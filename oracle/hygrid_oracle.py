@@ -30,6 +30,7 @@ __all__ = [
     "hex_to_rect_resample", "hexresize", "warp_coords", "hex_warp",
     "offset_to_axial", "axial_to_offset",
     "hex_to_type1", "hex_to_type2", "type1_to_hex", "type2_to_hex",
+    "heximpad", "hex_impad_to_multiple",
 ]
 
 
@@ -364,3 +365,64 @@ def type1_to_hex(t1):
 def type2_to_hex(t2):
     """HexImage.py:111 ``data[:, ::2, 1:-1:2]``."""
     return np.asarray(t2)[..., ::2, 1:-1:2]
+
+
+# --------------------------------------------------------------------------
+# heximpad / hex_impad_to_multiple (geometry_np.py:683-749)
+# --------------------------------------------------------------------------
+def heximpad(img, shape=None, padding=None, pad_val=0, padding_mode="constant"):
+    """(H, W[, C]) image padded the way geometry_np.py:683-732 does it through ``cv2.copyMakeBorder``:
+
+    * ``shape`` pads right / bottom only (:692-696); ``padding`` is an int, ``(w, h)`` -- which the reference expands
+      to ``(0, h, w, h)`` (:706-707) -- or ``(left, top, right, bottom)``;
+    * the top pad is rounded DOWN to an even number of rows and the remainder goes to the bottom (:724-725), which
+      keeps the row parity of the hex lattice;
+    * modes (:716-721): constant, edge = replicate, reflect = without repeating the border cell
+      (``BORDER_REFLECT_101``), symmetric = repeating it (``BORDER_REFLECT``);
+    * constant value: a tuple gives one value per channel; a scalar is an OpenCV ``Scalar(v)`` = ``(v, 0, 0, 0)``, so
+      on a multi-band image only band 0 receives it and the others get 0 -- and more than 4 bands raise unless the
+      value is 0; integer images take the value rounded half-to-even and saturated (``saturate_cast``).
+    The reference itself raises NameError (it forgets ``import numbers``); the fixtures inject that one name."""
+    img = np.asarray(img)
+    assert (shape is not None) ^ (padding is not None)
+    if shape is not None:
+        padding = (0, 0, max(shape[1] - img.shape[1], 0), max(shape[0] - img.shape[0], 0))
+    if isinstance(padding, tuple) and len(padding) in (2, 4):
+        if len(padding) == 2:
+            padding = (0, padding[1], padding[0], padding[1])
+    elif isinstance(padding, (int, float)):
+        padding = (padding,) * 4
+    else:
+        raise ValueError("Padding must be a int or a 2, or 4 element tuple.")
+    left, top, right, bottom = (int(v) for v in padding)
+    top, bottom = top - top % 2, bottom + top % 2
+    bands = 1 if img.ndim == 2 else img.shape[2]
+    if isinstance(pad_val, tuple):
+        assert len(pad_val) == img.shape[-1]
+        vals = [float(v) for v in pad_val]
+    else:
+        vals = [float(pad_val)] + [0.0] * (bands - 1)
+        if bands > 4 and float(pad_val) != 0.0:
+            raise Exception("cv2.copyMakeBorder: a scalar border value must be 0 for images with more than 4 channels")
+    mode = {"constant": "constant", "edge": "edge", "reflect": "reflect", "symmetric": "symmetric"}[padding_mode]
+    planes = img[..., None] if img.ndim == 2 else img
+    out = []
+    for c in range(bands):
+        if mode == "constant":
+            v = vals[c]
+            if np.issubdtype(img.dtype, np.integer):
+                info = np.iinfo(img.dtype)
+                v = int(min(max(np.rint(v), info.min), info.max))
+            out.append(np.pad(planes[..., c], ((top, bottom), (left, right)), mode="constant", constant_values=v))
+        else:
+            out.append(np.pad(planes[..., c], ((top, bottom), (left, right)), mode=mode))
+    res = np.stack(out, -1).astype(img.dtype, copy=False)
+    return res[..., 0] if bands == 1 else res          # OpenCV drops a single-band axis: (H, W, 1) comes back as (H', W')
+
+
+def hex_impad_to_multiple(img, divisor, pad_val=0):
+    """geometry_np.py:734-749."""
+    img = np.asarray(img)
+    pad_h = int(np.ceil(img.shape[0] / divisor)) * divisor
+    pad_w = int(np.ceil(img.shape[1] / divisor)) * divisor
+    return heximpad(img, shape=(pad_h, pad_w), pad_val=pad_val)

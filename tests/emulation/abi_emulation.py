@@ -67,6 +67,12 @@ def emulated_call(name, *a):
         for b in range(B):
             for c in range(Cn):
                 o[b * bs + c * cs + t[keep]] = g[b, c][keep]
+    elif name == "hg_pad2d":
+        x, y, planes, H, W, pl, pr, pt, pb, mode, value, dt, _ = a
+        s = view(x, planes * H * W, dt).reshape(planes, H, W)
+        np_mode = {0: "constant", 1: "reflect", 2: "edge", 3: "wrap", 4: "symmetric"}[mode]
+        kw = {"constant_values": NP[dt](value)} if mode == 0 else {}
+        view(y, planes * (H + pt + pb) * (W + pl + pr), dt)[:] = np.pad(s, ((0, 0), (pt, pb), (pl, pr)), mode=np_mode, **kw).reshape(-1)
     elif name == "hg_host_hex2rect":
         src, dst, xs, ys, c, h, w, h1, w1, sdt, ddt, interp, _, _ = a
         s = view(src, c * h * w, sdt).reshape(c, h, w)
@@ -132,8 +138,10 @@ def main():
     body(T3.test_gpu_mosaic_equals_the_oracle_raster)(); print("ok hex mosaic")
     body(T4.test_gpu_module_returns_the_numba_fixture)(numba); print("ok numba twin: resampler and warp")
     body(T4.test_gpu_hexresize_follows_the_numpy_twin)(); print("ok numba twin: hexresize")
+    import test_zz_heximpad as T5
+    body(T5.test_gpu_heximpad_returns_the_reference_arrays)(np.load(T5.GOLDEN)); print("ok heximpad")
     used = sorted(set(calls))
-    assert {"hg_plane_gather", "hg_plane_scatter", "hg_host_hex2rect", "hg_hexwarp_linear", "hg_hexwarp_nearest"} <= set(used), used
+    assert {"hg_plane_gather", "hg_plane_scatter", "hg_host_hex2rect", "hg_hexwarp_linear", "hg_hexwarp_nearest", "hg_pad2d"} <= set(used), used
     print("emulated entry points:", ", ".join(used))
 
 

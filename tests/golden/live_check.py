@@ -165,6 +165,21 @@ def main():
         yo = HO.hex_conv_transpose2d(x, m.kernel.detach(), m.bias.detach(), off, r, s_)
         assert yo.shape == yr.shape and float((yo - yr).abs().max()) <= 1e-5 * max(1.0, float(yr.abs().max())), "transposed conv"
         checked += 1
+    # heximpad (geometry_np.py:683-732) through cv2, with the one name the reference forgets to import injected
+    import numbers
+    import make_impad_golden as MI
+    gnp.numbers = numbers
+    for _ in range(60):
+        img, kw = MI.random_case(rng)
+        try:
+            ref = gnp.heximpad(img.copy(), **kw)
+        except Exception:
+            try:
+                O.heximpad(img, **kw)
+            except Exception:
+                continue
+            raise AssertionError(f"heximpad: the reference raises but the oracle does not ({kw}, {img.shape}, {img.dtype})")
+        eq(O.heximpad(img, **kw), ref, f"heximpad {kw} {img.shape} {img.dtype}")
     print(f"live reference check ok: {checked} comparisons")
 
 
