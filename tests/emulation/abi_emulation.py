@@ -78,6 +78,29 @@ def emulated_call(name, *a):
         s = view(src, c * h * w, sdt).reshape(c, h, w)
         r = O.hexsrc_resample(s, view(xs, h1, nv.F64)[:, None], view(ys, w1, nv.F64)[None, :], interp)
         view(dst, c * h1 * w1, ddt)[:] = np.asarray(r).reshape(-1).astype(NP[ddt])
+    elif name == "hg_host_rect2hex":          # the oracle's two stages on the caller's own coordinate tables
+        src, dst, xs, ys, c, h, w, h1, w1, sdt, ddt, interp, _, _ = a
+        s = view(src, c * h * w, sdt).reshape(c, h, w)
+        i_n, i_f, j_n, j_f = O.rect2hex_index(h, w, view(xs, h1, nv.F64), view(ys, w1, nv.F64))
+        def tap(ii, jj):
+            ok = ((ii >= 0) & (ii < h))[:, None] & ((jj >= 0) & (jj < w))[None, :]
+            return np.where(ok, s[:, np.clip(ii, 0, h - 1)][:, :, np.clip(jj, 0, w - 1)], 0)
+        if interp == 0:
+            r = tap(i_n, j_n)
+        else:                                  # geometry_np.py:514-517
+            p1, p2, p3, p4 = (tap(i_n, j_n).astype(np.float64), tap(i_n, j_n + 1).astype(np.float64),
+                              tap(i_n + 1, j_n).astype(np.float64), tap(i_n + 1, j_n + 1).astype(np.float64))
+            fi, fj = i_f[None, :, None], j_f[None, None, :]
+            t1 = fi * p3 + (1 - fi) * p1
+            t2 = fi * p4 + (1 - fi) * p2
+            r = fj * t2 + (1 - fj) * t1
+        view(dst, c * h1 * w1, ddt)[:] = np.asarray(r).reshape(-1).astype(NP[ddt])
+    elif name in ("hg_hex_to_type1", "hg_hex_to_type2"):
+        hexp, t, planes, H, W, off, sdt, ddt, _ = a
+        s = view(hexp, planes * H * W, sdt).reshape(planes, H, W)
+        fn = O.hex_to_type1 if name.endswith("1") else O.hex_to_type2
+        r = np.asarray(fn(s, off, NP[ddt]))
+        view(t, r.size, ddt)[:] = r.reshape(-1)
     elif name in ("hg_hexwarp_linear", "hg_hexwarp_nearest"):
         if name == "hg_hexwarp_linear":
             src, dst, cx, cy, f32, planes, h, w, h1, w1, sdt, ddt, _ = a
@@ -98,6 +121,16 @@ def install():
     nv.require_cuda = lambda t, what="tensor": t
     nv.stream_ptr = lambda device=None: None
     torch.Tensor.cuda = lambda self, *a, **k: self.detach().clone()
+    real_to = torch.Tensor.to
+
+    def is_cuda_device(v):
+        return (isinstance(v, torch.device) and v.type == "cuda") or (isinstance(v, str) and v.startswith("cuda"))
+
+    def to(self, *a, **k):                    # .to(<cuda device>) stays on the CPU
+        a = tuple("cpu" if is_cuda_device(v) else v for v in a)
+        k = {key: ("cpu" if is_cuda_device(v) else v) for key, v in k.items()}
+        return real_to(self, *a, **k)
+    torch.Tensor.to = to
     torch.cuda.is_available = lambda: True
     torch.cuda.current_device = lambda: 0
     _hostapi.device_index = lambda device=None: 0
@@ -109,16 +142,6 @@ def install():
         return torch.from_numpy(np.ascontiguousarray(img))
     for m in (_hostapi, _G, _GN, _GT):
         m.to_device = to_device
-    tables = Fn._tables.__wrapped__
-    real_device = torch.device
-
-    def cpu_tables(kind, h, w, h1, w1, twin, device):
-        torch.device = lambda *a, **k: real_device("cpu")
-        try:
-            return tables(kind, h, w, h1, w1, twin, "cpu")
-        finally:
-            torch.device = real_device
-    Fn._tables = cpu_tables
     # HexConvTranspose2d calls the hex conv through HexFrames.hexconv2d: the (differentiable) oracle stands in for the kernels
     hf.hexconv2d = lambda x, kernel, bias=None, even_odd_offset=0, radius=2, stride=1, padding=0, dilation=1, groups=1, **kw: \
         HO.hexconv2d(x.float(), kernel, bias, even_odd_offset, radius, stride, padding, dilation, groups)
@@ -138,6 +161,12 @@ def main():
     body(T3.test_gpu_mosaic_equals_the_oracle_raster)(); print("ok hex mosaic")
     body(T4.test_gpu_module_returns_the_numba_fixture)(numba); print("ok numba twin: resampler and warp")
     body(T4.test_gpu_hexresize_follows_the_numpy_twin)(); print("ok numba twin: hexresize")
+    import test_zz_numpy_api as T6
+    golden = np.load(os.path.join(ROOT, "tests", "golden", "resample_golden.npz"))
+    body(T6.test_geometry_np_against_the_reference_outputs)(golden); print("ok geometry_np")
+    body(T6.test_geometry_torch_against_the_reference_outputs)(golden); print("ok geometry_torch")
+    body(T6.test_error_behaviour_of_the_numpy_api)(); print("ok numpy api errors")
+    body(T6.test_image_and_heximage_classes)(golden); print("ok IMAGE / HEXIMAGE")
     import test_zz_heximpad as T5
     body(T5.test_gpu_heximpad_returns_the_reference_arrays)(np.load(T5.GOLDEN)); print("ok heximpad")
     used = sorted(set(calls))
