@@ -71,7 +71,9 @@ def hexresize(image, dsize, interpolation="linear", offset=0):
 def heximpad(img: np.ndarray, *, shape: Optional[Tuple[int, int]] = None, padding: Union[int, tuple, None] = None,
              pad_val: Union[float, List] = 0, padding_mode: str = 'constant') -> np.ndarray:
     """geometry_np.py:683-732: pad an (H, W[, C]) image; the top pad is rounded down to an even number of
-    rows (and the remainder moved to the bottom) so that the row parity of the hex lattice is kept."""
+    rows (and the remainder moved to the bottom) so that the row parity of the hex lattice is kept.
+    Limitation: ``'reflect'`` needs every pad smaller than the image side (one bounce, like ``F.pad``); OpenCV
+    would keep bouncing -- the library call reports that case instead of guessing."""
     assert (shape is not None) ^ (padding is not None)
     if shape is not None:
         width = max(shape[1] - img.shape[1], 0)
