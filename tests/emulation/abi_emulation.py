@@ -43,6 +43,124 @@ def f32_to_bf16(x):
     return torch.from_numpy(np.ascontiguousarray(x)).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
 
 
+def tensor(ptr, shape, dt):
+    """float32 torch tensor holding the values of a raw buffer of hg dtype ``dt``."""
+    n = int(np.prod(shape))
+    raw = view(ptr, n, dt)
+    vals = bf16_to_f32(raw) if dt == nv.BF16 else raw.astype(np.float32 if dt != nv.F64 else np.float64)
+    return torch.from_numpy(np.ascontiguousarray(vals)).reshape(tuple(int(v) for v in shape))
+
+
+def store(ptr, t, dt):
+    flat = t.detach().reshape(-1)
+    out = view(ptr, flat.numel(), dt)
+    out[:] = f32_to_bf16(flat.float().numpy()) if dt == nv.BF16 else flat.numpy().astype(NP[dt])
+
+
+def conv_entry(name, a):
+    """hg_hexconv_*: the oracle's closed form (and autograd through it) on the descriptor's geometry."""
+    d = a[0]._obj
+    eo = (d.parity - d.pad) % 2                # the oracle re-derives the parity from even_odd_offset + padding
+    K = 3 * d.radius * d.radius - 3 * d.radius + 1
+    wshape = (d.Cout, d.Cin // d.groups, 1, K)
+
+    def run(x, w, b):
+        return HO.hexconv2d(x, w, b, eo, d.radius, d.stride, d.pad, d.dilation, d.groups, "constant", d.pad_value)
+    if name in ("hg_hexconv_fwd", "hg_hexconv_fwd_affine"):
+        if name == "hg_hexconv_fwd":
+            _, x, w, b, y, _ = a
+            scale = None
+        else:
+            _, x, w, scale, b, y, _ = a
+        xt, wt = tensor(x, (d.N, d.Cin, d.H, d.W), d.x_dtype), tensor(w, wshape, nv.F32)
+        out = run(xt, wt, None)
+        if scale is not None and scale.value:
+            out = out * tensor(scale, (d.Cout,), nv.F32).view(1, -1, 1, 1)
+        if b is not None and b.value:
+            out = out + tensor(b, (d.Cout,), nv.F32).view(1, -1, 1, 1)
+        assert tuple(out.shape) == (d.N, d.Cout, d.Ho, d.Wo), (tuple(out.shape), d.Ho, d.Wo)
+        store(y, out.clamp_min(0) if d.relu else out, d.y_dtype)
+    elif name == "hg_hexconv_dgrad":          # (the product's backward runs under no_grad: re-enable it for the oracle)
+        _, gy, w, gx, _ = a
+        xt = torch.zeros(d.N, d.Cin, d.H, d.W, requires_grad=True)
+        with torch.enable_grad():
+            run(xt, tensor(w, wshape, nv.F32), None).backward(tensor(gy, (d.N, d.Cout, d.Ho, d.Wo), d.y_dtype))
+        store(gx, xt.grad, d.x_dtype)
+    else:
+        _, x, gy, gw, gb, _ = a
+        wt = torch.zeros(wshape, requires_grad=True)
+        bt = torch.zeros(d.Cout, requires_grad=True)
+        with torch.enable_grad():
+            run(tensor(x, (d.N, d.Cin, d.H, d.W), d.x_dtype), wt, bt).backward(tensor(gy, (d.N, d.Cout, d.Ho, d.Wo), d.y_dtype))
+        view(gw, wt.numel(), nv.F32)[:] += wt.grad.reshape(-1).numpy()           # accumulates, like the kernel
+        if gb is not None and gb.value:
+            view(gb, d.Cout, nv.F32)[:] += bt.grad.numpy()
+
+
+def bn_entry(name, a):
+    """hg_bn_*: the formulas of include/hygrid_b200.h in float64 (float32 where the header says so)."""
+    def f32(ptr, n):
+        return view(ptr, n, nv.F32) if ptr is not None and getattr(ptr, "value", ptr) else None
+    if name == "hg_bn_stats":
+        x, sums, N, Cn, HW, _ = a
+        xs = view(x, N * Cn * HW, nv.F32).reshape(N, Cn, HW).astype(np.float64)
+        out = view(sums, 2 * Cn, nv.F64)
+        out[0::2] += xs.sum((0, 2))
+        out[1::2] += (xs * xs).sum((0, 2))
+        return
+    if name == "hg_bn_apply":
+        x, y, sums, mean_in, var_in, gamma, beta, mean_out, var_out, rstd_out, N, Cn, HW, eps, relu, _ = a
+        eps = eps.value if hasattr(eps, "value") else float(eps)
+        xs = view(x, N * Cn * HW, nv.F32).reshape(N, Cn, HW)
+        if sums is not None and getattr(sums, "value", sums):
+            sm = view(sums, 2 * Cn, nv.F64)
+            n = N * HW
+            mean = sm[0::2] / n
+            var = np.maximum(sm[1::2] / n - mean * mean, 0.0)
+        else:
+            mean, var = f32(mean_in, Cn).astype(np.float64), f32(var_in, Cn).astype(np.float64)
+        rstd = 1.0 / np.sqrt(var + eps)
+        g, b = f32(gamma, Cn), f32(beta, Cn)
+        scale = ((g if g is not None else 1.0) * rstd).astype(np.float32)
+        shift = (-(mean.astype(np.float32)) * scale + (b if b is not None else 0.0)).astype(np.float32)
+        out = xs * scale[None, :, None] + shift[None, :, None]
+        view(y, N * Cn * HW, nv.F32)[:] = (np.maximum(out, 0) if relu else out).reshape(-1)
+        for ptr, val in ((mean_out, mean), (var_out, var), (rstd_out, rstd)):
+            if f32(ptr, Cn) is not None:
+                f32(ptr, Cn)[:] = val.astype(np.float32)
+        return
+    if name == "hg_bn_bwd_reduce":
+        x, dy, mean, rstd, gamma, beta, dsums, N, Cn, HW, relu, _ = a
+        training = None
+    else:
+        x, dy, mean, rstd, gamma, beta, dsums, dx, dgamma, dbeta, N, Cn, HW, relu, training, _ = a
+    xs = view(x, N * Cn * HW, nv.F32).reshape(N, Cn, HW).astype(np.float64)
+    dz = view(dy, N * Cn * HW, nv.F32).reshape(N, Cn, HW).astype(np.float64)
+    mu, rs = f32(mean, Cn).astype(np.float64)[None, :, None], f32(rstd, Cn).astype(np.float64)[None, :, None]
+    g, b = f32(gamma, Cn), f32(beta, Cn)
+    gam = (g.astype(np.float64) if g is not None else np.ones(Cn))[None, :, None]
+    xhat = (xs - mu) * rs
+    if relu:
+        z = xhat * gam + (b.astype(np.float64) if b is not None else np.zeros(Cn))[None, :, None]
+        dz = np.where(z > 0, dz, 0.0)
+    if name == "hg_bn_bwd_reduce":
+        out = view(dsums, 2 * Cn, nv.F64)
+        out[0::2] += dz.sum((0, 2))
+        out[1::2] += (dz * xhat).sum((0, 2))
+        return
+    ds = view(dsums, 2 * Cn, nv.F64)
+    n = N * HW
+    if training:
+        res = gam * rs * (dz - ds[0::2][None, :, None] / n - xhat * ds[1::2][None, :, None] / n)
+    else:
+        res = gam * rs * dz
+    view(dx, N * Cn * HW, nv.F32)[:] = res.reshape(-1).astype(np.float32)
+    if f32(dgamma, Cn) is not None:
+        f32(dgamma, Cn)[:] = ds[1::2].astype(np.float32)
+    if f32(dbeta, Cn) is not None:
+        f32(dbeta, Cn)[:] = ds[0::2].astype(np.float32)
+
+
 real_call = nv.call
 calls = []
 
@@ -67,6 +185,18 @@ def emulated_call(name, *a):
         for b in range(B):
             for c in range(Cn):
                 o[b * bs + c * cs + t[keep]] = g[b, c][keep]
+    elif name in ("hg_hexconv_fwd", "hg_hexconv_fwd_affine", "hg_hexconv_dgrad", "hg_hexconv_wgrad"):
+        conv_entry(name, a)
+    elif name.startswith("hg_bn_"):
+        bn_entry(name, a)
+    elif name == "hg_pad2d_bwd":              # adjoint of the pad through autograd on F.pad
+        gy, gx, planes, H, W, pl, pr, pt, pb, mode, dt, _ = a
+        g = tensor(gy, (planes, H + pt + pb, W + pl + pr), dt)
+        x = torch.zeros(1, planes, H, W, dtype=torch.float64, requires_grad=True)
+        tmode = {0: "constant", 1: "reflect", 2: "replicate", 3: "circular"}[mode]
+        with torch.enable_grad():
+            torch.nn.functional.pad(x, (pl, pr, pt, pb), mode=tmode).backward(g[None].double())
+        store(gx, x.grad[0], dt)
     elif name == "hg_pad2d":
         x, y, planes, H, W, pl, pr, pt, pb, mode, value, dt, _ = a
         s = view(x, planes * H * W, dt).reshape(planes, H, W)
@@ -142,6 +272,12 @@ def install():
         return torch.from_numpy(np.ascontiguousarray(img))
     for m in (_hostapi, _G, _GN, _GT):
         m.to_device = to_device
+    from HyGrid import _norm
+    _norm.bn_supported = lambda bn, x: (type(bn) is torch.nn.BatchNorm2d and isinstance(x, torch.Tensor) and x.dim() == 4
+                                        and x.dtype == torch.float32 and x.numel() > 0
+                                        and (bn.weight is None or bn.weight.dtype == torch.float32))   # = the product's rule minus is_cuda
+    real_query = nv.query
+    nv.query = lambda name, *a: 0 if name == "hg_hexconv_umma_eligible" else real_query(name, *a)   # no tcgen05 routing here
     # HexConvTranspose2d calls the hex conv through HexFrames.hexconv2d: the (differentiable) oracle stands in for the kernels
     hf.hexconv2d = lambda x, kernel, bias=None, even_odd_offset=0, radius=2, stride=1, padding=0, dilation=1, groups=1, **kw: \
         HO.hexconv2d(x.float(), kernel, bias, even_odd_offset, radius, stride, padding, dilation, groups)
@@ -167,6 +303,14 @@ def main():
     body(T6.test_geometry_torch_against_the_reference_outputs)(golden); print("ok geometry_torch")
     body(T6.test_error_behaviour_of_the_numpy_api)(); print("ok numpy api errors")
     body(T6.test_image_and_heximage_classes)(golden); print("ok IMAGE / HEXIMAGE")
+    import test_zz_hexconvmodule_variants as T7
+    for order in T7.ORDERS:
+        body(T7.test_every_order_with_batchnorm_and_relu)(order)
+    print("ok HexConvModule: 6 orders x flags x train/eval x grad")
+    params = [m.args[1] for m in T7.test_layer_types_padding_modes_and_flags.pytestmark if m.name == "parametrize"][0]
+    for cfg in params:
+        body(T7.test_layer_types_padding_modes_and_flags)(cfg)
+    print(f"ok HexConvModule: {len(params)} layer / padding / flag variants")
     import test_zz_heximpad as T5
     body(T5.test_gpu_heximpad_returns_the_reference_arrays)(np.load(T5.GOLDEN)); print("ok heximpad")
     used = sorted(set(calls))

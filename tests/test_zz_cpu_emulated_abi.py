@@ -12,5 +12,5 @@ def test_python_layer_against_the_emulated_c_abi():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emulation", "abi_emulation.py")], capture_output=True,
                        text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-3000:])
-    assert r.stdout.count("\nok ") + r.stdout.startswith("ok ") == 11, r.stdout
+    assert r.stdout.count("\nok ") + r.stdout.startswith("ok ") == 13, r.stdout
     assert "emulated entry points:" in r.stdout
