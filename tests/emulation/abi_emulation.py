@@ -32,6 +32,8 @@ def view(ptr, n, dt):
     """numpy view of ``n`` elements of hg dtype ``dt`` at a raw pointer (bfloat16 as its uint16 bit pattern)."""
     addr = ptr.value if hasattr(ptr, "value") else ptr
     ct = C.c_uint16 if dt == nv.BF16 else CT[NP[dt]]
+    if n == 0 or not addr:
+        return np.zeros(0, np.uint16 if dt == nv.BF16 else NP[dt])       # empty tensors come with a null pointer
     return np.ctypeslib.as_array((ct * n).from_address(addr))
 
 
@@ -278,9 +280,6 @@ def install():
                                         and (bn.weight is None or bn.weight.dtype == torch.float32))   # = the product's rule minus is_cuda
     real_query = nv.query
     nv.query = lambda name, *a: 0 if name == "hg_hexconv_umma_eligible" else real_query(name, *a)   # no tcgen05 routing here
-    # HexConvTranspose2d calls the hex conv through HexFrames.hexconv2d: the (differentiable) oracle stands in for the kernels
-    hf.hexconv2d = lambda x, kernel, bias=None, even_odd_offset=0, radius=2, stride=1, padding=0, dilation=1, groups=1, **kw: \
-        HO.hexconv2d(x.float(), kernel, bias, even_odd_offset, radius, stride, padding, dilation, groups)
 
 
 def main():
