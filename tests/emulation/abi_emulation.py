@@ -66,7 +66,11 @@ def conv_entry(name, a):
     K = 3 * d.radius * d.radius - 3 * d.radius + 1
     wshape = (d.Cout, d.Cin // d.groups, 1, K)
 
-    def run(x, w, b):
+    op = {"hg_hexconv_fwd": 0, "hg_hexconv_fwd_affine": 0, "hg_hexconv_dgrad": 1, "hg_hexconv_wgrad": 2}[name]
+    tc = d.algo == 2 or (d.algo == 0 and umma_eligible(d, op))
+    bf = (lambda t: t.bfloat16().float()) if tc else (lambda t: t)   # the tcgen05 kernels read activations and weights as bfloat16
+
+    def run(x, w, b):                          # callers round the operands the kernel reads (never the autograd leaf)
         return HO.hexconv2d(x, w, b, eo, d.radius, d.stride, d.pad, d.dilation, d.groups, "constant", d.pad_value)
     if name in ("hg_hexconv_fwd", "hg_hexconv_fwd_affine"):
         if name == "hg_hexconv_fwd":
@@ -75,9 +79,9 @@ def conv_entry(name, a):
         else:
             _, x, w, scale, b, y, _ = a
         xt, wt = tensor(x, (d.N, d.Cin, d.H, d.W), d.x_dtype), tensor(w, wshape, nv.F32)
-        out = run(xt, wt, None)
-        if scale is not None and scale.value:
-            out = out * tensor(scale, (d.Cout,), nv.F32).view(1, -1, 1, 1)
+        if scale is not None and scale.value:       # folded into the weights on their way into shared memory (before the bf16 rounding)
+            wt = wt * tensor(scale, (d.Cout,), nv.F32).view(-1, 1, 1, 1)
+        out = run(bf(xt), bf(wt), None)
         if b is not None and b.value:
             out = out + tensor(b, (d.Cout,), nv.F32).view(1, -1, 1, 1)
         assert tuple(out.shape) == (d.N, d.Cout, d.Ho, d.Wo), (tuple(out.shape), d.Ho, d.Wo)
@@ -86,14 +90,14 @@ def conv_entry(name, a):
         _, gy, w, gx, _ = a
         xt = torch.zeros(d.N, d.Cin, d.H, d.W, requires_grad=True)
         with torch.enable_grad():
-            run(xt, tensor(w, wshape, nv.F32), None).backward(tensor(gy, (d.N, d.Cout, d.Ho, d.Wo), d.y_dtype))
+            run(xt, bf(tensor(w, wshape, nv.F32)), None).backward(bf(tensor(gy, (d.N, d.Cout, d.Ho, d.Wo), d.y_dtype)))
         store(gx, xt.grad, d.x_dtype)
     else:
         _, x, gy, gw, gb, _ = a
         wt = torch.zeros(wshape, requires_grad=True)
         bt = torch.zeros(d.Cout, requires_grad=True)
         with torch.enable_grad():
-            run(tensor(x, (d.N, d.Cin, d.H, d.W), d.x_dtype), wt, bt).backward(tensor(gy, (d.N, d.Cout, d.Ho, d.Wo), d.y_dtype))
+            run(bf(tensor(x, (d.N, d.Cin, d.H, d.W), d.x_dtype)), wt, bt).backward(bf(tensor(gy, (d.N, d.Cout, d.Ho, d.Wo), d.y_dtype)))
         view(gw, wt.numel(), nv.F32)[:] += wt.grad.reshape(-1).numpy()           # accumulates, like the kernel
         if gb is not None and gb.value:
             view(gb, d.Cout, nv.F32)[:] += bt.grad.numpy()
@@ -165,6 +169,27 @@ def bn_entry(name, a):
 
 real_call = nv.call
 calls = []
+
+
+def umma_eligible(d, op):
+    """hg_hexconv_umma_eligible restated (csrc/hg_conv_umma.cu conv_umma_eligible, hg_conv_wgrad_umma.cu
+    conv_wgrad_umma_eligible) without their shared-memory fit check, which asks the device."""
+    if d.radius != 2 or d.stride != 1 or d.dilation != 1 or d.groups != 1:
+        return False
+    if op == 2:
+        ok = d.Cin % 16 == 0 and 16 <= d.Cin <= 1024 and d.Cout % 8 == 0 and 8 <= d.Cout <= 1024
+        return ok and not (d.algo == 0 and (d.x_dtype != nv.BF16 or d.Cin * d.Cout < 1024))
+    cred, nout = (d.Cin, d.Cout) if op == 0 else (d.Cout, d.Cin)
+    if cred % 16 or not 16 <= cred <= 512 or nout % 16 or not 16 <= nout <= 256 or (op == 1 and d.relu):
+        return False
+    return not (d.algo == 0 and ((d.x_dtype if op == 0 else d.y_dtype) != nv.BF16 or cred * nout < 1024))
+
+
+def real_query(name, dref, op):
+    assert name == "hg_hexconv_umma_eligible"
+    d = dref._obj
+    forced = type(d).from_buffer_copy(d)
+    return int(umma_eligible(forced, op))
 
 
 def emulated_call(name, *a):

@@ -17,11 +17,11 @@ def test_python_layer_against_the_emulated_c_abi():
 
 
 def test_gpu_test_bodies_against_the_emulated_c_abi():
-    """Every ``-m gpu`` test that does not need the hardware itself (autocast / tcgen05 routing, BASELINE-sized inputs,
-    pinned memory are deselected) passes with numpy / the oracle standing in for the kernels: the wrappers, autograd
+    """Every ``-m gpu`` test that does not need the hardware itself (BASELINE-sized inputs and pinned memory are
+    deselected) passes with numpy / the oracle standing in for the kernels: the wrappers, autograd
     Functions, modules and numpy shims hand the C ABI what include/hygrid_b200.h says."""
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emulation", "run_gpu_tests_on_cpu.py")], capture_output=True,
                        text=True, timeout=1800, cwd=ROOT)
     tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ""
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-2000:])
-    assert " passed" in tail and "failed" not in tail and int(tail.split(" passed")[0].split()[-1]) >= 180, tail
+    assert " passed" in tail and "failed" not in tail and int(tail.split(" passed")[0].split()[-1]) >= 220, tail
