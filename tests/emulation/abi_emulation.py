@@ -24,8 +24,9 @@ from HyGrid import _native as nv, HexFrames as hf, functional as Fn, _hostapi   
 import HyGrid.geometry as _G, HyGrid.geometry_np as _GN, HyGrid.geometry_torch as _GT   # noqa: E402
 from oracle import hexframes_oracle as HO, hygrid_oracle as O   # noqa: E402
 
-NP = {nv.U8: np.uint8, nv.F32: np.float32, nv.F64: np.float64, nv.I64: np.int64, nv.U16: np.uint16}
-CT = {np.uint8: C.c_uint8, np.float32: C.c_float, np.float64: C.c_double, np.int64: C.c_int64, np.uint16: C.c_uint16}
+NP = {nv.U8: np.uint8, nv.I16: np.int16, nv.I32: np.int32, nv.I64: np.int64, nv.F32: np.float32, nv.F64: np.float64, nv.U16: np.uint16}
+CT = {np.uint8: C.c_uint8, np.int16: C.c_int16, np.int32: C.c_int32, np.int64: C.c_int64, np.float32: C.c_float, np.float64: C.c_double,
+      np.uint16: C.c_uint16}
 
 
 def view(ptr, n, dt):

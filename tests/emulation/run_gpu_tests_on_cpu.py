@@ -121,7 +121,6 @@ def globalpool_entry(name, a):
             side = np.where(np.take_along_axis(nan, side[:, None], -1)[:, 0], -1, side)
         store(y, torch.from_numpy(out), dt)
         if aux is not None and getattr(aux, "value", aux):
-            view(aux, planes, nv.I32 if nv.I32 in NP else nv.I32)
             np.ctypeslib.as_array((E.C.c_int32 * planes).from_address(aux.value))[:] = side.astype(np.int32)
         return
     gy, x, aux, gx, planes, L, method, dt, _ = a
@@ -248,8 +247,6 @@ def main(argv):
     nv.query = query
     nv.launch_count = lambda: LAUNCHES[0]
     nv.reset_launch_count = lambda: LAUNCHES.__setitem__(0, 0)
-    NP.setdefault(nv.I32, np.int32)
-    E.CT.setdefault(np.int32, E.C.c_int32)
     os.chdir(ROOT)
     files = [a for a in argv if not a.startswith("-")] or ["tests/test_gpu_hexframes.py", "tests/test_gpu_resample.py"] + \
         sorted(f"tests/{f}" for f in os.listdir("tests") if f.startswith("test_zz_") and f != "test_zz_cpu_emulated_abi.py")

@@ -25,3 +25,9 @@ def test_gpu_test_bodies_against_the_emulated_c_abi():
     tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ""
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-2000:])
     assert " passed" in tail and "failed" not in tail and int(tail.split(" passed")[0].split()[-1]) >= 220, tail
+
+
+def test_smoke_and_bench_step_against_the_emulated_c_abi():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emulation", "smoke_on_cpu.py")], capture_output=True,
+                       text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0 and "ok smoke and bench step" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
