@@ -111,9 +111,9 @@ def test_gpu_module_matches_fixture_and_oracle(golden):
         xo, ko = x.clone().requires_grad_(True), kernel.clone().requires_grad_(True)
         bo = bias.clone().requires_grad_(True) if bias is not None else None
         HO.hex_conv_transpose2d(xo, ko, bo, eo, r, st, g).backward(gy.cpu())
-        for got, ref in ((xg.grad, xo.grad), (m.kernel.grad, ko.grad)) + (((m.bias.grad, bo.grad),) if bias is not None else ()):
-            tol = 1e-4 * max(1.0, float(ref.abs().max()))
-            assert float((got.cpu() - ref).abs().max()) <= tol
+        # tolerances of tests/test_gpu_hexframes.py: data gradient 1e-4, weight / bias gradient (float atomics) 1e-3 of the range
+        for got, ref, rel in ((xg.grad, xo.grad, 1e-4), (m.kernel.grad, ko.grad, 1e-3)) + (((m.bias.grad, bo.grad, 1e-3),) if bias is not None else ()):
+            assert float((got.cpu() - ref).abs().max()) <= rel * max(1.0, float(ref.abs().max()))
 
 
 def test_selection_table_is_split_into_injective_layers_for_the_adjoint():
