@@ -124,6 +124,9 @@ class _HexConvFn(torch.autograd.Function):
         ctx.has_bias = bias is not None
         ctx.param_dtypes = (kernel.dtype, bias.dtype if bias is not None else None)
         ctx.out_shape = (Ho, Wo)
+        # gradient sinks (HyGrid.distributed.FlatGradBucket): the weight-gradient kernel accumulates straight into the
+        # all-reduce bucket instead of a zero-filled temporary that autograd then adds to .grad
+        ctx.sinks = (getattr(kernel, "_hg_grad_sink", None), getattr(bias, "_hg_grad_sink", None) if bias is not None else None)
         return y
 
     @staticmethod
@@ -146,7 +149,6 @@ class _HexConvFn(torch.autograd.Function):
             gx = torch.empty_like(x)
             nv.call("hg_hexconv_dgrad", C.byref(pick(1)), nv.ptr(gy), nv.ptr(w), nv.ptr(gx), st)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            gb = torch.zeros(w.shape[0], dtype=torch.float32, device=x.device) if ctx.has_bias else None
             Cin = x.shape[1]
             xw, dw = x, pick(2)
             if Cin < 16 and groups == 1 and algo != 1 and x.dtype == torch.bfloat16:
@@ -157,13 +159,29 @@ class _HexConvFn(torch.autograd.Function):
                 if nv.query("hg_hexconv_umma_eligible", C.byref(dp), 2):
                     dp.algo = 2
                     xw, dw = xp, dp
+            sink_w, sink_b = ctx.sinks
+            if xw is not x or sink_w is None or tuple(sink_w.view.shape) != tuple(w.shape):
+                sink_w = None
+            if not ctx.has_bias or sink_b is None:
+                sink_b = None
             cin_w = w.shape[1] if xw is x else xw.shape[1]          # Cin / groups, or the padded channel count
-            gw = torch.zeros((w.shape[0], cin_w) + tuple(w.shape[2:]), dtype=torch.float32, device=x.device)
+            gw = sink_w.view if sink_w is not None else \
+                torch.zeros((w.shape[0], cin_w) + tuple(w.shape[2:]), dtype=torch.float32, device=x.device)
+            gb = None
+            if ctx.has_bias:
+                gb = sink_b.view if sink_b is not None else torch.zeros(w.shape[0], dtype=torch.float32, device=x.device)
             nv.call("hg_hexconv_wgrad", C.byref(dw), nv.ptr(xw), nv.ptr(gy), nv.ptr(gw), nv.ptr(gb), st)
-            if xw is not x:
-                gw = gw[:, :Cin].contiguous()
-            gw = gw.to(ctx.param_dtypes[0])
-            if gb is not None:
+            if sink_w is not None:
+                gw = None
+                sink_w.landed()
+            else:
+                if xw is not x:
+                    gw = gw[:, :Cin].contiguous()
+                gw = gw.to(ctx.param_dtypes[0])
+            if sink_b is not None:
+                gb = None
+                sink_b.landed()
+            elif gb is not None:
                 gb = gb.to(ctx.param_dtypes[1])
         return gx, gw, gb, None, None
 
@@ -305,7 +323,7 @@ class HexConv2dAdaptivePadding(HexConv2d):
         return (f"HexConv2dAdaptivePadding({self.in_channels}, {self.out_channels}, kernel_radius={self.hexkernel_radius}, "
                 f"stride={self.sh}, padding={self.pad}, dilation={self.dilation}, groups={self.groups}, bias={self.b})")
 
-    def forward(self, input: Tensor, relu: bool = False) -> Tensor:
+    def forward(self, input: Tensor, relu: bool = False, affine=None) -> Tensor:
         input = pad(input, self.pad, self.padding_mode, self.padding_value)
         self.pad = 0
         img_h, img_w = input.size()[-2:]
@@ -318,7 +336,7 @@ class HexConv2dAdaptivePadding(HexConv2d):
         input = _as4(self._activation(input)[0])
         if pad_h > 0 or pad_w > 0:
             input = _pad4(input, pad_w // 2, pad_w - pad_w // 2, pad_h // 2, pad_h - pad_h // 2)
-        return super().forward(input, relu)
+        return super().forward(input, relu, affine)
 
 
 # ------------------------------------------------------------------------------------------------

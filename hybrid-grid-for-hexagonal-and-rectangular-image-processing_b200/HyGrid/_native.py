@@ -74,6 +74,8 @@ _SIGS = {
     "hg_hexconv_wgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],
     "hg_host_rect2hex": [_p, _p, _p, _p, _l, _l, _l, _l, _l, _i, _i, _i, _i, _i],
     "hg_host_hex2rect": [_p, _p, _p, _p, _l, _l, _l, _l, _l, _i, _i, _i, _i, _i],
+    "hg_host_hex_to_type": [_p, _p, _l, _l, _l, _i, _i, _i, _i, _i],
+    "hg_host_type_to_hex": [_p, _p, _l, _l, _l, _i, _i, _i, _i],
 }
 
 _lib = None
@@ -90,6 +92,7 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.hg_version.restype = C.c_int
         L.hg_last_error.restype = C.c_char_p
+        L.hg_last_launch.restype = C.c_char_p
         L.hg_launch_count.restype = C.c_int64
         L.hg_reset_launch_count.restype = None
         L.hg_host_release.restype = None
@@ -121,6 +124,11 @@ def call(name, *args):
         rc = getattr(L, name)(*args)
     if rc != 0:
         raise HyGridNativeError(f"{name} failed with code {rc}: {L.hg_last_error().decode()}")
+
+
+def last_launch() -> str:
+    """Kernel family of this thread's last launch (hg_last_launch)."""
+    return lib().hg_last_launch().decode()
 
 
 def launch_count() -> int:

@@ -6,6 +6,7 @@
 
 namespace hg {
 static thread_local char g_err[512] = "";
+static thread_local const char* g_last_launch = "";
 static std::atomic<int64_t> g_launches{0};   // process-wide: the autograd engine launches the backward kernels from its own thread
 
 void set_error(const char* fmt, ...) {
@@ -18,6 +19,7 @@ void count_launch(int n) { g_launches += n; }
 int finish_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   g_launches += 1;
+  g_last_launch = what;
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));
     return (int)e;
@@ -42,6 +44,7 @@ PFN_encodeTiled get_encode_tiled() {
 extern "C" {
 int hg_version(void) { return HG_VERSION; }
 const char* hg_last_error(void) { return hg::g_err; }
+const char* hg_last_launch(void) { return hg::g_last_launch; }
 int64_t hg_launch_count(void) { return hg::g_launches.load(); }
 void hg_reset_launch_count(void) { hg::g_launches.store(0); }
 }

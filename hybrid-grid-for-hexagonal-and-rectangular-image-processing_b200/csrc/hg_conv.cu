@@ -26,7 +26,7 @@ static int make_geom(const hg_conv_desc* d, ConvGeom& g, ConvTaps& tp) {
   HG_REQUIRE(d->H < (1 << 24) && d->W < (1 << 24) && d->N < (1ll << 31) && d->Cin < (1 << 24) && d->Cout < (1 << 24), HG_E_SHAPE, "conv shape too large");
   int64_t re, ro, cols;
   conv_out_shape(d->H + 2 * d->pad, d->W + 2 * d->pad, d->radius, d->stride, d->dilation, re, ro, cols);
-  HG_REQUIRE(re > 0 && ro > 0 && cols > 0 && (re - ro == 0 || re - ro == 1), HG_E_SHAPE,
+  HG_REQUIRE(re > 0 && ro >= 0 && cols > 0 && (re - ro == 0 || re - ro == 1), HG_E_SHAPE,
              "input %lldx%lld is too small for this hex kernel (even rows %lld, odd rows %lld, cols %lld)", (long long)d->H,
              (long long)d->W, (long long)re, (long long)ro, (long long)cols);
   HG_REQUIRE(d->Ho == re + ro && d->Wo == cols, HG_E_SHAPE, "output shape must be %lldx%lld (got %lldx%lld)", (long long)(re + ro),
@@ -61,7 +61,7 @@ int hg_hexconv_out_shape(int64_t H, int64_t W, int radius, int stride, int dilat
   HG_REQUIRE(H > 0 && W > 0 && radius >= 1 && stride >= 1 && dilation >= 1 && pad >= 0 && Ho && Wo, HG_E_ARG, "bad arguments");
   int64_t re, ro, cols;
   conv_out_shape(H + 2 * pad, W + 2 * pad, radius, stride, dilation, re, ro, cols);
-  HG_REQUIRE(re > 0 && ro > 0 && cols > 0 && (re - ro == 0 || re - ro == 1), HG_E_SHAPE,
+  HG_REQUIRE(re > 0 && ro >= 0 && cols > 0 && (re - ro == 0 || re - ro == 1), HG_E_SHAPE,
              "input %lldx%lld is too small for this hex kernel", (long long)H, (long long)W);
   *Ho = re + ro;
   *Wo = cols;

@@ -115,7 +115,10 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
     if (TMA) ptx::prefetch_tensormap(&tmap);
     ptx::fence_barrier_init();
   }
-  const uint32_t tmem_cols = 2 * P.Nout <= 32 ? 32 : 2 * P.Nout <= 64 ? 64 : 2 * P.Nout <= 128 ? 128 : 2 * P.Nout <= 256 ? 256 : 512;
+  // two accumulator stages of Nout columns; the epilogue always loads 32-column chunks, so the last chunk of stage 1
+  // may reach up to Nout + roundup32(Nout): the allocation covers that (Nout = 16: 64 columns, not 32)
+  const uint32_t tmem_need = (uint32_t)P.Nout + (((uint32_t)P.Nout + 31u) & ~31u);
+  const uint32_t tmem_cols = tmem_need <= 32 ? 32 : tmem_need <= 64 ? 64 : tmem_need <= 128 ? 128 : tmem_need <= 256 ? 256 : 512;
   if (warp == kUmMmaWarp) { ptx::tmem_alloc(tmem_slot, tmem_cols); ptx::tmem_relinquish(); }
   ptx::fence_proxy_async_smem();            // weight image written by the generic proxy, read by tcgen05.mma
   ptx::tc_fence_before_sync();

@@ -448,6 +448,10 @@ static int check_plane(int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t
 // hg_hexsrc_tma.cu: same contract
 int try_hexsrc_linear_tma(const void* src, void* dst, const double* xs, const double* ys, const double* host_xs, const double* host_ys,
                           int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1, int sdt, int ddt, int math, cudaStream_t st);
+// hg_resample_stream.cu: same contract; lattices of (almost) the same pitch (hex_dsize = None)
+int try_rect2hex_bilinear_stream(const void* src, void* dst, const double* xs, const double* ys, const double* host_xs,
+                                 const double* host_ys, int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1, int sdt,
+                                 int ddt, int math, cudaStream_t st);
 // hg_resample_tma.cu: HG_OK launched, 1 not applicable (fall back to the direct gather), else error
 int try_rect2hex_bilinear_tma(const void* src, void* dst, const double* xs, const double* ys, const double* host_xs,
                               const double* host_ys, int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1, int sdt,
@@ -621,6 +625,9 @@ int hg_rect2hex_bilinear(const void* src, void* dst, const double* xs, const dou
   HG_REQUIRE(math == HG_MATH_EXACT || math == HG_MATH_FAST, HG_E_ARG, "bad math mode %d", math);
   if (planes == 0 || h1 == 0 || w1 == 0) return HG_OK;
   cudaStream_t st = as_stream(stream);
+  // same-pitch lattices (hex_dsize = None): row-streaming kernel, no staging at all
+  rc = try_rect2hex_bilinear_stream(src, dst, xs, ys, host_xs, host_ys, planes, h, w, h1, w1, src_dtype, dst_dtype, math, st);
+  if (rc != 1) return rc;
   // TMA-staged tiles when the host copies of the tables are available and the lattices have similar pitch
   rc = try_rect2hex_bilinear_tma(src, dst, xs, ys, host_xs, host_ys, planes, h, w, h1, w1, src_dtype, dst_dtype, math, st);
   if (rc != 1) return rc;

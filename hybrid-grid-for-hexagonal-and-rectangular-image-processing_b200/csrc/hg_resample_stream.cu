@@ -1,0 +1,241 @@
+// hg_resample_stream.cu -- rect -> hex bilinear resampling between lattices of (almost) the SAME pitch: the
+// row-streaming kernel (sm_100a).
+//
+// ref: geometry_np.py:358-519 rect_to_hex_resample(img, hex_dsize=None | same size, 'bilinear').
+//
+// With hex_dsize = None (the API default; BASELINE configs 2 and 4) the output lattice has the size of the image and
+// the sample of output cell (a, b) sits at most one source cell up / left of it:
+//     j_n(b) - b in {-1, 0}   (or both taps outside the image: the last column, j_ = w exactly)
+//     i_n(a+1) - i_n(a) in {0, 1, 2}
+// (checked on the host against the very same float64 tables the kernel reads; anything else takes the TMA-tiled or the
+// direct-gather kernel).  Then no staging through shared memory is needed at all:
+//   * a lane owns FOUR ADJACENT output columns b0 .. b0+3 (b0 = 4 * lane inside a 128-column warp strip); the taps of
+//     those four outputs are source columns b0-1 .. b0+4 of two source rows;
+//   * per source row it loads ONE aligned 16-byte vector (columns b0 .. b0+3 -- the warp reads 512 contiguous bytes)
+//     and receives columns b0-1 and b0+4 from its neighbours by warp shuffle (the strip's two edge lanes load one
+//     scalar instead);
+//   * the warp walks DOWN its strip: every source row is loaded once and serves the two output rows that touch it
+//     (rows are prefetched two ahead in registers); out-of-range rows / columns are never loaded, they are the
+//     reference's zero fill;
+//   * float32 math blends horizontally first (once per source row, re-used by both output rows), then vertically;
+//     HG_MATH_EXACT evaluates the reference's float64 expression in its own operation order (vertical blends of the
+//     left and right taps, then the horizontal blend; geometry_np.py:514-517), so a float64 result is bit-identical;
+//   * every output row leaves as one 16-byte streaming store per lane (512 contiguous bytes per warp).
+// CTA = 8 warps = 8 adjacent strips (1024 columns) of one band of rows of one plane: the CTA streams whole 4 KB row
+// segments, top to bottom.
+#include "hg_common.cuh"
+#include <stdlib.h>
+#include <type_traits>
+
+namespace hg {
+
+constexpr int kStW = 128;          // columns per warp strip
+constexpr int kStWarps = 8;
+
+__device__ __forceinline__ void rect_axis_s(double coord, int n, int& idx, double& frac) {
+  // i_ = x_ + (h-1)*0.5 ; i_n = trunc(i_) ; i_f = i_ - float32(i_n)      (geometry_np.py:440-449)
+  const double c = dadd(coord, (double)(n - 1) * 0.5);
+  idx = trunc_i32(c);
+  frac = dsub(c, (double)(float)idx);
+}
+
+struct SrcRow {      // one source row as a lane holds it
+  float4 v;          // columns b0 .. b0+3
+  float e;           // lane 0: column c0 - 1; lane 31: column c0 + 128; otherwise unused
+};
+
+template <typename TD> __device__ __forceinline__ void store4(TD* p, const TD (&o)[4]);
+template <> __device__ __forceinline__ void store4<float>(float* p, const float (&o)[4]) {
+  __stcs(reinterpret_cast<float4*>(p), make_float4(o[0], o[1], o[2], o[3]));
+}
+template <> __device__ __forceinline__ void store4<double>(double* p, const double (&o)[4]) {
+  __stcs(reinterpret_cast<double2*>(p), make_double2(o[0], o[1]));
+  __stcs(reinterpret_cast<double2*>(p) + 1, make_double2(o[2], o[3]));
+}
+
+template <typename TD, bool EXACT, int PF>     // PF = source rows prefetched ahead in registers
+__global__ void __launch_bounds__(kStWarps * 32)
+rect2hex_stream_kernel(const float* __restrict__ src, TD* __restrict__ dst, const double* __restrict__ xs,
+                       const double* __restrict__ ys, int h, int w, int h1, int w1, int bands, int xgroups, int band_rows) {
+  using WT = typename std::conditional<EXACT, double, float>::type;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long blk = blockIdx.x;
+  const int xg = (int)(blk % xgroups); blk /= xgroups;
+  const int band = (int)(blk % bands);
+  const long long plane = blk / bands;
+  const int c0 = (xg * kStWarps + warp) * kStW;
+  if (c0 >= w1) return;                                    // whole warp: no shuffle partner is lost
+  const int b0 = c0 + 4 * lane;
+  const bool store_ok = b0 < w1;                           // w1 % 4 == 0: all four columns or none
+  const bool load_ok = b0 < w;                             // w  % 4 == 0
+  const bool edge_l = lane == 0 && c0 > 0, edge_r = lane == 31 && c0 + kStW < w;
+  const int edge_col = lane == 0 ? c0 - 1 : c0 + kStW;
+
+  // column tables of this lane: tap offset d = j_n - b in {-1, 0}, fraction, "both taps outside" flag
+  bool dm1[4], zero[4];
+  WT jf[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    int jn = 0; double f = 0.0;
+    if (store_ok) rect_axis_s(ys[b0 + c], w, jn, f);
+    dm1[c] = jn - (b0 + c) == -1;
+    zero[c] = jn >= w || jn <= -2;
+    jf[c] = (WT)f;
+  }
+
+  const float* __restrict__ sp = src + plane * (long long)h * w;
+  auto load_row = [&](int r) {
+    SrcRow q;
+    q.v = make_float4(0.f, 0.f, 0.f, 0.f);
+    q.e = 0.f;
+    if (r >= 0 && r < h) {
+      const float* __restrict__ rp = sp + (long long)r * w;
+      if (load_ok) q.v = __ldg(reinterpret_cast<const float4*>(rp + b0));
+      if (edge_l || edge_r) q.e = __ldg(rp + edge_col);
+    }
+    return q;
+  };
+  // columns b0-1 .. b0+4 of a source row: own vector + one element from each neighbour lane
+  auto widen = [&](const SrcRow& q, float (&V)[6]) {
+    float prev = __shfl_up_sync(0xffffffffu, q.v.w, 1);
+    float next = __shfl_down_sync(0xffffffffu, q.v.x, 1);
+    if (lane == 0) prev = q.e;
+    if (lane == 31) next = q.e;
+    V[0] = prev; V[1] = q.v.x; V[2] = q.v.y; V[3] = q.v.z; V[4] = q.v.w; V[5] = next;
+  };
+
+  const int a0 = band * band_rows, a1 = min(a0 + band_rows, h1);
+  int pa; double ua;
+  rect_axis_s(xs[a0], h, pa, ua);
+  int r_next = pa;                                         // source row held in q[0]
+  SrcRow q[PF];
+#pragma unroll
+  for (int k = 0; k < PF; ++k) q[k] = load_row(r_next + k);
+  auto pop_row = [&]() {                                   // oldest prefetched row; a new load takes the freed slot
+    const SrcRow cur = q[0];
+#pragma unroll
+    for (int k = 0; k + 1 < PF; ++k) q[k] = q[k + 1];
+    q[PF - 1] = load_row(r_next + PF);
+    ++r_next;
+    return cur;
+  };
+  int newest = pa - 1;                                     // source row currently in `bot`
+  double x_next = a0 + 1 < a1 ? xs[a0 + 1] : 0.0;
+  TD* __restrict__ dp = dst + plane * (long long)h1 * w1 + (long long)a0 * w1 + b0;
+
+  if (!EXACT) {
+    float top[4], bot[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) top[c] = bot[c] = 0.f;
+    for (int a = a0; a < a1; ++a, dp += w1) {
+      while (newest < pa + 1) {                            // warp-uniform: 0, 1 or 2 rows
+        float V[6];
+        widen(pop_row(), V);
+        ++newest;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          top[c] = bot[c];
+          const float L = dm1[c] ? V[c] : V[c + 1], R = dm1[c] ? V[c + 1] : V[c + 2];
+          bot[c] = zero[c] ? 0.f : fmaf((float)jf[c], R - L, L);
+        }
+      }
+      const float u = (float)ua;
+      float o[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o[c] = fmaf(u, bot[c] - top[c], top[c]);
+      if (store_ok) {
+        TD od[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) od[c] = (TD)o[c];
+        store4<TD>(dp, od);
+      }
+      if (a + 1 < a1) {
+        rect_axis_s(x_next, h, pa, ua);
+        if (a + 2 < a1) x_next = xs[a + 2];
+      }
+    }
+  } else {
+    float Vt[6], Vb[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) Vt[k] = Vb[k] = 0.f;
+    for (int a = a0; a < a1; ++a, dp += w1) {
+      while (newest < pa + 1) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) Vt[k] = Vb[k];
+        widen(pop_row(), Vb);
+        ++newest;
+      }
+      const double u = ua, u1 = dsub(1.0, u);
+      TD od[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {   // literal operation order of geometry_np.py:514-517, no contraction
+        const double tl = dm1[c] ? Vt[c] : Vt[c + 1], tr = dm1[c] ? Vt[c + 1] : Vt[c + 2];
+        const double bl = dm1[c] ? Vb[c] : Vb[c + 1], br = dm1[c] ? Vb[c + 1] : Vb[c + 2];
+        const double v = jf[c], v1 = dsub(1.0, v);
+        const double t1 = dadd(dmul(u, bl), dmul(u1, tl));
+        const double t2 = dadd(dmul(u, br), dmul(u1, tr));
+        const double r = dadd(dmul(v, t2), dmul(v1, t1));
+        od[c] = zero[c] ? (TD)0 : (TD)r;
+      }
+      if (store_ok) store4<TD>(dp, od);
+      if (a + 1 < a1) {
+        rect_axis_s(x_next, h, pa, ua);
+        if (a + 2 < a1) x_next = xs[a + 2];
+      }
+    }
+  }
+}
+
+static inline int host_axis_index_s(double coord, int64_t n) {
+  const double c = coord + (double)(n - 1) * 0.5;
+  return (int)c;  // truncation toward zero, like the device path
+}
+
+// HG_OK launched, 1 not applicable, else error
+int try_rect2hex_bilinear_stream(const void* src, void* dst, const double* xs, const double* ys, const double* host_xs,
+                                 const double* host_ys, int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1, int sdt,
+                                 int ddt, int math, cudaStream_t st) {
+  // read on every call (two getenv): the tests and the A/B benches flip these inside one process
+  const char* e_on = getenv("HG_R2H_STREAM");
+  const char* e_rows = getenv("HG_R2H_STREAM_ROWS");
+  const char* e_pf = getenv("HG_R2H_STREAM_PF");
+  const int enabled = e_on ? atoi(e_on) : 1, band_env = e_rows ? atoi(e_rows) : 64, pf = e_pf ? atoi(e_pf) : 3;
+  if (!enabled || !host_xs || !host_ys || sdt != HG_F32) return 1;
+  if (!(ddt == HG_F32 || (ddt == HG_F64 && math == HG_MATH_EXACT))) return 1;
+  if (w % 4 != 0 || w1 % 4 != 0 || h1 < 1 || w1 < 1) return 1;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) != 0 || (reinterpret_cast<uintptr_t>(dst) & (ddt == HG_F64 ? 15 : 15)) != 0) return 1;
+  if (h >= (1 << 30) || w >= (1 << 30) || h1 >= (1 << 30) || w1 >= (1 << 30)) return 1;
+  for (int64_t b = 0; b < w1; ++b) {
+    const int jn = host_axis_index_s(host_ys[b], w);
+    const int d = jn - (int)b;
+    if (!(d == -1 || d == 0 || jn >= w || jn <= -2)) return 1;
+  }
+  int prev = host_axis_index_s(host_xs[0], h);
+  for (int64_t a = 1; a < h1; ++a) {
+    const int cur = host_axis_index_s(host_xs[a], h);
+    if (cur - prev < 0 || cur - prev > 2) return 1;
+    prev = cur;
+  }
+  const int band_rows = band_env >= 8 ? band_env : 64;
+  const int64_t bands = ceil_div(h1, band_rows), xgroups = ceil_div(w1, (int64_t)kStW * kStWarps);
+  const int64_t blocks = planes * bands * xgroups;
+  if (blocks <= 0 || blocks >= (1ll << 31)) return 1;
+  const float* s = (const float*)src;
+#define HG_LAUNCH1(TD, EX, PF)                                                                                          \
+  rect2hex_stream_kernel<TD, EX, PF><<<(unsigned)blocks, kStWarps * 32, 0, st>>>(s, (TD*)dst, xs, ys, (int)h, (int)w, (int)h1, \
+                                                                                  (int)w1, (int)bands, (int)xgroups, band_rows)
+#define HG_LAUNCH(TD, EX)                      \
+  do {                                         \
+    if (pf <= 2) HG_LAUNCH1(TD, EX, 2);        \
+    else if (pf == 3) HG_LAUNCH1(TD, EX, 3);   \
+    else HG_LAUNCH1(TD, EX, 4);                \
+  } while (0)
+  if (ddt == HG_F64) HG_LAUNCH(double, true);
+  else if (math == HG_MATH_EXACT) HG_LAUNCH(float, true);
+  else HG_LAUNCH(float, false);
+#undef HG_LAUNCH1
+#undef HG_LAUNCH
+  return finish_launch("rect2hex_bilinear_stream");
+}
+
+}  // namespace hg

@@ -13,7 +13,8 @@
  *     enqueue work; they do not synchronise.
  *   - return 0 on success, <0 invalid argument (HG_E_*), >0 a cudaError_t.  hg_last_error()
  *     returns a thread-local message for the last non-zero return.
- *   - re-entrant, no global mutable state besides the thread-local error string.
+ *   - re-entrant, no global mutable state besides the thread-local error string (and the per-device workspace
+ *     of the hg_host_* entry points, guarded by one lock per device).
  */
 #ifndef HYGRID_B200_H_
 #define HYGRID_B200_H_
@@ -46,6 +47,9 @@ const char* hg_last_error(void);
 /* number of kernels launched by this thread since the last hg_reset_launch_count() (bench.py's
  * gpu_launches claim is read from here, not guessed). */
 int64_t hg_launch_count(void);
+/* name of the kernel family the calling thread launched last ("rect2hex_bilinear_stream", "hexconv_umma_tma", ...):
+ * which of the library's kernels took a call is part of what the tests and the bench line state. */
+const char* hg_last_launch(void);
 void hg_reset_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
@@ -243,6 +247,15 @@ int hg_host_rect2hex(const void* host_src, void* host_dst, const double* host_xs
 int hg_host_hex2rect(const void* host_src, void* host_dst, const double* host_xs, const double* host_ys,
                      int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1,
                      int src_dtype, int dst_dtype, int interp, int math, int device);
+/* Host-buffer writers / readers of the doubled rasters (the formats either side of the path): a host hex matrix
+ * [planes,H,W] -> type1 [planes,H,2W+1] (rows_mul = 1) or type2 [planes,2H,2W+1] (rows_mul = 2) raster in host memory and
+ * back, through the same pinned ring.  ref: HexImage.py:139-170 GenerateType1Image / GenerateType2Image (python loops over
+ * bands x rows with np.insert / np.append), :106-111 (decode), :171-218 SaveHexImage (which writes those rasters).
+ * Calls on different devices run concurrently (one ring and one lock per device). */
+int hg_host_hex_to_type(const void* host_hex, void* host_raster, int64_t planes, int64_t H, int64_t W, int offset,
+                        int src_dtype, int dst_dtype, int rows_mul, int device);
+int hg_host_type_to_hex(const void* host_raster, void* host_hex, int64_t planes, int64_t H, int64_t W,
+                        int src_dtype, int dst_dtype, int rows_mul, int device);
 /* frees the streams, device ring and pinned bounce buffers the host entry points created lazily
  * (the only memory the library ever owns). */
 void hg_host_release(void);

@@ -78,8 +78,10 @@ def hexconv2d(x, kernel, bias=None, even_odd_offset=0, radius=2, stride=1, paddi
     Cout = kernel.shape[0]
     o = (even_odd_offset + padding) % 2
     rows_e, rows_o, cols = hexconv_out_shape(Hp, Wp, r, s, d)
-    if rows_e <= 0 or rows_o <= 0 or cols <= 0:
+    if rows_e <= 0 or rows_o < 0 or cols <= 0:
         raise ValueError("input too small: the reference takes an undefined path here")
+    # rows_o == 0 (padded height in [k_h, k_h + s)): the odd conv is skipped and the reference returns the even-row
+    # result alone (HexFrames.py:163-164) -- one output row, which the formula below yields with Ho = 1
     if rows_e - rows_o not in (0, 1):
         raise ValueError("even/odd row counts cannot be interleaved (the reference raises too)")
     Ho = rows_e + rows_o

@@ -76,6 +76,17 @@ def main():
         yo = HO.hexconv2d(x, m.kernel.detach(), m.bias.detach(), off, r, s_, pad, d, 1)
         assert yo.shape == yr.shape and float((yo - yr.detach()).abs().max()) <= 1e-5 * max(1.0, float(yr.abs().max())), "C1"
         checked += 1
+    # even rows only: a padded height in [k_h, k_h + s) skips the odd conv and the reference returns the even-row result
+    # alone (HexFrames.py:163-164): one output row
+    for (H, W, r, s_, d, pad, off) in ((3, 9, 2, 1, 1, 0, 0), (3, 8, 2, 1, 1, 0, 1), (5, 12, 3, 1, 1, 0, 0), (1, 7, 2, 1, 1, 1, 0),
+                                       (4, 11, 2, 2, 1, 0, 1), (5, 13, 2, 1, 2, 0, 0)):
+        m = hf.HexConv2d(2, 3, off, r, stride=s_, padding=pad, dilation=d)
+        x = torch.randn(2, 2, H, W)
+        yr = m(x)
+        yo = HO.hexconv2d(x, m.kernel.detach(), m.bias.detach(), off, r, s_, pad, d, 1)
+        assert yr.shape[2] == 1, ("expected the even-rows-only case", yr.shape)
+        assert yo.shape == yr.shape and float((yo - yr.detach()).abs().max()) <= 1e-5 * max(1.0, float(yr.abs().max())), "C1 even rows only"
+        checked += 1
     for _ in range(12):
         B, C_, H, W = int(rng.integers(1, 3)), int(rng.integers(1, 4)), int(rng.integers(4, 24)), int(rng.integers(5, 30))
         method = ("max", "min", "average")[int(rng.integers(0, 3))]

@@ -4,9 +4,9 @@ The reference runs the three layers one after the other in ``order``; this build
 BatchNorm into the conv epilogue, BatchNorm + ReLU into one streaming pass), which adds control flow the reference does
 not have.  Here every combination of layer order, ``activate`` / ``norm`` flags, training / eval, grad / no-grad, norm
 and activation type, explicit padding mode and spectral norm is compared with the plain loop evaluated on the module's
-own sub-layers (the fused paths must be numerically equivalent: 1e-4 of the range for outputs and statistics, 5e-4 /
-1e-3 for data / parameter gradients) -- outputs, running
-statistics and gradients."""
+own sub-layers (the fused paths must be numerically equivalent: 1e-4 of the range for outputs, statistics and data
+gradients -- SURVEY.md 8c's fp32 conv tolerance -- and 1e-3 for parameter gradients, which sum over every pixel with
+float atomics) -- outputs, running statistics and gradients."""
 import copy
 import itertools
 
@@ -68,7 +68,7 @@ def _check(cfg, training, grad, activate=True, norm=True, Cin=4, Cout=6):
         g = torch.randn_like(ya)
         ya.backward(g)
         yb.backward(g)
-        _close(xa.grad.cpu(), xb.grad.cpu(), what + ("dx",), 5e-4)
+        _close(xa.grad.cpu(), xb.grad.cpu(), what + ("dx",), 1e-4)
         for (na, pa), (_, pb) in zip(m.named_parameters(), ref.named_parameters()):
             if pa.grad is None and pb.grad is None:
                 continue
@@ -105,6 +105,8 @@ def test_every_order_with_batchnorm_and_relu(order):
     dict(inplace=False, norm_cfg=dict(type="BN")),
     dict(groups=2, norm_cfg=dict(type="BN")),
     dict(stride=2, dilation=1, norm_cfg=dict(type="BN")),
+    dict(conv_cfg=dict(type="HexConv2dAdaptivePadding"), norm_cfg=dict(type="BN")),     # eval: fused affine epilogue
+    dict(conv_cfg=dict(type="HexConv2dAdaptivePadding")),                               # eval: fused ReLU epilogue
 ])
 def test_layer_types_padding_modes_and_flags(cfg):
     for training, grad in ((True, True), (False, False)):
