@@ -292,11 +292,14 @@ int try_hexsrc_linear_tma(const void* src, void* dst, const double* xs, const do
   const long long per = (total + grid - 1) / grid;
   grid = (total + per - 1) / per;
   const double hx = (h - 1) / 2.0, wy = (w - 0.5) / 2.0;     // python-float expressions of geometry_np.py:326-331
-  static const int order_env = [] { const char* e = getenv("HG_HEXSRC_ORDER"); return e ? atoi(e) : -1; }();   // A/B: 0 row-, 1 column-major
+  // A/B switches, read on every call so that one process can sweep them (tools/sweep_kernels.py)
+  const char* e_order = getenv("HG_HEXSRC_ORDER");            // 0 row-, 1 column-major tile order
+  const int order_env = e_order ? atoi(e_order) : -1;
   const int col_major = order_env > 0 ? 1 : 0;
   // plane groups that share one geometry evaluation (consecutive items of a CTA): more re-use of the float64 / index
   // arithmetic against a longer L2 re-use distance of the tile halos (measured)
-  static const int share_env = [] { const char* e = getenv("HG_HEXSRC_SHARE"); return e ? atoi(e) : 0; }();
+  const char* e_share = getenv("HG_HEXSRC_SHARE");
+  const int share_env = e_share ? atoi(e_share) : 0;
   // measured on B200 (C4 / C2, fraction of the HBM copy rate): float32 weights R = 1: 0.70 / 0.88, R = 2: 0.85 / 0.83,
   // R = 4: 0.75 / 0.75 -- sharing pays when a row of tiles is so long that the halo rows leave L2 anyway (4K images);
   // float64 weights (exact): R = 1: 0.28, 2: 0.41, 4: 0.52, 8: 0.61 -- bound by the fp64 pipe, so share as much as possible.

@@ -127,6 +127,31 @@ def test_c3_stack_four_layers_autocast_step():
         assert _rel(l.bias.grad.cpu(), b.grad) <= 2e-2
 
 
+def test_c3_bfloat16_activations_end_to_end():
+    """The opt-in `out_dtype = torch.bfloat16` (bfloat16 tensors at the layer boundary instead of the reference's float32
+    buffer): output and data gradient are the oracle's values rounded once to bfloat16 (2^-8 relative), the weight
+    gradient accumulates in float32."""
+    from HyGrid import HexFrames as hf
+    torch.manual_seed(34)
+    m = hf.HexConv2d(64, 64, 0, 2, stride=1, padding=1).cuda()
+    m.out_dtype = torch.bfloat16
+    with torch.no_grad():
+        m.kernel.copy_(m.kernel.bfloat16().float())
+    xq = torch.randn(2, 64, 128, 256).bfloat16().float()
+    gyq = torch.randn(2, 64, 128, 256).bfloat16().float()
+    ref, dx, dw, db = _c3_oracle(xq, m.kernel.detach().cpu(), m.bias.detach().cpu(), gyq)
+    x = xq.cuda().bfloat16().requires_grad_()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = m(x)
+    assert y.dtype == torch.bfloat16 and m._autocast_tc
+    (y.float() * gyq.cuda()).sum().backward()
+    assert x.grad.dtype == torch.bfloat16
+    assert _rel(y.detach().float().cpu(), ref) <= 8e-3
+    assert _rel(x.grad.float().cpu(), dx) <= 8e-3
+    assert _rel(m.kernel.grad.cpu(), dw) <= 1e-3
+    assert _rel(m.bias.grad.cpu(), db) <= 1e-3
+
+
 # ----------------------------------------------------------------------------------------------------
 # C4
 # ----------------------------------------------------------------------------------------------------

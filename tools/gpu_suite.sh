@@ -1,5 +1,5 @@
 #!/bin/bash
-# One-stop GPU run (use under gpurun):   bash tools/gpu_suite.sh <tag> [tests] [bench] [path] [conv] [cnn] [ncu] [stress]
+# One-stop GPU run (use under gpurun):   bash tools/gpu_suite.sh <tag> [tests] [bench] [path] [conv] [cnn] [ncu] [stress] [sweep] [cudnn]
 # Everything lands in gpurun_out/<tag>/ ; copy what should be judged into profiles/.
 TAG=${1:-run}; shift
 WHAT=${*:-tests bench path conv cnn}
@@ -7,19 +7,21 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 has() { [[ " $WHAT " == *" $1 "* ]]; }
 if has tests; then
-  timeout 1200 python -m pytest tests -m gpu -q --timeout 600 > $OUT/pytest_gpu.log 2>&1; echo "pytest(gpu) rc=$?"; tail -3 $OUT/pytest_gpu.log | cut -c1-200
+  timeout 2400 python -m pytest tests -m gpu -q --timeout 900 --durations=15 > $OUT/pytest_gpu.log 2>&1; echo "pytest(gpu) rc=$?"; grep -E "^(FAILED|ERROR)|passed|failed" $OUT/pytest_gpu.log | cut -c1-300 | head -40
   HG_CONV_NO_TMA=1 timeout 900 python -m pytest tests -m gpu -q --timeout 600 -k tcgen05 > $OUT/pytest_tcgen05_notma.log 2>&1; echo "pytest(tcgen05, LDG staging) rc=$?"; tail -1 $OUT/pytest_tcgen05_notma.log
   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $OUT/smoke.log
 fi
+if has sweep; then timeout 1200 python tools/sweep_kernels.py --reps 10 > $OUT/sweep_kernels.jsonl 2> $OUT/sweep_kernels.err; echo "sweep rc=$?"; cut -c1-230 $OUT/sweep_kernels.jsonl; fi
+if has cudnn; then timeout 900 python tools/bench_conv.py --cudnn-only --reps 9 > $OUT/bench_conv_cudnn.jsonl 2> $OUT/bench_conv_cudnn.err; echo "cudnn route rc=$?"; grep -v '"rows"' $OUT/bench_conv_cudnn.jsonl | cut -c1-300; tail -3 $OUT/bench_conv_cudnn.err; fi
 if has stress; then   # the tcgen05 wgrad staging race showed up once per few processes: repeat fresh processes
   for k in 0 1 2 3 4 5; do timeout 300 python tests/stress/wgrad_cfg.py 2>&1 | grep -c BAD; done > $OUT/wgrad_stress.log 2>&1
   echo "wgrad stress (BAD configurations per process):" $(tr '\n' ' ' < $OUT/wgrad_stress.log)
 fi
 if has bench; then
-  timeout 900 python bench.py --steps 20 --warmup 5 > $OUT/bench_c2.json 2> $OUT/bench_c2.err; echo "bench rc=$?"; cut -c1-300 $OUT/bench_c2.json
+  timeout 1500 python bench.py --steps 20 --warmup 5 > $OUT/bench_c2.json 2> $OUT/bench_c2.err; echo "bench rc=$?"; cut -c1-6000 $OUT/bench_c2.json; tail -5 $OUT/bench_c2.err
   timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "bench(reference) rc=$?"; cut -c1-200 $OUT/bench_ref.json
-  for wl in c2half c4; do timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu --e2e-steps 1 --workload $wl > $OUT/bench_$wl.json 2> $OUT/bench_$wl.err; done
-  timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu --e2e-steps 1 --math exact > $OUT/bench_c2_exact.json 2> $OUT/bench_c2_exact.err
+  for wl in c2half c4; do timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu --no-extra --e2e-steps 1 --workload $wl > $OUT/bench_$wl.json 2> $OUT/bench_$wl.err; done
+  timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu --no-extra --e2e-steps 1 --math exact > $OUT/bench_c2_exact.json 2> $OUT/bench_c2_exact.err
 fi
 if has path; then timeout 900 python tools/bench_path.py --reps 10 > $OUT/bench_path.jsonl 2>&1; echo "bench_path rc=$?"; grep -v '"rows"' $OUT/bench_path.jsonl | cut -c1-200; fi
 if has conv; then timeout 900 python tools/bench_conv.py --reps 10 > $OUT/bench_conv.jsonl 2>&1; echo "bench_conv rc=$?"; grep -v '"rows"' $OUT/bench_conv.jsonl | cut -c1-220; fi
@@ -30,10 +32,10 @@ if has cnn; then
   timeout 300 python tools/hexcnn_ddp.py --batch 64 --steps 10 > $OUT/hexcnn_fp32.log 2>&1; echo "hexcnn(fp32) rc=$?"; tail -1 $OUT/hexcnn_fp32.log
 fi
 if has ncu; then   # launch list of the bench + one --set full capture per dominant kernel, each after its plain run exited 0
-  B="python bench.py --steps 3 --warmup 3 --no-cpu --e2e-steps 1"
+  B="python bench.py --steps 3 --warmup 3 --no-cpu --no-extra --e2e-steps 1"
   timeout 600 $B > $OUT/plain_bench.log 2>&1 && \
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/bench_launches.csv $B > $OUT/ncu_launches.log 2>&1; echo "launch list rc=$?"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:rect2hex_bilinear_ws -s 3 -c 1 -o $OUT/prof_rect2hex_ws $B > $OUT/ncu_r2h.log 2>&1; echo "ncu rect2hex rc=$?"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:rect2hex_ -s 3 -c 1 -o $OUT/prof_rect2hex $B > $OUT/ncu_r2h.log 2>&1; echo "ncu rect2hex rc=$?"
   cap() { P="python tools/bench_path.py --reps 2 --small --only"; timeout 600 $P "$3" > $OUT/plain_$1.log 2>&1 && timeout 900 ncu --set full --clock-control none --import-source on -k regex:$2 -s 2 -c 1 -o $OUT/prof_$1 $P "$3" > $OUT/ncu_$1.log 2>&1; echo "ncu $1 rc=$?"; }
   timeout 300 python tools/bench_pcie.py > $OUT/bench_pcie.json 2>&1; echo "pcie probe rc=$?"; cat $OUT/bench_pcie.json
   cap hexsrc_tma hexsrc_linear_tma "c4 hex->rect linear fast"

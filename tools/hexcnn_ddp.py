@@ -7,8 +7,9 @@
 
 Model (builder-defined): HexConvModule 3->32->64->128 (BN + ReLU), HexPool2d('max', 2, 2) between,
 global average, Linear -> 10, on 128 x 128 hex lattices.  Every gradient lives in one flat fp32 bucket
-(HyGrid.distributed.FlatGradBucket) that is all-reduced ONCE per step over NCCL; conv / pool kernels are the
-library's.  Prints one JSON line: ms per step (max over ranks, CUDA events), images/s, bucket size, and whether
+(HyGrid.distributed.FlatGradBucket) cut into a few groups; each group is all-reduced over NCCL as soon as backward
+has produced its last gradient (the collective overlaps the backward of the earlier layers); conv / pool kernels are
+the library's and write their weight gradients straight into the bucket.  Prints one JSON line: ms per step (max over ranks, CUDA events), images/s, bucket size, and whether
 all ranks hold identical parameters after the steps (the all-reduce did its job)."""
 import argparse
 import json
@@ -21,28 +22,10 @@ import torch.nn as nn
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "hybrid-grid-for-hexagonal-and-rectangular-image-processing_b200"))
-from HyGrid import HexFrames as hf  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 from HyGrid import _native as nv  # noqa: E402
-from HyGrid.HexModules import HexConvModule  # noqa: E402
 from HyGrid.distributed import FlatGradBucket, shard_range  # noqa: E402
-
-
-class HexCNN(nn.Module):
-    def __init__(self, classes=10):
-        super().__init__()
-        bn = dict(type='BN')
-        self.c1 = HexConvModule(3, 32, 0, 2, padding=1, norm_cfg=bn)
-        self.c2 = HexConvModule(32, 64, 0, 2, padding=1, norm_cfg=bn)
-        self.c3 = HexConvModule(64, 128, 0, 2, padding=1, norm_cfg=bn)
-        self.pool = hf.HexPool2d('max', 2, 2)
-        self.gap = hf.HexGlobalPool2d('average')
-        self.fc = nn.Linear(128, classes)
-
-    def forward(self, x):
-        x = self.pool(self.c1(x))
-        x = self.pool(self.c2(x))
-        x = self.c3(x)
-        return self.fc(self.gap(x))
+from hexcnn import HexCNN  # noqa: E402
 
 
 def main():
@@ -52,6 +35,8 @@ def main():
     ap.add_argument("--hw", type=int, default=128)
     ap.add_argument("--autocast", action="store_true")
     ap.add_argument("--graph", action="store_true", help="capture the whole training step in one CUDA graph and replay it")
+    ap.add_argument("--groups", type=int, default=3, help="bucket groups; every group is all-reduced as soon as its gradients landed")
+    ap.add_argument("--blocking", action="store_true", help="round-1 behaviour: one blocking all-reduce after backward")
     a = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -60,7 +45,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)                                     # identical initial weights on every rank
     model = HexCNN().to(dev)
-    bucket = FlatGradBucket(model.parameters())
+    bucket = FlatGradBucket(model.parameters(), groups=1 if a.blocking else a.groups, overlap=not a.blocking)
     opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9)
     g = torch.Generator(device="cpu").manual_seed(1)
     data = torch.randn(a.batch * world, 3, a.hw, a.hw, generator=g)
@@ -72,8 +57,8 @@ def main():
         bucket.zero_()
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=a.autocast):
             loss = nn.functional.cross_entropy(model(x).float(), t)
-        loss.backward()
-        bucket.all_reduce(average=True)                      # the path's only collective: one flat bucket
+        loss.backward()                                      # groups of the flat bucket are all-reduced from inside backward
+        bucket.finish()                                      # join (blocking mode: the one collective happens here)
         opt.step()
         return loss
 
@@ -122,7 +107,7 @@ def main():
                           "hex_mpix_per_s": round(a.batch * world * a.hw * a.hw / float(ms) / 1e3, 1),
                           "grad_bucket_bytes": bucket.nbytes, "ranks_in_sync": same, "loss": round(float(loss), 4),
                           "library_launches_per_step": nv.launch_count() // a.steps, "autocast": a.autocast,
-                          "cuda_graph": a.graph}), flush=True)
+                          "cuda_graph": a.graph, "overlap": not a.blocking, "group_bytes": list(bucket.group_bytes())}), flush=True)
     if world > 1:
         if a.graph:
             # tearing the process group down while a captured graph still holds NCCL kernels hung the run on 8 GPUs
