@@ -1,174 +1,141 @@
-"""``HyGrid.HexImage.HEXIMAGE`` (/root/reference/HyGrid/HexImage.py:43-276): hex image container.
-The doubled-raster encoders ``GenerateType1Image`` / ``GenerateType2Image`` (per-row Python loops of
-``np.insert`` / ``np.append`` in the reference, :139-170) run as one pack kernel; the type1 / type2 decode of
-the constructor is the reference's own strided view.  Saving rasters and the OpenGL viewer are outside the
-hot path (lazy, optional back-ends)."""
+"""``HyGrid.HexImage.HEXIMAGE`` -- the hex image container of the reference (HexImage.py:43-276) on the formats either
+side of the path: type1 / type2 doubled rasters and ``.heximg`` pickles.
+
+* decode (constructor, ``heximagetype`` 1 / 2): the reference's own strided views (HexImage.py:106-111);
+* encode (``GenerateType1Image`` / ``GenerateType2Image``; per-row ``np.insert`` / ``np.append`` loops in the reference,
+  :139-170): the pack kernel, fed from and drained into HOST memory by the C ABI's pinned ring
+  (``hg_host_hex_to_type``: chunks of bands flow H2D -> kernel -> D2H on three streams) -- no torch tensors involved;
+* ``SaveHexImage``: ``.heximg`` pickles are written here, rasters through the lazy back-ends of ``_rasterio``;
+* ``Hex_imshow`` needs a display; ``HexMosaic()`` returns the raster its fragment shader would draw.
+
+Same constructor signature, attributes and error messages as the reference."""
 from __future__ import annotations
 
-import inspect
+import ctypes as C
 import os
 import pickle
 import warnings
 
 import numpy as np
-import torch
 
-from . import functional as Fn
-from .Image import IMAGE, _need
+from . import _native as nv
+from . import _rasterio as rio
+from .Image import IMAGE, _IDENTITY_GEOTRANS, _as_bands, _one_source
 from ._hostapi import device_index
 
 __all__ = ["HEXIMAGE"]
+
+_BAD_TYPE = ("不支持的文件类型\n要么输入的是普通图像文件：None\n要么输入的是六边形图像通用格式：1\n"
+             "要么输入后缀为‘.heximg'的六边形图像专用文件格式：2")           # HexImage.py:85-88
+# hex matrix inside a doubled raster handed over as an array (HexImage.py:106-111)
+_DECODE = {None: lambda a: a, 1: lambda a: a[:, :, 1:-1:2], 2: lambda a: a[:, ::2, 1:-1:2]}
+_HEXIMG_KEYS = (("height", "height"), ("width", "width"), ("bands", "bands"), ("geotrans", "geotransform"),
+                ("proj", "projection"), ("even_odd_offset", "offset"), ("HexagonImage", "HexMatrix"))
 
 
 class HEXIMAGE(IMAGE):
     def __init__(self, pathname=None, heximagetype=None, data=None, geotrans=None, proj=None, even_odd_offset=False,
                  backend='gdal'):
-        if pathname is None and data is None:
-            raise ValueError("pathname and data can not be None at the same time")
-        if pathname is not None and data is not None:
-            raise ValueError("pathname and data can not be Given at the same time")
-        if pathname is not None:
-            file_name, file_extension = os.path.splitext(pathname)
-            if file_extension == ".heximg":
-                if not os.path.exists(pathname):
-                    raise OSError("path dosen't exist.")
-                self.path = self.datapath = pathname
-                with open(pathname, "rb") as f:
-                    self.Heximagedataset = pickle.load(f)
-                self.filetype = 2
-                self.height = self.Heximagedataset['height']
-                self.width = self.Heximagedataset['width']
-                self.bands = self.Heximagedataset['bands']
-                self.geotrans = self.Heximagedataset['geotransform']
-                self.proj = self.Heximagedataset['projection']
-                even_odd_offset = self.Heximagedataset['offset']
-                self.HexagonImage = self.Heximagedataset['HexMatrix']
-                if self.HexagonImage.ndim < 3:
-                    self.HexagonImage = np.broadcast_to(self.HexagonImage, (3, self.height, self.width))
-                self.backend = backend
-                self.heximagetype = heximagetype
-            else:
-                super().__init__(pathname, backend=backend)
-                self.heximagetype = heximagetype
-                if heximagetype == None:  # noqa: E711
-                    self.HexagonImage = self.ConvertToHexagon()
-                    if self.HexagonImage.ndim == 2:
-                        self.HexagonImage = self.HexagonImage[None]
-                    self.bands, self.height, self.width = self.HexagonImage.shape[0:3]
-                elif heximagetype == 1:
-                    tmp = self.LoadImageArray()
-                    self.width = (self.width - 1) // 2
-                    self.HexagonImage = np.zeros([self.bands, self.height, self.width])
-                    self.HexagonImage[:, :, :] = tmp[:, :, 1::2]
-                elif heximagetype == 2:
-                    tmp = self.LoadImageArray()
-                    if (self.width & 1) == 0:
-                        zeros = np.zeros((self.bands, self.height, 1))
-                        tmp = np.append(tmp, zeros, axis=2)
-                        self.width += 1
-                    self.height = self.height // 2
-                    self.width = (self.width - 1) // 2
-                    self.HexagonImage = np.zeros([self.bands, self.height, self.width])
-                    self.HexagonImage[:, :, :] = tmp[:, ::2, 1::2] if tmp.ndim == 3 else tmp[::2, 1::2]
-                else:
-                    raise Exception("不支持的文件类型\n要么输入的是普通图像文件：None\n要么输入的是六边形图像通用格式：1\n"
-                                    "要么输入后缀为‘.heximg'的六边形图像专用文件格式：2")
-        elif data is not None:
-            if data.ndim == 2:
-                data = np.broadcast_to(data, (1, data.shape[0], data.shape[1]))
-            if heximagetype == None:  # noqa: E711
-                self.HexagonImage = data
-            elif heximagetype == 1:
-                self.HexagonImage = data[:, :, 1:-1:2]
-            elif heximagetype == 2:
-                self.HexagonImage = data[:, ::2, 1:-1:2]
-            self.heximagetype = heximagetype
-            self.bands = self.HexagonImage.shape[0]
-            self.height = self.HexagonImage.shape[1]
-            self.width = self.HexagonImage.shape[2]
-            self.geotrans = geotrans
-            if self.geotrans == None:  # noqa: E711
-                self.geotrans = (0, 1, 0, 0, 0, 1)
-            self.proj = proj
-            self.path = inspect.signature(self.__init__).parameters['data'].name
-            self.backend = backend
+        if not _one_source(pathname, data):
+            self._from_hex_array(data, heximagetype, geotrans, proj)
+        elif os.path.splitext(pathname)[1] == ".heximg":
+            even_odd_offset = self._from_heximg(pathname)
+        else:
+            self._from_raster(pathname, heximagetype, backend)
+        self.backend = backend
+        self.heximagetype = heximagetype
         self.even_odd_offset = int(even_odd_offset)
         self.shape = (self.bands, self.height, self.width)
 
+    # -- construction ---------------------------------------------------------------------------
+    def _from_hex_array(self, data, heximagetype, geotrans, proj):
+        self.HexagonImage = _DECODE[heximagetype](_as_bands(data)) if heximagetype in _DECODE else _as_bands(data)
+        self.bands, self.height, self.width = self.HexagonImage.shape[:3]
+        self.geotrans = _IDENTITY_GEOTRANS if geotrans == None else geotrans  # noqa: E711
+        self.proj = proj
+        self.path = 'data'                                   # the reference stores the parameter's name (HexImage.py:121)
+
+    def _from_heximg(self, pathname):
+        self.path = self.datapath = rio.require_file(pathname)
+        with open(pathname, "rb") as f:
+            self.Heximagedataset = pickle.load(f)
+        self.filetype = 2
+        stored = {attr: self.Heximagedataset[key] for attr, key in _HEXIMG_KEYS}
+        offset = stored.pop("even_odd_offset")
+        self.__dict__.update(stored)
+        if self.HexagonImage.ndim < 3:                       # HexImage.py:99-100
+            self.HexagonImage = np.broadcast_to(self.HexagonImage, (3, self.height, self.width))
+        return offset
+
+    def _from_raster(self, pathname, heximagetype, backend):
+        IMAGE.__init__(self, pathname, backend=backend)
+        if heximagetype == None:  # noqa: E711                 a plain picture: resample it onto the hex lattice (:61-64)
+            hexed = self.ConvertToHexagon()
+            self.HexagonImage = hexed[None] if hexed.ndim == 2 else hexed
+            self.bands, self.height, self.width = self.HexagonImage.shape[:3]
+            return
+        if heximagetype not in (1, 2):
+            raise Exception(_BAD_TYPE)
+        raster = self.LoadImageArray()
+        if heximagetype == 2:                                # :72-84: rows were written twice; an even width lost its last zero
+            if (self.width & 1) == 0:
+                raster = np.append(raster, np.zeros((self.bands, self.height, 1)), axis=2)
+                self.width += 1
+            self.height //= 2
+            raster = raster[:, ::2] if raster.ndim == 3 else raster[::2]
+        self.width = (self.width - 1) // 2
+        self.HexagonImage = np.zeros([self.bands, self.height, self.width])
+        self.HexagonImage[:, :, :] = raster[..., 1::2]
+
+    # -- reference surface ----------------------------------------------------------------------
     def size(self, index):
         return self.HexagonImage.shape[index]
 
     def build_Heximagedataset(self):
-        self.Heximagedataset = {}
-        self.Heximagedataset['height'] = self.height
-        self.Heximagedataset['width'] = self.width
-        self.Heximagedataset['bands'] = self.bands
-        self.Heximagedataset['geotransform'] = self.geotrans
-        self.Heximagedataset['projection'] = self.proj
-        self.Heximagedataset['offset'] = self.even_odd_offset
-        self.Heximagedataset['HexMatrix'] = self.HexagonImage
+        self.Heximagedataset = {key: getattr(self, attr) for attr, key in _HEXIMG_KEYS}
 
-    def _pack(self, rows_mul):
+    def _encode(self, rows_mul):
+        """(C, rows_mul*H, 2W+1) float64 doubled raster of the hex matrix: host array in, host array out through the
+        library's pinned ring (HexImage.py:139-170)."""
         hexm = np.ascontiguousarray(self.HexagonImage)
-        if hexm.dtype not in (np.uint8, np.int16, np.uint16, np.int32, np.int64, np.float32, np.float64):
+        if hexm.dtype not in nv._NP2HG:
             hexm = hexm.astype(np.float64)
-        if hexm.dtype == np.uint16:          # torch has no device uint16 arithmetic: same bits as int16 would
-            hexm = hexm.astype(np.int32)     # change sign; widen instead (exact)
-        x = torch.from_numpy(hexm).to(torch.device("cuda", device_index()))
-        fn = Fn.hex_to_type1 if rows_mul == 1 else Fn.hex_to_type2
-        return fn(x, self.even_odd_offset, out_dtype=torch.float64).cpu().numpy()
+        out = np.empty((self.bands, rows_mul * self.height, 2 * self.width + 1), dtype=np.float64)
+        nv.call("hg_host_hex_to_type", C.c_void_p(hexm.ctypes.data), C.c_void_p(out.ctypes.data), self.bands, self.height,
+                self.width, self.even_odd_offset, nv.hg_dtype(hexm.dtype), nv.F64, rows_mul, device_index())
+        return out
 
     def GenerateType1Image(self):
-        """HexImage.py:139-153 -> (C x H x (2W+1) float64, geotrans with [5] doubled)."""
-        Heximg_type1 = self._pack(1)
-        geotrans_type1 = (self.geotrans[0], self.geotrans[1], self.geotrans[2],
-                          self.geotrans[3], self.geotrans[4], self.geotrans[5] * 2,)
-        return Heximg_type1, geotrans_type1
+        """-> (C x H x (2W+1) float64, geotrans with the row pitch doubled) (HexImage.py:139-153)."""
+        g = self.geotrans
+        return self._encode(1), (g[0], g[1], g[2], g[3], g[4], g[5] * 2,)
 
     def GenerateType2Image(self):
-        """HexImage.py:154-170 -> (C x 2H x (2W+1) float64, geotrans)."""
-        Heximg_type2 = self._pack(2)
-        geotrans_type2 = (self.geotrans[0], self.geotrans[1], self.geotrans[2],
-                          self.geotrans[3], self.geotrans[4], self.geotrans[5],)
-        return Heximg_type2, geotrans_type2
+        """-> (C x 2H x (2W+1) float64, geotrans) (HexImage.py:154-170)."""
+        g = self.geotrans
+        return self._encode(2), (g[0], g[1], g[2], g[3], g[4], g[5],)
 
     def SaveHexImage(self, pathname, imagetype=1, filetype=1):
-        """HexImage.py:171-218: '.heximg' pickles are written here; raster formats need an I/O back-end."""
-        file_name, file_extension = os.path.splitext(pathname)
-        if file_extension == ".heximg":
+        """HexImage.py:171-218."""
+        stem, suffix = os.path.splitext(pathname)
+        if suffix == ".heximg":
             filetype = 2
-        if file_extension in (".tif", ".TIF", ".tiff", ".TIFF", ".png", "bmp"):
+        if suffix in (".tif", ".TIF", ".tiff", ".TIFF", ".png", "bmp"):
             self.filetype = 1
-        if file_extension in ("JPG", ".jpg", "JPEG", "jpeg"):
+        if suffix in ("JPG", ".jpg", "JPEG", "jpeg"):
             warnings.warn("jpg and jpeg are lossy compression formats, switching to png")
-            file_extension = ".png"
-        pathname = file_name + file_extension
-        if filetype == 1:
-            tmp, geotrans_out = self.GenerateType1Image() if imagetype == 1 else self.GenerateType2Image()
-            if 'int16' in self.HexagonImage.dtype.name:
-                tmp = tmp.astype(np.uint16)
-            else:
-                tmp = tmp.astype(np.uint8)
-            if self.backend == 'gdal':
-                gdal = _need("osgeo.gdal")
-                datatype = gdal.GDT_UInt16 if tmp.dtype == np.uint16 else gdal.GDT_Byte
-                driver = gdal.GetDriverByName("GTiff")
-                self.Hex_dataset = driver.Create(pathname, tmp.shape[2], tmp.shape[1], tmp.shape[0], datatype,
-                                                 options=["TILED=YES", "COMPRESS=LZW"])
-                self.Hex_dataset.SetGeoTransform(geotrans_out)
-                if self.proj != None:  # noqa: E711
-                    self.Hex_dataset.SetProjection(self.proj)
-                for i in range(tmp.shape[0]):
-                    self.Hex_dataset.GetRasterBand(i + 1).WriteArray(tmp[i])
-                self.Hex_dataset.FlushCache()
-            elif self.backend == 'mmcv':
-                _need("mmcv").imwrite(tmp[::-1, ...].transpose(1, 2, 0), pathname)
-            elif self.backend == 'cv2':
-                _need("cv2").imwrite(pathname, tmp[::-1, ...].transpose(1, 2, 0))
-        else:
+            suffix = ".png"
+        pathname = stem + suffix
+        if filetype != 1:
+            self.build_Heximagedataset()
             with open(pathname, "wb") as f:
-                self.build_Heximagedataset()
                 pickle.dump(self.Heximagedataset, f)
+            return
+        raster, geotrans_out = self.GenerateType1Image() if imagetype == 1 else self.GenerateType2Image()
+        raster = raster.astype(np.uint16 if 'int16' in self.HexagonImage.dtype.name else np.uint8)
+        handle = rio.write_raster(pathname, raster, self.backend, geotrans_out, self.proj)
+        if handle is not None:
+            self.Hex_dataset = handle
 
     def Hex_imshow(self):
         raise NotImplementedError("the interactive OpenGL viewer (HexImage.py:219-276) has no place on a headless GPU node; "

@@ -38,6 +38,16 @@ class ConvDesc(C.Structure):
                 ("x_dtype", C.c_int), ("y_dtype", C.c_int), ("algo", C.c_int), ("relu", C.c_int)]
 
 
+class TapsSet(C.Structure):
+    _fields_ = [("T", C.c_int), ("sx", C.c_int), ("doubled", C.c_int), ("ry", C.c_int * 64), ("ex", C.c_int * 64)]
+
+
+class DwTapsDesc(C.Structure):
+    _fields_ = [("N", C.c_int64), ("C", C.c_int64), ("H", C.c_int64), ("W", C.c_int64), ("Ho", C.c_int64), ("Wo", C.c_int64),
+                ("sy", C.c_int), ("odd_limit", C.c_int), ("parity", C.c_int), ("pad", C.c_int), ("pad_value", C.c_float),
+                ("set", TapsSet * 2)]
+
+
 _p, _i, _l, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
 _SIGS = {
     "hg_axial_to_offset_i32": [_p, _p, _p, _l, _p],
@@ -72,6 +82,9 @@ _SIGS = {
     "hg_bn_bwd_apply": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _l, _l, _i, _i, _p],
     "hg_hexconv_dgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p],
     "hg_hexconv_wgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],
+    "hg_dwtaps_fwd": [C.POINTER(DwTapsDesc), _p, _p, _p, _p, _p],
+    "hg_dwtaps_dgrad": [C.POINTER(DwTapsDesc), _p, _p, _p, _p, _p],
+    "hg_dwtaps_wgrad": [C.POINTER(DwTapsDesc), _p, _p, _p, _i, _p],
     "hg_host_rect2hex": [_p, _p, _p, _p, _l, _l, _l, _l, _l, _i, _i, _i, _i, _i],
     "hg_host_hex2rect": [_p, _p, _p, _p, _l, _l, _l, _l, _l, _i, _i, _i, _i, _i],
     "hg_host_hex_to_type": [_p, _p, _l, _l, _l, _i, _i, _i, _i, _i],

@@ -15,8 +15,8 @@
 //     and receives columns b0-1 and b0+4 from its neighbours by warp shuffle (the strip's two edge lanes load one
 //     scalar instead);
 //   * the warp walks DOWN its strip: every source row is loaded once and serves the two output rows that touch it
-//     (rows are prefetched two ahead in registers); out-of-range rows / columns are never loaded, they are the
-//     reference's zero fill;
+//     (PF rows are in flight per warp, held in a statically indexed register ring); out-of-range rows / columns are
+//     never loaded, they are the reference's zero fill;
 //   * float32 math blends horizontally first (once per source row, re-used by both output rows), then vertically;
 //     HG_MATH_EXACT evaluates the reference's float64 expression in its own operation order (vertical blends of the
 //     left and right taps, then the horizontal blend; geometry_np.py:514-517), so a float64 result is bit-identical;
@@ -105,82 +105,89 @@ rect2hex_stream_kernel(const float* __restrict__ src, TD* __restrict__ dst, cons
   };
 
   const int a0 = band * band_rows, a1 = min(a0 + band_rows, h1);
-  int pa; double ua;
+  int a = a0, pa; double ua;
   rect_axis_s(xs[a0], h, pa, ua);
-  int r_next = pa;                                         // source row held in q[0]
-  SrcRow q[PF];
-#pragma unroll
-  for (int k = 0; k < PF; ++k) q[k] = load_row(r_next + k);
-  auto pop_row = [&]() {                                   // oldest prefetched row; a new load takes the freed slot
-    const SrcRow cur = q[0];
-#pragma unroll
-    for (int k = 0; k + 1 < PF; ++k) q[k] = q[k + 1];
-    q[PF - 1] = load_row(r_next + PF);
-    ++r_next;
-    return cur;
-  };
-  int newest = pa - 1;                                     // source row currently in `bot`
+  int r_last;                                              // last source row the band touches
+  { double f; rect_axis_s(xs[a1 - 1], h, r_last, f); ++r_last; }
   double x_next = a0 + 1 < a1 ? xs[a0 + 1] : 0.0;
   TD* __restrict__ dp = dst + plane * (long long)h1 * w1 + (long long)a0 * w1 + b0;
+  auto next_output = [&]() {                               // advance to output row a + 1
+    ++a; dp += w1;
+    if (a < a1) {
+      rect_axis_s(x_next, h, pa, ua);
+      if (a + 1 < a1) x_next = xs[a + 1];
+    }
+  };
+
+  // The loop runs over SOURCE rows, PF of them in flight: the ring of prefetched rows is indexed statically (the loop is
+  // unrolled by PF), so no register that is the target of an outstanding load is ever moved.  (The first version
+  // shifted the ring with register moves; every move waited for its load and at most one row was in flight -- 0.70 of
+  // the HBM copy rate, profiles/r3a_sweep_kernels.jsonl.)  After source row r has been consumed, every output row whose
+  // lower tap row is r (0, 1 or 2 of them) is emitted.
+  SrcRow q[PF];
+  int r = pa;
+#pragma unroll
+  for (int k = 0; k < PF; ++k) q[k] = r + k <= r_last ? load_row(r + k) : load_row(-1);
 
   if (!EXACT) {
     float top[4], bot[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) top[c] = bot[c] = 0.f;
-    for (int a = a0; a < a1; ++a, dp += w1) {
-      while (newest < pa + 1) {                            // warp-uniform: 0, 1 or 2 rows
-        float V[6];
-        widen(pop_row(), V);
-        ++newest;
+    for (; r <= r_last; r += PF) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          top[c] = bot[c];
-          const float L = dm1[c] ? V[c] : V[c + 1], R = dm1[c] ? V[c + 1] : V[c + 2];
-          bot[c] = zero[c] ? 0.f : fmaf((float)jf[c], R - L, L);
+      for (int k = 0; k < PF; ++k) {
+        if (r + k <= r_last) {                             // warp-uniform
+          float V[6];
+          widen(q[k], V);
+          q[k] = r + k + PF <= r_last ? load_row(r + k + PF) : load_row(-1);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            top[c] = bot[c];
+            const float L = dm1[c] ? V[c] : V[c + 1], R = dm1[c] ? V[c + 1] : V[c + 2];
+            bot[c] = zero[c] ? 0.f : fmaf((float)jf[c], R - L, L);
+          }
+          while (a < a1 && pa + 1 == r + k) {
+            const float u = (float)ua;
+            if (store_ok) {
+              TD od[4];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) od[c] = (TD)fmaf(u, bot[c] - top[c], top[c]);
+              store4<TD>(dp, od);
+            }
+            next_output();
+          }
         }
-      }
-      const float u = (float)ua;
-      float o[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) o[c] = fmaf(u, bot[c] - top[c], top[c]);
-      if (store_ok) {
-        TD od[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) od[c] = (TD)o[c];
-        store4<TD>(dp, od);
-      }
-      if (a + 1 < a1) {
-        rect_axis_s(x_next, h, pa, ua);
-        if (a + 2 < a1) x_next = xs[a + 2];
       }
     }
   } else {
     float Vt[6], Vb[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) Vt[k] = Vb[k] = 0.f;
-    for (int a = a0; a < a1; ++a, dp += w1) {
-      while (newest < pa + 1) {
+    for (; r <= r_last; r += PF) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) Vt[k] = Vb[k];
-        widen(pop_row(), Vb);
-        ++newest;
-      }
-      const double u = ua, u1 = dsub(1.0, u);
-      TD od[4];
+      for (int k = 0; k < PF; ++k) {
+        if (r + k <= r_last) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {   // literal operation order of geometry_np.py:514-517, no contraction
-        const double tl = dm1[c] ? Vt[c] : Vt[c + 1], tr = dm1[c] ? Vt[c + 1] : Vt[c + 2];
-        const double bl = dm1[c] ? Vb[c] : Vb[c + 1], br = dm1[c] ? Vb[c + 1] : Vb[c + 2];
-        const double v = jf[c], v1 = dsub(1.0, v);
-        const double t1 = dadd(dmul(u, bl), dmul(u1, tl));
-        const double t2 = dadd(dmul(u, br), dmul(u1, tr));
-        const double r = dadd(dmul(v, t2), dmul(v1, t1));
-        od[c] = zero[c] ? (TD)0 : (TD)r;
-      }
-      if (store_ok) store4<TD>(dp, od);
-      if (a + 1 < a1) {
-        rect_axis_s(x_next, h, pa, ua);
-        if (a + 2 < a1) x_next = xs[a + 2];
+          for (int j = 0; j < 6; ++j) Vt[j] = Vb[j];
+          widen(q[k], Vb);
+          q[k] = r + k + PF <= r_last ? load_row(r + k + PF) : load_row(-1);
+          while (a < a1 && pa + 1 == r + k) {
+            const double u = ua, u1 = dsub(1.0, u);
+            TD od[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {   // literal operation order of geometry_np.py:514-517, no contraction
+              const double tl = dm1[c] ? Vt[c] : Vt[c + 1], tr = dm1[c] ? Vt[c + 1] : Vt[c + 2];
+              const double bl = dm1[c] ? Vb[c] : Vb[c + 1], br = dm1[c] ? Vb[c + 1] : Vb[c + 2];
+              const double v = jf[c], v1 = dsub(1.0, v);
+              const double t1 = dadd(dmul(u, bl), dmul(u1, tl));
+              const double t2 = dadd(dmul(u, br), dmul(u1, tr));
+              const double res = dadd(dmul(v, t2), dmul(v1, t1));
+              od[c] = zero[c] ? (TD)0 : (TD)res;
+            }
+            if (store_ok) store4<TD>(dp, od);
+            next_output();
+          }
+        }
       }
     }
   }
@@ -232,6 +239,8 @@ int try_rect2hex_bilinear_stream(const void* src, void* dst, const double* xs, c
   } while (0)
   if (ddt == HG_F64) HG_LAUNCH(double, true);
   else if (math == HG_MATH_EXACT) HG_LAUNCH(float, true);
+  else if (pf >= 8) HG_LAUNCH1(float, false, 8);
+  else if (pf >= 5) HG_LAUNCH1(float, false, 6);
   else HG_LAUNCH(float, false);
 #undef HG_LAUNCH1
 #undef HG_LAUNCH

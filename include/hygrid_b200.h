@@ -236,6 +236,32 @@ int hg_hexconv_wgrad(const hg_conv_desc* d, const void* x, const void* gy, float
                      hg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Depthwise weighted tap gathers on doubled coordinates: the learned lattice resamplers the reference retired into
+ * "HyGrid/codes in old versions.txt" -- Hex_to_Square_Conv2d_by_Double_Stride (:1-66), Square_to_Hex_Conv2d_by_Double_Stride
+ * (:421-493), Hex_to_Square_original_resolution (:587-636).  One operator covers all three:
+ *   y[n,c,R,J] = sum_t w_s[c,t] * A_s(sy*R + ry_s[t], sx_s*J + ex_s[t]),   s = (R odd and R < odd_limit) ? 1 : 0
+ * A_s: set[s].doubled != 0 -> the doubled ("type1") view of the virtually padded hex lattice (column c of row i is cell
+ * (c - s_i) >> 1 for s_i <= c < 2*Wp + s_i, s_i = (i + parity) & 1, literal 0 elsewhere); == 0 -> the plain padded image.
+ * x [N,C,H,W] float32, y [N,C,Ho,Wo] float32, w_even / w_odd [C, set[s].T] float32 (NULL = all ones).
+ *   hg_dwtaps_dgrad  gx += adjoint (caller zeroes gx);  hg_dwtaps_wgrad  gw[C, set[set].T] += sum gy * A  (caller zeroes).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct hg_taps_set {
+  int T, sx, doubled;          /* taps (1..64), column step per output, coordinate kind */
+  int ry[64], ex[64];          /* row / column offset of every tap (may be negative) */
+} hg_taps_set;
+typedef struct hg_dwtaps_desc {
+  int64_t N, C, H, W, Ho, Wo;
+  int sy, odd_limit;           /* row step per output; odd output rows >= odd_limit use the even tap set */
+  int parity, pad;             /* (even_odd_offset + pad) & 1; frame of pad_value cells around x */
+  float pad_value;
+  hg_taps_set set[2];          /* [0] even output rows, [1] odd output rows */
+} hg_dwtaps_desc;
+int hg_dwtaps_fwd(const hg_dwtaps_desc* d, const float* x, const float* w_even, const float* w_odd, float* y, hg_stream_t stream);
+int hg_dwtaps_dgrad(const hg_dwtaps_desc* d, const float* gy, const float* w_even, const float* w_odd, float* gx,
+                    hg_stream_t stream);
+int hg_dwtaps_wgrad(const hg_dwtaps_desc* d, const float* x, const float* gy, float* gw, int set, hg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Host-buffer entry points (what a numpy caller binds): pinned-staged, chunked over planes,
  * H2D / kernel / D2H overlapped on internal streams.  host_src / host_dst are HOST pointers
  * (pageable or pinned).  device: CUDA device ordinal.  Synchronous (returns when host_dst is

@@ -27,7 +27,8 @@ __all__ = [
     "hexpool_out_shape", "hexpool2d", "hexadaptivepool2d", "hexglobalpool2d",
     "reduce_max", "reduce_min", "reduce_average",
     "heximage_to_type1", "heximage_to_type2", "type1_to_heximage", "hex_pixel_shuffle",
-    "hex_conv_transpose2d",
+    "hex_conv_transpose2d", "resampler_weight", "hex_to_square_double_stride", "square_to_hex_double_stride",
+    "hex_to_square_original_resolution",
 ]
 
 
@@ -305,4 +306,104 @@ def hex_conv_transpose2d(x, kernel, bias=None, even_odd_offset=0, radius=2, stri
     out = torch.empty(B, kernel.shape[0], even.shape[2] + odd.shape[2], wmin, dtype=torch.float32)
     out[:, :, 0::2] = even
     out[:, :, 1::2] = odd
+    return out
+
+
+# --------------------------------------------------------------------------
+# learned lattice resamplers (retired; "codes in old versions.txt":1-66, 421-493, 587-636)
+# --------------------------------------------------------------------------
+# All three are depthwise (one small kernel per channel) weighted gathers on DOUBLED coordinates.  Restated here as the
+# closed form  y[R, J] = sum_t w[c, t] * A(sy*R + ry[t], sx*J + ex[t])  with A the doubled ("type1") view of the padded
+# hex lattice -- A(i, c) = P[i, (c - s_i) // 2] for s_i <= c < 2*Wp + s_i (s_i = (i + o) % 2), 0 elsewhere -- or the
+# plain padded image for the square source; differentiable (autograd supplies the backward oracle).
+def _doubled(P, o, rows, dcols):
+    """P: (N,C,Hp,Wp); rows (Ho,1) and doubled columns (Ho,Wo) index tensors -> (N,C,Ho,Wo) values of the type1 view."""
+    Wp = P.shape[3]
+    si = (rows + o) % 2
+    ok = (dcols >= si) & (dcols < 2 * Wp + si)
+    pc = torch.div(dcols - si, 2, rounding_mode="floor").clamp(0, Wp - 1)
+    return P[:, :, rows.expand_as(dcols), pc] * ok.to(P.dtype)
+
+
+def resampler_weight(f, kind):
+    """Initial (C-independent) f x f weights of the three layers: inverse distance to the output sample, normalised.
+    kind 'hex_to_square' (:36-49), 'square_to_hex' (:445-459), 'original_resolution' (:616-623)."""
+    x = torch.arange(0, f).float()
+    coor = torch.cartesian_prod(x, x).view(f, f, 2)
+    a, b = coor[:, :, 0], coor[:, :, 1]
+    if kind == "hex_to_square":
+        d2 = (a - (f - 1) / 2) * (a - (f - 1) / 2) + (0.5 * a + b - 3 * (f - 1) / 4) * (0.5 * a + b - 3 * (f - 1) / 4)
+    elif kind == "square_to_hex":
+        d2 = (a - (f - 1) / 2) * (a - (f - 1) / 2) + (b - (f - 1) / 2) * (b - (f - 1) / 2)
+    else:
+        d2 = (a + b - (f - 1)) * (a + b - (f - 1)) + (0.5 * a - 0.5 * b) * (0.5 * a - 0.5 * b)
+    dist = 1 / torch.sqrt(d2)
+    return dist / dist.sum()
+
+
+def hex_to_square_double_stride(x, kernel, even_odd_offset=0, downsample_factor=2, padding=0, padding_mode="constant",
+                                padding_value=0):
+    """Hex_to_Square_Conv2d_by_Double_Stride.forward (:50-64): kernel (C, f, f); tap (i, m) sits at type1 row i, sub-column
+    i + 2m of the window (:53-54); the window moves f rows and 2f-1 sub-columns per output (:34) over type1[..., 1:]
+    (one more column is cut on the right when the padded parity is odd, :60)."""
+    f = int(downsample_factor)
+    while x.dim() < 4:
+        x = x.unsqueeze(0)
+    P = F.pad(x, (padding,) * 4, padding_mode, padding_value)
+    o = (even_odd_offset + padding) % 2
+    Hp, Wp = P.shape[-2:]
+    wt = 2 * Wp if o % 2 == 0 else 2 * Wp - 1
+    Ho, Wo = (Hp - f) // f + 1, (wt - (3 * f - 2)) // (2 * f - 1) + 1
+    R = torch.arange(Ho).view(Ho, 1)
+    J = torch.arange(Wo).view(1, Wo)
+    y = 0
+    for i in range(f):
+        for m in range(f):
+            y = y + kernel[:, i, m].view(1, -1, 1, 1) * _doubled(P, o, f * R + i, 1 + (2 * f - 1) * J + i + 2 * m + 0 * R)
+    return y
+
+
+def square_to_hex_double_stride(x, kernel, padding=0, padding_mode="constant", padding_value=0):
+    """Square_to_Hex_Conv2d_by_Double_Stride.forward (:461-489) for downsample_factor 2 (the unfold is hard-wired to a
+    2 x 2 window, :468-469, so every other factor raises a size mismatch in the reference): kernel (C, 4);
+    out[R, J] = sum_{i,j<2} k[2i+j] * P[2R + i, 2J + (R odd) + j] -- a learned 2 x 2 box whose odd rows start one pixel
+    (half a hex cell) further right.  Even rows come from P[..., :-1], odd rows from P[:, 2:, 1:] (:468-469)."""
+    while x.dim() < 4:
+        x = x.unsqueeze(0)
+    P = F.pad(x, (padding,) * 4, padding_mode, padding_value)
+    Hp, Wp = P.shape[-2:]
+    he, ho = math.ceil((Hp - 1) / 4), math.ceil((Hp - 3) / 4)
+    Wo = int((Wp - 2) / 2)
+    if he - ho not in (0, 1) or he < 1 or Wo < 1:
+        raise ValueError("even / odd rows cannot be interleaved (the reference raises a shape mismatch)")
+    Ho = he + ho
+    R = torch.arange(Ho).view(Ho, 1)
+    J = torch.arange(Wo).view(1, Wo)
+    y = 0
+    for i in range(2):
+        for j in range(2):
+            y = y + kernel[:, 2 * i + j].view(1, -1, 1, 1) * P[:, :, (2 * R + i).expand(Ho, Wo), 2 * J + (R % 2) + j]
+    return y
+
+
+def hex_to_square_original_resolution(x, kernel, even_odd_offset=0, padding=0, padding_mode="constant", padding_value=0):
+    """Hex_to_Square_original_resolution.forward (:624-636): kernel (C, 4).  Even rows of the padded lattice are kept; odd
+    rows 1, 3, ... (< Hp - 1; they sit half a cell to the side) are re-interpolated at the even rows' column positions
+    from the rhombus {(R-1, 2J+2), (R, 2J+1), (R, 2J+3), (R+1, 2J+2)} of the type1 view (:630-632, unfold :645-669);
+    the first column is dropped (:635)."""
+    while x.dim() < 4:
+        x = x.unsqueeze(0)
+    P = F.pad(x, (padding,) * 4, padding_mode, padding_value)
+    o = (even_odd_offset + padding) % 2
+    Hp, Wp = P.shape[-2:]
+    if Hp < 3:
+        raise ValueError("fewer than three rows: the reference's unfold raises a shape mismatch")
+    out = P[:, :, :, 1:].clone()
+    rows = torch.arange(1, Hp - 1, 2).view(-1, 1)
+    J = torch.arange(Wp - 1).view(1, -1)
+    if rows.numel() and Wp > 1:
+        tmp = 0
+        for t, (dr, dc) in enumerate(((-1, 2), (0, 1), (0, 3), (1, 2))):
+            tmp = tmp + kernel[:, t].view(1, -1, 1, 1) * _doubled(P, o, rows + dr, 2 * J + dc + 0 * rows)
+        out[:, :, 1:Hp - 1:2] = tmp
     return out

@@ -259,6 +259,11 @@ def emulated_call(name, *a):
         fn = O.hex_to_type1 if name.endswith("1") else O.hex_to_type2
         r = np.asarray(fn(s, off, NP[ddt]))
         view(t, r.size, ddt)[:] = r.reshape(-1)
+    elif name == "hg_host_hex_to_type":       # host writer of the doubled rasters: same encoder, host pointers
+        hexp, t, planes, H, W, off, sdt, ddt, rows_mul, _ = a
+        s = view(hexp, planes * H * W, sdt).reshape(planes, H, W)
+        r = np.asarray((O.hex_to_type1 if rows_mul == 1 else O.hex_to_type2)(s, off, NP[ddt]))
+        view(t, r.size, ddt)[:] = r.reshape(-1)
     elif name in ("hg_hexwarp_linear", "hg_hexwarp_nearest"):
         if name == "hg_hexwarp_linear":
             src, dst, cx, cy, f32, planes, h, w, h1, w1, sdt, ddt, _ = a

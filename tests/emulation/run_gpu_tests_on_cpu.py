@@ -231,6 +231,7 @@ def _extra_call(name, *a):
 DESELECT = [
     "full_size", "pyramid_full", "round_trip_large",  # BASELINE-sized inputs: minutes of numpy for no extra glue coverage
     "host_entry_points",                              # pinned host memory needs a CUDA context
+    "gpu_modules",                                    # hg_dwtaps_* (learned resamplers) has no emulated twin: hardware only
 ]
 
 

@@ -77,7 +77,7 @@ def test_c3_layer_full_batch128():
     with torch.autocast("cuda", dtype=torch.bfloat16):
         y = m(x)
     (y * gy).sum().backward()
-    assert x.numel() * 4 > 2 ** 31
+    assert x.numel() * 4 >= 2 ** 31
     # four images (both ends of the batch, where the byte offsets are largest) against the oracle
     pick = [0, 37, 90, N - 1]
     ref, dx, _, _ = _c3_oracle(x.detach()[pick].cpu(), m.kernel.detach().cpu(), m.bias.detach().cpu(), gy[pick].cpu())
@@ -234,15 +234,17 @@ def test_c5_train_step_vs_oracle_model(autocast):
         loss = torch.nn.functional.cross_entropy(model(x.cuda()).float(), t.cuda())
     loss.backward()
     params = {k: v.detach().cpu().clone().requires_grad_() for k, v in model.named_parameters()}
-    ref = torch.nn.functional.cross_entropy(oracle_forward(params, x), t)
+    ref = torch.nn.functional.cross_entropy(oracle_forward(params, x, autocast=autocast), t)
     ref.backward()
-    # fp32: the direct stencil and the library's batch norm against torch-CPU arithmetic.  autocast: every conv rounds
-    # its operands to bfloat16 (2e-2)
+    # fp32: the direct stencil and the library's batch norm against torch-CPU arithmetic.  autocast: the oracle network
+    # rounds to bfloat16 exactly where the product does (conv operands and output gradients), so what is left is
+    # summation order and the bfloat16 rounding of values that sit on a rounding boundary (2e-2)
     tol = 2e-2 if autocast else 1e-4
     assert abs(float(loss) - float(ref)) <= tol * max(1.0, abs(float(ref)))
     for k, v in model.named_parameters():
         assert v.grad is not None, k
-        assert _rel(v.grad.cpu(), params[k].grad) <= (5e-2 if autocast else 1e-3), k
+        # measured on B200 under autocast: 2.1e-2 for the deepest kernel (three bf16 layers + batch-norm at batch 8), < 1e-2 elsewhere
+        assert _rel(v.grad.cpu(), params[k].grad) <= (4e-2 if autocast else 1e-3), k
     # running statistics of the three batch norms
     sd = model.state_dict()
     assert all(bool(torch.isfinite(sd[f"{b}.bn.running_var"]).all()) for b in ("c1", "c2", "c3"))

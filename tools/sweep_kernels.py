@@ -78,7 +78,7 @@ def main():
             rec(cfg, "r2h fast: TMA warp-specialised", {"HG_R2H_STREAM": 0}, fast, 8 * n)
             rec(cfg, "r2h exact f32: TMA warp-specialised", {"HG_R2H_STREAM": 0}, exact, 8 * n)
             for rows in (32, 64, 128, 256):
-                for pf in (2, 3, 4):
+                for pf in (2, 3, 4, 6, 8):
                     rec(cfg, "r2h fast: stream", {"HG_R2H_STREAM_ROWS": rows, "HG_R2H_STREAM_PF": pf}, fast, 8 * n)
             for rows in (64, 128):
                 for pf in (2, 3, 4):
