@@ -25,8 +25,7 @@
 namespace hg {
 
 constexpr int kHsTW = 128;
-constexpr int kHsRW = 2;                 // output rows per warp
-constexpr int kHsTH = 8 * kHsRW;         // 16 output rows per tile
+constexpr int kHsTH = 16;                // output rows per tile (2 or 1 per warp)
 constexpr int kHsThreads = 256;
 constexpr int kHsStages = 3;
 constexpr int kHsG = 3;                  // planes per item
@@ -46,13 +45,14 @@ __device__ __forceinline__ int hs_col_origin(double y0, double cj) {
   return c & ~3;
 }
 
-template <typename TD, bool EXACT>
-__global__ void __launch_bounds__(kHsThreads, 2)
+template <typename TD, bool EXACT, int NWARPS>     // NWARPS = 8 (two output rows per warp) or 16 (one row per warp: twice
+__global__ void __launch_bounds__(NWARPS * 32, 2)    //  the warps per SM for the latency-bound float64 variant)
 hexsrc_linear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __restrict__ dst, const double* __restrict__ xs,
                          const double* __restrict__ ys, int h, int w, int h1, int w1, int planes, int tiles_x, int tiles_y,
                          long long total_items, long long items_per_cta, int BW, int BH, int stage_bytes, double ci, double cj,
                          double hx, double wy, int col_major, int R, int groups) {
   using WT = typename std::conditional<EXACT, double, float>::type;
+  constexpr int kHsRW = kHsTH / NWARPS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kHsStages * stage_bytes);
   HsTables* tabs = reinterpret_cast<HsTables*>(smem_raw + (size_t)kHsStages * stage_bytes + 64);
@@ -271,11 +271,15 @@ int try_hexsrc_linear_tma(const void* src, void* dst, const double* xs, const do
     return 1;
   const int stage_bytes = (int)ceil_div((int64_t)kHsG * BW * BH * 4, 128) * 128;
   const int smem = kHsStages * stage_bytes + 64 + 2 * (int)sizeof(HsTables);
-  const int variant = math == HG_MATH_FAST ? 0 : (ddt == HG_F32 ? 1 : 2);
-  const void* kern = variant == 0 ? (const void*)hexsrc_linear_tma_kernel<float, false>
-                   : variant == 1 ? (const void*)hexsrc_linear_tma_kernel<float, true>
-                                  : (const void*)hexsrc_linear_tma_kernel<double, true>;
-  static SmemReservation reservation[3];
+  const char* e_warps = getenv("HG_HEXSRC_WARPS");
+  const int nw16 = (e_warps ? atoi(e_warps) : 8) == 16 ? 1 : 0;   // 16 warps / CTA measured within +-2 % of 8 (profiles/r3d_sweep_kernels.jsonl)
+  const int variant = (math == HG_MATH_FAST ? 0 : (ddt == HG_F32 ? 1 : 2)) + 3 * nw16;
+  const int threads = nw16 ? 512 : 256;
+  const void* kerns[6] = {(const void*)hexsrc_linear_tma_kernel<float, false, 8>, (const void*)hexsrc_linear_tma_kernel<float, true, 8>,
+                          (const void*)hexsrc_linear_tma_kernel<double, true, 8>, (const void*)hexsrc_linear_tma_kernel<float, false, 16>,
+                          (const void*)hexsrc_linear_tma_kernel<float, true, 16>, (const void*)hexsrc_linear_tma_kernel<double, true, 16>};
+  const void* kern = kerns[variant];
+  static SmemReservation reservation[6];
   if (reservation[variant].reserve(kern, (size_t)smem) != cudaSuccess) return 1;
   if (g_hs_sms == 0) {
     int dev = 0;
@@ -283,7 +287,7 @@ int try_hexsrc_linear_tma(const void* src, void* dst, const double* xs, const do
     cudaDeviceGetAttribute(&g_hs_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kHsThreads, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); return 1; }
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); return 1; }
   const int tiles_x = (int)ceil_div(w1, kHsTW), tiles_y = (int)ceil_div(h1, kHsTH);
   const long long groups = ceil_div(planes, kHsG);
   const long long total = (long long)tiles_x * tiles_y * groups;
@@ -304,14 +308,21 @@ int try_hexsrc_linear_tma(const void* src, void* dst, const double* xs, const do
   // R = 4: 0.75 / 0.75 -- sharing pays when a row of tiles is so long that the halo rows leave L2 anyway (4K images);
   // float64 weights (exact): R = 1: 0.28, 2: 0.41, 4: 0.52, 8: 0.61 -- bound by the fp64 pipe, so share as much as possible.
   const long long halo_footprint = (long long)tiles_x * stage_bytes * grid;        // bytes staged between two vertically adjacent tiles
-  int R = share_env > 0 ? share_env : (math == HG_MATH_EXACT ? 8 : (halo_footprint > (100ll << 20) ? 2 : 1));
+  // (round 2 sweep, profiles/r3d_sweep_kernels.jsonl: exact R = 8 / 16 / 32 / 64 -> C4 0.59 / 0.64 / 0.65 / 0.65, C2 0.61 / 0.67 / 0.70 / 0.70;
+  //  at R = 64 the kernel moves 16.4 GB of DRAM traffic for 12.7 GB of algorithmic bytes at the same 5.7 TB/s as the float32
+  //  kernels -- every tile halo is re-read from DRAM -- so it is DRAM-bound there, no longer fp64-latency-bound)
+  int R = share_env > 0 ? share_env : (math == HG_MATH_EXACT ? 64 : (halo_footprint > (100ll << 20) ? 2 : 1));
   if (R > (int)groups) R = (int)groups;
-  if (variant == 0)
-    hexsrc_linear_tma_kernel<float, false><<<(unsigned)grid, kHsThreads, smem, st>>>(tmap, (float*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, (int)planes, tiles_x, tiles_y, total, per, BW, BH, stage_bytes, ci, cj, hx, wy, col_major, R, (int)groups);
-  else if (variant == 1)
-    hexsrc_linear_tma_kernel<float, true><<<(unsigned)grid, kHsThreads, smem, st>>>(tmap, (float*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, (int)planes, tiles_x, tiles_y, total, per, BW, BH, stage_bytes, ci, cj, hx, wy, col_major, R, (int)groups);
-  else
-    hexsrc_linear_tma_kernel<double, true><<<(unsigned)grid, kHsThreads, smem, st>>>(tmap, (double*)dst, xs, ys, (int)h, (int)w, (int)h1, (int)w1, (int)planes, tiles_x, tiles_y, total, per, BW, BH, stage_bytes, ci, cj, hx, wy, col_major, R, (int)groups);
+  void* args[] = {(void*)&tmap, (void*)&dst, (void*)&xs, (void*)&ys, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                  nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int hi = (int)h, wi = (int)w, h1i = (int)h1, w1i = (int)w1, pi = (int)planes, gi = (int)groups;
+  long long total_ = total, per_ = per;
+  int bw_ = BW, bh_ = BH, sb_ = stage_bytes, cm_ = col_major, r_ = R;
+  double ci_ = ci, cj_ = cj, hx_ = hx, wy_ = wy;
+  args[4] = &hi; args[5] = &wi; args[6] = &h1i; args[7] = &w1i; args[8] = &pi; args[9] = (void*)&tiles_x; args[10] = (void*)&tiles_y;
+  args[11] = &total_; args[12] = &per_; args[13] = &bw_; args[14] = &bh_; args[15] = &sb_; args[16] = &ci_; args[17] = &cj_;
+  args[18] = &hx_; args[19] = &wy_; args[20] = &cm_; args[21] = &r_; args[22] = &gi;
+  cudaLaunchKernel(kern, dim3((unsigned)grid), dim3((unsigned)threads), args, (size_t)smem, st);
   return finish_launch("hexsrc_linear_tma");
 }
 

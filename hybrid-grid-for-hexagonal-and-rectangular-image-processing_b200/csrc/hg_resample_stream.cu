@@ -193,6 +193,159 @@ rect2hex_stream_kernel(const float* __restrict__ src, TD* __restrict__ dst, cons
   }
 }
 
+// ---- float32 fast path, third generation ---------------------------------------------------------------------------
+// What ncu showed for the kernel above (profiles/r3c_stream_v2_ncu_full.txt): 126 warp instructions per row and lane
+// (float64 row table, per-column selects, 64-bit addressing) and loads that never overlap -- a warp has six scoreboards
+// for outstanding loads, so a rolling prefetch whose loads all have different ages degenerates to one row in flight.
+// Here: (1) source rows are loaded in BATCHES of kSfB rows, the next batch issued in one go before the current one is
+// processed, one wait per batch; (2) the band's row table (i_n, i_f) is evaluated once, one row per lane, and read by
+// shuffle; (3) lanes whose four columns share one tap offset (all but the lane at the column where j_n skips) pick their
+// taps with 5 selects per row instead of 12; (4) pointers advance by one row pitch per row.
+constexpr int kSfBand = 64;        // output rows per band
+
+template <typename TD, bool EXACT, int kSfB, int MINB>      // kSfB = source rows per batch
+__global__ void __launch_bounds__(kStWarps * 32, MINB)
+rect2hex_stream_fast_kernel(const float* __restrict__ src, TD* __restrict__ dst, const double* __restrict__ xs,
+                            const double* __restrict__ ys, int h, int w, int h1, int w1, int bands, int xgroups) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long blk = blockIdx.x;
+  const int xg = (int)(blk % xgroups); blk /= xgroups;
+  const int band = (int)(blk % bands);
+  const long long plane = blk / bands;
+  // row table of the band, shared by the CTA's eight strips: (i_n, i_f) of output rows a0 .. a0 + 63 plus one sentinel
+  // (filled before any warp leaves: strips beyond the image width have no work but their threads hold table slots)
+  using WT = typename std::conditional<EXACT, double, float>::type;
+  __shared__ int s_pa[kSfBand + 1];
+  __shared__ WT s_u[kSfBand + 1];
+  const int a0 = band * kSfBand, a1 = min(a0 + kSfBand, h1);
+  if (threadIdx.x <= kSfBand) {
+    int p = 1 << 30; double f = 0.0;                       // sentinel: no source row ever matches
+    if (a0 + (int)threadIdx.x < a1) rect_axis_s(xs[a0 + threadIdx.x], h, p, f);
+    s_pa[threadIdx.x] = p;
+    s_u[threadIdx.x] = (WT)f;
+  }
+  __syncthreads();
+  const int c0 = (xg * kStWarps + warp) * kStW;
+  if (c0 >= w1) return;
+  const int b0 = c0 + 4 * lane;
+  const bool store_ok = b0 < w1, load_ok = b0 < w;
+  const bool edge = (lane == 0 && c0 > 0) || (lane == 31 && c0 + kStW < w);
+  const int edge_off = (lane == 0 ? -1 : kStW) - 4 * lane;          // relative to this lane's b0
+
+  // column tables
+  bool dm1[4];
+  WT jf[4];
+  bool zero3 = false, generic = false;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    int jn = b0 + c; double f = 0.0;
+    if (store_ok) rect_axis_s(ys[b0 + c], w, jn, f);
+    dm1[c] = jn - (b0 + c) == -1;
+    jf[c] = (WT)f;
+    const bool z = jn >= w || jn <= -2;
+    if (c == 3) zero3 = z; else generic |= z;
+  }
+  generic |= !((dm1[0] == dm1[1]) && (dm1[1] == dm1[2]) && (dm1[2] == dm1[3]));
+  const bool warp_generic = __any_sync(0xffffffffu, generic);
+  bool zero[4] = {false, false, false, zero3};
+  if (warp_generic || EXACT) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      int jn = b0 + c; double f = 0.0;
+      if (store_ok) rect_axis_s(ys[b0 + c], w, jn, f);
+      zero[c] = jn >= w || jn <= -2;
+    }
+  }
+  const bool mode_m1 = dm1[0];
+
+  const int r_first = s_pa[0], r_last = s_pa[a1 - 1 - a0] + 1;
+  const int vlo = max(r_first, 0), vspan = min(r_last, h - 1) - vlo;      // rows that exist: vlo .. vlo + vspan
+
+  // running pointers: one add per row instead of a 64-bit multiply
+  const float* __restrict__ rp = src + plane * (long long)h * w + (long long)r_first * w + b0;    // never dereferenced out of range
+  int rl = r_first;                                        // row rp points at
+  TD* __restrict__ dp = dst + plane * (long long)h1 * w1 + (long long)a0 * w1 + b0;
+  auto load_next = [&]() {
+    SrcRow q;
+    q.v = make_float4(0.f, 0.f, 0.f, 0.f);
+    q.e = 0.f;
+    if ((unsigned)(rl - vlo) <= (unsigned)vspan && vspan >= 0) {           // warp-uniform
+      if (load_ok) q.v = __ldg(reinterpret_cast<const float4*>(rp));
+      if (edge) q.e = __ldg(rp + edge_off);
+    }
+    rp += w; ++rl;
+    return q;
+  };
+
+  // float32 math: horizontally blended rows (4 values); exact: the raw six-column windows of the two source rows
+  float top[EXACT ? 6 : 4], bot[EXACT ? 6 : 4];
+#pragma unroll
+  for (int c = 0; c < (EXACT ? 6 : 4); ++c) top[c] = bot[c] = 0.f;
+  SrcRow cur[kSfB], nxt[kSfB];
+#pragma unroll
+  for (int k = 0; k < kSfB; ++k) cur[k] = load_next();
+  int ka = 0;                                              // next output row of the band (a = a0 + ka)
+  int want = s_pa[0] + 1;                                  // source row that completes it
+  WT ua = s_u[0];
+  for (int r = r_first; r <= r_last; r += kSfB) {
+#pragma unroll
+    for (int k = 0; k < kSfB; ++k) nxt[k] = load_next();   // the whole next batch is in flight while this one is blended
+#pragma unroll
+    for (int k = 0; k < kSfB; ++k) {
+      float prev = __shfl_up_sync(0xffffffffu, cur[k].v.w, 1);
+      float next = __shfl_down_sync(0xffffffffu, cur[k].v.x, 1);
+      if (lane == 0) prev = cur[k].e;
+      if (lane == 31) next = cur[k].e;
+      const float V[6] = {prev, cur[k].v.x, cur[k].v.y, cur[k].v.z, cur[k].v.w, next};
+#pragma unroll
+      for (int c = 0; c < (EXACT ? 6 : 4); ++c) top[c] = bot[c];
+      if (EXACT) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) bot[c] = V[c];
+      } else if (!warp_generic) {
+        float S[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) S[j] = mode_m1 ? V[j] : V[j + 1];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) bot[c] = fmaf((float)jf[c], S[c + 1] - S[c], S[c]);
+        if (zero3) bot[3] = 0.f;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float L = dm1[c] ? V[c] : V[c + 1], R = dm1[c] ? V[c + 1] : V[c + 2];
+          bot[c] = zero[c] ? 0.f : fmaf((float)jf[c], R - L, L);
+        }
+      }
+      while (want == r + k) {                              // 0, 1 or 2 output rows end at this source row
+        TD od[4];
+        if (EXACT) {                                       // literal operation order of geometry_np.py:514-517, no contraction
+          const double u = ua, u1 = dsub(1.0, u);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int m = EXACT ? c : 0;                   // (keeps the non-exact instantiation from indexing past its 4-element arrays)
+            const double tl = dm1[c] ? top[m] : top[m + 1], tr = dm1[c] ? top[m + 1] : top[m + 2];
+            const double bl = dm1[c] ? bot[m] : bot[m + 1], br = dm1[c] ? bot[m + 1] : bot[m + 2];
+            const double v = jf[c], v1 = dsub(1.0, v);
+            const double t1 = dadd(dmul(u, bl), dmul(u1, tl));
+            const double t2 = dadd(dmul(u, br), dmul(u1, tr));
+            od[c] = ((c == 3 ? zero3 : false) || zero[c]) ? (TD)0 : (TD)dadd(dmul(v, t2), dmul(v1, t1));
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) od[c] = (TD)fmaf((float)ua, bot[c] - top[c], top[c]);
+        }
+        if (store_ok) store4<TD>(dp, od);
+        dp += w1;
+        ++ka;
+        want = s_pa[ka] + 1;                               // sentinel past the band's last row
+        ua = s_u[ka];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kSfB; ++k) cur[k] = nxt[k];
+  }
+}
+
 static inline int host_axis_index_s(double coord, int64_t n) {
   const double c = coord + (double)(n - 1) * 0.5;
   return (int)c;  // truncation toward zero, like the device path
@@ -209,6 +362,10 @@ int try_rect2hex_bilinear_stream(const void* src, void* dst, const double* xs, c
   const int enabled = e_on ? atoi(e_on) : 1, band_env = e_rows ? atoi(e_rows) : 64, pf = e_pf ? atoi(e_pf) : 3;
   if (!enabled || !host_xs || !host_ys || sdt != HG_F32) return 1;
   if (!(ddt == HG_F32 || (ddt == HG_F64 && math == HG_MATH_EXACT))) return 1;
+  // measured (profiles/r3f_sweep_r2h_exact.jsonl, C2 / C4 fraction of the HBM copy rate): float32 math 0.96 / 0.93 and the
+  // float64 result of HG_MATH_EXACT 0.97 / 0.93 here; HG_MATH_EXACT with a float32 result is bound by the fp64 pipe
+  // (0.78 / 0.74) and stays with the TMA warp-specialised kernel (0.85 / 0.81) unless HG_R2H_STREAM=2 forces this one
+  if (math == HG_MATH_EXACT && ddt == HG_F32 && enabled < 2) return 1;
   if (w % 4 != 0 || w1 % 4 != 0 || h1 < 1 || w1 < 1) return 1;
   if ((reinterpret_cast<uintptr_t>(src) & 15) != 0 || (reinterpret_cast<uintptr_t>(dst) & (ddt == HG_F64 ? 15 : 15)) != 0) return 1;
   if (h >= (1 << 30) || w >= (1 << 30) || h1 >= (1 << 30) || w1 >= (1 << 30)) return 1;
@@ -223,11 +380,27 @@ int try_rect2hex_bilinear_stream(const void* src, void* dst, const double* xs, c
     if (cur - prev < 0 || cur - prev > 2) return 1;
     prev = cur;
   }
-  const int band_rows = band_env >= 8 ? band_env : 64;
+  const char* e_v3 = getenv("HG_R2H_STREAM_V3");
+  const bool v3 = (e_v3 ? atoi(e_v3) : 1) != 0;
+  const int band_rows = v3 ? kSfBand : (band_env >= 8 ? band_env : 64);
   const int64_t bands = ceil_div(h1, band_rows), xgroups = ceil_div(w1, (int64_t)kStW * kStWarps);
   const int64_t blocks = planes * bands * xgroups;
   if (blocks <= 0 || blocks >= (1ll << 31)) return 1;
   const float* s = (const float*)src;
+  if (v3) {
+#define HG_V3(TD, EX, B, MINB)                                                                                                      \
+  rect2hex_stream_fast_kernel<TD, EX, B, MINB><<<(unsigned)blocks, kStWarps * 32, 0, st>>>(s, (TD*)dst, xs, ys, (int)h, (int)w, (int)h1, \
+                                                                                           (int)w1, (int)bands, (int)xgroups)
+    const int vb = e_pf ? atoi(e_pf) : 4;                  // HG_R2H_STREAM_PF doubles as the batch size of this kernel
+    if (ddt == HG_F64) { if (vb <= 2) HG_V3(double, true, 2, 3); else HG_V3(double, true, 4, 2); }
+    else if (math == HG_MATH_EXACT) { if (vb <= 2) HG_V3(float, true, 2, 3); else HG_V3(float, true, 4, 2); }
+    else if (vb <= 2) HG_V3(float, false, 2, 4);
+    else if (vb <= 4) HG_V3(float, false, 4, 3);
+    else if (vb <= 6) HG_V3(float, false, 6, 2);
+    else HG_V3(float, false, 8, 2);
+#undef HG_V3
+    return finish_launch("rect2hex_bilinear_stream");
+  }
 #define HG_LAUNCH1(TD, EX, PF)                                                                                          \
   rect2hex_stream_kernel<TD, EX, PF><<<(unsigned)blocks, kStWarps * 32, 0, st>>>(s, (TD*)dst, xs, ys, (int)h, (int)w, (int)h1, \
                                                                                   (int)w1, (int)bands, (int)xgroups, band_rows)

@@ -34,14 +34,28 @@ def test_stream_kernel_same_size_vs_oracle(shape):
         assert float(np.abs(fast - ref).max()) <= 1e-5 * 255
         e64, k = _run(Fn, nv, img, None)                                   # float64, HG_MATH_EXACT: the drop-in call
         assert k == "rect2hex_bilinear_stream" and e64.dtype == np.float64 and np.array_equal(e64, ref)
-        e32, k = _run(Fn, nv, img, None, out_dtype=torch.float32, math="exact")
+        e32, k = _run(Fn, nv, img, None, out_dtype=torch.float32, math="exact")      # default: the TMA kernel keeps this variant
+        assert np.array_equal(e32, ref.astype(np.float32))
+        os.environ["HG_R2H_STREAM"] = "2"                                             # forced onto the streaming kernel
+        try:
+            e32, k = _run(Fn, nv, img, None, out_dtype=torch.float32, math="exact")
+        finally:
+            os.environ.pop("HG_R2H_STREAM", None)
         assert k == "rect2hex_bilinear_stream" and np.array_equal(e32, ref.astype(np.float32))
     os.environ.pop("HG_R2H_STREAM_ROWS", None)
-    for pf in ("2", "4"):
+    for pf in ("2", "4", "8"):                                                        # batch sizes of the batched-load kernel
         os.environ["HG_R2H_STREAM_PF"] = pf
         e64, k = _run(Fn, nv, img, None)
         assert k == "rect2hex_bilinear_stream" and np.array_equal(e64, ref)
+        fast, k = _run(Fn, nv, img, None, out_dtype=torch.float32, math="fast")
+        assert k == "rect2hex_bilinear_stream" and float(np.abs(fast - ref).max()) <= 1e-5 * 255
     os.environ.pop("HG_R2H_STREAM_PF", None)
+    os.environ["HG_R2H_STREAM_V3"] = "0"                                              # the rolling-prefetch predecessor (A/B runs)
+    try:
+        e64, k = _run(Fn, nv, img, None)
+        assert k == "rect2hex_bilinear_stream" and np.array_equal(e64, ref)
+    finally:
+        os.environ.pop("HG_R2H_STREAM_V3", None)
     # the same call with the streaming kernel switched off: tiled / direct kernels, identical exact result
     os.environ["HG_R2H_STREAM"] = "0"
     try:

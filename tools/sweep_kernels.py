@@ -6,7 +6,7 @@ every call): which variant ships as the default is decided from this file's outp
 
 rect->hex bilinear (C2 256x3x1024^2, C4 64x3x2160x3840): the row-streaming kernel (HG_R2H_STREAM_ROWS x HG_R2H_STREAM_PF)
 against the TMA warp-specialised kernel (HG_R2H_STREAM=0), float32 fast / exact, and exact with a float64 result.
-hex->rect linear: plane-group sharing HG_HEXSRC_SHARE x tile order HG_HEXSRC_ORDER, fast and exact.
+hex->rect linear: plane-group sharing HG_HEXSRC_SHARE x warps per CTA HG_HEXSRC_WARPS, fast and exact.
 CUDA events on the launching stream, 3 warm-ups, every tensor far larger than the 126 MB L2."""
 import argparse
 import json
@@ -77,27 +77,29 @@ def main():
             exact = lambda: Fn.rect_to_hex(x, None, "bilinear", out_dtype=torch.float32, math="exact", out=y)
             rec(cfg, "r2h fast: TMA warp-specialised", {"HG_R2H_STREAM": 0}, fast, 8 * n)
             rec(cfg, "r2h exact f32: TMA warp-specialised", {"HG_R2H_STREAM": 0}, exact, 8 * n)
-            for rows in (32, 64, 128, 256):
-                for pf in (2, 3, 4, 6, 8):
-                    rec(cfg, "r2h fast: stream", {"HG_R2H_STREAM_ROWS": rows, "HG_R2H_STREAM_PF": pf}, fast, 8 * n)
-            for rows in (64, 128):
-                for pf in (2, 3, 4):
-                    rec(cfg, "r2h exact f32: stream", {"HG_R2H_STREAM_ROWS": rows, "HG_R2H_STREAM_PF": pf}, exact, 8 * n)
+            for pf in (2, 4, 6, 8):
+                rec(cfg, "r2h fast: stream v3 (batched loads)", {"HG_R2H_STREAM_PF": pf}, fast, 8 * n)
+            for rows in (64,):
+                for pf in (2, 4):
+                    rec(cfg, "r2h fast: stream v2 (rolling prefetch)", {"HG_R2H_STREAM_V3": 0, "HG_R2H_STREAM_ROWS": rows, "HG_R2H_STREAM_PF": pf}, fast, 8 * n)
+            for pf in (2, 4):
+                rec(cfg, "r2h exact f32: stream v3", {"HG_R2H_STREAM_PF": pf}, exact, 8 * n)
+            rec(cfg, "r2h exact f32: stream v2", {"HG_R2H_STREAM_V3": 0, "HG_R2H_STREAM_PF": 2}, exact, 8 * n)
             y64 = torch.empty(shp, device="cuda", dtype=torch.float64)
             e64 = lambda: Fn.rect_to_hex(x, None, "bilinear", out_dtype=torch.float64, math="exact", out=y64)
             rec(cfg, "r2h exact f64: direct gather", {"HG_R2H_STREAM": 0}, e64, 12 * n)
-            for rows in (64, 128):
-                for pf in (2, 3):
-                    rec(cfg, "r2h exact f64: stream", {"HG_R2H_STREAM_ROWS": rows, "HG_R2H_STREAM_PF": pf}, e64, 12 * n)
+            for pf in (2, 4):
+                rec(cfg, "r2h exact f64: stream v3", {"HG_R2H_STREAM_PF": pf}, e64, 12 * n)
+            rec(cfg, "r2h exact f64: stream v2", {"HG_R2H_STREAM_V3": 0, "HG_R2H_STREAM_PF": 2}, e64, 12 * n)
             del y64
         if "h2r" in a.what:
             hf_ = lambda: Fn.hex_to_rect(x, None, "linear", out_dtype=torch.float32, math="fast", twin="np", out=y)
             he_ = lambda: Fn.hex_to_rect(x, None, "linear", out_dtype=torch.float32, math="exact", twin="np", out=y)
-            for order in (0, 1):
+            for warps in (8, 16):
                 for R in (1, 2, 4):
-                    rec(cfg, "h2r fast", {"HG_HEXSRC_SHARE": R, "HG_HEXSRC_ORDER": order}, hf_, 8 * n)
+                    rec(cfg, "h2r fast", {"HG_HEXSRC_SHARE": R, "HG_HEXSRC_WARPS": warps}, hf_, 8 * n)
                 for R in (8, 16, 32, 64):
-                    rec(cfg, "h2r exact f32", {"HG_HEXSRC_SHARE": R, "HG_HEXSRC_ORDER": order}, he_, 8 * n)
+                    rec(cfg, "h2r exact f32", {"HG_HEXSRC_SHARE": R, "HG_HEXSRC_WARPS": warps}, he_, 8 * n)
             rec(cfg, "h2r fast (shipped heuristic)", {}, hf_, 8 * n)
             rec(cfg, "h2r exact f32 (shipped heuristic)", {}, he_, 8 * n)
         del x, y
