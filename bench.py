@@ -538,7 +538,9 @@ def extra_c5(cx):
     t = torch.randint(0, 10, (B,), generator=g).to(cx.dev)
     out = {"workload": f"C5: hex CNN (3->32->64->128, BN+ReLU, max pool, GAP, Linear) train step, {B} img/GPU x {cx.world} GPU, "
                        f"{HW}x{HW}, autocast bf16, SGD momentum", "scaling": "weak", "variants": {}}
-    for name, kw in (("overlapped (3 groups, all-reduce issued from backward)", dict(groups=3, overlap=True)),
+    # groups by layer: {c1: conv kernel + BN affine}, {c2: ...}, {c3: ... + the classifier}; the last group is complete --
+    # and its all-reduce in flight -- after the first third of the backward pass
+    for name, kw in (("overlapped (3 layer groups, all-reduce issued from backward)", dict(groups=[3, 3, 5], overlap=True)),
                      ("blocking (one all-reduce after backward)", dict(groups=1, overlap=False))):
         bucket = FlatGradBucket(model.parameters(), **kw)
         opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9)

@@ -85,10 +85,10 @@ def pad(input: Tensor, padding: int = 0, mode="constant", value=0) -> Tensor:
 # ------------------------------------------------------------------------------------------------
 # hex convolution (HexFrames.py:22-185)
 # ------------------------------------------------------------------------------------------------
-def _conv_desc(x, Cout, Ho, Wo, radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, relu):
+def _conv_desc(x, Cout, Ho, Wo, radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, relu, pad_mode=0):
     N, Cin, H, W = x.shape
     return nv.ConvDesc(N, Cin, Cout, H, W, Ho, Wo, radius, stride, dilation, groups, pad_, parity, float(pad_value),
-                       nv.hg_dtype(x.dtype), nv.hg_dtype(y_dtype), algo, int(relu))
+                       nv.hg_dtype(x.dtype), nv.hg_dtype(y_dtype), algo, int(relu), int(pad_mode) if pad_ else 0)
 
 
 def _conv_out_shape(H, W, radius, stride, dilation, pad_):
@@ -103,7 +103,7 @@ def _conv_out_shape(H, W, radius, stride, dilation, pad_):
 class _HexConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, kernel, bias, meta, scale=None):
-        radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, relu = meta
+        radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, relu, pad_mode = meta
         x = nv.require_cuda(x, "input").contiguous()
         w = kernel.detach().float().contiguous()
         b = bias.detach().float().contiguous() if bias is not None else None
@@ -111,7 +111,7 @@ class _HexConvFn(torch.autograd.Function):
         Cout = w.shape[0]
         Ho, Wo = _conv_out_shape(H, W, radius, stride, dilation, pad_)
         y = torch.empty((N, Cout, Ho, Wo), dtype=y_dtype, device=x.device)
-        d = _conv_desc(x, Cout, Ho, Wo, radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, relu)
+        d = _conv_desc(x, Cout, Ho, Wo, radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, relu, pad_mode)
         if scale is not None:      # inference-only fused per-channel affine (HexConvModule conv -> BN(eval) -> ReLU); b is the shift
             sc = scale.detach().float().contiguous()
             nv.call("hg_hexconv_fwd_affine", C.byref(d), nv.ptr(x), nv.ptr(w), nv.ptr(sc), nv.ptr(b), nv.ptr(y),
@@ -133,21 +133,33 @@ class _HexConvFn(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
-        radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, relu = ctx.meta
+        radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, relu, pad_mode = ctx.meta
         if relu:
             raise RuntimeError("the fused ReLU epilogue is inference-only")
         Ho, Wo = ctx.out_shape
         gy = gy.to(y_dtype).contiguous()
-        d = _conv_desc(x, w.shape[0], Ho, Wo, radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, 0)
+        d = _conv_desc(x, w.shape[0], Ho, Wo, radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, 0, pad_mode)
         st = nv.stream_ptr(x.device)
+        framed = bool(pad_) and pad_mode != 0          # reflect / replicate / circular frame, resolved inside the loaders
 
-        def pick(op):   # a forced tcgen05 forward does not oblige the backward ops to have a tcgen05 kernel
-            d.algo = algo if (algo != 2 or nv.query("hg_hexconv_umma_eligible", C.byref(d), op)) else 1
-            return d
+        def pick(op, desc=None):   # a forced tcgen05 forward does not oblige the backward ops to have a tcgen05 kernel
+            desc = d if desc is None else desc
+            desc.algo = algo if (algo != 2 or nv.query("hg_hexconv_umma_eligible", C.byref(desc), op)) else 1
+            return desc
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = torch.empty_like(x)
-            nv.call("hg_hexconv_dgrad", C.byref(pick(1)), nv.ptr(gy), nv.ptr(w), nv.ptr(gx), st)
+            if framed:
+                # the data gradient of the frame folds back onto the image: gradient of the virtually padded input
+                # (pad = 0 on the [H + 2p, W + 2p] geometry), then the pad kernel's adjoint
+                N, Cin, H, W = x.shape
+                gp = torch.empty((N, Cin, H + 2 * pad_, W + 2 * pad_), dtype=x.dtype, device=x.device)
+                dp = _conv_desc(gp, w.shape[0], Ho, Wo, radius, stride, dilation, groups, 0, parity, 0.0, y_dtype, algo, 0)
+                nv.call("hg_hexconv_dgrad", C.byref(pick(1, dp)), nv.ptr(gy), nv.ptr(w), nv.ptr(gp), st)
+                gx = torch.empty_like(x)
+                nv.call("hg_pad2d_bwd", nv.ptr(gp), nv.ptr(gx), N * Cin, H, W, pad_, pad_, pad_, pad_, pad_mode, nv.hg_dtype(x.dtype), st)
+            else:
+                gx = torch.empty_like(x)
+                nv.call("hg_hexconv_dgrad", C.byref(pick(1)), nv.ptr(gy), nv.ptr(w), nv.ptr(gx), st)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             Cin = x.shape[1]
             xw, dw = x, pick(2)
@@ -155,10 +167,10 @@ class _HexConvFn(torch.autograd.Function):
                 # first layers (RGB): zero-pad the input channels to 16 so that the tcgen05 weight-gradient kernel
                 # takes the layer (the padded channels' gradients are dropped); 20x faster than the CUDA-core stencil
                 xp = torch.nn.functional.pad(x, (0, 0, 0, 0, 0, 16 - Cin))
-                dp = _conv_desc(xp, w.shape[0], Ho, Wo, radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, 0)
-                if nv.query("hg_hexconv_umma_eligible", C.byref(dp), 2):
-                    dp.algo = 2
-                    xw, dw = xp, dp
+                dpw = _conv_desc(xp, w.shape[0], Ho, Wo, radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, 0, pad_mode)
+                if nv.query("hg_hexconv_umma_eligible", C.byref(dpw), 2):
+                    dpw.algo = 2
+                    xw, dw = xp, dpw
             sink_w, sink_b = ctx.sinks
             if xw is not x or sink_w is None or tuple(sink_w.view.shape) != tuple(w.shape):
                 sink_w = None
@@ -187,14 +199,16 @@ class _HexConvFn(torch.autograd.Function):
 
 
 def hexconv2d(x: Tensor, kernel: Tensor, bias: Optional[Tensor] = None, even_odd_offset=0, radius=2, stride=1, padding=0,
-              dilation=1, groups=1, padding_value=0.0, out_dtype=torch.float32, algo=0, relu=False) -> Tensor:
-    """Functional hex convolution with virtual constant padding (closed form of HexFrames.py:96-169)."""
+              dilation=1, groups=1, padding_value=0.0, out_dtype=torch.float32, algo=0, relu=False, padding_mode='constant') -> Tensor:
+    """Functional hex convolution with virtual padding in any F.pad mode (closed form of HexFrames.py:96-169)."""
     x = _as4(x)
     if x.dtype not in (torch.float32, torch.bfloat16):
         raise TypeError(f"hex convolution runs on float32 or bfloat16 activations, got {x.dtype}")
     parity = (int(even_odd_offset) + int(padding)) % 2
+    if padding_mode not in _PAD_MODES:
+        raise NotImplementedError(f"Unrecognised padding mode {padding_mode}")
     meta = (int(radius), int(stride), int(dilation), int(groups), int(padding), parity, float(padding_value or 0),
-            out_dtype, int(algo), bool(relu))
+            out_dtype, int(algo), bool(relu), _PAD_MODES[padding_mode])
     return _HexConvFn.apply(x, kernel, bias, meta)
 
 
@@ -250,43 +264,54 @@ class HexConv2d(nn.Module):
                 bound = 1 / math.sqrt(fan_in)
                 init.uniform_(self.bias, -bound, bound)
 
-    def _tensor_core_ok(self, input: Tensor) -> bool:
+    def _tensor_core_ok(self, input: Tensor, pad_=None) -> bool:
         """Would the tcgen05 kernel take this layer?  Then fp32 activations are fed to it directly (it rounds
         them to bfloat16 on the way into shared memory) instead of paying a separate cast pass."""
         x = _as4(input)
-        if x.dtype not in (torch.float32, torch.bfloat16) or self.padding_mode != 'constant' or x.dim() != 4:
+        if x.dtype not in (torch.float32, torch.bfloat16) or x.dim() != 4:
             return False
+        pad_ = self.pad if pad_ is None else pad_
         try:
-            Ho, Wo = _conv_out_shape(x.shape[2], x.shape[3], self.hexkernel_radius, self.stride, self.dilation, self.pad)
+            Ho, Wo = _conv_out_shape(x.shape[2], x.shape[3], self.hexkernel_radius, self.stride, self.dilation, pad_)
         except ValueError:
             return False
         d = _conv_desc(x, self.out_channels, Ho, Wo, self.hexkernel_radius, self.stride, self.dilation, self.groups,
-                       self.pad, self.padded_even_odd_offset, 0.0, self.out_dtype, 2, 0)
+                       pad_, self.padded_even_odd_offset, 0.0, self.out_dtype, 2, 0)
         return bool(nv.query("hg_hexconv_umma_eligible", C.byref(d), 0))
 
-    def _activation(self, input: Tensor):
+    def _activation(self, input: Tensor, pad_=None):
         """(input in the dtype the kernels read, whether autocast routes this call to the tcgen05 kernel)."""
         if torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16:
-            if self.algo != 1 and self._tensor_core_ok(input):
+            if self.algo != 1 and self._tensor_core_ok(input, pad_):
                 return (input if input.dtype in (torch.float32, torch.bfloat16) else input.float()), True
             return input.to(torch.bfloat16), False
         if self.kernel.dtype not in (torch.float32, torch.bfloat16):
             raise TypeError(f"HexConv2d parameters must be float32 (or bfloat16), got {self.kernel.dtype}")
         return input.to(self.kernel.dtype), False
 
-    def forward(self, input: Tensor, relu: bool = False, affine=None) -> Tensor:
+    def forward(self, input: Tensor, relu: bool = False, affine=None, frame=None) -> Tensor:
         """``affine=(scale, shift)``: inference-only fused ``act(conv(x) * scale[c] + shift[c])`` (the conv's own bias must
-        already be folded into ``shift``); ``relu=True`` fuses the ReLU.  Neither records anything for backward."""
-        input, autocast_tc = self._activation(input)
+        already be folded into ``shift``); ``relu=True`` fuses the ReLU.  Neither records anything for backward.
+        ``frame=(p, mode)``: an explicit padding layer in front of a ``padding=0`` conv (HexConvModule, HexModules.py:185-190)
+        folded into the kernel -- ``p`` cells of ``mode`` around the input, WITHOUT the parity change ``padding=p`` would
+        make (the reference builds that conv with padding 0, so its row parity ignores the frame)."""
+        input, autocast_tc = self._activation(input, None if frame is None else int(frame[0]))
         self._autocast_tc = autocast_tc          # record of the last call (introspection / tests); not read by the forward
         input = _as4(input)
         algo = 2 if autocast_tc else self.algo
-        pad_, parity = self.pad, self.padded_even_odd_offset
-        if self.pad and self.padding_mode != 'constant':
-            input = pad(input, self.pad, self.padding_mode, self.padding_value)
-            pad_ = 0
+        pad_, parity, mode, value = self.pad, self.padded_even_odd_offset, self.padding_mode, self.padding_value
+        if frame is not None:
+            if self.pad:
+                raise ValueError("frame= is for convolutions built with padding=0")
+            pad_, mode, value = int(frame[0]), frame[1], 0
+        if mode not in _PAD_MODES:
+            raise NotImplementedError(f"Unrecognised padding mode {mode}")
+        if pad_ and mode != 'constant':          # the loaders read the reflected / replicated / wrapped image in place
+            H, W = input.shape[-2:]
+            if (mode == 'reflect' and (pad_ >= H or pad_ >= W)) or (mode == 'circular' and (pad_ > H or pad_ > W)):
+                raise RuntimeError(f"{mode} padding of {pad_} does not fit a {H} x {W} input")
         meta = (self.hexkernel_radius, self.stride, self.dilation, self.groups, pad_, parity,
-                float(self.padding_value or 0), self.out_dtype, algo, bool(relu))
+                float(value or 0), self.out_dtype, algo, bool(relu), _PAD_MODES[mode])
         if affine is not None:
             if torch.is_grad_enabled() and (input.requires_grad or self.kernel.requires_grad):
                 raise RuntimeError("the fused affine epilogue is inference-only: call it under torch.no_grad()")

@@ -226,21 +226,37 @@ class HexConvModule(nn.Module):
         relu = bool(tail) and tail[0] == 'act' and activate and self.with_activation and type(self.activate) is nn.ReLU
         return scale, shift, relu
 
+    def _frame(self):
+        """The explicit padding layer as a frame the conv kernel resolves itself (no padded copy): ``(p, mode)`` when the
+        layer is one of this module's pad layers with the same padding on all four sides in front of a plain HexConv2d,
+        else None.  ref: HexModules.py:185-190, :279-281."""
+        if not self.with_explicit_padding or self.with_spectral_norm or type(self.conv) is not hnn.HexConv2d or self.conv.pad:
+            return None
+        layer = self.padding_layer
+        if not isinstance(layer, _HexPad2d) or len(set(layer.padding)) != 1:
+            return None
+        return (int(layer.padding[0]), layer._mode) if layer.padding[0] > 0 else None
+
     def forward(self, x: torch.Tensor, activate: bool = True, norm: bool = True) -> torch.Tensor:
         fused = False
         skip_norm = False
         for idx, layer in enumerate(self.order):
             if layer == 'conv':
+                kw = {}
                 if self.with_explicit_padding:
-                    x = self.padding_layer(x)
+                    frame = self._frame()
+                    if frame is not None and x.dim() >= 3 and (frame[1] != 'reflect' or frame[0] < min(x.shape[-2:])):
+                        kw = dict(frame=frame)
+                    else:
+                        x = self.padding_layer(x)
                 bn = self._fusable_bn(idx, activate, norm)
                 if bn is not None:
                     scale, shift, fused = bn
                     skip_norm = True
-                    x = self.conv(x, relu=fused, affine=(scale, shift))
+                    x = self.conv(x, relu=fused, affine=(scale, shift), **kw)
                     continue
                 fused = self._fusable_relu(idx, x, activate, norm)
-                x = self.conv(x, relu=True) if fused else self.conv(x)
+                x = self.conv(x, relu=True, **kw) if fused else self.conv(x, **kw)
             elif layer == 'norm' and norm and self.with_norm:
                 if skip_norm:
                     skip_norm = False

@@ -35,7 +35,7 @@ class ConvDesc(C.Structure):
                 ("Ho", C.c_int64), ("Wo", C.c_int64),
                 ("radius", C.c_int), ("stride", C.c_int), ("dilation", C.c_int), ("groups", C.c_int),
                 ("pad", C.c_int), ("parity", C.c_int), ("pad_value", C.c_float),
-                ("x_dtype", C.c_int), ("y_dtype", C.c_int), ("algo", C.c_int), ("relu", C.c_int)]
+                ("x_dtype", C.c_int), ("y_dtype", C.c_int), ("algo", C.c_int), ("relu", C.c_int), ("pad_mode", C.c_int)]
 
 
 class TapsSet(C.Structure):

@@ -79,8 +79,12 @@ class FlatGradBucket:
     bfloat16 parameters in a float32 bucket) keep their own ``.grad`` tensor; it is copied into the bucket when it lands
     and the reduced value is written back by ``finish()`` / ``all_reduce()``."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], dtype: torch.dtype = torch.float32, groups: int = 1,
+    def __init__(self, params: Iterable[torch.nn.Parameter], dtype: torch.dtype = torch.float32, groups=1,
                  overlap: bool = False, group=None, average: bool = True):
+        """``groups``: an int (that many runs of consecutive parameters, cut by tensor count so that a run ends with a
+        layer's last tensor rather than in the middle of the largest one) or a sequence of run lengths, e.g.
+        ``[3, 3, 5]`` = first three tensors, next three, last five.  Backward produces gradients last layer first, so
+        the LAST run is reduced first, while the earlier layers' backward is still running."""
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
@@ -94,7 +98,14 @@ class FlatGradBucket:
         self.total = total
         self.flat = torch.zeros(total, dtype=dtype, device=dev)
         self.group, self.average, self.overlap = group, average, bool(overlap)
-        self.bounds = self._cut(max(1, min(int(groups), len(self.params))))
+        if isinstance(groups, int):
+            self.bounds = self._cut(max(1, min(int(groups), len(self.params))))
+        else:
+            sizes = [int(v) for v in groups]
+            if sum(sizes) != len(self.params) or any(v < 1 for v in sizes):
+                raise ValueError(f"group sizes {sizes} do not tile the {len(self.params)} trainable parameters")
+            ends = [sum(sizes[:i + 1]) for i in range(len(sizes))]
+            self.bounds = list(zip([0] + ends[:-1], ends))
         self.group_of = [g for g, (a, b) in enumerate(self.bounds) for _ in range(a, b)]
         self.trace: List[Tuple[str, int]] = []           # ("ready", param index) / ("launch", group index), per step
         self._hooks = []
@@ -103,18 +114,18 @@ class FlatGradBucket:
 
     # ------------------------------------------------------------------ layout
     def _cut(self, n: int) -> List[Tuple[int, int]]:
-        """``n`` contiguous runs of parameters holding about equal numbers of elements: [(first, last+1), ...]."""
-        sizes = [p.numel() for p in self.params]
-        target, acc, cuts, start = sum(sizes) / n, 0, [], 0
-        for i, s in enumerate(sizes):
-            acc += s
-            left_groups = n - len(cuts) - 1
-            left_params = len(sizes) - (i + 1)
-            if left_groups and (acc >= target * (len(cuts) + 1) or left_params == left_groups):
-                cuts.append((start, i + 1))
-                start = i + 1
-        cuts.append((start, len(sizes)))
-        return [c for c in cuts if c[1] > c[0]]
+        """``n`` runs of consecutive parameters with (almost) equal numbers of TENSORS: [(first, last+1), ...].  The
+        messages are latency-bound (a few hundred KB in total), so balancing bytes buys nothing; what matters is that a
+        run is complete -- and its collective launched -- as early in the backward pass as possible."""
+        count = len(self.params)
+        base, rem = divmod(count, n)
+        cuts, start = [], 0
+        for g in range(n):
+            size = base + (1 if g >= n - rem else 0)          # the later (first-ready) runs take the remainder
+            if size:
+                cuts.append((start, start + size))
+                start += size
+        return cuts
 
     def view(self, i: int) -> torch.Tensor:
         p = self.params[i]

@@ -34,7 +34,10 @@ static int make_geom(const hg_conv_desc* d, ConvGeom& g, ConvTaps& tp) {
   g.N = (int)d->N; g.Cin = (int)d->Cin; g.Cout = (int)d->Cout; g.H = (int)d->H; g.W = (int)d->W; g.Ho = (int)d->Ho; g.Wo = (int)d->Wo;
   g.s = d->stride; g.d = d->dilation; g.groups = d->groups; g.pad = d->pad;
   g.cin_g = g.Cin / g.groups; g.cout_g = g.Cout / g.groups;
-  g.pad_value = d->pad_value; g.relu = d->relu;
+  g.pad_value = d->pad_value; g.relu = d->relu; g.pad_mode = d->pad_mode;
+  HG_REQUIRE(d->pad_mode >= 0 && d->pad_mode <= 3, HG_E_ARG, "pad_mode must be 0 (constant), 1 (reflect), 2 (replicate) or 3 (circular)");
+  HG_REQUIRE(d->pad_mode != 1 || (d->pad < d->H && d->pad < d->W), HG_E_SHAPE, "reflect padding must be smaller than the image");
+  HG_REQUIRE(d->pad_mode != 3 || (d->pad <= d->H && d->pad <= d->W), HG_E_SHAPE, "circular padding must not exceed the image");
   conv_make_taps(d->radius, d->stride, d->dilation, d->parity & 1, tp);
   return HG_OK;
 }
@@ -96,6 +99,8 @@ int hg_hexconv_dgrad(const hg_conv_desc* d, const void* gy, const float* w, void
   ConvGeom g; ConvTaps tp;
   int rc = make_geom(d, g, tp);
   if (rc) return rc;
+  HG_REQUIRE(g.pad_mode == 0 || g.pad == 0, HG_E_UNSUPPORTED,
+             "hg_hexconv_dgrad: reflect / replicate / circular frames are folded by the caller (pad = 0 on the padded geometry, then hg_pad2d_bwd)");
   if (g.N == 0) return HG_OK;
   bool umma;
   if ((rc = pick_algo(d, OP_DGRAD, umma))) return rc;

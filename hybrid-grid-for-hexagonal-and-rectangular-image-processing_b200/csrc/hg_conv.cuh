@@ -30,7 +30,16 @@ struct ConvGeom {
   int s, d, groups, pad, cin_g, cout_g;
   float pad_value;
   int relu;
+  int pad_mode;          // 0 constant, 1 reflect, 2 replicate, 3 circular
 };
+
+// Source index of frame coordinate i (in [-pad, n + pad)) for the non-constant padding modes of F.pad.
+__host__ __device__ __forceinline__ int conv_pad_remap(int i, int n, int mode) {
+  if (mode == 1) { if (i < 0) i = -i; if (i >= n) i = 2 * (n - 1) - i; }         // reflect (pad < n)
+  else if (mode == 2) { i = i < 0 ? 0 : (i >= n ? n - 1 : i); }                   // replicate
+  else { if (i < 0) i += n; else if (i >= n) i -= n; }                            // circular (pad <= n)
+  return i;
+}
 
 static inline int conv_num_taps(int r) { return 3 * r * r - 3 * r + 1; }
 

@@ -78,6 +78,8 @@ hexconv_fwd_direct(const TX* __restrict__ x, const float* __restrict__ w, const 
           if (j < g.W + g.pad) {
             v = g.pad_value;                               // inside the frame, outside the image
             if (in_r && j >= 0 && j < g.W) v = ldf(xc + (int64_t)i * g.W + j);
+            else if (g.pad_mode)                           // reflect / replicate / circular frame: read the image in place
+              v = ldf(xc + (int64_t)conv_pad_remap(i, g.H, g.pad_mode) * g.W + conv_pad_remap(j, g.W, g.pad_mode));
           }
           xv[p] = v;
         }
@@ -262,6 +264,7 @@ hexconv_wgrad_direct(const TX* __restrict__ x, const TG* __restrict__ gy, float*
             if (cl_ok && k < kn && j < g.W + g.pad) {
               v = g.pad_value;
               if (i >= 0 && i < g.H && j >= 0 && j < g.W) v = ldf(xc + (int64_t)i * g.W + j);
+              else if (g.pad_mode) v = ldf(xc + (int64_t)conv_pad_remap(i, g.H, g.pad_mode) * g.W + conv_pad_remap(j, g.W, g.pad_mode));
             }
 #pragma unroll
             for (int a = 0; a < kWgC; ++a) acc[a][b][k] = fmaf(gv[a], v, acc[a][b][k]);

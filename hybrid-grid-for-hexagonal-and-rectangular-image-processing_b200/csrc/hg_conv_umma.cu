@@ -50,6 +50,7 @@ struct UmmaParams {
   int sh[2][kTaps];              // column shift 0..3 of each tap, per output-row parity
   int pad;                       // frame of pad_value around the input; literal zero beyond
   float pad_value;
+  int pad_mode;                  // 1 reflect / 2 replicate / 3 circular frame: the loader reads the image in place (LDG variant)
   int relu, has_bias, transpose_w;   // transpose_w: weights indexed [red][out] (dgrad)
   int cred_total, c_off, accumulate; // reduction channels > 64 run as passes of <= 64: this pass covers channels
                                      // [c_off, c_off + Cred) of cred_total and (accumulate) adds to the output of the previous pass
@@ -173,17 +174,20 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
           ptx::mbar_wait(&empty[slot], (use & 1) ^ 1);
         } else {
           ptx::mbar_wait(&empty[slot], (use & 1) ^ 1);
-          const int i = r0 + P.row0 + t;
-          const bool row_in = i >= 0 && i < P.Hi;
+          int i = r0 + P.row0 + t;
           const bool row_frame = i >= -P.pad && i < P.Hi + P.pad;
+          if (P.pad_mode && row_frame) i = conv_pad_remap(i, P.Hi, P.pad_mode);      // frame rows read the image in place
+          const bool row_in = i >= 0 && i < P.Hi;
 #pragma unroll
           for (int q = 0; q < kUmMaxQ; ++q) {
             const int task = tid + q * kUmLoaders;
             if (task < ntasks) {
               const int kc = task / kUmPW, p = task - kc * kUmPW;
-              const int j = c0 + P.col0 + p;
+              int j = c0 + P.col0 + p;
+              const bool col_frame = j >= -P.pad && j < P.Wi + P.pad;
+              if (P.pad_mode && col_frame) j = conv_pad_remap(j, P.Wi, P.pad_mode);
               const bool col_in = j >= 0 && j < P.Wi;
-              const float fill = (row_frame && j >= -P.pad && j < P.Wi + P.pad) ? P.pad_value : 0.f;
+              const float fill = (row_frame && col_frame) ? P.pad_value : 0.f;
               const TIN* __restrict__ src = in_n + (size_t)(kc * 8) * plane + (size_t)i * P.Wi + j;
               float v[8];
 #pragma unroll
@@ -446,7 +450,7 @@ static int launch_umma_any(const void* in, const float* w, const float* scale, c
   memset(&tmap, 0, sizeof(tmap));
   constexpr int es = (int)sizeof(TIN), A = 16 / es;
   PFN_encodeTiled enc = get_encode_tiled();
-  bool tma = !g_um_no_tma && enc != nullptr && P.pad_value == 0.f && ((int64_t)P.Wi * es) % 16 == 0 &&
+  bool tma = !g_um_no_tma && enc != nullptr && P.pad_value == 0.f && P.pad_mode == 0 && ((int64_t)P.Wi * es) % 16 == 0 &&
              (reinterpret_cast<uintptr_t>(in) & 15) == 0;
   if (tma) {
     int slots, rst, rb;
@@ -532,7 +536,7 @@ int conv_fwd_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp, 
     for (int par = 0; par < 2; ++par) P.sh[par][k] = tp.co[par][k] - cmin;
   }
   P.row0 = -g.pad; P.col0 = cmin - g.pad;
-  P.pad = g.pad; P.pad_value = g.pad_value;
+  P.pad = g.pad; P.pad_value = g.pad_value; P.pad_mode = g.pad ? g.pad_mode : 0;
   P.relu = g.relu; P.has_bias = bias != nullptr; P.transpose_w = 0;
   umma_common(P, g.Ho, g.Wo, g.N);
   return dispatch_umma(d->x_dtype, d->y_dtype, x, w, scale, bias, y, P, st);
@@ -558,7 +562,7 @@ int conv_dgrad_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp
     for (int ipar = 0; ipar < 2; ++ipar) P.sh[ipar][k] = cs[ipar][k] - cmin;
   }
   P.row0 = g.pad - 2; P.col0 = cmin;
-  P.pad = 0; P.pad_value = 0.f;
+  P.pad = 0; P.pad_value = 0.f; P.pad_mode = 0;
   P.relu = 0; P.has_bias = 0; P.transpose_w = 1;
   umma_common(P, g.H, g.W, g.N);
   return dispatch_umma(d->y_dtype, d->x_dtype, gy, w, nullptr, nullptr, gx, P, st);

@@ -45,6 +45,7 @@ struct WgParams {
   int sh[2][kWuTaps];
   int pad;
   float pad_value;
+  int pad_mode;                  // 1 reflect / 2 replicate / 3 circular frame, resolved by the x loader (LDG variant)
   int xslots, gslots, bands, ctiles, has_bias;
   int rstages, raw_bytes;        // TMA variant
   int m64;                       // Cout <= 64: UMMA M = 64 (half the A-operand shared-memory reads of an M = 128 view)
@@ -136,7 +137,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
       pk.x = wu_pack(v[0], v[1]); pk.y = wu_pack(v[2], v[3]); pk.z = wu_pack(v[4], v[5]); pk.w = wu_pack(v[6], v[7]);
       return pk;
     };
-    auto load_x = [&](const TX* __restrict__ xn, int i, int c0) {
+    auto load_x = [&](const TX* __restrict__ xn, int i, int c0) {    // i: frame row, remapped below for the non-constant modes
       unsigned char* sb = xring + (size_t)xs * xslot_bytes;
       uint4 pk[kWuMaxQ];
       if (TMA) {
@@ -157,15 +158,19 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
         ptx::mbar_wait(&xempty[xs], xph ^ 1);
       } else {
         ptx::mbar_wait(&xempty[xs], xph ^ 1);
-        const bool row_in = i >= 0 && i < P.H, row_frame = i >= -P.pad && i < P.H + P.pad;
+        const bool row_frame = i >= -P.pad && i < P.H + P.pad;
+        if (P.pad_mode && row_frame) i = conv_pad_remap(i, P.H, P.pad_mode);          // frame rows read the image in place
+        const bool row_in = i >= 0 && i < P.H;
 #pragma unroll
         for (int q = 0; q < kWuMaxQ; ++q) {
           const int task = tid + q * kWuConv;
           if (task < xtasks) {
             const int kc = task / kWuPW, p = task - kc * kWuPW;
-            const int j = c0 + P.col0 + p;
+            int j = c0 + P.col0 + p;
+            const bool col_frame = j >= -P.pad && j < P.W + P.pad;
+            if (P.pad_mode && col_frame) j = conv_pad_remap(j, P.W, P.pad_mode);
             const bool col_in = j >= 0 && j < P.W;
-            const float fill = (row_frame && j >= -P.pad && j < P.W + P.pad) ? P.pad_value : 0.f;
+            const float fill = (row_frame && col_frame) ? P.pad_value : 0.f;
             const TX* __restrict__ src = xn + (size_t)(kc * 8) * xplane + (size_t)i * P.W + j;
             float v[8];
 #pragma unroll
@@ -465,7 +470,7 @@ static int launch_wu_any(const void* x, const void* gy, float* gw, float* gb, Wg
   memset(&gmap, 0, sizeof(gmap));
   constexpr int xes = (int)sizeof(TX), ges = (int)sizeof(TG), A = 16 / xes;
   PFN_encodeTiled enc = get_encode_tiled();
-  bool tma = !g_wu_no_tma && enc != nullptr && P.pad_value == 0.f && ((int64_t)P.W * xes) % 16 == 0 && ((int64_t)P.Wo * ges) % 16 == 0 &&
+  bool tma = !g_wu_no_tma && enc != nullptr && P.pad_value == 0.f && P.pad_mode == 0 && ((int64_t)P.W * xes) % 16 == 0 && ((int64_t)P.Wo * ges) % 16 == 0 &&
              (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(gy) & 15) == 0;
   if (tma) {
     int xs_, gs_, rst, rb;
@@ -504,7 +509,7 @@ int conv_wgrad_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp
     for (int par = 0; par < 2; ++par) P.sh[par][k] = tp.co[par][k] - cmin;
   }
   P.row0 = -g.pad; P.col0 = cmin - g.pad;
-  P.pad = g.pad; P.pad_value = g.pad_value;
+  P.pad = g.pad; P.pad_value = g.pad_value; P.pad_mode = g.pad ? g.pad_mode : 0;
   P.has_bias = gbias != nullptr;
   P.bands = (int)ceil_div(g.Ho, kWuBand);
   P.ctiles = (int)ceil_div(g.Wo, kWuTile);

@@ -197,8 +197,8 @@ int hg_hexglobalpool_bwd(const void* gy, const void* x, const int32_t* aux_idx, 
  * Hex convolution.  ref: HexFrames.py:22-185 HexConv2d.forward (closed form in DESIGN.md):
  *   y[n,co,R,q] = bias[co] + sum_{ci,tap} w[co,ci,0,tap] * D[s*R + a*d, 1 + (R%2)*s + 2*s*q + t*d + 2*d*m]
  * with D the doubled view of the (virtually) padded input, parity o = (even_odd_offset+pad)%2.
- * x [N,Cin,H,W], w [Cout,Cin/groups,1,K] (K = 3r^2-3r+1), y [N,Cout,Ho,Wo].  Padding is virtual
- * (constant pad_value); other padding modes are applied by the caller (pad = 0, parity passed).
+ * x [N,Cin,H,W], w [Cout,Cin/groups,1,K] (K = 3r^2-3r+1), y [N,Cout,Ho,Wo].  Padding is virtual in every
+ * mode (pad_mode): the frame is pad_value, or the reflected / replicated / wrapped image, read in place.
  * io_dtype: element type of x / y / gradients in {HG_F32, HG_BF16}; weights and bias are
  * float32, accumulation is float32.  algo: 0 = auto, 1 = direct stencil, 2 = tcgen05 implicit GEMM.
  * ---------------------------------------------------------------------------------------- */
@@ -209,6 +209,10 @@ typedef struct hg_conv_desc {
   int x_dtype, y_dtype; /* HG_F32 / HG_BF16 */
   int algo;
   int relu;             /* fused epilogue of HexConvModule (conv -> act), 0/1 */
+  int pad_mode;         /* how the `pad` frame is filled: 0 constant pad_value, 1 reflect, 2 replicate, 3 circular (F.pad modes,
+                           ref HexFrames.py:13-21, :121; HexModules.py:185-190).  Modes 1..3 are resolved by the forward and
+                           weight-gradient loaders by coordinate remapping -- no padded copy of x exists; hg_hexconv_dgrad
+                           takes them on the padded geometry (pad = 0 on an [H+2p, W+2p] gradient) followed by hg_pad2d_bwd. */
 } hg_conv_desc;
 
 int hg_hexconv_out_shape(int64_t H, int64_t W, int radius, int stride, int dilation, int pad,

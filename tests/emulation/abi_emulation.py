@@ -72,7 +72,8 @@ def conv_entry(name, a):
     bf = (lambda t: t.bfloat16().float()) if tc else (lambda t: t)   # the tcgen05 kernels read activations and weights as bfloat16
 
     def run(x, w, b):                          # callers round the operands the kernel reads (never the autograd leaf)
-        return HO.hexconv2d(x, w, b, eo, d.radius, d.stride, d.pad, d.dilation, d.groups, "constant", d.pad_value)
+        mode = ("constant", "reflect", "replicate", "circular")[d.pad_mode if d.pad else 0]      # header: frame filled in place
+        return HO.hexconv2d(x, w, b, eo, d.radius, d.stride, d.pad, d.dilation, d.groups, mode, d.pad_value)
     if name in ("hg_hexconv_fwd", "hg_hexconv_fwd_affine"):
         if name == "hg_hexconv_fwd":
             _, x, w, b, y, _ = a

@@ -293,3 +293,66 @@ def test_even_rows_only_output(cfg):
     assert y.shape == ref.shape and _rel(y.detach().cpu(), ref.detach()) <= 1e-4
     ref.sum().backward(); y.sum().backward()
     assert _rel(xg.grad.cpu(), xr.grad) <= 1e-4
+
+
+# ----------------------------------------------------------------------------------------------------
+# reflect / replicate / circular frames resolved inside the conv loaders (no padded copy of x)
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["reflect", "replicate", "circular"])
+@pytest.mark.parametrize("cfg", [
+    # Cin, Cout, H, W, radius, stride, pad, offset, tensor cores
+    (4, 6, 20, 22, 2, 1, 2, 1, False),
+    (5, 7, 17, 19, 3, 2, 3, 0, False),
+    (64, 64, 40, 136, 2, 1, 1, 0, True),
+    (32, 48, 33, 130, 2, 1, 2, 1, True),
+])
+def test_conv_padding_modes_in_kernel(mode, cfg):
+    from HyGrid import HexFrames as hf
+    from HyGrid import _native as nv
+    Cin, Cout, H, W, r, s, pad, off, tc = cfg
+    torch.manual_seed(71)
+    m = hf.HexConv2d(Cin, Cout, off, r, stride=s, padding=pad, padding_mode=mode).cuda()
+    x = torch.randn(2, Cin, H, W)
+    if tc:                                                   # bf16-exact operands: what is left is the summation order
+        x = x.bfloat16().float()
+        with torch.no_grad():
+            m.kernel.copy_(m.kernel.bfloat16().float())
+        m.algo = 2
+    xr = x.clone().requires_grad_()
+    wr, br = m.kernel.detach().cpu().requires_grad_(), m.bias.detach().cpu().requires_grad_()
+    ref = HO.hexconv2d(xr, wr, br, off, r, s, pad, 1, 1, padding_mode=mode)
+    gy = torch.randn_like(ref)
+    if tc:
+        gy = gy.bfloat16().float()
+    (ref * gy).sum().backward()
+    xg = x.cuda().requires_grad_()
+    nv.reset_launch_count()
+    y = m(xg)
+    assert nv.launch_count() == 1, "the frame must be resolved by the conv kernel itself, not by a pad launch"
+    assert y.shape == ref.shape and _rel(y.detach().cpu(), ref.detach()) <= 1e-4
+    (y * gy.cuda()).sum().backward()
+    assert _rel(xg.grad.cpu(), xr.grad) <= 1e-4
+    assert _rel(m.kernel.grad.cpu(), wr.grad) <= 1e-3
+    assert _rel(m.bias.grad.cpu(), br.grad) <= 1e-3
+
+
+@pytest.mark.parametrize("mode", ["reflect", "replicate"])
+def test_hexconvmodule_explicit_padding_is_one_launch(mode):
+    """HexConvModule(padding_mode='reflect' | 'replicate') puts a padding layer in front of a padding = 0 conv
+    (HexModules.py:185-190); here the frame is folded into the conv kernel: one launch in inference, same numbers as the
+    module's own two-step route (pad kernel, then conv)."""
+    from HyGrid import HexModules as hm
+    from HyGrid import _native as nv
+    torch.manual_seed(72)
+    m = hm.HexConvModule(8, 12, 1, 2, padding=2, padding_mode=mode).cuda().eval()
+    x = torch.randn(2, 8, 21, 26).cuda()
+    with torch.no_grad():
+        nv.reset_launch_count()
+        y = m(x)
+        assert nv.launch_count() == 1
+        two_step = torch.relu(m.conv(m.padding_layer(x)))
+    assert y.shape == two_step.shape and _rel(y.cpu(), two_step.cpu()) <= 1e-5
+    xr = x.cpu()
+    ref = torch.relu(HO.hexconv2d(torch.nn.functional.pad(xr, (2, 2, 2, 2), mode), m.conv.kernel.detach().cpu(), m.conv.bias.detach().cpu(),
+                                  1, 2, 1, 0))
+    assert _rel(y.cpu(), ref) <= 1e-4
