@@ -275,6 +275,7 @@ class Ctx:
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
         self.peak, self.peak_src = measured_peak()
+        self.graphs = []
 
     def barrier(self):
         if self.world > 1:
@@ -568,6 +569,40 @@ def extra_c5(cx):
                                  "ranks_in_sync": bool(torch.allclose(lo_, hi_, rtol=0, atol=1e-6 * float(hi_.abs()) + 1e-9)),
                                  "collective": "NCCL all-reduce inside the timed region" if cx.world > 1 else "single GPU: no collective"}
         bucket.detach()
+    if cx.args.c5_graph:
+        # The eager step is host-bound (about 130 launches of a few microseconds in 2 ms): every rank replays the WHOLE
+        # step -- forward, backward, the NCCL all-reduce of the flat bucket, SGD -- as one captured CUDA graph.
+        try:
+            bucket = FlatGradBucket(model.parameters(), groups=1, overlap=False)
+            opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9)
+
+            def step():
+                bucket.zero_()
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    loss = torch.nn.functional.cross_entropy(model(x).float(), t)
+                loss.backward()
+                bucket.finish()
+                opt.step()
+                return loss
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    step()
+            torch.cuda.current_stream().wait_stream(side)
+            cx.barrier()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+            cx.barrier()
+            total, _ = cx.timed(graph.replay, 50, warmup=5)
+            out["variants"]["whole step replayed as one CUDA graph (all-reduce captured)"] = {
+                "ms_per_step": total, "images_per_s": cx.world * B / (total * 1e-3), "value": cx.world * B * HW * HW / (total * 1e-3) / 1e6,
+                "unit": UNIT, "collective": "NCCL all-reduce inside the graph" if cx.world > 1 else "single GPU: no collective"}
+            cx.graphs.append(graph)                        # kept alive until the process leaves (see run_ours)
+            bucket.detach()
+        except Exception as e:                              # noqa: BLE001
+            out["variants"]["whole step replayed as one CUDA graph (all-reduce captured)"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     return out
 
 
@@ -600,10 +635,16 @@ def run_ours(args):
         if cx.world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args.workload, args.cpu_images)
         print(json.dumps(line), flush=True)
+    nv.lib().hg_host_release()
     if cx.world > 1:
         cx.dist.barrier()
+        if cx.graphs:
+            # tearing the process group down while a captured graph still holds NCCL kernels hung an 8-GPU run in round 1
+            # (after the result line was out): the line above is flushed, leave without the collective teardown
+            cx.torch.cuda.synchronize()
+            sys.stdout.flush()
+            os._exit(0)
         cx.dist.destroy_process_group()
-    nv.lib().hg_host_release()
     return 0
 
 
@@ -617,6 +658,7 @@ def main():
     ap.add_argument("--math", default="fast", choices=["fast", "exact"])
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs (extra block)")
+    ap.add_argument("--no-c5-graph", dest="c5_graph", action="store_false", help="skip the CUDA-graph variant of the C5 step")
     ap.add_argument("--extra", default="", help="comma list of extra legs to run (c2_exact_f64,c4,c3,c5); default all")
     ap.add_argument("--cpu-images", type=int, default=48)
     ap.add_argument("--no-cpu", action="store_true")

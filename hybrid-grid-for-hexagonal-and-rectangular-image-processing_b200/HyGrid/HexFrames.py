@@ -161,34 +161,28 @@ class _HexConvFn(torch.autograd.Function):
                 gx = torch.empty_like(x)
                 nv.call("hg_hexconv_dgrad", C.byref(pick(1)), nv.ptr(gy), nv.ptr(w), nv.ptr(gx), st)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            Cin = x.shape[1]
-            xw, dw = x, pick(2)
-            if Cin < 16 and groups == 1 and algo != 1 and x.dtype == torch.bfloat16:
-                # first layers (RGB): zero-pad the input channels to 16 so that the tcgen05 weight-gradient kernel
-                # takes the layer (the padded channels' gradients are dropped); 20x faster than the CUDA-core stencil
-                xp = torch.nn.functional.pad(x, (0, 0, 0, 0, 0, 16 - Cin))
-                dpw = _conv_desc(xp, w.shape[0], Ho, Wo, radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, 0, pad_mode)
-                if nv.query("hg_hexconv_umma_eligible", C.byref(dpw), 2):
-                    dpw.algo = 2
-                    xw, dw = xp, dpw
+            dw = pick(2)
+            if x.shape[1] < 16 and groups == 1 and algo != 1 and x.dtype == torch.bfloat16:
+                # first layers (RGB under autocast): the tcgen05 weight-gradient kernel takes them with the channel slice
+                # rounded up to 16 inside the kernel (zeros for the channels that do not exist); 20x faster than the
+                # CUDA-core stencil, and no zero-padded copy of x
+                forced = _conv_desc(x, w.shape[0], Ho, Wo, radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, 2, 0, pad_mode)
+                if nv.query("hg_hexconv_umma_eligible", C.byref(forced), 2):
+                    dw = forced
             sink_w, sink_b = ctx.sinks
-            if xw is not x or sink_w is None or tuple(sink_w.view.shape) != tuple(w.shape):
+            if sink_w is None or tuple(sink_w.view.shape) != tuple(w.shape):
                 sink_w = None
             if not ctx.has_bias or sink_b is None:
                 sink_b = None
-            cin_w = w.shape[1] if xw is x else xw.shape[1]          # Cin / groups, or the padded channel count
-            gw = sink_w.view if sink_w is not None else \
-                torch.zeros((w.shape[0], cin_w) + tuple(w.shape[2:]), dtype=torch.float32, device=x.device)
+            gw = sink_w.view if sink_w is not None else torch.zeros(w.shape, dtype=torch.float32, device=x.device)
             gb = None
             if ctx.has_bias:
                 gb = sink_b.view if sink_b is not None else torch.zeros(w.shape[0], dtype=torch.float32, device=x.device)
-            nv.call("hg_hexconv_wgrad", C.byref(dw), nv.ptr(xw), nv.ptr(gy), nv.ptr(gw), nv.ptr(gb), st)
+            nv.call("hg_hexconv_wgrad", C.byref(dw), nv.ptr(x), nv.ptr(gy), nv.ptr(gw), nv.ptr(gb), st)
             if sink_w is not None:
                 gw = None
                 sink_w.landed()
             else:
-                if xw is not x:
-                    gw = gw[:, :Cin].contiguous()
                 gw = gw.to(ctx.param_dtypes[0])
             if sink_b is not None:
                 gb = None

@@ -172,9 +172,10 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
             const bool col_in = j >= 0 && j < P.W;
             const float fill = (row_frame && col_frame) ? P.pad_value : 0.f;
             const TX* __restrict__ src = xn + (size_t)(kc * 8) * xplane + (size_t)i * P.W + j;
+            const int c_left = P.cin_total - P.ci_off - kc * 8;      // channels of x that exist from this group on (RGB: 3 of 16)
             float v[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = (row_in && col_in) ? wu_ld(src + (size_t)e * xplane) : fill;
+            for (int e = 0; e < 8; ++e) v[e] = e < c_left ? ((row_in && col_in) ? wu_ld(src + (size_t)e * xplane) : fill) : 0.f;
             pk[q] = pack8(v);
           }
         }
@@ -264,7 +265,8 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
           if (co < P.Cout) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (cb + j < P.Cin) atomicAdd(gw + ((size_t)(P.co_off + co) * P.cin_total + P.ci_off + cb + j) * kWuTaps + k, __uint_as_float(v[j]));
+              if (cb + j < P.Cin && P.ci_off + cb + j < P.cin_total)
+                atomicAdd(gw + ((size_t)(P.co_off + co) * P.cin_total + P.ci_off + cb + j) * kWuTaps + k, __uint_as_float(v[j]));
           }
         }
       }
@@ -427,12 +429,15 @@ bool conv_wgrad_umma_eligible(const hg_conv_desc* d) {
   if (d->radius != 2 || d->stride != 1 || d->dilation != 1 || d->groups != 1) return false;
   // one launch covers <= 64 input channels (7*Cin + 16 TMEM columns <= 512) x <= 128 output channels (UMMA M);
   // larger layers run as a grid of launches over channel slices (independent blocks of gw)
-  if (d->Cin % 16 != 0 || d->Cin < 16 || d->Cin > 1024) return false;
+  // (input channels that are not a multiple of 16 -- an RGB first layer -- run with the slice rounded up: the loader
+  //  supplies zeros for the channels that do not exist and the epilogue drops their gradients)
+  if (d->Cin < 1 || d->Cin > 1024) return false;
+  const int64_t cin16 = (d->Cin + 15) / 16 * 16;
   if (d->Cout % 8 != 0 || d->Cout < 8 || d->Cout > 1024) return false;
   int a, b, c, e;
-  if (!wu_pick((int)(d->Cin > 64 ? 64 : d->Cin), (int)(d->Cout > 128 ? 128 : d->Cout), 4, 4, false, a, b, c, e)) return false;
-  if (d->Cin > 64 && d->Cin % 64 != 0 && !wu_pick((int)(d->Cin % 64), (int)(d->Cout > 128 ? 128 : d->Cout), 4, 4, false, a, b, c, e)) return false;
-  if (d->Cout > 128 && d->Cout % 128 != 0 && !wu_pick((int)(d->Cin > 64 ? 64 : d->Cin), (int)(d->Cout % 128), 4, 4, false, a, b, c, e)) return false;
+  if (!wu_pick((int)(cin16 > 64 ? 64 : cin16), (int)(d->Cout > 128 ? 128 : d->Cout), 4, 4, false, a, b, c, e)) return false;
+  if (cin16 > 64 && cin16 % 64 != 0 && !wu_pick((int)(cin16 % 64), (int)(d->Cout > 128 ? 128 : d->Cout), 4, 4, false, a, b, c, e)) return false;
+  if (d->Cout > 128 && d->Cout % 128 != 0 && !wu_pick((int)(cin16 > 64 ? 64 : cin16), (int)(d->Cout % 128), 4, 4, false, a, b, c, e)) return false;
   if (d->algo == 0 && (d->x_dtype != HG_BF16 || d->Cin * d->Cout < 32 * 32)) return false;
   return true;
 }
@@ -470,7 +475,8 @@ static int launch_wu_any(const void* x, const void* gy, float* gw, float* gb, Wg
   memset(&gmap, 0, sizeof(gmap));
   constexpr int xes = (int)sizeof(TX), ges = (int)sizeof(TG), A = 16 / xes;
   PFN_encodeTiled enc = get_encode_tiled();
-  bool tma = !g_wu_no_tma && enc != nullptr && P.pad_value == 0.f && P.pad_mode == 0 && ((int64_t)P.W * xes) % 16 == 0 && ((int64_t)P.Wo * ges) % 16 == 0 &&
+  bool tma = !g_wu_no_tma && enc != nullptr && P.pad_value == 0.f && P.pad_mode == 0 && P.ci_off + P.Cin <= P.cin_total &&
+             ((int64_t)P.W * xes) % 16 == 0 && ((int64_t)P.Wo * ges) % 16 == 0 &&
              (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(gy) & 15) == 0;
   if (tma) {
     int xs_, gs_, rst, rb;
@@ -519,7 +525,7 @@ int conv_wgrad_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp
   for (int co0 = 0; co0 < g.Cout; co0 += 128) {
     for (int ci0 = 0; ci0 < g.Cin; ci0 += 64) {
       P.co_off = co0; P.Cout = g.Cout - co0 < 128 ? g.Cout - co0 : 128;
-      P.ci_off = ci0; P.Cin = g.Cin - ci0 < 64 ? g.Cin - ci0 : 64;
+      P.ci_off = ci0; P.Cin = g.Cin - ci0 < 64 ? (g.Cin - ci0 + 15) / 16 * 16 : 64;      // rounded up: see the eligibility note
       P.has_bias = gbias != nullptr && ci0 == 0;
       // The kernel is shared-memory-bandwidth bound (per gy row: 64 MMAs x 6 KB of operand reads + ~175 KB of
       // staging / conversion traffic at 128 B/clk): with Cout <= 64 an M = 64 tile reads 2 KB of A per MMA

@@ -101,7 +101,20 @@ def main():
     del x2, y2
     torch.cuda.empty_cache()
 
-    # table-driven gathers (added after the last GPU run of round 1: first numbers come from the next one)
+    # R3: hex -> hex affine warp with the inverse map evaluated in-kernel (2 degree rotation + shift), float32 coordinates
+    import numpy as np
+    Nw = 4 if a.small else 32
+    xw = torch.rand(Nw, 3, 2160, 3840, device=dev)
+    th = np.deg2rad(2.0)
+    Hm = np.array([[np.cos(th), -np.sin(th), 3.0], [np.sin(th), np.cos(th), -5.0], [0, 0, 1.0]])
+    for interp in ("linear", "nearest"):
+        yw = Fn.hex_warp_affine(xw, Hm, interp)
+        rec(f"r3 hex warp affine {interp} 2160x3840", lambda: timeit(lambda: Fn.hex_warp_affine(xw, Hm, interp), a.reps),
+            4 * (xw.numel() + yw.numel()), Nw * yw.shape[-2] * yw.shape[-1])
+    del xw, yw
+    torch.cuda.empty_cache()
+
+    # table-driven gathers
     Ns = 4 if a.small else 32
     xs_ = torch.randn(Ns, 64 * 4, 256, 256, device=dev)                      # 64 output channels, upscale 2
     ps = hf.HexPixelShuffle(2)
