@@ -26,8 +26,9 @@ from oracle import hygrid_oracle as O
 pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-if os.path.join(ROOT, "tools") not in sys.path:
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
+for _p in (os.path.join(ROOT, "tools"), os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
 
 
 def _rel(a, b):
@@ -224,7 +225,8 @@ def test_c4_pool_pyramid_full_planes(c4_batch):
 # ----------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("autocast", [False, True])
 def test_c5_train_step_vs_oracle_model(autocast):
-    from hexcnn import HexCNN, oracle_forward
+    from hexcnn import HexCNN
+    from hexcnn_oracle import oracle_forward
     torch.manual_seed(51)
     model = HexCNN().cuda().train()
     g = torch.Generator().manual_seed(52)

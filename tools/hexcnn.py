@@ -1,11 +1,8 @@
 """The hex CNN of BASELINE config 5 (builder-defined): HexConvModule 3->32->64->128 (BN + ReLU),
 HexPool2d('max', 2, 2) between, global average, Linear -> 10, on 128 x 128 hex lattices.
 
-``HexCNN``        the product model (HyGrid modules over libhygrid_b200.so) -- used by bench.py, tools/hexcnn_ddp.py and
-                  the parity test.
-``oracle_forward`` the same network evaluated with the CPU oracle's operators (oracle/hexframes_oracle.py: the closed
-                  forms of HexConv2d / HexPool2d pinned against the live reference) and torch's own batch norm / linear, on
-                  the product model's parameters.  Test infrastructure: only tests/ and bench.py's CPU leg call it.
+``HexCNN``: the product model (HyGrid modules over libhygrid_b200.so) -- used by bench.py, tools/hexcnn_ddp.py and the parity
+test.  Its CPU twin built from the oracle's operators lives with the tests (tests/hexcnn_oracle.py).
 """
 import os
 import sys
@@ -38,47 +35,3 @@ class HexCNN(nn.Module):
         x = self.pool(self.c2(x))
         x = self.c3(x)
         return self.fc(self.gap(x))
-
-
-class _RoundGradBf16(torch.autograd.Function):
-    """Identity whose backward rounds the gradient to bfloat16: the tensor-core data / weight gradient kernels read the
-    float32 gradient of a conv output through a bfloat16 conversion on its way into shared memory."""
-
-    @staticmethod
-    def forward(ctx, y):
-        return y.view_as(y)
-
-    @staticmethod
-    def backward(ctx, g):
-        return g.bfloat16().float()
-
-
-def _round_bf16(t):
-    """Value rounded to bfloat16, gradient passed through unchanged (what a kernel that rounds its operand on load does)."""
-    return t + (t.bfloat16().float() - t).detach()
-
-
-def oracle_forward(params, x, eps=1e-5, autocast=False):
-    """Forward of the same network on CPU tensors with the oracle's operators.  ``params``: dict name -> CPU tensor
-    (requires_grad as wanted) with the product model's ``named_parameters()`` names; training-mode batch norm (batch
-    statistics), conv without bias (HexConvModule's bias='auto' with a norm layer).  ``autocast``: restate where the
-    product rounds to bfloat16 under torch.autocast -- every conv reads bfloat16 activations and output gradients; the
-    tensor-core layers (c2, c3) also round their weights (the RGB layer runs the direct stencil with float32 weights)."""
-    from oracle import hexframes_oracle as HO
-    F = torch.nn.functional
-    for blk in ("c1", "c2", "c3"):
-        w = params[f"{blk}.conv.kernel"]
-        if autocast:
-            x = _round_bf16(x)
-            if blk != "c1":
-                w = _round_bf16(w)
-        x = HO.hexconv2d(x, w, None, 0, 2, 1, 1)
-        if autocast:
-            x = _RoundGradBf16.apply(x)
-        x = F.batch_norm(x, None, None, params[f"{blk}.bn.weight"], params[f"{blk}.bn.bias"], True, 0.1, eps)
-        x = F.relu(x)
-        if blk != "c3":
-            x = HO.hexpool2d(x, "max", 2, 2)
-    x = HO.hexglobalpool2d(x, "average")
-    with torch.autocast("cpu", dtype=torch.bfloat16, enabled=autocast):    # nn.Linear is an autocast op in the product too
-        return F.linear(x, params["fc.weight"], params["fc.bias"])
