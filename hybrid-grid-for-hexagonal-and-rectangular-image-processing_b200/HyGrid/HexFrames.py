@@ -30,7 +30,7 @@ from . import _native as nv
 __all__ = ["pad", "HexConv2d", "HexConv2dAdaptivePadding", "HexPool2d", "HexAdaptivePool2d", "HexGlobalPool2d",
            "heximage_to_type1", "heximage_to_type2", "type1_to_heximage", "max_pooling", "min_pooling",
            "average_pooling", "hexconv2d", "hexpool2d", "HexPixelShuffle", "pixel_shuffle_table",
-           "HexConvTranspose2d", "conv_transpose_tables"]
+           "HexConvTranspose2d", "conv_transpose_tables", "set_fp32_tensor_cores"]
 
 _PAD_MODES = {"constant": 0, "reflect": 1, "replicate": 2, "circular": 3}
 _POOL = {"max": nv.POOL_MAX, "min": nv.POOL_MIN, "average": nv.POOL_AVG}
@@ -85,10 +85,42 @@ def pad(input: Tensor, padding: int = 0, mode="constant", value=0) -> Tensor:
 # ------------------------------------------------------------------------------------------------
 # hex convolution (HexFrames.py:22-185)
 # ------------------------------------------------------------------------------------------------
-def _conv_desc(x, Cout, Ho, Wo, radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, relu, pad_mode=0):
+def _conv_desc(x, Cout, Ho, Wo, radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, relu, pad_mode=0,
+               accumulate=0, x_dtype=None):
     N, Cin, H, W = x.shape
     return nv.ConvDesc(N, Cin, Cout, H, W, Ho, Wo, radius, stride, dilation, groups, pad_, parity, float(pad_value),
-                       nv.hg_dtype(x.dtype), nv.hg_dtype(y_dtype), algo, int(relu), int(pad_mode) if pad_ else 0)
+                       nv.hg_dtype(x_dtype or x.dtype), nv.hg_dtype(y_dtype), algo, int(relu), int(pad_mode) if pad_ else 0,
+                       int(accumulate))
+
+
+# float32 callers on the tensor cores: three bfloat16 passes over split operands (x = x_hi + x_lo, w = w_hi + w_lo;
+# y ~ x_hi*w_hi + x_hi*w_lo + x_lo*w_hi, float32 accumulation, the dropped lo*lo term is 2^-16 relative) keep float32-class
+# accuracy (measured ~2e-5 of the range; the contract is 1e-4) at a fraction of the CUDA-core stencil's time.
+_FP32_TENSOR_CORES = True
+
+
+def set_fp32_tensor_cores(enabled: bool) -> None:
+    """Route float32 (non-autocast) hex convolutions whose channel contraction is dense enough through the tcgen05 kernels
+    as three bfloat16 passes over split operands (default on).  Off: the CUDA-core direct stencil, plain float32 FMAs."""
+    global _FP32_TENSOR_CORES
+    _FP32_TENSOR_CORES = bool(enabled)
+
+
+def _split_bf16(t: Tensor):
+    t = t.contiguous()
+    hi = torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
+    lo = torch.empty_like(hi)
+    nv.call("hg_split_bf16", nv.ptr(t), nv.ptr(hi), nv.ptr(lo), t.numel(), nv.stream_ptr(t.device))
+    return hi, lo
+
+
+def _x3_eligible(x, Cout, Ho, Wo, radius, stride, dilation, groups, pad_, parity, need_grad):
+    """Do the tcgen05 kernels cover all the passes of the split route (forward; data and weight gradient when training)?"""
+    d = _conv_desc(x, Cout, Ho, Wo, radius, stride, dilation, groups, pad_, parity, 0.0, torch.float32, 2, 0, x_dtype=torch.bfloat16)
+    if x.shape[1] * Cout < 1024:
+        return False
+    ops = (0, 1, 2) if need_grad else (0,)
+    return all(nv.query("hg_hexconv_umma_eligible", C.byref(d), op) for op in ops)
 
 
 def _conv_out_shape(H, W, radius, stride, dilation, pad_):
@@ -121,6 +153,27 @@ class _HexConvFn(torch.autograd.Function):
         Cout = w.shape[0]
         Ho, Wo = _conv_out_shape(H, W, radius, stride, dilation, pad_)
         y = torch.empty((N, Cout, Ho, Wo), dtype=y_dtype, device=x.device)
+        if algo == 3:              # float32 on the tensor cores: three bfloat16 passes over split operands
+            if scale is not None:  # BN-inference affine folded into the weights before the split; b is the shift
+                w = w * scale.detach().float().view(-1, 1, 1, 1)
+            xh, xl = _split_bf16(x)
+            wh, wl = (t.float() for t in _split_bf16(w))
+            st = nv.stream_ptr(x.device)
+            for k, (xa, wa) in enumerate(((xh, wh), (xh, wl), (xl, wh))):
+                dk = _conv_desc(xa, Cout, Ho, Wo, radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, 2,
+                                relu and k == 2, pad_mode, accumulate=int(k > 0))
+                nv.call("hg_hexconv_fwd", C.byref(dk), nv.ptr(xa), nv.ptr(wa), nv.ptr(b if k == 0 else None), nv.ptr(y), st)
+            if scale is not None:
+                ctx.mark_non_differentiable(y)
+                return y
+            ctx.save_for_backward(xh, xl, wh, wl)
+            ctx.meta = meta
+            ctx.has_bias = bias is not None
+            ctx.param_dtypes = (kernel.dtype, bias.dtype if bias is not None else None)
+            ctx.out_shape = (Ho, Wo)
+            ctx.x_shape = tuple(x.shape)
+            ctx.sinks = (getattr(kernel, "_hg_grad_sink", None), getattr(bias, "_hg_grad_sink", None) if bias is not None else None)
+            return y
         d = _conv_desc(x, Cout, Ho, Wo, radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, relu, pad_mode)
         if scale is not None:      # inference-only fused per-channel affine (HexConvModule conv -> BN(eval) -> ReLU); b is the shift
             sc = scale.detach().float().contiguous()
@@ -142,6 +195,8 @@ class _HexConvFn(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
+        if ctx.meta[8] == 3:
+            return _HexConvFn._backward_x3(ctx, gy)
         x, w = ctx.saved_tensors
         radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, relu, pad_mode = ctx.meta
         if relu:
@@ -200,6 +255,65 @@ class _HexConvFn(torch.autograd.Function):
             elif gb is not None:
                 gb = gb.to(ctx.param_dtypes[1])
         return gx, gw, gb, None, None
+
+
+def _backward_x3(ctx, gy):
+    """Backward of the split float32 route: data gradient = three accumulating tcgen05 passes over (gy_hi, gy_lo) x (w_hi, w_lo),
+    weight gradient = three accumulating passes over (x_hi, x_lo) x (gy_hi, gy_lo); the bias gradient sums gy_hi + gy_lo."""
+    xh, xl, wh, wl = ctx.saved_tensors
+    radius, stride, dilation, groups, pad_, parity, pad_value, y_dtype, algo, relu, pad_mode = ctx.meta
+    if relu:
+        raise RuntimeError("the fused ReLU epilogue is inference-only")
+    Ho, Wo = ctx.out_shape
+    N, Cin, H, W = ctx.x_shape
+    Cout = wh.shape[0]
+    gh, gl = _split_bf16(_dense_grad(gy, torch.float32))
+    st = nv.stream_ptr(xh.device)
+    bf = torch.bfloat16
+    framed = bool(pad_) and pad_mode != 0
+    gx = gw = gb = None
+    if ctx.needs_input_grad[0]:
+        if framed:      # gradient of the virtually padded input, then the pad kernel's adjoint (see the plain backward)
+            tgt = torch.empty((N, Cin, H + 2 * pad_, W + 2 * pad_), dtype=torch.float32, device=xh.device)
+            geo = (tgt, 0, 0.0, 0)
+        else:
+            tgt = torch.empty((N, Cin, H, W), dtype=torch.float32, device=xh.device)
+            geo = (tgt, pad_, pad_value, pad_mode)
+        for k, (ga, wa) in enumerate(((gh, wh), (gh, wl), (gl, wh))):
+            dk = _conv_desc(geo[0], Cout, Ho, Wo, radius, stride, dilation, groups, geo[1], parity, geo[2], bf, 2, 0, geo[3],
+                            accumulate=int(k > 0))
+            nv.call("hg_hexconv_dgrad", C.byref(dk), nv.ptr(ga), nv.ptr(wa), nv.ptr(tgt), st)
+        if framed:
+            gx = torch.empty((N, Cin, H, W), dtype=torch.float32, device=xh.device)
+            nv.call("hg_pad2d_bwd", nv.ptr(tgt), nv.ptr(gx), N * Cin, H, W, pad_, pad_, pad_, pad_, pad_mode, nv.F32, st)
+        else:
+            gx = tgt
+    if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+        sink_w, sink_b = ctx.sinks
+        if sink_w is None or tuple(sink_w.view.shape) != tuple(wh.shape):
+            sink_w = None
+        if not ctx.has_bias or sink_b is None:
+            sink_b = None
+        gw = sink_w.view if sink_w is not None else torch.zeros(wh.shape, dtype=torch.float32, device=xh.device)
+        if ctx.has_bias:
+            gb = sink_b.view if sink_b is not None else torch.zeros(Cout, dtype=torch.float32, device=xh.device)
+        dw = _conv_desc(xh, Cout, Ho, Wo, radius, stride, dilation, groups, pad_, parity, pad_value, bf, 2, 0, pad_mode)
+        for k, (xa, ga) in enumerate(((xh, gh), (xh, gl), (xl, gh))):
+            nv.call("hg_hexconv_wgrad", C.byref(dw), nv.ptr(xa), nv.ptr(ga), nv.ptr(gw), nv.ptr(gb if k < 2 else None), st)
+        if sink_w is not None:
+            gw = None
+            sink_w.landed()
+        else:
+            gw = gw.to(ctx.param_dtypes[0])
+        if sink_b is not None:
+            gb = None
+            sink_b.landed()
+        elif gb is not None:
+            gb = gb.to(ctx.param_dtypes[1])
+    return gx, gw, gb, None, None
+
+
+_HexConvFn._backward_x3 = staticmethod(_backward_x3)
 
 
 def hexconv2d(x: Tensor, kernel: Tensor, bias: Optional[Tensor] = None, even_odd_offset=0, radius=2, stride=1, padding=0,
@@ -314,6 +428,16 @@ class HexConv2d(nn.Module):
             H, W = input.shape[-2:]
             if (mode == 'reflect' and (pad_ >= H or pad_ >= W)) or (mode == 'circular' and (pad_ > H or pad_ > W)):
                 raise RuntimeError(f"{mode} padding of {pad_} does not fit a {H} x {W} input")
+        if (algo == 0 and _FP32_TENSOR_CORES and input.dtype == torch.float32 and self.out_dtype == torch.float32
+                and self.kernel.dtype == torch.float32 and input.is_cuda and not autocast_tc):
+            try:
+                Ho, Wo = _conv_out_shape(input.shape[2], input.shape[3], self.hexkernel_radius, self.stride, self.dilation, pad_)
+                need_grad = torch.is_grad_enabled() and (input.requires_grad or self.kernel.requires_grad) and affine is None
+                if _x3_eligible(input, self.out_channels, Ho, Wo, self.hexkernel_radius, self.stride, self.dilation, self.groups,
+                                pad_, parity, need_grad):
+                    algo = 3
+            except ValueError:
+                pass
         meta = (self.hexkernel_radius, self.stride, self.dilation, self.groups, pad_, parity,
                 float(value or 0), self.out_dtype, algo, bool(relu), _PAD_MODES[mode])
         if affine is not None:

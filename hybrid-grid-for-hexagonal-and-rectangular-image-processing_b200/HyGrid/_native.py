@@ -35,7 +35,7 @@ class ConvDesc(C.Structure):
                 ("Ho", C.c_int64), ("Wo", C.c_int64),
                 ("radius", C.c_int), ("stride", C.c_int), ("dilation", C.c_int), ("groups", C.c_int),
                 ("pad", C.c_int), ("parity", C.c_int), ("pad_value", C.c_float),
-                ("x_dtype", C.c_int), ("y_dtype", C.c_int), ("algo", C.c_int), ("relu", C.c_int), ("pad_mode", C.c_int)]
+                ("x_dtype", C.c_int), ("y_dtype", C.c_int), ("algo", C.c_int), ("relu", C.c_int), ("pad_mode", C.c_int), ("accumulate", C.c_int)]
 
 
 class TapsSet(C.Structure):
@@ -72,6 +72,7 @@ _SIGS = {
     "hg_hexpool_bwd": [_p, _p, _i, _p, _p, _l, _l, _l, _l, _l, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "hg_hexglobalpool_fwd": [_p, _p, _p, _l, _l, _i, _i, _p],
     "hg_hexglobalpool_bwd": [_p, _p, _p, _p, _l, _l, _i, _i, _p],
+    "hg_split_bf16": [_p, _p, _p, _l, _p],
     "hg_hexconv_out_shape": [_l, _l, _i, _i, _i, _i, C.POINTER(_l), C.POINTER(_l)],
     "hg_hexconv_umma_eligible": [C.POINTER(ConvDesc), _i],
     "hg_hexconv_fwd": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],

@@ -87,6 +87,8 @@ int hg_hexconv_fwd_affine(const hg_conv_desc* d, const void* x, const float* w, 
   if (g.N == 0) return HG_OK;
   bool umma;
   if ((rc = pick_algo(d, OP_FWD, umma))) return rc;
+  HG_REQUIRE(!d->accumulate || (umma && shift == nullptr && scale == nullptr), HG_E_UNSUPPORTED,
+             "accumulate is a tcgen05-path option without bias / scale");
   if (umma) return conv_fwd_umma(d, g, tp, x, w, scale, shift, y, as_stream(stream));
   return conv_fwd_direct(g, tp, x, d->x_dtype, w, scale, shift, y, d->y_dtype, as_stream(stream));
 }
@@ -104,6 +106,7 @@ int hg_hexconv_dgrad(const hg_conv_desc* d, const void* gy, const float* w, void
   if (g.N == 0) return HG_OK;
   bool umma;
   if ((rc = pick_algo(d, OP_DGRAD, umma))) return rc;
+  HG_REQUIRE(!d->accumulate || umma, HG_E_UNSUPPORTED, "accumulate is a tcgen05-path option");
   if (umma) return conv_dgrad_umma(d, g, tp, gy, w, gx, as_stream(stream));
   return conv_dgrad_direct(g, tp, gy, d->y_dtype, w, gx, d->x_dtype, as_stream(stream));
 }

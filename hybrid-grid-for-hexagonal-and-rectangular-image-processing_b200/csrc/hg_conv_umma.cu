@@ -502,12 +502,12 @@ static int dispatch_umma_pass(int in_dt, int out_dt, const void* in, const float
 // output of the previous one in the epilogue (bias in the first pass, ReLU in the last).
 static int dispatch_umma(int in_dt, int out_dt, const void* in, const float* w, const float* scale, const float* bias, void* out, UmmaParams P,
                          cudaStream_t st) {
-  const int total = P.Cred, relu = P.relu, has_bias = P.has_bias;
+  const int total = P.Cred, relu = P.relu, has_bias = P.has_bias, base_acc = P.accumulate;
   P.cred_total = total;
   for (int c0 = 0; c0 < total; c0 += 64) {
     P.c_off = c0;
     P.Cred = total - c0 < 64 ? total - c0 : 64;
-    P.accumulate = c0 > 0;
+    P.accumulate = c0 > 0 || base_acc;
     P.has_bias = has_bias && c0 == 0;
     P.relu = relu && c0 + 64 >= total;
     int rc = dispatch_umma_pass(in_dt, out_dt, in, w, scale, P.has_bias ? bias : nullptr, out, P, st);
@@ -539,6 +539,7 @@ int conv_fwd_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp, 
   P.pad = g.pad; P.pad_value = g.pad_value; P.pad_mode = g.pad ? g.pad_mode : 0;
   P.relu = g.relu; P.has_bias = bias != nullptr; P.transpose_w = 0;
   umma_common(P, g.Ho, g.Wo, g.N);
+  P.accumulate = d->accumulate ? 1 : 0;
   return dispatch_umma(d->x_dtype, d->y_dtype, x, w, scale, bias, y, P, st);
 }
 
@@ -565,6 +566,7 @@ int conv_dgrad_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp
   P.pad = 0; P.pad_value = 0.f; P.pad_mode = 0;
   P.relu = 0; P.has_bias = 0; P.transpose_w = 1;
   umma_common(P, g.H, g.W, g.N);
+  P.accumulate = d->accumulate ? 1 : 0;
   return dispatch_umma(d->y_dtype, d->x_dtype, gy, w, nullptr, nullptr, gx, P, st);
 }
 

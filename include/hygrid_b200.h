@@ -213,7 +213,13 @@ typedef struct hg_conv_desc {
                            ref HexFrames.py:13-21, :121; HexModules.py:185-190).  Modes 1..3 are resolved by the forward and
                            weight-gradient loaders by coordinate remapping -- no padded copy of x exists; hg_hexconv_dgrad
                            takes them on the padded geometry (pad = 0 on an [H+2p, W+2p] gradient) followed by hg_pad2d_bwd. */
+  int accumulate;       /* forward / data gradient on the tcgen05 path only: add to what y / gx already hold (bias must be NULL).
+                           Used by the float32 route that runs three bfloat16 tensor-core passes over split operands. */
 } hg_conv_desc;
+
+/* x = hi + lo with hi = bf16(x), lo = bf16(x - hi): the operand split of the float32 tensor-core route
+ * (y ~ x_hi*w_hi + x_hi*w_lo + x_lo*w_hi, relative error ~2^-16).  hi / lo: bfloat16 [n]; either may be NULL. */
+int hg_split_bf16(const float* x, void* hi, void* lo, int64_t n, hg_stream_t stream);
 
 int hg_hexconv_out_shape(int64_t H, int64_t W, int radius, int stride, int dilation, int pad,
                          int64_t* Ho, int64_t* Wo);

@@ -87,13 +87,15 @@ def conv_entry(name, a):
         if b is not None and b.value:
             out = out + tensor(b, (d.Cout,), nv.F32).view(1, -1, 1, 1)
         assert tuple(out.shape) == (d.N, d.Cout, d.Ho, d.Wo), (tuple(out.shape), d.Ho, d.Wo)
+        if d.accumulate:                       # header: add to what y already holds (tcgen05 path only)
+            out = out + tensor(y, (d.N, d.Cout, d.Ho, d.Wo), d.y_dtype)
         store(y, out.clamp_min(0) if d.relu else out, d.y_dtype)
     elif name == "hg_hexconv_dgrad":          # (the product's backward runs under no_grad: re-enable it for the oracle)
         _, gy, w, gx, _ = a
         xt = torch.zeros(d.N, d.Cin, d.H, d.W, requires_grad=True)
         with torch.enable_grad():
             run(xt, bf(tensor(w, wshape, nv.F32)), None).backward(bf(tensor(gy, (d.N, d.Cout, d.Ho, d.Wo), d.y_dtype)))
-        store(gx, xt.grad, d.x_dtype)
+        store(gx, xt.grad + tensor(gx, (d.N, d.Cin, d.H, d.W), d.x_dtype) if d.accumulate else xt.grad, d.x_dtype)
     else:
         _, x, gy, gw, gb, _ = a
         wt = torch.zeros(wshape, requires_grad=True)
@@ -179,7 +181,7 @@ def umma_eligible(d, op):
     if d.radius != 2 or d.stride != 1 or d.dilation != 1 or d.groups != 1:
         return False
     if op == 2:
-        ok = d.Cin % 16 == 0 and 16 <= d.Cin <= 1024 and d.Cout % 8 == 0 and 8 <= d.Cout <= 1024
+        ok = 1 <= d.Cin <= 1024 and d.Cout % 8 == 0 and 8 <= d.Cout <= 1024        # input channels are rounded up to 16 in-kernel
         return ok and not (d.algo == 0 and (d.x_dtype != nv.BF16 or d.Cin * d.Cout < 1024))
     cred, nout = (d.Cin, d.Cout) if op == 0 else (d.Cout, d.Cin)
     if cred % 16 or not 16 <= cred <= 512 or nout % 16 or not 16 <= nout <= 256 or (op == 1 and d.relu):
@@ -260,6 +262,14 @@ def emulated_call(name, *a):
         fn = O.hex_to_type1 if name.endswith("1") else O.hex_to_type2
         r = np.asarray(fn(s, off, NP[ddt]))
         view(t, r.size, ddt)[:] = r.reshape(-1)
+    elif name == "hg_split_bf16":             # hi = bf16(x), lo = bf16(x - hi)
+        x, hi, lo, n, _ = a
+        xs = torch.from_numpy(view(x, n, nv.F32).copy())
+        h = xs.bfloat16()
+        if hi is not None and getattr(hi, "value", hi):
+            store(hi, h.float(), nv.BF16)
+        if lo is not None and getattr(lo, "value", lo):
+            store(lo, (xs - h.float()), nv.BF16)
     elif name == "hg_host_hex_to_type":       # host writer of the doubled rasters: same encoder, host pointers
         hexp, t, planes, H, W, off, sdt, ddt, rows_mul, _ = a
         s = view(hexp, planes * H * W, sdt).reshape(planes, H, W)

@@ -75,6 +75,19 @@ def bench_cudnn(a, res, flops, hbm, tf):
     print(json.dumps({"check": "cudnn route vs hg_hexconv_fwd (fp32, direct stencil)", "rel_err": agree}), flush=True)
     assert agree < 1e-3, agree
     xg = x.clone().requires_grad_()
+    if not a.cudnn_only or True:
+        # the CUDA-core direct stencil the float32 route replaced (round 1's float32 path), for the record
+        hf.set_fp32_tensor_cores(False)
+        md = hf.HexConv2d(Ci, Co, 0, 2, padding=1).cuda()
+
+        def direct_fwd_bwd():
+            md.kernel.grad = md.bias.grad = xg.grad = None
+            y = md(xg)
+            y.backward(torch.ones_like(y))
+        ms_d = timeit(direct_fwd_bwd, 2)
+        hf.set_fp32_tensor_cores(True)
+        print(json.dumps({"op": "fwd+bwd", "mode": "f32", "ours_direct_stencil_ms": round(ms_d, 3)}), flush=True)
+        del md
     for label, ac in (("f32", False), ("autocast-bf16", True)):
         def fwd():
             with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=ac):
@@ -103,7 +116,7 @@ def bench_cudnn(a, res, flops, hbm, tf):
                    "ratio_cudnn_over_ours": round(ms_ref / ms_ours, 2),
                    "cudnn_route_tflops": round(passes * flops / ms_ref / 1e9, 1), "ours_tflops": round(passes * flops / ms_ours / 1e9, 1),
                    "note": "reference route = F.pad + type1 materialisation + 2 x F.conv2d (cuDNN) + interleave; ours = HexConv2d module"
-                           + (" (tcgen05 kernels)" if ac else " (CUDA-core direct stencil: fp32 callers keep fp32 accuracy)")}
+                           + (" (tcgen05 kernels)" if ac else " (tcgen05, three bfloat16 passes over split operands: float32-class accuracy)")}
             res["rows"].append(row)
             print(json.dumps(row), flush=True)
 
