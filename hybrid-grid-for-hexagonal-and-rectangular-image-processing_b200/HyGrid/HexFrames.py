@@ -114,15 +114,23 @@ def _split_bf16(t: Tensor):
     return hi, lo
 
 
+_eligible_cache = {}
+
+
 def _x3_eligible(x, Cout, Ho, Wo, radius, stride, dilation, groups, pad_, parity, need_grad):
     """Do the tcgen05 kernels cover all the passes of the split route (forward; data and weight gradient when training)?"""
-    d = _conv_desc(x, Cout, Ho, Wo, radius, stride, dilation, groups, pad_, parity, 0.0, torch.float32, 2, 0, x_dtype=torch.bfloat16)
     if x.shape[1] * Cout < 1024:
         return False
-    ops = (0, 1, 2) if need_grad else (0,)
-    return all(nv.query("hg_hexconv_umma_eligible", C.byref(d), op) for op in ops)
+    key = ("x3", tuple(x.shape), Cout, radius, stride, dilation, groups, pad_, parity, bool(need_grad), x.device.index)
+    hit = _eligible_cache.get(key)
+    if hit is None:
+        d = _conv_desc(x, Cout, Ho, Wo, radius, stride, dilation, groups, pad_, parity, 0.0, torch.float32, 2, 0, x_dtype=torch.bfloat16)
+        ops = (0, 1, 2) if need_grad else (0,)
+        hit = _eligible_cache[key] = all(nv.query("hg_hexconv_umma_eligible", C.byref(d), op) for op in ops)
+    return hit
 
 
+@functools.lru_cache(maxsize=512)
 def _conv_out_shape(H, W, radius, stride, dilation, pad_):
     Ho, Wo = C.c_int64(0), C.c_int64(0)
     try:
@@ -389,13 +397,19 @@ class HexConv2d(nn.Module):
         if x.dtype not in (torch.float32, torch.bfloat16) or x.dim() != 4:
             return False
         pad_ = self.pad if pad_ is None else pad_
-        try:
-            Ho, Wo = _conv_out_shape(x.shape[2], x.shape[3], self.hexkernel_radius, self.stride, self.dilation, pad_)
-        except ValueError:
-            return False
-        d = _conv_desc(x, self.out_channels, Ho, Wo, self.hexkernel_radius, self.stride, self.dilation, self.groups,
-                       pad_, self.padded_even_odd_offset, 0.0, self.out_dtype, 2, 0)
-        return bool(nv.query("hg_hexconv_umma_eligible", C.byref(d), 0))
+        key = ("tc", tuple(x.shape), x.dtype, self.out_channels, self.hexkernel_radius, self.stride, self.dilation, self.groups, pad_,
+               self.padded_even_odd_offset, self.out_dtype, x.device.index)
+        hit = _eligible_cache.get(key)
+        if hit is None:
+            try:
+                Ho, Wo = _conv_out_shape(x.shape[2], x.shape[3], self.hexkernel_radius, self.stride, self.dilation, pad_)
+                d = _conv_desc(x, self.out_channels, Ho, Wo, self.hexkernel_radius, self.stride, self.dilation, self.groups,
+                               pad_, self.padded_even_odd_offset, 0.0, self.out_dtype, 2, 0)
+                hit = bool(nv.query("hg_hexconv_umma_eligible", C.byref(d), 0))
+            except ValueError:
+                hit = False
+            _eligible_cache[key] = hit
+        return hit
 
     def _activation(self, input: Tensor, pad_=None):
         """(input in the dtype the kernels read, whether autocast routes this call to the tcgen05 kernel)."""

@@ -120,24 +120,35 @@ def lib():
     return _lib
 
 
+_fn_cache = {}
+
+
+def _fn(name):
+    """Bound ctypes function by name (the attribute lookup on a CDLL is the slow part of a call)."""
+    f = _fn_cache.get(name)
+    if f is None:
+        f = _fn_cache[name] = getattr(lib(), name)
+    return f
+
+
 def query(name, *args) -> int:
     """Call an entry point whose return value is an answer, not a status."""
-    return int(getattr(lib(), name)(*args))
+    return int(_fn(name)(*args))
 
 
 def call(name, *args):
     """Run one entry point; a non-zero status becomes an exception carrying hg_last_error().
     When the stream argument (always last) belongs to another device than the current one, the call is made with
     that device current, so tensors on ``cuda:1`` work from a process whose current device is ``cuda:0``."""
-    L = lib()
+    f = _fn(name)
     st = args[-1] if args else None
     if isinstance(st, StreamArg) and st.device_index != torch.cuda.current_device():
         with torch.cuda.device(st.device_index):
-            rc = getattr(L, name)(*args)
+            rc = f(*args)
     else:
-        rc = getattr(L, name)(*args)
+        rc = f(*args)
     if rc != 0:
-        raise HyGridNativeError(f"{name} failed with code {rc}: {L.hg_last_error().decode()}")
+        raise HyGridNativeError(f"{name} failed with code {rc}: {lib().hg_last_error().decode()}")
 
 
 def last_launch() -> str:
@@ -178,10 +189,23 @@ class StreamArg(C.c_void_p):
     device_index = -1
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr(device=None):
-    s = torch.cuda.current_stream(device)
-    arg = StreamArg(s.cuda_stream)
-    arg.device_index = int(s.device_index)
+    """cudaStream_t of torch's current stream on ``device`` (the raw handle, without building a Stream object: these
+    wrappers sit on a host-bound path -- a C5 training step is ~130 launches in 2 ms)."""
+    if device is None:
+        idx = torch.cuda.current_device()
+    else:
+        idx = device.index if isinstance(device, torch.device) else torch.device(device).index
+        if idx is None:
+            idx = torch.cuda.current_device()
+    if _raw_stream is not None:
+        arg = StreamArg(_raw_stream(idx))
+    else:  # pragma: no cover - older torch
+        arg = StreamArg(torch.cuda.current_stream(idx).cuda_stream)
+    arg.device_index = int(idx)
     return arg
 
 

@@ -266,8 +266,17 @@ int try_hexsrc_linear_tma(const void* src, void* dst, const double* xs, const do
   const cuuint64_t gstr[2] = {(cuuint64_t)w * 4, (cuuint64_t)w * h * 4};
   const cuuint32_t box[3] = {(cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)kHsG};
   const cuuint32_t estr[3] = {1, 1, 1};
+  // L2 promotion of the box rows (HG_HEXSRC_L2PROMO: 0 none, 1 64 B, 2 128 B, 3 256 B).  The exact variant at 64 shared plane
+  // groups reads 10.0 GB for 6.4 GB of source (ncu, profiles/r3c_hexsrc_exact_R64_ncu_full.txt); the promotion width was the
+  // suspect -- a 544-byte box row touches 5-6 128-byte lines -- but the sweep says it is not: 0.62-0.69 of the HBM copy rate for
+  // every setting, float32 variants 0.81-0.84 (profiles/r3o_sweep_h2r_l2promo.jsonl).  128 B stays.
+  const char* e_promo = getenv("HG_HEXSRC_L2PROMO");
+  const int promo_sel = e_promo ? atoi(e_promo) : 2;
+  const CUtensorMapL2promotion promo = promo_sel == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                       : promo_sel == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                       : promo_sel == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
   if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(src), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+          CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return 1;
   const int stage_bytes = (int)ceil_div((int64_t)kHsG * BW * BH * 4, 128) * 128;
   const int smem = kHsStages * stage_bytes + 64 + 2 * (int)sizeof(HsTables);

@@ -100,6 +100,10 @@ def main():
                     rec(cfg, "h2r fast", {"HG_HEXSRC_SHARE": R, "HG_HEXSRC_WARPS": warps}, hf_, 8 * n)
                 for R in (8, 16, 32, 64):
                     rec(cfg, "h2r exact f32", {"HG_HEXSRC_SHARE": R, "HG_HEXSRC_WARPS": warps}, he_, 8 * n)
+            for promo in (0, 1, 2, 3):
+                rec(cfg, "h2r exact f32, L2 promotion", {"HG_HEXSRC_SHARE": 64, "HG_HEXSRC_L2PROMO": promo}, he_, 8 * n)
+                rec(cfg, "h2r exact f32, L2 promotion", {"HG_HEXSRC_SHARE": 16, "HG_HEXSRC_L2PROMO": promo}, he_, 8 * n)
+                rec(cfg, "h2r fast, L2 promotion", {"HG_HEXSRC_L2PROMO": promo}, hf_, 8 * n)
             rec(cfg, "h2r fast (shipped heuristic)", {}, hf_, 8 * n)
             rec(cfg, "h2r exact f32 (shipped heuristic)", {}, he_, 8 * n)
         del x, y
