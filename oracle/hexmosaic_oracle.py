@@ -2,9 +2,13 @@
 
 TEST INFRASTRUCTURE ONLY (see the header of ``hygrid_oracle.py`` for who may import this).
 
-**Parity unpinned.**  The reference's implementation of this step is a GLSL fragment shader
+**Pin.**  The reference's implementation of this step is a GLSL fragment shader
 (HyGrid/HexPixelArt/hexagon_mosaic_shader.py:25-81) that only runs inside an OpenGL context; the build container has
-no OpenGL / GLFW, so no output of the reference itself could be recorded.  What follows restates the shader statement
+no OpenGL / GLFW.  The shader's own source text was therefore executed on the CPU: tests/golden/make_mosaic_golden.py cuts it
+out of the reference file, tests/golden/glsl_mini.py translates it statement by statement (binary32 floats, truncating
+integer division / conversion, implicit int -> float) and the texel coordinates it produces are committed as
+tests/golden/mosaic_golden.npz; tests/test_zz_hex_mosaic.py checks this restatement against them fragment by fragment.
+The GL pipeline around the shader (texture filtering, mip-mapping) stays unpinned.  What follows restates the shader statement
 by statement in float32 (GLSL ``float``), with ``int()`` as truncation and ``/`` on ints as C division; texture
 filtering is reduced to what it evaluates to at a texel centre (the texel itself; black outside,
 ``GL_CLAMP_TO_BORDER``, texture.py:47-48).  Mip-mapped minification (texture.py:50) is not modelled.

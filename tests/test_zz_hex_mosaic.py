@@ -1,8 +1,12 @@
 """Hex-mosaic preview rasteriser (``HyGrid.HexPixelArt.hexagon_mosaic``).
 
-Parity is UNPINNED for this row: the reference is a GLSL fragment shader that cannot run without OpenGL.  The checker
-is ``oracle/hexmosaic_oracle.py`` (the shader restated per fragment).  CPU: the product's vectorised host table equals
-the per-fragment oracle cell by cell, plus geometric properties of the rule.  GPU: the gather through the C ABI equals
+The reference is a GLSL fragment shader that cannot run without OpenGL (absent here).  Pin: ``tests/golden/make_mosaic_golden.py``
+cut the shader SOURCE TEXT out of the reference file, translated it statement by statement (``tests/golden/glsl_mini.py``:
+binary32 floats, truncating int division / conversion, implicit int -> float) and executed it for every fragment of six
+rasters; ``test_oracle_and_host_table_match_the_reference_shader_text`` holds the oracle (``oracle/hexmosaic_oracle.py``, the
+shader restated by hand) and the product's vectorised host table to those texel coordinates.  What stays unpinned is the GL
+pipeline around the shader (texture filtering / mip-mapping, texture.py:47-50).  CPU: additionally the product's host table
+against the per-fragment oracle cell by cell, plus geometric properties of the rule.  GPU: the gather through the C ABI equals
 the oracle raster exactly (pure index shuffle)."""
 import numpy as np
 import pytest
@@ -25,6 +29,26 @@ def _oracle_table(H, W, oh, ow, eo, hier):
             if 0 <= r < H and 0 <= c < W:
                 tab[py, px] = r * W + c
     return tab
+
+
+def test_oracle_and_host_table_match_the_reference_shader_text():
+    import os
+    from HyGrid.HexPixelArt import mosaic_table
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mosaic_golden.npz"))
+    assert int(G["count"]) >= 6 and "even_odd_offset" in str(G["translated_source"])
+    for n in range(int(G["count"])):
+        th, tw, oh, ow, eo, hier = (int(v) for v in G[f"{n}_cfg"])
+        sx, sy = G[f"{n}_sx"], G[f"{n}_sy"]                       # texel coordinate handed to texture2D: a texel centre
+        assert np.array_equal(sx - np.floor(sx), np.full_like(sx, 0.5)) and np.array_equal(sy - np.floor(sy), np.full_like(sy, 0.5))
+        col, row = np.floor(sx).astype(np.int64), np.floor(sy).astype(np.int64)
+        for py in range(oh):
+            v = (np.float32(py) + np.float32(0.5)) / np.float32(oh)
+            for px in range(ow):
+                u = (np.float32(px) + np.float32(0.5)) / np.float32(ow)
+                assert MO.fragment_cell(u, v, tw, th, eo, 2.0 ** (-hier)) == (row[py, px], col[py, px]), (n, py, px)
+        inside = (row >= 0) & (row < th) & (col >= 0) & (col < tw)
+        want = np.where(inside, row * tw + col, -1)
+        assert np.array_equal(mosaic_table(th, tw, oh, ow, eo, hier), want), n
 
 
 def test_host_table_equals_the_per_fragment_oracle():
