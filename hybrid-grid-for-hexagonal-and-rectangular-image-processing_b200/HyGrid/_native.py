@@ -73,6 +73,7 @@ _SIGS = {
     "hg_hexglobalpool_fwd": [_p, _p, _p, _l, _l, _i, _i, _p],
     "hg_hexglobalpool_bwd": [_p, _p, _p, _p, _l, _l, _i, _i, _p],
     "hg_split_bf16": [_p, _p, _p, _l, _p],
+    "hg_broadcast_fill": [_p, _p, _l, _i, _p],
     "hg_hexconv_out_shape": [_l, _l, _i, _i, _i, _i, C.POINTER(_l), C.POINTER(_l)],
     "hg_hexconv_umma_eligible": [C.POINTER(ConvDesc), _i],
     "hg_hexconv_fwd": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],

@@ -317,11 +317,39 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
   }
 }
 
+// dst[0..n) = *scalar (both in device memory): 16-byte streaming stores
+template <typename T>
+__global__ void __launch_bounds__(256) broadcast_fill_kernel(T* __restrict__ dst, const T* __restrict__ scalar, int64_t n) {
+  constexpr int V = 16 / (int)sizeof(T);
+  const T v = *scalar;
+  union { uint4 q; T e[V]; } pack;
+#pragma unroll
+  for (int k = 0; k < V; ++k) pack.e[k] = v;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * V;
+  for (int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V; e < n; e += stride) {
+    if (e + V <= n) __stcs(reinterpret_cast<uint4*>(dst + e), pack.q);
+    else for (int64_t k = e; k < n; ++k) dst[k] = v;
+  }
+}
+
 }  // namespace hg
 
 using namespace hg;
 
 extern "C" {
+
+int hg_broadcast_fill(void* dst, const void* scalar, int64_t n, int dtype, hg_stream_t stream) {
+  HG_REQUIRE(n >= 0, HG_E_SHAPE, "bad length");
+  if (n == 0) return HG_OK;
+  HG_REQUIRE(dst && scalar && (reinterpret_cast<uintptr_t>(dst) & 15) == 0, HG_E_ARG, "NULL or unaligned buffer");
+  int64_t blocks = ceil_div(n, 256 * 8);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  cudaStream_t st = as_stream(stream);
+  if (dtype == HG_F32) broadcast_fill_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((float*)dst, (const float*)scalar, n);
+  else if (dtype == HG_BF16) broadcast_fill_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((__nv_bfloat16*)dst, (const __nv_bfloat16*)scalar, n);
+  else { set_error("broadcast_fill: float32 or bfloat16"); return HG_E_DTYPE; }
+  return finish_launch("broadcast_fill");
+}
 
 int hg_split_bf16(const float* x, void* hi, void* lo, int64_t n, hg_stream_t stream) {
   HG_REQUIRE(n >= 0, HG_E_SHAPE, "bad length");

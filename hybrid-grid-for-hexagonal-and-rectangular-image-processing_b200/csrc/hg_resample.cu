@@ -445,6 +445,9 @@ static int check_plane(int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t
   return HG_OK;
 }
 
+// hg_resample_stream.cu: same contract; float32 weights between lattices of the same pitch
+int try_hexsrc_linear_stream(const void* src, void* dst, const double* xs, const double* ys, const double* host_xs, const double* host_ys,
+                             int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1, int sdt, int ddt, int math, cudaStream_t st);
 // hg_hexsrc_tma.cu: same contract
 int try_hexsrc_linear_tma(const void* src, void* dst, const double* xs, const double* ys, const double* host_xs, const double* host_ys,
                           int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1, int sdt, int ddt, int math, cudaStream_t st);
@@ -659,6 +662,8 @@ int hg_hex2rect_linear(const void* src, void* dst, const double* xs, const doubl
   if (rc) return rc;
   HG_REQUIRE(math == HG_MATH_EXACT || math == HG_MATH_FAST, HG_E_ARG, "bad math mode %d", math);
   if (planes == 0 || h1 == 0 || w1 == 0) return HG_OK;
+  rc = try_hexsrc_linear_stream(src, dst, xs, ys, host_xs, host_ys, planes, h, w, h1, w1, src_dtype, dst_dtype, math, as_stream(stream));
+  if (rc != 1) return rc;
   rc = try_hexsrc_linear_tma(src, dst, xs, ys, host_xs, host_ys, planes, h, w, h1, w1, src_dtype, dst_dtype, math, as_stream(stream));
   if (rc != 1) return rc;
   CoordTables c{xs, ys};

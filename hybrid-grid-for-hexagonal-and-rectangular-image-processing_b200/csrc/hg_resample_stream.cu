@@ -346,6 +346,161 @@ rect2hex_stream_fast_kernel(const float* __restrict__ src, TD* __restrict__ dst,
   }
 }
 
+// ---- hex -> rect / hexresize between lattices of the same pitch, float32 weights -------------------------------------------
+// ref: geometry_np.py:276-354 (hex_to_rect_resample), :520-681 (hexresize), geometry_torch.py:278-356.
+// Same choreography as the kernel above (four adjacent columns per lane, one 16-byte load per source row, neighbours by
+// shuffle, batched loads, 16-byte streaming stores); what differs is the per-sample geometry, which is not separable:
+//   i_ = x_a + (h-1)/2,  j_ = 0.5*i_ + y_b + (w-0.5)/2,  cell (i_n, j_n) = trunc, (u, v) = fractions, triangle u > v,
+//   lattice points P1 (i_n, j_n - (i_n+1)/2), P2 (i_n+1, j_n - (i_n+2)/2) | P3 (i_n, . + 1), P4 (i_n+1, . + 1).
+// For same-pitch lattices y_b + (w-0.5)/2 = b + s_b with s_b in [0, 0.5] (hex->rect: 0.25; hexresize: 0 .. 0.5; checked on the
+// host), so  j_ - b = (i_n >> 1) + t,  t = 0.5*(i_n & 1) + 0.5*u + s_b in [0, 1.5):  j_n = b + (i_n >> 1) + floor(t), v = t - floor(t)
+// -- small quantities, evaluated in float32 per sample (|error| ~ 1e-7: the interpolant is continuous across cell and triangle
+// borders, so a sample that lands 1e-7 on the other side of one changes the result by ~1e-7 of the range; HG_MATH_FAST is
+// toleranced at 1e-5).  All taps then lie in source columns b-1 .. b+1 of rows i_n, i_n+1: the lane's six-column window.
+template <int kSfB, int MINB>
+__global__ void __launch_bounds__(kStWarps * 32, MINB)
+hexsrc_stream_fast_kernel(const float* __restrict__ src, float* __restrict__ dst, const double* __restrict__ xs,
+                          const double* __restrict__ ys, int h, int w, int h1, int w1, int bands, int xgroups, double ci, double cj) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long blk = blockIdx.x;
+  const int xg = (int)(blk % xgroups); blk /= xgroups;
+  const int band = (int)(blk % bands);
+  const long long plane = blk / bands;
+  __shared__ int s_pa[kSfBand + 1];                        // i_n of the band's output rows (+ sentinel)
+  __shared__ float s_u[kSfBand + 1];                       // i_f
+  const int a0 = band * kSfBand, a1 = min(a0 + kSfBand, h1);
+  if (threadIdx.x <= kSfBand) {
+    int p = 1 << 30; float uf = 0.f;
+    if (a0 + (int)threadIdx.x < a1) {
+      const double i_ = dadd(xs[a0 + threadIdx.x], ci);    // geometry_np.py:276
+      p = trunc_i32(i_);
+      uf = (float)dsub(i_, (double)(float)p);              // :284
+    }
+    s_pa[threadIdx.x] = p;
+    s_u[threadIdx.x] = uf;
+  }
+  __syncthreads();
+  const int c0 = (xg * kStWarps + warp) * kStW;
+  if (c0 >= w1) return;
+  const int b0 = c0 + 4 * lane;
+  const bool store_ok = b0 < w1, load_ok = b0 < w;
+  const bool edge = (lane == 0 && c0 > 0) || (lane == 31 && c0 + kStW < w);
+  const int edge_off = (lane == 0 ? -1 : kStW) - 4 * lane;
+
+  float sb[4];                                             // s_b = (y_b + (w-0.5)/2) - b
+#pragma unroll
+  for (int c = 0; c < 4; ++c) sb[c] = store_ok ? (float)dsub(dadd(ys[b0 + c], cj), (double)(b0 + c)) : 0.25f;
+
+  const int r_first = s_pa[0], r_last = s_pa[a1 - 1 - a0] + 1;
+  const int vlo = max(r_first, 0), vspan = min(r_last, h - 1) - vlo;
+  const float* __restrict__ rp = src + plane * (long long)h * w + (long long)r_first * w + b0;
+  int rl = r_first;
+  float* __restrict__ dp = dst + plane * (long long)h1 * w1 + (long long)a0 * w1 + b0;
+  auto load_next = [&]() {
+    SrcRow q;
+    q.v = make_float4(0.f, 0.f, 0.f, 0.f);
+    q.e = 0.f;
+    if ((unsigned)(rl - vlo) <= (unsigned)vspan && vspan >= 0) {
+      if (load_ok) q.v = __ldg(reinterpret_cast<const float4*>(rp));
+      if (edge) q.e = __ldg(rp + edge_off);
+    }
+    rp += w; ++rl;
+    return q;
+  };
+
+  float top[6], bot[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) top[c] = bot[c] = 0.f;
+  SrcRow cur[kSfB], nxt[kSfB];
+#pragma unroll
+  for (int k = 0; k < kSfB; ++k) cur[k] = load_next();
+  int ka = 0;
+  int in = s_pa[0], want = in + 1;
+  float ua = s_u[0];
+  for (int r = r_first; r <= r_last; r += kSfB) {
+#pragma unroll
+    for (int k = 0; k < kSfB; ++k) nxt[k] = load_next();
+#pragma unroll
+    for (int k = 0; k < kSfB; ++k) {
+      float prev = __shfl_up_sync(0xffffffffu, cur[k].v.w, 1);
+      float next = __shfl_down_sync(0xffffffffu, cur[k].v.x, 1);
+      if (lane == 0) prev = cur[k].e;
+      if (lane == 31) next = cur[k].e;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) top[c] = bot[c];
+      bot[0] = prev; bot[1] = cur[k].v.x; bot[2] = cur[k].v.y; bot[3] = cur[k].v.z; bot[4] = cur[k].v.w; bot[5] = next;
+      while (want == r + k) {                              // output rows whose lower lattice row is this source row
+        // per row: m = i_n >> 1, column offsets of P1 / P4 relative to b before the floor(t) term
+        const int m = in >> 1;
+        const int rowA = m - ((in + 1) >> 1);              // 0 (i_n even) or -1 (odd)
+        const int rowC = m + 1 - ((in + 2) >> 1);          // 0 in both cases
+        const float crow = 0.5f * (float)(in & 1) + 0.5f * ua;
+        float o[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float t = crow + sb[c];
+          const bool up = t >= 1.f;                        // floor(t) in {0, 1}
+          const float v = up ? t - 1.f : t;
+          const bool f = ua > v;                           // :298 up_down_flag
+          const bool a_m1 = (rowA + (up ? 1 : 0)) < 0;     // P1 column offset -1 (else 0)
+          const bool c_p1 = (rowC + (up ? 1 : 0)) > 0;     // P4 column offset +1 (else 0)
+          const float p1 = a_m1 ? top[c] : top[c + 1];
+          const float p3 = a_m1 ? top[c + 1] : top[c + 2];
+          const float p4 = c_p1 ? bot[c + 2] : bot[c + 1];
+          const float p2 = c_p1 ? bot[c + 1] : bot[c];
+          const float wa = f ? 1.f - ua : 1.f - v, wb = f ? ua - v : v - ua, wc = f ? v : ua;
+          o[c] = fmaf(wc, p4, fmaf(wb, f ? p2 : p3, wa * p1));
+        }
+        if (store_ok) __stcs(reinterpret_cast<float4*>(dp), make_float4(o[0], o[1], o[2], o[3]));
+        dp += w1;
+        ++ka;
+        in = s_pa[ka];
+        want = in + 1;
+        ua = s_u[ka];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kSfB; ++k) cur[k] = nxt[k];
+  }
+}
+
+// HG_OK launched, 1 not applicable, else error
+int try_hexsrc_linear_stream(const void* src, void* dst, const double* xs, const double* ys, const double* host_xs,
+                             const double* host_ys, int64_t planes, int64_t h, int64_t w, int64_t h1, int64_t w1, int sdt, int ddt,
+                             int math, cudaStream_t st) {
+  const char* e_on = getenv("HG_H2R_STREAM");
+  const char* e_pf = getenv("HG_H2R_STREAM_PF");
+  if ((e_on ? atoi(e_on) : 1) == 0 || !host_xs || !host_ys || sdt != HG_F32 || ddt != HG_F32 || math != HG_MATH_FAST) return 1;
+  if (w % 4 != 0 || w1 % 4 != 0 || h1 < 1 || w1 < 1) return 1;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) != 0 || (reinterpret_cast<uintptr_t>(dst) & 15) != 0) return 1;
+  if (h >= (1 << 30) || w >= (1 << 30) || h1 >= (1 << 30) || w1 >= (1 << 30)) return 1;
+  const double ci = (h - 1) * 0.5, cj = (w - 0.5) * 0.5;
+  for (int64_t b = 0; b < w1; ++b) {
+    const double sbv = (host_ys[b] + cj) - (double)b;
+    if (!(sbv >= 0.0 && sbv <= 0.5)) return 1;
+  }
+  int prev = -1;
+  for (int64_t a = 0; a < h1; ++a) {
+    const double i_ = host_xs[a] + ci;
+    if (!(i_ >= 0.0)) return 1;
+    const int cur = (int)i_;
+    if (a > 0 && (cur - prev < 0 || cur - prev > 2)) return 1;
+    prev = cur;
+  }
+  const int64_t bands = ceil_div(h1, kSfBand), xgroups = ceil_div(w1, (int64_t)kStW * kStWarps);
+  const int64_t blocks = planes * bands * xgroups;
+  if (blocks <= 0 || blocks >= (1ll << 31)) return 1;
+  const int vb = e_pf ? atoi(e_pf) : 4;
+#define HG_HS(B, MINB)                                                                                                            \
+  hexsrc_stream_fast_kernel<B, MINB><<<(unsigned)blocks, kStWarps * 32, 0, st>>>((const float*)src, (float*)dst, xs, ys, (int)h, (int)w, \
+                                                                                 (int)h1, (int)w1, (int)bands, (int)xgroups, ci, cj)
+  if (vb <= 2) HG_HS(2, 3);
+  else if (vb <= 4) HG_HS(4, 3);
+  else HG_HS(6, 2);
+#undef HG_HS
+  return finish_launch("hexsrc_linear_stream");
+}
+
 static inline int host_axis_index_s(double coord, int64_t n) {
   const double c = coord + (double)(n - 1) * 0.5;
   return (int)c;  // truncation toward zero, like the device path

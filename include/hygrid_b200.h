@@ -217,6 +217,9 @@ typedef struct hg_conv_desc {
                            Used by the float32 route that runs three bfloat16 tensor-core passes over split operands. */
 } hg_conv_desc;
 
+/* dst[0..n) = *scalar, both in device memory, dtype HG_F32 or HG_BF16 (dst 16-byte aligned): materialises the broadcast
+ * gradient a `sum()` loss hands to the conv backward (torch's strided broadcast copy runs at a third of the HBM rate). */
+int hg_broadcast_fill(void* dst, const void* scalar, int64_t n, int dtype, hg_stream_t stream);
 /* x = hi + lo with hi = bf16(x), lo = bf16(x - hi): the operand split of the float32 tensor-core route
  * (y ~ x_hi*w_hi + x_hi*w_lo + x_lo*w_hi, relative error ~2^-16).  hi / lo: bfloat16 [n]; either may be NULL. */
 int hg_split_bf16(const float* x, void* hi, void* lo, int64_t n, hg_stream_t stream);

@@ -262,6 +262,9 @@ def emulated_call(name, *a):
         fn = O.hex_to_type1 if name.endswith("1") else O.hex_to_type2
         r = np.asarray(fn(s, off, NP[ddt]))
         view(t, r.size, ddt)[:] = r.reshape(-1)
+    elif name == "hg_broadcast_fill":
+        dst, scalar, n, dt, _ = a
+        store(dst, tensor(scalar, (1,), dt).expand(n), dt)
     elif name == "hg_split_bf16":             # hi = bf16(x), lo = bf16(x - hi)
         x, hi, lo, n, _ = a
         xs = torch.from_numpy(view(x, n, nv.F32).copy())

@@ -97,3 +97,54 @@ def test_stream_kernel_handles_non_finite_neighbours():
     assert np.array_equal(np.isnan(e64), np.isnan(ref)) and np.array_equal(np.isinf(e64), np.isinf(ref))
     ok = np.isfinite(ref)
     assert np.array_equal(e64[ok], ref[ok])
+
+
+# ----------------------------------------------------------------------------------------------------
+# hex -> rect / hexresize between lattices of the same pitch (float32 weights)
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(2, 64, 128), (3, 37, 132), (1, 100, 1028), (2, 5, 4), (1, 130, 2052), (3, 257, 260),
+                                   (1, 1030, 1024), (1, 2, 8), (2, 66, 4)])
+def test_hexsrc_stream_kernel_same_size_vs_oracle(shape):
+    """HG_MATH_FAST hex->rect / hexresize with the output the size of the input: the row-streaming kernel evaluates the
+    cell / triangle / weights of every sample in float32 from small quantities (|error| ~ 1e-7, continuous interpolant);
+    the contract is 1e-5 of the range against the float64 oracle."""
+    from HyGrid import _native as nv
+    from HyGrid import functional as Fn
+    rng = np.random.default_rng(sum(shape) + 1)
+    img = (rng.random(shape, dtype=np.float32) * 255).astype(np.float32)
+    x = torch.from_numpy(img).cuda()
+    full = lambda fn: np.stack([np.asarray(fn(img[i:i + 1])).reshape(shape[1:]) for i in range(shape[0])])
+    for twin in ("np", "torch"):
+        ref = full(lambda a: O.hex_to_rect_resample(a, None, "linear", twin=twin))
+        for pf in ("2", "4", "6"):
+            os.environ["HG_H2R_STREAM_PF"] = pf
+            got = Fn.hex_to_rect(x, None, "linear", out_dtype=torch.float32, math="fast", twin=twin)
+            assert nv.last_launch() == "hexsrc_linear_stream", nv.last_launch()
+            assert float(np.abs(got.cpu().numpy() - ref).max()) <= 1e-5 * 255
+        os.environ.pop("HG_H2R_STREAM_PF", None)
+    ref = full(lambda a: O.hexresize(a, shape[1:], "linear"))
+    got = Fn.hex_resize(x, shape[1:], "linear", out_dtype=torch.float32, math="fast")
+    assert nv.last_launch() == "hexsrc_linear_stream" and float(np.abs(got.cpu().numpy() - ref).max()) <= 1e-5 * 255
+    # switched off: the TMA-tiled / direct kernels, same tolerance; exact mode never takes the streaming kernel
+    os.environ["HG_H2R_STREAM"] = "0"
+    try:
+        got = Fn.hex_to_rect(x, None, "linear", out_dtype=torch.float32, math="fast", twin="np")
+        assert nv.last_launch() != "hexsrc_linear_stream"
+        assert float(np.abs(got.cpu().numpy() - full(lambda a: O.hex_to_rect_resample(a, None, "linear", twin="np"))).max()) <= 1e-5 * 255
+    finally:
+        os.environ.pop("HG_H2R_STREAM", None)
+    e64 = Fn.hex_to_rect(x, None, "linear", twin="np")
+    assert nv.last_launch() != "hexsrc_linear_stream"
+    assert np.array_equal(e64.cpu().numpy(), full(lambda a: O.hex_to_rect_resample(a, None, "linear", twin="np")))
+
+
+@pytest.mark.parametrize("case", [((2, 40, 64), (44, 64)), ((1, 64, 128), (128, 256)), ((1, 33, 256), (33, 252)), ((2, 48, 96), (24, 48))])
+def test_hexsrc_other_geometries_decline_and_match(case):
+    from HyGrid import _native as nv
+    from HyGrid import functional as Fn
+    shape, dsize = case
+    rng = np.random.default_rng(11)
+    img = (rng.random(shape, dtype=np.float32) * 255).astype(np.float32)
+    ref = np.stack([np.asarray(O.hex_to_rect_resample(img[i:i + 1], dsize, "linear", twin="np")).reshape(dsize) for i in range(shape[0])])
+    got = Fn.hex_to_rect(torch.from_numpy(img).cuda(), dsize, "linear", out_dtype=torch.float32, math="fast", twin="np")
+    assert float(np.abs(got.cpu().numpy() - ref).max()) <= 1e-5 * 255

@@ -95,15 +95,17 @@ def main():
         if "h2r" in a.what:
             hf_ = lambda: Fn.hex_to_rect(x, None, "linear", out_dtype=torch.float32, math="fast", twin="np", out=y)
             he_ = lambda: Fn.hex_to_rect(x, None, "linear", out_dtype=torch.float32, math="exact", twin="np", out=y)
+            for pf in (2, 4, 6):
+                rec(cfg, "h2r fast: stream (batched loads)", {"HG_H2R_STREAM_PF": pf}, hf_, 8 * n)
             for warps in (8, 16):
                 for R in (1, 2, 4):
-                    rec(cfg, "h2r fast", {"HG_HEXSRC_SHARE": R, "HG_HEXSRC_WARPS": warps}, hf_, 8 * n)
+                    rec(cfg, "h2r fast: TMA tiles", {"HG_H2R_STREAM": 0, "HG_HEXSRC_SHARE": R, "HG_HEXSRC_WARPS": warps}, hf_, 8 * n)
                 for R in (8, 16, 32, 64):
                     rec(cfg, "h2r exact f32", {"HG_HEXSRC_SHARE": R, "HG_HEXSRC_WARPS": warps}, he_, 8 * n)
             for promo in (0, 1, 2, 3):
                 rec(cfg, "h2r exact f32, L2 promotion", {"HG_HEXSRC_SHARE": 64, "HG_HEXSRC_L2PROMO": promo}, he_, 8 * n)
                 rec(cfg, "h2r exact f32, L2 promotion", {"HG_HEXSRC_SHARE": 16, "HG_HEXSRC_L2PROMO": promo}, he_, 8 * n)
-                rec(cfg, "h2r fast, L2 promotion", {"HG_HEXSRC_L2PROMO": promo}, hf_, 8 * n)
+                rec(cfg, "h2r fast: TMA tiles, L2 promotion", {"HG_H2R_STREAM": 0, "HG_HEXSRC_L2PROMO": promo}, hf_, 8 * n)
             rec(cfg, "h2r fast (shipped heuristic)", {}, hf_, 8 * n)
             rec(cfg, "h2r exact f32 (shipped heuristic)", {}, he_, 8 * n)
         del x, y
