@@ -50,18 +50,29 @@ __global__ void __launch_bounds__(NWARPS * 32, 2)    //  the warps per SM for th
 hexsrc_linear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __restrict__ dst, const double* __restrict__ xs,
                          const double* __restrict__ ys, int h, int w, int h1, int w1, int planes, int tiles_x, int tiles_y,
                          long long total_items, long long items_per_cta, int BW, int BH, int stage_bytes, double ci, double cj,
-                         double hx, double wy, int col_major, int R, int groups) {
+                         double hx, double wy, int col_major, int R, int groups, int interleave) {
   using WT = typename std::conditional<EXACT, double, float>::type;
   constexpr int kHsRW = kHsTH / NWARPS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kHsStages * stage_bytes);
   HsTables* tabs = reinterpret_cast<HsTables*>(smem_raw + (size_t)kHsStages * stage_bytes + 64);
 
-  const long long g_begin = (long long)blockIdx.x * items_per_cta;
-  const long long g_end = min(total_items, g_begin + items_per_cta);
+  const int npos = tiles_x * tiles_y;
+  // Two ways to hand work to the persistent CTAs.  Contiguous: CTA b owns a consecutive range of items.  Interleaved: the
+  // units (R plane groups of one tile position) are dealt round-robin, unit = block * npos + position, CTA b takes units
+  // b, b + grid, ... -- at any moment the grid works on `grid` ADJACENT positions of the same plane groups, so the halo
+  // rows / columns two neighbouring tiles share are requested within microseconds of each other and the second request hits
+  // L2.  (Contiguous ranges with R shared plane groups put R * 3 planes * grid tiles = several hundred MB between the two
+  // visits: every halo came from DRAM, 16.4 GB moved for 12.7 GB at R = 64, profiles/r3c_hexsrc_exact_R64_ncu_full.txt;
+  // interleaved: 12.9 GB, profiles/r4b_hexsrc_exact_interleaved_ncu_full.txt.)
+  const int full_blocks_ = groups / R, tail_ = groups - full_blocks_ * R;
+  const long long n_units = (long long)npos * (full_blocks_ + (tail_ ? 1 : 0)), n_full_units = (long long)npos * full_blocks_;
+  auto dealt = [&](long long n) { return n > (long long)blockIdx.x ? (n - blockIdx.x + gridDim.x - 1) / gridDim.x : 0ll; };
+  const long long g_begin = interleave ? 0 : (long long)blockIdx.x * items_per_cta;
+  const long long g_end = interleave ? dealt(n_full_units) * R + (dealt(n_units) - dealt(n_full_units)) * tail_
+                                     : min(total_items, g_begin + items_per_cta);
   if (g_begin >= g_end) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int npos = tiles_x * tiles_y;
   const int plane_elems = BW * BH;
 
   if (threadIdx.x == 0) {
@@ -74,12 +85,23 @@ hexsrc_linear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __restric
   // at once, was measured and rejected: C4 0.73 -> 0.71, C2 0.88 -> 0.69 -- DRAM page locality of consecutive row
   // segments matters more than the halo; HG_HEXSRC_ORDER=1 keeps it for A/B runs.)  A CTA's items are
   // consecutive, so positions advance by carries.
-  struct Pos { int grp, tx, ty, blk, sub; };
+  struct Pos { int grp, tx, ty, blk, sub, pos; long long unit; };
   // Items run in blocks of R plane groups: inside a block the R groups of one tile position are consecutive, so a
   // thread evaluates the (plane independent) geometry of its samples once per position and re-uses it R times.
   const int full_blocks = groups / R, tail = groups - full_blocks * R;
+  auto set_tile = [&](Pos& q) {
+    if (col_major) { q.tx = q.pos / tiles_y; q.ty = q.pos - q.tx * tiles_y; }
+    else { q.ty = q.pos / tiles_x; q.tx = q.pos - q.ty * tiles_x; }
+  };
   auto decode = [&](long long g) {
     Pos q;
+    if (interleave) {                        // only ever called with the CTA's first item
+      q.unit = blockIdx.x;
+      q.blk = (int)(q.unit / npos); q.pos = (int)(q.unit - (long long)q.blk * npos);
+      q.sub = 0; q.grp = q.blk * R;
+      set_tile(q);
+      return q;
+    }
     const long long per_block = (long long)R * npos;
     int rb, pos;
     if (g < (long long)full_blocks * per_block) {
@@ -92,14 +114,21 @@ hexsrc_linear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __restric
       pos = rem / rb; q.sub = rem - pos * rb;
     }
     q.grp = q.blk * R + q.sub;
-    if (col_major) { q.tx = pos / tiles_y; q.ty = pos - q.tx * tiles_y; }
-    else { q.ty = pos / tiles_x; q.tx = pos - q.ty * tiles_x; }
+    q.pos = pos;
+    set_tile(q);
     return q;
   };
   auto advance = [&](Pos& q) {
     const int rb = q.blk < full_blocks ? R : tail;
     if (++q.sub < rb) { ++q.grp; return; }
     q.sub = 0;
+    if (interleave) {
+      q.unit += gridDim.x;
+      q.blk = (int)(q.unit / npos); q.pos = (int)(q.unit - (long long)q.blk * npos);
+      set_tile(q);
+      q.grp = q.blk * R;
+      return;
+    }
     bool wrapped = false;
     if (col_major) { if (++q.ty == tiles_y) { q.ty = 0; if (++q.tx == tiles_x) { q.tx = 0; wrapped = true; } } }
     else if (++q.tx == tiles_x) { q.tx = 0; if (++q.ty == tiles_y) { q.ty = 0; wrapped = true; } }
@@ -195,6 +224,31 @@ hexsrc_linear_tma_kernel(const __grid_constant__ CUtensorMap tmap, TD* __restric
     ptx::mbar_wait(&full[s], parity);
     const float* __restrict__ t = reinterpret_cast<const float*>(smem_raw + (size_t)s * stage_bytes);
     TD* __restrict__ dp = dst + ((size_t)grp * kHsG * h1 + (size_t)(ty * kHsTH + warp * kHsRW)) * w1 + (tx * kHsTW + lane);
+    // Full tiles (all but the right / bottom edge): every load of a plane first, then the blends, then the stores -- straight-line
+    // code the scheduler can interleave.  With the per-sample bounds test around each sample (the edge path below) the
+    // compiler sinks load, conversion and blend into the predicated region and the 24 samples of a plane group run as 24
+    // serial LDS -> F2F -> DMUL -> DADD -> DADD -> F2F -> STG chains (ncu r4b: stall_wait 3.0, short_scoreboard 2.3 per issue).
+    const bool full_tile = nrows == kHsRW && T.ncols == kHsTW;
+    if (full_tile) {
+      for (int p = 0; p < np; ++p, t += plane_elems, dp += (size_t)h1 * w1) {
+        float v1[kHsRW][4], vB[kHsRW][4], v4[kHsRW][4];
+#pragma unroll
+        for (int r = 0; r < kHsRW; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { v1[r][c] = t[o1[r][c]]; vB[r][c] = t[oB[r][c]]; v4[r][c] = t[o4[r][c]]; }
+#pragma unroll
+        for (int r = 0; r < kHsRW; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            TD o;
+            if (EXACT)
+              o = (TD)dadd(dadd(dmul(wa[r][c], (double)v1[r][c]), dmul(wb[r][c], (double)vB[r][c])), dmul(wc[r][c], (double)v4[r][c]));
+            else
+              o = (TD)fmaf((float)wc[r][c], v4[r][c], fmaf((float)wb[r][c], vB[r][c], (float)wa[r][c] * v1[r][c]));
+            st_stream(dp + (size_t)r * w1 + 32 * c, o);
+          }
+      }
+    } else
     for (int p = 0; p < np; ++p, t += plane_elems, dp += (size_t)h1 * w1) {
 #pragma unroll
       for (int r = 0; r < kHsRW; ++r) {
@@ -300,10 +354,14 @@ int try_hexsrc_linear_tma(const void* src, void* dst, const double* xs, const do
   const int tiles_x = (int)ceil_div(w1, kHsTW), tiles_y = (int)ceil_div(h1, kHsTH);
   const long long groups = ceil_div(planes, kHsG);
   const long long total = (long long)tiles_x * tiles_y * groups;
+  const char* e_dist = getenv("HG_HEXSRC_DIST");              // 0 contiguous item ranges per CTA, 1 (default) interleaved tile positions
+  const int interleave = e_dist ? (atoi(e_dist) != 0) : 1;
   long long grid = (long long)g_hs_sms * occ;
   if (grid > total) grid = total;
-  const long long per = (total + grid - 1) / grid;
-  grid = (total + per - 1) / per;
+  long long per = (total + grid - 1) / grid;
+  if (!interleave) {
+    grid = (total + per - 1) / per;
+  }
   const double hx = (h - 1) / 2.0, wy = (w - 0.5) / 2.0;     // python-float expressions of geometry_np.py:326-331
   // A/B switches, read on every call so that one process can sweep them (tools/sweep_kernels.py)
   const char* e_order = getenv("HG_HEXSRC_ORDER");            // 0 row-, 1 column-major tile order
@@ -313,24 +371,28 @@ int try_hexsrc_linear_tma(const void* src, void* dst, const double* xs, const do
   // arithmetic against a longer L2 re-use distance of the tile halos (measured)
   const char* e_share = getenv("HG_HEXSRC_SHARE");
   const int share_env = e_share ? atoi(e_share) : 0;
-  // measured on B200 (C4 / C2, fraction of the HBM copy rate): float32 weights R = 1: 0.70 / 0.88, R = 2: 0.85 / 0.83,
-  // R = 4: 0.75 / 0.75 -- sharing pays when a row of tiles is so long that the halo rows leave L2 anyway (4K images);
-  // float64 weights (exact): R = 1: 0.28, 2: 0.41, 4: 0.52, 8: 0.61 -- bound by the fp64 pipe, so share as much as possible.
+  // Measured on B200 (C4 / C2, fraction of the HBM copy rate; profiles/r3d_, r4a_, r4c_sweep*.jsonl).
+  //  contiguous ranges: float32 weights R = 1 / 2 / 4: 0.84 / 0.81 / 0.77 and 0.85 / 0.82 / 0.78; float64 weights (exact)
+  //    R = 8 / 16 / 64: 0.68 / 0.64 / 0.65 and 0.67 / 0.64 / 0.66 -- every halo re-read from DRAM (16.4 GB moved for 12.7 GB);
+  //  interleaved units:  exact R = 8 / 16 / 64 / 256: 0.72 / 0.78 / 0.75 / 0.77 and 0.65 / 0.73 / 0.74 / 0.72 (12.9 GB moved).
+  // Sharing amortises the ~250 float64 instructions of a sample's geometry; 32 groups are enough once the halos hit L2.
   const long long halo_footprint = (long long)tiles_x * stage_bytes * grid;        // bytes staged between two vertically adjacent tiles
-  // (round 2 sweep, profiles/r3d_sweep_kernels.jsonl: exact R = 8 / 16 / 32 / 64 -> C4 0.59 / 0.64 / 0.65 / 0.65, C2 0.61 / 0.67 / 0.70 / 0.70;
-  //  at R = 64 the kernel moves 16.4 GB of DRAM traffic for 12.7 GB of algorithmic bytes at the same 5.7 TB/s as the float32
-  //  kernels -- every tile halo is re-read from DRAM -- so it is DRAM-bound there, no longer fp64-latency-bound)
-  int R = share_env > 0 ? share_env : (math == HG_MATH_EXACT ? 64 : (halo_footprint > (100ll << 20) ? 2 : 1));
+  int R = share_env > 0 ? share_env
+                        : (math == HG_MATH_EXACT ? (interleave ? 32 : 64) : (interleave ? 1 : (halo_footprint > (100ll << 20) ? 2 : 1)));
   if (R > (int)groups) R = (int)groups;
+  if (interleave) {
+    const long long n_units = (long long)tiles_x * tiles_y * ceil_div(groups, (long long)R);
+    if (grid > n_units) grid = n_units;
+  }
   void* args[] = {(void*)&tmap, (void*)&dst, (void*)&xs, (void*)&ys, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                  nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+                  nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int hi = (int)h, wi = (int)w, h1i = (int)h1, w1i = (int)w1, pi = (int)planes, gi = (int)groups;
   long long total_ = total, per_ = per;
-  int bw_ = BW, bh_ = BH, sb_ = stage_bytes, cm_ = col_major, r_ = R;
+  int bw_ = BW, bh_ = BH, sb_ = stage_bytes, cm_ = col_major, r_ = R, il_ = interleave;
   double ci_ = ci, cj_ = cj, hx_ = hx, wy_ = wy;
   args[4] = &hi; args[5] = &wi; args[6] = &h1i; args[7] = &w1i; args[8] = &pi; args[9] = (void*)&tiles_x; args[10] = (void*)&tiles_y;
   args[11] = &total_; args[12] = &per_; args[13] = &bw_; args[14] = &bh_; args[15] = &sb_; args[16] = &ci_; args[17] = &cj_;
-  args[18] = &hx_; args[19] = &wy_; args[20] = &cm_; args[21] = &r_; args[22] = &gi;
+  args[18] = &hx_; args[19] = &wy_; args[20] = &cm_; args[21] = &r_; args[22] = &gi; args[23] = &il_;
   cudaLaunchKernel(kern, dim3((unsigned)grid), dim3((unsigned)threads), args, (size_t)smem, st);
   return finish_launch("hexsrc_linear_tma");
 }

@@ -336,6 +336,7 @@ hexsrc_linear_fast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, Coor
   }
   const TS* __restrict__ sp = src + p0 * sps;
   TD* __restrict__ dp = dst + p0 * dps + (int64_t)(ty * kFastTileH + warp * kFastRows) * w1 + tx * kTileW + lane;
+  // (two planes per trip -- 48 gathers in flight per thread -- spills: 8 samples x (3 offsets + 3 weights) are 48 registers already)
   for (int p = 0; p < np; ++p, sp += sps, dp += dps) {
 #pragma unroll
     for (int rr = 0; rr < kFastRows; ++rr) {
@@ -491,7 +492,9 @@ template <typename TS, typename TD, typename Coord, bool FAST>
 static int launch_hexsrc_linear(const void* src, void* dst, const Coord& c, int64_t planes, int64_t h, int64_t w,
                                 int64_t h1, int64_t w1, cudaStream_t st) {
   Tiling t;
-  if (FAST) {   // exact mode measured slower with the plane loop outermost (C4: 14.0 ms vs 9.2 ms row-outer, 7.1 ms TMA tiles)
+  // 32-bit weights (HG_MATH_FAST, or the torch twin's float32 coordinates): plane loop outermost.  With float64 weights the
+  // 8 samples of a thread do not fit the register budget (C4: 14.0 ms vs 9.2 ms row-outer, 7.1 ms TMA tiles).
+  if (FAST || std::is_same<typename Coord::CT, float>::value) {
     static const bool rows_outer = [] { const char* e = getenv("HG_HEXSRC_ROWS_OUTER"); return e && e[0] == '1'; }();
     if (!rows_outer) {
       const int pc = plane_chunk(planes, ceil_div(h1, kFastTileH) * ceil_div(w1, kTileW));

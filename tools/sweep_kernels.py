@@ -106,6 +106,25 @@ def main():
                 rec(cfg, "h2r exact f32, L2 promotion", {"HG_HEXSRC_SHARE": 64, "HG_HEXSRC_L2PROMO": promo}, he_, 8 * n)
                 rec(cfg, "h2r exact f32, L2 promotion", {"HG_HEXSRC_SHARE": 16, "HG_HEXSRC_L2PROMO": promo}, he_, 8 * n)
                 rec(cfg, "h2r fast: TMA tiles, L2 promotion", {"HG_H2R_STREAM": 0, "HG_HEXSRC_L2PROMO": promo}, hf_, 8 * n)
+        if "dist" in a.what:          # tile positions: contiguous ranges per CTA (0) against interleaved over the grid (1)
+            hf_ = lambda: Fn.hex_to_rect(x, None, "linear", out_dtype=torch.float32, math="fast", twin="np", out=y)
+            he_ = lambda: Fn.hex_to_rect(x, None, "linear", out_dtype=torch.float32, math="exact", twin="np", out=y)
+            y64 = torch.empty(shp, device="cuda", dtype=torch.float64)
+            he64 = lambda: Fn.hex_to_rect(x, None, "linear", math="exact", twin="np", out=y64)
+            for dist in (0, 1):
+                for R in (8, 16, 32, 64, 256):
+                    rec(cfg, "h2r exact f32", {"HG_HEXSRC_DIST": dist, "HG_HEXSRC_SHARE": R}, he_, 8 * n)
+                rec(cfg, "h2r exact f32, 16 warps", {"HG_HEXSRC_DIST": dist, "HG_HEXSRC_SHARE": 64, "HG_HEXSRC_WARPS": 16}, he_, 8 * n)
+                rec(cfg, "h2r exact f32, column-major", {"HG_HEXSRC_DIST": dist, "HG_HEXSRC_SHARE": 64, "HG_HEXSRC_ORDER": 1}, he_, 8 * n)
+                for R in (16, 64):
+                    rec(cfg, "h2r exact f64", {"HG_HEXSRC_DIST": dist, "HG_HEXSRC_SHARE": R}, he64, 12 * n)
+                for R in (1, 2, 4, 8):
+                    rec(cfg, "h2r fast: TMA tiles", {"HG_H2R_STREAM": 0, "HG_HEXSRC_DIST": dist, "HG_HEXSRC_SHARE": R}, hf_, 8 * n)
+            rec(cfg, "h2r exact f32 (shipped heuristic)", {}, he_, 8 * n)
+            rec(cfg, "h2r exact f64 (shipped heuristic)", {}, he64, 12 * n)
+            rec(cfg, "h2r fast: TMA tiles (shipped heuristic)", {"HG_H2R_STREAM": 0}, hf_, 8 * n)
+            del y64
+        if "h2r" in a.what:
             rec(cfg, "h2r fast (shipped heuristic)", {}, hf_, 8 * n)
             rec(cfg, "h2r exact f32 (shipped heuristic)", {}, he_, 8 * n)
         del x, y
