@@ -544,7 +544,7 @@ def extra_c5(cx):
     for name, kw in (("overlapped (3 layer groups, all-reduce issued from backward)", dict(groups=[3, 3, 5], overlap=True)),
                      ("blocking (one all-reduce after backward)", dict(groups=1, overlap=False))):
         bucket = FlatGradBucket(model.parameters(), **kw)
-        opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9)
+        opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, fused=True)
 
         def step():
             bucket.zero_()
@@ -574,7 +574,7 @@ def extra_c5(cx):
         # step -- forward, backward, the NCCL all-reduce of the flat bucket, SGD -- as one captured CUDA graph.
         try:
             bucket = FlatGradBucket(model.parameters(), groups=1, overlap=False)
-            opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9)
+            opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, fused=True)
 
             def step():
                 bucket.zero_()

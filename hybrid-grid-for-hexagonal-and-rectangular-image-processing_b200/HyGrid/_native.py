@@ -82,6 +82,8 @@ _SIGS = {
     "hg_bn_apply": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _l, _l, C.c_float, _i, _p],
     "hg_bn_bwd_reduce": [_p, _p, _p, _p, _p, _p, _p, _l, _l, _l, _i, _p],
     "hg_bn_bwd_apply": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _l, _l, _i, _i, _p],
+    "hg_bn_train_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _d, _l, _l, _l, C.c_float, _i, _p],
+    "hg_bn_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _l, _l, _l, _i, _i, _p],
     "hg_hexconv_dgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p],
     "hg_hexconv_wgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],
     "hg_dwtaps_fwd": [C.POINTER(DwTapsDesc), _p, _p, _p, _p, _p],

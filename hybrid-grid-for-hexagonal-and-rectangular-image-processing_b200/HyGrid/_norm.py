@@ -28,7 +28,10 @@ def bn_supported(bn: nn.Module, x: torch.Tensor) -> bool:
 
 class _BatchNormReluFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, running_mean, running_var, use_batch_stats, factor, eps, relu):
+    def forward(ctx, x, weight, bias, running_mean, running_var, batches, use_batch_stats, momentum, eps, relu):
+        """``momentum``: None = do not touch the running statistics, < 0 = cumulative average over ``batches``
+        (torch's ``momentum=None``), else the blend factor.  One library call per mode (``hg_bn_train_fwd`` zeroes its
+        scratch, bumps ``num_batches_tracked`` and updates the running statistics inside the kernels)."""
         x = x.contiguous()
         N, Cc, H, W = x.shape
         HW = H * W
@@ -41,22 +44,33 @@ class _BatchNormReluFn(torch.autograd.Function):
         if use_batch_stats:
             if N * HW <= 1:
                 raise ValueError(f"Expected more than 1 value per channel when training, got input size {tuple(x.shape)}")
-            sums = torch.zeros(2 * Cc, dtype=torch.float64, device=dev)
-            var = torch.empty(Cc, dtype=torch.float32, device=dev)
-            nv.call("hg_bn_stats", nv.ptr(x), nv.ptr(sums), N, Cc, HW, st)
-            nv.call("hg_bn_apply", nv.ptr(x), nv.ptr(y), nv.ptr(sums), None, None, nv.ptr(w), nv.ptr(b), nv.ptr(mean),
-                    nv.ptr(var), nv.ptr(rstd), N, Cc, HW, C.c_float(eps), int(relu), st)
-            if running_mean is not None and factor is not None:
+            sums = torch.empty(2 * Cc, dtype=torch.float64, device=dev)
+            update = momentum is not None and running_mean is not None
+            fused = update and running_mean.dtype == torch.float32 and running_var.dtype == torch.float32 \
+                and running_mean.is_contiguous() and running_var.is_contiguous() \
+                and (batches is None or batches.dtype == torch.int64)
+            nv.call("hg_bn_train_fwd", nv.ptr(x), nv.ptr(y), nv.ptr(sums), nv.ptr(w), nv.ptr(b), nv.ptr(mean), nv.ptr(rstd),
+                    nv.ptr(running_mean) if fused else None, nv.ptr(running_var) if fused else None,
+                    nv.ptr(batches) if fused and batches is not None else None, float(momentum) if fused else 0.0,
+                    N, Cc, HW, C.c_float(eps), int(relu), st)
+            if update and not fused:          # running statistics in another dtype: torch's own arithmetic
                 n = N * HW
                 with torch.no_grad():
-                    running_mean.mul_(1 - factor).add_(mean, alpha=factor)
-                    running_var.mul_(1 - factor).add_(var, alpha=factor * n / (n - 1))
+                    if batches is not None:
+                        batches.add_(1)
+                    f = momentum if momentum >= 0 else 1.0 / float(batches)
+                    var = (sums[1::2] / n - (sums[0::2] / n) ** 2).clamp_(min=0).to(running_var.dtype)
+                    running_mean.mul_(1 - f).add_(mean.to(running_mean.dtype), alpha=f)
+                    running_var.mul_(1 - f).add_(var, alpha=f * n / (n - 1))
         else:
             rm, rv = running_mean.detach().float().contiguous(), running_var.detach().float().contiguous()
             nv.call("hg_bn_apply", nv.ptr(x), nv.ptr(y), None, nv.ptr(rm), nv.ptr(rv), nv.ptr(w), nv.ptr(b), nv.ptr(mean),
                     None, nv.ptr(rstd), N, Cc, HW, C.c_float(eps), int(relu), st)
         ctx.save_for_backward(x, w, b, mean, rstd)
         ctx.cfg = (bool(use_batch_stats), bool(relu), weight is not None, bias is not None)
+        # gradient sinks (HyGrid.distributed.FlatGradBucket): dgamma / dbeta are added straight to their bucket slices
+        ctx.sinks = (getattr(weight, "_hg_grad_sink", None) if weight is not None else None,
+                     getattr(bias, "_hg_grad_sink", None) if bias is not None else None)
         return y
 
     @staticmethod
@@ -68,25 +82,39 @@ class _BatchNormReluFn(torch.autograd.Function):
         HW = H * W
         dev, st = x.device, nv.stream_ptr(x.device)
         dy = dy.contiguous().float()
-        dsums = torch.zeros(2 * Cc, dtype=torch.float64, device=dev)
-        nv.call("hg_bn_bwd_reduce", nv.ptr(x), nv.ptr(dy), nv.ptr(mean), nv.ptr(rstd), nv.ptr(w), nv.ptr(b), nv.ptr(dsums),
-                N, Cc, HW, int(relu), st)
+        dsums = torch.empty(2 * Cc, dtype=torch.float64, device=dev)
         dx = torch.empty_like(x)
-        dg = torch.empty(Cc, dtype=torch.float32, device=dev) if has_w and ctx.needs_input_grad[1] else None
-        db = torch.empty(Cc, dtype=torch.float32, device=dev) if has_b and ctx.needs_input_grad[2] else None
-        nv.call("hg_bn_bwd_apply", nv.ptr(x), nv.ptr(dy), nv.ptr(mean), nv.ptr(rstd), nv.ptr(w), nv.ptr(b), nv.ptr(dsums),
-                nv.ptr(dx), nv.ptr(dg), nv.ptr(db), N, Cc, HW, int(relu), int(training), st)
-        return dx, dg, db, None, None, None, None, None, None
+        want_g, want_b = has_w and ctx.needs_input_grad[1], has_b and ctx.needs_input_grad[2]
+        sink_g, sink_b = ctx.sinks
+        # both affine gradients go to the bucket, or neither does (one accumulate flag for the pair)
+        sunk = bool(want_g and want_b and sink_g is not None and sink_b is not None
+                    and sink_g.view.numel() == Cc and sink_b.view.numel() == Cc)
+        if sunk:
+            dg, db = sink_g.view, sink_b.view
+        else:
+            dg = torch.empty(Cc, dtype=torch.float32, device=dev) if want_g else None
+            db = torch.empty(Cc, dtype=torch.float32, device=dev) if want_b else None
+        nv.call("hg_bn_bwd", nv.ptr(x), nv.ptr(dy), nv.ptr(mean), nv.ptr(rstd), nv.ptr(w), nv.ptr(b), nv.ptr(dsums),
+                nv.ptr(dx), nv.ptr(dg), nv.ptr(db), int(sunk), N, Cc, HW, int(relu), int(training), st)
+        if sunk:
+            sink_g.landed()
+            sink_b.landed()
+            dg = db = None
+        return dx, dg, db, None, None, None, None, None, None, None
 
 
 def batch_norm_relu(bn: nn.BatchNorm2d, x: torch.Tensor, relu: bool = False) -> torch.Tensor:
-    """``relu(bn(x))`` (or ``bn(x)``) with torch.nn.BatchNorm2d's bookkeeping (nn/modules/batchnorm.py ``forward``)."""
-    factor = 0.0 if bn.momentum is None else bn.momentum
-    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
-        factor = 1.0 / float(bn.num_batches_tracked) if bn.momentum is None else bn.momentum
+    """``relu(bn(x))`` (or ``bn(x)``) with torch.nn.BatchNorm2d's bookkeeping (nn/modules/batchnorm.py ``forward``):
+    ``num_batches_tracked`` is incremented and the running averages are blended in training mode when the module tracks
+    them -- by the kernels themselves, the step is launch-bound."""
     use_batch_stats = bn.training or (bn.running_mean is None and bn.running_var is None)
-    update = bn.training and bn.track_running_stats
-    return _BatchNormReluFn.apply(x, bn.weight, bn.bias, bn.running_mean if (update or not use_batch_stats) else None,
-                                  bn.running_var if (update or not use_batch_stats) else None, use_batch_stats,
-                                  factor if update else None, bn.eps, relu)
+    update = bn.training and bn.track_running_stats and bn.running_mean is not None
+    momentum = None
+    if update:
+        momentum = -1.0 if bn.momentum is None else float(bn.momentum)
+        if bn.momentum is None and bn.num_batches_tracked is None:
+            momentum = 0.0
+    needs_running = update or not use_batch_stats
+    return _BatchNormReluFn.apply(x, bn.weight, bn.bias, bn.running_mean if needs_running else None,
+                                  bn.running_var if needs_running else None, bn.num_batches_tracked if update else None,
+                                  use_batch_stats, momentum, bn.eps, relu)

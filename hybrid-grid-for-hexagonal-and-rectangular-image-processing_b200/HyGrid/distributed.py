@@ -109,6 +109,7 @@ class FlatGradBucket:
         self.group_of = [g for g, (a, b) in enumerate(self.bounds) for _ in range(a, b)]
         self.trace: List[Tuple[str, int]] = []           # ("ready", param index) / ("launch", group index), per step
         self._hooks = []
+        self._views: List[Optional[torch.Tensor]] = [None] * len(self.params)
         self._reset_step()
         self.attach()
 
@@ -128,8 +129,13 @@ class FlatGradBucket:
         return cuts
 
     def view(self, i: int) -> torch.Tensor:
-        p = self.params[i]
-        return self.flat[self.offsets[i]:self.offsets[i] + p.numel()].view_as(p)
+        v = self._views[i] if i < len(self._views) else None      # cached: _ready() runs once per parameter and step
+        if v is None:
+            p = self.params[i]
+            v = self.flat[self.offsets[i]:self.offsets[i] + p.numel()].view_as(p)
+            if i < len(self._views):
+                self._views[i] = v
+        return v
 
     def _slice(self, g: int) -> torch.Tensor:
         a, b = self.bounds[g]

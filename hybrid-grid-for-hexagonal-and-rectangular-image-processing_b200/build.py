@@ -27,6 +27,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3",
     "--expt-relaxed-constexpr",
 ]
+# debugging builds, e.g. HG_EXTRA_NVCC_FLAGS="-DHG_TRAP_DEBUG -DHG_SPIN_LIMIT=(1u<<22)" (csrc/hg_ptx.cuh)
+NVCC_FLAGS += os.environ.get("HG_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _nvcc():

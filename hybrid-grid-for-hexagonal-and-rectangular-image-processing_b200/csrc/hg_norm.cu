@@ -46,6 +46,16 @@ struct BnGeom {
   double inv_n;        // 1 / (N * HW)
 };
 
+// torch.nn.BatchNorm2d's training-mode bookkeeping, done by the kernels that have the numbers anyway (hg_bn_train_fwd):
+// the stats kernel bumps num_batches_tracked, the apply kernel blends mean / unbiased variance into the running buffers.
+struct BnRunning {
+  float* mean;                 // running_mean [C] or NULL
+  float* var;                  // running_var  [C]
+  long long* batches;          // num_batches_tracked (int64 scalar) or NULL
+  float momentum;              // < 0: cumulative moving average, factor = 1 / num_batches_tracked (after the increment)
+  float unbias;                // n / (n - 1)
+};
+
 __device__ __forceinline__ void bn_locate(const BnGeom& g, long long& base, int& n, int& c) {
   const long long plane = blockIdx.x / g.chunks;
   const int ck = (int)(blockIdx.x - plane * g.chunks);
@@ -58,9 +68,10 @@ __device__ __forceinline__ void bn_locate(const BnGeom& g, long long& base, int&
 // sums[2c] += sum x, sums[2c+1] += sum x^2 over this CTA's chunk
 template <bool VEC>
 __global__ void __launch_bounds__(kBnThreads)
-bn_stats_kernel(const float* __restrict__ x, double* __restrict__ sums, BnGeom g) {
+bn_stats_kernel(const float* __restrict__ x, double* __restrict__ sums, BnGeom g, long long* __restrict__ batches) {
   long long base; int n, c;
   bn_locate(g, base, n, c);
+  if (batches && blockIdx.x == 0 && threadIdx.x == 0) *batches += 1;      // read by the apply kernel that follows in the stream
   const float* __restrict__ p = x + base;
   float s = 0.f, ss = 0.f;
   if (VEC) {
@@ -93,7 +104,8 @@ template <bool VEC>
 __global__ void __launch_bounds__(kBnThreads)
 bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, const double* __restrict__ sums, const float* __restrict__ mean_in,
                 const float* __restrict__ var_in, const float* __restrict__ gamma, const float* __restrict__ beta,
-                float* __restrict__ mean_out, float* __restrict__ var_out, float* __restrict__ rstd_out, BnGeom g, float eps, int relu) {
+                float* __restrict__ mean_out, float* __restrict__ var_out, float* __restrict__ rstd_out, BnGeom g, float eps, int relu,
+                BnRunning run) {
   long long base; int n, c;
   bn_locate(g, base, n, c);
   float mean, rstd, scale, shift;
@@ -105,9 +117,17 @@ bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, const double
       const double m = sums[2 * c] * g.inv_n;
       const double v = sums[2 * c + 1] * g.inv_n - m * m;
       mean_out[c] = (float)m;
-      var_out[c] = (float)(v < 0.0 ? 0.0 : v);
+      if (var_out) var_out[c] = (float)(v < 0.0 ? 0.0 : v);
     } else if (mean_out) {
       mean_out[c] = mean;
+    }
+    if (sums && run.mean) {      // running = (1 - f) * running + f * batch statistic, float32 as torch does it; unbiased variance
+      const double m = sums[2 * c] * g.inv_n;
+      double v = sums[2 * c + 1] * g.inv_n - m * m;
+      if (v < 0.0) v = 0.0;
+      const float f = run.momentum >= 0.f ? run.momentum : 1.f / (float)(*run.batches);
+      run.mean[c] = run.mean[c] * (1.f - f) + f * (float)m;
+      run.var[c] = run.var[c] * (1.f - f) + (f * run.unbias) * (float)v;
     }
   }
   const float* __restrict__ p = x + base;
@@ -159,15 +179,16 @@ template <bool VEC>
 __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ gamma, const float* __restrict__ beta, const double* __restrict__ dsums,
-                    float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, BnGeom g, int relu, int training) {
+                    float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, BnGeom g, int relu, int training,
+                    int accumulate) {
   long long base; int n, c;
   bn_locate(g, base, n, c);
   const float m = mean[c], r = rstd[c];
   const float sc = (gamma ? gamma[c] : 1.f) * r, shift = fmaf(-m, sc, beta ? beta[c] : 0.f);
   const float sdz = (float)dsums[2 * c], sdzx = (float)dsums[2 * c + 1];
   if (blockIdx.x < (unsigned)(g.C * g.chunks) && blockIdx.x % g.chunks == 0 && threadIdx.x == 0) {
-    if (dbeta) dbeta[c] = sdz;
-    if (dgamma) dgamma[c] = sdzx;
+    if (dbeta) dbeta[c] = accumulate ? dbeta[c] + sdz : sdz;          // accumulate: the slot is a slice of the all-reduce bucket
+    if (dgamma) dgamma[c] = accumulate ? dgamma[c] + sdzx : sdzx;
   }
   // training: statistics depend on x; inference (running statistics): dx = gamma * rstd * dz
   const float k0 = training ? (float)((double)sdz * g.inv_n) : 0.f, k1 = training ? (float)((double)sdzx * g.inv_n) : 0.f;
@@ -215,8 +236,8 @@ int hg_bn_stats(const float* x, double* sums, int64_t N, int64_t C, int64_t HW, 
   if (rc) return rc;
   HG_REQUIRE(x && sums, HG_E_ARG, "NULL buffer");
   cudaStream_t st = as_stream(stream);
-  if (vec) bn_stats_kernel<true><<<grid, kBnThreads, 0, st>>>(x, sums, g);
-  else bn_stats_kernel<false><<<grid, kBnThreads, 0, st>>>(x, sums, g);
+  if (vec) bn_stats_kernel<true><<<grid, kBnThreads, 0, st>>>(x, sums, g, nullptr);
+  else bn_stats_kernel<false><<<grid, kBnThreads, 0, st>>>(x, sums, g, nullptr);
   return finish_launch("bn_stats");
 }
 
@@ -228,8 +249,9 @@ int hg_bn_apply(const float* x, float* y, const double* sums, const float* mean_
   if (rc) return rc;
   HG_REQUIRE(x && y && (sums || (mean_in && var_in)), HG_E_ARG, "batch-norm needs either the batch sums or mean / var");
   cudaStream_t st = as_stream(stream);
-  if (vec) bn_apply_kernel<true><<<grid, kBnThreads, 0, st>>>(x, y, sums, mean_in, var_in, gamma, beta, mean_out, var_out, rstd_out, g, eps, relu);
-  else bn_apply_kernel<false><<<grid, kBnThreads, 0, st>>>(x, y, sums, mean_in, var_in, gamma, beta, mean_out, var_out, rstd_out, g, eps, relu);
+  const BnRunning none{nullptr, nullptr, nullptr, 0.f, 1.f};
+  if (vec) bn_apply_kernel<true><<<grid, kBnThreads, 0, st>>>(x, y, sums, mean_in, var_in, gamma, beta, mean_out, var_out, rstd_out, g, eps, relu, none);
+  else bn_apply_kernel<false><<<grid, kBnThreads, 0, st>>>(x, y, sums, mean_in, var_in, gamma, beta, mean_out, var_out, rstd_out, g, eps, relu, none);
   return finish_launch("bn_apply");
 }
 
@@ -253,8 +275,59 @@ int hg_bn_bwd_apply(const float* x, const float* dy, const float* mean, const fl
   if (rc) return rc;
   HG_REQUIRE(x && dy && mean && rstd && dsums && dx, HG_E_ARG, "NULL buffer");
   cudaStream_t st = as_stream(stream);
-  if (vec) bn_bwd_apply_kernel<true><<<grid, kBnThreads, 0, st>>>(x, dy, mean, rstd, gamma, beta, dsums, dx, dgamma, dbeta, g, relu, training);
-  else bn_bwd_apply_kernel<false><<<grid, kBnThreads, 0, st>>>(x, dy, mean, rstd, gamma, beta, dsums, dx, dgamma, dbeta, g, relu, training);
+  if (vec) bn_bwd_apply_kernel<true><<<grid, kBnThreads, 0, st>>>(x, dy, mean, rstd, gamma, beta, dsums, dx, dgamma, dbeta, g, relu, training, 0);
+  else bn_bwd_apply_kernel<false><<<grid, kBnThreads, 0, st>>>(x, dy, mean, rstd, gamma, beta, dsums, dx, dgamma, dbeta, g, relu, training, 0);
+  return finish_launch("bn_bwd_apply");
+}
+
+// One call per training-mode forward: the C5 step is launch-bound (about 85 launches in 2 ms), and the torch-side bookkeeping
+// of a BatchNorm2d -- zero the sums, bump the counter, two mul_ / add_ pairs for the running statistics -- was six launches
+// per layer next to the two kernels that do the work.
+int hg_bn_train_fwd(const float* x, float* y, double* sums, const float* gamma, const float* beta, float* mean_out, float* rstd_out,
+                    float* running_mean, float* running_var, int64_t* num_batches_tracked, double momentum, int64_t N, int64_t C,
+                    int64_t HW, float eps, int relu, hg_stream_t stream) {
+  BnGeom g; unsigned grid; bool vec;
+  int rc = bn_geom(N, C, HW, g, grid, vec, x, y, nullptr);
+  if (rc) return rc;
+  HG_REQUIRE(x && y && sums && mean_out && rstd_out, HG_E_ARG, "NULL buffer");
+  HG_REQUIRE((running_mean == nullptr) == (running_var == nullptr), HG_E_ARG, "running_mean and running_var come together");
+  HG_REQUIRE(momentum >= 0.0 || running_mean == nullptr || num_batches_tracked != nullptr, HG_E_ARG,
+             "a cumulative moving average (momentum < 0) needs num_batches_tracked");
+  HG_REQUIRE(N * HW > 1, HG_E_SHAPE, "training-mode batch norm needs more than one value per channel");
+  cudaStream_t st = as_stream(stream);
+  cudaError_t me = cudaMemsetAsync(sums, 0, (size_t)(2 * C) * sizeof(double), st);
+  HG_REQUIRE(me == cudaSuccess, (int)me, "hg_bn_train_fwd: cudaMemsetAsync: %s", cudaGetErrorString(me));
+  long long* nbt = reinterpret_cast<long long*>(num_batches_tracked);
+  if (vec) bn_stats_kernel<true><<<grid, kBnThreads, 0, st>>>(x, sums, g, nbt);
+  else bn_stats_kernel<false><<<grid, kBnThreads, 0, st>>>(x, sums, g, nbt);
+  rc = finish_launch("bn_stats");
+  if (rc) return rc;
+  const double n = (double)N * (double)HW;
+  const BnRunning run{running_mean, running_var, nbt, (float)momentum, (float)(n / (n - 1.0))};
+  if (vec) bn_apply_kernel<true><<<grid, kBnThreads, 0, st>>>(x, y, sums, nullptr, nullptr, gamma, beta, mean_out, nullptr, rstd_out, g, eps, relu, run);
+  else bn_apply_kernel<false><<<grid, kBnThreads, 0, st>>>(x, y, sums, nullptr, nullptr, gamma, beta, mean_out, nullptr, rstd_out, g, eps, relu, run);
+  return finish_launch("bn_apply");
+}
+
+// Backward in one call: zeroes `dsums`, reduces, applies.  accumulate_affine != 0 adds dgamma / dbeta to their destinations
+// (slices of HyGrid.distributed.FlatGradBucket, zeroed at the start of the step) instead of overwriting them.
+int hg_bn_bwd(const float* x, const float* dy, const float* mean, const float* rstd, const float* gamma, const float* beta,
+              double* dsums, float* dx, float* dgamma, float* dbeta, int accumulate_affine, int64_t N, int64_t C, int64_t HW,
+              int relu, int training, hg_stream_t stream) {
+  BnGeom g; unsigned grid; bool vec;
+  int rc = bn_geom(N, C, HW, g, grid, vec, x, dy, dx);
+  if (rc) return rc;
+  HG_REQUIRE(x && dy && mean && rstd && dsums && dx, HG_E_ARG, "NULL buffer");
+  cudaStream_t st = as_stream(stream);
+  cudaError_t me = cudaMemsetAsync(dsums, 0, (size_t)(2 * C) * sizeof(double), st);
+  HG_REQUIRE(me == cudaSuccess, (int)me, "hg_bn_bwd: cudaMemsetAsync: %s", cudaGetErrorString(me));
+  if (vec) bn_bwd_reduce_kernel<true><<<grid, kBnThreads, 0, st>>>(x, dy, mean, rstd, gamma, beta, dsums, g, relu);
+  else bn_bwd_reduce_kernel<false><<<grid, kBnThreads, 0, st>>>(x, dy, mean, rstd, gamma, beta, dsums, g, relu);
+  rc = finish_launch("bn_bwd_reduce");
+  if (rc) return rc;
+  const int acc = accumulate_affine ? 1 : 0;
+  if (vec) bn_bwd_apply_kernel<true><<<grid, kBnThreads, 0, st>>>(x, dy, mean, rstd, gamma, beta, dsums, dx, dgamma, dbeta, g, relu, training, acc);
+  else bn_bwd_apply_kernel<false><<<grid, kBnThreads, 0, st>>>(x, dy, mean, rstd, gamma, beta, dsums, dx, dgamma, dbeta, g, relu, training, acc);
   return finish_launch("bn_bwd_apply");
 }
 

@@ -1,6 +1,7 @@
 // hg_ptx.cuh -- thin inline-PTX wrappers for the sm_100a features the kernels use: mbarrier, TMA
 // (cp.async.bulk.tensor), tcgen05 (TMEM alloc / mma / commit / ld) and the fences between proxies.
 #pragma once
+#include <cstdio>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -44,7 +45,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (HG_SPIN_LIMIT && ++spins > HG_SPIN_LIMIT) __trap();
+    if (HG_SPIN_LIMIT && ++spins > HG_SPIN_LIMIT) {
+#ifdef HG_TRAP_DEBUG   // which waits starved: -DHG_TRAP_DEBUG -DHG_SPIN_LIMIT=(1u<<22) via HG_EXTRA_NVCC_FLAGS; every stuck warp
+      if (spins == HG_SPIN_LIMIT + 1 && blockIdx.x == 0)      // reports once, the trap comes later
+        printf("mbar_wait starved: block %d thread %d barrier@smem+%u parity %u\n", (int)blockIdx.x, (int)threadIdx.x,
+               (unsigned)__cvta_generic_to_shared(bar), parity);
+      if (spins < 4096u * HG_SPIN_LIMIT) continue;
+#endif
+      __trap();
+    }
   }
 }
 

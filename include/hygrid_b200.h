@@ -323,6 +323,24 @@ int hg_bn_bwd_apply(const float* x, const float* dy, const float* mean, const fl
                     const float* beta, const double* dsums, float* dx, float* dgamma, float* dbeta, int64_t N,
                     int64_t C, int64_t HW, int relu, int training, hg_stream_t stream);
 
+/* The same two passes per direction as ONE call each, with torch.nn.BatchNorm2d's training-mode bookkeeping done by the
+ * kernels (the C5 training step is launch-bound: zeroing the sums, bumping num_batches_tracked and the mul_ / add_ pairs of
+ * the running statistics were six extra launches per layer and step).
+ *   hg_bn_train_fwd  zeroes `sums` (float64 [2*C] scratch), accumulates the batch statistics, writes y = act(bn(x)) and
+ *                    mean / rstd for backward; when running_mean / running_var (float32 [C]) are given, increments
+ *                    *num_batches_tracked (int64, may be NULL when momentum >= 0) and blends
+ *                    running = (1 - f) * running + f * (mean | var * n / (n - 1)),  f = momentum, or
+ *                    1 / num_batches_tracked when momentum < 0 (torch's momentum=None cumulative average).
+ *                    ref: HexModules.py:57-76 (mmcv build_norm_layer -> torch.nn.BatchNorm2d), :275-288 forward order.
+ *   hg_bn_bwd        zeroes `dsums`, reduces, writes dx; dgamma / dbeta (may be NULL) are overwritten, or added to when
+ *                    accumulate_affine != 0 (slices of the all-reduce bucket, HyGrid/distributed.py). */
+int hg_bn_train_fwd(const float* x, float* y, double* sums, const float* gamma, const float* beta, float* mean_out,
+                    float* rstd_out, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                    double momentum, int64_t N, int64_t C, int64_t HW, float eps, int relu, hg_stream_t stream);
+int hg_bn_bwd(const float* x, const float* dy, const float* mean, const float* rstd, const float* gamma,
+              const float* beta, double* dsums, float* dx, float* dgamma, float* dbeta, int accumulate_affine,
+              int64_t N, int64_t C, int64_t HW, int relu, int training, hg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

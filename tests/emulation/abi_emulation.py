@@ -111,6 +111,35 @@ def bn_entry(name, a):
     """hg_bn_*: the formulas of include/hygrid_b200.h in float64 (float32 where the header says so)."""
     def f32(ptr, n):
         return view(ptr, n, nv.F32) if ptr is not None and getattr(ptr, "value", ptr) else None
+    if name == "hg_bn_train_fwd":      # = zero the sums + hg_bn_stats + hg_bn_apply + BatchNorm2d's running-statistics update
+        x, y, sums, gamma, beta, mean_out, rstd_out, rmean, rvar, nbt, momentum, N, Cn, HW, eps, relu, st = a
+        view(sums, 2 * Cn, nv.F64)[:] = 0.0
+        bn_entry("hg_bn_stats", (x, sums, N, Cn, HW, st))
+        bn_entry("hg_bn_apply", (x, y, sums, None, None, gamma, beta, mean_out, None, rstd_out, N, Cn, HW, eps, relu, st))
+        if f32(rmean, Cn) is not None:
+            momentum = momentum.value if hasattr(momentum, "value") else float(momentum)
+            if nbt is not None and getattr(nbt, "value", nbt):
+                cnt = view(nbt, 1, nv.I64)
+                cnt[0] += 1
+            f = np.float32(momentum if momentum >= 0 else 1.0 / float(cnt[0]))
+            sm = view(sums, 2 * Cn, nv.F64)
+            n = N * HW
+            mean = sm[0::2] / n
+            var = np.maximum(sm[1::2] / n - mean * mean, 0.0)
+            f32(rmean, Cn)[:] = f32(rmean, Cn) * (np.float32(1) - f) + f * mean.astype(np.float32)
+            f32(rvar, Cn)[:] = f32(rvar, Cn) * (np.float32(1) - f) + (f * np.float32(n / (n - 1.0))) * var.astype(np.float32)
+        return
+    if name == "hg_bn_bwd":            # = zero the sums + hg_bn_bwd_reduce + hg_bn_bwd_apply (optionally accumulating dgamma / dbeta)
+        x, dy, mean, rstd, gamma, beta, dsums, dx, dgamma, dbeta, acc, N, Cn, HW, relu, training, st = a
+        view(dsums, 2 * Cn, nv.F64)[:] = 0.0
+        bn_entry("hg_bn_bwd_reduce", (x, dy, mean, rstd, gamma, beta, dsums, N, Cn, HW, relu, st))
+        old = [None if f32(p_, Cn) is None else f32(p_, Cn).copy() for p_ in (dgamma, dbeta)]
+        bn_entry("hg_bn_bwd_apply", (x, dy, mean, rstd, gamma, beta, dsums, dx, dgamma, dbeta, N, Cn, HW, relu, training, st))
+        if acc:
+            for p_, o in zip((dgamma, dbeta), old):
+                if o is not None:
+                    f32(p_, Cn)[:] += o
+        return
     if name == "hg_bn_stats":
         x, sums, N, Cn, HW, _ = a
         xs = view(x, N * Cn * HW, nv.F32).reshape(N, Cn, HW).astype(np.float64)

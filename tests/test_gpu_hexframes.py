@@ -428,6 +428,34 @@ def test_batch_norm_relu_kernels_vs_torch(hf, cfg):
             assert int(ours.num_batches_tracked) == int(ref.num_batches_tracked)
 
 
+def test_batch_norm_affine_gradients_land_in_the_flat_bucket(hf):
+    """With a FlatGradBucket attached, dgamma / dbeta of the library batch norm are ADDED to their bucket slices by the
+    backward kernel itself (gradient sink, no autograd accumulate launch): equal to the plain gradients after one backward
+    pass, twice that after two, and the bucket is told that both tensors landed."""
+    from HyGrid import HexModules as hm
+    from HyGrid.distributed import FlatGradBucket
+    torch.manual_seed(8)
+    m = hm.HexConvModule(8, 16, 0, 2, padding=1, norm_cfg=dict(type='BN')).cuda()
+    x = torch.randn(3, 8, 12, 16, device="cuda")
+    g = torch.randn(3, 16, 12, 16, device="cuda")
+    (m(x) * g).sum().backward()
+    plain = {k: p.grad.clone() for k, p in m.named_parameters()}
+    m.zero_grad(set_to_none=True)
+    bucket = FlatGradBucket(m.parameters(), groups=1, overlap=False)
+    names = [k for k, _ in m.named_parameters()]
+    for rep in (1, 2):
+        (m(x) * g).sum().backward()
+        for i, k in enumerate(names):
+            got = bucket.view(i)
+            assert float((got - rep * plain[k]).abs().max()) <= 1e-4 * max(1e-3, float(plain[k].abs().max())), (k, rep)
+        if rep == 1:
+            assert sorted(i for kind, i in bucket.trace if kind == "ready") == list(range(len(names)))
+    bucket.zero_()
+    iw = [i for i, (_, p) in enumerate(m.named_parameters()) if p is m.norm.weight][0]
+    assert float(bucket.flat.abs().max()) == 0.0 and m.norm.weight.grad.data_ptr() == bucket.view(iw).data_ptr()
+    bucket.detach()
+
+
 def test_hexconvmodule_training_uses_library_bn(hf):
     """conv -> BN -> ReLU in training mode: 1 conv + 2 batch-norm launches forward, gradients equal to the torch
     composition of the same conv output."""

@@ -47,7 +47,7 @@ def main():
     model = HexCNN().to(dev)
     bucket = FlatGradBucket(model.parameters(), groups=1 if a.blocking else ([3, 3, 5] if a.groups == 3 else a.groups),
                             overlap=not a.blocking)
-    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9)
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, fused=True)
     g = torch.Generator(device="cpu").manual_seed(1)
     data = torch.randn(a.batch * world, 3, a.hw, a.hw, generator=g)
     target = torch.randint(0, 10, (a.batch * world,), generator=g)
