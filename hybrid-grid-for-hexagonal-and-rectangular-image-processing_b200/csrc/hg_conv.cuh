@@ -14,6 +14,7 @@
 //   o = (even_odd_offset + pad) & 1  ("parity" in hg_conv_desc).
 #pragma once
 #include "hg_common.cuh"
+#include <stdlib.h>
 
 namespace hg {
 
@@ -67,6 +68,18 @@ static inline void conv_out_shape(int64_t Hp, int64_t Wp, int radius, int s, int
   cols = wt >= k_w ? (wt - k_w) / (2 * s) + 1 : 0;
   rows_e = Hp >= k_h ? (Hp - k_h) / (2 * s) + 1 : 0;
   rows_o = Hp - s >= k_h ? (Hp - s - k_h) / (2 * s) + 1 : 0;
+}
+
+// Output rows per work item of the persistent tcgen05 kernels: `max_band` rows when the problem has plenty of items, shorter
+// bands (down to 8 rows; each band re-stages its 2 halo rows) while a launch would otherwise leave most of the 148 SMs with
+// one item or none -- the C5 layers (64 images of 64 x 64 or 32 x 32 cells) are 64-128 items at 32 rows per band.
+// HG_CONV_BAND=<rows> forces a value (A/B runs).
+static inline int conv_pick_band(int max_band, long long N, int Ho, int ctiles) {
+  const char* e = getenv("HG_CONV_BAND");
+  if (e && atoi(e) >= 1) return atoi(e) < max_band ? atoi(e) : max_band;
+  int band = max_band;
+  while (band > 8 && N * ((Ho + band - 1) / band) * ctiles < 4 * 148) band >>= 1;
+  return band;
 }
 
 }  // namespace hg

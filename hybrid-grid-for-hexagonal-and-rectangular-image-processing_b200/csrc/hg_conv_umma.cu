@@ -38,7 +38,7 @@ constexpr int kUmLoaders = 256;
 constexpr int kUmEpiWarps = 8;               // two warps per TMEM lane quadrant, alternating 32-channel chunks
 constexpr int kUmMmaWarp = kUmLoaders / 32 + kUmEpiWarps;
 constexpr int kUmThreads = kUmLoaders + kUmEpiWarps * 32 + 32 + 32;
-constexpr int kUmBand = 32;                  // output rows per work item
+constexpr int kUmBand = 32;                  // output rows per work item (upper bound; small problems take shorter bands, umma_common)
 constexpr int kUmMaxQ = 5;                   // ceil(8 * 144 / 256): (chunk, pixel) tasks per loader thread, Cred <= 64
 constexpr int kTaps = 7;
 constexpr int kUmMaxCred = 512;              // reduction channels per call (passes of <= 64)
@@ -55,6 +55,7 @@ struct UmmaParams {
   int cred_total, c_off, accumulate; // reduction channels > 64 run as passes of <= 64: this pass covers channels
                                      // [c_off, c_off + Cred) of cred_total and (accumulate) adds to the output of the previous pass
   int slots, bands, ctiles;
+  int band;                      // output rows per work item
   int rstages, raw_bytes;        // TMA variant: raw staging ring
   long long items;
 };
@@ -102,8 +103,10 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
       const int kc = r / (P.Nout * 8), r2 = r - kc * P.Nout * 8;
       const int n = r2 >> 3, j = r2 & 7;
       const int red = P.c_off + kc * 8 + j;
-      const float v = P.transpose_w ? __ldg(w + ((size_t)red * P.Nout + n) * kTaps + k)          // w[co=red][ci=n][k]
-                                    : __ldg(w + ((size_t)n * P.cred_total + red) * kTaps + k);   // w[co=n][ci=red][k]
+      // (forward with Cin rounded up to 16 -- RGB first layers: the channels that do not exist carry zero weights)
+      const float v = red >= P.cred_total ? 0.f
+                      : P.transpose_w ? __ldg(w + ((size_t)red * P.Nout + n) * kTaps + k)          // w[co=red][ci=n][k]
+                                      : __ldg(w + ((size_t)n * P.cred_total + red) * kTaps + k);   // w[co=n][ci=red][k]
       // per-output-channel scale (BN-inference affine of HexConvModule) folded into the weight image: free at run time
       reinterpret_cast<__nv_bfloat16*>(w_smem)[e] = __float2bfloat16_rn(scale ? v * __ldg(scale + n) : v);
     }
@@ -138,7 +141,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
       const int n = (int)(item / per_n);
       const int rem = (int)(item - (long long)n * per_n);
       const int band = rem / P.ctiles, ct = rem - band * P.ctiles;
-      const int r0 = band * kUmBand, rows = min(kUmBand, P.Ho - r0), c0 = ct * kUmTile;
+      const int r0 = band * P.band, rows = min(P.band, P.Ho - r0), c0 = ct * kUmTile;
       const TIN* __restrict__ in_n = in + ((size_t)n * P.cred_total + P.c_off) * plane;
       for (int t = 0; t < rows + 2; ++t, ++lt) {
         const int slot = (int)(lt % P.slots);
@@ -189,9 +192,10 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
               const bool col_in = j >= 0 && j < P.Wi;
               const float fill = (row_frame && col_frame) ? P.pad_value : 0.f;
               const TIN* __restrict__ src = in_n + (size_t)(kc * 8) * plane + (size_t)i * P.Wi + j;
+              const int c_left = P.cred_total - P.c_off - kc * 8;      // channels that exist from this group on (RGB: 3 of 16)
               float v[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = (row_in && col_in) ? ld_in(src + (size_t)e * plane) : fill;
+              for (int e = 0; e < 8; ++e) v[e] = e < c_left ? ((row_in && col_in) ? ld_in(src + (size_t)e * plane) : fill) : 0.f;
               pk[q] = pack8(v);
             }
           }
@@ -220,7 +224,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
       const int n = (int)(item / per_n);
       const int rem = (int)(item - (long long)n * per_n);
       const int band = rem / P.ctiles, ct = rem - band * P.ctiles;
-      const int r0 = band * kUmBand, rows = min(kUmBand, P.Ho - r0), c = ct * kUmTile + px;
+      const int r0 = band * P.band, rows = min(P.band, P.Ho - r0), c = ct * kUmTile + px;
       TOUT* __restrict__ orow = out + (((size_t)n * P.Nout) * P.Ho + r0) * P.Wo + c;
       for (int rr = 0; rr < rows; ++rr, orow += P.Wo) {
         ptx::mbar_wait(&tfull[acc], acc_phase);
@@ -298,7 +302,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
     for (long long item = blockIdx.x; item < P.items; item += gridDim.x) {
       const int rem = (int)(item % per_n);
       const int band = rem / P.ctiles;
-      const int r0 = band * kUmBand, rows = min(kUmBand, P.Ho - r0);
+      const int r0 = band * P.band, rows = min(P.band, P.Ho - r0);
       for (int rr = 0; rr < rows; ++rr) {
         uint32_t s1 = slot0, p1 = phase0; next_slot(s1, p1);
         uint32_t s2 = s1, p2 = p1; next_slot(s2, p2);
@@ -347,7 +351,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
         const int n = (int)(item / per_n);
         const int rem = (int)(item - (long long)n * per_n);
         const int band = rem / P.ctiles, ct = rem - band * P.ctiles;
-        const int r0 = band * kUmBand, rows = min(kUmBand, P.Ho - r0), c0 = ct * kUmTile;
+        const int r0 = band * P.band, rows = min(P.band, P.Ho - r0), c0 = ct * kUmTile;
         for (int t = 0; t < rows + 2; ++t, ++rt) {
           const int rs = (int)(rt % P.rstages);
           ptx::mbar_wait(&rempty[rs], (uint32_t)(((rt / P.rstages) & 1) ^ 1));
@@ -408,7 +412,9 @@ bool conv_wgrad_umma_eligible(const hg_conv_desc* d);   // hg_conv_wgrad_umma.cu
 bool conv_umma_eligible(const hg_conv_desc* d, int op) {
   if (op == 2) return conv_wgrad_umma_eligible(d);
   if (d->radius != 2 || d->stride != 1 || d->dilation != 1 || d->groups != 1) return false;
-  const int64_t Cred = op == 0 ? d->Cin : d->Cout, Nout = op == 0 ? d->Cout : d->Cin;
+  int64_t Cred = op == 0 ? d->Cin : d->Cout;
+  const int64_t Nout = op == 0 ? d->Cout : d->Cin;
+  if (op == 0 && Cred >= 1) Cred = (Cred + 15) / 16 * 16;                  // forward: input channels are rounded up to 16 in the loader
   if (Cred % 16 != 0 || Cred < 16 || Cred > kUmMaxCred) return false;      // > 64: passes of <= 64 channels
   if (Nout % 16 != 0 || Nout < 16 || Nout > 256) return false;
   if (op == 1 && d->relu) return false;
@@ -450,7 +456,8 @@ static int launch_umma_any(const void* in, const float* w, const float* scale, c
   memset(&tmap, 0, sizeof(tmap));
   constexpr int es = (int)sizeof(TIN), A = 16 / es;
   PFN_encodeTiled enc = get_encode_tiled();
-  bool tma = !g_um_no_tma && enc != nullptr && P.pad_value == 0.f && P.pad_mode == 0 && ((int64_t)P.Wi * es) % 16 == 0 &&
+  bool tma = !g_um_no_tma && enc != nullptr && P.pad_value == 0.f && P.pad_mode == 0 && P.c_off + P.Cred <= P.cred_total &&
+             ((int64_t)P.Wi * es) % 16 == 0 &&
              (reinterpret_cast<uintptr_t>(in) & 15) == 0;
   if (tma) {
     int slots, rst, rb;
@@ -503,7 +510,7 @@ static int dispatch_umma_pass(int in_dt, int out_dt, const void* in, const float
 static int dispatch_umma(int in_dt, int out_dt, const void* in, const float* w, const float* scale, const float* bias, void* out, UmmaParams P,
                          cudaStream_t st) {
   const int total = P.Cred, relu = P.relu, has_bias = P.has_bias, base_acc = P.accumulate;
-  P.cred_total = total;
+  if (P.cred_total <= 0) P.cred_total = total;           // the forward sets the real channel count when it rounded Cred up
   for (int c0 = 0; c0 < total; c0 += 64) {
     P.c_off = c0;
     P.Cred = total - c0 < 64 ? total - c0 : 64;
@@ -518,15 +525,16 @@ static int dispatch_umma(int in_dt, int out_dt, const void* in, const float* w, 
 
 static void umma_common(UmmaParams& P, int Ho, int Wo, int N) {
   P.N = N; P.Ho = Ho; P.Wo = Wo;
-  P.bands = (int)ceil_div(Ho, kUmBand);
   P.ctiles = (int)ceil_div(Wo, kUmTile);
+  P.band = conv_pick_band(kUmBand, N, Ho, P.ctiles);
+  P.bands = (int)ceil_div(Ho, P.band);
   P.items = (long long)N * P.bands * P.ctiles;
 }
 
 int conv_fwd_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp, const void* x, const float* w, const float* scale,
                   const float* bias, void* y, cudaStream_t st) {
   UmmaParams P{};
-  P.Cred = g.Cin; P.Nout = g.Cout; P.Hi = g.H; P.Wi = g.W;
+  P.Cred = (g.Cin + 15) / 16 * 16; P.cred_total = g.Cin; P.Nout = g.Cout; P.Hi = g.H; P.Wi = g.W;
   int cmin = 1 << 30, cmax = -(1 << 30);
   for (int par = 0; par < 2; ++par)
     for (int k = 0; k < kTaps; ++k) { cmin = min(cmin, tp.co[par][k]); cmax = max(cmax, tp.co[par][k]); }

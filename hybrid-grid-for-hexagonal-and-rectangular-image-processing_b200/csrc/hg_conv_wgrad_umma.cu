@@ -47,6 +47,7 @@ struct WgParams {
   float pad_value;
   int pad_mode;                  // 1 reflect / 2 replicate / 3 circular frame, resolved by the x loader (LDG variant)
   int xslots, gslots, bands, ctiles, has_bias;
+  int band;                      // output rows per work item
   int rstages, raw_bytes;        // TMA variant
   int m64;                       // Cout <= 64: UMMA M = 64 (half the A-operand shared-memory reads of an M = 128 view)
   int cin_total, ci_off, cout_total, co_off;   // this launch covers x channels [ci_off, ci_off + Cin) and gy channels [co_off, co_off + Cout)
@@ -237,7 +238,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
       const int n = (int)(item / per_n);
       const int rem = (int)(item - (long long)n * per_n);
       const int band = rem / P.ctiles, ct = rem - band * P.ctiles;
-      const int r0 = band * kWuBand, rows = min(kWuBand, P.Ho - r0), c0 = ct * kWuTile;
+      const int r0 = band * P.band, rows = min(P.band, P.Ho - r0), c0 = ct * kWuTile;
       const TX* __restrict__ xn = x + ((size_t)n * P.cin_total + P.ci_off) * xplane;
       const TG* __restrict__ gn = gy + ((size_t)n * P.cout_total + P.co_off) * gplane;
       load_x(xn, r0 + P.row0 + 0, c0);
@@ -295,7 +296,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
     for (long long item = blockIdx.x; item < P.items; item += gridDim.x) {
       const int rem = (int)(item % per_n);
       const int band = rem / P.ctiles;
-      const int r0 = band * kWuBand, rows = min(kWuBand, P.Ho - r0);
+      const int r0 = band * P.band, rows = min(P.band, P.Ho - r0);
       for (int rr = 0; rr < rows; ++rr) {
         uint32_t s1 = slot0, p1 = phase0; next_slot(s1, p1);
         uint32_t s2 = s1, p2 = p1; next_slot(s2, p2);
@@ -363,7 +364,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
         const int n = (int)(item / per_n);
         const int rem = (int)(item - (long long)n * per_n);
         const int band = rem / P.ctiles, ct = rem - band * P.ctiles;
-        const int r0 = band * kWuBand, rows = min(kWuBand, P.Ho - r0), c0 = ct * kWuTile;
+        const int r0 = band * P.band, rows = min(P.band, P.Ho - r0), c0 = ct * kWuTile;
         push(&xmap, xbytes, c0 + P.col0, r0 + P.row0 + 0, P.ci_off, n);
         push(&xmap, xbytes, c0 + P.col0, r0 + P.row0 + 1, P.ci_off, n);
         for (int rr = 0; rr < rows; ++rr) {
@@ -517,8 +518,9 @@ int conv_wgrad_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp
   P.row0 = -g.pad; P.col0 = cmin - g.pad;
   P.pad = g.pad; P.pad_value = g.pad_value; P.pad_mode = g.pad ? g.pad_mode : 0;
   P.has_bias = gbias != nullptr;
-  P.bands = (int)ceil_div(g.Ho, kWuBand);
   P.ctiles = (int)ceil_div(g.Wo, kWuTile);
+  P.band = conv_pick_band(kWuBand, g.N, g.Ho, P.ctiles);
+  P.bands = (int)ceil_div(g.Ho, P.band);
   P.items = (long long)g.N * P.bands * P.ctiles;
   const int xdt = d->x_dtype, gdt = d->y_dtype;
   P.cin_total = g.Cin; P.cout_total = g.Cout;

@@ -60,6 +60,9 @@ def store(ptr, t, dt):
     out[:] = f32_to_bf16(flat.float().numpy()) if dt == nv.BF16 else flat.numpy().astype(NP[dt])
 
 
+last_launch = [""]
+
+
 def conv_entry(name, a):
     """hg_hexconv_*: the oracle's closed form (and autograd through it) on the descriptor's geometry."""
     d = a[0]._obj
@@ -70,6 +73,7 @@ def conv_entry(name, a):
     op = {"hg_hexconv_fwd": 0, "hg_hexconv_fwd_affine": 0, "hg_hexconv_dgrad": 1, "hg_hexconv_wgrad": 2}[name]
     tc = d.algo == 2 or (d.algo == 0 and umma_eligible(d, op))
     bf = (lambda t: t.bfloat16().float()) if tc else (lambda t: t)   # the tcgen05 kernels read activations and weights as bfloat16
+    last_launch[0] = "hexconv_umma" if tc else "hexconv_direct"      # what hg_last_launch() would answer (kernel family)
 
     def run(x, w, b):                          # callers round the operands the kernel reads (never the autograd leaf)
         mode = ("constant", "reflect", "replicate", "circular")[d.pad_mode if d.pad else 0]      # header: frame filled in place
@@ -213,6 +217,8 @@ def umma_eligible(d, op):
         ok = 1 <= d.Cin <= 1024 and d.Cout % 8 == 0 and 8 <= d.Cout <= 1024        # input channels are rounded up to 16 in-kernel
         return ok and not (d.algo == 0 and (d.x_dtype != nv.BF16 or d.Cin * d.Cout < 1024))
     cred, nout = (d.Cin, d.Cout) if op == 0 else (d.Cout, d.Cin)
+    if op == 0 and cred >= 1:
+        cred = (cred + 15) // 16 * 16                 # the forward loader rounds the input channels up to 16
     if cred % 16 or not 16 <= cred <= 512 or nout % 16 or not 16 <= nout <= 256 or (op == 1 and d.relu):
         return False
     return not (d.algo == 0 and ((d.x_dtype if op == 0 else d.y_dtype) != nv.BF16 or cred * nout < 1024))

@@ -248,6 +248,7 @@ def main(argv):
         return int(E.umma_eligible(forced, op))
     nv.query = query
     nv.launch_count = lambda: LAUNCHES[0]
+    nv.last_launch = lambda: E.last_launch[0]
     nv.reset_launch_count = lambda: LAUNCHES.__setitem__(0, 0)
     os.chdir(ROOT)
     files = [a for a in argv if not a.startswith("-")] or ["tests/test_gpu_hexframes.py", "tests/test_gpu_resample.py"] + \

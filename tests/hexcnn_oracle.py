@@ -26,16 +26,16 @@ def oracle_forward(params, x, eps=1e-5, autocast=False):
     """Forward of the same network on CPU tensors with the oracle's operators.  ``params``: dict name -> CPU tensor
     (requires_grad as wanted) with the product model's ``named_parameters()`` names; training-mode batch norm (batch
     statistics), conv without bias (HexConvModule's bias='auto' with a norm layer).  ``autocast``: restate where the
-    product rounds to bfloat16 under torch.autocast -- every conv reads bfloat16 activations and output gradients; the
-    tensor-core layers (c2, c3) also round their weights (the RGB layer runs the direct stencil with float32 weights)."""
+    product rounds to bfloat16 under torch.autocast -- every conv runs on the tensor cores (the RGB layer with its input
+    channels rounded up to 16 in the loader) and reads bfloat16 activations, weights and output gradients, which is also
+    what the reference's cuDNN convolution does under autocast."""
     from oracle import hexframes_oracle as HO
     F = torch.nn.functional
     for blk in ("c1", "c2", "c3"):
         w = params[f"{blk}.conv.kernel"]
         if autocast:
             x = _round_bf16(x)
-            if blk != "c1":
-                w = _round_bf16(w)
+            w = _round_bf16(w)
         x = HO.hexconv2d(x, w, None, 0, 2, 1, 1)
         if autocast:
             x = _RoundGradBf16.apply(x)

@@ -481,13 +481,16 @@ def test_hexconvmodule_training_uses_library_bn(hf):
 
 
 def test_hexconv_autocast_rgb_first_layer(hf):
-    """Cin = 3 under autocast: forward on the direct stencil, weight gradient through the tcgen05 kernel with the
-    input channels zero-padded to 16 (the padded channels' gradients are dropped); vs the fp32 oracle at bf16 tolerance."""
+    """Cin = 3 under autocast: forward and weight gradient through the tcgen05 kernels with the input channels rounded up
+    to 16 inside the loaders (zero weights / dropped gradients for the channels that do not exist); vs the fp32 oracle at
+    bf16 tolerance."""
+    from HyGrid import _native as nv
     torch.manual_seed(9)
     conv = hf.HexConv2d(3, 32, 0, 2, padding=1).cuda()
     x = torch.randn(4, 3, 40, 128, device="cuda").bfloat16().float()
     with torch.autocast("cuda", dtype=torch.bfloat16):
         y = conv(x)
+    assert conv._autocast_tc and nv.last_launch().startswith("hexconv_umma"), nv.last_launch()
     g = torch.randn_like(y).bfloat16().float()
     (y * g).sum().backward()
     wr, br = conv.kernel.detach().cpu().clone().requires_grad_(), conv.bias.detach().cpu().clone().requires_grad_()
@@ -498,6 +501,21 @@ def test_hexconv_autocast_rgb_first_layer(hf):
     assert conv.kernel.grad.shape == wr.grad.shape
     assert float((conv.kernel.grad.cpu() - wr.grad).abs().max()) <= 2e-2 * float(wr.grad.abs().max())
     assert float((conv.bias.grad.cpu() - br.grad).abs().max()) <= 2e-2 * float(br.grad.abs().max())
+
+
+@pytest.mark.parametrize("cin", [5, 20, 70])
+def test_hexconv_tcgen05_forward_any_input_channel_count(hf, cin):
+    """Forced tcgen05 forward with input channels that are not a multiple of 16 (one ragged 16-channel slice; 70 = one
+    full 64-channel pass + a pass with 6 of 16 channels): bf16-rounded operands against the oracle."""
+    from HyGrid import _native as nv
+    torch.manual_seed(cin)
+    x = torch.randn(2, cin, 21, 140).bfloat16().float()
+    w = (torch.randn(32, cin, 1, 7) * 0.2).bfloat16().float()
+    b = torch.randn(32)
+    ref = HO.hexconv2d(x, w, b, 1, 2, 1, 1, 1, 1)
+    y = hf.hexconv2d(x.cuda(), w.cuda(), b.cuda(), 1, 2, 1, 1, 1, 1, algo=2)
+    assert nv.last_launch().startswith("hexconv_umma"), nv.last_launch()
+    assert float((y.cpu() - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
 
 
 def _pool_fuzz(n, seed):
