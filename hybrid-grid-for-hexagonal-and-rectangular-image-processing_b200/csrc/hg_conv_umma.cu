@@ -26,6 +26,7 @@
 //            by tcgen05.commit), tmem_full/tmem_empty per accumulator stage (MMA <-> epilogue).
 #include "hg_conv.cuh"
 #include "hg_ptx.cuh"
+#include <algorithm>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -56,7 +57,8 @@ struct UmmaParams {
                                      // [c_off, c_off + Cred) of cred_total and (accumulate) adds to the output of the previous pass
   int slots, bands, ctiles;
   int band;                      // output rows per work item
-  int rstages, raw_bytes;        // TMA variant: raw staging ring
+  int rstages, raw_bytes;        // TMA / cp.async variants: raw staging ring
+  int rpitch;                    // pixels of a row that are staged (<= kUmPW; narrow lattices stage only what their outputs read)
   long long items;
 };
 
@@ -72,11 +74,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <typename TIN, typename TOUT, bool TMA, bool ACC>   // ACC: add to the output of the previous channel-slice pass
+// SRC: 0 = LDG (loads straight into registers), 1 = TMA boxes, 2 = cp.async rows ("software TMA") into the raw ring
+template <typename TIN, typename TOUT, int SRC, bool ACC>   // ACC: add to the output of the previous channel-slice pass
 __global__ void __launch_bounds__(kUmThreads, 1)
 hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restrict__ in, const float* __restrict__ w,
                     const float* __restrict__ scale, const float* __restrict__ bias, TOUT* __restrict__ out, UmmaParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
+  constexpr bool TMA = SRC == 1, CPA = SRC == 2, RAW = SRC != 0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nkc = P.Cred >> 3;
   const int slot_bytes = P.Cred * kUmPW * 2;
@@ -96,26 +100,37 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
 
   // ---- one-time setup ---------------------------------------------------------------------------------
   // weights: fp32 [Cout][Cin][1][7] in global -> bf16 UMMA B image in shared memory
+  // A thread owns (reduction channel, output channel) pairs and moves the pair's 7 taps -- 28 contiguous bytes in global
+  // memory -- with independent loads, four pairs in flight.  (The first version walked the image element by element:
+  // one dependent L2 round trip and two integer divisions per element, 100 elements per thread at 64 -> 128 channels =
+  // 55 us before the first MMA -- more than the whole layer on a small lattice; measured with one-image launches.)
   {
     const int per_tap = P.Cred * P.Nout;
-    for (int e = tid; e < kTaps * per_tap; e += kUmThreads) {
-      const int k = e / per_tap, r = e - k * per_tap;
-      const int kc = r / (P.Nout * 8), r2 = r - kc * P.Nout * 8;
+    const int per_kc = P.Nout * 8;
+    __nv_bfloat16* wimg = reinterpret_cast<__nv_bfloat16*>(w_smem);
+#pragma unroll 4
+    for (int r = tid; r < per_tap; r += kUmThreads) {          // r = offset of the pair inside a tap image: [kc][n][j]
+      const int kc = r / per_kc, r2 = r - kc * per_kc;
       const int n = r2 >> 3, j = r2 & 7;
       const int red = P.c_off + kc * 8 + j;
       // (forward with Cin rounded up to 16 -- RGB first layers: the channels that do not exist carry zero weights)
-      const float v = red >= P.cred_total ? 0.f
-                      : P.transpose_w ? __ldg(w + ((size_t)red * P.Nout + n) * kTaps + k)          // w[co=red][ci=n][k]
-                                      : __ldg(w + ((size_t)n * P.cred_total + red) * kTaps + k);   // w[co=n][ci=red][k]
+      const bool real = red < P.cred_total;
+      const float* __restrict__ wp = w + (P.transpose_w ? ((size_t)red * P.Nout + n)           // w[co=red][ci=n][k]
+                                                        : ((size_t)n * P.cred_total + red)) * kTaps;   // w[co=n][ci=red][k]
+      float v[kTaps];
+#pragma unroll
+      for (int k = 0; k < kTaps; ++k) v[k] = real ? __ldg(wp + k) : 0.f;
       // per-output-channel scale (BN-inference affine of HexConvModule) folded into the weight image: free at run time
-      reinterpret_cast<__nv_bfloat16*>(w_smem)[e] = __float2bfloat16_rn(scale ? v * __ldg(scale + n) : v);
+      const float sc = scale ? __ldg(scale + n) : 1.f;
+#pragma unroll
+      for (int k = 0; k < kTaps; ++k) wimg[k * per_tap + r] = __float2bfloat16_rn(v[k] * sc);
     }
     for (int e = tid; e < ((P.Nout + 31) & ~31); e += kUmThreads) bias_s[e] = (P.has_bias && e < P.Nout) ? __ldg(bias + e) : 0.f;
   }
   if (tid == 0) {
     for (int s = 0; s < P.slots; ++s) { ptx::mbar_init(&full[s], kUmLoaders / 32); ptx::mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull[s], 1); ptx::mbar_init(&tempty[s], kUmEpiWarps * 32); }
-    for (int s = 0; s < P.rstages; ++s) { ptx::mbar_init(&rfull[s], 1); ptx::mbar_init(&rempty[s], kUmLoaders / 32); }
+    for (int s = 0; s < P.rstages; ++s) { ptx::mbar_init(&rfull[s], CPA ? kUmLoaders : 1); ptx::mbar_init(&rempty[s], kUmLoaders / 32); }
     if (TMA) ptx::prefetch_tensormap(&tmap);
     ptx::fence_barrier_init();
   }
@@ -134,8 +149,57 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
 
   if (warp < 8) {
     // ===== loaders ========================================================================================
-    const int ntasks = nkc * kUmPW;
+    // tasks = (8-channel group, pixel) pairs over the staged width P.rpitch; ring address of a task: [kc][p] 16-byte units
+    const int ntasks = nkc * P.rpitch;
     const size_t plane = (size_t)P.Hi * P.Wi;
+    // cp.async variant: this thread's own producer cursor runs rstages - 1 rows ahead of the row being converted
+    struct RowCur { long long item; int t, rows, r0, c0; const TIN* in_n; };
+    auto cur_set = [&](RowCur& c, long long item) {
+      c.item = item; c.t = 0;
+      if (item < P.items) {
+        const int n = (int)(item / per_n);
+        const int rem = (int)(item - (long long)n * per_n);
+        const int band = rem / P.ctiles, ct = rem - band * P.ctiles;
+        c.r0 = band * P.band; c.rows = min(P.band, P.Ho - c.r0); c.c0 = ct * kUmTile;
+        c.in_n = in + ((size_t)n * P.cred_total + P.c_off) * plane;
+      }
+    };
+    auto cur_next = [&](RowCur& c) { if (++c.t == c.rows + 2) cur_set(c, c.item + gridDim.x); };
+    long long prow = 0;                      // rows issued so far
+    auto cpa_issue = [&](const RowCur& c) {
+      const int rs = (int)(prow % P.rstages);
+      ptx::mbar_wait(&rempty[rs], (uint32_t)(((prow / P.rstages) & 1) ^ 1));    // every converter warp has the old row in registers
+      int i = c.r0 + P.row0 + c.t;
+      const bool row_frame = i >= -P.pad && i < P.Hi + P.pad;
+      if (P.pad_mode && row_frame) i = conv_pad_remap(i, P.Hi, P.pad_mode);
+      const bool row_in = i >= 0 && i < P.Hi;
+      const uint32_t dst0 = ptx::smem_u32(raw + (size_t)rs * P.raw_bytes);
+      for (int p = lane; p < P.rpitch; p += 32) {             // lanes along the row (coalesced), warps over the channels
+        int j = c.c0 + P.col0 + p;
+        const bool col_frame = j >= -P.pad && j < P.Wi + P.pad;
+        if (P.pad_mode && col_frame) j = conv_pad_remap(j, P.Wi, P.pad_mode);
+        const bool ok = row_in && j >= 0 && j < P.Wi;
+        const TIN* __restrict__ src = ok ? c.in_n + (size_t)i * P.Wi + j : in;
+        const int nch = ok ? min(P.Cred, P.cred_total - P.c_off) : 0;        // channels that exist (RGB: 3 of 16); the rest is zero fill
+        for (int ch = warp; ch < P.Cred; ch += kUmLoaders / 32)
+          ptx::cp_async_4(dst0 + (uint32_t)(ch * P.rpitch + p) * 4u, ch < nch ? src + (size_t)ch * plane : in, ch < nch ? 4u : 0u);
+      }
+      ptx::cp_async_mbar_arrive_noinc(&rfull[rs]);
+      ++prow;
+    };
+    RowCur pc;
+    if (CPA) {
+      cur_set(pc, blockIdx.x);
+      for (int d = 0; d < P.rstages - 1 && pc.item < P.items; ++d) { cpa_issue(pc); cur_next(pc); }
+    }
+    // the (channel group, pixel) of this thread's tasks never changes: worked out once (a division by the run-time
+    // width inside the row loop cost the C3 forward 10 %)
+    int tkc[kUmMaxQ], tp[kUmMaxQ];
+#pragma unroll
+    for (int q = 0; q < kUmMaxQ; ++q) {
+      const int task = tid + q * kUmLoaders;
+      tkc[q] = task / P.rpitch; tp[q] = task - tkc[q] * P.rpitch;
+    }
     long long lt = 0;                        // input rows produced so far (ring position)
     for (long long item = blockIdx.x; item < P.items; item += gridDim.x) {
       const int n = (int)(item / per_n);
@@ -153,8 +217,11 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
           r.x = pack_bf16(v[0], v[1]); r.y = pack_bf16(v[2], v[3]); r.z = pack_bf16(v[4], v[5]); r.w = pack_bf16(v[6], v[7]);
           return r;
         };
-        if (TMA) {
-          // raw row [Cred][PW] landed by TMA (halo rows / columns already zero-filled) -> registers
+        if (RAW) {
+          if (CPA) {
+            if constexpr (sizeof(TIN) == 4) { if (pc.item < P.items) { cpa_issue(pc); cur_next(pc); } }
+          }
+          // raw row [Cred][rpitch] landed by TMA / cp.async (halo rows / columns already zero-filled) -> registers
           const int rs = (int)(lt % P.rstages);
           ptx::mbar_wait(&rfull[rs], (uint32_t)((lt / P.rstages) & 1));
           const TIN* __restrict__ rp = reinterpret_cast<const TIN*>(raw + (size_t)rs * P.raw_bytes);
@@ -162,10 +229,10 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
           for (int q = 0; q < kUmMaxQ; ++q) {
             const int task = tid + q * kUmLoaders;
             if (task < ntasks) {
-              const int kc = task / kUmPW, p = task - kc * kUmPW;
+              const int kc = tkc[q], p = tp[q];
               float v[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = to_f32(rp[(kc * 8 + e) * kUmPW + p]);
+              for (int e = 0; e < 8; ++e) v[e] = to_f32(rp[(kc * 8 + e) * P.rpitch + p]);
               pk[q] = pack8(v);
             }
           }
@@ -185,7 +252,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
           for (int q = 0; q < kUmMaxQ; ++q) {
             const int task = tid + q * kUmLoaders;
             if (task < ntasks) {
-              const int kc = task / kUmPW, p = task - kc * kUmPW;
+              const int kc = tkc[q], p = tp[q];
               int j = c0 + P.col0 + p;
               const bool col_frame = j >= -P.pad && j < P.Wi + P.pad;
               if (P.pad_mode && col_frame) j = conv_pad_remap(j, P.Wi, P.pad_mode);
@@ -203,7 +270,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
 #pragma unroll
         for (int q = 0; q < kUmMaxQ; ++q) {
           const int task = tid + q * kUmLoaders;
-          if (task < ntasks) *reinterpret_cast<uint4*>(sb + (size_t)task * 16) = pk[q];      // task == kc * PW + p
+          if (task < ntasks) *reinterpret_cast<uint4*>(sb + (size_t)(tkc[q] * kUmPW + tp[q]) * 16) = pk[q];
         }
         ptx::fence_proxy_async_smem();       // generic-proxy smem writes -> visible to tcgen05.mma
         __syncwarp();
@@ -355,7 +422,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
         for (int t = 0; t < rows + 2; ++t, ++rt) {
           const int rs = (int)(rt % P.rstages);
           ptx::mbar_wait(&rempty[rs], (uint32_t)(((rt / P.rstages) & 1) ^ 1));
-          ptx::mbar_arrive_expect_tx(&rfull[rs], (uint32_t)P.raw_bytes);
+          ptx::mbar_arrive_expect_tx(&rfull[rs], (uint32_t)(P.Cred * P.rpitch * (int)sizeof(TIN)));
           ptx::tma_load_4d(raw + (size_t)rs * P.raw_bytes, &tmap, &rfull[rs], c0 + P.col0, r0 + P.row0 + t, P.c_off, n);
         }
       }
@@ -390,13 +457,16 @@ static bool umma_device_limits() {
   return true;
 }
 
-// ring slots (and raw stages for the TMA variant) that fit; 0 slots = does not fit
-static void umma_pick_stages(int Cred, int Nout, int in_elem, bool tma, int& slots, int& rstages, int& raw_bytes) {
+// ring slots (and raw stages for the TMA / cp.async variants) that fit; 0 slots = does not fit.  src: 0 LDG, 1 TMA, 2 cp.async
+static void umma_pick_stages(int Cred, int Nout, int in_elem, int src, int rpitch, int& slots, int& rstages, int& raw_bytes) {
   slots = rstages = raw_bytes = 0;
   if (!umma_device_limits()) return;
-  if (tma) {
-    raw_bytes = (int)ceil_div((int64_t)Cred * kUmPW * in_elem, 128) * 128;
-    for (int r = (in_elem == 2 ? 3 : 2); r >= 2 && !slots; --r)
+  if (src) {
+    raw_bytes = (int)ceil_div((int64_t)Cred * rpitch * in_elem, 128) * 128;
+    // TMA prefetches in hardware: two (float32) / three stages keep it busy.  The cp.async rows are issued by the converter
+    // threads themselves, rstages - 1 rows ahead: take up to four stages when the shared memory is there (small layers)
+    const int rmax = src == 2 ? 4 : (in_elem == 2 ? 3 : 2);
+    for (int r = rmax; r >= 2 && !slots; --r)
       for (int sl = 6; sl >= 4; --sl)
         if (umma_smem_bytes(Cred, Nout, sl, r, raw_bytes) <= (size_t)g_um_smem_max) { slots = sl; rstages = r; break; }
     if (!slots) raw_bytes = 0;
@@ -422,57 +492,62 @@ bool conv_umma_eligible(const hg_conv_desc* d, int op) {
   // channel contraction is dense enough to feed a 128 x Nout x Cred tile
   if (d->algo == 0 && ((op == 0 ? d->x_dtype : d->y_dtype) != HG_BF16 || Cred * Nout < 32 * 32)) return false;
   int slots, rst, rb;
-  umma_pick_stages((int)(Cred > 64 ? 64 : Cred), (int)Nout, 4, false, slots, rst, rb);
+  umma_pick_stages((int)(Cred > 64 ? 64 : Cred), (int)Nout, 4, 0, kUmPW, slots, rst, rb);
   return slots > 0;
 }
 
 static bool g_um_no_tma = [] { const char* e = getenv("HG_CONV_NO_TMA"); return e && e[0] == '1'; }();
 
-template <typename TIN, typename TOUT, bool TMA, bool ACC>
+static bool g_um_no_cpa = [] { const char* e = getenv("HG_CONV_NO_CPASYNC"); return e && e[0] == '1'; }();
+
+template <typename TIN, typename TOUT, int SRC, bool ACC>
 static int launch_umma_acc(const CUtensorMap& tmap, const void* in, const float* w, const float* scale, const float* bias, void* out,
                            const UmmaParams& P, cudaStream_t st) {
   const size_t smem = umma_smem_bytes(P.Cred, P.Nout, P.slots, P.rstages, P.raw_bytes);
-  auto kern = hexconv_umma_kernel<TIN, TOUT, TMA, ACC>;
+  auto kern = hexconv_umma_kernel<TIN, TOUT, SRC, ACC>;
   static SmemReservation reservation;
   cudaError_t e = reservation.reserve(kern, smem);
   if (e != cudaSuccess) { set_error("hexconv_umma: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e)); return (int)e; }
   long long grid = g_um_sms > 0 ? g_um_sms : 148;
   if (grid > P.items) grid = P.items;
   kern<<<(unsigned)grid, kUmThreads, smem, st>>>(tmap, (const TIN*)in, w, scale, bias, (TOUT*)out, P);
-  return finish_launch(TMA ? "hexconv_umma_tma" : "hexconv_umma");
+  return finish_launch(SRC == 1 ? "hexconv_umma_tma" : SRC == 2 ? "hexconv_umma_cpasync" : "hexconv_umma");
 }
 
-template <typename TIN, typename TOUT, bool TMA>
+template <typename TIN, typename TOUT, int SRC>
 static int launch_umma(const CUtensorMap& tmap, const void* in, const float* w, const float* scale, const float* bias, void* out,
                        const UmmaParams& P, cudaStream_t st) {
-  return P.accumulate ? launch_umma_acc<TIN, TOUT, TMA, true>(tmap, in, w, scale, bias, out, P, st)
-                      : launch_umma_acc<TIN, TOUT, TMA, false>(tmap, in, w, scale, bias, out, P, st);
+  return P.accumulate ? launch_umma_acc<TIN, TOUT, SRC, true>(tmap, in, w, scale, bias, out, P, st)
+                      : launch_umma_acc<TIN, TOUT, SRC, false>(tmap, in, w, scale, bias, out, P, st);
 }
 
-// Completes P (stage counts, column alignment) and launches the TMA variant when the input qualifies.
+// Completes P (stage counts, column alignment, staged width) and launches the variant the input qualifies for: TMA boxes
+// (16-byte aligned rows, zero frame), else cp.async rows (float32, zero frame or a frame read from the image), else plain loads.
 template <typename TIN, typename TOUT>
 static int launch_umma_any(const void* in, const float* w, const float* scale, const float* bias, void* out, UmmaParams P, cudaStream_t st) {
   alignas(64) CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   constexpr int es = (int)sizeof(TIN), A = 16 / es;
+  // a lattice narrower than one 128-pixel tile stages only the pixels its outputs read (tile + tap shifts + alignment slack)
+  P.rpitch = P.ctiles == 1 ? (int)std::min<int64_t>(kUmPW, ((int64_t)std::min(P.Wo, kUmTile) + 16 + 7) / 8 * 8) : kUmPW;
   PFN_encodeTiled enc = get_encode_tiled();
-  bool tma = !g_um_no_tma && enc != nullptr && P.pad_value == 0.f && P.pad_mode == 0 && P.c_off + P.Cred <= P.cred_total &&
+  bool tma = !g_um_no_tma && enc != nullptr && P.pad_value == 0.f && P.pad_mode == 0 &&      // (channels past cred_total -- RGB rounded up to 16 -- are TMA zero fill)
              ((int64_t)P.Wi * es) % 16 == 0 &&
              (reinterpret_cast<uintptr_t>(in) & 15) == 0;
   if (tma) {
     int slots, rst, rb;
-    umma_pick_stages(P.Cred, P.Nout, es, true, slots, rst, rb);
+    umma_pick_stages(P.Cred, P.Nout, es, 1, P.rpitch, slots, rst, rb);
     tma = slots > 0;
     if (tma) {
       // 16-byte aligned box origin: move the ring origin left by e0 pixels and the tap views right by e0
       const int col0a = (int)(floor((double)P.col0 / A)) * A, e0 = P.col0 - col0a;
       int smax = 0;
       for (int par = 0; par < 2; ++par) for (int k = 0; k < kTaps; ++k) smax = max(smax, P.sh[par][k] + e0);
-      if (kUmTile + smax > kUmPW) tma = false;
+      if (std::min(P.Wo, kUmTile) + smax > P.rpitch) tma = false;
       else {
         const cuuint64_t gdim[4] = {(cuuint64_t)P.Wi, (cuuint64_t)P.Hi, (cuuint64_t)P.cred_total, (cuuint64_t)P.N};
         const cuuint64_t gstr[3] = {(cuuint64_t)P.Wi * es, (cuuint64_t)P.Wi * P.Hi * es, (cuuint64_t)P.Wi * P.Hi * P.cred_total * es};
-        const cuuint32_t box[4] = {(cuuint32_t)kUmPW, 1, (cuuint32_t)P.Cred, 1};
+        const cuuint32_t box[4] = {(cuuint32_t)P.rpitch, 1, (cuuint32_t)P.Cred, 1};
         const cuuint32_t estr[4] = {1, 1, 1, 1};
         const CUtensorMapDataType dt = es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
         if (enc(&tmap, dt, 4, const_cast<void*>(in), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -482,16 +557,28 @@ static int launch_umma_any(const void* in, const float* w, const float* scale, c
           P.col0 = col0a;
           for (int par = 0; par < 2; ++par) for (int k = 0; k < kTaps; ++k) P.sh[par][k] += e0;
           P.slots = slots; P.rstages = rst; P.raw_bytes = rb;
-          return launch_umma<TIN, TOUT, true>(tmap, in, w, scale, bias, out, P, st);
+          return launch_umma<TIN, TOUT, 1>(tmap, in, w, scale, bias, out, P, st);
         }
       }
     }
   }
+  if constexpr (es == 4) {
+    // measured: rows of several tiles gain from the deeper prefetch (C3 at width 255: 2.48 -> 1.89 ms); on a lattice narrower
+    // than one tile the plain loads of the few staged pixels are quicker than the extra hop through the raw ring
+    if (!g_um_no_cpa && P.ctiles > 1 && (P.pad_value == 0.f || P.pad_mode != 0)) {
+      int slots, rst, rb;
+      umma_pick_stages(P.Cred, P.Nout, es, 2, P.rpitch, slots, rst, rb);
+      if (slots > 0) {
+        P.slots = slots; P.rstages = rst; P.raw_bytes = rb;
+        return launch_umma<TIN, TOUT, 2>(tmap, in, w, scale, bias, out, P, st);
+      }
+    }
+  }
   int rst, rb;
-  umma_pick_stages(P.Cred, P.Nout, es, false, P.slots, rst, rb);
+  umma_pick_stages(P.Cred, P.Nout, es, 0, P.rpitch, P.slots, rst, rb);
   P.rstages = 0; P.raw_bytes = 0;
   HG_REQUIRE(P.slots > 0, HG_E_UNSUPPORTED, "hexconv_umma: shared memory does not fit");
-  return launch_umma<TIN, TOUT, false>(tmap, in, w, scale, bias, out, P, st);
+  return launch_umma<TIN, TOUT, 0>(tmap, in, w, scale, bias, out, P, st);
 }
 
 static int dispatch_umma_pass(int in_dt, int out_dt, const void* in, const float* w, const float* scale, const float* bias, void* out,

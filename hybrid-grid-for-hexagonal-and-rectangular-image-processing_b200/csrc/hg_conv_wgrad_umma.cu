@@ -37,6 +37,8 @@ constexpr int kWuThreads = 480;               // 12 converter warps, MMA issuer 
 constexpr int kWuBand = 32;
 constexpr int kWuMaxQ = 3;                   // ceil(8 * 144 / 384)
 constexpr int kWuTaps = 7;
+constexpr int kWuStagePitch = kWuTaps * 32 + 1;   // final epilogue: one gw row chunk ([32 ci][7 taps]) per accumulator row, + 1 word
+constexpr int kWuStageBytes = 4 * 32 * kWuStagePitch * 4;   // four epilogue warps x 32 rows (reuses the ring memory)
 
 struct WgParams {
   int N, Cin, Cout, H, W, Ho, Wo;
@@ -48,7 +50,10 @@ struct WgParams {
   int pad_mode;                  // 1 reflect / 2 replicate / 3 circular frame, resolved by the x loader (LDG variant)
   int xslots, gslots, bands, ctiles, has_bias;
   int band;                      // output rows per work item
-  int rstages, raw_bytes;        // TMA variant
+  int rstages, raw_bytes;        // TMA / cp.async variants
+  int epi_direct;
+  int xpitch, gpitch, ksteps;    // pixels of an x / gy row that are staged and 16-pixel reduction steps per row: a lattice narrower
+                                 // than one 128-pixel tile stages and multiplies only ceil(Wo / 16) steps (gy is zero beyond Wo)
   int m64;                       // Cout <= 64: UMMA M = 64 (half the A-operand shared-memory reads of an M = 128 view)
   int cin_total, ci_off, cout_total, co_off;   // this launch covers x channels [ci_off, ci_off + Cin) and gy channels [co_off, co_off + Cout)
   long long items;
@@ -70,19 +75,26 @@ __host__ __device__ constexpr uint32_t wu_idesc(int M, int N) {   // bf16 x bf16
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <typename TX, typename TG, bool TMA>
+// SRC: 0 = LDG (loads straight into registers), 1 = TMA boxes, 2 = cp.async rows ("software TMA") into the raw ring
+// FULL: rows of whole 128-pixel tiles -- staged widths, reduction steps and the task -> (channel group, pixel) map are
+// compile-time constants (the run-time versions cost the C3 layer 3 %)
+template <typename TX, typename TG, int SRC, bool FULL>
 __global__ void __launch_bounds__(kWuThreads, 1)
 hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap gmap,
                           const TX* __restrict__ x, const TG* __restrict__ gy, float* __restrict__ gw, float* __restrict__ gb,
                           WgParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
+  constexpr bool TMA = SRC == 1, CPA = SRC == 2, RAW = SRC != 0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int xpitch = FULL ? kWuPW : P.xpitch, gpitch = FULL ? kWuTile : P.gpitch, ksteps = FULL ? kWuTile / 16 : P.ksteps;
   const int gslot_bytes = P.Cout * kWuTile * 2;         // [Cout/8][128 px][16 B]
   const int xslot_bytes = P.Cin * kWuPW * 2;            // [Cin/8][PW px][16 B]
   unsigned char* gring = smem;                          // gy ring first: its M = 128 view may run into the x ring
   unsigned char* xring = gring + P.gslots * gslot_bytes;
   unsigned char* raw = xring + P.xslots * xslot_bytes;  // [rstage] raw rows (TMA variant)
-  unsigned char* ones = raw + (size_t)P.rstages * P.raw_bytes;   // 512 B of bf16 1.0 (bias accumulator operand)
+  const int front = P.gslots * gslot_bytes + P.xslots * xslot_bytes + P.rstages * P.raw_bytes;
+  unsigned char* ones = smem + max(front, kWuStageBytes);        // 512 B of bf16 1.0 (bias accumulator operand); the front
+                                                                 // region doubles as the final epilogue's staging space
   uint64_t* bars = reinterpret_cast<uint64_t*>(ones + 512);
   uint64_t* xfull = bars;                   // [xslots]   converters -> MMA   (one arrival per converter warp)
   uint64_t* xempty = xfull + P.xslots;      // [xslots]   MMA commit -> converters
@@ -97,7 +109,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
   if (tid == 0) {
     for (int s = 0; s < P.xslots; ++s) { ptx::mbar_init(&xfull[s], kWuConvWarps); ptx::mbar_init(&xempty[s], 2); }   // one commit per issuer
     for (int s = 0; s < P.gslots; ++s) { ptx::mbar_init(&gfull[s], kWuConvWarps); ptx::mbar_init(&gempty[s], 2); }
-    for (int s = 0; s < P.rstages; ++s) { ptx::mbar_init(&rfull[s], 1); ptx::mbar_init(&rempty[s], kWuConvWarps); }
+    for (int s = 0; s < P.rstages; ++s) { ptx::mbar_init(&rfull[s], CPA ? kWuConv : 1); ptx::mbar_init(&rempty[s], kWuConvWarps); }
     ptx::mbar_init(done, 2);
     if (TMA) { ptx::prefetch_tensormap(&xmap); ptx::prefetch_tensormap(&gmap); }
     ptx::fence_barrier_init();
@@ -114,7 +126,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
   if (warp < kWuConvWarps) {
     // ===== converters ========================================================================================
     const size_t xplane = (size_t)P.H * P.W, gplane = (size_t)P.Ho * P.Wo;
-    const int xtasks = (P.Cin >> 3) * kWuPW, gtasks = (P.Cout >> 3) * kWuTile;
+    const int xtasks = (P.Cin >> 3) * xpitch, gtasks = (P.Cout >> 3) * gpitch;
     uint32_t xs = 0, xph = 0, gs = 0, gph = 0, rs = 0, rph = 0;      // ring positions / parities
     auto publish = [&](uint64_t* bar) {     // all of this warp's writes fenced, then one arrival per warp
       ptx::fence_proxy_async_smem();
@@ -138,20 +150,96 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
       pk.x = wu_pack(v[0], v[1]); pk.y = wu_pack(v[2], v[3]); pk.z = wu_pack(v[4], v[5]); pk.w = wu_pack(v[6], v[7]);
       return pk;
     };
+    // ---- cp.async variant: every converter thread copies its share of the raw rows rstages - 1 rows ahead of the row
+    // being converted.  The raw rows of an item come in the order x0, x1, (x[rr + 2], gy[rr]) for rr = 0 .. rows - 1.
+    struct RawCur { long long item; int step, rows, r0, c0; const TX* xn; const TG* gn; };
+    auto cur_set = [&](RawCur& c, long long item) {
+      c.item = item; c.step = 0;
+      if (item < P.items) {
+        const int n = (int)(item / per_n);
+        const int rem = (int)(item - (long long)n * per_n);
+        const int band = rem / P.ctiles, ct = rem - band * P.ctiles;
+        c.r0 = band * P.band; c.rows = min(P.band, P.Ho - c.r0); c.c0 = ct * kWuTile;
+        c.xn = x + ((size_t)n * P.cin_total + P.ci_off) * xplane;
+        c.gn = gy + ((size_t)n * P.cout_total + P.co_off) * gplane;
+      }
+    };
+    uint32_t prs = 0, prph = 0;              // producer side position in the raw ring
+    auto cpa_issue = [&](RawCur& c) {
+      ptx::mbar_wait(&rempty[prs], prph ^ 1);                 // every converter warp has the stage's old row in registers
+      const uint32_t dst0 = ptx::smem_u32(raw + (size_t)prs * P.raw_bytes);
+      const bool is_g = c.step >= 2 && ((c.step - 2) & 1);
+      if (!is_g) {
+        int i = c.r0 + P.row0 + (c.step < 2 ? c.step : 2 + ((c.step - 2) >> 1));
+        const bool row_frame = i >= -P.pad && i < P.H + P.pad;
+        if (P.pad_mode && row_frame) i = conv_pad_remap(i, P.H, P.pad_mode);
+        const bool row_in = i >= 0 && i < P.H;
+        for (int p = lane; p < xpitch; p += 32) {           // lanes along the row (coalesced), warps over the channels
+          int j = c.c0 + P.col0 + p;
+          const bool col_frame = j >= -P.pad && j < P.W + P.pad;
+          if (P.pad_mode && col_frame) j = conv_pad_remap(j, P.W, P.pad_mode);
+          const bool ok = row_in && j >= 0 && j < P.W;
+          const TX* __restrict__ src = ok ? c.xn + (size_t)i * P.W + j : x;
+          const int nch = ok ? min(P.Cin, P.cin_total - P.ci_off) : 0;       // channels that exist; the rest is zero fill
+          for (int ch = warp; ch < P.Cin; ch += kWuConvWarps)
+            ptx::cp_async_4(dst0 + (uint32_t)(ch * xpitch + p) * 4u, ch < nch ? src + (size_t)ch * xplane : x, ch < nch ? 4u : 0u);
+        }
+      } else {
+        const int R = c.r0 + ((c.step - 2) >> 1);
+        for (int p = lane; p < gpitch; p += 32) {
+          const int cc = c.c0 + p;
+          const bool ok = cc < P.Wo;
+          const TG* __restrict__ src = ok ? c.gn + (size_t)R * P.Wo + cc : gy;
+          for (int ch = warp; ch < P.Cout; ch += kWuConvWarps)
+            ptx::cp_async_4(dst0 + (uint32_t)(ch * gpitch + p) * 4u, ok ? src + (size_t)ch * gplane : gy, ok ? 4u : 0u);
+        }
+      }
+      ptx::cp_async_mbar_arrive_noinc(&rfull[prs]);
+      if (++prs == (uint32_t)P.rstages) { prs = 0; prph ^= 1; }
+      if (++c.step == 2 + 2 * c.rows) cur_set(c, c.item + gridDim.x);
+    };
+    RawCur pc;
+    auto cpa_ahead = [&]() {
+      if constexpr (CPA && sizeof(TX) == 4 && sizeof(TG) == 4) { if (pc.item < P.items) cpa_issue(pc); }
+    };
+    if constexpr (CPA && sizeof(TX) == 4 && sizeof(TG) == 4) {
+      cur_set(pc, blockIdx.x);
+      for (int d = 0; d < P.rstages - 1 && pc.item < P.items; ++d) cpa_issue(pc);
+    }
+    // the (channel group, pixel) of this thread's tasks never changes: narrow lattices work it out once (run-time widths),
+    // full tiles divide by constants on the spot
+    int xkc_[kWuMaxQ], xp_[kWuMaxQ], gkc_[2 * kWuMaxQ], gp_[2 * kWuMaxQ];
+    if (!FULL) {
+#pragma unroll
+      for (int q = 0; q < kWuMaxQ; ++q) {
+        const int task = tid + q * kWuConv;
+        xkc_[q] = task / xpitch; xp_[q] = task - xkc_[q] * xpitch;
+      }
+#pragma unroll
+      for (int q = 0; q < 2 * kWuMaxQ; ++q) {
+        const int task = tid + q * kWuConv;
+        gkc_[q] = task / gpitch; gp_[q] = task - gkc_[q] * gpitch;
+      }
+    }
+    auto xkc = [&](int q) { return FULL ? (tid + q * kWuConv) / kWuPW : xkc_[q]; };
+    auto xp = [&](int q) { return FULL ? (tid + q * kWuConv) % kWuPW : xp_[q]; };
+    auto gkc = [&](int q) { return FULL ? (tid + q * kWuConv) / kWuTile : gkc_[q]; };
+    auto gp = [&](int q) { return FULL ? (tid + q * kWuConv) % kWuTile : gp_[q]; };
     auto load_x = [&](const TX* __restrict__ xn, int i, int c0) {    // i: frame row, remapped below for the non-constant modes
       unsigned char* sb = xring + (size_t)xs * xslot_bytes;
       uint4 pk[kWuMaxQ];
-      if (TMA) {
+      if (RAW) {
+        cpa_ahead();
         ptx::mbar_wait(&rfull[rs], rph);
         const TX* __restrict__ rp = reinterpret_cast<const TX*>(raw + (size_t)rs * P.raw_bytes);
 #pragma unroll
         for (int q = 0; q < kWuMaxQ; ++q) {
           const int task = tid + q * kWuConv;
           if (task < xtasks) {
-            const int kc = task / kWuPW, p = task - kc * kWuPW;
+            const int kc = xkc(q), p = xp(q);
             float v[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = to_f32(rp[(kc * 8 + e) * kWuPW + p]);
+            for (int e = 0; e < 8; ++e) v[e] = to_f32(rp[(kc * 8 + e) * xpitch + p]);
             pk[q] = pack8(v);
           }
         }
@@ -166,7 +254,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
         for (int q = 0; q < kWuMaxQ; ++q) {
           const int task = tid + q * kWuConv;
           if (task < xtasks) {
-            const int kc = task / kWuPW, p = task - kc * kWuPW;
+            const int kc = xkc(q), p = xp(q);
             int j = c0 + P.col0 + p;
             const bool col_frame = j >= -P.pad && j < P.W + P.pad;
             if (P.pad_mode && col_frame) j = conv_pad_remap(j, P.W, P.pad_mode);
@@ -184,7 +272,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
 #pragma unroll
       for (int q = 0; q < kWuMaxQ; ++q) {
         const int task = tid + q * kWuConv;
-        if (task < xtasks) *reinterpret_cast<uint4*>(sb + (size_t)task * 16) = pk[q];
+        if (task < xtasks) *reinterpret_cast<uint4*>(sb + (size_t)(xkc(q) * kWuPW + xp(q)) * 16) = pk[q];
       }
       publish(&xfull[xs]);
       if (++xs == (uint32_t)P.xslots) { xs = 0; xph ^= 1; }
@@ -192,19 +280,23 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
     auto load_g = [&](const TG* __restrict__ gn, int R, int c0) {
       unsigned char* sb = gring + (size_t)gs * gslot_bytes;
       bool waited = false;
-      for (int base = 0; base < gtasks; base += kWuMaxQ * kWuConv) {   // Cout = 128 needs two passes
+      if (RAW) cpa_ahead();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {                           // Cout = 128 needs two passes
+        const int base = half * kWuMaxQ * kWuConv;
+        if (base >= gtasks) break;
         uint4 pk[kWuMaxQ];
-        if (TMA) {
+        if (RAW) {
           if (base == 0) ptx::mbar_wait(&rfull[rs], rph);
           const TG* __restrict__ rp = reinterpret_cast<const TG*>(raw + (size_t)rs * P.raw_bytes);
 #pragma unroll
           for (int q = 0; q < kWuMaxQ; ++q) {
             const int task = base + tid + q * kWuConv;
             if (task < gtasks) {
-              const int kc = task / kWuTile, p = task - kc * kWuTile;
+              const int kc = gkc(half * kWuMaxQ + q), p = gp(half * kWuMaxQ + q);
               float v[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = to_f32(rp[(kc * 8 + e) * kWuTile + p]);
+              for (int e = 0; e < 8; ++e) v[e] = to_f32(rp[(kc * 8 + e) * gpitch + p]);
               pk[q] = pack8(v);
             }
           }
@@ -214,7 +306,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
           for (int q = 0; q < kWuMaxQ; ++q) {
             const int task = base + tid + q * kWuConv;
             if (task < gtasks) {
-              const int kc = task / kWuTile, p = task - kc * kWuTile;
+              const int kc = gkc(half * kWuMaxQ + q), p = gp(half * kWuMaxQ + q);
               const int c = c0 + p;
               const TG* __restrict__ src = gn + (size_t)(kc * 8) * gplane + (size_t)R * P.Wo + c;
               float v[8];
@@ -228,7 +320,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
 #pragma unroll
         for (int q = 0; q < kWuMaxQ; ++q) {
           const int task = base + tid + q * kWuConv;
-          if (task < gtasks) *reinterpret_cast<uint4*>(sb + (size_t)task * 16) = pk[q];
+          if (task < gtasks) *reinterpret_cast<uint4*>(sb + (size_t)(gkc(half * kWuMaxQ + q) * kWuTile + gp(half * kWuMaxQ + q)) * 16) = pk[q];
         }
       }
       publish(&gfull[gs]);
@@ -250,31 +342,65 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
     }
     if (warp >= 8) {
       // ===== final epilogue (warps 8-11): TMEM partials -> fp32 atomics ======================================
+      // A TMEM lane is an output channel, so a warp-wide atomic straight from the registers would touch 32 rows of gw
+      // (32 sectors per instruction; measured: ~230 cycles each, 50 us for the 448 of a 64 -> 128 layer -- the whole
+      // kernel on a small lattice).  Each warp transposes its rows through shared memory instead (the rings are dead
+      // once `done` has completed): a row of gw holds [ci][tap] contiguously, so the warp then adds 32 consecutive
+      // floats per instruction (4 sectors).  Row pitch 7 * 32 + 1 words: conflict-free both ways.
       const int q4 = warp & 3;
       // accumulator row (= output channel) held by this thread's TMEM lane.  M = 128: row == lane.  M = 64
       // (cta_group::1): row r sits in lane 32 * (r / 16) + r % 16, i.e. 16 rows in the lower half of every
       // 32-lane quadrant (measured on B200 against the oracle: the "first 64 lanes" reading is wrong).
-      int co = q4 * 32 + lane;
-      if (P.m64) co = lane < 16 ? q4 * 16 + lane : (1 << 30);
+      const int rows_q = P.m64 ? 16 : 32;                       // accumulator rows per TMEM lane quadrant
+      const int co0 = q4 * rows_q;
+      float* stg = reinterpret_cast<float*>(smem) + (size_t)q4 * 32 * kWuStagePitch;
       ptx::mbar_wait(done, 0);
       ptx::tc_fence_after_sync();
-      for (int k = 0; k < kWuTaps; ++k) {
-        for (int cb = 0; cb < P.Cin; cb += 32) {
+      if (P.epi_direct) {                   // A/B switch (HG_WU_EPI_DIRECT=1): adds straight from the registers, 32 gw rows per instruction
+        const int co = lane < rows_q ? co0 + lane : (1 << 30);
+        for (int k = 0; k < kWuTaps; ++k)
+          for (int cb = 0; cb < P.Cin; cb += 32) {
+            uint32_t v[32];
+            ptx::tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(k * P.Cin + cb), v);
+            ptx::tmem_ld_wait();
+            if (co < P.Cout) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (cb + j < P.Cin && P.ci_off + cb + j < P.cin_total)
+                  atomicAdd(gw + ((size_t)(P.co_off + co) * P.cin_total + P.ci_off + cb + j) * kWuTaps + k, __uint_as_float(v[j]));
+            }
+          }
+      } else
+      for (int cb = 0; cb < P.Cin; cb += 32) {
+        const int cwv = max(0, min(min(32, P.Cin - cb), P.cin_total - P.ci_off - cb));   // channels of this chunk that exist
+        for (int k = 0; k < kWuTaps; ++k) {
           uint32_t v[32];
           ptx::tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(k * P.Cin + cb), v);
           ptx::tmem_ld_wait();
-          if (co < P.Cout) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (cb + j < P.Cin && P.ci_off + cb + j < P.cin_total)
-                atomicAdd(gw + ((size_t)(P.co_off + co) * P.cin_total + P.ci_off + cb + j) * kWuTaps + k, __uint_as_float(v[j]));
-          }
+          for (int j = 0; j < 32; ++j) stg[lane * kWuStagePitch + j * kWuTaps + k] = __uint_as_float(v[j]);
         }
+        __syncwarp();
+        const int run = kWuTaps * cwv;                          // contiguous floats of one gw row in this chunk
+        // every CTA adds to the same gw: each CTA starts at a different 32-float unit of the block and wraps around, or all
+        // of them would queue on the same L2 lines at the same time (measured at the C3 shape, every CTA walking the rows in
+        // the same order: 0.79 -> 0.92 ms)
+        const int nrows = min(rows_q, P.Cout - co0);
+        const int upr = (run + 31) >> 5;                        // units per row
+        const int units = nrows * upr;
+        for (int u0 = 0; u0 < units; ++u0) {
+          const int u = (u0 + (int)blockIdx.x * 5) % units;
+          const int c = u / upr, t = (u - c * upr) * 32 + lane;
+          if (t < run)
+            atomicAdd(gw + ((size_t)(P.co_off + co0 + c) * P.cin_total + P.ci_off + cb) * kWuTaps + t, stg[c * kWuStagePitch + t]);
+        }
+        __syncwarp();
       }
       if (P.has_bias) {
         uint32_t v[32];
         ptx::tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)bias_col, v);
         ptx::tmem_ld_wait();
+        const int co = lane < rows_q ? co0 + lane : (1 << 30);
         if (co < P.Cout) atomicAdd(gb + P.co_off + co, __uint_as_float(v[0]));
       }
     }
@@ -318,16 +444,23 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
             uint32_t b_lo = (ra == 0 ? xb0 : (ra == 1 ? xb1 : xb2)) + (uint32_t)P.sh[par][k] + lo_const;
             uint32_t a_lo = a_lo0;
             const uint32_t d_tmem = tmem_base + (uint32_t)(k * P.Cin);
+            if (FULL) {                                       // full tiles: straight-line issue
 #pragma unroll
-            for (int j = 0; j < kWuTile / 16; ++j) {
-              ptx::umma_bf16(d_tmem, ((uint64_t)g_hi << 32) | a_lo, ((uint64_t)x_hi << 32) | b_lo, idesc, started | (uint32_t)j);
-              a_lo += 16; b_lo += 16;                       // 16 pixels = 256 bytes
+              for (int j = 0; j < kWuTile / 16; ++j) {
+                ptx::umma_bf16(d_tmem, ((uint64_t)g_hi << 32) | a_lo, ((uint64_t)x_hi << 32) | b_lo, idesc, started | (uint32_t)j);
+                a_lo += 16; b_lo += 16;                       // 16 pixels = 256 bytes
+              }
+            } else {
+              for (int j = 0; j < ksteps; ++j) {
+                ptx::umma_bf16(d_tmem, ((uint64_t)g_hi << 32) | a_lo, ((uint64_t)x_hi << 32) | b_lo, idesc, started | (uint32_t)j);
+                a_lo += 16; b_lo += 16;
+              }
             }
           }
           if (do_bias) {
             uint32_t a_lo = a_lo0;
-#pragma unroll
-            for (int j = 0; j < kWuTile / 16; ++j) {
+#pragma unroll 8
+            for (int j = 0; j < ksteps; ++j) {
               ptx::umma_bf16(tmem_base + (uint32_t)bias_col, ((uint64_t)g_hi << 32) | a_lo, od, idesc_b, started | (uint32_t)j);
               a_lo += 16;
             }
@@ -359,7 +492,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
         ptx::tma_load_4d(raw + (size_t)rs * P.raw_bytes, m, &rfull[rs], c, r, ch, n);
         if (++rs == (uint32_t)P.rstages) { rs = 0; rph ^= 1; }
       };
-      const uint32_t xbytes = (uint32_t)(P.Cin * kWuPW * (int)sizeof(TX)), gbytes = (uint32_t)(P.Cout * kWuTile * (int)sizeof(TG));
+      const uint32_t xbytes = (uint32_t)(P.Cin * xpitch * (int)sizeof(TX)), gbytes = (uint32_t)(P.Cout * gpitch * (int)sizeof(TG));
       for (long long item = blockIdx.x; item < P.items; item += gridDim.x) {
         const int n = (int)(item / per_n);
         const int rem = (int)(item - (long long)n * per_n);
@@ -388,7 +521,8 @@ static int g_wu_sms = 0, g_wu_smem_max = 0;
 static bool g_wu_no_tma = [] { const char* e = getenv("HG_CONV_NO_TMA"); return e && e[0] == '1'; }();
 
 static size_t wu_smem_bytes(int Cin, int Cout, int xslots, int gslots, int rstages, int raw_bytes) {
-  return (size_t)gslots * Cout * kWuTile * 2 + (size_t)xslots * Cin * kWuPW * 2 + (size_t)rstages * raw_bytes + 512 +
+  const size_t front = (size_t)gslots * Cout * kWuTile * 2 + (size_t)xslots * Cin * kWuPW * 2 + (size_t)rstages * raw_bytes;
+  return (front > (size_t)kWuStageBytes ? front : (size_t)kWuStageBytes) + 512 +
          (size_t)(2 * xslots + 2 * gslots + 2 * rstages + 1) * 8 + 16;
 }
 
@@ -408,14 +542,16 @@ static bool wu_view_fits(int Cin, int Cout, int xslots) {
   return (size_t)(16 - Cout / 8) * kWuTile * 16 <= (size_t)xslots * Cin * kWuPW * 2;
 }
 
-static bool wu_pick(int Cin, int Cout, int xes, int ges, bool tma, int& xslots, int& gslots, int& rstages, int& raw_bytes) {
+// src: 0 LDG, 1 TMA, 2 cp.async; xpitch / gpitch: staged pixels per x / gy row
+static bool wu_pick(int Cin, int Cout, int xes, int ges, int src, int xpitch, int gpitch, int& xslots, int& gslots, int& rstages, int& raw_bytes) {
   xslots = gslots = rstages = raw_bytes = 0;
   if (!wu_limits()) return false;
-  if (tma) {
-    const int64_t xb = (int64_t)Cin * kWuPW * xes, gb = (int64_t)Cout * kWuTile * ges;
+  if (src) {
+    const int64_t xb = (int64_t)Cin * xpitch * xes, gb = (int64_t)Cout * gpitch * ges;
     raw_bytes = (int)ceil_div(xb > gb ? xb : gb, 128) * 128;
   }
-  for (int r = tma ? 3 : 0; r >= (tma ? 2 : 0); --r)
+  // the cp.async rows are issued by the converter threads themselves, rstages - 1 rows ahead: up to five stages on small layers
+  for (int r = src == 2 ? 5 : src ? 3 : 0; r >= (src ? 2 : 0); --r)
     for (int g = 3; g >= 2; --g)
       for (int xsl = 6; xsl >= 4; --xsl)
         if (wu_smem_bytes(Cin, Cout, xsl, g, r, raw_bytes) <= (size_t)g_wu_smem_max && wu_view_fits(Cin, Cout, xsl)) {
@@ -436,25 +572,32 @@ bool conv_wgrad_umma_eligible(const hg_conv_desc* d) {
   const int64_t cin16 = (d->Cin + 15) / 16 * 16;
   if (d->Cout % 8 != 0 || d->Cout < 8 || d->Cout > 1024) return false;
   int a, b, c, e;
-  if (!wu_pick((int)(cin16 > 64 ? 64 : cin16), (int)(d->Cout > 128 ? 128 : d->Cout), 4, 4, false, a, b, c, e)) return false;
-  if (cin16 > 64 && cin16 % 64 != 0 && !wu_pick((int)(cin16 % 64), (int)(d->Cout > 128 ? 128 : d->Cout), 4, 4, false, a, b, c, e)) return false;
-  if (d->Cout > 128 && d->Cout % 128 != 0 && !wu_pick((int)(cin16 > 64 ? 64 : cin16), (int)(d->Cout % 128), 4, 4, false, a, b, c, e)) return false;
+  if (!wu_pick((int)(cin16 > 64 ? 64 : cin16), (int)(d->Cout > 128 ? 128 : d->Cout), 4, 4, 0, kWuPW, kWuTile, a, b, c, e)) return false;
+  if (cin16 > 64 && cin16 % 64 != 0 && !wu_pick((int)(cin16 % 64), (int)(d->Cout > 128 ? 128 : d->Cout), 4, 4, 0, kWuPW, kWuTile, a, b, c, e)) return false;
+  if (d->Cout > 128 && d->Cout % 128 != 0 && !wu_pick((int)(cin16 > 64 ? 64 : cin16), (int)(d->Cout % 128), 4, 4, 0, kWuPW, kWuTile, a, b, c, e)) return false;
   if (d->algo == 0 && (d->x_dtype != HG_BF16 || d->Cin * d->Cout < 32 * 32)) return false;
   return true;
 }
 
-template <typename TX, typename TG, bool TMA>
-static int launch_wu(const CUtensorMap& xmap, const CUtensorMap& gmap, const void* x, const void* gy, float* gw, float* gb,
+template <typename TX, typename TG, int SRC, bool FULL>
+static int launch_wu_full(const CUtensorMap& xmap, const CUtensorMap& gmap, const void* x, const void* gy, float* gw, float* gb,
                      const WgParams& P, cudaStream_t st) {
   const size_t smem = wu_smem_bytes(P.Cin, P.Cout, P.xslots, P.gslots, P.rstages, P.raw_bytes);
-  auto kern = hexconv_wgrad_umma_kernel<TX, TG, TMA>;
+  auto kern = hexconv_wgrad_umma_kernel<TX, TG, SRC, FULL>;
   static SmemReservation reservation;
   cudaError_t e = reservation.reserve(kern, smem);
   if (e != cudaSuccess) { set_error("hexconv_wgrad_umma: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e)); return (int)e; }
   long long grid = g_wu_sms > 0 ? g_wu_sms : 148;
   if (grid > P.items) grid = P.items;
   kern<<<(unsigned)grid, kWuThreads, smem, st>>>(xmap, gmap, (const TX*)x, (const TG*)gy, gw, gb, P);
-  return finish_launch(TMA ? "hexconv_wgrad_umma_tma" : "hexconv_wgrad_umma");
+  return finish_launch(SRC == 1 ? "hexconv_wgrad_umma_tma" : SRC == 2 ? "hexconv_wgrad_umma_cpasync" : "hexconv_wgrad_umma");
+}
+
+template <typename TX, typename TG, int SRC>
+static int launch_wu(const CUtensorMap& xmap, const CUtensorMap& gmap, const void* x, const void* gy, float* gw, float* gb,
+                     const WgParams& P, cudaStream_t st) {
+  return P.ksteps == kWuTile / 16 ? launch_wu_full<TX, TG, SRC, true>(xmap, gmap, x, gy, gw, gb, P, st)
+                                  : launch_wu_full<TX, TG, SRC, false>(xmap, gmap, x, gy, gw, gb, P, st);
 }
 
 template <typename T>
@@ -469,38 +612,54 @@ static bool wu_encode(PFN_encodeTiled enc, CUtensorMap* m, const void* base, int
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+static bool g_wu_no_cpa = [] { const char* e = getenv("HG_CONV_NO_CPASYNC"); return e && e[0] == '1'; }();
+
 template <typename TX, typename TG>
 static int launch_wu_any(const void* x, const void* gy, float* gw, float* gb, WgParams P, cudaStream_t st) {
   alignas(64) CUtensorMap xmap, gmap;
   memset(&xmap, 0, sizeof(xmap));
   memset(&gmap, 0, sizeof(gmap));
   constexpr int xes = (int)sizeof(TX), ges = (int)sizeof(TG), A = 16 / xes;
+  // a lattice narrower than one tile: reduce over ceil(Wo / 16) 16-pixel steps only; gy is staged (zero beyond Wo) for exactly
+  // those pixels and x for the same plus the tap shifts and the alignment slack -- every staged pixel is written every row
+  P.ksteps = P.ctiles == 1 ? (int)ceil_div(P.Wo < kWuTile ? P.Wo : kWuTile, 16) : kWuTile / 16;
+  P.gpitch = 16 * P.ksteps;
+  P.xpitch = P.ksteps == kWuTile / 16 ? kWuPW : P.gpitch + 16;
   PFN_encodeTiled enc = get_encode_tiled();
-  bool tma = !g_wu_no_tma && enc != nullptr && P.pad_value == 0.f && P.pad_mode == 0 && P.ci_off + P.Cin <= P.cin_total &&
+  bool tma = !g_wu_no_tma && enc != nullptr && P.pad_value == 0.f && P.pad_mode == 0 &&      // (channels past cin_total -- RGB rounded up to 16 -- are TMA zero fill)
              ((int64_t)P.W * xes) % 16 == 0 && ((int64_t)P.Wo * ges) % 16 == 0 &&
              (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(gy) & 15) == 0;
   if (tma) {
     int xs_, gs_, rst, rb;
-    tma = wu_pick(P.Cin, P.Cout, xes, ges, true, xs_, gs_, rst, rb);
+    tma = wu_pick(P.Cin, P.Cout, xes, ges, 1, P.xpitch, P.gpitch, xs_, gs_, rst, rb);
     if (tma) {
       const int col0a = (int)(floor((double)P.col0 / A)) * A, e0 = P.col0 - col0a;
       int smax = 0;
       for (int par = 0; par < 2; ++par) for (int k = 0; k < kWuTaps; ++k) smax = max(smax, P.sh[par][k] + e0);
-      if (kWuTile + smax > kWuPW || !wu_encode<TX>(enc, &xmap, x, P.W, P.H, P.cin_total, P.N, kWuPW, P.Cin) ||
-          !wu_encode<TG>(enc, &gmap, gy, P.Wo, P.Ho, P.cout_total, P.N, kWuTile, P.Cout))
+      if (P.gpitch + smax > P.xpitch || !wu_encode<TX>(enc, &xmap, x, P.W, P.H, P.cin_total, P.N, P.xpitch, P.Cin) ||
+          !wu_encode<TG>(enc, &gmap, gy, P.Wo, P.Ho, P.cout_total, P.N, P.gpitch, P.Cout))
         tma = false;
       else {
         P.col0 = col0a;
         for (int par = 0; par < 2; ++par) for (int k = 0; k < kWuTaps; ++k) P.sh[par][k] += e0;
         P.xslots = xs_; P.gslots = gs_; P.rstages = rst; P.raw_bytes = rb;
-        return launch_wu<TX, TG, true>(xmap, gmap, x, gy, gw, gb, P, st);
+        return launch_wu<TX, TG, 1>(xmap, gmap, x, gy, gw, gb, P, st);
+      }
+    }
+  }
+  if constexpr (xes == 4 && ges == 4) {
+    if (!g_wu_no_cpa && P.ctiles > 1 && (P.pad_value == 0.f || P.pad_mode != 0)) {     // see hg_conv_umma.cu: wide rows only
+      int rst, rb;
+      if (wu_pick(P.Cin, P.Cout, xes, ges, 2, P.xpitch, P.gpitch, P.xslots, P.gslots, rst, rb)) {
+        P.rstages = rst; P.raw_bytes = rb;
+        return launch_wu<TX, TG, 2>(xmap, gmap, x, gy, gw, gb, P, st);
       }
     }
   }
   int rst, rb;
-  HG_REQUIRE(wu_pick(P.Cin, P.Cout, xes, ges, false, P.xslots, P.gslots, rst, rb), HG_E_UNSUPPORTED, "hexconv_wgrad_umma: shared memory does not fit");
+  HG_REQUIRE(wu_pick(P.Cin, P.Cout, xes, ges, 0, P.xpitch, P.gpitch, P.xslots, P.gslots, rst, rb), HG_E_UNSUPPORTED, "hexconv_wgrad_umma: shared memory does not fit");
   P.rstages = 0; P.raw_bytes = 0;
-  return launch_wu<TX, TG, false>(xmap, gmap, x, gy, gw, gb, P, st);
+  return launch_wu<TX, TG, 0>(xmap, gmap, x, gy, gw, gb, P, st);
 }
 
 int conv_wgrad_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp, const void* x, const void* gy, float* gw,
@@ -534,6 +693,8 @@ int conv_wgrad_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp
       // instead of 4 KB (half of an M = 128 view would be the neighbouring ring slots): 1.11 -> 0.81 ms on C3.
       static const bool m128_only = [] { const char* e = getenv("HG_WU_M128"); return e && e[0] == '1'; }();
       P.m64 = (P.Cout <= 64 && !m128_only) ? 1 : 0;
+      static const bool epi_direct = [] { const char* e = getenv("HG_WU_EPI_DIRECT"); return e && e[0] == '1'; }();
+      P.epi_direct = epi_direct ? 1 : 0;
       float* gb = P.has_bias ? gbias : nullptr;
       int rc;
       if (xdt == HG_F32 && gdt == HG_F32) rc = launch_wu_any<float, float>(x, gy, gw, gb, P, st);

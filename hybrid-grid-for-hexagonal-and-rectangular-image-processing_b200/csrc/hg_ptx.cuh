@@ -77,6 +77,17 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// ---- cp.async (LDGSTS) with mbarrier completion: "software TMA" for rows TMA cannot address (row pitch not a
+// multiple of 16 bytes).  4-byte copies; src_size = 0 writes zeros without reading.
+__device__ __forceinline__ void cp_async_4(uint32_t smem_dst, const void* gsrc, uint32_t src_size) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_size) : "memory");
+}
+// the barrier receives one arrival from this thread once all of its earlier cp.async copies have landed (.noinc: the
+// arrival counts against the barrier's initial count -- initialise it with the number of copying threads)
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // ---- tcgen05 / TMEM ---------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {  // one full warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");

@@ -127,6 +127,7 @@ def main():
     ap.add_argument("--cin", type=int, default=64)
     ap.add_argument("--cout", type=int, default=64)
     ap.add_argument("--hw", type=int, default=256)
+    ap.add_argument("--w", type=int, default=0, help="lattice width when it differs from --hw (the pooled layers of C5: 64 x 63, 32 x 31)")
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--direct", action="store_true", help="also time the CUDA-core direct stencil (slow at 64x64)")
     ap.add_argument("--only", default="", help="comma list of ops to run (fwd,dgrad,wgrad); default all")
@@ -135,12 +136,13 @@ def main():
     ap.add_argument("--cudnn-only", action="store_true")
     a = ap.parse_args()
     N, Ci, Co, H = a.batch, a.cin, a.cout, a.hw
+    W = a.w or H
     dev = "cuda"
     torch.manual_seed(0)
     w = (torch.randn(Co, Ci, 1, 7, device=dev) * 0.05)
     bias = torch.randn(Co, device=dev)
-    flops = 2.0 * 7 * Ci * Co * N * H * H
-    res = {"config": f"HexConv2d {Ci}->{Co} r=2 s=1 pad=1, {N}x{Ci}x{H}x{H}", "flop_per_pass": flops, "rows": []}
+    flops = 2.0 * 7 * Ci * Co * N * H * W
+    res = {"config": f"HexConv2d {Ci}->{Co} r=2 s=1 pad=1, {N}x{Ci}x{H}x{W}", "flop_per_pass": flops, "rows": []}
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     hbm, tf = peaks.get("hbm_gbs", 6650.0), peaks.get("bf16_tflops_sustained", 1400.0)
     if a.cudnn or a.cudnn_only:
@@ -155,19 +157,19 @@ def main():
     elif a.dtypes == "bf16bf16":
         pairs = pairs[1:2]
     for xdt, ydt in pairs:
-        x = torch.randn(N, Ci, H, H, device=dev).to(xdt)
-        gy = torch.randn(N, Co, H, H, device=dev).to(ydt)
-        y = torch.empty(N, Co, H, H, device=dev, dtype=ydt)
+        x = torch.randn(N, Ci, H, W, device=dev).to(xdt)
+        gy = torch.randn(N, Co, H, W, device=dev).to(ydt)
+        y = torch.empty(N, Co, H, W, device=dev, dtype=ydt)
         gx = torch.empty_like(x)
         gw = torch.zeros_like(w)
         gb = torch.zeros_like(bias)
         st = nv.stream_ptr(x.device)
         for algo in ([2, 1] if a.direct else [2]):
-            d = nv.ConvDesc(N, Ci, Co, H, H, H, H, 2, 1, 1, 1, 1, 1, 0.0, nv.hg_dtype(xdt), nv.hg_dtype(ydt), algo, 0)
+            d = nv.ConvDesc(N, Ci, Co, H, W, H, W, 2, 1, 1, 1, 1, 1, 0.0, nv.hg_dtype(xdt), nv.hg_dtype(ydt), algo, 0)
             ops = {"fwd": lambda: nv.call("hg_hexconv_fwd", C.byref(d), nv.ptr(x), nv.ptr(w), nv.ptr(bias), nv.ptr(y), st),
                    "dgrad": lambda: nv.call("hg_hexconv_dgrad", C.byref(d), nv.ptr(gy), nv.ptr(w), nv.ptr(gx), st)}
             if algo == 1 or not nv.query("hg_hexconv_umma_eligible", C.byref(d), 2):
-                dw = nv.ConvDesc(N, Ci, Co, H, H, H, H, 2, 1, 1, 1, 1, 1, 0.0, nv.hg_dtype(xdt), nv.hg_dtype(ydt), 1, 0)
+                dw = nv.ConvDesc(N, Ci, Co, H, W, H, W, 2, 1, 1, 1, 1, 1, 0.0, nv.hg_dtype(xdt), nv.hg_dtype(ydt), 1, 0)
                 if a.direct or algo == 2:
                     ops["wgrad(direct)"] = lambda: nv.call("hg_hexconv_wgrad", C.byref(dw), nv.ptr(x), nv.ptr(gy), nv.ptr(gw), nv.ptr(gb), st)
             else:
@@ -182,7 +184,7 @@ def main():
                        "x": str(xdt).split(".")[1], "y": str(ydt).split(".")[1], "ms": round(ms, 4),
                        "tflops": round(flops / ms / 1e9, 1), "tensor_frac": round(flops / ms / 1e9 / tf, 3),
                        "gbs": round(nbytes / ms / 1e6, 1), "hbm_frac": round(nbytes / ms / 1e6 / hbm, 3),
-                       "hex_mpix_s": round(N * H * H / ms / 1e3, 1)}
+                       "hex_mpix_s": round(N * H * W / ms / 1e3, 1)}
                 res["rows"].append(row)
                 print(json.dumps(row), flush=True)
         del x, gy, y, gx
