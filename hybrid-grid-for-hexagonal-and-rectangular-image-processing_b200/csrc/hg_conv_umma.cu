@@ -58,6 +58,7 @@ struct UmmaParams {
   int slots, bands, ctiles;
   int band;                      // output rows per work item
   int rstages, raw_bytes;        // TMA / cp.async variants: raw staging ring
+  int wpr;                       // LDG variant: loader warps per row (8, or fewer on narrow lattices: several rows in flight)
   int rpitch;                    // pixels of a row that are staged (<= kUmPW; narrow lattices stage only what their outputs read)
   long long items;
 };
@@ -83,7 +84,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
   constexpr bool TMA = SRC == 1, CPA = SRC == 2, RAW = SRC != 0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nkc = P.Cred >> 3;
-  const int slot_bytes = P.Cred * kUmPW * 2;
+  const int slot_bytes = P.Cred * P.rpitch * 2;            // ring slot: [Cred/8][rpitch][8] bf16
   const int wtap_bytes = P.Cred * P.Nout * 2;
   unsigned char* w_smem = smem;                                   // [tap][Cred/8][Nout][8] bf16
   unsigned char* ring = smem + kTaps * wtap_bytes;                // [slot][Cred/8][PW][8] bf16
@@ -128,7 +129,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
     for (int e = tid; e < ((P.Nout + 31) & ~31); e += kUmThreads) bias_s[e] = (P.has_bias && e < P.Nout) ? __ldg(bias + e) : 0.f;
   }
   if (tid == 0) {
-    for (int s = 0; s < P.slots; ++s) { ptx::mbar_init(&full[s], kUmLoaders / 32); ptx::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < P.slots; ++s) { ptx::mbar_init(&full[s], RAW ? kUmLoaders / 32 : P.wpr); ptx::mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull[s], 1); ptx::mbar_init(&tempty[s], kUmEpiWarps * 32); }
     for (int s = 0; s < P.rstages; ++s) { ptx::mbar_init(&rfull[s], CPA ? kUmLoaders : 1); ptx::mbar_init(&rempty[s], kUmLoaders / 32); }
     if (TMA) ptx::prefetch_tensormap(&tmap);
@@ -165,10 +166,10 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
       }
     };
     auto cur_next = [&](RowCur& c) { if (++c.t == c.rows + 2) cur_set(c, c.item + gridDim.x); };
-    long long prow = 0;                      // rows issued so far
+    uint32_t prs = 0, prph = 0;              // producer position in the raw ring / parity (advanced without divisions)
     auto cpa_issue = [&](const RowCur& c) {
-      const int rs = (int)(prow % P.rstages);
-      ptx::mbar_wait(&rempty[rs], (uint32_t)(((prow / P.rstages) & 1) ^ 1));    // every converter warp has the old row in registers
+      const int rs = (int)prs;
+      ptx::mbar_wait(&rempty[rs], prph ^ 1);    // every converter warp has the old row in registers
       int i = c.r0 + P.row0 + c.t;
       const bool row_frame = i >= -P.pad && i < P.Hi + P.pad;
       if (P.pad_mode && row_frame) i = conv_pad_remap(i, P.Hi, P.pad_mode);
@@ -185,7 +186,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
           ptx::cp_async_4(dst0 + (uint32_t)(ch * P.rpitch + p) * 4u, ch < nch ? src + (size_t)ch * plane : in, ch < nch ? 4u : 0u);
       }
       ptx::cp_async_mbar_arrive_noinc(&rfull[rs]);
-      ++prow;
+      if (++prs == (uint32_t)P.rstages) { prs = 0; prph ^= 1; }
     };
     RowCur pc;
     if (CPA) {
@@ -194,22 +195,34 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
     }
     // the (channel group, pixel) of this thread's tasks never changes: worked out once (a division by the run-time
     // width inside the row loop cost the C3 forward 10 %)
-    int tkc[kUmMaxQ], tp[kUmMaxQ];
+    // LDG variant on narrow lattices: a row needs only P.wpr of the eight loader warps, so the warps form 8 / wpr groups
+    // that load consecutive rows at the same time (one row in flight per CTA made these layers latency-bound)
+    const int wpr = RAW ? kUmLoaders / 32 : P.wpr, ngroups = (kUmLoaders / 32) / wpr;
+    const int group = warp / wpr, gthreads = wpr * 32, tid_g = tid - group * gthreads;
+    int tkc[kUmMaxQ], tp[kUmMaxQ];           // tkc < 0: no task
 #pragma unroll
     for (int q = 0; q < kUmMaxQ; ++q) {
-      const int task = tid + q * kUmLoaders;
+      const int task = tid_g + q * gthreads;
       tkc[q] = task / P.rpitch; tp[q] = task - tkc[q] * P.rpitch;
+      if (task >= ntasks) tkc[q] = -1;
     }
-    long long lt = 0;                        // input rows produced so far (ring position)
+    // ring positions advance by counters: the 64-bit % and / by run-time stage counts this loop started with were a fifth of
+    // the kernel's instructions on a small layer, and in the serial chain of every row
+    uint32_t lslot = 0, lph = 0, lrs = 0, lrph = 0, lgrp = 0;   // ring slot / parity, raw stage / parity, row's loader group
     for (long long item = blockIdx.x; item < P.items; item += gridDim.x) {
       const int n = (int)(item / per_n);
       const int rem = (int)(item - (long long)n * per_n);
       const int band = rem / P.ctiles, ct = rem - band * P.ctiles;
       const int r0 = band * P.band, rows = min(P.band, P.Ho - r0), c0 = ct * kUmTile;
       const TIN* __restrict__ in_n = in + ((size_t)n * P.cred_total + P.c_off) * plane;
-      for (int t = 0; t < rows + 2; ++t, ++lt) {
-        const int slot = (int)(lt % P.slots);
-        const uint32_t use = (uint32_t)(lt / P.slots);
+      for (int t = 0; t < rows + 2; ++t) {
+        const int slot = (int)lslot, rs = (int)lrs;
+        const uint32_t eph = lph ^ 1, rph = lrph;                // parities to wait for: slot empty, raw stage full
+        const bool mine = RAW || (int)lgrp == group;
+        if (++lslot == (uint32_t)P.slots) { lslot = 0; lph ^= 1; }
+        if (RAW) { if (++lrs == (uint32_t)P.rstages) { lrs = 0; lrph ^= 1; } }
+        else if (++lgrp == (uint32_t)ngroups) lgrp = 0;
+        if (!mine) continue;                                     // another group's row
         unsigned char* sb = ring + (size_t)slot * slot_bytes;
         uint4 pk[kUmMaxQ];                   // 8 channels of one pixel, packed to bf16 as soon as they are loaded
         auto pack8 = [](const float (&v)[8]) {
@@ -222,13 +235,11 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
             if constexpr (sizeof(TIN) == 4) { if (pc.item < P.items) { cpa_issue(pc); cur_next(pc); } }
           }
           // raw row [Cred][rpitch] landed by TMA / cp.async (halo rows / columns already zero-filled) -> registers
-          const int rs = (int)(lt % P.rstages);
-          ptx::mbar_wait(&rfull[rs], (uint32_t)((lt / P.rstages) & 1));
+          ptx::mbar_wait(&rfull[rs], rph);
           const TIN* __restrict__ rp = reinterpret_cast<const TIN*>(raw + (size_t)rs * P.raw_bytes);
 #pragma unroll
           for (int q = 0; q < kUmMaxQ; ++q) {
-            const int task = tid + q * kUmLoaders;
-            if (task < ntasks) {
+            if (tkc[q] >= 0) {
               const int kc = tkc[q], p = tp[q];
               float v[8];
 #pragma unroll
@@ -241,17 +252,16 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
           ptx::fence_proxy_async_smem();
           __syncwarp();                      // the whole warp holds its values in registers:
           if (lane == 0) ptx::mbar_arrive(&rempty[rs]);   // one arrival per warp, the stage can be refilled
-          ptx::mbar_wait(&empty[slot], (use & 1) ^ 1);
+          ptx::mbar_wait(&empty[slot], eph);
         } else {
-          ptx::mbar_wait(&empty[slot], (use & 1) ^ 1);
+          ptx::mbar_wait(&empty[slot], eph);
           int i = r0 + P.row0 + t;
           const bool row_frame = i >= -P.pad && i < P.Hi + P.pad;
           if (P.pad_mode && row_frame) i = conv_pad_remap(i, P.Hi, P.pad_mode);      // frame rows read the image in place
           const bool row_in = i >= 0 && i < P.Hi;
 #pragma unroll
           for (int q = 0; q < kUmMaxQ; ++q) {
-            const int task = tid + q * kUmLoaders;
-            if (task < ntasks) {
+            if (tkc[q] >= 0) {
               const int kc = tkc[q], p = tp[q];
               int j = c0 + P.col0 + p;
               const bool col_frame = j >= -P.pad && j < P.Wi + P.pad;
@@ -269,8 +279,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
         }
 #pragma unroll
         for (int q = 0; q < kUmMaxQ; ++q) {
-          const int task = tid + q * kUmLoaders;
-          if (task < ntasks) *reinterpret_cast<uint4*>(sb + (size_t)(tkc[q] * kUmPW + tp[q]) * 16) = pk[q];
+          if (tkc[q] >= 0) *reinterpret_cast<uint4*>(sb + (size_t)(tkc[q] * P.rpitch + tp[q]) * 16) = pk[q];
         }
         ptx::fence_proxy_async_smem();       // generic-proxy smem writes -> visible to tcgen05.mma
         __syncwarp();
@@ -297,12 +306,18 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
         ptx::mbar_wait(&tfull[acc], acc_phase);
         ptx::tc_fence_after_sync();
         const int last_cb = ((P.Nout - 1) >> 5) << 5;                      // first channel of the last chunk
-        const int my_last = ((last_cb >> 5) & 1) == half ? last_cb : last_cb - 32;   // last chunk this warp owns (< 0: none)
-        if (my_last < 0) {                   // Nout <= 32: the odd warps have no chunk, they only release the accumulator
+        int my_last = ((last_cb >> 5) & 1) == half ? last_cb : last_cb - 32;   // last chunk this warp owns (< 0: none)
+        int cb0 = half * 32;
+        if (P.Nout <= 32) {                  // a single chunk: the two warps of a quadrant take alternate rows (= accumulator stages),
+          const bool own = (int)acc == half; //  so two rows are being stored at any time (C5 first layer: the stores paced the kernel)
+          my_last = own ? 0 : -1;
+          cb0 = own ? 0 : P.Nout;
+        }
+        if (my_last < 0) {                   // no chunk in this row: only release the accumulator
           ptx::tc_fence_before_sync();
           ptx::mbar_arrive(&tempty[acc]);
         }
-        for (int cb = half * 32; cb < P.Nout; cb += 64) {
+        for (int cb = cb0; cb < P.Nout; cb += 64) {
           TOUT* __restrict__ op = orow + (size_t)cb * cstride;
           uint32_t v[32];
           ptx::tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * (uint32_t)P.Nout + (uint32_t)cb, v);
@@ -358,7 +373,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
     // high word and a low word that only gets an address increment added.
     const uint32_t idesc = ptx::umma_idesc_bf16(kUmTile, P.Nout);
     const uint32_t ring_addr = ptx::smem_u32(ring), w_addr = ptx::smem_u32(w_smem);
-    const uint32_t lbo_a = kUmPW * 16, lbo_b = (uint32_t)P.Nout * 16;
+    const uint32_t lbo_a = (uint32_t)P.rpitch * 16, lbo_b = (uint32_t)P.Nout * 16;
     const uint32_t desc_hi = (128u >> 4) | (1u << 14);                       // SBO = 128 B, descriptor version 1
     const uint32_t a_lo_const = ((lbo_a >> 4) << 16), b_lo_const = ((lbo_b >> 4) << 16);
     const uint32_t a_step = (2u * lbo_a) >> 4, b_step = (2u * lbo_b) >> 4;  // one K = 16 step, in 16-byte units
@@ -413,15 +428,16 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
   } else if (TMA) {
     // ===== TMA producer (one lane) ===========================================================================
     if (lane == 0) {
-      long long rt = 0;
+      uint32_t trs = 0, tph = 0;
       for (long long item = blockIdx.x; item < P.items; item += gridDim.x) {
         const int n = (int)(item / per_n);
         const int rem = (int)(item - (long long)n * per_n);
         const int band = rem / P.ctiles, ct = rem - band * P.ctiles;
         const int r0 = band * P.band, rows = min(P.band, P.Ho - r0), c0 = ct * kUmTile;
-        for (int t = 0; t < rows + 2; ++t, ++rt) {
-          const int rs = (int)(rt % P.rstages);
-          ptx::mbar_wait(&rempty[rs], (uint32_t)(((rt / P.rstages) & 1) ^ 1));
+        for (int t = 0; t < rows + 2; ++t) {
+          const int rs = (int)trs;
+          ptx::mbar_wait(&rempty[rs], tph ^ 1);
+          if (++trs == (uint32_t)P.rstages) { trs = 0; tph ^= 1; }
           ptx::mbar_arrive_expect_tx(&rfull[rs], (uint32_t)(P.Cred * P.rpitch * (int)sizeof(TIN)));
           ptx::tma_load_4d(raw + (size_t)rs * P.raw_bytes, &tmap, &rfull[rs], c0 + P.col0, r0 + P.row0 + t, P.c_off, n);
         }
@@ -441,8 +457,11 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
 // ---- host side --------------------------------------------------------------------------------------------
 static int g_um_sms = 0, g_um_smem_max = 0;
 
-static size_t umma_smem_bytes(int Cred, int Nout, int slots, int rstages, int raw_bytes) {
-  return (size_t)kTaps * Cred * Nout * 2 + (size_t)slots * Cred * kUmPW * 2 + (size_t)rstages * raw_bytes + (size_t)((Nout + 31) & ~31) * 4 +
+static size_t umma_smem_bytes(int Cred, int Nout, int slots, int rstages, int raw_bytes, int rpitch) {
+  // the UMMA A view is always 128 pixels (+ tap shift) long: with a slot pitch below that it runs past its channel group --
+  // harmless, those accumulator rows are never stored -- and, for the last group of the last slot, past the ring: slack
+  const size_t slack = rpitch < kUmPW ? (size_t)(kUmPW - rpitch) * 16 : 0;
+  return slack + (size_t)kTaps * Cred * Nout * 2 + (size_t)slots * Cred * rpitch * 2 + (size_t)rstages * raw_bytes + (size_t)((Nout + 31) & ~31) * 4 +
          (size_t)(2 * slots + 4 + 2 * rstages) * 8 + 16;
 }
 
@@ -463,17 +482,17 @@ static void umma_pick_stages(int Cred, int Nout, int in_elem, int src, int rpitc
   if (!umma_device_limits()) return;
   if (src) {
     raw_bytes = (int)ceil_div((int64_t)Cred * rpitch * in_elem, 128) * 128;
-    // TMA prefetches in hardware: two (float32) / three stages keep it busy.  The cp.async rows are issued by the converter
-    // threads themselves, rstages - 1 rows ahead: take up to four stages when the shared memory is there (small layers)
-    const int rmax = src == 2 ? 4 : (in_elem == 2 ? 3 : 2);
-    for (int r = rmax; r >= 2 && !slots; --r)
-      for (int sl = 6; sl >= 4; --sl)
-        if (umma_smem_bytes(Cred, Nout, sl, r, raw_bytes) <= (size_t)g_um_smem_max) { slots = sl; rstages = r; break; }
+    // as many ring slots as fit first (what the large layers had: 6 slots + 2 raw stages fill the shared memory at 64
+    // channels), then as many raw stages as still fit, up to six: on small layers a TMA row is ~1 us of latency and two
+    // stages in flight bounded the kernel at 0.5 us per row (C5 first layer)
+    for (int sl = 6; sl >= 4 && !slots; --sl)
+      for (int r = 6; r >= 2; --r)
+        if (umma_smem_bytes(Cred, Nout, sl, r, raw_bytes, rpitch) <= (size_t)g_um_smem_max) { slots = sl; rstages = r; break; }
     if (!slots) raw_bytes = 0;
     return;
   }
   for (int sl = 6; sl >= 4; --sl)
-    if (umma_smem_bytes(Cred, Nout, sl, 0, 0) <= (size_t)g_um_smem_max) { slots = sl; return; }
+    if (umma_smem_bytes(Cred, Nout, sl, 0, 0, rpitch) <= (size_t)g_um_smem_max) { slots = sl; return; }
 }
 
 // op: 0 forward (reduce over Cin), 1 dgrad (reduce over Cout), 2 wgrad (reduce over pixels)
@@ -503,7 +522,7 @@ static bool g_um_no_cpa = [] { const char* e = getenv("HG_CONV_NO_CPASYNC"); ret
 template <typename TIN, typename TOUT, int SRC, bool ACC>
 static int launch_umma_acc(const CUtensorMap& tmap, const void* in, const float* w, const float* scale, const float* bias, void* out,
                            const UmmaParams& P, cudaStream_t st) {
-  const size_t smem = umma_smem_bytes(P.Cred, P.Nout, P.slots, P.rstages, P.raw_bytes);
+  const size_t smem = umma_smem_bytes(P.Cred, P.Nout, P.slots, P.rstages, P.raw_bytes, P.rpitch);
   auto kern = hexconv_umma_kernel<TIN, TOUT, SRC, ACC>;
   static SmemReservation reservation;
   cudaError_t e = reservation.reserve(kern, smem);
@@ -575,9 +594,17 @@ static int launch_umma_any(const void* in, const float* w, const float* scale, c
     }
   }
   int rst, rb;
+  if (P.ctiles == 1) P.rpitch = (int)std::min<int64_t>(kUmPW, ((int64_t)std::min(P.Wo, kUmTile) + 3 + 7) / 8 * 8);   // no alignment slack needed
   umma_pick_stages(P.Cred, P.Nout, es, 0, P.rpitch, P.slots, rst, rb);
   P.rstages = 0; P.raw_bytes = 0;
   HG_REQUIRE(P.slots > 0, HG_E_UNSUPPORTED, "hexconv_umma: shared memory does not fit");
+  // fewest warps per row that still cover its tasks (kUmMaxQ per thread), at most slots - 2 rows in flight
+  static const int wpr_env = [] { const char* e = getenv("HG_CONV_WPR"); return e ? atoi(e) : 0; }();
+  P.wpr = kUmLoaders / 32;
+  for (int wv = 2; wv < kUmLoaders / 32; wv *= 2)
+    if ((P.Cred / 8) * P.rpitch <= kUmMaxQ * 32 * wv && (kUmLoaders / 32) / wv <= P.slots - 2) { P.wpr = wv; break; }
+  if (wpr_env == 1 || wpr_env == 2 || wpr_env == 4 || wpr_env == 8) P.wpr = wpr_env;      // A/B switch (the task bound still has to hold)
+  if ((P.Cred / 8) * P.rpitch > kUmMaxQ * 32 * P.wpr) P.wpr = kUmLoaders / 32;
   return launch_umma<TIN, TOUT, 0>(tmap, in, w, scale, bias, out, P, st);
 }
 
@@ -598,12 +625,20 @@ static int dispatch_umma(int in_dt, int out_dt, const void* in, const float* w, 
                          cudaStream_t st) {
   const int total = P.Cred, relu = P.relu, has_bias = P.has_bias, base_acc = P.accumulate;
   if (P.cred_total <= 0) P.cred_total = total;           // the forward sets the real channel count when it rounded Cred up
-  for (int c0 = 0; c0 < total; c0 += 64) {
+  // a narrow lattice has short ring slots: 128 reduction channels fit in one pass (no second launch, no read-back of the output)
+  int step = 64;
+  if (total > 64 && P.ctiles == 1) {
+    const int rp = (int)std::min<int64_t>(kUmPW, ((int64_t)std::min(P.Wo, kUmTile) + 16 + 7) / 8 * 8);
+    int sl, rst, rb;
+    umma_pick_stages(128, P.Nout, 4, 1, rp, sl, rst, rb);
+    if (sl > 0 && (128 / 8) * rp <= kUmMaxQ * kUmLoaders) step = 128;
+  }
+  for (int c0 = 0; c0 < total; c0 += step) {
     P.c_off = c0;
-    P.Cred = total - c0 < 64 ? total - c0 : 64;
+    P.Cred = total - c0 < step ? total - c0 : step;
     P.accumulate = c0 > 0 || base_acc;
     P.has_bias = has_bias && c0 == 0;
-    P.relu = relu && c0 + 64 >= total;
+    P.relu = relu && c0 + step >= total;
     int rc = dispatch_umma_pass(in_dt, out_dt, in, w, scale, P.has_bias ? bias : nullptr, out, P, st);
     if (rc) return rc;
   }

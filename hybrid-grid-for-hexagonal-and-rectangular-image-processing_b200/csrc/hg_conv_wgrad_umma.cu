@@ -52,6 +52,7 @@ struct WgParams {
   int band;                      // output rows per work item
   int rstages, raw_bytes;        // TMA / cp.async variants
   int epi_direct;
+  int split;                     // narrow lattices, LDG variant: x rows and gy rows loaded by separate warp groups
   int xpitch, gpitch, ksteps;    // pixels of an x / gy row that are staged and 16-pixel reduction steps per row: a lattice narrower
                                  // than one 128-pixel tile stages and multiplies only ceil(Wo / 16) steps (gy is zero beyond Wo)
   int m64;                       // Cout <= 64: UMMA M = 64 (half the A-operand shared-memory reads of an M = 128 view)
@@ -107,8 +108,9 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
 
   for (int e = tid; e < 256; e += kWuThreads) reinterpret_cast<__nv_bfloat16*>(ones)[e] = __float2bfloat16_rn(1.f);
   if (tid == 0) {
-    for (int s = 0; s < P.xslots; ++s) { ptx::mbar_init(&xfull[s], kWuConvWarps); ptx::mbar_init(&xempty[s], 2); }   // one commit per issuer
-    for (int s = 0; s < P.gslots; ++s) { ptx::mbar_init(&gfull[s], kWuConvWarps); ptx::mbar_init(&gempty[s], 2); }
+    const int fill_warps = (!FULL && !RAW && P.split) ? kWuConvWarps / 2 : kWuConvWarps;     // arrivals per filled slot
+    for (int s = 0; s < P.xslots; ++s) { ptx::mbar_init(&xfull[s], fill_warps); ptx::mbar_init(&xempty[s], 2); }   // one commit per issuer
+    for (int s = 0; s < P.gslots; ++s) { ptx::mbar_init(&gfull[s], fill_warps); ptx::mbar_init(&gempty[s], 2); }
     for (int s = 0; s < P.rstages; ++s) { ptx::mbar_init(&rfull[s], CPA ? kWuConv : 1); ptx::mbar_init(&rempty[s], kWuConvWarps); }
     ptx::mbar_init(done, 2);
     if (TMA) { ptx::prefetch_tensormap(&xmap); ptx::prefetch_tensormap(&gmap); }
@@ -208,23 +210,33 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
     }
     // the (channel group, pixel) of this thread's tasks never changes: narrow lattices work it out once (run-time widths),
     // full tiles divide by constants on the spot
-    int xkc_[kWuMaxQ], xp_[kWuMaxQ], gkc_[2 * kWuMaxQ], gp_[2 * kWuMaxQ];
+    // Narrow lattices, LDG variant: the twelve converter warps split into an x group (warps 0-5) and a gy group (6-11),
+    // so an x row and a gy row are in flight together (one after the other -- gy in two passes at 128 channels -- the
+    // converters waited for global loads 40 % of the time on the C5 layers)
+    const bool split = !FULL && !RAW && P.split;
+    const bool grp_g = split && warp >= kWuConvWarps / 2;
+    const int cthreads = split ? kWuConv / 2 : kWuConv, ctid = grp_g ? tid - kWuConv / 2 : tid;
+    int xkc_[kWuMaxQ], xp_[kWuMaxQ], gkc_[2 * kWuMaxQ], gp_[2 * kWuMaxQ];      // < 0: no task
     if (!FULL) {
 #pragma unroll
       for (int q = 0; q < kWuMaxQ; ++q) {
-        const int task = tid + q * kWuConv;
+        const int task = ctid + q * cthreads;
         xkc_[q] = task / xpitch; xp_[q] = task - xkc_[q] * xpitch;
+        if (task >= xtasks) xkc_[q] = -1;
       }
 #pragma unroll
       for (int q = 0; q < 2 * kWuMaxQ; ++q) {
-        const int task = tid + q * kWuConv;
+        const int task = ctid + q * cthreads;
         gkc_[q] = task / gpitch; gp_[q] = task - gkc_[q] * gpitch;
+        if (task >= gtasks) gkc_[q] = -1;
       }
     }
     auto xkc = [&](int q) { return FULL ? (tid + q * kWuConv) / kWuPW : xkc_[q]; };
     auto xp = [&](int q) { return FULL ? (tid + q * kWuConv) % kWuPW : xp_[q]; };
     auto gkc = [&](int q) { return FULL ? (tid + q * kWuConv) / kWuTile : gkc_[q]; };
     auto gp = [&](int q) { return FULL ? (tid + q * kWuConv) % kWuTile : gp_[q]; };
+    auto xok = [&](int q) { return FULL ? (tid + q * kWuConv) < xtasks : xkc_[q] >= 0; };
+    auto gok = [&](int q) { return FULL ? (tid + q * kWuConv) < gtasks : gkc_[q] >= 0; };
     auto load_x = [&](const TX* __restrict__ xn, int i, int c0) {    // i: frame row, remapped below for the non-constant modes
       unsigned char* sb = xring + (size_t)xs * xslot_bytes;
       uint4 pk[kWuMaxQ];
@@ -234,8 +246,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
         const TX* __restrict__ rp = reinterpret_cast<const TX*>(raw + (size_t)rs * P.raw_bytes);
 #pragma unroll
         for (int q = 0; q < kWuMaxQ; ++q) {
-          const int task = tid + q * kWuConv;
-          if (task < xtasks) {
+          if (xok(q)) {
             const int kc = xkc(q), p = xp(q);
             float v[8];
 #pragma unroll
@@ -252,8 +263,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
         const bool row_in = i >= 0 && i < P.H;
 #pragma unroll
         for (int q = 0; q < kWuMaxQ; ++q) {
-          const int task = tid + q * kWuConv;
-          if (task < xtasks) {
+          if (xok(q)) {
             const int kc = xkc(q), p = xp(q);
             int j = c0 + P.col0 + p;
             const bool col_frame = j >= -P.pad && j < P.W + P.pad;
@@ -271,8 +281,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
       }
 #pragma unroll
       for (int q = 0; q < kWuMaxQ; ++q) {
-        const int task = tid + q * kWuConv;
-        if (task < xtasks) *reinterpret_cast<uint4*>(sb + (size_t)(xkc(q) * kWuPW + xp(q)) * 16) = pk[q];
+        if (xok(q)) *reinterpret_cast<uint4*>(sb + (size_t)(xkc(q) * kWuPW + xp(q)) * 16) = pk[q];
       }
       publish(&xfull[xs]);
       if (++xs == (uint32_t)P.xslots) { xs = 0; xph ^= 1; }
@@ -283,7 +292,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
       if (RAW) cpa_ahead();
 #pragma unroll
       for (int half = 0; half < 2; ++half) {                           // Cout = 128 needs two passes
-        const int base = half * kWuMaxQ * kWuConv;
+        const int base = half * kWuMaxQ * cthreads;
         if (base >= gtasks) break;
         uint4 pk[kWuMaxQ];
         if (RAW) {
@@ -291,8 +300,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
           const TG* __restrict__ rp = reinterpret_cast<const TG*>(raw + (size_t)rs * P.raw_bytes);
 #pragma unroll
           for (int q = 0; q < kWuMaxQ; ++q) {
-            const int task = base + tid + q * kWuConv;
-            if (task < gtasks) {
+            if (gok(half * kWuMaxQ + q)) {
               const int kc = gkc(half * kWuMaxQ + q), p = gp(half * kWuMaxQ + q);
               float v[8];
 #pragma unroll
@@ -300,12 +308,11 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
               pk[q] = pack8(v);
             }
           }
-          if (base + kWuMaxQ * kWuConv >= gtasks) raw_done();
+          if (base + kWuMaxQ * cthreads >= gtasks) raw_done();
         } else {
 #pragma unroll
           for (int q = 0; q < kWuMaxQ; ++q) {
-            const int task = base + tid + q * kWuConv;
-            if (task < gtasks) {
+            if (gok(half * kWuMaxQ + q)) {
               const int kc = gkc(half * kWuMaxQ + q), p = gp(half * kWuMaxQ + q);
               const int c = c0 + p;
               const TG* __restrict__ src = gn + (size_t)(kc * 8) * gplane + (size_t)R * P.Wo + c;
@@ -319,8 +326,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
         if (!waited) { ptx::mbar_wait(&gempty[gs], gph ^ 1); waited = true; }
 #pragma unroll
         for (int q = 0; q < kWuMaxQ; ++q) {
-          const int task = base + tid + q * kWuConv;
-          if (task < gtasks) *reinterpret_cast<uint4*>(sb + (size_t)(gkc(half * kWuMaxQ + q) * kWuTile + gp(half * kWuMaxQ + q)) * 16) = pk[q];
+          if (gok(half * kWuMaxQ + q)) *reinterpret_cast<uint4*>(sb + (size_t)(gkc(half * kWuMaxQ + q) * kWuTile + gp(half * kWuMaxQ + q)) * 16) = pk[q];
         }
       }
       publish(&gfull[gs]);
@@ -333,11 +339,16 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
       const int r0 = band * P.band, rows = min(P.band, P.Ho - r0), c0 = ct * kWuTile;
       const TX* __restrict__ xn = x + ((size_t)n * P.cin_total + P.ci_off) * xplane;
       const TG* __restrict__ gn = gy + ((size_t)n * P.cout_total + P.co_off) * gplane;
-      load_x(xn, r0 + P.row0 + 0, c0);
-      load_x(xn, r0 + P.row0 + 1, c0);
-      for (int rr = 0; rr < rows; ++rr) {
-        load_x(xn, r0 + P.row0 + rr + 2, c0);
-        load_g(gn, r0 + rr, c0);
+      if (split) {
+        if (grp_g) { for (int rr = 0; rr < rows; ++rr) load_g(gn, r0 + rr, c0); }
+        else { for (int t = 0; t < rows + 2; ++t) load_x(xn, r0 + P.row0 + t, c0); }
+      } else {
+        load_x(xn, r0 + P.row0 + 0, c0);
+        load_x(xn, r0 + P.row0 + 1, c0);
+        for (int rr = 0; rr < rows; ++rr) {
+          load_x(xn, r0 + P.row0 + rr + 2, c0);
+          load_g(gn, r0 + rr, c0);
+        }
       }
     }
     if (warp >= 8) {
@@ -388,11 +399,15 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
         const int nrows = min(rows_q, P.Cout - co0);
         const int upr = (run + 31) >> 5;                        // units per row
         const int units = nrows * upr;
+        int c, m;                                               // row / unit in the row, advanced without divisions
+        { const int u = ((int)blockIdx.x * 5) % units; c = u / upr; m = u - c * upr; }
+        float* __restrict__ gbase = gw + ((size_t)(P.co_off + co0) * P.cin_total + P.ci_off + cb) * kWuTaps;
+        const size_t grow = (size_t)P.cin_total * kWuTaps;
+#pragma unroll 4
         for (int u0 = 0; u0 < units; ++u0) {
-          const int u = (u0 + (int)blockIdx.x * 5) % units;
-          const int c = u / upr, t = (u - c * upr) * 32 + lane;
-          if (t < run)
-            atomicAdd(gw + ((size_t)(P.co_off + co0 + c) * P.cin_total + P.ci_off + cb) * kWuTaps + t, stg[c * kWuStagePitch + t]);
+          const int t = m * 32 + lane;
+          if (t < run) atomicAdd(gbase + c * grow + t, stg[c * kWuStagePitch + t]);
+          if (++m == upr) { m = 0; if (++c == nrows) c = 0; }
         }
         __syncwarp();
       }
@@ -550,8 +565,13 @@ static bool wu_pick(int Cin, int Cout, int xes, int ges, int src, int xpitch, in
     const int64_t xb = (int64_t)Cin * xpitch * xes, gb = (int64_t)Cout * gpitch * ges;
     raw_bytes = (int)ceil_div(xb > gb ? xb : gb, 128) * 128;
   }
-  // the cp.async rows are issued by the converter threads themselves, rstages - 1 rows ahead: up to five stages on small layers
-  for (int r = src == 2 ? 5 : src ? 3 : 0; r >= (src ? 2 : 0); --r)
+  // small layers are bound by the latency of the rows in flight: up to six raw stages when they fit next to full rings
+  for (int r = 6; src && r >= 4; --r)
+    if (wu_smem_bytes(Cin, Cout, 6, 3, r, raw_bytes) <= (size_t)g_wu_smem_max && wu_view_fits(Cin, Cout, 6)) {
+      xslots = 6; gslots = 3; rstages = r;
+      return true;
+    }
+  for (int r = src ? 3 : 0; r >= (src ? 2 : 0); --r)
     for (int g = 3; g >= 2; --g)
       for (int xsl = 6; xsl >= 4; --xsl)
         if (wu_smem_bytes(Cin, Cout, xsl, g, r, raw_bytes) <= (size_t)g_wu_smem_max && wu_view_fits(Cin, Cout, xsl)) {
@@ -659,6 +679,9 @@ static int launch_wu_any(const void* x, const void* gy, float* gw, float* gb, Wg
   int rst, rb;
   HG_REQUIRE(wu_pick(P.Cin, P.Cout, xes, ges, 0, P.xpitch, P.gpitch, P.xslots, P.gslots, rst, rb), HG_E_UNSUPPORTED, "hexconv_wgrad_umma: shared memory does not fit");
   P.rstages = 0; P.raw_bytes = 0;
+  static const bool no_split = [] { const char* e = getenv("HG_WU_NO_SPLIT"); return e && e[0] == '1'; }();
+  P.split = (!no_split && P.ksteps < kWuTile / 16 && (P.Cin / 8) * P.xpitch <= kWuMaxQ * (kWuConv / 2) &&
+             (P.Cout / 8) * P.gpitch <= 2 * kWuMaxQ * (kWuConv / 2)) ? 1 : 0;
   return launch_wu<TX, TG, 0>(xmap, gmap, x, gy, gw, gb, P, st);
 }
 
