@@ -215,6 +215,24 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
       const int band = rem / P.ctiles, ct = rem - band * P.ctiles;
       const int r0 = band * P.band, rows = min(P.band, P.Ho - r0), c0 = ct * kUmTile;
       const TIN* __restrict__ in_n = in + ((size_t)n * P.cred_total + P.c_off) * plane;
+      // LDG variant: what a task reads does not depend on the row -- column (frame columns remapped), frame flag and
+      // the pointer to the first of its 8 channels are worked out per item; a row adds i * Wi.  (ncu on the C5 layers: a
+      // third of all instructions were this address arithmetic, repeated per row, in warps that run one row at a time.)
+      const TIN* tsrc[kUmMaxQ];              // nullptr: column outside the image
+      uint32_t cframe = 0;                   // bit q: the task's column lies in the pad_value frame
+      if (!RAW) {
+#pragma unroll
+        for (int q = 0; q < kUmMaxQ; ++q) {
+          tsrc[q] = nullptr;
+          if (tkc[q] >= 0) {
+            int j = c0 + P.col0 + tp[q];
+            const bool col_frame = j >= -P.pad && j < P.Wi + P.pad;
+            if (P.pad_mode && col_frame) j = conv_pad_remap(j, P.Wi, P.pad_mode);
+            if (col_frame) cframe |= 1u << q;
+            if (j >= 0 && j < P.Wi) tsrc[q] = in_n + (size_t)(tkc[q] * 8) * plane + j;
+          }
+        }
+      }
       for (int t = 0; t < rows + 2; ++t) {
         const int slot = (int)lslot, rs = (int)lrs;
         const uint32_t eph = lph ^ 1, rph = lrph;                // parities to wait for: slot empty, raw stage full
@@ -262,17 +280,13 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
 #pragma unroll
           for (int q = 0; q < kUmMaxQ; ++q) {
             if (tkc[q] >= 0) {
-              const int kc = tkc[q], p = tp[q];
-              int j = c0 + P.col0 + p;
-              const bool col_frame = j >= -P.pad && j < P.Wi + P.pad;
-              if (P.pad_mode && col_frame) j = conv_pad_remap(j, P.Wi, P.pad_mode);
-              const bool col_in = j >= 0 && j < P.Wi;
-              const float fill = (row_frame && col_frame) ? P.pad_value : 0.f;
-              const TIN* __restrict__ src = in_n + (size_t)(kc * 8) * plane + (size_t)i * P.Wi + j;
-              const int c_left = P.cred_total - P.c_off - kc * 8;      // channels that exist from this group on (RGB: 3 of 16)
+              const float fill = (row_frame && ((cframe >> q) & 1u)) ? P.pad_value : 0.f;
+              const bool in_img = row_in && tsrc[q] != nullptr;
+              const TIN* __restrict__ src = tsrc[q] + (size_t)i * P.Wi;
+              const int c_left = P.cred_total - P.c_off - tkc[q] * 8;  // channels that exist from this group on (RGB: 3 of 16)
               float v[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = e < c_left ? ((row_in && col_in) ? ld_in(src + (size_t)e * plane) : fill) : 0.f;
+              for (int e = 0; e < 8; ++e) { v[e] = e < c_left ? (in_img ? ld_in(src) : fill) : 0.f; src += plane; }
               pk[q] = pack8(v);
             }
           }

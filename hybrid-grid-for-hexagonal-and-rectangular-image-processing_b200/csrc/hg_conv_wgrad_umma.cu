@@ -237,6 +237,30 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
     auto gp = [&](int q) { return FULL ? (tid + q * kWuConv) % kWuTile : gp_[q]; };
     auto xok = [&](int q) { return FULL ? (tid + q * kWuConv) < xtasks : xkc_[q] >= 0; };
     auto gok = [&](int q) { return FULL ? (tid + q * kWuConv) < gtasks : gkc_[q] >= 0; };
+    // LDG variant: what a task reads does not depend on the row -- per item, the pointer to the first of its 8 channels at
+    // its (frame-remapped) column, or nullptr outside the image; a row adds i * W (see hg_conv_umma.cu)
+    const TX* xsrc[kWuMaxQ];
+    const TG* gsrc[2 * kWuMaxQ];
+    uint32_t xframe = 0;                     // bit q: the x task's column lies in the pad_value frame
+    auto item_tasks = [&](const TX* __restrict__ xn, const TG* __restrict__ gn, int c0) {
+      xframe = 0;
+#pragma unroll
+      for (int q = 0; q < kWuMaxQ; ++q) {
+        xsrc[q] = nullptr;
+        if (xok(q)) {
+          int j = c0 + P.col0 + xp(q);
+          const bool col_frame = j >= -P.pad && j < P.W + P.pad;
+          if (P.pad_mode && col_frame) j = conv_pad_remap(j, P.W, P.pad_mode);
+          if (col_frame) xframe |= 1u << q;
+          if (j >= 0 && j < P.W) xsrc[q] = xn + (size_t)(xkc(q) * 8) * xplane + j;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 2 * kWuMaxQ; ++q) {
+        gsrc[q] = nullptr;
+        if (gok(q) && c0 + gp(q) < P.Wo) gsrc[q] = gn + (size_t)(gkc(q) * 8) * gplane + c0 + gp(q);
+      }
+    };
     auto load_x = [&](const TX* __restrict__ xn, int i, int c0) {    // i: frame row, remapped below for the non-constant modes
       unsigned char* sb = xring + (size_t)xs * xslot_bytes;
       uint4 pk[kWuMaxQ];
@@ -264,17 +288,13 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
 #pragma unroll
         for (int q = 0; q < kWuMaxQ; ++q) {
           if (xok(q)) {
-            const int kc = xkc(q), p = xp(q);
-            int j = c0 + P.col0 + p;
-            const bool col_frame = j >= -P.pad && j < P.W + P.pad;
-            if (P.pad_mode && col_frame) j = conv_pad_remap(j, P.W, P.pad_mode);
-            const bool col_in = j >= 0 && j < P.W;
-            const float fill = (row_frame && col_frame) ? P.pad_value : 0.f;
-            const TX* __restrict__ src = xn + (size_t)(kc * 8) * xplane + (size_t)i * P.W + j;
-            const int c_left = P.cin_total - P.ci_off - kc * 8;      // channels of x that exist from this group on (RGB: 3 of 16)
+            const float fill = (row_frame && ((xframe >> q) & 1u)) ? P.pad_value : 0.f;
+            const bool in_img = row_in && xsrc[q] != nullptr;
+            const TX* __restrict__ src = xsrc[q] + (size_t)i * P.W;
+            const int c_left = P.cin_total - P.ci_off - xkc(q) * 8;  // channels of x that exist from this group on (RGB: 3 of 16)
             float v[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = e < c_left ? ((row_in && col_in) ? wu_ld(src + (size_t)e * xplane) : fill) : 0.f;
+            for (int e = 0; e < 8; ++e) { v[e] = e < c_left ? (in_img ? wu_ld(src) : fill) : 0.f; src += xplane; }
             pk[q] = pack8(v);
           }
         }
@@ -313,12 +333,11 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
 #pragma unroll
           for (int q = 0; q < kWuMaxQ; ++q) {
             if (gok(half * kWuMaxQ + q)) {
-              const int kc = gkc(half * kWuMaxQ + q), p = gp(half * kWuMaxQ + q);
-              const int c = c0 + p;
-              const TG* __restrict__ src = gn + (size_t)(kc * 8) * gplane + (size_t)R * P.Wo + c;
+              const TG* __restrict__ src = gsrc[half * kWuMaxQ + q] + (size_t)R * P.Wo;
+              const bool in_img = gsrc[half * kWuMaxQ + q] != nullptr;
               float v[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = c < P.Wo ? wu_ld(src + (size_t)e * gplane) : 0.f;
+              for (int e = 0; e < 8; ++e) { v[e] = in_img ? wu_ld(src) : 0.f; src += gplane; }
               pk[q] = pack8(v);
             }
           }
@@ -339,6 +358,7 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
       const int r0 = band * P.band, rows = min(P.band, P.Ho - r0), c0 = ct * kWuTile;
       const TX* __restrict__ xn = x + ((size_t)n * P.cin_total + P.ci_off) * xplane;
       const TG* __restrict__ gn = gy + ((size_t)n * P.cout_total + P.co_off) * gplane;
+      if (!RAW) item_tasks(xn, gn, c0);
       if (split) {
         if (grp_g) { for (int rr = 0; rr < rows; ++rr) load_g(gn, r0 + rr, c0); }
         else { for (int t = 0; t < rows + 2; ++t) load_x(xn, r0 + P.row0 + t, c0); }
