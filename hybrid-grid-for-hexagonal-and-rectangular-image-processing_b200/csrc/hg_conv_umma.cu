@@ -129,7 +129,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
     for (int e = tid; e < ((P.Nout + 31) & ~31); e += kUmThreads) bias_s[e] = (P.has_bias && e < P.Nout) ? __ldg(bias + e) : 0.f;
   }
   if (tid == 0) {
-    for (int s = 0; s < P.slots; ++s) { ptx::mbar_init(&full[s], RAW ? kUmLoaders / 32 : P.wpr); ptx::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < P.slots; ++s) { ptx::mbar_init(&full[s], CPA ? kUmLoaders / 32 : P.wpr); ptx::mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull[s], 1); ptx::mbar_init(&tempty[s], kUmEpiWarps * 32); }
     for (int s = 0; s < P.rstages; ++s) { ptx::mbar_init(&rfull[s], CPA ? kUmLoaders : 1); ptx::mbar_init(&rempty[s], kUmLoaders / 32); }
     if (TMA) ptx::prefetch_tensormap(&tmap);
@@ -197,7 +197,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
     // width inside the row loop cost the C3 forward 10 %)
     // LDG variant on narrow lattices: a row needs only P.wpr of the eight loader warps, so the warps form 8 / wpr groups
     // that load consecutive rows at the same time (one row in flight per CTA made these layers latency-bound)
-    const int wpr = RAW ? kUmLoaders / 32 : P.wpr, ngroups = (kUmLoaders / 32) / wpr;
+    const int wpr = CPA ? kUmLoaders / 32 : P.wpr, ngroups = (kUmLoaders / 32) / wpr;     // (the cp.async rows are copied by all eight warps)
     const int group = warp / wpr, gthreads = wpr * 32, tid_g = tid - group * gthreads;
     int tkc[kUmMaxQ], tp[kUmMaxQ];           // tkc < 0: no task
 #pragma unroll
@@ -236,11 +236,21 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
       for (int t = 0; t < rows + 2; ++t) {
         const int slot = (int)lslot, rs = (int)lrs;
         const uint32_t eph = lph ^ 1, rph = lrph;                // parities to wait for: slot empty, raw stage full
-        const bool mine = RAW || (int)lgrp == group;
+        const bool mine = (int)lgrp == group;
         if (++lslot == (uint32_t)P.slots) { lslot = 0; lph ^= 1; }
         if (RAW) { if (++lrs == (uint32_t)P.rstages) { lrs = 0; lrph ^= 1; } }
-        else if (++lgrp == (uint32_t)ngroups) lgrp = 0;
-        if (!mine) continue;                                     // another group's row
+        if (++lgrp == (uint32_t)ngroups) lgrp = 0;
+        if (!mine) {                                             // another group's row
+          // TMA variant: wait for it and release it all the same.  A parity wait only works for a waiter that has observed
+          // every earlier phase of the barrier, and a stage must not be recycled past a group that has not seen it yet
+          // (the weight-gradient kernel's x / gy groups failed both ways before they did this).
+          if (RAW) {
+            ptx::mbar_wait(&rfull[rs], rph);
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&rempty[rs]);
+          }
+          continue;
+        }
         unsigned char* sb = ring + (size_t)slot * slot_bytes;
         uint4 pk[kUmMaxQ];                   // 8 channels of one pixel, packed to bf16 as soon as they are loaded
         auto pack8 = [](const float (&v)[8]) {
@@ -531,6 +541,17 @@ bool conv_umma_eligible(const hg_conv_desc* d, int op) {
 
 static bool g_um_no_tma = [] { const char* e = getenv("HG_CONV_NO_TMA"); return e && e[0] == '1'; }();
 
+// Loader warps per row: the fewest that still cover the row's tasks (kUmMaxQ per thread), so that the eight warps form
+// several groups working on consecutive rows at once -- at most max_rows of them (ring slots / raw stages that can be in flight).
+static void umma_pick_wpr(UmmaParams& P, int max_rows) {
+  static const int wpr_env = [] { const char* e = getenv("HG_CONV_WPR"); return e ? atoi(e) : 0; }();
+  P.wpr = kUmLoaders / 32;
+  for (int wv = 2; wv < kUmLoaders / 32; wv *= 2)
+    if ((P.Cred / 8) * P.rpitch <= kUmMaxQ * 32 * wv && (kUmLoaders / 32) / wv <= max_rows) { P.wpr = wv; break; }
+  if (wpr_env == 1 || wpr_env == 2 || wpr_env == 4 || wpr_env == 8) P.wpr = wpr_env;      // A/B switch (the task bound still has to hold)
+  if ((P.Cred / 8) * P.rpitch > kUmMaxQ * 32 * P.wpr) P.wpr = kUmLoaders / 32;
+}
+
 static bool g_um_no_cpa = [] { const char* e = getenv("HG_CONV_NO_CPASYNC"); return e && e[0] == '1'; }();
 
 template <typename TIN, typename TOUT, int SRC, bool ACC>
@@ -590,6 +611,7 @@ static int launch_umma_any(const void* in, const float* w, const float* scale, c
           P.col0 = col0a;
           for (int par = 0; par < 2; ++par) for (int k = 0; k < kTaps; ++k) P.sh[par][k] += e0;
           P.slots = slots; P.rstages = rst; P.raw_bytes = rb;
+          umma_pick_wpr(P, std::min(slots - 2, rst - 1));
           return launch_umma<TIN, TOUT, 1>(tmap, in, w, scale, bias, out, P, st);
         }
       }
@@ -602,7 +624,7 @@ static int launch_umma_any(const void* in, const float* w, const float* scale, c
       int slots, rst, rb;
       umma_pick_stages(P.Cred, P.Nout, es, 2, P.rpitch, slots, rst, rb);
       if (slots > 0) {
-        P.slots = slots; P.rstages = rst; P.raw_bytes = rb;
+        P.slots = slots; P.rstages = rst; P.raw_bytes = rb; P.wpr = kUmLoaders / 32;
         return launch_umma<TIN, TOUT, 2>(tmap, in, w, scale, bias, out, P, st);
       }
     }
@@ -612,13 +634,7 @@ static int launch_umma_any(const void* in, const float* w, const float* scale, c
   umma_pick_stages(P.Cred, P.Nout, es, 0, P.rpitch, P.slots, rst, rb);
   P.rstages = 0; P.raw_bytes = 0;
   HG_REQUIRE(P.slots > 0, HG_E_UNSUPPORTED, "hexconv_umma: shared memory does not fit");
-  // fewest warps per row that still cover its tasks (kUmMaxQ per thread), at most slots - 2 rows in flight
-  static const int wpr_env = [] { const char* e = getenv("HG_CONV_WPR"); return e ? atoi(e) : 0; }();
-  P.wpr = kUmLoaders / 32;
-  for (int wv = 2; wv < kUmLoaders / 32; wv *= 2)
-    if ((P.Cred / 8) * P.rpitch <= kUmMaxQ * 32 * wv && (kUmLoaders / 32) / wv <= P.slots - 2) { P.wpr = wv; break; }
-  if (wpr_env == 1 || wpr_env == 2 || wpr_env == 4 || wpr_env == 8) P.wpr = wpr_env;      // A/B switch (the task bound still has to hold)
-  if ((P.Cred / 8) * P.rpitch > kUmMaxQ * 32 * P.wpr) P.wpr = kUmLoaders / 32;
+  umma_pick_wpr(P, P.slots - 2);
   return launch_umma<TIN, TOUT, 0>(tmap, in, w, scale, bias, out, P, st);
 }
 

@@ -360,6 +360,10 @@ hexconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid
       const TG* __restrict__ gn = gy + ((size_t)n * P.cout_total + P.co_off) * gplane;
       if (!RAW) item_tasks(xn, gn, c0);
       if (split) {
+        // (LDG variant only.  With TMA the raw ring carries x and gy rows in ONE sequence: each group has to wait for and
+        //  release the other group's stages as well -- a parity wait only works for a waiter that has observed every earlier
+        //  phase; skipping blindly failed both ways on B200 -- and then the split gains nothing: 0.080 -> 0.086 ms on the
+        //  C5 first layer, with more registers.)
         if (grp_g) { for (int rr = 0; rr < rows; ++rr) load_g(gn, r0 + rr, c0); }
         else { for (int t = 0; t < rows + 2; ++t) load_x(xn, r0 + P.row0 + t, c0); }
       } else {
@@ -636,7 +640,7 @@ static int launch_wu_full(const CUtensorMap& xmap, const CUtensorMap& gmap, cons
 template <typename TX, typename TG, int SRC>
 static int launch_wu(const CUtensorMap& xmap, const CUtensorMap& gmap, const void* x, const void* gy, float* gw, float* gb,
                      const WgParams& P, cudaStream_t st) {
-  return P.ksteps == kWuTile / 16 ? launch_wu_full<TX, TG, SRC, true>(xmap, gmap, x, gy, gw, gb, P, st)
+  return (P.ksteps == kWuTile / 16 && !P.split) ? launch_wu_full<TX, TG, SRC, true>(xmap, gmap, x, gy, gw, gb, P, st)
                                   : launch_wu_full<TX, TG, SRC, false>(xmap, gmap, x, gy, gw, gb, P, st);
 }
 
@@ -650,6 +654,13 @@ static bool wu_encode(PFN_encodeTiled enc, CUtensorMap* m, const void* base, int
   const CUtensorMapDataType dt = es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   return enc(m, dt, 4, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// x rows and gy rows converted by separate warp groups (two rows in flight instead of one after the other): whenever a group
+// of six warps covers a row's tasks -- narrow lattices, or few channels (an RGB first layer)
+static int wu_can_split(const WgParams& P) {
+  static const bool no_split = [] { const char* e = getenv("HG_WU_NO_SPLIT"); return e && e[0] == '1'; }();
+  return (!no_split && (P.Cin / 8) * P.xpitch <= kWuMaxQ * (kWuConv / 2) && (P.Cout / 8) * P.gpitch <= 2 * kWuMaxQ * (kWuConv / 2)) ? 1 : 0;
 }
 
 static bool g_wu_no_cpa = [] { const char* e = getenv("HG_CONV_NO_CPASYNC"); return e && e[0] == '1'; }();
@@ -683,6 +694,7 @@ static int launch_wu_any(const void* x, const void* gy, float* gw, float* gb, Wg
         P.col0 = col0a;
         for (int par = 0; par < 2; ++par) for (int k = 0; k < kWuTaps; ++k) P.sh[par][k] += e0;
         P.xslots = xs_; P.gslots = gs_; P.rstages = rst; P.raw_bytes = rb;
+        P.split = 0;
         return launch_wu<TX, TG, 1>(xmap, gmap, x, gy, gw, gb, P, st);
       }
     }
@@ -691,7 +703,7 @@ static int launch_wu_any(const void* x, const void* gy, float* gw, float* gb, Wg
     if (!g_wu_no_cpa && P.ctiles > 1 && (P.pad_value == 0.f || P.pad_mode != 0)) {     // see hg_conv_umma.cu: wide rows only
       int rst, rb;
       if (wu_pick(P.Cin, P.Cout, xes, ges, 2, P.xpitch, P.gpitch, P.xslots, P.gslots, rst, rb)) {
-        P.rstages = rst; P.raw_bytes = rb;
+        P.rstages = rst; P.raw_bytes = rb; P.split = 0;
         return launch_wu<TX, TG, 2>(xmap, gmap, x, gy, gw, gb, P, st);
       }
     }
@@ -699,9 +711,7 @@ static int launch_wu_any(const void* x, const void* gy, float* gw, float* gb, Wg
   int rst, rb;
   HG_REQUIRE(wu_pick(P.Cin, P.Cout, xes, ges, 0, P.xpitch, P.gpitch, P.xslots, P.gslots, rst, rb), HG_E_UNSUPPORTED, "hexconv_wgrad_umma: shared memory does not fit");
   P.rstages = 0; P.raw_bytes = 0;
-  static const bool no_split = [] { const char* e = getenv("HG_WU_NO_SPLIT"); return e && e[0] == '1'; }();
-  P.split = (!no_split && P.ksteps < kWuTile / 16 && (P.Cin / 8) * P.xpitch <= kWuMaxQ * (kWuConv / 2) &&
-             (P.Cout / 8) * P.gpitch <= 2 * kWuMaxQ * (kWuConv / 2)) ? 1 : 0;
+  P.split = wu_can_split(P);
   return launch_wu<TX, TG, 0>(xmap, gmap, x, gy, gw, gb, P, st);
 }
 
