@@ -12,6 +12,7 @@
 // HBM-bound: algorithmic bytes = sizeof(src elem) * gathered cells + sizeof(dst elem) * cells (+ 8-byte table entry
 // per cell, amortised over the planes a block walks: the table value lives in a register across the plane loop).
 #include "hg_common.cuh"
+#include <stdlib.h>
 #include <type_traits>
 
 namespace hg {
@@ -42,34 +43,72 @@ plane_gather_kernel(const TS* __restrict__ src, TD* __restrict__ dst, const int6
   }
 }
 
-// One-byte cells (the hex-mosaic preview of a uint8 image): four adjacent cells per thread -- two 16-byte table loads, four
-// byte gathers and ONE 4-byte store per plane -- and 32 planes per table load, so that the 8-byte table entry costs 0.25 B per
-// output byte instead of 1 B (round-2 measurement of the scalar kernel on 96 x 1024^2 -> 4096^2: 0.13 of the HBM copy rate,
-// half of the traffic was the table and every store was a single byte).
+// One-byte cells (the hex-mosaic preview of a uint8 image): EIGHT adjacent cells per thread -- four 16-byte table loads once,
+// then per plane byte gathers and ONE 8-byte store -- and 32 planes per table load, so that the 8-byte table entry costs 0.25 B
+// per output byte instead of 1 B.  History (96 x 1024^2 -> 4096^2 on B200): scalar kernel 0.13 of the HBM copy rate (half of the
+// traffic was the table, every store a single byte); four cells per thread 0.27, instruction-bound: every output byte cost one
+// predicated byte load with 64-bit index arithmetic and a bounds test.  Now (a) the offsets are checked once per thread, not per
+// plane and byte: a plane whose largest offset stays inside the source takes a path without tests, through a plane pointer and
+// 32-bit offsets; (b) neighbouring cells of a magnified image mostly read the SAME source texel: a group of four equal offsets
+// is one load and a multiply by 0x01010101.
 constexpr int kGatherPlanesU8 = 32;
 
+template <int CELLS>     // cells per thread: 16 (one 16-byte store per plane) or 8
 __global__ void __launch_bounds__(kGatherThreads)
-plane_gather_u8x4_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const int64_t* __restrict__ table, int64_t planes,
-                         int chans, int64_t cells, int64_t batch_stride, int64_t chan_stride, int64_t src_total, int planes_per_block) {
-  const int64_t e = ((int64_t)blockIdx.x * kGatherThreads + threadIdx.x) * 4;
+plane_gather_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const int64_t* __restrict__ table, int64_t planes,
+                       int chans, int64_t cells, int64_t batch_stride, int64_t chan_stride, int64_t src_total, int planes_per_block) {
+  constexpr int G = CELLS / 4;               // 4-byte groups
+  const int64_t e = ((int64_t)blockIdx.x * kGatherThreads + threadIdx.x) * CELLS;
   if (e >= cells) return;
-  const longlong2 t01 = __ldg(reinterpret_cast<const longlong2*>(table + e));
-  const longlong2 t23 = __ldg(reinterpret_cast<const longlong2*>(table + e + 2));
-  const int64_t off[4] = {t01.x, t01.y, t23.x, t23.y};
+  int64_t off[CELLS];
+#pragma unroll
+  for (int k = 0; k < CELLS; k += 2) {
+    const longlong2 t = __ldg(reinterpret_cast<const longlong2*>(table + e + k));
+    off[k] = t.x; off[k + 1] = t.y;
+  }
+  int64_t omin = off[0], omax = off[0];
+#pragma unroll
+  for (int k = 1; k < CELLS; ++k) { omin = min(omin, off[k]); omax = max(omax, off[k]); }
+  const bool small = omin >= 0 && omax < (1ll << 31);            // every cell has a source, offsets fit 32 bits
+  uint32_t eq = 0;                                               // bit g: the four cells of group g read the same texel
+#pragma unroll
+  for (int g = 0; g < G; ++g)
+    if (off[4 * g] == off[4 * g + 1] && off[4 * g + 1] == off[4 * g + 2] && off[4 * g + 2] == off[4 * g + 3]) eq |= 1u << g;
   const int64_t p0 = (int64_t)blockIdx.y * planes_per_block;
   const int64_t p1 = min(p0 + planes_per_block, planes);
   int64_t b = p0 / chans;
   int c = (int)(p0 - b * chans);
-  for (int64_t p = p0; p < p1; ++p) {
+  uint8_t* __restrict__ out = dst + p0 * cells + e;
+  // (unrolling this loop by four measured slower: 0.75 vs 0.67 ms)
+#pragma unroll 1
+  for (int64_t p = p0; p < p1; ++p, out += cells) {
     const int64_t base = b * batch_stride + c * chan_stride;
-    uint32_t word = 0;
+    uint32_t w[G];
+    if (small && base + omax < src_total) {
+      const uint8_t* __restrict__ sp = src + base;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int64_t idx = base + off[k];
-      const uint32_t v = (off[k] >= 0 && idx < src_total) ? (uint32_t)__ldg(src + idx) : 0u;
-      word |= v << (8 * k);
+      for (int g = 0; g < G; ++g) {
+        if ((eq >> g) & 1u) w[g] = (uint32_t)__ldg(sp + (uint32_t)off[4 * g]) * 0x01010101u;
+        else {
+          w[g] = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) w[g] |= (uint32_t)__ldg(sp + (uint32_t)off[4 * g + k]) << (8 * k);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        w[g] = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int64_t idx = base + off[4 * g + k];
+          const uint32_t v = (off[4 * g + k] >= 0 && idx < src_total) ? (uint32_t)__ldg(src + idx) : 0u;
+          w[g] |= v << (8 * k);
+        }
+      }
     }
-    __stcs(reinterpret_cast<uint32_t*>(dst + p * cells + e), word);
+    if (CELLS == 16) __stcs(reinterpret_cast<uint4*>(out), make_uint4(w[0], w[1], w[2 % G], w[3 % G]));
+    else __stcs(reinterpret_cast<uint2*>(out), make_uint2(w[0], w[1]));
     if (++c == chans) { c = 0; ++b; }
   }
 }
@@ -120,14 +159,20 @@ template <typename TS, typename TD>
 static int launch_gather(const void* src, void* dst, const int64_t* table, int64_t batches, int64_t chans, int64_t cells,
                          int64_t batch_stride, int64_t chan_stride, cudaStream_t st) {
   const int64_t planes = batches * chans;
-  if (std::is_same<TS, uint8_t>::value && std::is_same<TD, uint8_t>::value && cells % 4 == 0 &&
-      (reinterpret_cast<uintptr_t>(dst) & 3) == 0 && (reinterpret_cast<uintptr_t>(table) & 15) == 0) {
-    int64_t ppb = kGatherPlanesU8;
+  if (std::is_same<TS, uint8_t>::value && std::is_same<TD, uint8_t>::value && cells % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (reinterpret_cast<uintptr_t>(table) & 15) == 0) {
+    static const int env_cells = [] { const char* e = getenv("HG_GATHER_CELLS"); return e ? atoi(e) : 0; }();
+    static const int env_ppb = [] { const char* e = getenv("HG_GATHER_PPB"); return e ? atoi(e) : 0; }();
+    const int per = (cells % 16 == 0 && env_cells == 16) ? 16 : 8;     // 16 measured slower (0.79 vs 0.67 ms on the 96-plane mosaic)
+    const int64_t bx = ceil_div(cells / per, kGatherThreads);
+    int64_t ppb = kGatherPlanesU8;           // (16 / 32 / 48 / 96 planes per table load: 0.70 / 0.67 / 0.67 / 0.69 ms)
+    if (env_ppb > 0) ppb = env_ppb;
     if (ceil_div(planes, ppb) > 65535) ppb = ceil_div(planes, 65535);
-    dim3 grid((unsigned)ceil_div(cells / 4, kGatherThreads), (unsigned)ceil_div(planes, ppb), 1);
-    plane_gather_u8x4_kernel<<<grid, kGatherThreads, 0, st>>>((const uint8_t*)src, (uint8_t*)dst, table, planes, (int)chans, cells,
-                                                              batch_stride, chan_stride, batches * batch_stride, (int)ppb);
-    return finish_launch("plane_gather_u8x4");
+    dim3 grid((unsigned)bx, (unsigned)ceil_div(planes, ppb), 1);
+    auto kern = per == 16 ? plane_gather_u8_kernel<16> : plane_gather_u8_kernel<8>;
+    kern<<<grid, kGatherThreads, 0, st>>>((const uint8_t*)src, (uint8_t*)dst, table, planes, (int)chans, cells,
+                                          batch_stride, chan_stride, batches * batch_stride, (int)ppb);
+    return finish_launch("plane_gather_u8");
   }
   const GatherGrid g = gather_grid(planes, cells);
   plane_gather_kernel<TS, TD><<<g.grid, kGatherThreads, 0, st>>>((const TS*)src, (TD*)dst, table, planes, (int)chans, cells,
