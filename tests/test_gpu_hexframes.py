@@ -284,6 +284,14 @@ def test_reductions_and_converters(hf, hexframes_golden, resample_golden):
     (1, 128, 64, 20, 128, 1, 0, torch.float32),
     (1, 64, 160, 18, 64, 1, 1, torch.float32),
     (1, 96, 128, 12, 128, 1, 0, torch.bfloat16),
+    # lattices narrower than one 128-pixel tile (the pooled layers of BASELINE config 5): rows staged as wide as the lattice,
+    # loader warp groups (several rows in flight), x / gy converter groups and ceil(W / 16) reduction steps in the weight
+    # gradient, 128 reduction channels in one pass; 40 images = more work items than CTAs (rings wrap across items)
+    (4, 32, 64, 64, 63, 1, 1, torch.float32),
+    (40, 64, 128, 32, 31, 1, 0, torch.float32),
+    (3, 128, 64, 24, 32, 1, 0, torch.float32),
+    (2, 64, 64, 40, 48, 1, 1, torch.bfloat16),
+    (2, 16, 32, 19, 20, 1, 0, torch.float32),
 ])
 @pytest.mark.parametrize("pad_value", [0.0, 0.25])      # 0 -> TMA-staged input path, != 0 -> coalesced-load path
 def test_hexconv_tcgen05_vs_oracle(hf, cfg, pad_value):
