@@ -570,39 +570,51 @@ def extra_c5(cx):
                                  "collective": "NCCL all-reduce inside the timed region" if cx.world > 1 else "single GPU: no collective"}
         bucket.detach()
     if cx.args.c5_graph:
-        # The eager step is host-bound (about 130 launches of a few microseconds in 2 ms): every rank replays the WHOLE
-        # step -- forward, backward, the NCCL all-reduce of the flat bucket, SGD -- as one captured CUDA graph.
-        try:
-            bucket = FlatGradBucket(model.parameters(), groups=1, overlap=False)
-            opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, fused=True)
+        # The eager step is host-bound (about 85 launches of a few microseconds against 1.1 ms of GPU work): every rank replays the
+        # WHOLE step -- forward, backward, the NCCL all-reduce of the flat bucket, SGD -- as one captured CUDA graph.  Two captures:
+        # one all-reduce after backward, and the three layer groups reduced from inside backward (parallel branches of the graph:
+        # only the first layer's 3 KB group is left to reduce when backward ends).
+        for gname, kw in (("whole step replayed as one CUDA graph (all-reduce captured)", dict(groups=1, overlap=False)),
+                          ("whole step as one CUDA graph, 3 layer groups all-reduced from inside backward", dict(groups=[3, 3, 5], overlap=True))):
+            if cx.world == 1 and kw["overlap"]:
+                continue                                   # no collective on one GPU: the two captures are the same graph
+            try:
+                bucket = FlatGradBucket(model.parameters(), **kw)
+                opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, fused=True)
 
-            def step():
-                bucket.zero_()
-                with torch.autocast("cuda", dtype=torch.bfloat16):
-                    loss = torch.nn.functional.cross_entropy(model(x).float(), t)
-                loss.backward()
-                bucket.finish()
-                opt.step()
-                return loss
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(3):
+                def step():
+                    bucket.zero_()
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        loss = torch.nn.functional.cross_entropy(model(x).float(), t)
+                    loss.backward()
+                    bucket.finish()
+                    opt.step()
+                    return loss
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(3):
+                        step()
+                torch.cuda.current_stream().wait_stream(side)
+                cx.barrier()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
                     step()
-            torch.cuda.current_stream().wait_stream(side)
-            cx.barrier()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                step()
-            cx.barrier()
-            total, _ = cx.timed(graph.replay, 50, warmup=5)
-            out["variants"]["whole step replayed as one CUDA graph (all-reduce captured)"] = {
-                "ms_per_step": total, "images_per_s": cx.world * B / (total * 1e-3), "value": cx.world * B * HW * HW / (total * 1e-3) / 1e6,
-                "unit": UNIT, "collective": "NCCL all-reduce inside the graph" if cx.world > 1 else "single GPU: no collective"}
-            cx.graphs.append(graph)                        # kept alive until the process leaves (see run_ours)
-            bucket.detach()
-        except Exception as e:                              # noqa: BLE001
-            out["variants"]["whole step replayed as one CUDA graph (all-reduce captured)"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                cx.barrier()
+                total, _ = cx.timed(graph.replay, 50, warmup=5)
+                check = torch.stack([p.detach().double().sum() for p in model.parameters()]).sum().reshape(1)
+                lo_, hi_ = check.clone(), check.clone()
+                if cx.world > 1:
+                    cx.dist.all_reduce(lo_, op=cx.dist.ReduceOp.MIN)
+                    cx.dist.all_reduce(hi_, op=cx.dist.ReduceOp.MAX)
+                out["variants"][gname] = {
+                    "ms_per_step": total, "images_per_s": cx.world * B / (total * 1e-3), "value": cx.world * B * HW * HW / (total * 1e-3) / 1e6,
+                    "unit": UNIT, "ranks_in_sync": bool(torch.allclose(lo_, hi_, rtol=0, atol=1e-6 * float(hi_.abs()) + 1e-9)),
+                    "collective": "NCCL all-reduce inside the graph" if cx.world > 1 else "single GPU: no collective"}
+                cx.graphs.append(graph)                    # kept alive until the process leaves (see run_ours)
+                bucket.detach()
+            except Exception as e:                          # noqa: BLE001
+                out["variants"][gname] = {"error": f"{type(e).__name__}: {e}"[:300]}
     return out
 
 
