@@ -42,6 +42,7 @@ constexpr int kUmThreads = kUmLoaders + kUmEpiWarps * 32 + 32 + 32;
 constexpr int kUmBand = 32;                  // output rows per work item (upper bound; small problems take shorter bands, umma_common)
 constexpr int kUmMaxQ = 5;                   // ceil(8 * 144 / 256): (chunk, pixel) tasks per loader thread, Cred <= 64
 constexpr int kTaps = 7;
+constexpr int kUmMaxAcc = 8;                 // accumulator stages in TMEM (barrier arrays are sized for this)
 constexpr int kUmMaxCred = 512;              // reduction channels per call (passes of <= 64)
 
 struct UmmaParams {
@@ -58,6 +59,7 @@ struct UmmaParams {
   int slots, bands, ctiles;
   int band;                      // output rows per work item
   int rstages, raw_bytes;        // TMA / cp.async variants: raw staging ring
+  int nacc;                      // accumulator stages in TMEM (2 .. kUmMaxAcc)
   int wpr;                       // LDG variant: loader warps per row (8, or fewer on narrow lattices: several rows in flight)
   int rpitch;                    // pixels of a row that are staged (<= kUmPW; narrow lattices stage only what their outputs read)
   long long items;
@@ -93,9 +95,9 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + ((P.Nout + 31) & ~31));
   uint64_t* full = bars;                    // [slots]  loaders -> MMA        (one arrival per loader warp)
   uint64_t* empty = bars + P.slots;         // [slots]  MMA commit -> loaders (count 1)
-  uint64_t* tfull = empty + P.slots;        // [2]      MMA commit -> epilogue
-  uint64_t* tempty = tfull + 2;             // [2]      epilogue -> MMA       (count 128)
-  uint64_t* rfull = tempty + 2;             // [rstages] TMA bytes landed
+  uint64_t* tfull = empty + P.slots;        // [kUmMaxAcc] MMA commit -> epilogue   (P.nacc accumulator stages in use)
+  uint64_t* tempty = tfull + kUmMaxAcc;     // [kUmMaxAcc] epilogue -> MMA          (count: all epilogue threads)
+  uint64_t* rfull = tempty + kUmMaxAcc;     // [rstages] TMA bytes landed
   uint64_t* rempty = rfull + P.rstages;     // [rstages] converters done      (one arrival per warp)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + P.rstages);
 
@@ -130,14 +132,16 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
   }
   if (tid == 0) {
     for (int s = 0; s < P.slots; ++s) { ptx::mbar_init(&full[s], CPA ? kUmLoaders / 32 : P.wpr); ptx::mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull[s], 1); ptx::mbar_init(&tempty[s], kUmEpiWarps * 32); }
+    for (int s = 0; s < kUmMaxAcc; ++s) { ptx::mbar_init(&tfull[s], 1); ptx::mbar_init(&tempty[s], kUmEpiWarps * 32); }
     for (int s = 0; s < P.rstages; ++s) { ptx::mbar_init(&rfull[s], CPA ? kUmLoaders : 1); ptx::mbar_init(&rempty[s], kUmLoaders / 32); }
     if (TMA) ptx::prefetch_tensormap(&tmap);
     ptx::fence_barrier_init();
   }
   // two accumulator stages of Nout columns; the epilogue always loads 32-column chunks, so the last chunk of stage 1
   // may reach up to Nout + roundup32(Nout): the allocation covers that (Nout = 16: 64 columns, not 32)
-  const uint32_t tmem_need = (uint32_t)P.Nout + (((uint32_t)P.Nout + 31u) & ~31u);
+  // P.nacc accumulator stages of Nout columns; the epilogue always loads 32-column chunks, so the last chunk of the last stage
+  // may reach up to roundup32(Nout) past its start: the allocation covers that (Nout = 16, two stages: 64 columns, not 32)
+  const uint32_t tmem_need = (uint32_t)(P.nacc - 1) * (uint32_t)P.Nout + (((uint32_t)P.Nout + 31u) & ~31u);
   const uint32_t tmem_cols = tmem_need <= 32 ? 32 : tmem_need <= 64 ? 64 : tmem_need <= 128 ? 128 : tmem_need <= 256 ? 256 : 512;
   if (warp == kUmMmaWarp) { ptx::tmem_alloc(tmem_slot, tmem_cols); ptx::tmem_relinquish(); }
   ptx::fence_proxy_async_smem();            // weight image written by the generic proxy, read by tcgen05.mma
@@ -333,7 +337,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
         int my_last = ((last_cb >> 5) & 1) == half ? last_cb : last_cb - 32;   // last chunk this warp owns (< 0: none)
         int cb0 = half * 32;
         if (P.Nout <= 32) {                  // a single chunk: the two warps of a quadrant take alternate rows (= accumulator stages),
-          const bool own = (int)acc == half; //  so two rows are being stored at any time (C5 first layer: the stores paced the kernel)
+          const bool own = (int)(acc & 1u) == half; //  so two rows are being stored at any time (C5 first layer: the stores paced the kernel)
           my_last = own ? 0 : -1;
           cb0 = own ? 0 : P.Nout;
         }
@@ -387,7 +391,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
             }
           }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == (uint32_t)P.nacc) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp == kUmMmaWarp) {
@@ -444,7 +448,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
         }
         __syncwarp();
         next_slot(slot0, phase0);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == (uint32_t)P.nacc) { acc = 0; acc_phase ^= 1; }
       }
       next_slot(slot0, phase0);              // the band's two trailing input rows
       next_slot(slot0, phase0);
@@ -486,7 +490,7 @@ static size_t umma_smem_bytes(int Cred, int Nout, int slots, int rstages, int ra
   // harmless, those accumulator rows are never stored -- and, for the last group of the last slot, past the ring: slack
   const size_t slack = rpitch < kUmPW ? (size_t)(kUmPW - rpitch) * 16 : 0;
   return slack + (size_t)kTaps * Cred * Nout * 2 + (size_t)slots * Cred * rpitch * 2 + (size_t)rstages * raw_bytes + (size_t)((Nout + 31) & ~31) * 4 +
-         (size_t)(2 * slots + 4 + 2 * rstages) * 8 + 16;
+         (size_t)(2 * slots + 2 * kUmMaxAcc + 2 * rstages) * 8 + 16;
 }
 
 static bool umma_device_limits() {
@@ -681,6 +685,15 @@ static void umma_common(UmmaParams& P, int Ho, int Wo, int N) {
   P.band = conv_pick_band(kUmBand, N, Ho, P.ctiles);
   P.bands = (int)ceil_div(Ho, P.band);
   P.items = (long long)N * P.bands * P.ctiles;
+  // accumulator stages: two.  (HG_CONV_NACC = 4 / 8 takes more of the 512 TMEM columns; measured on the C5 and C3 layers it
+  // changes nothing -- the issuer never waits for a free accumulator.  What paces a small layer is the single issuing thread:
+  // with one tap's MMAs per row instead of seven the RGB layer ran in 46 instead of 78 us, ~190 cycles per tcgen05.mma of
+  // address selection, descriptor moves and issue, against 16 cycles of tensor work; profiles/r5j.)
+  static const int nacc_env = [] { const char* e = getenv("HG_CONV_NACC"); return e ? atoi(e) : 0; }();
+  const int nround = (P.Nout + 31) & ~31;
+  int nacc = 2;
+  if (nacc_env >= 2 && nacc_env <= kUmMaxAcc && (nacc_env & 1) == 0 && (nacc_env - 1) * P.Nout + nround <= 512) nacc = nacc_env;
+  P.nacc = nacc;
 }
 
 int conv_fwd_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp, const void* x, const float* w, const float* scale,
