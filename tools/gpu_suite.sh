@@ -16,6 +16,8 @@ if has cudnn; then timeout 900 python tools/bench_conv.py --cudnn-only --reps 9 
 if has stress; then   # the tcgen05 wgrad staging race showed up once per few processes: repeat fresh processes
   for k in 0 1 2 3 4 5; do timeout 300 python tests/stress/wgrad_cfg.py 2>&1 | grep -c BAD; done > $OUT/wgrad_stress.log 2>&1
   echo "wgrad stress (BAD configurations per process):" $(tr '\n' ' ' < $OUT/wgrad_stress.log)
+  for s in 11 12 13; do timeout 400 python tests/stress/conv_narrow_fuzz.py 120 $s 2>&1 | tail -1; done > $OUT/conv_narrow_fuzz.log 2>&1
+  echo "narrow-lattice conv fuzz:" $(tr '\n' ' ' < $OUT/conv_narrow_fuzz.log)
 fi
 if has bench; then
   timeout 1500 python bench.py --steps 20 --warmup 5 > $OUT/bench_c2.json 2> $OUT/bench_c2.err; echo "bench rc=$?"; cut -c1-6000 $OUT/bench_c2.json; tail -5 $OUT/bench_c2.err
