@@ -300,8 +300,9 @@ hexsrc_linear_kernel(const TS* __restrict__ src, TD* __restrict__ dst, Coord coo
 constexpr int kFastRows = 2;                 // output rows per warp of the plane-outer linear kernel (8 samples per thread in registers)
 constexpr int kFastTileH = 8 * kFastRows;
 
+// (float32 coordinates -- the torch twin's warps -- fit 80 registers without spilling: three blocks per SM instead of two)
 template <typename TS, typename TD, typename Coord, bool FAST>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, (!FAST && sizeof(typename Coord::CT) == 4 && sizeof(TD) == 4) ? 3 : 2)
 hexsrc_linear_fast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, Coord coord, HexConsts hc, int64_t planes, int chunk,
                           int h, int w, int h1, int w1, int tiles_x, int tiles_y) {
   using CT = typename Coord::CT;
