@@ -12,16 +12,17 @@
 // rows that touch it.  NCHW activations are read with plain coalesced loads (lanes along the row) -- the
 // [pixel][channel] transposition TMA cannot do happens in registers on the way to shared memory.
 //
-// Persistent CTA = 14 warps:  warps 0-7 loaders / converters (-> bf16 -> smem ring of input rows),
-//                             warps 8-11 epilogue (TMEM -> registers -> bias/ReLU -> coalesced NCHW stores),
-//                             warp 12 MMA issuer (one lane) + TMEM allocator,
-//                             warp 13 TMA producer (one lane; TMA variant only).
-// Two variants of the input path:
+// Persistent CTA = 19 warps:  warps 0-7 loaders / converters (-> bf16 -> smem ring of input rows),
+//                             warps 8-15 epilogue (TMEM -> registers -> bias/ReLU -> coalesced NCHW stores),
+//                             warps 16 and 18 MMA issuers (one lane each, alternate output rows; 16 also allocates TMEM),
+//                             warp 17 TMA producer (one lane; TMA variant only).
+// Three variants of the input path:
 //   TMA  : a 4-D tensor map over NCHW; one cp.async.bulk.tensor box [Cred][1 row][PW px] per input row lands
 //          in a raw staging ring (deep hardware prefetch, zero-fill of halo rows / columns for free); the
 //          converter warps read it conflict-free (lanes along pixels), pack 8 channels to 16 bytes, and
 //          write the K-major ring.  Needs pad_value == 0 and 16-byte aligned rows.
 //   LDG  : the same conversion straight from global memory with coalesced loads (any pad value / width).
+//   CPA  : cp.async rows into the raw ring for wide lattices whose rows TMA cannot address (float32, zero frame).
 // Pipelines: raw full/empty (TMA <-> converters), full/empty per ring slot (converters <-> MMA, slots released
 //            by tcgen05.commit), tmem_full/tmem_empty per accumulator stage (MMA <-> epilogue).
 #include "hg_conv.cuh"
@@ -38,7 +39,9 @@ constexpr int kUmPW = 144;                   // pixels per ring slot: tile + tap
 constexpr int kUmLoaders = 256;
 constexpr int kUmEpiWarps = 8;               // two warps per TMEM lane quadrant, alternating 32-channel chunks
 constexpr int kUmMmaWarp = kUmLoaders / 32 + kUmEpiWarps;
-constexpr int kUmThreads = kUmLoaders + kUmEpiWarps * 32 + 32 + 32;
+constexpr int kUmTmaWarp = kUmMmaWarp + 1;
+constexpr int kUmMmaWarpB = kUmMmaWarp + 2;    // second MMA issuer (alternate output rows; P.dual)
+constexpr int kUmThreads = kUmLoaders + kUmEpiWarps * 32 + 32 + 32 + 32;
 constexpr int kUmBand = 32;                  // output rows per work item (upper bound; small problems take shorter bands, umma_common)
 constexpr int kUmMaxQ = 5;                   // ceil(8 * 144 / 256): (chunk, pixel) tasks per loader thread, Cred <= 64
 constexpr int kTaps = 7;
@@ -60,6 +63,7 @@ struct UmmaParams {
   int band;                      // output rows per work item
   int rstages, raw_bytes;        // TMA / cp.async variants: raw staging ring
   int nacc;                      // accumulator stages in TMEM (2 .. kUmMaxAcc)
+  int dual;                      // two MMA-issuing warps take alternate output rows (small layers are paced by the issuing thread)
   int wpr;                       // LDG variant: loader warps per row (8, or fewer on narrow lattices: several rows in flight)
   int rpitch;                    // pixels of a row that are staged (<= kUmPW; narrow lattices stage only what their outputs read)
   long long items;
@@ -131,7 +135,7 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
     for (int e = tid; e < ((P.Nout + 31) & ~31); e += kUmThreads) bias_s[e] = (P.has_bias && e < P.Nout) ? __ldg(bias + e) : 0.f;
   }
   if (tid == 0) {
-    for (int s = 0; s < P.slots; ++s) { ptx::mbar_init(&full[s], CPA ? kUmLoaders / 32 : P.wpr); ptx::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < P.slots; ++s) { ptx::mbar_init(&full[s], CPA ? kUmLoaders / 32 : P.wpr); ptx::mbar_init(&empty[s], P.dual ? 2 : 1); }
     for (int s = 0; s < kUmMaxAcc; ++s) { ptx::mbar_init(&tfull[s], 1); ptx::mbar_init(&tempty[s], kUmEpiWarps * 32); }
     for (int s = 0; s < P.rstages; ++s) { ptx::mbar_init(&rfull[s], CPA ? kUmLoaders : 1); ptx::mbar_init(&rempty[s], kUmLoaders / 32); }
     if (TMA) ptx::prefetch_tensormap(&tmap);
@@ -394,8 +398,8 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
         if (++acc == (uint32_t)P.nacc) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp == kUmMmaWarp) {
-    // ===== MMA issuer ======================================================================================
+  } else if (warp == kUmMmaWarp || (warp == kUmMmaWarpB && P.dual)) {
+    // ===== MMA issuer(s) ======================================================================================
     // Single-lane issue loop: everything that does not change per instruction is hoisted -- ring slots and
     // mbarrier parities advance incrementally (no 64-bit division), descriptors are built from a constant
     // high word and a low word that only gets an address increment added.
@@ -408,52 +412,73 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
     const int ksteps = P.Cred >> 4;
     uint32_t slot0 = 0, phase0 = 0;          // ring slot / parity of the current output row's first input row
     uint32_t acc = 0, acc_phase = 0;         // accumulator stage / parity
+    // Two issuers (P.dual): consecutive output rows alternate between them, each row into its own accumulator stage.  A ring
+    // slot is read by three consecutive output rows, i.e. by BOTH issuers, and a tcgen05.commit only tracks the MMAs of the
+    // thread that issues it: empty[] counts two arrivals and each issuer releases a slot after ITS last row that reads it
+    // (input slot t of a band is read by output rows t-2, t-1, t: the owner of row q releases slots q and q+1, and q+2 when it
+    // has no later row in the band; a slot that only one issuer reads -- the band's first and last -- gets both arrivals from it).
+    const uint32_t me = warp == kUmMmaWarp ? 0u : 1u;
+    uint32_t rowc = 0;                       // rows seen so far (parity = the row's issuer when dual)
     auto next_slot = [&](uint32_t& sl, uint32_t& ph) { if (++sl == (uint32_t)P.slots) { sl = 0; ph ^= 1; } };
     for (long long item = blockIdx.x; item < P.items; item += gridDim.x) {
       const int rem = (int)(item % per_n);
       const int band = rem / P.ctiles;
       const int r0 = band * P.band, rows = min(P.band, P.Ho - r0);
-      for (int rr = 0; rr < rows; ++rr) {
+      for (int rr = 0; rr < rows; ++rr, ++rowc) {
         uint32_t s1 = slot0, p1 = phase0; next_slot(s1, p1);
         uint32_t s2 = s1, p2 = p1; next_slot(s2, p2);
-        ptx::mbar_wait(&full[slot0], phase0);
-        ptx::mbar_wait(&full[s1], p1);
-        ptx::mbar_wait(&full[s2], p2);
-        ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
-        ptx::tc_fence_after_sync();
-        if (ptx::elect_one()) {                // single-thread region: descriptors travel R -> UR once per MMA
-          const int par = (r0 + rr) & 1;
-          const uint32_t d_tmem = tmem_base + acc * (uint32_t)P.Nout;
-          const uint32_t rb0 = (ring_addr + slot0 * (uint32_t)slot_bytes) >> 4;
-          const uint32_t rb1 = (ring_addr + s1 * (uint32_t)slot_bytes) >> 4;
-          const uint32_t rb2 = (ring_addr + s2 * (uint32_t)slot_bytes) >> 4;
-          uint32_t accum = 0;
-          uint32_t b_lo = (w_addr >> 4) + b_lo_const;            // taps are contiguous: one running weight descriptor
+        if (!P.dual || (rowc & 1u) == me) {
+          ptx::mbar_wait(&full[slot0], phase0);
+          ptx::mbar_wait(&full[s1], p1);
+          ptx::mbar_wait(&full[s2], p2);
+          ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+          ptx::tc_fence_after_sync();
+          if (ptx::elect_one()) {                // single-thread region: descriptors travel R -> UR once per MMA
+            const int par = (r0 + rr) & 1;
+            const uint32_t d_tmem = tmem_base + acc * (uint32_t)P.Nout;
+            const uint32_t rb0 = (ring_addr + slot0 * (uint32_t)slot_bytes) >> 4;
+            const uint32_t rb1 = (ring_addr + s1 * (uint32_t)slot_bytes) >> 4;
+            const uint32_t rb2 = (ring_addr + s2 * (uint32_t)slot_bytes) >> 4;
+            uint32_t accum = 0;
+            uint32_t b_lo = (w_addr >> 4) + b_lo_const;            // taps are contiguous: one running weight descriptor
 #pragma unroll
-          for (int k = 0; k < kTaps; ++k) {
-            const int ra = P.ra[k];
-            uint32_t a_lo = (ra == 0 ? rb0 : (ra == 1 ? rb1 : rb2)) + (uint32_t)P.sh[par][k] + a_lo_const;
-            for (int j = 0; j < ksteps; ++j) {
-              ptx::umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, accum);
-              accum = 1;
-              a_lo += a_step; b_lo += b_step;
+            for (int k = 0; k < kTaps; ++k) {
+              const int ra = P.ra[k];
+              uint32_t a_lo = (ra == 0 ? rb0 : (ra == 1 ? rb1 : rb2)) + (uint32_t)P.sh[par][k] + a_lo_const;
+              for (int j = 0; j < ksteps; ++j) {
+                ptx::umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, accum);
+                accum = 1;
+                a_lo += a_step; b_lo += b_step;
+              }
+            }
+            ptx::umma_commit(&tfull[acc]);                         // accumulator ready for the epilogue
+            const bool last = rr == rows - 1;
+            if (!P.dual) {
+              ptx::umma_commit(&empty[slot0]);                     // input row rr is not needed any more
+              if (last) {                                          // band done: release its two trailing rows too
+                ptx::umma_commit(&empty[s1]);
+                ptx::umma_commit(&empty[s2]);
+              }
+            } else {
+              ptx::umma_commit(&empty[slot0]);                     // slot q: this issuer's last read
+              if (rr == 0) ptx::umma_commit(&empty[slot0]);        //   (the band's first slot has no other reader)
+              ptx::umma_commit(&empty[s1]);                        // slot q + 1: this issuer's next row (q + 2) does not read it
+              if (rows == 1) ptx::umma_commit(&empty[s1]);
+              if (rr + 2 > rows - 1) {                             // slot q + 2: no later row of this issuer in the band
+                ptx::umma_commit(&empty[s2]);
+                if (last) ptx::umma_commit(&empty[s2]);            //   (the band's last slot: read by the last row only)
+              }
             }
           }
-          ptx::umma_commit(&tfull[acc]);                         // accumulator ready for the epilogue
-          ptx::umma_commit(&empty[slot0]);                       // input row rr is not needed any more
-          if (rr == rows - 1) {                                  // band done: release its two trailing rows too
-            ptx::umma_commit(&empty[s1]);
-            ptx::umma_commit(&empty[s2]);
-          }
+          __syncwarp();
         }
-        __syncwarp();
         next_slot(slot0, phase0);
         if (++acc == (uint32_t)P.nacc) { acc = 0; acc_phase ^= 1; }
       }
       next_slot(slot0, phase0);              // the band's two trailing input rows
       next_slot(slot0, phase0);
     }
-  } else if (TMA) {
+  } else if (TMA && warp == kUmTmaWarp) {
     // ===== TMA producer (one lane) ===========================================================================
     if (lane == 0) {
       uint32_t trs = 0, tph = 0;
@@ -694,6 +719,9 @@ static void umma_common(UmmaParams& P, int Ho, int Wo, int N) {
   int nacc = 2;
   if (nacc_env >= 2 && nacc_env <= kUmMaxAcc && (nacc_env & 1) == 0 && (nacc_env - 1) * P.Nout + nround <= 512) nacc = nacc_env;
   P.nacc = nacc;
+  static const int dual_env = [] { const char* e = getenv("HG_CONV_DUAL"); return e ? atoi(e) : -1; }();
+  P.dual = dual_env >= 0 ? (dual_env ? 1 : 0) : 1;
+  if (P.dual) P.nacc = 2;                    // a row's accumulator stage = its issuer
 }
 
 int conv_fwd_umma(const hg_conv_desc* d, const ConvGeom& g, const ConvTaps& tp, const void* x, const float* w, const float* scale,
