@@ -20,7 +20,12 @@
 // instruction streams need no ordering), warp 12 also allocates TMEM, warp 13 TMA producer.  Input path as in hg_conv_umma.cu:
 //   TMA : 4-D boxes [C][1 row][px] of x and gy land in a shared raw staging ring (zero-fill of halos and of the
 //         columns past Wo for free); needs pad_value == 0 and 16-byte aligned rows of both tensors.
-//   LDG : coalesced global loads (any pad value / width).
+//   LDG : coalesced global loads (any pad value / width); on lattices narrower than one tile the converter warps split into an
+//         x group and a gy group so that both rows are in flight together.
+//   CPA : cp.async rows into the raw ring for wide lattices whose rows TMA cannot address (float32, zero frame).
+// Lattices narrower than a 128-pixel tile stage and reduce only ceil(Wo / 16) 16-pixel steps (template parameter FULL = whole
+// tiles).  The final epilogue transposes the accumulators through the (then dead) ring memory so that every atomic adds 32
+// consecutive floats of gw, and every CTA starts at a different place of gw.
 #include "hg_conv.cuh"
 #include "hg_ptx.cuh"
 #include <math.h>
