@@ -28,6 +28,7 @@
 #include "hg_conv.cuh"
 #include "hg_ptx.cuh"
 #include <algorithm>
+#include <type_traits>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -439,18 +440,36 @@ hexconv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const TIN* __restr
             const uint32_t rb0 = (ring_addr + slot0 * (uint32_t)slot_bytes) >> 4;
             const uint32_t rb1 = (ring_addr + s1 * (uint32_t)slot_bytes) >> 4;
             const uint32_t rb2 = (ring_addr + s2 * (uint32_t)slot_bytes) >> 4;
-            uint32_t accum = 0;
             uint32_t b_lo = (w_addr >> 4) + b_lo_const;            // taps are contiguous: one running weight descriptor
+            // the K loop of a tap is straight-line code for the usual channel counts (16 / 32 / 64 reduction channels): its
+            // run-time trip count cost the issuing thread a loop dispatch per tap
+            auto issue_row = [&](auto ks_tag) {
+              constexpr int KS = decltype(ks_tag)::value;          // 0: run-time trip count
+              uint32_t accum = 0;
 #pragma unroll
-            for (int k = 0; k < kTaps; ++k) {
-              const int ra = P.ra[k];
-              uint32_t a_lo = (ra == 0 ? rb0 : (ra == 1 ? rb1 : rb2)) + (uint32_t)P.sh[par][k] + a_lo_const;
-              for (int j = 0; j < ksteps; ++j) {
-                ptx::umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, accum);
-                accum = 1;
-                a_lo += a_step; b_lo += b_step;
+              for (int k = 0; k < kTaps; ++k) {
+                const int ra = P.ra[k];
+                uint32_t a_lo = (ra == 0 ? rb0 : (ra == 1 ? rb1 : rb2)) + (uint32_t)P.sh[par][k] + a_lo_const;
+                if constexpr (KS > 0) {
+#pragma unroll
+                  for (int j = 0; j < KS; ++j) {
+                    ptx::umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, accum);
+                    accum = 1;
+                    a_lo += a_step; b_lo += b_step;
+                  }
+                } else {
+                  for (int j = 0; j < ksteps; ++j) {
+                    ptx::umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, accum);
+                    accum = 1;
+                    a_lo += a_step; b_lo += b_step;
+                  }
+                }
               }
-            }
+            };
+            if (ksteps == 4) issue_row(std::integral_constant<int, 4>{});
+            else if (ksteps == 1) issue_row(std::integral_constant<int, 1>{});
+            else if (ksteps == 2) issue_row(std::integral_constant<int, 2>{});
+            else issue_row(std::integral_constant<int, 0>{});
             ptx::umma_commit(&tfull[acc]);                         // accumulator ready for the epilogue
             const bool last = rr == rows - 1;
             if (!P.dual) {
