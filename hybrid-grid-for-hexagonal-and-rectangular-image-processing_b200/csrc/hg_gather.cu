@@ -147,7 +147,12 @@ struct GatherGrid {
 };
 
 static GatherGrid gather_grid(int64_t planes, int64_t cells) {
+  // planes walked per table load: 8, or 32 while the grid still has several waves of blocks (the 8-byte table entry is
+  // 1 byte per moved cell at 8 planes -- an eighth of a float32 shuffle's traffic -- and a quarter of that at 32)
+  static const int env_ppb = [] { const char* e = getenv("HG_GATHER_PPB"); return e ? atoi(e) : 0; }();
   int64_t ppb = kGatherPlanes;
+  if (ceil_div(cells, kGatherThreads) * ceil_div(planes, 32) >= 148 * 16) ppb = 32;
+  if (env_ppb > 0) ppb = env_ppb;
   if (ceil_div(planes, ppb) > 65535) ppb = ceil_div(planes, 65535);
   GatherGrid g;
   g.grid = dim3((unsigned)ceil_div(cells, kGatherThreads), (unsigned)ceil_div(planes, ppb), 1);
